@@ -1,0 +1,347 @@
+#!/usr/bin/env python
+"""bench.py -- FLMR / PLAID late-interaction search throughput on B200.
+
+A "step" is one pass of the whole search path (centroid scoring -> candidate pids ->
+two-stage filter -> decompression -> exact MaxSim -> top-k) over one batch of synthetic queries.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg1|cfg2|cfg3]
+
+N = 1  : BASELINE.json configs[1] (OK-VQA GS-112K-shaped index, 1024 FLMR queries, k = 100).
+N > 1  : launched by torchrun, one rank per GPU; every rank owns a pid-range shard of the same size
+         as the N = 1 index (weak scaling), queries are replicated, and the only exchange is one
+         all-gather of the per-shard top-k lists followed by the merge kernel.
+`--impl reference` times the reference's CPU implementation of the same path on the host cores
+(oracle/ref_search.py) on a bounded sample of the same workload.
+One JSON line on stdout (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: passages, doclen lo/hi, nbits, queries per step, Lq, k   
+    "cfg1": dict(N=10_000, lo=120, hi=239, nbits=2, B=256, Lq=64, k=100,
+                 desc="10k-passage synthetic PLAID index, nbits=2, 256 FLMR queries (32+32 tokens), k=100"),
+    "cfg2": dict(N=112_000, lo=120, hi=239, nbits=2, B=1024, Lq=64, k=100,
+                 desc="OK-VQA GS-112K-shaped synthetic index (112k passages, ~180 tok/passage, nbits=2), "
+                      "1024 FLMR queries (32+32 tokens), k=100"),
+    "cfg3": dict(N=100_000, lo=128, hi=512, nbits=4, B=256, Lq=320, k=100,
+                 desc="E-VQA/InfoSeek-shaped 100k-passage index, nbits=4, 256 PreFLMR 320-token queries, k=100"),
+}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sustained=d["bf16_tflops_sustained"], source="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.lines, self.proc = [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_workload(w, rank, device):
+    """Synthetic index (code-space generator) + gold-planted queries, on `device`."""
+    import torch
+    from reranking_multimodal_retrievers_b200 import synthetic
+    sx = synthetic.make_synthetic_index(w["N"], w["lo"], w["hi"], w["nbits"], seed=1234 + 17 * rank, mode="codes",
+                                        device=device)
+    Q = synthetic.make_queries(sx, w["B"], w["Lq"], seed=99)      # same queries on every rank
+    return sx, Q.to(torch.float32)
+
+
+def cpu_index_from(sx):
+    from oracle import plaid_oracle as po
+    c = sx.cpu()
+    return po.OracleIndex(centroids=c.centroids, bucket_weights=c.bucket_weights, codes=c.codes, residuals=c.residuals,
+                          doclens=c.doclens, ivf=c.ivf, ivf_lengths=c.ivf_lengths, nbits=c.nbits)
+
+
+def make_cpu_searcher(sx):
+    from oracle.ref_search import CpuSearcher
+    return CpuSearcher(cpu_index_from(sx))
+
+
+def run_cpu_sample(cs, Q, k, budget_s, max_queries, warm=True):
+    """Reference CPU path on a bounded sample of the step's queries.  Returns dict for `cpu_baseline`."""
+    Qc = Q.cpu()
+    if warm:
+        cs.search_all(Qc[:2], k)                   # warm-up (thread pools, page-in)
+    for key in cs.stage_s:
+        cs.stage_s[key] = 0.0
+    t0 = time.perf_counter()
+    n, toks = 0, 0
+    while n < min(max_queries, Qc.shape[0]) and (time.perf_counter() - t0) < budget_s:
+        _, t3 = cs.search_all(Qc[n:n + 1], k)
+        n += 1
+        toks += t3
+    dt = time.perf_counter() - t0
+    return dict(queries=n, seconds=dt, tokens=toks, kind=cs.kind, cores=cs.cores,
+                stage_share={s: round(v / max(dt, 1e-9), 3) for s, v in cs.stage_s.items()})
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--cpu-budget-s", type=float, default=15.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    w = WORKLOADS[args.workload]
+    peaks = load_peaks()
+
+    # ------------------------------------------------------------------ reference arm (CPU, rank 0 only)
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        dev = "cuda" if torch.cuda.is_available() else "cpu"
+        sx, Q = build_workload(w, 0, dev)
+        sample_q = 8
+        cs = make_cpu_searcher(sx)
+        tot_q, tot_s, tot_tok, info = 0, 0.0, 0, None
+        for step in range(args.warmup + args.steps):
+            lo = (step * sample_q) % max(1, Q.shape[0] - sample_q)
+            r = run_cpu_sample(cs, Q[lo:lo + sample_q], w["k"], 1e9, sample_q, warm=(step == 0))
+            info = r
+            if step >= args.warmup:
+                tot_q += r["queries"]; tot_s += r["seconds"]; tot_tok += r["tokens"]
+        tok_s = tot_tok / max(tot_s, 1e-9)
+        line = {
+            "impl": "reference", "metric": "scored_doc_tokens_per_s", "value": tok_s, "unit": "doc-tokens/s",
+            "queries_per_s": tot_q / max(tot_s, 1e-9), "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * tot_s / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {w['desc']}", "step": f"{sample_q}-query sample of the batch"},
+            "cpu_baseline": {"value": tok_s, "unit": "doc-tokens/s", "cores": info["cores"], "kind": info["kind"],
+                             "sample": f"{tot_q} queries of the step's {w['B']} (reference CPU path, all host threads)",
+                             "queries_per_s": tot_q / max(tot_s, 1e-9), "stage_share": info["stage_share"]},
+            "e2e": {"value": tok_s, "unit": "doc-tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+        }
+        print(json.dumps(line))
+        return
+
+    # ------------------------------------------------------------------ our arm
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    import torch.distributed as dist
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from reranking_multimodal_retrievers_b200 import sharded
+    from reranking_multimodal_retrievers_b200.engine import SearchEngine
+    from reranking_multimodal_retrievers_b200.index import DeviceIndex
+
+    sx, Qdev = build_workload(w, rank, dev)
+    index = DeviceIndex(sx, dev)
+    index.pid_base = rank * w["N"]                      # this rank's shard of the N*world passage collection
+    eng = SearchEngine(index)
+    B, Lq, k = w["B"], w["Lq"], w["k"]
+    Qhost = Qdev.cpu().pin_memory()
+    out_host = (torch.empty(B, k, dtype=torch.int32).pin_memory(), torch.empty(B, k, dtype=torch.float32).pin_memory(),
+                torch.empty(B, dtype=torch.int32).pin_memory())
+
+    def step(q):
+        p, s, c = eng.search_batch(q, k=k)
+        if world > 1:
+            gathered = sharded.all_gather_lists(sharded.pack_lists(p, s, c), world)
+            gp, gs, gc = sharded.unpack_lists(gathered, k)
+            p, s, c = sharded.merge_topk(gs, gp, gc, k)
+            eng.launch_count += 1
+        return p, s, c
+
+    def step_e2e():
+        q = Qhost.to(dev, non_blocking=True)            # H2D of this step's inputs from pinned memory
+        p, s, c = step(q)
+        out_host[0].copy_(p, non_blocking=True); out_host[1].copy_(s, non_blocking=True)
+        out_host[2].copy_(c, non_blocking=True)         # D2H of the step's result
+        torch.cuda.current_stream().synchronize()
+
+    def timed(fn, steps, sampler=None):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        if sampler:
+            sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        clocks = sampler.stop() if sampler else None
+        if world > 1:
+            dist.barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)   # max over ranks
+        return float(ms.item()), clocks
+
+    # accounting pass (untimed): tokens entering each stage, summed over the batch
+    stats = dict(ncand=0, T1=0, T2=0, T3=0, found=0)
+
+    def account(ws, n):
+        dl = index.doclens
+        cc = ws["cand_counts"][:n].long()
+        m = torch.arange(ws["cand_stride"], device=dev).unsqueeze(0) < cc.unsqueeze(1)
+        stats["ncand"] += int(cc.sum())
+        stats["T1"] += int((dl[ws["cand_pids"][:n].clamp(min=0).long()] * m).sum())
+        c1 = ws["s1_counts"][:n].long()
+        m1 = torch.arange(ws["s1_pids"].shape[1], device=dev).unsqueeze(0) < c1.unsqueeze(1)
+        stats["T2"] += int((dl[ws["s1_pids"][:n].clamp(min=0).long()] * m1).sum())
+        c2 = ws["s2_counts"][:n].long()
+        stats["T3"] += int(ws["tok_offsets"][:n].gather(1, c2.unsqueeze(1)).sum())
+        stats["found"] += int(ws["out_counts"][:n].sum())
+
+    eng.search_batch(Qdev, k=k, on_chunk=account)
+    torch.cuda.synchronize()
+    eng.check_flags()
+
+    for _ in range(args.warmup):
+        step(Qdev)
+    # timed region 1: inputs resident in HBM, per-kernel CUDA events on the launching stream
+    eng.events = []
+    l0 = eng.launch_count
+    sampler = ClockSampler(local_rank)
+    ms_total, clocks = timed(lambda: step(Qdev), args.steps, sampler)
+    launches = eng.launch_count - l0
+    events, eng.events = eng.events, None
+    stage_ms = {}
+    for stage, a, b in events:
+        stage_ms.setdefault(stage, []).append(a.elapsed_time(b))
+    eng.check_flags()
+    # timed region 2: end to end through host buffers
+    for _ in range(2):
+        step_e2e()
+    ms_e2e, _ = timed(step_e2e, args.steps)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    ms_step = ms_total / args.steps
+    C, nbits = index.num_centroids, index.nbits
+    chunks = (B + eng.chunk_size(B) - 1) // eng.chunk_size(B)
+    T1, T2, T3, ncand = stats["T1"], stats["T2"], stats["T3"], stats["ncand"]
+    # ALGORITHMIC bytes / flops per step, per stage
+    alg = {
+        "centroid_scores": dict(bytes=4.0 * C * 32 * B + 2.0 * C * 128 * chunks, flops=2.0 * C * 128 * 32 * B),
+        "filter_stage1": dict(bytes=4.0 * T1 + 16.0 * ncand, flops=0.0),
+        "filter_stage2": dict(bytes=4.0 * T2 + 16.0 * 1024 * B + 128.0 * T2, flops=0.0),
+        "decompress": dict(bytes=(4.0 + 16 * nbits + 256.0 + 256.0) * T3, flops=0.0),   # codes+residual+f16 centroid row in, bf16 out
+        "maxsim": dict(bytes=256.0 * T3, flops=2.0 * Lq * 128 * T3),
+    }
+    kernels = {}
+    for stage, v in stage_ms.items():
+        per_step = sum(v) / args.steps
+        d = {"ms_per_step": round(per_step, 4), "share": round(per_step / ms_step, 4), "launches_per_step": len(v) // args.steps}
+        if stage in alg:
+            d["achieved_GBps"] = round(alg[stage]["bytes"] / (per_step * 1e-3) / 1e9, 1)
+            d["frac_hbm"] = round(d["achieved_GBps"] / peaks["hbm"], 4)
+            if alg[stage]["flops"]:
+                d["achieved_TFLOPs"] = round(alg[stage]["flops"] / (per_step * 1e-3) / 1e12, 2)
+                d["frac_tensor"] = round(d["achieved_TFLOPs"] / peaks["tf_sustained"], 4)
+        kernels[stage] = d
+    dom = max((s for s in kernels if s in alg), key=lambda s: kernels[s]["ms_per_step"])
+    nl = kernels[dom]["launches_per_step"]
+    per_launch_s = kernels[dom]["ms_per_step"] * 1e-3 / nl
+    roofline = {"kernel": dom, "bound": "hbm", "achieved": round(alg[dom]["bytes"] / nl / per_launch_s / 1e9, 1),
+                "peak": peaks["hbm"], "unit": "GB/s", "peak_source": peaks["source"] + " (sustained: timed inside the step)",
+                "traffic": None, "algorithmic_bytes_per_launch": alg[dom]["bytes"] / nl,
+                "avg_launch_ms": round(per_launch_s * 1e3, 4)}
+    roofline["frac"] = round(roofline["achieved"] / roofline["peak"], 4)
+
+    tok_s = world * T3 / (ms_step * 1e-3)               # every rank exact-scores ~T3 tokens of its own shard
+    e2e_ms = ms_e2e / args.steps
+    line = {
+        "metric": "scored_doc_tokens_per_s", "value": tok_s, "unit": "doc-tokens/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "queries_per_s": B / (ms_step * 1e-3),
+        "config": {"workload": f"{args.workload}: {w['desc']}", "passages_per_gpu": w["N"], "tokens_per_gpu": index.num_embeddings,
+                   "centroids": C, "queries_per_step": B, "parallelism": f"pid-range shards x{world}, all-gather top-k merge",
+                   "l2": "inputs larger than L2 (index + centroid-score table >> 126 MB), no explicit flush",
+                   "candidates_per_query": ncand / B, "T1_tokens_per_query": T1 / B, "T2_tokens_per_query": T2 / B,
+                   "T3_tokens_per_query": T3 / B, "results_per_query": stats["found"] / B},
+        "e2e": {"value": world * T3 / (e2e_ms * 1e-3), "unit": "doc-tokens/s", "queries_per_s": B / (e2e_ms * 1e-3),
+                "ms_per_step": e2e_ms, "h2d_bytes_per_step": B * Lq * 128 * 4, "d2h_bytes_per_step": B * k * 8 + B * 4},
+        "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "kernels": kernels,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        r = run_cpu_sample(make_cpu_searcher(sx), Qdev, k, args.cpu_budget_s, 64)
+        line["cpu_baseline"] = {"value": r["tokens"] / r["seconds"], "unit": "doc-tokens/s", "cores": r["cores"],
+                                "kind": r["kind"], "queries_per_s": r["queries"] / r["seconds"],
+                                "sample": f"first {r['queries']} of the step's {B} queries, same index, {r['seconds']:.1f} s",
+                                "stage_share": r["stage_share"]}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

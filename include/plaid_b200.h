@@ -1,0 +1,199 @@
+/*
+ * plaid_b200.h -- C ABI of libplaid_b200.so: the B200 (sm_100a) kernels behind FLMR's
+ * ColBERT/PLAID late-interaction search path.
+ *
+ * This is the drop-in boundary.  The reference binds its native operators through
+ * pybind11/torch (`torch.utils.cpp_extension.load`); a maintainer replaces those loads with a
+ * ctypes binding of the functions below (INTEGRATION.md shows the stubs).  Conventions:
+ *
+ *   - every pointer is a DEVICE pointer unless its name ends in `_host`;
+ *   - tensors are dense, row-major, no strides honoured (exactly like the reference operators,
+ *     which read `data_ptr<T>()` directly);
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); calls only enqueue
+ *     work, they never synchronise;
+ *   - return value: 0 on success, a negative PLAID_ERR_* otherwise (never aborts, never exits,
+ *     unlike filter_pids.cpp:98-101 / the active asserts at filter_pids.cpp:47);
+ *     plaid_last_error() returns the message of the calling thread's last failure;
+ *   - nothing is allocated behind the caller's back: outputs and workspaces are caller-owned.
+ *
+ * Paths below are relative to /root/reference/third_party/ColBERT/colbert/ ("CB/").
+ */
+#ifndef PLAID_B200_H
+#define PLAID_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PLAID_OK 0
+#define PLAID_ERR_ARG (-1)         /* bad argument (null pointer, unsupported size) */
+#define PLAID_ERR_CUDA (-2)        /* CUDA runtime / driver error (launch, tensor-map encode) */
+#define PLAID_ERR_UNSUPPORTED (-3) /* shape outside what the kernels implement */
+
+#define PLAID_DIM 128          /* embedding dim of the path (CB/infra/config/settings.py:101) */
+#define PLAID_NQ_MAX 32        /* candidate-stage query tokens = query_maxlen (settings.py:108) */
+#define PLAID_NCELLS_MAX 8     /* ncells is 1/2/4 in CB/searcher.py:96-122 */
+#define PLAID_NO_PID (-1)      /* filler for unused (pid) slots */
+
+/* ---- library ---------------------------------------------------------------------------- */
+int plaid_abi_version(void);
+const char* plaid_last_error(void);
+/* compiled-for architecture string, e.g. "sm_100a" */
+const char* plaid_arch(void);
+
+/* ---- a1: query preparation (CB/searcher.py:124-130, CB/search/index_storage.py:77) -------
+ * Q fp32 [B, Lq, 128] -> per query: rows with sum(|q|) > 0 kept in order (remove_zero_rows != 0),
+ * converted to bf16 into Qb [B_pad, Lq_pad, 128] (rows past the kept ones and queries >= B are zero),
+ * qlens[b] = rows kept (0 for the padding queries b >= B; qlens has B_pad entries).  B_pad must be a
+ * multiple of 4, Lq_pad a multiple of 32 and >= Lq. */
+int plaid_prepare_queries(const float* Q, int B, int Lq, int remove_zero_rows, int B_pad, int Lq_pad,
+                          void* Qb_bf16, int32_t* qlens, void* stream);
+
+/* fp32 -> bf16 row conversion used when loading the codebook (round-to-nearest-even). */
+int plaid_f32_to_bf16(const float* src, void* dst_bf16, int64_t n, void* stream);
+
+/* ---- a2 + a4: centroid scoring (CB/search/candidate_generation.py:12-20, index_storage.py:115)
+ * S[b, c, k] = <centroids[c], Qb[b, k]> for k < nq_max=32 (bf16 operands, fp32 accumulate on
+ * tcgen05; operands fed by TMA).  Fused epilogue products:
+ *   idx_bits[b, c/32] bit (c%32)  = max_{k < nq_b} S[b,c,k] >= threshold      (centroid pruning mask)
+ *   cell_val/cell_idx[b, k, l, j] = the ncells best (score, centroid) of query token k inside the
+ *                                   l-th of 2*csplit partial lists (csplit centroid ranges x two
+ *                                   128-column halves), best first, ties -> lowest centroid id;
+ *                                   cell_idx = -1 where there is no entry.
+ * nq_b = min(qlens[b], 32).  S is laid out [B_pad, C, 32] fp32 -- per query exactly the reference's
+ * `centroid_scores` [C, nq] tensor (row = centroid).  C must be a multiple of 32; the grid is
+ * (B_pad/4) x csplit CTAs.  Rows of Qb beyond qlens[b] must be zero (plaid_prepare_queries does it).
+ * *watchdog (device int, may be NULL) is set to 1 if an in-kernel pipeline wait ever times out. */
+int plaid_centroid_scores(const void* centroids_bf16, int C, const void* Qb_bf16, const int32_t* qlens,
+                          int B_pad, int Lq_pad, float threshold, int ncells, int csplit,
+                          float* S, uint32_t* idx_bits, float* cell_val, int32_t* cell_idx, int* watchdog,
+                          void* stream);
+
+/* ---- a3: candidate pids (candidate_generation.py:31-37,57-60; strided_tensor.py:77-99;
+ *          segmented_lookup.cpp:51-125) --------------------------------------------------------
+ * Merges the `nlists` partial lists into cells[b, k, 0..ncells) (i32 [B, 32, ncells], -1 = none),
+ * takes the union of their IVF pid lists and emits it sorted + unique through a per-query pid
+ * bitmap: bitmap_ws [B, ceil(N/32)] u32 (zeroed by the call), cand_pids [B, cand_stride] i32
+ * ascending, cand_counts[b].  If a query would need more than cand_stride slots the list is
+ * truncated and *overflow is set to 1. */
+int plaid_candidates(const float* cell_val, const int32_t* cell_idx, const int32_t* qlens, int B, int ncells,
+                     int nlists, const int32_t* ivf_pids, const int64_t* ivf_offsets, int C, int N,
+                     int32_t* cells, uint32_t* bitmap_ws, int32_t* cand_pids, int32_t* cand_counts,
+                     int cand_stride, int* overflow, void* stream);
+
+/* ---- a5: filter_pids (CB/search/filter_pids.cpp:27-164) ---------------------------------------
+ * Approximate score of every listed passage: sum over k < nq_b (sequential fp32, in k order) of
+ * max over the passage's codes with idx bit set (all codes when idx_bits == NULL) of S[b, code, k],
+ * each per-token max initialised to -9999.  pids [B, pid_stride] with counts[b] valid entries;
+ * scores written to the same slots of out_scores.  One warp per passage, lane = query token. */
+int plaid_approx_scores(const int32_t* pids, const int32_t* counts, int B, int pid_stride, const float* S,
+                        const int32_t* qlens, const uint32_t* idx_bits, int C, const int32_t* codes,
+                        const int64_t* offsets, float* out_scores, void* stream);
+
+/* Per query the `keep` largest (score, pid) pairs in descending (score, pid) order -- the order of
+ * std::pair<float,int> in filter_pids.cpp:24,108-123.  Emits min(counts[b], keep) entries
+ * (the rule of the reference's GPU branch, index_storage.py:138-139; the C++ pops an empty heap).
+ * Unused output slots get PLAID_NO_PID / -inf.  ws_keys: u64 workspace [B, in_stride]. */
+int plaid_select_top(const int32_t* pids, const float* scores, const int32_t* counts, int B, int in_stride,
+                     int keep, int32_t* out_pids, float* out_scores, int32_t* out_counts, int out_stride,
+                     uint64_t* ws_keys, void* stream);
+
+/* The two-stage filter exactly as IndexScorer.filter_pids is called (index_storage.py:153-156):
+ * stage 1 with the pruning mask keeps ndocs, stage 2 with all codes keeps ndocs/4.
+ * Workspaces: ws_scores f32 [B, max(pid_stride, ndocs)], ws_keys u64 [B, max(pid_stride, ndocs)],
+ * stage1_pids i32 [B, ndocs] / stage1_scores f32 [B, ndocs] / stage1_counts [B] (outputs too, for
+ * stage-wise parity), stage2_* likewise with ndocs/4. */
+int plaid_filter_pids(const int32_t* pids, const int32_t* counts, int B, int pid_stride, const float* S,
+                      const int32_t* qlens, const uint32_t* idx_bits, int C, const int32_t* codes,
+                      const int64_t* offsets, int ndocs, float* ws_scores, uint64_t* ws_keys,
+                      int32_t* stage1_pids, float* stage1_scores, int32_t* stage1_counts,
+                      int32_t* stage2_pids, float* stage2_scores, int32_t* stage2_counts, void* stream);
+
+/* ---- a6: decompress_residuals (CB/search/decompress_residuals.cpp:27-155;
+ *          tables: CB/indexing/codecs/residual.py:54-89) ---------------------------------------
+ * Builds the fused weight table W[x][l] = bucket_weights[lookup[reversed_bit_map[x]][l]],
+ * x in 0..255, l in 0..8/nbits, from the reference's three codec tensors. */
+int plaid_build_weight_table(const float* bucket_weights, const uint8_t* reversed_bit_map,
+                             const uint8_t* lookup, int nbits, float* W, void* stream);
+
+/* out[row, d] = W[residual_byte][l] + centroids[code][d]  (one fp32 add, bit-exact), rows packed in
+ * pid order: out_offsets[i] = first output row of pids[i] (exclusive prefix sum of the lengths,
+ * npids+1 entries, device).  centroids fp32 [C, 128]. */
+int plaid_decompress_residuals(const int32_t* pids, int npids, const int64_t* offsets, const int64_t* out_offsets,
+                               const float* W, const uint8_t* residuals, const int32_t* codes,
+                               const float* centroids, int C, int nbits, float* out, void* stream);
+
+/* Integer part only: bucket index of every dimension, u8 [ntokens, 128] (parity tap). */
+int plaid_unpack_residual_codes(const uint8_t* residuals, int64_t ntokens, int nbits,
+                                const uint8_t* reversed_bit_map, const uint8_t* lookup, uint8_t* out,
+                                void* stream);
+
+/* Exclusive per-query prefix sums of the passage lengths of pids [B, pid_stride] (counts[b] valid):
+ * tok_offsets [B, pid_stride+1] (i32, local to the query). */
+int plaid_doc_token_offsets(const int32_t* pids, const int32_t* counts, int B, int pid_stride,
+                            const int64_t* offsets, int32_t* tok_offsets, void* stream);
+
+/* a6 + a7 for the search pipeline: decompress, L2-normalise (eps 1e-12, index_storage.py:175) and
+ * round to bf16 into D [B, tok_stride, 128]; token j of passage i of query b lands on row
+ * b*tok_stride + tok_offsets[b, i] + j.  centroids [C,128] either fp32 or, with centroids_are_f16 != 0,
+ * the fp16 values exactly as stored in centroids.pt (CB/indexing/codecs/residual.py:161; the CPU
+ * reference widens them to fp32, residual.py:29 -- the same numbers).  The add is done in fp32
+ * before normalisation, as the reference does. */
+int plaid_decompress_normalize_bf16(const int32_t* pids, const int32_t* counts, int B, int pid_stride,
+                                    const int32_t* tok_offsets, int tok_stride, const int64_t* offsets,
+                                    const float* W, const uint8_t* residuals, const int32_t* codes,
+                                    const void* centroids, int centroids_are_f16, int C, int nbits,
+                                    void* D_bf16, void* stream);
+
+/* ---- a8: colbert_score_packed + segmented_maxsim (CB/modeling/colbert.py:289-311,
+ *          CB/modeling/segmented_maxsim.cpp:22-93) ---------------------------------------------
+ * scores[b, i] = sum_{k < qlens[b]} max(0, max_{t in passage i} <D[b, t], Qb[b, k]>): a tcgen05
+ * Qb . D^T tile per 256 passage tokens with the per-passage running max and the sum over query
+ * tokens done in the epilogue straight out of TMEM (the similarity matrix never reaches HBM).
+ * clamp_zero = 1 reproduces the zero-initialised max buffer of segmented_maxsim.cpp:58-59. */
+int plaid_maxsim_packed(const void* Qb_bf16, const int32_t* qlens, int B, int B_pad, int Lq_pad,
+                        const void* D_bf16, const int32_t* tok_offsets, const int32_t* counts, int pid_stride,
+                        int tok_stride, int clamp_zero, float* scores, int* watchdog, void* stream);
+
+/* The operator the reference binds as ColBERT.segmented_maxsim (colbert.py:60): scores f32 [T, nq]
+ * already computed, lengths i64 [ndocs] -> f32 [ndocs]; zero-initialised running max, then a
+ * left-to-right fp32 sum over the nq columns. */
+int plaid_segmented_maxsim(const float* scores, int nq, const int64_t* lengths, const int64_t* row_offsets,
+                           int ndocs, float* out, void* stream);
+
+/* ---- a9: colbert_score / colbert_score_reduce (CB/modeling/colbert.py:235-286;
+ *          FLMR copy src/models/flmr/models/flmr/flmr_utils.py:22-48) ---------------------------
+ * Padded MaxSim: D_padded bf16 [n, Ld, 128], D_mask u8 [n, Ld] (non-zero = real token), passage d is
+ * scored against query d / docs_per_query of Qb [nQ_pad, Lq_pad, 128]; masked positions count as -9999,
+ * max over Ld, sum over the query's qlens rows (no clamp).  scores_raw (optional, may be NULL) receives
+ * the masked similarity matrix fp32 [n, Ld, Lq_out] that flmr_utils.colbert_score also returns. */
+int plaid_colbert_score_padded(const void* Qb_bf16, const int32_t* qlens, int nQ, int nQ_pad, int Lq_pad,
+                               const void* D_padded_bf16, const uint8_t* D_mask, int64_t n, int Ld,
+                               int docs_per_query, float* scores, float* scores_raw, int Lq_out,
+                               int* watchdog, void* stream);
+
+/* colbert_score_reduce on an existing fp32 scores_padded [n, Ld, Lq] + mask (colbert.py:237-263,
+ * 'colbert' interaction): -9999 fill, max over Ld, sum over Lq (left to right). */
+int plaid_colbert_score_reduce(const float* scores_padded, const uint8_t* D_mask, int64_t n, int Ld, int Lq,
+                               float* scores, void* stream);
+
+/* ---- a10 + multi-GPU merge (index_storage.py:95-96, searcher.py:136) -----------
+ * Merge G per-shard lists (as laid out by an all-gather: [G, B, k] scores / pids, [G, B] counts)
+ * into the global top-k per query, (score, pid) descending.  ws_keys: u64 [B, G*k]. */
+int plaid_merge_topk(const float* scores, const int32_t* pids, const int32_t* counts, int G, int B, int k,
+                     int32_t* out_pids, float* out_scores, int32_t* out_counts, uint64_t* ws_keys,
+                     void* stream);
+
+/* ---- a11: ragged gather (CB/search/segmented_lookup.cpp:36-125) ------------------------------
+ * out rows = concatenation over i of input[offsets[i] .. offsets[i]+lengths[i]) (row_bytes each);
+ * out_offsets = exclusive prefix sum of lengths (device, n+1). */
+int plaid_segmented_lookup(const uint8_t* input, int64_t row_bytes, const int64_t* lengths,
+                           const int64_t* offsets, const int64_t* out_offsets, int n, uint8_t* out,
+                           void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PLAID_B200_H */

@@ -1,0 +1,222 @@
+// centroid.cu -- centroid scoring on tcgen05 / TMEM, operands fed by TMA.
+//
+// Replaces `scores = centroids @ Q.T` + `topk(ncells, dim=0)` of
+// CB/search/candidate_generation.py:12-20 and `idx = centroid_scores.max(-1).values >= thr` of
+// CB/search/index_storage.py:115, for a whole batch of queries at once.
+//
+// Tile orientation: M = 128 accumulator lanes = 4 queries x 32 candidate-stage tokens (so each
+// epilogue warp owns exactly one query and lane = query token), N = 256 centroids per tile,
+// K = 128 = 8 UMMA k-steps of 16.  A CTA keeps its 4 queries' A operand resident in shared memory
+// and streams a contiguous range of centroid tiles through a 2-stage TMA ring; two 256-column fp32
+// accumulators in TMEM (all 512 columns) let the MMA of tile i+1 overlap the epilogue of tile i.
+//
+// Epilogue (8 warps; warp = (lane quadrant, 128-column half)), straight out of TMEM:
+//   * S[b, c, 0..31] -- for one centroid the warp's 32 lanes write 32 consecutive floats, i.e. one
+//     full 128-byte line of the reference's [C, nq] layout;
+//   * idx bit (b, c) = max over the query's tokens >= threshold, via redux.sync.max on
+//     order-preserving integer images of the scores;
+//   * per thread (= query token) a running top-ncells (score desc, centroid id asc) over all
+//     columns it sees -- partial per centroid range, merged in candidates.cu.
+// The kernel is bound by the S write (4*C*32 bytes per query), not by the tensor pipe.
+#include "common.cuh"
+
+namespace plaid {
+
+static constexpr int kCsM = 128;            // accumulator rows: 4 queries x 32 tokens
+static constexpr int kCsN = 256;            // centroids per tile
+static constexpr int kCsStages = 2;         // B-operand ring depth
+static constexpr int kCsThreads = 384;      // warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4..11 epilogue
+static constexpr int kCsABytes = kCsM * kDim * 2;        // 32 KB
+static constexpr int kCsBBytes = kCsN * kDim * 2;        // 64 KB per stage
+static constexpr int kCsSmemBytes = 1024 + kCsABytes + kCsStages * kCsBBytes + 256;
+
+struct CsBarriers {
+    uint64_t a_full;
+    uint64_t full[kCsStages];
+    uint64_t empty[kCsStages];
+    uint64_t tmem_full[2];
+    uint64_t tmem_empty[2];
+    uint32_t tmem_base;
+    int abort_flag;
+};
+
+__global__ void __launch_bounds__(kCsThreads, 1)
+centroid_scores_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_c,
+                       const int32_t* __restrict__ qlens, int C, int Lq_pad, float threshold, int ncells, int csplit,
+                       float* __restrict__ S, uint32_t* __restrict__ idx_bits, float* __restrict__ cell_val,
+                       int32_t* __restrict__ cell_idx, int* __restrict__ watchdog) {
+    extern __shared__ uint8_t smem_raw[];
+    // 1024-byte alignment: required by the 128B swizzle atoms the UMMA descriptors describe
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sA = smem;                          // [2 k-halves][128 rows][128 B]
+    uint8_t* sB = smem + kCsABytes;              // [stage][2 k-halves][256 rows][128 B]
+    CsBarriers* bar = reinterpret_cast<CsBarriers*>(smem + kCsABytes + kCsStages * kCsBBytes);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int qgroup = blockIdx.x, split = blockIdx.y;
+    const int tiles_total = (C + kCsN - 1) / kCsN;
+    const int tiles_per_split = (tiles_total + csplit - 1) / csplit;
+    const int tile_begin = split * tiles_per_split;
+    const int tile_end = min(tiles_total, tile_begin + tiles_per_split);
+    const int ntiles = max(0, tile_end - tile_begin);
+
+    if (threadIdx.x == 0) {
+        mbar_init(&bar->a_full, 1);
+        for (int s = 0; s < kCsStages; s++) { mbar_init(&bar->full[s], 1); mbar_init(&bar->empty[s], 1); }
+        for (int a = 0; a < 2; a++) { mbar_init(&bar->tmem_full[a], 1); mbar_init(&bar->tmem_empty[a], 8); }
+        bar->abort_flag = 0;
+        fence_mbar_init();
+    }
+    if (warp == 2) {
+        tmem_alloc(&bar->tmem_base, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = bar->tmem_base;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            tma_prefetch_desc(&map_q);
+            tma_prefetch_desc(&map_c);
+            mbar_expect_tx(&bar->a_full, kCsABytes);
+            for (int h = 0; h < 2; h++)
+                for (int q = 0; q < 4; q++)
+                    tma_load_2d(sA + h * (kCsM * 128) + q * (32 * 128), &map_q, &bar->a_full, h * 64,
+                                (qgroup * 4 + q) * Lq_pad);
+            for (int it = 0; it < ntiles; it++) {
+                const int s = it % kCsStages;
+                if (!mbar_wait(&bar->empty[s], ((it / kCsStages) & 1) ^ 1, watchdog)) break;
+                mbar_expect_tx(&bar->full[s], kCsBBytes);
+                uint8_t* dst = sB + s * kCsBBytes;
+                const int row = (tile_begin + it) * kCsN;
+                tma_load_2d(dst, &map_c, &bar->full[s], 0, row);
+                tma_load_2d(dst + kCsN * 128, &map_c, &bar->full[s], 64, row);
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (one thread) =====================
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_bf16(kCsM, kCsN);
+            bool ok = mbar_wait(&bar->a_full, 0, watchdog);
+            for (int it = 0; ok && it < ntiles; it++) {
+                const int s = it % kCsStages, acc = it & 1;
+                if (!mbar_wait(&bar->tmem_empty[acc], ((it >> 1) & 1) ^ 1, watchdog)) break;
+                if (!mbar_wait(&bar->full[s], (it / kCsStages) & 1, watchdog)) break;
+                tc_fence_after();
+                const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB + s * kCsBBytes);
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    // k-step of 16 bf16 = 32 B inside a 128 B swizzle row; k >= 4 -> second k-half sub-tile
+                    const uint64_t da = umma_smem_desc_sw128(a0 + (k >> 2) * (kCsM * 128) + (k & 3) * 32);
+                    const uint64_t db = umma_smem_desc_sw128(b0 + (k >> 2) * (kCsN * 128) + (k & 3) * 32);
+                    umma_bf16(tmem_base + acc * kCsN, da, db, idesc, k > 0);
+                }
+                umma_commit(&bar->empty[s]);        // smem stage reusable once these MMAs retire
+                umma_commit(&bar->tmem_full[acc]);  // accumulator ready for the epilogue
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue =====================
+        const int quad = warp & 3, half = (warp - 4) >> 2;
+        const int bq = qgroup * 4 + quad;
+        const int nq = min(qlens[bq], PLAID_NQ_MAX);
+        const bool tok_valid = lane < nq;
+        float* Sq = S + (size_t)bq * C * PLAID_NQ_MAX + lane;
+        uint32_t* bits_q = idx_bits + (size_t)bq * (C >> 5);
+        float bv[PLAID_NCELLS_MAX];
+        int bi[PLAID_NCELLS_MAX];
+#pragma unroll
+        for (int p = 0; p < PLAID_NCELLS_MAX; p++) { bv[p] = -INFINITY; bi[p] = -1; }
+        float cut = -INFINITY;  // current ncells-th best value of this thread
+        for (int it = 0; it < ntiles; it++) {
+            const int acc = it & 1;
+            if (!mbar_wait(&bar->tmem_full[acc], (it >> 1) & 1, watchdog)) break;
+            tc_fence_after();
+            const int c_tile = (tile_begin + it) * kCsN + half * 128;
+#pragma unroll 1
+            for (int ch = 0; ch < 4; ch++) {
+                uint32_t r[32];
+                tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + acc * kCsN + half * 128 + ch * 32, r);
+                tc_wait_ld();
+                const int c0 = c_tile + ch * 32;
+                if (c0 < C) {  // C is a multiple of 32: a chunk is entirely inside or outside
+                    uint32_t word = 0;
+#pragma unroll
+                    for (int j = 0; j < 32; j++) {
+                        const float v = __uint_as_float(r[j]);
+                        st_stream_f32(Sq + (size_t)(c0 + j) * PLAID_NQ_MAX, v);
+                        const int ord = tok_valid ? float_to_ordered_s32(v) : INT_MIN;
+                        const int mx = __reduce_max_sync(0xffffffffu, ord);
+                        const float fmx = __int_as_float(mx ^ ((mx >> 31) & 0x7fffffff));
+                        word |= (fmx >= threshold ? 1u : 0u) << j;
+                        if (tok_valid && v > cut) {
+                            float cv = v;
+                            int ci = c0 + j;
+#pragma unroll
+                            for (int p = 0; p < PLAID_NCELLS_MAX; p++) {
+                                if (p < ncells) {
+                                    const bool ahead = cv > bv[p] || (cv == bv[p] && (unsigned)ci < (unsigned)bi[p]);
+                                    if (ahead) {
+                                        const float tv = bv[p]; bv[p] = cv; cv = tv;
+                                        const int ti = bi[p]; bi[p] = ci; ci = ti;
+                                    }
+                                    if (p == ncells - 1) cut = bv[p];
+                                }
+                            }
+                        }
+                    }
+                    if (lane == 0) bits_q[c0 >> 5] = word;
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar->tmem_empty[acc]);
+        }
+        // every (centroid range, column half) keeps its own partial list: slot = split*2 + half
+        const size_t base = (((size_t)bq * PLAID_NQ_MAX + lane) * (csplit * 2) + (split * 2 + half)) * ncells;
+#pragma unroll
+        for (int p = 0; p < PLAID_NCELLS_MAX; p++)
+            if (p < ncells) {
+                cell_val[base + p] = bv[p];
+                cell_idx[base + p] = tok_valid ? bi[p] : -1;
+            }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+}  // namespace plaid
+
+extern "C" int plaid_centroid_scores(const void* centroids_bf16, int C, const void* Qb_bf16, const int32_t* qlens,
+                                     int B_pad, int Lq_pad, float threshold, int ncells, int csplit, float* S,
+                                     uint32_t* idx_bits, float* cell_val, int32_t* cell_idx, int* watchdog,
+                                     void* stream) {
+    using namespace plaid;
+    PLAID_CHECK_ARG(centroids_bf16 && Qb_bf16 && qlens && S && idx_bits && cell_val && cell_idx, PLAID_ERR_ARG,
+                    "plaid_centroid_scores: null pointer");
+    PLAID_CHECK_ARG(C >= 32 && (C % 32) == 0, PLAID_ERR_UNSUPPORTED, "plaid_centroid_scores: C=%d must be a multiple of 32", C);
+    PLAID_CHECK_ARG(B_pad >= 0 && (B_pad % 4) == 0 && Lq_pad >= 32 && (Lq_pad % 32) == 0, PLAID_ERR_ARG,
+                    "plaid_centroid_scores: B_pad=%d must be a multiple of 4, Lq_pad=%d a multiple of 32", B_pad, Lq_pad);
+    PLAID_CHECK_ARG(ncells >= 1 && ncells <= PLAID_NCELLS_MAX && csplit >= 1 && csplit <= 64, PLAID_ERR_ARG,
+                    "plaid_centroid_scores: ncells=%d (1..%d), csplit=%d (1..64)", ncells, PLAID_NCELLS_MAX, csplit);
+    if (B_pad == 0) return PLAID_OK;
+    CUtensorMap map_q, map_c;
+    int rc;
+    if ((rc = make_bf16_2d_map(&map_q, Qb_bf16, (uint64_t)B_pad * Lq_pad, kDim, 32)) != PLAID_OK) return rc;
+    if ((rc = make_bf16_2d_map(&map_c, centroids_bf16, (uint64_t)C, kDim, kCsN)) != PLAID_OK) return rc;
+    static bool configured = false;
+    if (!configured) {
+        PLAID_CUDA_OK(cudaFuncSetAttribute(centroid_scores_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCsSmemBytes));
+        configured = true;
+    }
+    dim3 grid(B_pad / 4, csplit);
+    centroid_scores_kernel<<<grid, kCsThreads, kCsSmemBytes, (cudaStream_t)stream>>>(
+        map_q, map_c, qlens, C, Lq_pad, threshold, ncells, csplit, S, idx_bits, cell_val, cell_idx, watchdog);
+    PLAID_LAUNCH_OK("centroid_scores_kernel");
+    return PLAID_OK;
+}

@@ -1,0 +1,255 @@
+// common.cuh -- shared helpers for the sm_100a PLAID search kernels.
+//
+// Error handling for the C-ABI (int return codes + plaid_last_error), small device helpers
+// (orderable float keys, streaming loads), and the inline-PTX wrappers for mbarrier, TMA
+// (cp.async.bulk.tensor) and tcgen05 (alloc / mma / commit / ld) used by the two
+// tensor-core kernels (centroid scoring and MaxSim).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cuda.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/plaid_b200.h"
+
+// ----------------------------------------------------------------------------- host side
+namespace plaid {
+
+void set_error(const char* fmt, ...);   // capi.cu
+int  sm_count();                        // capi.cu (cached cudaDevAttrMultiProcessorCount)
+
+// Driver entry point for cuTensorMapEncodeTiled, fetched through the runtime so the library
+// does not link libcuda (it must dlopen on a CPU-only box for the symbol-export test).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn();        // capi.cu
+
+// 2-D bf16 row-major [rows, cols] tensor map, 128B swizzle, box = [box_rows, 64 cols (=128 B)].
+int make_bf16_2d_map(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows);
+
+}  // namespace plaid
+
+#define PLAID_CHECK_ARG(cond, code, ...)                 \
+    do {                                                 \
+        if (!(cond)) {                                   \
+            plaid::set_error(__VA_ARGS__);               \
+            return (code);                               \
+        }                                                \
+    } while (0)
+
+#define PLAID_CUDA_OK(expr)                                                                   \
+    do {                                                                                      \
+        cudaError_t _e = (expr);                                                              \
+        if (_e != cudaSuccess) {                                                              \
+            plaid::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return PLAID_ERR_CUDA;                                                            \
+        }                                                                                     \
+    } while (0)
+
+#define PLAID_LAUNCH_OK(name)                                                                 \
+    do {                                                                                      \
+        cudaError_t _e = cudaGetLastError();                                                  \
+        if (_e != cudaSuccess) {                                                              \
+            plaid::set_error("launch of %s failed: %s", name, cudaGetErrorString(_e));        \
+            return PLAID_ERR_CUDA;                                                            \
+        }                                                                                     \
+    } while (0)
+
+// ----------------------------------------------------------------------------- device side
+#ifdef __CUDACC__
+namespace plaid {
+
+static constexpr int kDim = 128;  // ColBERT/FLMR late-interaction dim (settings.py:101)
+
+__device__ __forceinline__ int ceil_div_d(int a, int b) { return (a + b - 1) / b; }
+
+// Monotone map float -> uint32 (larger float <=> larger key); -0.0 < +0.0, NaNs sort to the ends.
+__device__ __forceinline__ uint32_t float_to_ordered(float f) {
+    uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ordered_to_float(uint32_t k) {
+    uint32_t u = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
+    return __uint_as_float(u);
+}
+// Same order as a *signed* int (for redux.sync.max.s32).
+__device__ __forceinline__ int float_to_ordered_s32(float f) {
+    int i = __float_as_int(f);
+    return i ^ ((i >> 31) & 0x7fffffff);
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+// streaming (read-once) 128-bit / 32-bit global loads that do not allocate in L1
+__device__ __forceinline__ int4 ld_stream_v4(const void* p) {
+    int4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ int2 ld_stream_v2(const void* p) {
+    int2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.s32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ int ld_stream_s32(const void* p) {
+    int r;
+    asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(r) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void st_stream_f32(float* p, float v) {
+    asm volatile("st.global.L1::no_allocate.f32 [%0], %1;" :: "l"(p), "f"(v) : "memory");
+}
+__device__ __forceinline__ void st_stream_v4(void* p, const int4& v) {
+    asm volatile("st.global.L1::no_allocate.v4.s32 [%0], {%1,%2,%3,%4};"
+                 :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+__device__ __forceinline__ uint64_t globaltimer_ns() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// ---- mbarrier ---------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+                 :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol bug must never hang the GPU box.  After ~2 s without the phase
+// completing the waiter records the failure in *watchdog (device memory) and gives up.
+__device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, int* watchdog) {
+    if (mbar_try_wait(bar, parity)) return true;
+    const uint64_t t0 = globaltimer_ns();
+    while (!mbar_try_wait(bar, parity)) {
+        if (globaltimer_ns() - t0 > 2000000000ull) {
+            if (watchdog) atomicExch(watchdog, 1);
+            return false;
+        }
+    }
+    return true;
+}
+
+// ---- TMA --------------------------------------------------------------------------------------
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
+    asm volatile("prefetch.tensormap [%0];" :: "l"(reinterpret_cast<uint64_t>(m)) : "memory");
+}
+// 2-D tile load: crd0 = innermost (column) coordinate, crd1 = row coordinate.
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int crd0, int crd1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        :: "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(crd0), "r"(crd1)
+        : "memory");
+}
+// generic-proxy smem writes -> visible to the async proxy (UMMA / TMA)
+__device__ __forceinline__ void fence_proxy_async_smem() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+// ---- tcgen05 ----------------------------------------------------------------------------------
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                 :: "r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish() {
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after()  { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_wait_ld()      { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem] * B[smem]^T, bf16 x bf16 -> fp32, issued by ONE thread.
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        :: "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+// mbarrier arrive once all previously issued tcgen05.mma of this thread have completed
+// (implies tcgen05.fence::before_thread_sync).
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
+                 :: "r"(smem_u32(bar)) : "memory");
+}
+
+// Shared-memory matrix descriptor: K-major operand, 128-byte swizzle, rows of 128 B (64 bf16),
+// 8-row groups 1024 B apart (the layout TMA writes with CU_TENSOR_MAP_SWIZZLE_128B and a 64-column box).
+//   [0,14) start address >> 4 | [16,30) leading byte offset >> 4 (unused for swizzled K-major, =1)
+//   [32,46) stride byte offset >> 4 (=64) | [46,48) descriptor version (=1 on sm_100) | [61,64) layout (2 = SWIZZLE_128B)
+__device__ __forceinline__ uint64_t umma_smem_desc_sw128(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// Instruction descriptor for kind::f16: bf16 A and B (both K-major), fp32 accumulate, shape M x N x 16.
+//   [4,6) D format (1 = f32) | [7,10) A format (1 = bf16) | [10,13) B format (1 = bf16)
+//   [15] A major (0 = K) | [16] B major (0 = K) | [17,23) N >> 3 | [24,29) M >> 4
+__device__ __host__ __forceinline__ uint32_t umma_idesc_bf16(int M, int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// TMEM -> registers: this warp's 32 lanes x 32 consecutive fp32 columns (thread i <- lane base+i).
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr) : "memory");
+}
+
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "elect.sync _|P, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+
+}  // namespace plaid
+#endif  // __CUDACC__

@@ -1,0 +1,313 @@
+// decompress.cu -- residual decompression (2/4-bit bucket unpack + centroid add).
+//
+// Replaces CB/search/decompress_residuals.cpp:27-155 (CPU, byte-at-a-time table walks) and
+// CB/indexing/codecs/decompress_residuals.cu (one thread per packed byte, two global RMWs per
+// element).  Here a warp pulls 512 B of packed residuals per step with one 128-bit load per lane
+// (= 32/16/8/4 whole tokens at 1/2/4/8 bits), parks them in shared memory, and then emits one
+// token per iteration: lane l owns dimensions 4l..4l+3, so the centroid row is read and the output
+// row written as one fully coalesced request.  The reference's two byte tables
+// (reversed_bit_map, decompression_lookup_table; CB/indexing/codecs/residual.py:54-89) and
+// bucket_weights are folded into one 256-row weight table W[x][l] kept in shared memory.
+#include "common.cuh"
+#include <cuda_fp16.h>
+
+namespace plaid {
+
+static constexpr int kDecWarps = 4;
+
+__global__ void build_weight_table_kernel(const float* __restrict__ bucket_weights, const uint8_t* __restrict__ rbm,
+                                          const uint8_t* __restrict__ lookup, int nbits, float* __restrict__ W) {
+    const int keys = 8 / nbits, x = threadIdx.x;
+    if (x >= 256) return;
+    const int y = rbm[x];
+    for (int l = 0; l < keys; l++) W[x * keys + l] = bucket_weights[lookup[y * keys + l]];
+}
+
+__global__ void unpack_codes_kernel(const uint8_t* __restrict__ residuals, int64_t ntokens, int nbits,
+                                    const uint8_t* __restrict__ rbm, const uint8_t* __restrict__ lookup,
+                                    uint8_t* __restrict__ out) {
+    const int keys = 8 / nbits, pd = kDim / keys;
+    const int64_t total = ntokens * pd;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int y = rbm[residuals[i]];
+        const int64_t t = i / pd;
+        const int k = (int)(i - t * pd);
+        for (int l = 0; l < keys; l++) out[t * kDim + k * keys + l] = lookup[y * keys + l];
+    }
+}
+
+// bucket weights of dimensions 4*lane .. 4*lane+3 of one token whose packed row sits at `row` (smem)
+template <int NBITS>
+__device__ __forceinline__ float4 token_weights(const uint8_t* row, const float* sW, int lane) {
+    if constexpr (NBITS == 2) {
+        return reinterpret_cast<const float4*>(sW)[row[lane]];
+    } else if constexpr (NBITS == 4) {
+        const uchar2 x = reinterpret_cast<const uchar2*>(row)[lane];
+        const float2 a = reinterpret_cast<const float2*>(sW)[x.x], b = reinterpret_cast<const float2*>(sW)[x.y];
+        return make_float4(a.x, a.y, b.x, b.y);
+    } else if constexpr (NBITS == 1) {
+        return reinterpret_cast<const float4*>(sW)[row[lane >> 1] * 2 + (lane & 1)];
+    } else {
+        const uchar4 x = reinterpret_cast<const uchar4*>(row)[lane];
+        return make_float4(sW[x.x], sW[x.y], sW[x.z], sW[x.w]);
+    }
+}
+
+__device__ __forceinline__ float4 load_centroid4(const float* c, int lane) {
+    return __ldg(reinterpret_cast<const float4*>(c) + lane);
+}
+__device__ __forceinline__ float4 load_centroid4(const __half* c, int lane) {
+    const uint2 raw = __ldg(reinterpret_cast<const uint2*>(c) + lane);
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&raw.x));
+    const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
+    return make_float4(a.x, a.y, b.x, b.y);
+}
+
+// Decompress the tokens of ONE passage (codes/residual rows [tok0, tok0+len)) with the warps of a CTA.
+// emit(j, v, lane) receives the fp32 values of dims 4*lane..4*lane+3 of token j.
+template <int NBITS, typename CT, typename Emit>
+__device__ __forceinline__ void decompress_passage(int64_t tok0, int len, const uint8_t* __restrict__ residuals,
+                                                   const int32_t* __restrict__ codes, const CT* __restrict__ centroids,
+                                                   int C, const float* sW, uint8_t* s_stage, Emit emit) {
+    constexpr int PB = 16 * NBITS;   // packed bytes per token
+    constexpr int TB = 512 / PB;     // tokens per 512-byte warp batch
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    uint8_t* stage = s_stage + warp * 512;
+    for (int t0 = warp * TB; t0 < len; t0 += nw * TB) {
+        const int nt = min(TB, len - t0);
+        if (lane * 16 < nt * PB)  // one 128-bit streaming load per lane
+            reinterpret_cast<int4*>(stage)[lane] = ld_stream_v4(residuals + (tok0 + t0) * PB + lane * 16);
+        int code = (lane < nt) ? ld_stream_s32(codes + tok0 + t0 + lane) : 0;
+        __syncwarp();
+#pragma unroll 4
+        for (int j = 0; j < nt; j++) {
+            int c = __shfl_sync(0xffffffffu, code, j);
+            c = min(max(c, 0), C - 1);
+            const float4 w = token_weights<NBITS>(stage + j * PB, sW, lane);
+            const float4 e = load_centroid4(centroids + (size_t)c * kDim, lane);
+            emit(t0 + j, make_float4(w.x + e.x, w.y + e.y, w.z + e.z, w.w + e.w), lane);
+        }
+        __syncwarp();
+    }
+}
+
+template <int NBITS>
+__device__ __forceinline__ void load_weight_table(const float* __restrict__ W, float* sW) {
+    constexpr int n = 256 * (8 / NBITS);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) sW[i] = W[i];
+    __syncthreads();
+}
+
+// ---- operator form: fp32 out, rows packed in pid order (decompress_residuals.cpp semantics) ----
+template <int NBITS, typename CT>
+__global__ void __launch_bounds__(kDecWarps * 32)
+decompress_packed_kernel(const int32_t* __restrict__ pids, int npids, const int64_t* __restrict__ offsets,
+                         const int64_t* __restrict__ out_offsets, const float* __restrict__ W,
+                         const uint8_t* __restrict__ residuals, const int32_t* __restrict__ codes,
+                         const CT* __restrict__ centroids, int C, float* __restrict__ out) {
+    __shared__ __align__(16) float sW[256 * (8 / NBITS)];
+    __shared__ __align__(16) uint8_t s_stage[kDecWarps * 512];
+    load_weight_table<NBITS>(W, sW);
+    for (int i = blockIdx.x; i < npids; i += gridDim.x) {
+        const int pid = pids[i];
+        const int64_t tok0 = offsets[pid];
+        const int len = (int)(offsets[pid + 1] - tok0);
+        float* dst = out + out_offsets[i] * kDim;
+        decompress_passage<NBITS, CT>(tok0, len, residuals, codes, centroids, C, sW, s_stage,
+                                      [&](int j, float4 v, int lane) {
+                                          reinterpret_cast<float4*>(dst + (size_t)j * kDim)[lane] = v;
+                                      });
+    }
+}
+
+// ---- pipeline form: + L2 normalise + bf16, rows placed by per-query token offsets ----
+template <int NBITS, typename CT>
+__global__ void __launch_bounds__(kDecWarps * 32)
+decompress_normalize_kernel(const int32_t* __restrict__ pids, const int32_t* __restrict__ counts, int pid_stride,
+                            const int32_t* __restrict__ tok_offsets, int tok_stride, const int64_t* __restrict__ offsets,
+                            const float* __restrict__ W, const uint8_t* __restrict__ residuals,
+                            const int32_t* __restrict__ codes, const CT* __restrict__ centroids, int C,
+                            __nv_bfloat16* __restrict__ D) {
+    __shared__ __align__(16) float sW[256 * (8 / NBITS)];
+    __shared__ __align__(16) uint8_t s_stage[kDecWarps * 512];
+    const int b = blockIdx.y;
+    const int n = min(counts[b], pid_stride);
+    if ((int)blockIdx.x >= n) return;
+    load_weight_table<NBITS>(W, sW);
+    for (int i = blockIdx.x; i < n; i += gridDim.x) {
+        const int pid = pids[(size_t)b * pid_stride + i];
+        const int64_t tok0 = offsets[pid];
+        const int len = (int)(offsets[pid + 1] - tok0);
+        __nv_bfloat16* dst = D + ((size_t)b * tok_stride + tok_offsets[(size_t)b * (pid_stride + 1) + i]) * kDim;
+        decompress_passage<NBITS, CT>(tok0, len, residuals, codes, centroids, C, sW, s_stage,
+                                      [&](int j, float4 v, int lane) {
+                                          float ss = v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+#pragma unroll
+                                          for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+                                          // F.normalize: x / max(||x||_2, 1e-12)  (index_storage.py:175)
+                                          const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+                                          __nv_bfloat162 lo = __floats2bfloat162_rn(v.x * inv, v.y * inv);
+                                          __nv_bfloat162 hi = __floats2bfloat162_rn(v.z * inv, v.w * inv);
+                                          reinterpret_cast<uint2*>(dst + (size_t)j * kDim)[lane] =
+                                              make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+                                      });
+    }
+}
+
+// per query: exclusive prefix sums of passage lengths
+__global__ void __launch_bounds__(256)
+doc_token_offsets_kernel(const int32_t* __restrict__ pids, const int32_t* __restrict__ counts, int pid_stride,
+                         const int64_t* __restrict__ offsets, int32_t* __restrict__ tok_offsets) {
+    __shared__ int s_warp[8];
+    __shared__ int s_base;
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n = min(counts[b], pid_stride);
+    int32_t* out = tok_offsets + (size_t)b * (pid_stride + 1);
+    if (tid == 0) s_base = 0;
+    __syncthreads();
+    for (int i0 = 0; i0 < pid_stride; i0 += blockDim.x) {
+        const int i = i0 + tid;
+        int len = 0;
+        if (i < n) {
+            const int pid = pids[(size_t)b * pid_stride + i];
+            len = (int)(offsets[pid + 1] - offsets[pid]);
+        }
+        int incl = len;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        int wbase = 0;
+        for (int w = 0; w < warp; w++) wbase += s_warp[w];
+        const int excl = s_base + wbase + incl - len;
+        if (i < pid_stride) out[i] = excl;
+        __syncthreads();
+        if (tid == blockDim.x - 1) s_base = excl + len;
+        __syncthreads();
+    }
+    if (tid == 0) out[pid_stride] = s_base;
+}
+
+template <typename CT>
+static int launch_packed(int nbits, const int32_t* pids, int npids, const int64_t* offsets, const int64_t* out_offsets,
+                         const float* W, const uint8_t* residuals, const int32_t* codes, const CT* centroids, int C,
+                         float* out, cudaStream_t st) {
+    int grid = npids < 148 * 16 ? npids : 148 * 16;
+#define PLAID_DEC_CASE(NB)                                                                                              \
+    case NB:                                                                                                            \
+        decompress_packed_kernel<NB, CT><<<grid, kDecWarps * 32, 0, st>>>(pids, npids, offsets, out_offsets, W, residuals, \
+                                                                         codes, centroids, C, out);                   \
+        break;
+    switch (nbits) {
+        PLAID_DEC_CASE(1) PLAID_DEC_CASE(2) PLAID_DEC_CASE(4) PLAID_DEC_CASE(8)
+        default:
+            set_error("decompress: nbits=%d not in {1,2,4,8}", nbits);
+            return PLAID_ERR_UNSUPPORTED;
+    }
+#undef PLAID_DEC_CASE
+    PLAID_LAUNCH_OK("decompress_packed_kernel");
+    return PLAID_OK;
+}
+
+template <typename CT>
+static int launch_normalize(int nbits, const int32_t* pids, const int32_t* counts, int B, int pid_stride,
+                            const int32_t* tok_offsets, int tok_stride, const int64_t* offsets, const float* W,
+                            const uint8_t* residuals, const int32_t* codes, const CT* centroids, int C,
+                            __nv_bfloat16* D, cudaStream_t st) {
+    dim3 grid(pid_stride, B);
+#define PLAID_DEC_CASE(NB)                                                                                      \
+    case NB:                                                                                                    \
+        decompress_normalize_kernel<NB, CT><<<grid, kDecWarps * 32, 0, st>>>(pids, counts, pid_stride, tok_offsets, \
+                                                                            tok_stride, offsets, W, residuals, codes, \
+                                                                            centroids, C, D);                    \
+        break;
+    switch (nbits) {
+        PLAID_DEC_CASE(1) PLAID_DEC_CASE(2) PLAID_DEC_CASE(4) PLAID_DEC_CASE(8)
+        default:
+            set_error("decompress: nbits=%d not in {1,2,4,8}", nbits);
+            return PLAID_ERR_UNSUPPORTED;
+    }
+#undef PLAID_DEC_CASE
+    PLAID_LAUNCH_OK("decompress_normalize_kernel");
+    return PLAID_OK;
+}
+
+}  // namespace plaid
+
+extern "C" int plaid_build_weight_table(const float* bucket_weights, const uint8_t* reversed_bit_map,
+                                        const uint8_t* lookup, int nbits, float* W, void* stream) {
+    using namespace plaid;
+    PLAID_CHECK_ARG(bucket_weights && reversed_bit_map && lookup && W, PLAID_ERR_ARG, "plaid_build_weight_table: null pointer");
+    PLAID_CHECK_ARG(nbits == 1 || nbits == 2 || nbits == 4 || nbits == 8, PLAID_ERR_UNSUPPORTED,
+                    "plaid_build_weight_table: nbits=%d not in {1,2,4,8}", nbits);
+    build_weight_table_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(bucket_weights, reversed_bit_map, lookup, nbits, W);
+    PLAID_LAUNCH_OK("build_weight_table_kernel");
+    return PLAID_OK;
+}
+
+extern "C" int plaid_unpack_residual_codes(const uint8_t* residuals, int64_t ntokens, int nbits,
+                                           const uint8_t* reversed_bit_map, const uint8_t* lookup, uint8_t* out,
+                                           void* stream) {
+    using namespace plaid;
+    PLAID_CHECK_ARG(residuals && reversed_bit_map && lookup && out && ntokens >= 0, PLAID_ERR_ARG,
+                    "plaid_unpack_residual_codes: bad argument");
+    PLAID_CHECK_ARG(nbits == 1 || nbits == 2 || nbits == 4 || nbits == 8, PLAID_ERR_UNSUPPORTED,
+                    "plaid_unpack_residual_codes: nbits=%d not in {1,2,4,8}", nbits);
+    if (ntokens == 0) return PLAID_OK;
+    unpack_codes_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(residuals, ntokens, nbits, reversed_bit_map, lookup, out);
+    PLAID_LAUNCH_OK("unpack_codes_kernel");
+    return PLAID_OK;
+}
+
+extern "C" int plaid_decompress_residuals(const int32_t* pids, int npids, const int64_t* offsets,
+                                          const int64_t* out_offsets, const float* W, const uint8_t* residuals,
+                                          const int32_t* codes, const float* centroids, int C, int nbits, float* out,
+                                          void* stream) {
+    using namespace plaid;
+    PLAID_CHECK_ARG(pids && offsets && out_offsets && W && residuals && codes && centroids && out, PLAID_ERR_ARG,
+                    "plaid_decompress_residuals: null pointer");
+    PLAID_CHECK_ARG(npids >= 0 && C > 0, PLAID_ERR_ARG, "plaid_decompress_residuals: bad sizes");
+    PLAID_CHECK_ARG((reinterpret_cast<uintptr_t>(residuals) & 15) == 0 && (reinterpret_cast<uintptr_t>(centroids) & 15) == 0 &&
+                        (reinterpret_cast<uintptr_t>(out) & 15) == 0,
+                    PLAID_ERR_ARG, "plaid_decompress_residuals: residuals/centroids/out must be 16-byte aligned");
+    if (npids == 0) return PLAID_OK;
+    return launch_packed<float>(nbits, pids, npids, offsets, out_offsets, W, residuals, codes, centroids, C, out,
+                                (cudaStream_t)stream);
+}
+
+extern "C" int plaid_doc_token_offsets(const int32_t* pids, const int32_t* counts, int B, int pid_stride,
+                                       const int64_t* offsets, int32_t* tok_offsets, void* stream) {
+    using namespace plaid;
+    PLAID_CHECK_ARG(pids && counts && offsets && tok_offsets && B >= 0 && pid_stride >= 1, PLAID_ERR_ARG,
+                    "plaid_doc_token_offsets: bad argument");
+    if (B == 0) return PLAID_OK;
+    doc_token_offsets_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(pids, counts, pid_stride, offsets, tok_offsets);
+    PLAID_LAUNCH_OK("doc_token_offsets_kernel");
+    return PLAID_OK;
+}
+
+extern "C" int plaid_decompress_normalize_bf16(const int32_t* pids, const int32_t* counts, int B, int pid_stride,
+                                               const int32_t* tok_offsets, int tok_stride, const int64_t* offsets,
+                                               const float* W, const uint8_t* residuals, const int32_t* codes,
+                                               const void* centroids, int centroids_are_f16, int C, int nbits,
+                                               void* D_bf16, void* stream) {
+    using namespace plaid;
+    PLAID_CHECK_ARG(pids && counts && tok_offsets && offsets && W && residuals && codes && centroids && D_bf16, PLAID_ERR_ARG,
+                    "plaid_decompress_normalize_bf16: null pointer");
+    PLAID_CHECK_ARG(B >= 0 && pid_stride >= 1 && tok_stride >= 1 && C > 0, PLAID_ERR_ARG,
+                    "plaid_decompress_normalize_bf16: bad sizes");
+    PLAID_CHECK_ARG((reinterpret_cast<uintptr_t>(residuals) & 15) == 0 && (reinterpret_cast<uintptr_t>(centroids) & 15) == 0 &&
+                        (reinterpret_cast<uintptr_t>(D_bf16) & 15) == 0,
+                    PLAID_ERR_ARG, "plaid_decompress_normalize_bf16: residuals/centroids/D must be 16-byte aligned");
+    if (B == 0) return PLAID_OK;
+    PLAID_CHECK_ARG(B <= 65535, PLAID_ERR_UNSUPPORTED, "plaid_decompress_normalize_bf16: B=%d > 65535 per call", B);
+    __nv_bfloat16* D = reinterpret_cast<__nv_bfloat16*>(D_bf16);
+    if (centroids_are_f16)
+        return launch_normalize<__half>(nbits, pids, counts, B, pid_stride, tok_offsets, tok_stride, offsets, W, residuals,
+                                        codes, reinterpret_cast<const __half*>(centroids), C, D, (cudaStream_t)stream);
+    return launch_normalize<float>(nbits, pids, counts, B, pid_stride, tok_offsets, tok_stride, offsets, W, residuals, codes,
+                                   reinterpret_cast<const float*>(centroids), C, D, (cudaStream_t)stream);
+}

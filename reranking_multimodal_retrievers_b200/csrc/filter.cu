@@ -1,0 +1,326 @@
+// filter.cu -- centroid-only passage filtering and (score, pid) selection.
+//
+// Replaces CB/search/filter_pids.cpp (pthreads, priority queues) and the final
+// `scores.sort(descending=True)` of CB/search/index_storage.py:95-96.
+//
+// approx_scores: one warp per candidate passage, lane = query token (nq <= 32 = warp width).  The
+//   passage's centroid codes are read 32 at a time (one coalesced 128 B request), the pruning mask is
+//   a per-query bitmap, and every surviving code costs one coalesced 128 B read of the S row
+//   S[b, code, 0..31].  The per-passage score is summed sequentially in token order so that it is
+//   bit-identical to filter_pids.cpp:59-63.
+// select_top: one CTA per query; 64-bit keys (orderable(score) << 32 | pid) reproduce the
+//   std::pair<float,int> ordering of filter_pids.cpp:24; an 8-pass MSB radix select finds the
+//   keep-th key, survivors are bitonic-sorted in shared memory.
+#include "common.cuh"
+
+namespace plaid {
+
+static constexpr int kApproxWarps = 8;  // warps (= passages) per CTA
+
+template <bool USE_IDX>
+__global__ void __launch_bounds__(kApproxWarps * 32)
+approx_scores_kernel(const int32_t* __restrict__ pids, const int32_t* __restrict__ counts, int pid_stride,
+                     const float* __restrict__ S, const int32_t* __restrict__ qlens,
+                     const uint32_t* __restrict__ idx_bits, int C, const int32_t* __restrict__ codes,
+                     const int64_t* __restrict__ offsets, float* __restrict__ out) {
+    const int b = blockIdx.y, lane = threadIdx.x & 31;
+    const int i = blockIdx.x * kApproxWarps + (threadIdx.x >> 5);
+    const int n = min(counts[b], pid_stride);
+    if (i >= n) return;
+    const int pid = pids[(size_t)b * pid_stride + i];
+    const int64_t off = offsets[pid];
+    const int len = (int)(offsets[pid + 1] - off);
+    const int nq = min(qlens[b], PLAID_NQ_MAX);
+    const float* Sb = S + (size_t)b * C * PLAID_NQ_MAX + lane;
+    const uint32_t* bits = USE_IDX ? idx_bits + (size_t)b * (C >> 5) : nullptr;
+    float m = -9999.0f;  // filter_pids.cpp:30-33
+    for (int j0 = 0; j0 < len; j0 += 32) {
+        const int j = j0 + lane;
+        int code = (j < len) ? ld_stream_s32(codes + off + j) : -1;
+        bool keep = (unsigned)code < (unsigned)C;
+        if (USE_IDX) keep = keep && ((__ldg(bits + (code >> 5)) >> (code & 31)) & 1u);
+        unsigned mask = __ballot_sync(0xffffffffu, keep);
+        // four S rows in flight per step
+        while (mask) {
+            int src[4];
+            float v[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                src[u] = mask ? (__ffs(mask) - 1) : -1;
+                if (mask) mask &= mask - 1;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int c = __shfl_sync(0xffffffffu, code, src[u] < 0 ? 0 : src[u]);
+                v[u] = (src[u] >= 0) ? __ldg(Sb + (size_t)c * PLAID_NQ_MAX) : -9999.0f;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) m = fmaxf(m, v[u]);
+        }
+    }
+    float s = 0.0f;  // sequential fp32 sum in token order (filter_pids.cpp:59-63)
+    for (int k = 0; k < nq; k++) s += __shfl_sync(0xffffffffu, m, k);
+    if (lane == 0) out[(size_t)b * pid_stride + i] = s;
+}
+
+// ------------------------------------------------------------------------------------------ select
+static constexpr int kSelThreads = 1024;
+
+__device__ __forceinline__ uint64_t make_key(float score, int32_t pid) {
+    return ((uint64_t)float_to_ordered(score) << 32) | (uint32_t)pid;
+}
+
+// Block-wide: among keys[0..n) pick the `keep` largest into s_sel (sorted descending), return count.
+// s_sel has room for sel_cap = next_pow2(keep) keys; s_hist is 256 ints; s_misc 4 ints.
+__device__ int select_sorted_desc(const uint64_t* __restrict__ keys, int n, int keep, uint64_t* s_sel, int sel_cap,
+                                  int* s_hist, int* s_misc) {
+    const int tid = threadIdx.x;
+    const int m = min(n, keep);
+    uint64_t thresh = 0;  // with n <= keep every key is selected
+    int n_greater_needed = m;
+    if (n > keep) {
+        // MSB-first radix select of the keep-th largest key.
+        uint64_t prefix = 0, prefix_mask = 0;
+        int remaining = keep;  // rank (1-based, from the top) still to be located inside the prefix group
+        for (int shift = 56; shift >= 0; shift -= 8) {
+            for (int i = tid; i < 256; i += blockDim.x) s_hist[i] = 0;
+            __syncthreads();
+            for (int i = tid; i < n; i += blockDim.x) {
+                const uint64_t k = keys[i];
+                if ((k & prefix_mask) == prefix) atomicAdd(&s_hist[(int)((k >> shift) & 0xff)], 1);
+            }
+            __syncthreads();
+            if (tid == 0) {
+                int acc = 0, d = 255;
+                for (; d > 0; d--) {
+                    if (acc + s_hist[d] >= remaining) break;
+                    acc += s_hist[d];
+                }
+                s_misc[0] = d;
+                s_misc[1] = remaining - acc;
+            }
+            __syncthreads();
+            prefix |= (uint64_t)s_misc[0] << shift;
+            prefix_mask |= (uint64_t)0xff << shift;
+            remaining = s_misc[1];
+            __syncthreads();
+        }
+        thresh = prefix;              // the keep-th largest key
+        n_greater_needed = remaining; // how many copies of `thresh` itself belong to the selection
+    }
+    for (int i = tid; i < sel_cap; i += blockDim.x) s_sel[i] = 0;
+    if (tid == 0) { s_misc[2] = 0; s_misc[3] = 0; }
+    __syncthreads();
+    for (int i = tid; i < n; i += blockDim.x) {
+        const uint64_t k = keys[i];
+        bool take = (n <= keep) || (k > thresh);
+        if (!take && k == thresh) take = atomicAdd(&s_misc[3], 1) < n_greater_needed;
+        if (take) {
+            const int slot = atomicAdd(&s_misc[2], 1);
+            if (slot < sel_cap) s_sel[slot] = k;
+        }
+    }
+    __syncthreads();
+    // bitonic sort, descending (zero padding sinks to the end; real keys are > 0 because the
+    // ordered-float transform never yields 0 in the high word for non-NaN scores)
+    for (int size = 2; size <= sel_cap; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int t = tid; t < (sel_cap >> 1); t += blockDim.x) {
+                const int lo = 2 * t - (t & (stride - 1));
+                const int hi = lo + stride;
+                const bool desc = ((lo & size) == 0);
+                const uint64_t a = s_sel[lo], c = s_sel[hi];
+                if ((a < c) == desc) { s_sel[lo] = c; s_sel[hi] = a; }
+            }
+            __syncthreads();
+        }
+    }
+    return m;
+}
+
+__device__ void write_selection(const uint64_t* s_sel, int m, int out_stride, int32_t* out_pids, float* out_scores,
+                                int32_t* out_count) {
+    for (int i = threadIdx.x; i < out_stride; i += blockDim.x) {
+        if (i < m) {
+            const uint64_t k = s_sel[i];
+            out_pids[i] = (int32_t)(uint32_t)(k & 0xffffffffu);
+            if (out_scores) out_scores[i] = ordered_to_float((uint32_t)(k >> 32));
+        } else {
+            out_pids[i] = PLAID_NO_PID;
+            if (out_scores) out_scores[i] = -INFINITY;
+        }
+    }
+    if (threadIdx.x == 0 && out_count) *out_count = m;
+}
+
+__global__ void __launch_bounds__(kSelThreads)
+select_top_kernel(const int32_t* __restrict__ pids, const float* __restrict__ scores, const int32_t* __restrict__ counts,
+                  int in_stride, int keep, int sel_cap, int32_t* __restrict__ out_pids, float* __restrict__ out_scores,
+                  int32_t* __restrict__ out_counts, int out_stride, uint64_t* __restrict__ ws_keys) {
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    uint64_t* s_sel = reinterpret_cast<uint64_t*>(s_raw);
+    int* s_hist = reinterpret_cast<int*>(s_sel + sel_cap);
+    int* s_misc = s_hist + 256;
+    const int b = blockIdx.x;
+    const int n = min(counts[b], in_stride);
+    uint64_t* keys = ws_keys + (size_t)b * in_stride;
+    for (int i = threadIdx.x; i < n; i += blockDim.x)
+        keys[i] = make_key(scores[(size_t)b * in_stride + i], pids[(size_t)b * in_stride + i]);
+    __syncthreads();
+    const int m = select_sorted_desc(keys, n, keep, s_sel, sel_cap, s_hist, s_misc);
+    write_selection(s_sel, m, out_stride, out_pids + (size_t)b * out_stride,
+                    out_scores ? out_scores + (size_t)b * out_stride : nullptr, out_counts ? out_counts + b : nullptr);
+}
+
+// gathered layout [G, B, k] -> per query G*k keys
+__global__ void __launch_bounds__(kSelThreads)
+merge_topk_kernel(const float* __restrict__ scores, const int32_t* __restrict__ pids, const int32_t* __restrict__ counts,
+                  int G, int B, int k, int sel_cap, int32_t* __restrict__ out_pids, float* __restrict__ out_scores,
+                  int32_t* __restrict__ out_counts, uint64_t* __restrict__ ws_keys) {
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    uint64_t* s_sel = reinterpret_cast<uint64_t*>(s_raw);
+    int* s_hist = reinterpret_cast<int*>(s_sel + sel_cap);
+    int* s_misc = s_hist + 256;
+    const int b = blockIdx.x;
+    uint64_t* keys = ws_keys + (size_t)b * G * k;
+    // compact the valid entries of the G lists (serial prefix over G <= 64 lists)
+    if (threadIdx.x == 0) {
+        int acc = 0;
+        for (int g = 0; g < G; g++) {
+            s_hist[g] = acc;
+            acc += min(max(counts[(size_t)g * B + b], 0), k);
+        }
+        s_hist[G] = acc;
+    }
+    __syncthreads();
+    const int n = s_hist[G];
+    for (int t = threadIdx.x; t < G * k; t += blockDim.x) {
+        const int g = t / k, i = t - g * k;
+        const int cnt = min(max(counts[(size_t)g * B + b], 0), k);
+        if (i < cnt) {
+            const size_t src = ((size_t)g * B + b) * k + i;
+            keys[s_hist[g] + i] = make_key(scores[src], pids[src]);
+        }
+    }
+    __syncthreads();
+    const int m = select_sorted_desc(keys, n, k, s_sel, sel_cap, s_hist, s_misc);
+    write_selection(s_sel, m, k, out_pids + (size_t)b * k, out_scores + (size_t)b * k, out_counts ? out_counts + b : nullptr);
+}
+
+static int next_pow2(int v) {
+    int p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+static int launch_approx(const int32_t* pids, const int32_t* counts, int B, int pid_stride, const float* S,
+                         const int32_t* qlens, const uint32_t* idx_bits, int C, const int32_t* codes,
+                         const int64_t* offsets, float* out, cudaStream_t st) {
+    dim3 grid((pid_stride + kApproxWarps - 1) / kApproxWarps, B);
+    if (idx_bits)
+        approx_scores_kernel<true><<<grid, kApproxWarps * 32, 0, st>>>(pids, counts, pid_stride, S, qlens, idx_bits, C,
+                                                                       codes, offsets, out);
+    else
+        approx_scores_kernel<false><<<grid, kApproxWarps * 32, 0, st>>>(pids, counts, pid_stride, S, qlens, nullptr, C,
+                                                                        codes, offsets, out);
+    PLAID_LAUNCH_OK("approx_scores_kernel");
+    return PLAID_OK;
+}
+
+static int launch_select(const int32_t* pids, const float* scores, const int32_t* counts, int B, int in_stride, int keep,
+                         int32_t* out_pids, float* out_scores, int32_t* out_counts, int out_stride, uint64_t* ws_keys,
+                         cudaStream_t st) {
+    PLAID_CHECK_ARG(keep >= 1 && keep <= 16384, PLAID_ERR_UNSUPPORTED, "select_top: keep=%d outside [1, 16384]", keep);
+    PLAID_CHECK_ARG(out_stride >= keep, PLAID_ERR_ARG, "select_top: out_stride=%d < keep=%d", out_stride, keep);
+    const int sel_cap = next_pow2(keep < 2 ? 2 : keep);
+    const size_t smem = (size_t)sel_cap * 8 + 256 * 4 + 16;
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        PLAID_CUDA_OK(cudaFuncSetAttribute(select_top_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    select_top_kernel<<<B, kSelThreads, smem, st>>>(pids, scores, counts, in_stride, keep, sel_cap, out_pids, out_scores,
+                                                    out_counts, out_stride, ws_keys);
+    PLAID_LAUNCH_OK("select_top_kernel");
+    return PLAID_OK;
+}
+
+}  // namespace plaid
+
+extern "C" int plaid_approx_scores(const int32_t* pids, const int32_t* counts, int B, int pid_stride, const float* S,
+                                   const int32_t* qlens, const uint32_t* idx_bits, int C, const int32_t* codes,
+                                   const int64_t* offsets, float* out_scores, void* stream) {
+    using namespace plaid;
+    PLAID_CHECK_ARG(pids && counts && S && qlens && codes && offsets && out_scores, PLAID_ERR_ARG,
+                    "plaid_approx_scores: null pointer");
+    PLAID_CHECK_ARG(B >= 0 && pid_stride >= 0 && C > 0 && (C % 32) == 0, PLAID_ERR_ARG,
+                    "plaid_approx_scores: bad sizes (B=%d stride=%d C=%d; C must be a multiple of 32)", B, pid_stride, C);
+    if (B == 0 || pid_stride == 0) return PLAID_OK;
+    PLAID_CHECK_ARG(B <= 65535, PLAID_ERR_UNSUPPORTED, "plaid_approx_scores: B=%d > 65535 per call", B);
+    return launch_approx(pids, counts, B, pid_stride, S, qlens, idx_bits, C, codes, offsets, out_scores,
+                         (cudaStream_t)stream);
+}
+
+extern "C" int plaid_select_top(const int32_t* pids, const float* scores, const int32_t* counts, int B, int in_stride,
+                                int keep, int32_t* out_pids, float* out_scores, int32_t* out_counts, int out_stride,
+                                uint64_t* ws_keys, void* stream) {
+    using namespace plaid;
+    PLAID_CHECK_ARG(pids && scores && counts && out_pids && ws_keys, PLAID_ERR_ARG, "plaid_select_top: null pointer");
+    PLAID_CHECK_ARG(B >= 0 && in_stride >= 0, PLAID_ERR_ARG, "plaid_select_top: bad sizes");
+    if (B == 0) return PLAID_OK;
+    return launch_select(pids, scores, counts, B, in_stride, keep, out_pids, out_scores, out_counts, out_stride, ws_keys,
+                         (cudaStream_t)stream);
+}
+
+extern "C" int plaid_filter_pids(const int32_t* pids, const int32_t* counts, int B, int pid_stride, const float* S,
+                                 const int32_t* qlens, const uint32_t* idx_bits, int C, const int32_t* codes,
+                                 const int64_t* offsets, int ndocs, float* ws_scores, uint64_t* ws_keys,
+                                 int32_t* stage1_pids, float* stage1_scores, int32_t* stage1_counts,
+                                 int32_t* stage2_pids, float* stage2_scores, int32_t* stage2_counts, void* stream) {
+    using namespace plaid;
+    PLAID_CHECK_ARG(pids && counts && S && qlens && idx_bits && codes && offsets && ws_scores && ws_keys && stage1_pids &&
+                        stage1_scores && stage1_counts && stage2_pids && stage2_scores && stage2_counts,
+                    PLAID_ERR_ARG, "plaid_filter_pids: null pointer");
+    PLAID_CHECK_ARG(ndocs >= 4 && B >= 0 && pid_stride >= 0 && C > 0 && (C % 32) == 0, PLAID_ERR_ARG,
+                    "plaid_filter_pids: bad sizes (ndocs=%d B=%d stride=%d C=%d)", ndocs, B, pid_stride, C);
+    if (B == 0) return PLAID_OK;
+    PLAID_CHECK_ARG(B <= 65535, PLAID_ERR_UNSUPPORTED, "plaid_filter_pids: B=%d > 65535 per call", B);
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc;
+    // stage 1: pruned centroids only (filter_pids.cpp:139-146), keep ndocs
+    if (pid_stride > 0 &&
+        (rc = launch_approx(pids, counts, B, pid_stride, S, qlens, idx_bits, C, codes, offsets, ws_scores, st)) != PLAID_OK)
+        return rc;
+    if ((rc = launch_select(pids, ws_scores, counts, B, pid_stride, ndocs, stage1_pids, stage1_scores, stage1_counts, ndocs,
+                            ws_keys, st)) != PLAID_OK)
+        return rc;
+    // stage 2: all centroids (filter_pids.cpp:148-157), keep ndocs/4.  ws_scores is free again (its content
+    // was folded into the keys) and is reused with row stride ndocs.
+    if ((rc = launch_approx(stage1_pids, stage1_counts, B, ndocs, S, qlens, nullptr, C, codes, offsets, ws_scores, st)) !=
+        PLAID_OK)
+        return rc;
+    return launch_select(stage1_pids, ws_scores, stage1_counts, B, ndocs, ndocs / 4, stage2_pids, stage2_scores,
+                         stage2_counts, ndocs / 4, ws_keys, st);
+}
+
+extern "C" int plaid_merge_topk(const float* scores, const int32_t* pids, const int32_t* counts, int G, int B, int k,
+                                int32_t* out_pids, float* out_scores, int32_t* out_counts, uint64_t* ws_keys,
+                                void* stream) {
+    using namespace plaid;
+    PLAID_CHECK_ARG(scores && pids && counts && out_pids && out_scores && ws_keys, PLAID_ERR_ARG,
+                    "plaid_merge_topk: null pointer");
+    PLAID_CHECK_ARG(G >= 1 && G <= 64 && B >= 0 && k >= 1 && k <= 16384, PLAID_ERR_UNSUPPORTED,
+                    "plaid_merge_topk: G=%d (1..64), k=%d (1..16384)", G, k);
+    if (B == 0) return PLAID_OK;
+    const int sel_cap = next_pow2(k < 2 ? 2 : k);
+    const size_t smem = (size_t)sel_cap * 8 + 256 * 4 + 16;
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        PLAID_CUDA_OK(cudaFuncSetAttribute(merge_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    merge_topk_kernel<<<B, kSelThreads, smem, (cudaStream_t)stream>>>(scores, pids, counts, G, B, k, sel_cap, out_pids,
+                                                                      out_scores, out_counts, ws_keys);
+    PLAID_LAUNCH_OK("merge_topk_kernel");
+    return PLAID_OK;
+}

@@ -1,0 +1,420 @@
+// maxsim.cu -- late-interaction MaxSim on tcgen05 / TMEM with the per-passage max + sum fused into
+// the epilogue, so the [tokens x Lq] similarity matrix never reaches HBM.
+//
+// Replaces, for a whole batch of queries:
+//   packed form  : colbert_score_packed (CB/modeling/colbert.py:289-311) + segmented_maxsim.cpp:22-93
+//                  -- zero-initialised running max per (passage, query token), summed over query tokens;
+//   padded form  : colbert_score + colbert_score_reduce (CB/modeling/colbert.py:235-286,
+//                  src/models/flmr/models/flmr/flmr_utils.py:22-48) -- masked positions count as -9999,
+//                  max over passage tokens, sum over query tokens, optional masked matrix output.
+//
+// Orientation: accumulator lanes (M = 128 per m-tile, MT = ceil(Lq_pad/128) m-tiles) are QUERY tokens,
+// accumulator columns (NT per tile) are PASSAGE tokens of consecutive passages.  One epilogue thread
+// therefore owns one query token and walks passage tokens left to right: the running max is a
+// register, a passage boundary is a flush (clamp, warp-shuffle sum over the 32 query tokens of the
+// warp, add into a per-warp shared-memory slot), and a passage that straddles tiles simply keeps its
+// register.  Work item = (query, group of 16 consecutive passages); CTAs are persistent over a
+// contiguous range of items so the query operand (A, resident in smem) is reloaded only when the
+// query changes.  B tiles (passage tokens, bf16 [NT x 128]) stream through an NS-stage TMA ring;
+// accumulators are double-buffered in TMEM.
+#include "common.cuh"
+
+namespace plaid {
+
+static constexpr int kMsThreads = 256;   // warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4..7 epilogue
+static constexpr int kMsGD = 16;         // passages per work item
+static constexpr int kMsMaxStages = 8;
+static constexpr int kMsMaxMT = 4;       // Lq_pad <= 512
+
+struct MsParams {
+    const int32_t* qlens;        // [nQ] valid rows per query
+    int Lq_pad, MT, NT, NS;
+    int padded;                  // 0 = packed search form, 1 = padded colbert_score form
+    // packed
+    const int32_t* tok_offsets;  // [B, pid_stride+1] per-query exclusive prefix of passage lengths
+    const int32_t* counts;       // [B]
+    int pid_stride, tok_stride;
+    // padded
+    const uint8_t* mask;         // [n, Ld]
+    long long n_docs;
+    int Ld, docs_per_query;
+    float* scores_raw;           // optional [n, Ld, Lq_out]
+    int Lq_out;
+    // common
+    float* scores;
+    int groups_per_query, num_items, items_per_cta;
+    int clamp_zero;
+    int* watchdog;
+};
+
+struct MsItem {
+    int q;            // query index (row block of the A operand)
+    int nd;           // passages in this item
+    long long row0;   // first D row of the item
+    int ntok;         // D rows (tokens) in the item
+    long long out0;   // index of the first passage's score
+    const int32_t* ends;  // packed: &tok_offsets[b][d0] (ends[i+1]-ends[0] = end of passage i); padded: nullptr
+};
+
+__device__ __forceinline__ MsItem ms_item(const MsParams& p, int w) {
+    MsItem it;
+    const int q = w / p.groups_per_query, g = w - q * p.groups_per_query;
+    it.q = q;
+    if (!p.padded) {
+        const int cnt = min(p.counts[q], p.pid_stride);
+        const int d0 = g * kMsGD;
+        it.nd = max(0, min(kMsGD, cnt - d0));
+        const int32_t* to = p.tok_offsets + (size_t)q * (p.pid_stride + 1);
+        it.ends = to + d0;
+        const int t0 = it.nd > 0 ? to[d0] : 0;
+        it.ntok = it.nd > 0 ? to[d0 + it.nd] - t0 : 0;
+        it.row0 = (long long)q * p.tok_stride + t0;
+        it.out0 = (long long)q * p.pid_stride + d0;
+    } else {
+        const long long dq0 = (long long)q * p.docs_per_query;
+        const long long dq1 = min(dq0 + p.docs_per_query, p.n_docs);
+        const long long d0 = dq0 + (long long)g * kMsGD;
+        it.nd = (int)max(0ll, min((long long)kMsGD, dq1 - d0));
+        it.ends = nullptr;
+        it.ntok = it.nd * p.Ld;
+        it.row0 = d0 * p.Ld;
+        it.out0 = d0;
+    }
+    return it;
+}
+
+struct MsShared {
+    uint64_t a_full, a_empty;
+    uint64_t full[kMsMaxStages];
+    uint64_t empty[kMsMaxStages];
+    uint64_t tmem_full[2];
+    uint64_t tmem_empty[2];
+    uint32_t tmem_base;
+    float part[2][4][kMsGD];
+};
+
+// Barrier over the 128 epilogue threads that also ORs a predicate, so that a watchdog abort seen by
+// one warp stops all four at the same work item (a lone early exit would strand the others here).
+__device__ __forceinline__ bool epi_bar_or(bool pred) {
+    uint32_t r;
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t"
+        "setp.ne.u32 p, %1, 0;\n\t"
+        "bar.red.or.pred q, 1, 128, p;\n\t"
+        "selp.u32 %0, 1, 0, q;\n\t}"
+        : "=r"(r) : "r"((uint32_t)pred) : "memory");
+    return r != 0;
+}
+
+__global__ void __launch_bounds__(kMsThreads, 1)
+maxsim_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_d, const MsParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int a_bytes = p.MT * 128 * kDim * 2;
+    const int b_bytes = p.NT * kDim * 2;
+    uint8_t* sA = smem;                     // [MT][2 k-halves][128 rows][128 B]
+    uint8_t* sB = smem + a_bytes;           // [NS][2 k-halves][NT rows][128 B]
+    MsShared* sh = reinterpret_cast<MsShared*>(sB + p.NS * b_bytes);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int item_begin = blockIdx.x * p.items_per_cta;
+    const int item_end = min(p.num_items, item_begin + p.items_per_cta);
+
+    if (threadIdx.x == 0) {
+        mbar_init(&sh->a_full, 1);
+        mbar_init(&sh->a_empty, 1);
+        for (int s = 0; s < p.NS; s++) { mbar_init(&sh->full[s], 1); mbar_init(&sh->empty[s], 1); }
+        for (int a = 0; a < 2; a++) { mbar_init(&sh->tmem_full[a], 1); mbar_init(&sh->tmem_empty[a], 4); }
+        fence_mbar_init();
+    }
+    if (warp == 2) {
+        tmem_alloc(&sh->tmem_base, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = sh->tmem_base;
+    const int acc_cols = p.MT * p.NT;  // columns of one accumulator buffer
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            tma_prefetch_desc(&map_q);
+            tma_prefetch_desc(&map_d);
+            int cur_q = -1, a_loads = 0, it_tile = 0;
+            bool ok = true;
+            for (int w = item_begin; ok && w < item_end; w++) {
+                const MsItem it = ms_item(p, w);
+                if (it.nd == 0) continue;
+                if (it.q != cur_q) {
+                    if (a_loads > 0 && !mbar_wait(&sh->a_empty, (a_loads - 1) & 1, p.watchdog)) break;
+                    mbar_expect_tx(&sh->a_full, a_bytes);
+                    for (int m = 0; m < p.MT; m++)
+                        for (int h = 0; h < 2; h++)
+                            tma_load_2d(sA + (m * 2 + h) * (128 * 128), &map_q, &sh->a_full, h * 64,
+                                        it.q * p.Lq_pad + m * 128);
+                    cur_q = it.q;
+                    a_loads++;
+                }
+                const int ntiles = (it.ntok + p.NT - 1) / p.NT;
+                for (int t = 0; t < ntiles; t++, it_tile++) {
+                    const int s = it_tile % p.NS;
+                    if (!mbar_wait(&sh->empty[s], ((it_tile / p.NS) & 1) ^ 1, p.watchdog)) { ok = false; break; }
+                    mbar_expect_tx(&sh->full[s], b_bytes);
+                    uint8_t* dst = sB + s * b_bytes;
+                    const int row = (int)(it.row0 + (long long)t * p.NT);
+                    tma_load_2d(dst, &map_d, &sh->full[s], 0, row);
+                    tma_load_2d(dst + p.NT * 128, &map_d, &sh->full[s], 64, row);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_bf16(128, p.NT);
+            int cur_q = -1, a_loads = 0, it_tile = 0;
+            bool ok = true;
+            for (int w = item_begin; ok && w < item_end; w++) {
+                const MsItem it = ms_item(p, w);
+                if (it.nd == 0) continue;
+                if (it.q != cur_q) {
+                    if (a_loads > 0) umma_commit(&sh->a_empty);  // every MMA that read the old A has retired
+                    if (!mbar_wait(&sh->a_full, a_loads & 1, p.watchdog)) break;
+                    cur_q = it.q;
+                    a_loads++;
+                }
+                const int ntiles = (it.ntok + p.NT - 1) / p.NT;
+                for (int t = 0; t < ntiles; t++, it_tile++) {
+                    const int s = it_tile % p.NS, acc = it_tile & 1;
+                    if (!mbar_wait(&sh->tmem_empty[acc], ((it_tile >> 1) & 1) ^ 1, p.watchdog)) { ok = false; break; }
+                    if (!mbar_wait(&sh->full[s], (it_tile / p.NS) & 1, p.watchdog)) { ok = false; break; }
+                    tc_fence_after();
+                    const uint32_t b0 = smem_u32(sB + s * b_bytes);
+                    for (int m = 0; m < p.MT; m++) {
+                        const uint32_t a0 = smem_u32(sA + m * 2 * (128 * 128));
+                        const uint32_t d_tmem = tmem_base + acc * acc_cols + m * p.NT;
+#pragma unroll
+                        for (int k = 0; k < 8; k++) {
+                            const uint64_t da = umma_smem_desc_sw128(a0 + (k >> 2) * (128 * 128) + (k & 3) * 32);
+                            const uint64_t db = umma_smem_desc_sw128(b0 + (k >> 2) * (p.NT * 128) + (k & 3) * 32);
+                            umma_bf16(d_tmem, da, db, idesc, k > 0);
+                        }
+                    }
+                    umma_commit(&sh->empty[s]);
+                    umma_commit(&sh->tmem_full[acc]);
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue: 4 warps, warp = TMEM lane quadrant =====================
+        const int quad = warp & 3;
+        const float init = p.clamp_zero ? 0.0f : -INFINITY;
+        int it_tile = 0, parity = 0;
+        bool ok = true;
+        for (int w = item_begin; ok && w < item_end; w++) {
+            const MsItem it = ms_item(p, w);
+            if (it.nd == 0) continue;
+            const int lq = p.qlens[it.q];
+            float* part = sh->part[parity][quad];
+            if (lane < kMsGD) part[lane] = 0.0f;
+            __syncwarp();
+            float runmax[kMsMaxMT];
+            bool rowok[kMsMaxMT];
+#pragma unroll
+            for (int m = 0; m < kMsMaxMT; m++) {
+                runmax[m] = init;
+                rowok[m] = (m * 128 + quad * 32 + lane) < lq;
+            }
+            // passage boundary state, relative to the item's first token
+            const int base_off = it.ends ? it.ends[0] : 0;
+            int doc = 0;
+            int next_end = it.ends ? it.ends[1] - base_off : p.Ld;
+
+            auto doc_end = [&](int d) -> int {  // exclusive end of passage d (d < nd), item-relative
+                return it.ends ? it.ends[d + 1] - base_off : (d + 1) * p.Ld;
+            };
+            auto flush = [&](int m, int d) {
+                float v = rowok[m] ? (p.clamp_zero ? fmaxf(runmax[m], 0.0f) : runmax[m]) : 0.0f;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                if (lane == 0) part[d] += v;
+                runmax[m] = init;
+            };
+
+            const int ntiles = (it.ntok + p.NT - 1) / p.NT;
+            for (int t = 0; t < ntiles; t++, it_tile++) {
+                const int acc = it_tile & 1;
+                if (!mbar_wait(&sh->tmem_full[acc], (it_tile >> 1) & 1, p.watchdog)) { ok = false; break; }
+                tc_fence_after();
+                const int nchunks = p.NT >> 5;
+                for (int ch = 0; ch < nchunks; ch++) {
+                    const int tk0 = t * p.NT + ch * 32;       // item-relative token of column 0
+                    const int nv = min(32, it.ntok - tk0);    // valid columns in this chunk
+                    if (nv <= 0) break;
+                    uint32_t mword = 0xffffffffu;
+                    if (p.padded) {
+                        const int mb = (lane < nv) ? p.mask[it.row0 + tk0 + lane] : 0;
+                        mword = __ballot_sync(0xffffffffu, mb != 0);
+                    }
+                    const bool fast = (nv == 32) && (next_end >= tk0 + 32) && (mword == 0xffffffffu) &&
+                                      (p.scores_raw == nullptr);
+                    int doc_after = doc, end_after = next_end;
+#pragma unroll
+                    for (int m = 0; m < kMsMaxMT; m++) {
+                        if (m >= p.MT) break;
+                        uint32_t r[32];
+                        tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + acc * acc_cols + m * p.NT + ch * 32, r);
+                        tc_wait_ld();
+                        if (fast) {
+                            float mx = runmax[m];
+#pragma unroll
+                            for (int j = 0; j < 32; j++) mx = fmaxf(mx, __uint_as_float(r[j]));
+                            runmax[m] = mx;
+                        } else {
+                            int d = doc, e = next_end;
+                            const int krow = m * 128 + quad * 32 + lane;
+#pragma unroll
+                            for (int j = 0; j < 32; j++) {
+                                if (j < nv) {
+                                    while (tk0 + j == e && d + 1 < it.nd) {  // passage d ends before this token
+                                        flush(m, d);
+                                        d++;
+                                        e = doc_end(d);
+                                    }
+                                    float v = __uint_as_float(r[j]);
+                                    if (!((mword >> j) & 1u)) v = -9999.0f;  // colbert.py:240-241
+                                    if (p.scores_raw && krow < p.Lq_out)
+                                        p.scores_raw[(size_t)(it.row0 + tk0 + j) * p.Lq_out + krow] = v;
+                                    runmax[m] = fmaxf(runmax[m], v);
+                                }
+                            }
+                            doc_after = d;
+                            end_after = e;
+                        }
+                    }
+                    doc = doc_after;
+                    next_end = end_after;
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sh->tmem_empty[acc]);
+            }
+            // close the passages still open (the last one, plus trailing empty ones)
+#pragma unroll
+            for (int m = 0; m < kMsMaxMT; m++) {
+                if (m >= p.MT) break;
+                for (int d = doc; d < it.nd; d++) flush(m, d);
+            }
+            __syncwarp();
+            if (epi_bar_or(!ok)) ok = false;
+            const int te = threadIdx.x - 128;  // 0..127 among the epilogue threads
+            if (te < it.nd) {
+                const float s = ((sh->part[parity][0][te] + sh->part[parity][1][te]) + sh->part[parity][2][te]) +
+                                sh->part[parity][3][te];
+                p.scores[it.out0 + te] = s;
+            }
+            parity ^= 1;
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+static int ms_configure(MsParams& p, int Lq_pad) {
+    p.Lq_pad = Lq_pad;
+    p.MT = (Lq_pad + 127) / 128;
+    PLAID_CHECK_ARG(p.MT >= 1 && p.MT <= kMsMaxMT, PLAID_ERR_UNSUPPORTED, "maxsim: Lq_pad=%d > 512 query tokens", Lq_pad);
+    p.NT = (p.MT <= 2) ? 128 : 64;   // 2 accumulator buffers x MT x NT <= 512 TMEM columns
+    const int a_bytes = p.MT * 128 * kDim * 2, b_bytes = p.NT * kDim * 2;
+    int ns = (200 * 1024 - a_bytes) / b_bytes;
+    p.NS = ns > kMsMaxStages ? kMsMaxStages : ns;
+    PLAID_CHECK_ARG(p.NS >= 2, PLAID_ERR_UNSUPPORTED, "maxsim: no room for a 2-stage ring");
+    return PLAID_OK;
+}
+
+static int ms_launch(const void* Qb, int q_rows, const void* D, uint64_t d_rows, MsParams& p, cudaStream_t st) {
+    CUtensorMap map_q, map_d;
+    int rc;
+    if ((rc = make_bf16_2d_map(&map_q, Qb, (uint64_t)q_rows, kDim, 128)) != PLAID_OK) return rc;
+    if ((rc = make_bf16_2d_map(&map_d, D, d_rows, kDim, p.NT)) != PLAID_OK) return rc;
+    const int smem = 1024 + p.MT * 128 * kDim * 2 + p.NS * p.NT * kDim * 2 + (int)sizeof(MsShared) + 64;
+    static int configured = 0;
+    if (smem > configured) {
+        PLAID_CUDA_OK(cudaFuncSetAttribute(maxsim_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured = smem;
+    }
+    int grid = sm_count();
+    if (grid > p.num_items) grid = p.num_items;
+    p.items_per_cta = (p.num_items + grid - 1) / grid;
+    grid = (p.num_items + p.items_per_cta - 1) / p.items_per_cta;
+    maxsim_kernel<<<grid, kMsThreads, smem, st>>>(map_q, map_d, p);
+    PLAID_LAUNCH_OK("maxsim_kernel");
+    return PLAID_OK;
+}
+
+}  // namespace plaid
+
+extern "C" int plaid_maxsim_packed(const void* Qb_bf16, const int32_t* qlens, int B, int B_pad, int Lq_pad,
+                                   const void* D_bf16, const int32_t* tok_offsets, const int32_t* counts, int pid_stride,
+                                   int tok_stride, int clamp_zero, float* scores, int* watchdog, void* stream) {
+    using namespace plaid;
+    PLAID_CHECK_ARG(Qb_bf16 && qlens && D_bf16 && tok_offsets && counts && scores, PLAID_ERR_ARG,
+                    "plaid_maxsim_packed: null pointer");
+    PLAID_CHECK_ARG(B >= 0 && B_pad >= B && pid_stride >= 1 && tok_stride >= 1 && Lq_pad >= 32 && (Lq_pad % 32) == 0,
+                    PLAID_ERR_ARG, "plaid_maxsim_packed: bad sizes");
+    PLAID_CHECK_ARG((long long)B * tok_stride < (1ll << 31), PLAID_ERR_UNSUPPORTED,
+                    "plaid_maxsim_packed: B*tok_stride must stay below 2^31 rows per call");
+    if (B == 0) return PLAID_OK;
+    MsParams p{};
+    int rc;
+    if ((rc = ms_configure(p, Lq_pad)) != PLAID_OK) return rc;
+    p.qlens = qlens;
+    p.padded = 0;
+    p.tok_offsets = tok_offsets;
+    p.counts = counts;
+    p.pid_stride = pid_stride;
+    p.tok_stride = tok_stride;
+    p.scores = scores;
+    p.clamp_zero = clamp_zero;
+    p.watchdog = watchdog;
+    p.groups_per_query = (pid_stride + kMsGD - 1) / kMsGD;
+    p.num_items = B * p.groups_per_query;
+    return ms_launch(Qb_bf16, B_pad * Lq_pad, D_bf16, (uint64_t)B * tok_stride, p, (cudaStream_t)stream);
+}
+
+extern "C" int plaid_colbert_score_padded(const void* Qb_bf16, const int32_t* qlens, int nQ, int nQ_pad, int Lq_pad,
+                                          const void* D_padded_bf16, const uint8_t* D_mask, int64_t n, int Ld,
+                                          int docs_per_query, float* scores, float* scores_raw, int Lq_out,
+                                          int* watchdog, void* stream) {
+    using namespace plaid;
+    PLAID_CHECK_ARG(Qb_bf16 && qlens && D_padded_bf16 && D_mask && scores, PLAID_ERR_ARG,
+                    "plaid_colbert_score_padded: null pointer");
+    PLAID_CHECK_ARG(nQ >= 1 && nQ_pad >= nQ && n >= 0 && Ld >= 1 && docs_per_query >= 1 && Lq_pad >= 32 && (Lq_pad % 32) == 0,
+                    PLAID_ERR_ARG, "plaid_colbert_score_padded: bad sizes");
+    PLAID_CHECK_ARG((long long)nQ * docs_per_query >= n, PLAID_ERR_ARG,
+                    "plaid_colbert_score_padded: %d queries x %d passages/query < n=%lld", nQ, docs_per_query, (long long)n);
+    PLAID_CHECK_ARG(n * Ld < (1ll << 31), PLAID_ERR_UNSUPPORTED,
+                    "plaid_colbert_score_padded: n*Ld must stay below 2^31 rows per call");
+    if (n == 0) return PLAID_OK;
+    MsParams p{};
+    int rc;
+    if ((rc = ms_configure(p, Lq_pad)) != PLAID_OK) return rc;
+    p.qlens = qlens;
+    p.padded = 1;
+    p.mask = D_mask;
+    p.n_docs = n;
+    p.Ld = Ld;
+    p.docs_per_query = docs_per_query;
+    p.scores_raw = scores_raw;
+    p.Lq_out = Lq_out;
+    p.scores = scores;
+    p.clamp_zero = 0;
+    p.watchdog = watchdog;
+    p.groups_per_query = (docs_per_query + kMsGD - 1) / kMsGD;
+    const long long nq_used = (n + docs_per_query - 1) / docs_per_query;
+    p.num_items = (int)(nq_used * p.groups_per_query);
+    return ms_launch(Qb_bf16, nQ_pad * Lq_pad, D_padded_bf16, (uint64_t)n * Ld, p, (cudaStream_t)stream);
+}

@@ -1,0 +1,241 @@
+"""Batched PLAID search over one GPU-resident index shard.
+
+This is the hot path of SURVEY.md 8a as one stream of kernel launches per query chunk, with no
+host synchronisation between stages (the reference loops over queries one at a time,
+CB/searcher.py:80-93, and crosses PCIe several times per query on its GPU branch):
+
+  prepare_queries -> centroid_scores (tcgen05) -> candidates -> filter_pids (2 stages)
+  -> doc_token_offsets -> decompress+normalise -> maxsim_packed (tcgen05) -> select_top(k)
+
+Semantics follow the reference's CPU branch (IndexScorer.rank, CB/search/index_storage.py:86-184):
+the first `query_maxlen` (32) query tokens drive candidate generation, all tokens the final MaxSim;
+ties are ordered (score desc, pid desc).
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass
+
+import torch
+
+from . import _lib, ops
+from .index import DeviceIndex
+from .ops import _p, _stream
+
+NQ_MAX = ops.NQ_MAX
+
+
+def search_defaults(k: int):
+    """(ncells, centroid_score_threshold, ndocs) chosen by Searcher.dense_search (CB/searcher.py:96-122)."""
+    if k <= 100:
+        return 2, 0.45, 1024
+    return 4, 0.4, max(k * 4, 4096)
+
+
+@dataclass
+class StageTaps:
+    """Device tensors of every stage of the last chunk (parity tests read these)."""
+    Qb: torch.Tensor
+    qlens: torch.Tensor
+    S: torch.Tensor
+    idx_bits: torch.Tensor
+    cells: torch.Tensor
+    cand_pids: torch.Tensor
+    cand_counts: torch.Tensor
+    stage1_pids: torch.Tensor
+    stage1_scores: torch.Tensor
+    stage1_counts: torch.Tensor
+    stage2_pids: torch.Tensor
+    stage2_scores: torch.Tensor
+    stage2_counts: torch.Tensor
+    tok_offsets: torch.Tensor
+    D: torch.Tensor
+    tok_stride: int
+    scores: torch.Tensor
+
+
+class SearchEngine:
+    def __init__(self, index: DeviceIndex, s_budget_bytes: int = 6 << 30, max_chunk: int = 512):
+        self.index = index
+        self.s_budget_bytes = int(s_budget_bytes)
+        self.max_chunk = int(max_chunk)
+        self._ws_key = None
+        self._ws = None
+        self.last_taps: StageTaps | None = None
+        self.launch_count = 0      # kernels of libplaid_b200 launched so far (bench.py reports the delta)
+        self.events = None         # list of (stage, start, end) CUDA events when stage timing is on
+        dev = index.device
+        self.flags = torch.zeros(2, device=dev, dtype=torch.int32)  # [0] watchdog, [1] candidate overflow
+
+    # ----------------------------------------------------------------------------------- workspace
+    def chunk_size(self, B: int) -> int:
+        per_query = self.index.num_centroids * NQ_MAX * 4
+        bc = max(4, min(self.max_chunk, self.s_budget_bytes // per_query))
+        bc = min(bc, ((B + 3) // 4) * 4)
+        return max(4, (bc // 4) * 4)
+
+    def _workspace(self, Bc: int, Lq_pad: int, ncells: int, ndocs: int, k: int):
+        ix = self.index
+        key = (Bc, Lq_pad, ncells, ndocs, k)
+        if self._ws_key == key:
+            return self._ws
+        dev = ix.device
+        C, N = ix.num_centroids, ix.num_passages
+        tiles = (C + 255) // 256
+        csplit = max(1, min(tiles, -(-2 * 148 // (Bc // 4))))
+        nlists = 2 * csplit
+        nd4 = ndocs // 4
+        cand_stride = max(ndocs, min(N, NQ_MAX * ncells * max(ix.max_ivf_len, 1)))
+        cand_stride = ((cand_stride + 63) // 64) * 64
+        fstride = max(cand_stride, ndocs)
+        tok_stride = ((nd4 * max(ix.max_doclen, 1) + 127) // 128) * 128
+        e = lambda *shape, dtype: torch.empty(*shape, device=dev, dtype=dtype)
+        ws = dict(
+            csplit=csplit, nlists=nlists, cand_stride=cand_stride, fstride=fstride, tok_stride=tok_stride, nd4=nd4,
+            Qb=e(Bc, Lq_pad, 128, dtype=torch.bfloat16), qlens=e(Bc, dtype=torch.int32),
+            S=e(Bc, C, NQ_MAX, dtype=torch.float32), idx_bits=e(Bc, C // 32, dtype=torch.int32),
+            cell_val=e(Bc, NQ_MAX, nlists, ncells, dtype=torch.float32),
+            cell_idx=e(Bc, NQ_MAX, nlists, ncells, dtype=torch.int32),
+            cells=e(Bc, NQ_MAX, ncells, dtype=torch.int32),
+            bitmap=e(Bc, (N + 31) // 32, dtype=torch.int32),
+            cand_pids=e(Bc, cand_stride, dtype=torch.int32), cand_counts=e(Bc, dtype=torch.int32),
+            ws_scores=e(Bc, fstride, dtype=torch.float32), ws_keys=e(Bc, fstride, dtype=torch.int64),
+            s1_pids=e(Bc, ndocs, dtype=torch.int32), s1_scores=e(Bc, ndocs, dtype=torch.float32),
+            s1_counts=e(Bc, dtype=torch.int32),
+            s2_pids=e(Bc, nd4, dtype=torch.int32), s2_scores=e(Bc, nd4, dtype=torch.float32),
+            s2_counts=e(Bc, dtype=torch.int32),
+            tok_offsets=e(Bc, nd4 + 1, dtype=torch.int32),
+            D=e(Bc * tok_stride, 128, dtype=torch.bfloat16),
+            scores=e(Bc, nd4, dtype=torch.float32),
+            out_pids=e(Bc, k, dtype=torch.int32), out_scores=e(Bc, k, dtype=torch.float32),
+            out_counts=e(Bc, dtype=torch.int32),
+        )
+        self._ws_key, self._ws = key, ws
+        return ws
+
+    # ----------------------------------------------------------------------------------- one chunk
+    def _flag_ptrs(self):
+        return ctypes.c_void_p(self.flags.data_ptr()), ctypes.c_void_p(self.flags.data_ptr() + 4)
+
+    # kernels launched by each C-ABI entry point (memsets are not kernels)
+    _LAUNCHES = {"plaid_prepare_queries": 1, "plaid_centroid_scores": 1, "plaid_candidates": 3, "plaid_approx_scores": 1,
+                 "plaid_doc_token_offsets": 1, "plaid_decompress_normalize_bf16": 1, "plaid_maxsim_packed": 1,
+                 "plaid_select_top": 1}
+
+    def _call(self, stage, name, *args):
+        """One C-ABI call; with stage timing on, bracketed by CUDA events on the launching stream."""
+        self.launch_count += self._LAUNCHES[name]
+        if self.events is None:
+            _lib.call(name, *args)
+            return
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _lib.call(name, *args)
+        e1.record()
+        self.events.append((stage, e0, e1))
+
+    def stage_candidates(self, ws, Qc: torch.Tensor, Lq_pad: int, ncells: int, thr: float,
+                         remove_zero_rows: bool, Bc: int):
+        """a1-a4: query prep, centroid scoring (+ pruning mask, top-ncells), candidate pids."""
+        ix = self.index
+        b, Lq, _ = Qc.shape
+        st = _stream()
+        C, N = ix.num_centroids, ix.num_passages
+        wd, ovf = self._flag_ptrs()
+        call = self._call
+        call("prepare", "plaid_prepare_queries", _p(Qc), b, Lq, int(remove_zero_rows), Bc, Lq_pad, _p(ws["Qb"]), _p(ws["qlens"]), st)
+        call("centroid_scores", "plaid_centroid_scores", _p(ix.centroids_bf16), C, _p(ws["Qb"]), _p(ws["qlens"]), Bc, Lq_pad, float(thr),
+             ncells, ws["csplit"], _p(ws["S"]), _p(ws["idx_bits"]), _p(ws["cell_val"]), _p(ws["cell_idx"]), wd, st)
+        call("candidates", "plaid_candidates", _p(ws["cell_val"]), _p(ws["cell_idx"]), _p(ws["qlens"]), b, ncells, ws["nlists"],
+             _p(ix.ivf_pids), _p(ix.ivf_offsets), C, N, _p(ws["cells"]), _p(ws["bitmap"]), _p(ws["cand_pids"]),
+             _p(ws["cand_counts"]), ws["cand_stride"], ovf, st)
+
+    def stage_rank(self, ws, b: int, Lq_pad: int, ndocs: int, k: int, Bc: int):
+        """a5-a10: two-stage filter, decompression, exact MaxSim, top-k -- on ws['cand_pids'/'S'/'idx_bits']."""
+        ix = self.index
+        st = _stream()
+        C = ix.num_centroids
+        wd, _ = self._flag_ptrs()
+        call = self._call
+        # plaid_filter_pids' four launches issued one by one so each can be timed on its own
+        cs, fs, nd4_ = ws["cand_stride"], ws["fstride"], ndocs // 4
+        call("filter_stage1", "plaid_approx_scores", _p(ws["cand_pids"]), _p(ws["cand_counts"]), b, cs, _p(ws["S"]),
+             _p(ws["qlens"]), _p(ws["idx_bits"]), C, _p(ix.codes), _p(ix.offsets), _p(ws["ws_scores"]), st)
+        call("select1", "plaid_select_top", _p(ws["cand_pids"]), _p(ws["ws_scores"]), _p(ws["cand_counts"]), b, cs, ndocs,
+             _p(ws["s1_pids"]), _p(ws["s1_scores"]), _p(ws["s1_counts"]), ndocs, _p(ws["ws_keys"]), st)
+        call("filter_stage2", "plaid_approx_scores", _p(ws["s1_pids"]), _p(ws["s1_counts"]), b, ndocs, _p(ws["S"]),
+             _p(ws["qlens"]), None, C, _p(ix.codes), _p(ix.offsets), _p(ws["ws_scores"]), st)
+        call("select2", "plaid_select_top", _p(ws["s1_pids"]), _p(ws["ws_scores"]), _p(ws["s1_counts"]), b, ndocs, nd4_,
+             _p(ws["s2_pids"]), _p(ws["s2_scores"]), _p(ws["s2_counts"]), nd4_, _p(ws["ws_keys"]), st)
+        nd4 = ws["nd4"]
+        call("doc_offsets", "plaid_doc_token_offsets", _p(ws["s2_pids"]), _p(ws["s2_counts"]), b, nd4, _p(ix.offsets),
+             _p(ws["tok_offsets"]), st)
+        call("decompress", "plaid_decompress_normalize_bf16", _p(ws["s2_pids"]), _p(ws["s2_counts"]), b, nd4, _p(ws["tok_offsets"]),
+             ws["tok_stride"], _p(ix.offsets), _p(ix.weight_table), _p(ix.residuals), _p(ix.codes),
+             _p(ix.centroids_f16), 1, C, ix.nbits, _p(ws["D"]), st)
+        call("maxsim", "plaid_maxsim_packed", _p(ws["Qb"]), _p(ws["qlens"]), b, Bc, Lq_pad, _p(ws["D"]), _p(ws["tok_offsets"]),
+             _p(ws["s2_counts"]), nd4, ws["tok_stride"], 1, _p(ws["scores"]), wd, st)
+        call("topk", "plaid_select_top", _p(ws["s2_pids"]), _p(ws["scores"]), _p(ws["s2_counts"]), b, nd4, k, _p(ws["out_pids"]),
+             _p(ws["out_scores"]), _p(ws["out_counts"]), k, _p(ws["ws_keys"]), st)
+
+    def _run_chunk(self, Qc: torch.Tensor, Lq_pad: int, ncells: int, thr: float, ndocs: int, k: int,
+                   remove_zero_rows: bool, Bc: int):
+        """Qc f32 [b, Lq, 128] on device, b <= Bc.  Enqueues the whole pipeline; returns the workspace."""
+        ws = self._workspace(Bc, Lq_pad, ncells, ndocs, k)
+        self.stage_candidates(ws, Qc, Lq_pad, ncells, thr, remove_zero_rows, Bc)
+        self.stage_rank(ws, Qc.shape[0], Lq_pad, ndocs, k, Bc)
+        return ws
+
+    # ----------------------------------------------------------------------------------- public
+    def search_batch(self, Q: torch.Tensor, k: int = 100, ncells: int | None = None,
+                     centroid_score_threshold: float | None = None, ndocs: int | None = None,
+                     remove_zero_rows: bool = False, global_pids: bool = True, keep_taps: bool = False,
+                     on_chunk=None):
+        """Q f32 [B, Lq, 128] (host or device) -> (pids i32 [B, k], scores f32 [B, k], counts i32 [B]) on
+        the device.  Slots past counts[b] hold pid -1 / score -inf."""
+        d_ncells, d_thr, d_ndocs = search_defaults(k)
+        ncells = d_ncells if ncells is None else int(ncells)
+        thr = d_thr if centroid_score_threshold is None else float(centroid_score_threshold)
+        ndocs = d_ndocs if ndocs is None else int(ndocs)
+        if ndocs // 4 < 1:
+            raise ValueError("ndocs must be >= 4")
+        ix = self.index
+        dev = ix.device
+        B, Lq, dim = Q.shape
+        Lq_pad = ((Lq + 31) // 32) * 32
+        kk = min(k, ndocs // 4)
+        out_p = torch.full((B, k), -1, device=dev, dtype=torch.int32)
+        out_s = torch.full((B, k), float("-inf"), device=dev, dtype=torch.float32)
+        out_c = torch.zeros(B, device=dev, dtype=torch.int32)
+        if B == 0 or ix.num_passages == 0:
+            return out_p, out_s, out_c
+        Bc = self.chunk_size(B)
+        Qd = Q if Q.is_cuda else Q.pin_memory().to(dev, non_blocking=True)
+        Qd = Qd.to(torch.float32).contiguous()
+        for b0 in range(0, B, Bc):
+            b1 = min(B, b0 + Bc)
+            ws = self._run_chunk(Qd[b0:b1], Lq_pad, ncells, thr, ndocs, kk, remove_zero_rows, Bc)
+            n = b1 - b0
+            out_p[b0:b1, :kk] = ws["out_pids"][:n]
+            out_s[b0:b1, :kk] = ws["out_scores"][:n]
+            out_c[b0:b1] = ws["out_counts"][:n]
+            if on_chunk is not None:
+                on_chunk(ws, n)
+            if keep_taps:
+                self.last_taps = StageTaps(
+                    Qb=ws["Qb"], qlens=ws["qlens"], S=ws["S"], idx_bits=ws["idx_bits"], cells=ws["cells"],
+                    cand_pids=ws["cand_pids"], cand_counts=ws["cand_counts"], stage1_pids=ws["s1_pids"],
+                    stage1_scores=ws["s1_scores"], stage1_counts=ws["s1_counts"], stage2_pids=ws["s2_pids"],
+                    stage2_scores=ws["s2_scores"], stage2_counts=ws["s2_counts"], tok_offsets=ws["tok_offsets"],
+                    D=ws["D"], tok_stride=ws["tok_stride"], scores=ws["scores"])
+        if global_pids and ix.pid_base:
+            out_p = torch.where(out_p >= 0, out_p + ix.pid_base, out_p)
+        return out_p, out_s, out_c
+
+    def check_flags(self):
+        """Host-side check (synchronises): raises if a kernel watchdog fired or candidates overflowed."""
+        wd, ovf = self.flags.tolist()
+        if wd:
+            raise _lib.PlaidError("a tcgen05 pipeline wait timed out inside a kernel (watchdog flag set)")
+        if ovf:
+            raise _lib.PlaidError("candidate list overflowed its workspace (cand_stride too small)")

@@ -1,0 +1,191 @@
+"""PLAID index loading: the reference's on-disk format -> a GPU-resident, optionally pid-range-sharded
+``DeviceIndex`` (reference loader CB/search/index_loader.py:13-85,
+CB/indexing/codecs/residual_embeddings.py:27-52, CB/indexing/codecs/residual.py:134-150).
+
+Layout in HBM (one shard):
+  codes        i32 [NE]            nearest-centroid id per token, passage order
+  residuals    u8  [NE + pad, 16*nbits]   packed bucket indices (16-byte aligned rows)
+  offsets      i64 [N + 1]         exclusive prefix sum of doclens (strided_tensor_core.py:30-31)
+  ivf_pids     i32 [sum lens]      per centroid, sorted unique LOCAL pids (CB/indexing/utils.py:8-53)
+  ivf_offsets  i64 [C + 1]
+  centroids_f16  f16 [C, 128]      exactly centroids.pt (gathered by the decompressor)
+  centroids_bf16 bf16 [C, 128]     operand of the centroid-scoring contraction
+  weight_table f32 [256, 8/nbits]  bucket_weights o lookup o reversed_bit_map (residual.py:54-89)
+"""
+from __future__ import annotations
+
+import json
+import math
+import os
+from dataclasses import dataclass
+
+import torch
+
+from . import ops
+
+
+def codec_tables(nbits: int):
+    """reversed_bit_map u8[256] and decompression_lookup_table u8[256, 8/nbits], restated from
+    CB/indexing/codecs/residual.py:54-89 (bit-reverse every nbits-wide field; row r of the lookup
+    table = the base-2^nbits digits of r, most significant first)."""
+    mask, keys = (1 << nbits) - 1, 8 // nbits
+    rbm = []
+    for i in range(256):
+        z = 0
+        for f in range(keys):
+            x = (i >> (8 - nbits * (f + 1))) & mask
+            y = 0
+            for bit in range(nbits):
+                y |= ((x >> bit) & 1) << (nbits - 1 - bit)
+            z = (z << nbits) | y
+        rbm.append(z)
+    lut = [[(r >> (nbits * (keys - 1 - l))) & mask for l in range(keys)] for r in range(256)]
+    return torch.tensor(rbm, dtype=torch.uint8), torch.tensor(lut, dtype=torch.uint8)
+
+
+@dataclass
+class HostIndex:
+    """CPU tensors of (a pid range of) an index, as the reference's IndexLoader holds them."""
+    centroids: torch.Tensor        # f16 [C, 128]
+    bucket_cutoffs: torch.Tensor
+    bucket_weights: torch.Tensor   # f32 [2^nbits]
+    codes: torch.Tensor            # i32 [NE]
+    residuals: torch.Tensor        # u8 [NE, 16*nbits]
+    doclens: torch.Tensor          # i64 [N]
+    ivf: torch.Tensor | None       # i32 (LOCAL pids) or None -> rebuild from codes
+    ivf_lengths: torch.Tensor | None
+    nbits: int
+    dim: int = 128
+    pid_base: int = 0              # global pid of local passage 0
+    num_passages_total: int | None = None
+    config: dict | None = None
+
+
+def build_ivf(codes: torch.Tensor, doclens: torch.Tensor, num_centroids: int):
+    """Per centroid the sorted unique pids owning a token with that code
+    (CB/indexing/collection_indexer.py:393-431 + CB/indexing/utils.py:8-53)."""
+    dev = codes.device
+    n = doclens.numel()
+    tok2pid = torch.repeat_interleave(torch.arange(n, device=dev, dtype=torch.int64), doclens.to(dev))
+    key = torch.unique(codes.to(torch.int64) * n + tok2pid)
+    ivf_codes = torch.div(key, n, rounding_mode="floor")
+    ivf = (key - ivf_codes * n).to(torch.int32)
+    lengths = torch.bincount(ivf_codes, minlength=num_centroids).to(torch.int64)
+    return ivf.contiguous(), lengths.contiguous()
+
+
+def load_reference_index(index_path: str, pid_range: tuple[int, int] | None = None) -> HostIndex:
+    """Read a reference-format index directory; with pid_range=(p0, p1) only that passage slice
+    (only the chunk files that overlap it are opened)."""
+    with open(os.path.join(index_path, "metadata.json")) as f:
+        meta = json.load(f)
+    cfg = meta.get("config", {})
+    nbits, dim = int(cfg["nbits"]), int(cfg.get("dim", 128))
+    num_chunks = int(meta["num_chunks"])
+    centroids = torch.load(os.path.join(index_path, "centroids.pt"), map_location="cpu")
+    cutoffs, weights = torch.load(os.path.join(index_path, "buckets.pt"), map_location="cpu")
+    chunk_doclens = []
+    for i in range(num_chunks):
+        with open(os.path.join(index_path, f"doclens.{i}.json")) as f:
+            chunk_doclens.append(torch.tensor(json.load(f), dtype=torch.int64))
+    n_total = sum(int(d.numel()) for d in chunk_doclens)
+    p0, p1 = (0, n_total) if pid_range is None else (max(0, pid_range[0]), min(n_total, pid_range[1]))
+    codes_parts, res_parts, dl_parts = [], [], []
+    base = 0
+    for i, dl in enumerate(chunk_doclens):
+        c0, c1 = base, base + dl.numel()
+        base = c1
+        lo, hi = max(p0, c0), min(p1, c1)
+        if lo >= hi:
+            continue
+        codes = torch.load(os.path.join(index_path, f"{i}.codes.pt"), map_location="cpu")
+        res = torch.load(os.path.join(index_path, f"{i}.residuals.pt"), map_location="cpu")
+        off = torch.cat((torch.zeros(1, dtype=torch.int64), torch.cumsum(dl, 0)))
+        e0, e1 = int(off[lo - c0]), int(off[hi - c0])
+        codes_parts.append(codes[e0:e1].to(torch.int32))
+        res_parts.append(res[e0:e1])
+        dl_parts.append(dl[lo - c0:hi - c0])
+    doclens = torch.cat(dl_parts) if dl_parts else torch.zeros(0, dtype=torch.int64)
+    codes = torch.cat(codes_parts) if codes_parts else torch.zeros(0, dtype=torch.int32)
+    residuals = torch.cat(res_parts) if res_parts else torch.zeros(0, dim * nbits // 8, dtype=torch.uint8)
+    ivf = ivf_lengths = None
+    if pid_range is None or (p0 == 0 and p1 == n_total):
+        ivf_path = os.path.join(index_path, "ivf.pid.pt")
+        if os.path.exists(ivf_path):
+            ivf, ivf_lengths = torch.load(ivf_path, map_location="cpu")
+            ivf, ivf_lengths = ivf.to(torch.int32), ivf_lengths.to(torch.int64)
+    return HostIndex(centroids=centroids.half(), bucket_cutoffs=cutoffs.float(), bucket_weights=weights.float(),
+                     codes=codes, residuals=residuals.contiguous(), doclens=doclens, ivf=ivf, ivf_lengths=ivf_lengths,
+                     nbits=nbits, dim=dim, pid_base=p0, num_passages_total=n_total, config=cfg)
+
+
+def shard_bounds(num_passages: int, world_size: int, rank: int) -> tuple[int, int]:
+    """Contiguous pid range of `rank`: [rank*N/G, (rank+1)*N/G)."""
+    return (num_passages * rank) // world_size, (num_passages * (rank + 1)) // world_size
+
+
+def slice_host_index(ix, p0: int, p1: int) -> HostIndex:
+    """pid-range slice of an in-memory index (HostIndex or synthetic.SyntheticIndex)."""
+    doclens = ix.doclens.cpu() if ix.doclens.is_cuda else ix.doclens
+    off = torch.cat((torch.zeros(1, dtype=torch.int64), torch.cumsum(doclens, 0)))
+    e0, e1 = int(off[p0]), int(off[p1])
+    return HostIndex(centroids=ix.centroids, bucket_cutoffs=ix.bucket_cutoffs, bucket_weights=ix.bucket_weights,
+                     codes=ix.codes[e0:e1], residuals=ix.residuals[e0:e1], doclens=ix.doclens[p0:p1], ivf=None,
+                     ivf_lengths=None, nbits=ix.nbits, dim=ix.dim, pid_base=p0 + getattr(ix, "pid_base", 0),
+                     num_passages_total=int(doclens.numel()), config=getattr(ix, "config", None))
+
+
+class DeviceIndex:
+    """One shard of a PLAID index resident in HBM, in the layout the kernels read."""
+
+    def __init__(self, host, device=None):
+        dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.device = dev
+        self.nbits, self.dim = int(host.nbits), int(host.dim)
+        if self.dim != ops.DIM:
+            raise ValueError(f"index dim {self.dim} != {ops.DIM}")
+        self.pid_base = int(getattr(host, "pid_base", 0))
+        with torch.cuda.device(dev):
+            self.doclens = host.doclens.to(dev, torch.int64).contiguous()
+            self.num_passages = int(self.doclens.numel())
+            self.offsets = torch.zeros(self.num_passages + 1, device=dev, dtype=torch.int64)
+            self.offsets[1:] = torch.cumsum(self.doclens, 0)
+            self.codes = host.codes.to(dev, torch.int32).contiguous()
+            self.num_embeddings = int(self.codes.numel())
+            pd = self.dim * self.nbits // 8
+            # rows are read with 16-byte loads; keep 512 bytes of slack behind the last row
+            res = torch.zeros(self.num_embeddings * pd + 512, device=dev, dtype=torch.uint8)
+            res[: self.num_embeddings * pd] = host.residuals.to(dev).reshape(-1)
+            self._res_storage = res
+            self.residuals = res[: self.num_embeddings * pd].view(self.num_embeddings, pd)
+            self.centroids_f16 = host.centroids.to(dev, torch.float16).contiguous()
+            self.num_centroids = int(self.centroids_f16.shape[0])
+            if self.num_centroids % 32:
+                raise ValueError("number of centroids must be a multiple of 32")
+            self.centroids_f32 = self.centroids_f16.float()
+            self.centroids_bf16 = ops.to_bf16(self.centroids_f32)
+            self.bucket_weights = host.bucket_weights.to(dev, torch.float32).contiguous()
+            rbm, lut = codec_tables(self.nbits)
+            self.reversed_bit_map, self.lookup_table = rbm.to(dev), lut.to(dev)
+            self.weight_table = ops.build_weight_table(self.bucket_weights, self.reversed_bit_map, self.lookup_table,
+                                                       self.nbits)
+            if getattr(host, "ivf", None) is not None:
+                ivf, ivf_lengths = host.ivf.to(dev, torch.int32), host.ivf_lengths.to(dev, torch.int64)
+            else:
+                ivf, ivf_lengths = build_ivf(self.codes, self.doclens, self.num_centroids)
+            self.ivf_pids = ivf.contiguous()
+            self.ivf_lengths = ivf_lengths.contiguous()
+            self.ivf_offsets = torch.zeros(self.num_centroids + 1, device=dev, dtype=torch.int64)
+            self.ivf_offsets[1:] = torch.cumsum(self.ivf_lengths, 0)
+            self.max_doclen = int(self.doclens.max().item()) if self.num_passages else 0
+            self.max_ivf_len = int(self.ivf_lengths.max().item()) if self.num_centroids else 0
+
+    def bytes(self) -> int:
+        ts = [self.doclens, self.offsets, self.codes, self._res_storage, self.centroids_f16, self.centroids_f32,
+              self.centroids_bf16, self.ivf_pids, self.ivf_offsets]
+        return sum(t.numel() * t.element_size() for t in ts)
+
+
+def default_num_centroids(num_embeddings: int) -> int:
+    """2^floor(log2(16*sqrt(NE)))  (CB/indexing/collection_indexer.py:98)."""
+    return int(2 ** math.floor(math.log2(16 * math.sqrt(num_embeddings))))

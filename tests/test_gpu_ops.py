@@ -1,0 +1,179 @@
+"""GPU parity of the reference-named operators, called through the C ABI, against the CPU oracle and
+the golden vectors recorded from the reference.  Integer / byte / index results: bit-exact."""
+import numpy as np
+import pytest
+import torch
+
+from plaid_test_helpers import golden_oracle_index, nonzero_rows
+from oracle import plaid_oracle as po
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def P():
+    import reranking_multimodal_retrievers_b200 as pkg
+    from reranking_multimodal_retrievers_b200 import ops
+    assert torch.cuda.is_available()
+    return pkg, ops
+
+
+def test_prepare_queries_zero_rows_and_bf16(P):
+    _, ops = P
+    g = torch.Generator().manual_seed(3)
+    Q = torch.randn(5, 40, 128, generator=g)
+    Q[0, 3] = 0
+    Q[0, 10:14] = 0
+    Q[2, :] = 0          # a query that is entirely zero
+    Q[4, 39] = 0
+    Qb, qlens = ops.prepare_queries(Q, remove_zero_rows=True)
+    assert Qb.shape == (8, 64, 128) and qlens.shape == (8,)
+    for b in range(5):
+        kept = nonzero_rows(Q[b])
+        assert int(qlens[b]) == kept.shape[0]
+        assert torch.equal(Qb[b, :kept.shape[0]].cpu(), kept.bfloat16())       # RNE rounding, order preserved
+        assert torch.count_nonzero(Qb[b, kept.shape[0]:]) == 0
+    assert qlens[5:].tolist() == [0, 0, 0] and torch.count_nonzero(Qb[5:]) == 0
+    Qb2, qlens2 = ops.prepare_queries(Q, remove_zero_rows=False)
+    assert qlens2[:5].tolist() == [40] * 5
+    assert torch.equal(Qb2[:5, :40].cpu(), Q.bfloat16())
+
+
+def test_decompress_residuals_bit_exact_vs_golden(P, golden):
+    _, ops = P
+    g = golden
+    ix = golden_oracle_index(g)
+    pids = torch.from_numpy(g["stage2_0"])
+    out = ops.decompress_residuals(pids, ix.doclens, ix.offsets, ix.bucket_weights, ix.reversed_bit_map, ix.lookup,
+                                   ix.residuals, ix.codes, ix.centroids, 128, ix.nbits)
+    assert out.dtype == torch.float32
+    assert np.array_equal(out.cpu().numpy(), g["D_0"])                       # recorded from the reference
+    assert torch.equal(out.cpu(), po.decompress_residuals(ix, pids))
+
+
+@pytest.mark.parametrize("nbits", [1, 2, 4, 8])
+def test_decompress_and_unpack_all_bit_widths(P, nbits):
+    _, ops = P
+    from reranking_multimodal_retrievers_b200.synthetic import make_synthetic_index
+    sx = make_synthetic_index(300, 1, 70, nbits, seed=40 + nbits, num_centroids=256, mode="codes")
+    ix = po.OracleIndex(centroids=sx.centroids, bucket_weights=sx.bucket_weights, codes=sx.codes,
+                        residuals=sx.residuals, doclens=sx.doclens, ivf=sx.ivf, ivf_lengths=sx.ivf_lengths, nbits=nbits)
+    pids = torch.tensor([0, 299, 17, 17, 5, 123, 64], dtype=torch.int32)     # unordered, with a repeat
+    out = ops.decompress_residuals(pids, ix.doclens, ix.offsets, ix.bucket_weights, ix.reversed_bit_map, ix.lookup,
+                                   ix.residuals, ix.codes, ix.centroids, 128, nbits)
+    assert torch.equal(out.cpu(), po.decompress_residuals(ix, pids))
+    codes = ops.unpack_residual_codes(ix.residuals[:500], nbits, ix.reversed_bit_map, ix.lookup)
+    assert torch.equal(codes.cpu(), po.unpack_residual_codes(ix, ix.residuals[:500]))   # integer: bit-exact
+    empty = ops.decompress_residuals(pids[:0], ix.doclens, ix.offsets, ix.bucket_weights, ix.reversed_bit_map,
+                                     ix.lookup, ix.residuals, ix.codes, ix.centroids, 128, nbits)
+    assert empty.shape == (0, 128)
+
+
+def test_filter_pids_bit_exact_with_reference_S(P, golden):
+    """Injected-input protocol: the reference's own centroid-score table goes in, the
+    stage-2 pid list that comes out must equal the reference's, order included."""
+    _, ops = P
+    g = golden
+    ix = golden_oracle_index(g)
+    ndocs = int(g["ndocs"])
+    for b in (0, 1):
+        S, idx, cand = (torch.from_numpy(g[f"{n}_{b}"]) for n in ("S", "idx", "cand"))
+        p2, (p1, s1, s2) = ops.filter_pids(cand, S, ix.codes, ix.doclens, ix.offsets, idx, ndocs, return_stages=True)
+        assert np.array_equal(p2.cpu().numpy(), g[f"stage2_{b}"])
+        o2, (o1, os1, os2) = po.filter_pids(ix, cand, S, idx, ndocs, return_stages=True)
+        assert torch.equal(p1.cpu(), o1) and torch.equal(p2.cpu(), o2)
+        assert torch.equal(s1.cpu(), os1) and torch.equal(s2.cpu(), os2)     # sequential fp32 sums: bit-exact
+        a = ops.approx_scores(cand, S, ix.codes, ix.offsets, idx)
+        assert torch.equal(a.cpu(), po.approx_scores(ix, cand, S, idx))
+        a = ops.approx_scores(cand, S, ix.codes, ix.offsets, None)
+        assert torch.equal(a.cpu(), po.approx_scores(ix, cand, S, None))
+
+
+def test_filter_pids_fewer_candidates_than_ndocs_and_short_queries(P, golden):
+    _, ops = P
+    g = golden
+    ix = golden_oracle_index(g)
+    S, idx = torch.from_numpy(g["S_0"]), torch.from_numpy(g["idx_0"])
+    cand = torch.from_numpy(g["cand_0"])[:50]
+    p2, (p1, s1, s2) = ops.filter_pids(cand, S, ix.codes, ix.doclens, ix.offsets, idx, 128, return_stages=True)
+    o2, (o1, os1, os2) = po.filter_pids(ix, cand, S, idx, 128, return_stages=True)
+    assert p1.numel() == 50 and p2.numel() == 32
+    assert torch.equal(p1.cpu(), o1) and torch.equal(p2.cpu(), o2) and torch.equal(s2.cpu(), os2)
+    # nq < 32 query tokens (PreFLMR masks instruction tokens): the sum runs over nq columns only
+    S7 = S[:, :7].contiguous()
+    idx7 = S7.max(-1).values >= 0.45
+    cand = torch.from_numpy(g["cand_0"])
+    p2 = ops.filter_pids(cand, S7, ix.codes, ix.doclens, ix.offsets, idx7, 64)
+    assert torch.equal(p2.cpu(), po.filter_pids(ix, cand, S7, idx7, 64))
+    # no candidates at all
+    p2 = ops.filter_pids(cand[:0], S, ix.codes, ix.doclens, ix.offsets, idx, 64)
+    assert p2.numel() == 0
+
+
+def test_select_top_order_and_ties(P):
+    _, ops = P
+    g = torch.Generator().manual_seed(9)
+    n = 5000
+    scores = torch.randint(0, 40, (n,), generator=g).float() * 0.25 - 3.0      # heavy ties, negatives
+    scores[17] = float("-inf")
+    pids = torch.randperm(1 << 20, generator=g)[:n].to(torch.int32)
+    for keep in (1, 7, 256, 1024, 4096, 6000):
+        op, os_ = ops.select_top(pids, scores, keep)
+        rp, rs = po.select_top(pids, scores, keep)
+        assert torch.equal(op.cpu(), rp) and torch.equal(os_.cpu(), rs)
+
+
+def test_segmented_maxsim_and_lookup(P, golden):
+    _, ops = P
+    gen = torch.Generator().manual_seed(5)
+    lengths = torch.tensor([3, 1, 170, 0, 9, 64], dtype=torch.long)
+    for nq in (32, 40, 64, 128):
+        scores = torch.randn(int(lengths.sum()), nq, generator=gen)
+        out = ops.segmented_maxsim(scores, lengths)
+        assert torch.equal(out.cpu(), po.segmented_maxsim(scores, lengths))  # same left-to-right fp32 sum
+        assert float(out[3]) == 0.0
+    ix = golden_oracle_index(golden)
+    pids = torch.tensor([5, 0, 17, 3, 5], dtype=torch.long)
+    lengths, offsets = ix.doclens[pids], ix.offsets[pids]
+    for table in (ix.residuals, ix.codes):
+        out = ops.segmented_lookup(table, pids, lengths, offsets)
+        ref = torch.cat([table[o:o + l] for o, l in zip(offsets.tolist(), lengths.tolist())])
+        assert torch.equal(out.cpu(), ref)
+
+
+def test_colbert_score_reduce(P):
+    pkg, _ = P
+    g = torch.Generator().manual_seed(12)
+    sp = torch.randn(7, 19, 45, generator=g)
+    mask = torch.rand(7, 19, generator=g) > 0.3
+    mask[2] = False                                  # fully padded passage -> -9999 * Lq
+    out = pkg.colbert_score_reduce(sp, mask)
+    ref, _ = po.colbert_score_reduce(sp, mask)
+    torch.testing.assert_close(out.cpu(), ref, rtol=1e-6, atol=1e-4)
+    s, raw = pkg.flmr_colbert_score_reduce(sp, mask)
+    assert torch.equal(raw.cpu(), po.colbert_score_reduce(sp, mask)[1])
+
+
+def test_merge_topk_matches_cpu_merge(P):
+    from reranking_multimodal_retrievers_b200 import sharded
+    g = torch.Generator().manual_seed(21)
+    G, B, k = 8, 33, 100
+    scores = torch.randint(0, 500, (G, B, k), generator=g).float() / 7.0
+    scores = scores.sort(dim=-1, descending=True).values
+    pids = torch.randperm(G * B * k, generator=g).reshape(G, B, k).to(torch.int32)
+    counts = torch.randint(0, k + 1, (G, B), generator=g).to(torch.int32)
+    counts[0, 0] = k
+    counts[:, 1] = 0                                    # a query for which no shard found anything
+    op, os_, oc = sharded.merge_topk(scores.cuda(), pids.cuda(), counts.cuda(), k)
+    for b in range(B):
+        allp = torch.cat([pids[gk, b, :counts[gk, b]] for gk in range(G)])
+        alls = torch.cat([scores[gk, b, :counts[gk, b]] for gk in range(G)])
+        rp, rs = po.select_top(allp, alls, k) if allp.numel() else (allp, alls)
+        m = int(oc[b])
+        assert m == rp.numel()
+        assert torch.equal(op[b, :m].cpu(), rp) and torch.equal(os_[b, :m].cpu(), rs)
+        assert torch.all(op[b, m:] == -1)
+    # message packing used for the single all-gather
+    msg = sharded.pack_lists(pids[0].cuda(), scores[0].cuda(), counts[0].cuda())
+    p, s, c = sharded.unpack_lists(msg.unsqueeze(0), k)
+    assert torch.equal(p[0].cpu(), pids[0]) and torch.equal(s[0].cpu(), scores[0]) and torch.equal(c[0].cpu(), counts[0])

@@ -1,0 +1,238 @@
+"""GPU parity of the tensor-core kernels and of the whole search pipeline.
+
+Protocol: float stages are compared within stated tolerances; every integer stage
+(pruning mask, cells, candidate pids, stage-1 / stage-2 pids, top-k pids) must be BIT-EXACT when the
+oracle is fed the same centroid-score table our kernel produced (injected inputs), because a bf16
+contraction cannot reproduce an fp32 table bit for bit.
+"""
+import numpy as np
+import pytest
+import torch
+
+from plaid_test_helpers import golden_host_index, golden_oracle_index, nonzero_rows
+from oracle import plaid_oracle as po
+
+pytestmark = pytest.mark.gpu
+
+S_ABS_TOL = 4e-3        # bf16-rounded operands vs the fp32 reference table (measured 9.9e-4)
+SCORE_REL_TOL = 1e-3    # north_star: 1e-3 relative on fp32-accumulated MaxSim
+
+
+@pytest.fixture(scope="module")
+def pkg():
+    import reranking_multimodal_retrievers_b200 as p
+    assert torch.cuda.is_available()
+    return p
+
+
+def _engine(g):
+    from reranking_multimodal_retrievers_b200.engine import SearchEngine
+    from reranking_multimodal_retrievers_b200.index import DeviceIndex
+    return SearchEngine(DeviceIndex(golden_host_index(g)))
+
+
+def test_centroid_scores_tcgen05(pkg, golden):
+    from reranking_multimodal_retrievers_b200 import ops
+    g = golden
+    eng = _engine(g)
+    ix = golden_oracle_index(g)
+    Q = torch.from_numpy(g["Q"])
+    B = Q.shape[0]
+    ncells, thr = int(g["ncells"]), float(g["threshold"])
+    eng.search_batch(Q, k=int(g["k"]), ncells=ncells, centroid_score_threshold=thr, ndocs=int(g["ndocs"]),
+                     remove_zero_rows=True, keep_taps=True)
+    eng.check_flags()
+    t = eng.last_taps
+    cent_b = ix.centroids.bfloat16().float()
+    for b in range(B):
+        q = nonzero_rows(Q[b])
+        nq = min(32, q.shape[0])
+        assert int(t.qlens[b]) == q.shape[0]
+        S = t.S[b, :, :nq].cpu()
+        # (1) same bf16-rounded operands, fp32 accumulate: only the summation order differs
+        S_ref_b = cent_b @ q[:nq].bfloat16().float().T
+        torch.testing.assert_close(S, S_ref_b, rtol=0, atol=2e-6)
+        # (2) against the fp32 reference table
+        if f"S_{b}" in g:
+            assert np.abs(S.numpy() - g[f"S_{b}"]).max() <= S_ABS_TOL
+        # padded token lanes are exact zeros
+        assert torch.count_nonzero(t.S[b, :, nq:]) == 0
+        # pruning mask and cells are functions of OUR table: bit-exact
+        idx = ops.unpack_idx_bits(t.idx_bits[b], S.shape[0]).cpu()
+        assert torch.equal(idx, po.centroid_mask(S, thr))
+        cells = t.cells[b, :nq].cpu()
+        assert torch.equal(cells.long(), po.cells_per_token(S, ncells))
+        assert torch.all(t.cells[b, nq:] == -1)
+
+
+def test_pipeline_stagewise_bit_exact_with_injected_table(pkg, golden):
+    from reranking_multimodal_retrievers_b200 import ops
+    g = golden
+    eng = _engine(g)
+    ix = golden_oracle_index(g)
+    Q = torch.from_numpy(g["Q"])
+    B = Q.shape[0]
+    ncells, thr, ndocs, k = int(g["ncells"]), float(g["threshold"]), int(g["ndocs"]), int(g["k"])
+    pids, scores, counts = eng.search_batch(Q, k=k, ncells=ncells, centroid_score_threshold=thr, ndocs=ndocs,
+                                            remove_zero_rows=True, keep_taps=True)
+    eng.check_flags()
+    t = eng.last_taps
+    for b in range(B):
+        q = nonzero_rows(Q[b])
+        nq = min(32, q.shape[0])
+        S = t.S[b, :, :nq].cpu().contiguous()
+        r = po.rank(ix, q, ncells, thr, ndocs, S_override=S, taps=True)
+        nc = int(t.cand_counts[b])
+        assert torch.equal(t.cand_pids[b, :nc].cpu(), r["candidates"])                     # sorted unique pids
+        n1, n2 = int(t.stage1_counts[b]), int(t.stage2_counts[b])
+        assert torch.equal(t.stage1_pids[b, :n1].cpu(), r["stage1_pids"])
+        assert torch.equal(t.stage1_scores[b, :n1].cpu(), r["stage1_scores"])
+        assert torch.equal(t.stage2_pids[b, :n2].cpu(), r["stage2_pids"])
+        assert torch.equal(t.stage2_scores[b, :n2].cpu(), r["stage2_scores"])
+        # decompressed + normalised passages (bf16): within one bf16 ulp of the oracle's fp32 rows
+        lens = ix.doclens[r["stage2_pids"].long()]
+        to = t.tok_offsets[b, :n2 + 1].cpu()
+        assert torch.equal(to[1:] - to[:-1], lens.to(torch.int32))
+        T = int(to[-1])
+        D = t.D[b * t.tok_stride: b * t.tok_stride + T].float().cpu()
+        assert (D - r["D"]).abs().max() <= 2 ** -8
+        assert (D != r["D"].bfloat16().float()).float().mean() < 2e-3
+        # exact MaxSim: (a) same bf16 operands -> only summation order differs; (b) fp32 oracle within 1e-3
+        sc = t.scores[b, :n2].cpu()
+        ref_same = po.colbert_score_packed(q.bfloat16().float(), D, lens)
+        torch.testing.assert_close(sc, ref_same, rtol=2e-5, atol=2e-5)
+        assert ((sc - r["scores_unsorted"]).abs() <= SCORE_REL_TOL * r["scores_unsorted"].abs() + 1e-6).all()
+        # final order: (score desc, pid desc) of our own scores, exactly
+        m = int(counts[b])
+        assert m == min(k, n2)
+        rp, rs = po.select_top(r["stage2_pids"], sc, k)
+        assert torch.equal(pids[b, :m].cpu(), rp) and torch.equal(scores[b, :m].cpu(), rs)
+        # against the reference's own ranking (recorded): the planted passage leads, scores agree
+        assert int(pids[b, 0]) == int(g[f"rank_pids_{b}"][0])
+        gs = torch.from_numpy(g[f"rank_scores_{b}"])
+        assert ((scores[b, :m].cpu() - gs[:m]).abs() <= SCORE_REL_TOL * gs[:m].abs() + 1e-6).all()
+
+
+def test_colbert_score_padded_vs_reference(pkg, golden):
+    g = golden
+    Q, D, mask = (torch.from_numpy(g[n]) for n in ("cs_Q", "cs_D", "cs_mask"))
+    out = pkg.colbert_score(Q, D, mask)
+    ref = torch.from_numpy(g["cs_scores"])
+    assert out.dtype == torch.float32 and out.shape == ref.shape
+    assert ((out.cpu() - ref).abs() <= SCORE_REL_TOL * ref.abs() + 1e-5).all()
+    # same bf16 operands: tight
+    ref_b = po.colbert_score(Q.bfloat16().float(), D.bfloat16().float(), mask)
+    torch.testing.assert_close(out.cpu(), ref_b, rtol=2e-5, atol=2e-4)
+    # FLMR form: also returns the masked similarity matrix [n, Ld, Lq]
+    s2, raw = pkg.flmr_colbert_score(Q, D, mask)
+    assert torch.equal(s2, out)
+    full = (D.bfloat16().float() @ Q.bfloat16().float().permute(0, 2, 1))
+    _, raw_ref = po.colbert_score_reduce(full, mask)
+    torch.testing.assert_close(raw.cpu(), raw_ref, rtol=0, atol=2e-5)
+    # one query block per passage (Q.size(0) == n, colbert.py:276-281)
+    Qn = Q.repeat(D.shape[0], 1, 1).contiguous()
+    torch.testing.assert_close(pkg.colbert_score(Qn, D, mask), out, rtol=0, atol=0)
+
+
+@pytest.mark.parametrize("Lq,Ld,n,dpq", [(32, 7, 5, 5), (64, 180, 300, 100), (160, 33, 40, 8), (320, 97, 50, 25),
+                                         (500, 16, 9, 3)])
+def test_colbert_score_padded_shapes(pkg, Lq, Ld, n, dpq):
+    """Ragged masks, several m-tiles (Lq up to 512), passages spanning tile boundaries, short groups."""
+    g = torch.Generator().manual_seed(Lq * 1000 + Ld)
+    nQ = (n + dpq - 1) // dpq
+    Q = torch.nn.functional.normalize(torch.randn(nQ, Lq, 128, generator=g), dim=-1)
+    D = torch.nn.functional.normalize(torch.randn(n, Ld, 128, generator=g), dim=-1)
+    lens = torch.randint(1, Ld + 1, (n,), generator=g)
+    lens[0] = Ld
+    mask = torch.arange(Ld).unsqueeze(0) < lens.unsqueeze(1)
+    if n > 3:
+        mask[3] = False                                   # fully padded passage
+    out = pkg.colbert_score(Q, D, mask, docs_per_query=dpq).cpu()
+    Qd = Q.bfloat16().float().repeat_interleave(dpq, dim=0)[:n]
+    ref = po.colbert_score(Qd, D.bfloat16().float(), mask)
+    torch.testing.assert_close(out, ref, rtol=2e-5, atol=2e-3)
+
+
+@pytest.mark.parametrize("Lq,lens", [(64, [3, 1, 170, 0, 9, 64, 128, 129, 0]), (320, [40, 0, 0, 300, 17]),
+                                     (32, [0]), (45, [513, 2])])
+def test_colbert_score_packed_edge_cases(pkg, Lq, lens):
+    """Empty passages, passages longer than a tile, passage ends on tile boundaries."""
+    g = torch.Generator().manual_seed(Lq + len(lens))
+    lengths = torch.tensor(lens, dtype=torch.long)
+    T = int(lengths.sum())
+    Q = torch.nn.functional.normalize(torch.randn(1, Lq, 128, generator=g), dim=-1)
+    D = torch.nn.functional.normalize(torch.randn(max(T, 1), 128, generator=g), dim=-1)[:T]
+    out = pkg.colbert_score_packed(Q, D, lengths).cpu()
+    ref = po.colbert_score_packed(Q.bfloat16().float(), D.bfloat16().float(), lengths)
+    torch.testing.assert_close(out, ref, rtol=2e-5, atol=2e-5)
+    for i, l in enumerate(lens):
+        if l == 0:
+            assert float(out[i]) == 0.0                  # zero-initialised max buffer (segmented_maxsim.cpp:58-59)
+
+
+def test_searcher_dropin_on_reference_format_index(pkg, golden, tmp_path):
+    """create_searcher / search_custom_collection read a reference-format directory and return the
+    same Ranking structure FLMR_base_executor consumes."""
+    from reranking_multimodal_retrievers_b200.synthetic import SyntheticIndex, write_reference_format
+    g = golden
+    nbits = int(g["nbits"])
+    sx = SyntheticIndex(
+        centroids=torch.from_numpy(g["centroids"]), bucket_cutoffs=torch.from_numpy(g["bucket_cutoffs"]),
+        bucket_weights=torch.from_numpy(g["bucket_weights"]), avg_residual=torch.zeros(1),
+        codes=torch.from_numpy(g["codes"]), residuals=torch.from_numpy(g["residuals"]),
+        doclens=torch.from_numpy(g["doclens"]), ivf=torch.from_numpy(g["ivf"]),
+        ivf_lengths=torch.from_numpy(g["ivf_lengths"]), nbits=nbits)
+    path = tmp_path / "exp" / "indexes" / f"golden.nbits={nbits}"
+    write_reference_format(sx, str(path), chunk_passages=300)       # several chunk files
+    searcher = pkg.create_searcher(str(tmp_path), "exp", "golden", use_gpu=True, nbits=nbits)
+    searcher.configure(ndocs=int(g["ndocs"]))
+    Q = torch.from_numpy(g["Q"])
+    k = int(g["k"])
+    ranking = pkg.search_custom_collection(searcher, {i: f"q{i}" for i in range(Q.shape[0])}, Q,
+                                           num_document_to_retrieve=k, remove_zero_tensors=True)
+    rk = ranking.todict()
+    for b in range(Q.shape[0]):
+        rows = rk[b]
+        assert len(rows) == k and [r[1] for r in rows] == list(range(1, k + 1))
+        assert rows[0][0] == int(g[f"rank_pids_{b}"][0])
+        gs = g[f"rank_scores_{b}"]
+        assert np.allclose([r[2] for r in rows], gs, rtol=SCORE_REL_TOL, atol=1e-6)
+        # single-query API gives the same answer as the batch path
+        p1, ranks, s1 = searcher.dense_search(Q[b:b + 1], k=k, remove_zero_tensors=True)
+        assert p1 == [r[0] for r in rows] and np.allclose(s1, [r[2] for r in rows], rtol=0, atol=0)
+    # IndexScorer.rank with a filter_fn (reference signature): drop the best passage, it must vanish
+    best = rk[0][0][0]
+    q0 = nonzero_rows(Q[0]).unsqueeze(0)
+    p, s = searcher.ranker.rank(searcher.config, q0, filter_fn=lambda pids: pids[pids != best])
+    assert best not in p and len(p) > 0 and s == sorted(s, reverse=True)
+
+
+def test_sharded_search_equals_reference_per_shard_merge(pkg, golden):
+    """Oracle (A) of SURVEY 8e: run each pid-range shard separately, merge by (score, pid).  All G
+    shards are emulated on one GPU (one engine per shard), the merge goes through plaid_merge_topk."""
+    from reranking_multimodal_retrievers_b200 import sharded
+    from reranking_multimodal_retrievers_b200.engine import SearchEngine
+    from reranking_multimodal_retrievers_b200.index import DeviceIndex, shard_bounds, slice_host_index
+    g = golden
+    host = golden_host_index(g)
+    Q = torch.from_numpy(g["Q"])
+    G, k = 4, int(g["k"])
+    N = host.doclens.numel()
+    kw = dict(k=k, ncells=int(g["ncells"]), centroid_score_threshold=float(g["threshold"]), ndocs=int(g["ndocs"]),
+              remove_zero_rows=True)
+    lists = []
+    for r in range(G):
+        p0, p1 = shard_bounds(N, G, r)
+        eng = SearchEngine(DeviceIndex(slice_host_index(host, p0, p1)))
+        p, s, c = eng.search_batch(Q, **kw)
+        eng.check_flags()
+        assert int(p[p >= 0].min()) >= p0 and int(p.max()) < p1            # global pids of this shard only
+        lists.append((p, s, c))
+    gp = torch.stack([l[0] for l in lists]); gs = torch.stack([l[1] for l in lists]); gc = torch.stack([l[2] for l in lists])
+    mp, ms, mc = sharded.merge_topk(gs, gp, gc, k)
+    for b in range(Q.shape[0]):
+        allp = torch.cat([gp[r, b, :gc[r, b]] for r in range(G)]).cpu()
+        alls = torch.cat([gs[r, b, :gc[r, b]] for r in range(G)]).cpu()
+        rp, rs = po.select_top(allp, alls, k)
+        assert torch.equal(mp[b, :int(mc[b])].cpu(), rp) and torch.equal(ms[b, :int(mc[b])].cpu(), rs)
+        assert int(mp[b, 0]) == int(g[f"rank_pids_{b}"][0])                # the planted passage still leads

@@ -1,0 +1,156 @@
+"""Host-side logic that needs no GPU: codec tables, index files, sharding, settings, containers,
+and the world_size-2 exchange (gloo) of the per-shard top-k lists."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from plaid_test_helpers import ROOT
+from oracle import plaid_oracle as po
+from reranking_multimodal_retrievers_b200 import index as pindex
+from reranking_multimodal_retrievers_b200 import infra, ops, sharded, synthetic
+from reranking_multimodal_retrievers_b200.engine import search_defaults
+
+
+@pytest.mark.parametrize("nbits", [1, 2, 4, 8])
+def test_codec_tables_match_oracle(nbits):
+    rbm, lut = pindex.codec_tables(nbits)
+    orbm, olut = po.codec_tables(nbits)
+    assert torch.equal(rbm, orbm) and torch.equal(lut, olut)
+
+
+def test_codec_tables_match_reference_golden(golden):
+    rbm, lut = pindex.codec_tables(int(golden["nbits"]))
+    assert np.array_equal(rbm.numpy(), golden["reversed_bit_map"])
+    assert np.array_equal(lut.numpy(), golden["lookup_table"])
+
+
+def test_search_defaults_follow_reference():
+    # CB/searcher.py:96-122
+    assert search_defaults(10) == (2, 0.45, 1024)
+    assert search_defaults(100) == (2, 0.45, 1024)
+    assert search_defaults(101) == (4, 0.4, 4096)
+    assert search_defaults(2000) == (4, 0.4, 8000)
+    assert search_defaults(100) == po.search_defaults(100) and search_defaults(500) == po.search_defaults(500)
+
+
+def test_idx_bit_packing_roundtrip():
+    g = torch.Generator().manual_seed(1)
+    idx = torch.rand(3, 1024, generator=g) > 0.5
+    idx[0, 31] = True   # sign bit of word 0
+    words = ops.pack_idx_bits(idx)
+    assert words.dtype == torch.int32 and words.shape == (3, 32)
+    assert torch.equal(ops.unpack_idx_bits(words, 1024), idx)
+    assert (int(words[0, 0]) >> 31) & 1 == 1
+
+
+def test_reference_format_roundtrip_and_pid_range(tmp_path):
+    sx = synthetic.make_synthetic_index(700, 4, 40, 2, seed=5, num_centroids=256, mode="codes")
+    path = str(tmp_path / "e" / "indexes" / "t.nbits=2")
+    synthetic.write_reference_format(sx, path, chunk_passages=256)
+    assert sorted(f for f in os.listdir(path) if f.endswith(".codes.pt")) == ["0.codes.pt", "1.codes.pt", "2.codes.pt"]
+    full = pindex.load_reference_index(path)
+    assert torch.equal(full.codes, sx.codes) and torch.equal(full.residuals, sx.residuals)
+    assert torch.equal(full.doclens, sx.doclens) and torch.equal(full.ivf, sx.ivf)
+    assert full.nbits == 2 and full.pid_base == 0 and full.num_passages_total == 700
+    off = torch.cat((torch.zeros(1, dtype=torch.long), torch.cumsum(sx.doclens, 0)))
+    for r in range(3):
+        p0, p1 = pindex.shard_bounds(700, 3, r)
+        part = pindex.load_reference_index(path, (p0, p1))
+        assert part.pid_base == p0 and part.doclens.numel() == p1 - p0
+        assert torch.equal(part.codes, sx.codes[off[p0]:off[p1]])
+        assert torch.equal(part.residuals, sx.residuals[off[p0]:off[p1]])
+        mem = pindex.slice_host_index(sx, p0, p1)
+        assert torch.equal(mem.codes, part.codes) and mem.pid_base == p0
+        # a shard's IVF is rebuilt from its own codes: sorted unique local pids per centroid
+        ivf, lens = pindex.build_ivf(part.codes, part.doclens, 256)
+        tok2pid = torch.repeat_interleave(torch.arange(p1 - p0), part.doclens)
+        c = int(part.codes[0])
+        o = int(lens[:c].sum())
+        assert ivf[o:o + int(lens[c])].tolist() == sorted(set(tok2pid[part.codes == c].tolist()))
+    bounds = [pindex.shard_bounds(700, 8, r) for r in range(8)]
+    assert bounds[0][0] == 0 and bounds[-1][1] == 700 and all(a[1] == b[0] for a, b in zip(bounds, bounds[1:]))
+
+
+def test_build_ivf_matches_synthetic_and_reference_layout(golden):
+    ivf, lens = pindex.build_ivf(torch.from_numpy(golden["codes"]), torch.from_numpy(golden["doclens"]),
+                                 golden["centroids"].shape[0])
+    assert np.array_equal(ivf.numpy(), golden["ivf"]) and np.array_equal(lens.numpy(), golden["ivf_lengths"])
+
+
+def test_settings_and_containers(tmp_path):
+    cfg = infra.ColBERTConfig(total_visible_gpus=1)
+    assert cfg.ncells is None and cfg.ndocs is None and cfg.query_maxlen == 32 and cfg.dim == 128
+    with infra.Run().context(infra.RunConfig(nranks=1, rank=1, root=str(tmp_path), experiment="exp")):
+        merged = infra.ColBERTConfig.from_existing(cfg, infra.Run().config)
+        assert merged.index_root_ == os.path.join(str(tmp_path), "exp", "indexes/")
+    assert infra.Run().config.experiment == "default"
+    merged.configure(ndocs=64)
+    assert merged.ndocs == 64 and "ndocs" in merged._assigned
+    q = infra.Queries(data={7: "a", 9: {"question": "b"}})
+    assert list(q.keys()) == [7, 9] and list(q.values()) == ["a", "b"] and len(q) == 2
+    rk = infra.Ranking(data={7: [(3, 1, 2.5), (1, 2, 2.0)], 9: [(4, 1, 1.0)]}, provenance={"k": 2})
+    assert rk.tolist() == [(7, 3, 1, 2.5), (7, 1, 2, 2.0), (9, 4, 1, 1.0)] and rk.todict()[9] == [(4, 1, 1.0)]
+    out = rk.save(str(tmp_path / "r.tsv"))
+    assert open(out).read().splitlines()[0] == "7\t3\t1\t2.5"
+
+
+def test_product_path_fails_loudly_without_cuda():
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.prepare_queries(torch.zeros(1, 32, 128), False)
+    from reranking_multimodal_retrievers_b200.search import IndexScorer
+    with pytest.raises(RuntimeError, match="no CPU branch"):
+        IndexScorer("/nonexistent", use_gpu=True)
+
+
+def test_product_never_imports_the_oracle():
+    pkg_dir = os.path.join(ROOT, "reranking_multimodal_retrievers_b200")
+    for dirpath, _, files in os.walk(pkg_dir):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "plaid_oracle" not in text and "import oracle" not in text and "from oracle" not in text, f
+
+
+def _gloo_worker(rank, world, port, tmpdir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g = torch.Generator().manual_seed(100 + rank)
+        B, k = 5, 6
+        scores = torch.rand(B, k, generator=g).sort(dim=-1, descending=True).values
+        p0, p1 = pindex.shard_bounds(1000, world, rank)
+        pids = (torch.randperm(p1 - p0, generator=g)[:B * k].reshape(B, k) + p0).to(torch.int32)
+        counts = torch.tensor([k, k - 2, 0, 1, k], dtype=torch.int32)
+        msg = sharded.pack_lists(pids, scores, counts)
+        gathered = sharded.all_gather_lists(msg, world)
+        gp, gs, gc = sharded.unpack_lists(gathered, k)
+        assert torch.equal(gp[rank], pids) and torch.equal(gs[rank], scores) and torch.equal(gc[rank], counts)
+        # every rank holds identical gathered lists -> identical merges (checker: the oracle's select_top)
+        merged = []
+        for b in range(B):
+            allp = torch.cat([gp[r, b, :gc[r, b]] for r in range(world)])
+            alls = torch.cat([gs[r, b, :gc[r, b]] for r in range(world)])
+            merged.append(po.select_top(allp, alls, k) if allp.numel() else (allp, alls))
+        torch.save((gp, gs, gc, merged), os.path.join(tmpdir, f"r{rank}.pt"))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_exchange_gloo(tmp_path):
+    port = 29500 + (os.getpid() % 2000)
+    mp.spawn(_gloo_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    a = torch.load(tmp_path / "r0.pt")
+    b = torch.load(tmp_path / "r1.pt")
+    for x, y in zip(a[:3], b[:3]):
+        assert torch.equal(x, y)
+    for (pa, sa), (pb, sb) in zip(a[3], b[3]):
+        assert torch.equal(pa, pb) and torch.equal(sa, sb)
+    assert a[3][2][0].numel() == 0                       # the query nobody found anything for
+    assert a[3][0][0].numel() == 6 and int(a[3][0][0].max()) >= 500   # pids from both shards' ranges compete

@@ -1,0 +1,68 @@
+"""The C restatement (oracle/plaid_oracle.c) against the reference's own compiled operators
+(oracle/_ref, built from /root/reference by oracle/build_ref.py).  Skipped where oracle/_ref is absent."""
+import os
+import sys
+
+import pytest
+import torch
+
+from plaid_test_helpers import ROOT, golden_oracle_index
+from oracle import build_ref
+from oracle import plaid_oracle as po
+
+have_ref = all(os.path.exists(build_ref.ref_so_path(n)) for n in build_ref.SOURCES)
+pytestmark = pytest.mark.skipif(not have_ref, reason="oracle/_ref not built (needs /root/reference)")
+
+
+@pytest.fixture(scope="module")
+def ref():
+    return {n: build_ref.load(n) for n in build_ref.SOURCES}
+
+
+def test_filter_pids_bit_exact(golden, ref):
+    g = golden
+    ix = golden_oracle_index(g)
+    torch.set_num_threads(4)
+    for b in (0, 1):
+        S = torch.from_numpy(g[f"S_{b}"]).contiguous()
+        idx = torch.from_numpy(g[f"idx_{b}"])
+        cand = torch.from_numpy(g[f"cand_{b}"])
+        ndocs = int(g["ndocs"])
+        out = ref["filter_pids_cpp"].filter_pids_cpp(cand, S, ix.codes, ix.doclens, ix.offsets, idx, ndocs)
+        mine = po.filter_pids(ix, cand, S, idx, ndocs)
+        assert torch.equal(out, mine)
+
+
+def test_decompress_bit_exact(golden, ref):
+    g = golden
+    ix = golden_oracle_index(g)
+    pids = torch.from_numpy(g["stage2_0"])
+    out = ref["decompress_residuals_cpp"].decompress_residuals_cpp(
+        pids, ix.doclens, ix.offsets, ix.bucket_weights, ix.reversed_bit_map, ix.lookup, ix.residuals, ix.codes,
+        ix.centroids, ix.dim, ix.nbits)
+    assert torch.equal(out, po.decompress_residuals(ix, pids))
+
+
+def test_segmented_maxsim(golden, ref):
+    gen = torch.Generator().manual_seed(5)
+    lengths = torch.tensor([3, 1, 17, 0, 9], dtype=torch.long)
+    scores = torch.randn(int(lengths.sum()), 40, generator=gen)
+    out = ref["segmented_maxsim_cpp"].segmented_maxsim_cpp(scores, lengths)
+    mine = po.segmented_maxsim(scores, lengths)
+    torch.testing.assert_close(out, mine, rtol=1e-6, atol=1e-6)
+    assert mine[3] == 0  # empty passage: zero-initialised buffer
+
+
+def test_segmented_lookup(golden, ref):
+    g = golden
+    ix = golden_oracle_index(g)
+    pids = torch.tensor([5, 0, 17, 3], dtype=torch.long)
+    lengths, offsets = ix.doclens[pids], ix.offsets[pids]
+    out = ref["segmented_lookup_cpp"].segmented_lookup_cpp(ix.residuals, pids, lengths, offsets)
+    total = int(lengths.sum())
+    mine = torch.empty(total, ix.residuals.shape[1], dtype=torch.uint8)
+    import ctypes
+    po._lib().plaid_oracle_segmented_lookup(po._p(ix.residuals), ctypes.c_int64(ix.residuals.shape[1]), po._p(pids),
+                                            ctypes.c_int(4), po._p(lengths.contiguous()), po._p(offsets.contiguous()),
+                                            po._p(mine))
+    assert torch.equal(out, mine)
