@@ -249,10 +249,10 @@ def main():
         cc = ws["cand_counts"][:n].long()
         m = torch.arange(ws["cand_stride"], device=dev).unsqueeze(0) < cc.unsqueeze(1)
         stats["ncand"] += int(cc.sum())
-        stats["T1"] += int((dl[ws["cand_pids"][:n].clamp(min=0).long()] * m).sum())
+        stats["T1"] += int(dl[torch.where(m, ws["cand_pids"][:n], 0).long()].mul(m).sum())
         c1 = ws["s1_counts"][:n].long()
         m1 = torch.arange(ws["s1_pids"].shape[1], device=dev).unsqueeze(0) < c1.unsqueeze(1)
-        stats["T2"] += int((dl[ws["s1_pids"][:n].clamp(min=0).long()] * m1).sum())
+        stats["T2"] += int(dl[torch.where(m1, ws["s1_pids"][:n], 0).long()].mul(m1).sum())
         c2 = ws["s2_counts"][:n].long()
         stats["T3"] += int(ws["tok_offsets"][:n].gather(1, c2.unsqueeze(1)).sum())
         stats["found"] += int(ws["out_counts"][:n].sum())

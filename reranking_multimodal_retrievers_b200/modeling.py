@@ -103,7 +103,9 @@ def colbert_score_packed(Q, D_packed, D_lengths, config=None):
     tok_offsets = torch.zeros(nd + 1, device=dev, dtype=torch.int32)
     tok_offsets[1:] = torch.cumsum(lengths, 0).to(torch.int32)
     counts = torch.tensor([nd], device=dev, dtype=torch.int32)
-    scores = torch.empty(max(nd, 1), device=dev, dtype=torch.float32)
+    scores = torch.zeros(max(nd, 1), device=dev, dtype=torch.float32)
+    if nd == 0 or T == 0:      # nothing to contract: every (empty) passage scores sum_k max(0, -) = 0
+        return scores[:nd]
     wd = _watchdog(dev)
     _lib.call("plaid_maxsim_packed", _p(Qb), _p(qlens), 1, Qb.shape[0], Qb.shape[1], _p(Db), _p(tok_offsets), _p(counts),
               max(nd, 1), max(T, 1), 1, _p(scores), _p(wd), _stream())

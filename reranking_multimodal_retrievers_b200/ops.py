@@ -38,6 +38,8 @@ def _cu(t: torch.Tensor, dtype=None) -> torch.Tensor:
 
 
 def _p(t):
+    """Raw device pointer.  Only ever applied to a NAMED tensor: a temporary would be returned to the
+    caching allocator as soon as this call returns and could be handed to the next allocation."""
     return None if t is None else ctypes.c_void_p(t.data_ptr())
 
 
@@ -86,8 +88,9 @@ def approx_scores(pids, centroid_scores, codes, offsets, idx=None):
     qlens = torch.tensor([nq], device=pids.device, dtype=torch.int32)
     bits = pack_idx_bits(_cu(idx).bool()) if idx is not None else None
     out = torch.empty(max(n, 1), device=pids.device, dtype=torch.float32)
+    codes, offsets = _cu(codes, torch.int32), _cu(offsets, torch.int64)   # named: must outlive the launch
     _lib.call("plaid_approx_scores", _p(pids), _p(counts), 1, n, _p(S), _p(qlens), _p(bits), C,
-              _p(_cu(codes, torch.int32)), _p(_cu(offsets, torch.int64)), _p(out), _stream())
+              _p(codes), _p(offsets), _p(out), _stream())
     return out[:n]
 
 
@@ -131,8 +134,9 @@ def filter_pids(pids, centroid_scores, codes, doclens, offsets, idx, nfiltered_d
     s2p = torch.empty(ndocs // 4, device=dev, dtype=torch.int32)
     s2s = torch.empty(ndocs // 4, device=dev, dtype=torch.float32)
     s2c = torch.empty(1, device=dev, dtype=torch.int32)
+    codes, offsets = _cu(codes, torch.int32), _cu(offsets, torch.int64)   # named: must outlive the launch
     _lib.call("plaid_filter_pids", _p(pid_buf), _p(counts), 1, stride, _p(S), _p(qlens), _p(bits), C,
-              _p(_cu(codes, torch.int32)), _p(_cu(offsets, torch.int64)), ndocs, _p(ws_scores), _p(ws_keys),
+              _p(codes), _p(offsets), ndocs, _p(ws_scores), _p(ws_keys),
               _p(s1p), _p(s1s), _p(s1c), _p(s2p), _p(s2s), _p(s2c), _stream())
     n1, n2 = min(n, ndocs), min(n, ndocs // 4)
     if return_stages:
@@ -144,8 +148,8 @@ def filter_pids(pids, centroid_scores, codes, doclens, offsets, idx, nfiltered_d
 def build_weight_table(bucket_weights, reversed_bit_map, lookup, nbits):
     dev = _dev()
     W = torch.empty(256 * (8 // nbits), device=dev, dtype=torch.float32)
-    _lib.call("plaid_build_weight_table", _p(_cu(bucket_weights, torch.float32)), _p(_cu(reversed_bit_map, torch.uint8)),
-              _p(_cu(lookup, torch.uint8)), int(nbits), _p(W), _stream())
+    bw, rbm, lut = _cu(bucket_weights, torch.float32), _cu(reversed_bit_map, torch.uint8), _cu(lookup, torch.uint8)
+    _lib.call("plaid_build_weight_table", _p(bw), _p(rbm), _p(lut), int(nbits), _p(W), _stream())
     return W
 
 
@@ -169,9 +173,10 @@ def decompress_residuals(pids, lengths, offsets, bucket_weights, reversed_bit_ma
     W = build_weight_table(bucket_weights, reversed_bit_map, bucket_weight_combinations, nbits)
     cent = _cu(centroids, torch.float32)
     out = torch.empty(max(total, 1), dim, device=dev, dtype=torch.float32)
-    _lib.call("plaid_decompress_residuals", _p(pids), pids.numel(), _p(offsets), _p(out_offsets), _p(W),
-              _p(_cu(binary_residuals, torch.uint8)), _p(_cu(codes, torch.int32)), _p(cent), cent.shape[0], int(nbits),
-              _p(out), _stream())
+    res, codes = _cu(binary_residuals, torch.uint8), _cu(codes, torch.int32)   # named: must outlive the launch
+    if pids.numel():
+        _lib.call("plaid_decompress_residuals", _p(pids), pids.numel(), _p(offsets), _p(out_offsets), _p(W),
+                  _p(res), _p(codes), _p(cent), cent.shape[0], int(nbits), _p(out), _stream())
     return out[:total]
 
 
@@ -180,8 +185,8 @@ def unpack_residual_codes(residuals, nbits, reversed_bit_map, lookup):
     residuals = _cu(residuals, torch.uint8)
     n = residuals.shape[0]
     out = torch.empty(max(n, 1), DIM, device=residuals.device, dtype=torch.uint8)
-    _lib.call("plaid_unpack_residual_codes", _p(residuals), n, int(nbits), _p(_cu(reversed_bit_map, torch.uint8)),
-              _p(_cu(lookup, torch.uint8)), _p(out), _stream())
+    rbm, lut = _cu(reversed_bit_map, torch.uint8), _cu(lookup, torch.uint8)   # named: must outlive the launch
+    _lib.call("plaid_unpack_residual_codes", _p(residuals), n, int(nbits), _p(rbm), _p(lut), _p(out), _stream())
     return out[:n]
 
 
@@ -239,5 +244,6 @@ def to_bf16(x: torch.Tensor) -> torch.Tensor:
     """fp32 -> bf16 (RNE) through the library (codebook / passage embeddings)."""
     x = _cu(x, torch.float32)
     out = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
-    _lib.call("plaid_f32_to_bf16", _p(x), _p(out), x.numel(), _stream())
+    if x.numel():
+        _lib.call("plaid_f32_to_bf16", _p(x), _p(out), x.numel(), _stream())
     return out

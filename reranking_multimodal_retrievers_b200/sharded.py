@@ -25,7 +25,8 @@ def merge_topk(scores: torch.Tensor, pids: torch.Tensor, counts: torch.Tensor, k
     out_s = torch.empty(B, k, device=dev, dtype=torch.float32)
     out_c = torch.empty(B, device=dev, dtype=torch.int32)
     ws = torch.empty(max(B * G * k, 1), device=dev, dtype=torch.int64)
-    _lib.call("plaid_merge_topk", _p(scores.contiguous()), _p(pids.contiguous()), _p(counts.contiguous()), G, B, k,
+    scores, pids, counts = scores.contiguous(), pids.contiguous(), counts.contiguous()   # named: outlive the launch
+    _lib.call("plaid_merge_topk", _p(scores), _p(pids), _p(counts), G, B, k,
               _p(out_p), _p(out_s), _p(out_c), _p(ws), _stream())
     return out_p, out_s, out_c
 

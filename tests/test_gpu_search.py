@@ -119,7 +119,12 @@ def test_colbert_score_padded_vs_reference(pkg, golden):
     out = pkg.colbert_score(Q, D, mask)
     ref = torch.from_numpy(g["cs_scores"])
     assert out.dtype == torch.float32 and out.shape == ref.shape
-    assert ((out.cpu() - ref).abs() <= SCORE_REL_TOL * ref.abs() + 1e-5).all()
+    # 1e-3 relative to the magnitude of what is summed: sum_k |max_t <q_k, d_t>| (equal to |score| whenever
+    # the per-token maxima share a sign, which the packed path's clamp at 0 guarantees; these random
+    # unit vectors produce signed maxima that cancel)
+    full = D @ Q.permute(0, 2, 1)
+    mag = po.colbert_score_reduce(full, mask)[1].max(1).values.abs().sum(-1)
+    assert ((out.cpu() - ref).abs() <= SCORE_REL_TOL * mag + 1e-5).all()
     # same bf16 operands: tight
     ref_b = po.colbert_score(Q.bfloat16().float(), D.bfloat16().float(), mask)
     torch.testing.assert_close(out.cpu(), ref_b, rtol=2e-5, atol=2e-4)
