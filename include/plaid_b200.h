@@ -87,7 +87,7 @@ int plaid_candidates(const float* cell_val, const int32_t* cell_idx, const int32
  * Approximate score of every listed passage: sum over k < nq_b (sequential fp32, in k order) of
  * max over the passage's codes with idx bit set (all codes when idx_bits == NULL) of S[b, code, k],
  * each per-token max initialised to -9999.  pids [B, pid_stride] with counts[b] valid entries;
- * scores written to the same slots of out_scores.  One warp per passage, lane = query token. */
+ * scores written to the same slots of out_scores.  A CTA takes 32 passages of one query; lane = query token. */
 int plaid_approx_scores(const int32_t* pids, const int32_t* counts, int B, int pid_stride, const float* S,
                         const int32_t* qlens, const uint32_t* idx_bits, int C, const int32_t* codes,
                         const int64_t* offsets, float* out_scores, void* stream);
@@ -130,14 +130,16 @@ int plaid_unpack_residual_codes(const uint8_t* residuals, int64_t ntokens, int n
                                 const uint8_t* reversed_bit_map, const uint8_t* lookup, uint8_t* out,
                                 void* stream);
 
-/* Exclusive per-query prefix sums of the passage lengths of pids [B, pid_stride] (counts[b] valid):
- * tok_offsets [B, pid_stride+1] (i32, local to the query). */
+/* Exclusive per-query prefix sums of the passage lengths of pids [B, pid_stride] (counts[b] valid), each
+ * length rounded up to a multiple of `align` tokens (1 = packed back to back; 32 = the layout
+ * plaid_maxsim_packed's aligned mode reads): tok_offsets [B, pid_stride+1] (i32, local to the query). */
 int plaid_doc_token_offsets(const int32_t* pids, const int32_t* counts, int B, int pid_stride,
-                            const int64_t* offsets, int32_t* tok_offsets, void* stream);
+                            const int64_t* offsets, int align, int32_t* tok_offsets, void* stream);
 
 /* a6 + a7 for the search pipeline: decompress, L2-normalise (eps 1e-12, index_storage.py:175) and
  * round to bf16 into D [B, tok_stride, 128]; token j of passage i of query b lands on row
- * b*tok_stride + tok_offsets[b, i] + j.  centroids [C,128] either fp32 or, with centroids_are_f16 != 0,
+ * b*tok_stride + tok_offsets[b, i] + j; rows up to tok_offsets[b, i+1] (alignment padding) are zeroed.
+ * centroids [C,128] either fp32 or, with centroids_are_f16 != 0,
  * the fp16 values exactly as stored in centroids.pt (CB/indexing/codecs/residual.py:161; the CPU
  * reference widens them to fp32, residual.py:29 -- the same numbers).  The add is done in fp32
  * before normalisation, as the reference does. */
@@ -152,10 +154,13 @@ int plaid_decompress_normalize_bf16(const int32_t* pids, const int32_t* counts, 
  * scores[b, i] = sum_{k < qlens[b]} max(0, max_{t in passage i} <D[b, t], Qb[b, k]>): a tcgen05
  * Qb . D^T tile per 256 passage tokens with the per-passage running max and the sum over query
  * tokens done in the epilogue straight out of TMEM (the similarity matrix never reaches HBM).
- * clamp_zero = 1 reproduces the zero-initialised max buffer of segmented_maxsim.cpp:58-59. */
+ * clamp_zero = 1 reproduces the zero-initialised max buffer of segmented_maxsim.cpp:58-59.
+ * aligned32 = 1 promises that every passage starts on a 32-token boundary of D and that its pad rows are
+ * zero (what plaid_doc_token_offsets(align=32) + plaid_decompress_normalize_bf16 produce): with the clamp
+ * a zero row cannot change a maximum, so the epilogue never has to split a 32-column chunk. */
 int plaid_maxsim_packed(const void* Qb_bf16, const int32_t* qlens, int B, int B_pad, int Lq_pad,
                         const void* D_bf16, const int32_t* tok_offsets, const int32_t* counts, int pid_stride,
-                        int tok_stride, int clamp_zero, float* scores, int* watchdog, void* stream);
+                        int tok_stride, int clamp_zero, int aligned32, float* scores, int* watchdog, void* stream);
 
 /* The operator the reference binds as ColBERT.segmented_maxsim (colbert.py:60): scores f32 [T, nq]
  * already computed, lengths i64 [ndocs] -> f32 [ndocs]; zero-initialised running max, then a

@@ -13,8 +13,8 @@
 // Epilogue (8 warps; warp = (lane quadrant, 128-column half)), straight out of TMEM:
 //   * S[b, c, 0..31] -- for one centroid the warp's 32 lanes write 32 consecutive floats, i.e. one
 //     full 128-byte line of the reference's [C, nq] layout;
-//   * idx bit (b, c) = max over the query's tokens >= threshold, via redux.sync.max on
-//     order-preserving integer images of the scores;
+//   * idx bit (b, c) = max over the query's tokens >= threshold, as a warp vote (any token >= threshold),
+//     only evaluated per column when some thread's chunk maximum reaches the threshold;
 //   * per thread (= query token) a running top-ncells (score desc, centroid id asc) over all
 //     columns it sees -- partial per centroid range, merged in candidates.cu.
 // The kernel is bound by the S write (4*C*32 bytes per query), not by the tensor pipe.
@@ -39,6 +39,20 @@ struct CsBarriers {
     uint32_t tmem_base;
     int abort_flag;
 };
+
+// Insert (v, c) into the descending list bv/bi[0..ncells) (ties: lower centroid id first); returns the
+// new value of the last entry.  Called only with v > bv[ncells-1].  Deliberately out of line.
+__device__ __noinline__ float topk_insert(float* bv, int* bi, int ncells, float v, int c) {
+    int p = ncells - 1;
+    while (p > 0 && (v > bv[p - 1] || (v == bv[p - 1] && (unsigned)c < (unsigned)bi[p - 1]))) {
+        bv[p] = bv[p - 1];
+        bi[p] = bi[p - 1];
+        p--;
+    }
+    bv[p] = v;
+    bi[p] = c;
+    return bv[ncells - 1];
+}
 
 __global__ void __launch_bounds__(kCsThreads, 1)
 centroid_scores_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_c,
@@ -142,33 +156,29 @@ centroid_scores_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                 tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + acc * kCsN + half * 128 + ch * 32, r);
                 tc_wait_ld();
                 const int c0 = c_tile + ch * 32;
-                if (c0 < C) {  // C is a multiple of 32: a chunk is entirely inside or outside
-                    uint32_t word = 0;
+                if (c0 >= C) break;  // C is a multiple of 32: a chunk is entirely inside or outside
+                // (1) the S rows: for each centroid the warp stores 32 consecutive floats (one 128 B line)
+                float* dst = Sq + (size_t)c0 * PLAID_NQ_MAX;
 #pragma unroll
-                    for (int j = 0; j < 32; j++) {
-                        const float v = __uint_as_float(r[j]);
-                        st_stream_f32(Sq + (size_t)(c0 + j) * PLAID_NQ_MAX, v);
-                        const int ord = tok_valid ? float_to_ordered_s32(v) : INT_MIN;
-                        const int mx = __reduce_max_sync(0xffffffffu, ord);
-                        const float fmx = __int_as_float(mx ^ ((mx >> 31) & 0x7fffffff));
-                        word |= (fmx >= threshold ? 1u : 0u) << j;
-                        if (tok_valid && v > cut) {
-                            float cv = v;
-                            int ci = c0 + j;
+                for (int j = 0; j < 32; j++) __stcs(dst + j * PLAID_NQ_MAX, __uint_as_float(r[j]));
+                // (2) this thread's best value in the chunk decides whether the rare paths run at all
+                float mx = __uint_as_float(r[0]);
 #pragma unroll
-                            for (int p = 0; p < PLAID_NCELLS_MAX; p++) {
-                                if (p < ncells) {
-                                    const bool ahead = cv > bv[p] || (cv == bv[p] && (unsigned)ci < (unsigned)bi[p]);
-                                    if (ahead) {
-                                        const float tv = bv[p]; bv[p] = cv; cv = tv;
-                                        const int ti = bi[p]; bi[p] = ci; ci = ti;
-                                    }
-                                    if (p == ncells - 1) cut = bv[p];
-                                }
-                            }
-                        }
-                    }
-                    if (lane == 0) bits_q[c0 >> 5] = word;
+                for (int j = 1; j < 32; j++) mx = fmaxf(mx, __uint_as_float(r[j]));
+                // pruning mask: max_k S[c,k] >= thr  <=>  any valid token has S[c,k] >= thr
+                uint32_t word = 0;
+                if (__any_sync(0xffffffffu, tok_valid && mx >= threshold)) {
+#pragma unroll
+                    for (int j = 0; j < 32; j++)
+                        word |= (__any_sync(0xffffffffu, tok_valid && __uint_as_float(r[j]) >= threshold) ? 1u : 0u) << j;
+                }
+                if (lane == 0) bits_q[c0 >> 5] = word;
+                // (3) running top-ncells of this query token (score desc, centroid id asc); a thread gets
+                //     here only ~2 ln(C) times over the whole scan, so the list lives in local memory
+                if (tok_valid && mx > cut) {
+#pragma unroll
+                    for (int j = 0; j < 32; j++)
+                        if (__uint_as_float(r[j]) > cut) cut = topk_insert(bv, bi, ncells, __uint_as_float(r[j]), c0 + j);
                 }
             }
             tc_fence_before();

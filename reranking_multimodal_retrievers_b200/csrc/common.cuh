@@ -144,13 +144,14 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, int* watchdog) {
     if (mbar_try_wait(bar, parity)) return true;
     const uint64_t t0 = globaltimer_ns();
-    while (!mbar_try_wait(bar, parity)) {
-        if (globaltimer_ns() - t0 > 2000000000ull) {
+    for (uint32_t spins = 1;; spins++) {
+        if (mbar_try_wait(bar, parity)) return true;
+        if (spins > 8) __nanosleep(20);  // long wait: stop stealing issue slots from the warps doing the work
+        if ((spins & 255u) == 0 && globaltimer_ns() - t0 > 2000000000ull) {
             if (watchdog) atomicExch(watchdog, 1);
             return false;
         }
     }
-    return true;
 }
 
 // ---- TMA --------------------------------------------------------------------------------------

@@ -151,13 +151,17 @@ decompress_normalize_kernel(const int32_t* __restrict__ pids, const int32_t* __r
                                           reinterpret_cast<uint2*>(dst + (size_t)j * kDim)[lane] =
                                               make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
                                       });
+        // aligned layout: rows between this passage's last token and the next passage's first are zero
+        const int span = tok_offsets[(size_t)b * (pid_stride + 1) + i + 1] - tok_offsets[(size_t)b * (pid_stride + 1) + i];
+        for (int r = len + (threadIdx.x >> 5); r < span; r += (blockDim.x >> 5))
+            reinterpret_cast<uint2*>(dst + (size_t)r * kDim)[threadIdx.x & 31] = make_uint2(0u, 0u);
     }
 }
 
 // per query: exclusive prefix sums of passage lengths
 __global__ void __launch_bounds__(256)
 doc_token_offsets_kernel(const int32_t* __restrict__ pids, const int32_t* __restrict__ counts, int pid_stride,
-                         const int64_t* __restrict__ offsets, int32_t* __restrict__ tok_offsets) {
+                         const int64_t* __restrict__ offsets, int align, int32_t* __restrict__ tok_offsets) {
     __shared__ int s_warp[8];
     __shared__ int s_base;
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -171,6 +175,7 @@ doc_token_offsets_kernel(const int32_t* __restrict__ pids, const int32_t* __rest
         if (i < n) {
             const int pid = pids[(size_t)b * pid_stride + i];
             len = (int)(offsets[pid + 1] - offsets[pid]);
+            len = (len + align - 1) / align * align;   // every passage starts on an `align`-token boundary
         }
         int incl = len;
 #pragma unroll
@@ -279,12 +284,12 @@ extern "C" int plaid_decompress_residuals(const int32_t* pids, int npids, const 
 }
 
 extern "C" int plaid_doc_token_offsets(const int32_t* pids, const int32_t* counts, int B, int pid_stride,
-                                       const int64_t* offsets, int32_t* tok_offsets, void* stream) {
+                                       const int64_t* offsets, int align, int32_t* tok_offsets, void* stream) {
     using namespace plaid;
-    PLAID_CHECK_ARG(pids && counts && offsets && tok_offsets && B >= 0 && pid_stride >= 1, PLAID_ERR_ARG,
+    PLAID_CHECK_ARG(pids && counts && offsets && tok_offsets && B >= 0 && pid_stride >= 1 && align >= 1, PLAID_ERR_ARG,
                     "plaid_doc_token_offsets: bad argument");
     if (B == 0) return PLAID_OK;
-    doc_token_offsets_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(pids, counts, pid_stride, offsets, tok_offsets);
+    doc_token_offsets_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(pids, counts, pid_stride, offsets, align, tok_offsets);
     PLAID_LAUNCH_OK("doc_token_offsets_kernel");
     return PLAID_OK;
 }

@@ -15,52 +15,87 @@
 
 namespace plaid {
 
-static constexpr int kApproxWarps = 8;  // warps (= passages) per CTA
+static constexpr int kApproxWarps = 8;        // warps per CTA
+static constexpr int kApproxDocsPerWarp = 4;  // passages each warp walks through, one after the other
+static constexpr int kApproxDocs = kApproxWarps * kApproxDocsPerWarp;  // = 32 passages per CTA
 
+// A CTA scores 32 consecutive candidate passages of one query.  Warp w handles passages 4w..4w+3:
+// lane = query token; codes are pulled 128 at a time (one 128-bit load per lane), probed against the
+// query's pruning bitmap, and every surviving code costs one coalesced 128 B read of its S row.
+// The 32 per-token maxima of each passage are parked in shared memory; afterwards lane j of warp 0
+// adds up passage j's row left to right, which is exactly the sequential fp32 sum of
+// filter_pids.cpp:59-63 at 1/32 of the shuffle traffic of doing it inside every warp.
 template <bool USE_IDX>
 __global__ void __launch_bounds__(kApproxWarps * 32)
 approx_scores_kernel(const int32_t* __restrict__ pids, const int32_t* __restrict__ counts, int pid_stride,
                      const float* __restrict__ S, const int32_t* __restrict__ qlens,
                      const uint32_t* __restrict__ idx_bits, int C, const int32_t* __restrict__ codes,
                      const int64_t* __restrict__ offsets, float* __restrict__ out) {
-    const int b = blockIdx.y, lane = threadIdx.x & 31;
-    const int i = blockIdx.x * kApproxWarps + (threadIdx.x >> 5);
+    __shared__ float s_max[kApproxDocs][33];
+    const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int n = min(counts[b], pid_stride);
-    if (i >= n) return;
-    const int pid = pids[(size_t)b * pid_stride + i];
-    const int64_t off = offsets[pid];
-    const int len = (int)(offsets[pid + 1] - off);
-    const int nq = min(qlens[b], PLAID_NQ_MAX);
+    const int i0 = blockIdx.x * kApproxDocs;
+    if (i0 >= n) return;  // whole CTA past the end of this query's list
     const float* Sb = S + (size_t)b * C * PLAID_NQ_MAX + lane;
     const uint32_t* bits = USE_IDX ? idx_bits + (size_t)b * (C >> 5) : nullptr;
-    float m = -9999.0f;  // filter_pids.cpp:30-33
-    for (int j0 = 0; j0 < len; j0 += 32) {
-        const int j = j0 + lane;
-        int code = (j < len) ? ld_stream_s32(codes + off + j) : -1;
-        bool keep = (unsigned)code < (unsigned)C;
-        if (USE_IDX) keep = keep && ((__ldg(bits + (code >> 5)) >> (code & 31)) & 1u);
-        unsigned mask = __ballot_sync(0xffffffffu, keep);
-        // four S rows in flight per step
-        while (mask) {
-            int src[4];
-            float v[4];
+#pragma unroll 1
+    for (int d = 0; d < kApproxDocsPerWarp; d++) {
+        const int slot = warp * kApproxDocsPerWarp + d;
+        const int i = i0 + slot;
+        float m = -9999.0f;  // filter_pids.cpp:30-33
+        if (i < n) {
+            const int pid = pids[(size_t)b * pid_stride + i];
+            const int64_t off = offsets[pid];
+            const int len = (int)(offsets[pid + 1] - off);
+            const int64_t base = off & ~(int64_t)3;            // 16-byte aligned start of the code stream
+            const int head = (int)(off - base);
+            for (int e0 = 0; e0 < head + len; e0 += 128) {
+                const int e = e0 + lane * 4;                    // element index relative to `base`
+                int c4[4] = {-1, -1, -1, -1};
+                if (e >= head && e + 3 < head + len) {
+                    const int4 v = ld_stream_v4(codes + base + e);
+                    c4[0] = v.x; c4[1] = v.y; c4[2] = v.z; c4[3] = v.w;
+                } else {
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
-                src[u] = mask ? (__ffs(mask) - 1) : -1;
-                if (mask) mask &= mask - 1;
+                    for (int u = 0; u < 4; u++)
+                        if (e + u >= head && e + u < head + len) c4[u] = ld_stream_s32(codes + base + e + u);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int code = c4[u];
+                    bool keep = (unsigned)code < (unsigned)C;
+                    if (USE_IDX) keep = keep && ((__ldg(bits + (code >> 5)) >> (code & 31)) & 1u);
+                    unsigned mask = __ballot_sync(0xffffffffu, keep);
+                    while (mask) {  // four S rows in flight per step
+                        int src[4];
+                        float v[4];
+#pragma unroll
+                        for (int t = 0; t < 4; t++) {
+                            src[t] = mask ? (__ffs(mask) - 1) : -1;
+                            if (mask) mask &= mask - 1;
+                        }
+#pragma unroll
+                        for (int t = 0; t < 4; t++) {
+                            const int c = __shfl_sync(0xffffffffu, code, src[t] < 0 ? 0 : src[t]);
+                            v[t] = (src[t] >= 0) ? __ldg(Sb + (size_t)c * PLAID_NQ_MAX) : -9999.0f;
+                        }
+                        m = fmaxf(fmaxf(m, fmaxf(v[0], v[1])), fmaxf(v[2], v[3]));
+                    }
+                }
             }
-#pragma unroll
-            for (int u = 0; u < 4; u++) {
-                const int c = __shfl_sync(0xffffffffu, code, src[u] < 0 ? 0 : src[u]);
-                v[u] = (src[u] >= 0) ? __ldg(Sb + (size_t)c * PLAID_NQ_MAX) : -9999.0f;
-            }
-#pragma unroll
-            for (int u = 0; u < 4; u++) m = fmaxf(m, v[u]);
+        }
+        s_max[slot][lane] = m;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        const int i = i0 + lane;
+        if (i < n) {
+            const int nq = min(qlens[b], PLAID_NQ_MAX);
+            float s = 0.0f;  // sequential fp32 sum in token order (filter_pids.cpp:59-63)
+            for (int k = 0; k < nq; k++) s += s_max[lane][k];
+            out[(size_t)b * pid_stride + i] = s;
         }
     }
-    float s = 0.0f;  // sequential fp32 sum in token order (filter_pids.cpp:59-63)
-    for (int k = 0; k < nq; k++) s += __shfl_sync(0xffffffffu, m, k);
-    if (lane == 0) out[(size_t)b * pid_stride + i] = s;
 }
 
 // ------------------------------------------------------------------------------------------ select
@@ -216,7 +251,7 @@ static int next_pow2(int v) {
 static int launch_approx(const int32_t* pids, const int32_t* counts, int B, int pid_stride, const float* S,
                          const int32_t* qlens, const uint32_t* idx_bits, int C, const int32_t* codes,
                          const int64_t* offsets, float* out, cudaStream_t st) {
-    dim3 grid((pid_stride + kApproxWarps - 1) / kApproxWarps, B);
+    dim3 grid((pid_stride + kApproxDocs - 1) / kApproxDocs, B);
     if (idx_bits)
         approx_scores_kernel<true><<<grid, kApproxWarps * 32, 0, st>>>(pids, counts, pid_stride, S, qlens, idx_bits, C,
                                                                        codes, offsets, out);

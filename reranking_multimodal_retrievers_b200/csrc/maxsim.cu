@@ -21,7 +21,7 @@
 
 namespace plaid {
 
-static constexpr int kMsThreads = 256;   // warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4..7 epilogue
+static constexpr int kMsThreads = 256;   // warps 0-3 epilogue, 4-5 idle, 6 TMA producer, 7 TMEM alloc + MMA issue
 static constexpr int kMsGD = 16;         // passages per work item
 static constexpr int kMsMaxStages = 8;
 static constexpr int kMsMaxMT = 4;       // Lq_pad <= 512
@@ -30,6 +30,7 @@ struct MsParams {
     const int32_t* qlens;        // [nQ] valid rows per query
     int Lq_pad, MT, NT, NS;
     int padded;                  // 0 = packed search form, 1 = padded colbert_score form
+    int aligned;                 // packed only: passages start on 32-token boundaries of D, pad rows are zero
     // packed
     const int32_t* tok_offsets;  // [B, pid_stride+1] per-query exclusive prefix of passage lengths
     const int32_t* counts;       // [B]
@@ -93,8 +94,9 @@ struct MsShared {
     float part[2][4][kMsGD];
 };
 
-// Barrier over the 128 epilogue threads that also ORs a predicate, so that a watchdog abort seen by
-// one warp stops all four at the same work item (a lone early exit would strand the others here).
+// Barrier over the 128 epilogue threads (warps 0-3) that also ORs a predicate, so that a watchdog
+// abort seen by one warp stops all four at the same work item (a lone early exit would strand the
+// others at the barrier).
 __device__ __forceinline__ bool epi_bar_or(bool pred) {
     uint32_t r;
     asm volatile(
@@ -106,6 +108,21 @@ __device__ __forceinline__ bool epi_bar_or(bool pred) {
     return r != 0;
 }
 
+__device__ __forceinline__ float max32(const uint32_t (&r)[32], float seed) {
+    float a = seed;
+#pragma unroll
+    for (int j = 0; j < 32; j += 2) a = fmaxf(a, fmaxf(__uint_as_float(r[j]), __uint_as_float(r[j + 1])));
+    return a;
+}
+
+__device__ __noinline__ void store_raw(float* dst, float v) { *dst = v; }
+
+// MODE 0: packed + aligned (the search pipeline: every passage starts on a 32-token boundary of D and its
+//         pad rows are zero, so a 32-column chunk never straddles two passages and -- with the clamp at
+//         0 -- pad columns cannot change a maximum);
+// MODE 1: packed, arbitrary passage boundaries (colbert_score_packed operator);
+// MODE 2: padded with mask (colbert_score operator), optional masked-matrix output.
+template <int MODE>
 __global__ void __launch_bounds__(kMsThreads, 1)
 maxsim_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_d, const MsParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -116,6 +133,9 @@ maxsim_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
     uint8_t* sB = smem + a_bytes;           // [NS][2 k-halves][NT rows][128 B]
     MsShared* sh = reinterpret_cast<MsShared*>(sB + p.NS * b_bytes);
 
+    // warps 0-3: epilogue (warp = TMEM lane quadrant); 4-5: idle; 6: TMA producer; 7: TMEM alloc + MMA issue.
+    // The two single-thread roles sit on SM sub-partitions 2/3, away from the epilogue warps of the first
+    // 64 query tokens (the common Lq = 64 case leaves quadrants 2/3 without live rows).
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int item_begin = blockIdx.x * p.items_per_cta;
     const int item_end = min(p.num_items, item_begin + p.items_per_cta);
@@ -127,7 +147,7 @@ maxsim_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
         for (int a = 0; a < 2; a++) { mbar_init(&sh->tmem_full[a], 1); mbar_init(&sh->tmem_empty[a], 4); }
         fence_mbar_init();
     }
-    if (warp == 2) {
+    if (warp == 7) {
         tmem_alloc(&sh->tmem_base, 512);
         tmem_relinquish();
     }
@@ -137,7 +157,7 @@ maxsim_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
     const uint32_t tmem_base = sh->tmem_base;
     const int acc_cols = p.MT * p.NT;  // columns of one accumulator buffer
 
-    if (warp == 0) {
+    if (warp == 6) {
         // ===================== TMA producer =====================
         if (lane == 0) {
             tma_prefetch_desc(&map_q);
@@ -169,7 +189,7 @@ maxsim_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
                 }
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == 7) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
             const uint32_t idesc = umma_idesc_bf16(128, p.NT);
@@ -206,10 +226,11 @@ maxsim_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
                 }
             }
         }
-    } else if (warp >= 4) {
+    } else if (warp < 4) {
         // ===================== epilogue: 4 warps, warp = TMEM lane quadrant =====================
-        const int quad = warp & 3;
+        const int quad = warp;
         const float init = p.clamp_zero ? 0.0f : -INFINITY;
+        const uint32_t tmem_lane = tmem_base + ((uint32_t)(quad * 32) << 16);
         int it_tile = 0, parity = 0;
         bool ok = true;
         for (int w = item_begin; ok && w < item_end; w++) {
@@ -217,24 +238,37 @@ maxsim_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
             if (it.nd == 0) continue;
             const int lq = p.qlens[it.q];
             float* part = sh->part[parity][quad];
-            if (lane < kMsGD) part[lane] = 0.0f;
-            __syncwarp();
+            if (MODE != 0) {
+                if (lane < kMsGD) part[lane] = 0.0f;
+                __syncwarp();
+            }
             float runmax[kMsMaxMT];
-            bool rowok[kMsMaxMT];
+            bool rowok[kMsMaxMT], live[kMsMaxMT];
 #pragma unroll
             for (int m = 0; m < kMsMaxMT; m++) {
                 runmax[m] = init;
                 rowok[m] = (m * 128 + quad * 32 + lane) < lq;
+                live[m] = m < p.MT && (m * 128 + quad * 32) < lq;   // warp-uniform: some lane has a real query token
             }
-            // passage boundary state, relative to the item's first token
-            const int base_off = it.ends ? it.ends[0] : 0;
+            // passage ends of the item (relative to its first token) held one per lane: lane d+1 = end of passage d
+            int ends_reg = 0x7fffffff;
+            if (lane <= it.nd) ends_reg = it.ends ? (it.ends[lane] - it.ends[0]) : lane * p.Ld;
+            auto doc_end = [&](int d) -> int { return __shfl_sync(0xffffffffu, ends_reg, d + 1); };
             int doc = 0;
-            int next_end = it.ends ? it.ends[1] - base_off : p.Ld;
+            int next_end = doc_end(0);
 
-            auto doc_end = [&](int d) -> int {  // exclusive end of passage d (d < nd), item-relative
-                return it.ends ? it.ends[d + 1] - base_off : (d + 1) * p.Ld;
+            auto flush_all = [&](int d) {   // MODE 0: one write per passage, all m-tiles folded in
+                float v = 0.0f;
+#pragma unroll
+                for (int m = 0; m < kMsMaxMT; m++) {
+                    if (m < p.MT && rowok[m]) v += p.clamp_zero ? fmaxf(runmax[m], 0.0f) : runmax[m];
+                    runmax[m] = init;
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                if (lane == 0) part[d] = v;
             };
-            auto flush = [&](int m, int d) {
+            auto flush_one = [&](int m, int d) {
                 float v = rowok[m] ? (p.clamp_zero ? fmaxf(runmax[m], 0.0f) : runmax[m]) : 0.0f;
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -243,72 +277,91 @@ maxsim_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
             };
 
             const int ntiles = (it.ntok + p.NT - 1) / p.NT;
+            const int nchunks = p.NT >> 5;
             for (int t = 0; t < ntiles; t++, it_tile++) {
                 const int acc = it_tile & 1;
                 if (!mbar_wait(&sh->tmem_full[acc], (it_tile >> 1) & 1, p.watchdog)) { ok = false; break; }
                 tc_fence_after();
-                const int nchunks = p.NT >> 5;
+                const uint32_t tmem_acc = tmem_lane + acc * acc_cols;
                 for (int ch = 0; ch < nchunks; ch++) {
                     const int tk0 = t * p.NT + ch * 32;       // item-relative token of column 0
-                    const int nv = min(32, it.ntok - tk0);    // valid columns in this chunk
-                    if (nv <= 0) break;
-                    uint32_t mword = 0xffffffffu;
-                    if (p.padded) {
-                        const int mb = (lane < nv) ? p.mask[it.row0 + tk0 + lane] : 0;
-                        mword = __ballot_sync(0xffffffffu, mb != 0);
-                    }
-                    const bool fast = (nv == 32) && (next_end >= tk0 + 32) && (mword == 0xffffffffu) &&
-                                      (p.scores_raw == nullptr);
-                    int doc_after = doc, end_after = next_end;
-#pragma unroll
-                    for (int m = 0; m < kMsMaxMT; m++) {
-                        if (m >= p.MT) break;
-                        uint32_t r[32];
-                        tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + acc * acc_cols + m * p.NT + ch * 32, r);
-                        tc_wait_ld();
-                        if (fast) {
-                            float mx = runmax[m];
-#pragma unroll
-                            for (int j = 0; j < 32; j++) mx = fmaxf(mx, __uint_as_float(r[j]));
-                            runmax[m] = mx;
-                        } else {
-                            int d = doc, e = next_end;
-                            const int krow = m * 128 + quad * 32 + lane;
-#pragma unroll
-                            for (int j = 0; j < 32; j++) {
-                                if (j < nv) {
-                                    while (tk0 + j == e && d + 1 < it.nd) {  // passage d ends before this token
-                                        flush(m, d);
-                                        d++;
-                                        e = doc_end(d);
-                                    }
-                                    float v = __uint_as_float(r[j]);
-                                    if (!((mword >> j) & 1u)) v = -9999.0f;  // colbert.py:240-241
-                                    if (p.scores_raw && krow < p.Lq_out)
-                                        p.scores_raw[(size_t)(it.row0 + tk0 + j) * p.Lq_out + krow] = v;
-                                    runmax[m] = fmaxf(runmax[m], v);
-                                }
-                            }
-                            doc_after = d;
-                            end_after = e;
+                    if (tk0 >= it.ntok) break;
+                    if (MODE == 0) {
+                        while (tk0 == next_end && doc + 1 < it.nd) {   // this chunk opens the next passage
+                            flush_all(doc);
+                            doc++;
+                            next_end = doc_end(doc);
                         }
+#pragma unroll
+                        for (int m = 0; m < kMsMaxMT; m++) {
+                            if (!live[m]) continue;
+                            uint32_t r[32];
+                            tmem_ld_32x32(tmem_acc + m * p.NT + ch * 32, r);
+                            tc_wait_ld();
+                            runmax[m] = max32(r, runmax[m]);
+                        }
+                    } else {
+                        const int nv = min(32, it.ntok - tk0);    // valid columns in this chunk
+                        uint32_t mword = 0xffffffffu;
+                        if (MODE == 2) {
+                            const int mb = (lane < nv) ? p.mask[it.row0 + tk0 + lane] : 0;
+                            mword = __ballot_sync(0xffffffffu, mb != 0);
+                        }
+                        const bool fast = (nv == 32) && (next_end >= tk0 + 32) && (mword == 0xffffffffu) &&
+                                          (MODE != 2 || p.scores_raw == nullptr);
+                        int doc_after = doc, end_after = next_end;
+#pragma unroll
+                        for (int m = 0; m < kMsMaxMT; m++) {
+                            if (m >= p.MT) break;
+                            if (fast && !live[m]) continue;
+                            uint32_t r[32];
+                            tmem_ld_32x32(tmem_acc + m * p.NT + ch * 32, r);
+                            tc_wait_ld();
+                            if (fast) {
+                                runmax[m] = max32(r, runmax[m]);
+                            } else {
+                                int d = doc, e = next_end;
+                                const int krow = m * 128 + quad * 32 + lane;
+                                const bool raw = (MODE == 2) && p.scores_raw != nullptr && krow < p.Lq_out;
+#pragma unroll
+                                for (int j = 0; j < 32; j++) {
+                                    if (j < nv) {
+                                        while (tk0 + j == e && d + 1 < it.nd) {  // passage d ends before this token
+                                            flush_one(m, d);
+                                            d++;
+                                            e = doc_end(d);
+                                        }
+                                        float v = __uint_as_float(r[j]);
+                                        if (MODE == 2 && !((mword >> j) & 1u)) v = -9999.0f;  // colbert.py:240-241
+                                        if (raw) store_raw(p.scores_raw + (size_t)(it.row0 + tk0 + j) * p.Lq_out + krow, v);
+                                        runmax[m] = fmaxf(runmax[m], v);
+                                    }
+                                }
+                                doc_after = d;
+                                end_after = e;
+                            }
+                        }
+                        doc = doc_after;
+                        next_end = end_after;
                     }
-                    doc = doc_after;
-                    next_end = end_after;
                 }
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&sh->tmem_empty[acc]);
             }
             // close the passages still open (the last one, plus trailing empty ones)
+            if (MODE == 0) {
+                for (int d = doc; d < it.nd; d++) flush_all(d);
+            } else {
 #pragma unroll
-            for (int m = 0; m < kMsMaxMT; m++) {
-                if (m >= p.MT) break;
-                for (int d = doc; d < it.nd; d++) flush(m, d);
+                for (int m = 0; m < kMsMaxMT; m++) {
+                    if (m >= p.MT) break;
+                    for (int d = doc; d < it.nd; d++) flush_one(m, d);
+                }
             }
             __syncwarp();
             if (epi_bar_or(!ok)) ok = false;
-            const int te = threadIdx.x - 128;  // 0..127 among the epilogue threads
+            const int te = threadIdx.x;  // 0..127 among the epilogue threads
             if (te < it.nd) {
                 const float s = ((sh->part[parity][0][te] + sh->part[parity][1][te]) + sh->part[parity][2][te]) +
                                 sh->part[parity][3][te];
@@ -320,7 +373,7 @@ maxsim_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 2) tmem_dealloc(tmem_base, 512);
+    if (warp == 7) tmem_dealloc(tmem_base, 512);
 }
 
 static int ms_configure(MsParams& p, int Lq_pad) {
@@ -341,16 +394,21 @@ static int ms_launch(const void* Qb, int q_rows, const void* D, uint64_t d_rows,
     if ((rc = make_bf16_2d_map(&map_q, Qb, (uint64_t)q_rows, kDim, 128)) != PLAID_OK) return rc;
     if ((rc = make_bf16_2d_map(&map_d, D, d_rows, kDim, p.NT)) != PLAID_OK) return rc;
     const int smem = 1024 + p.MT * 128 * kDim * 2 + p.NS * p.NT * kDim * 2 + (int)sizeof(MsShared) + 64;
-    static int configured = 0;
-    if (smem > configured) {
-        PLAID_CUDA_OK(cudaFuncSetAttribute(maxsim_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        configured = smem;
+    const int mode = p.padded ? 2 : (p.aligned ? 0 : 1);
+    static int configured[3] = {0, 0, 0};
+    if (smem > configured[mode]) {
+        const void* fn = mode == 0 ? (const void*)maxsim_kernel<0> : mode == 1 ? (const void*)maxsim_kernel<1>
+                                                                               : (const void*)maxsim_kernel<2>;
+        PLAID_CUDA_OK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured[mode] = smem;
     }
     int grid = sm_count();
     if (grid > p.num_items) grid = p.num_items;
     p.items_per_cta = (p.num_items + grid - 1) / grid;
     grid = (p.num_items + p.items_per_cta - 1) / p.items_per_cta;
-    maxsim_kernel<<<grid, kMsThreads, smem, st>>>(map_q, map_d, p);
+    if (mode == 0) maxsim_kernel<0><<<grid, kMsThreads, smem, st>>>(map_q, map_d, p);
+    else if (mode == 1) maxsim_kernel<1><<<grid, kMsThreads, smem, st>>>(map_q, map_d, p);
+    else maxsim_kernel<2><<<grid, kMsThreads, smem, st>>>(map_q, map_d, p);
     PLAID_LAUNCH_OK("maxsim_kernel");
     return PLAID_OK;
 }
@@ -359,7 +417,8 @@ static int ms_launch(const void* Qb, int q_rows, const void* D, uint64_t d_rows,
 
 extern "C" int plaid_maxsim_packed(const void* Qb_bf16, const int32_t* qlens, int B, int B_pad, int Lq_pad,
                                    const void* D_bf16, const int32_t* tok_offsets, const int32_t* counts, int pid_stride,
-                                   int tok_stride, int clamp_zero, float* scores, int* watchdog, void* stream) {
+                                   int tok_stride, int clamp_zero, int aligned32, float* scores, int* watchdog,
+                                   void* stream) {
     using namespace plaid;
     PLAID_CHECK_ARG(Qb_bf16 && qlens && D_bf16 && tok_offsets && counts && scores, PLAID_ERR_ARG,
                     "plaid_maxsim_packed: null pointer");
@@ -379,6 +438,9 @@ extern "C" int plaid_maxsim_packed(const void* Qb_bf16, const int32_t* qlens, in
     p.tok_stride = tok_stride;
     p.scores = scores;
     p.clamp_zero = clamp_zero;
+    PLAID_CHECK_ARG(!aligned32 || clamp_zero, PLAID_ERR_ARG,
+                    "plaid_maxsim_packed: the aligned layout relies on the clamp at 0 to ignore its zero pad rows");
+    p.aligned = aligned32 ? 1 : 0;
     p.watchdog = watchdog;
     p.groups_per_query = (pid_stride + kMsGD - 1) / kMsGD;
     p.num_items = B * p.groups_per_query;

@@ -88,7 +88,8 @@ class SearchEngine:
         cand_stride = max(ndocs, min(N, NQ_MAX * ncells * max(ix.max_ivf_len, 1)))
         cand_stride = ((cand_stride + 63) // 64) * 64
         fstride = max(cand_stride, ndocs)
-        tok_stride = ((nd4 * max(ix.max_doclen, 1) + 127) // 128) * 128
+        tok_stride = nd4 * (((max(ix.max_doclen, 1) + 31) // 32) * 32)   # passages are 32-token aligned in D
+        tok_stride = ((tok_stride + 127) // 128) * 128
         e = lambda *shape, dtype: torch.empty(*shape, device=dev, dtype=dtype)
         ws = dict(
             csplit=csplit, nlists=nlists, cand_stride=cand_stride, fstride=fstride, tok_stride=tok_stride, nd4=nd4,
@@ -169,12 +170,12 @@ class SearchEngine:
              _p(ws["s2_pids"]), _p(ws["s2_scores"]), _p(ws["s2_counts"]), nd4_, _p(ws["ws_keys"]), st)
         nd4 = ws["nd4"]
         call("doc_offsets", "plaid_doc_token_offsets", _p(ws["s2_pids"]), _p(ws["s2_counts"]), b, nd4, _p(ix.offsets),
-             _p(ws["tok_offsets"]), st)
+             32, _p(ws["tok_offsets"]), st)
         call("decompress", "plaid_decompress_normalize_bf16", _p(ws["s2_pids"]), _p(ws["s2_counts"]), b, nd4, _p(ws["tok_offsets"]),
              ws["tok_stride"], _p(ix.offsets), _p(ix.weight_table), _p(ix.residuals), _p(ix.codes),
              _p(ix.centroids_f16), 1, C, ix.nbits, _p(ws["D"]), st)
         call("maxsim", "plaid_maxsim_packed", _p(ws["Qb"]), _p(ws["qlens"]), b, Bc, Lq_pad, _p(ws["D"]), _p(ws["tok_offsets"]),
-             _p(ws["s2_counts"]), nd4, ws["tok_stride"], 1, _p(ws["scores"]), wd, st)
+             _p(ws["s2_counts"]), nd4, ws["tok_stride"], 1, 1, _p(ws["scores"]), wd, st)
         call("topk", "plaid_select_top", _p(ws["s2_pids"]), _p(ws["scores"]), _p(ws["s2_counts"]), b, nd4, k, _p(ws["out_pids"]),
              _p(ws["out_scores"]), _p(ws["out_counts"]), k, _p(ws["ws_keys"]), st)
 
