@@ -3,9 +3,10 @@
 // Replaces CB/search/decompress_residuals.cpp:27-155 (CPU, byte-at-a-time table walks) and
 // CB/indexing/codecs/decompress_residuals.cu (one thread per packed byte, two global RMWs per
 // element).  Here a warp pulls 512 B of packed residuals per step with one 128-bit load per lane
-// (= 32/16/8/4 whole tokens at 1/2/4/8 bits), parks them in shared memory, and then emits one
-// token per iteration: lane l owns dimensions 4l..4l+3, so the centroid row is read and the output
-// row written as one fully coalesced request.  The reference's two byte tables
+// (= 32/16/8/4 whole tokens at 1/2/4/8 bits), parks them in shared memory, and then emits two
+// tokens per iteration: each half-warp owns a token, lane h of the half its dimensions 8h..8h+7, so
+// the fp16 centroid row is read with one 128-bit load per lane and the output row is written as one
+// fully coalesced request.  The reference's two byte tables
 // (reversed_bit_map, decompression_lookup_table; CB/indexing/codecs/residual.py:54-89) and
 // bucket_weights are folded into one 256-row weight table W[x][l] kept in shared memory.
 #include "common.cuh"
@@ -36,35 +37,52 @@ __global__ void unpack_codes_kernel(const uint8_t* __restrict__ residuals, int64
     }
 }
 
-// bucket weights of dimensions 4*lane .. 4*lane+3 of one token whose packed row sits at `row` (smem)
+// Bucket weights of the 8 dimensions 8h..8h+7 (h = 0..15) of one token whose packed row sits at `row` (smem).
 template <int NBITS>
-__device__ __forceinline__ float4 token_weights(const uint8_t* row, const float* sW, int lane) {
-    if constexpr (NBITS == 2) {
-        return reinterpret_cast<const float4*>(sW)[row[lane]];
-    } else if constexpr (NBITS == 4) {
-        const uchar2 x = reinterpret_cast<const uchar2*>(row)[lane];
+__device__ __forceinline__ void token_weights8(const uint8_t* row, const float* sW, int h, float (&w)[8]) {
+    if constexpr (NBITS == 2) {           // 4 dims per byte: bytes 2h, 2h+1
+        const uchar2 x = reinterpret_cast<const uchar2*>(row)[h];
+        const float4 a = reinterpret_cast<const float4*>(sW)[x.x], b = reinterpret_cast<const float4*>(sW)[x.y];
+        w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+    } else if constexpr (NBITS == 4) {    // 2 dims per byte: bytes 4h..4h+3
+        const uchar4 x = reinterpret_cast<const uchar4*>(row)[h];
         const float2 a = reinterpret_cast<const float2*>(sW)[x.x], b = reinterpret_cast<const float2*>(sW)[x.y];
-        return make_float4(a.x, a.y, b.x, b.y);
-    } else if constexpr (NBITS == 1) {
-        return reinterpret_cast<const float4*>(sW)[row[lane >> 1] * 2 + (lane & 1)];
-    } else {
-        const uchar4 x = reinterpret_cast<const uchar4*>(row)[lane];
-        return make_float4(sW[x.x], sW[x.y], sW[x.z], sW[x.w]);
+        const float2 c = reinterpret_cast<const float2*>(sW)[x.z], d = reinterpret_cast<const float2*>(sW)[x.w];
+        w[0] = a.x; w[1] = a.y; w[2] = b.x; w[3] = b.y; w[4] = c.x; w[5] = c.y; w[6] = d.x; w[7] = d.y;
+    } else if constexpr (NBITS == 1) {    // 8 dims per byte: byte h
+        const int x = row[h];
+        const float4 a = reinterpret_cast<const float4*>(sW)[x * 2], b = reinterpret_cast<const float4*>(sW)[x * 2 + 1];
+        w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+    } else {                              // 1 dim per byte: bytes 8h..8h+7
+        const uint2 x = reinterpret_cast<const uint2*>(row)[h];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            w[i] = sW[(x.x >> (8 * i)) & 0xff];
+            w[4 + i] = sW[(x.y >> (8 * i)) & 0xff];
+        }
     }
 }
 
-__device__ __forceinline__ float4 load_centroid4(const float* c, int lane) {
-    return __ldg(reinterpret_cast<const float4*>(c) + lane);
+// centroid elements 8h..8h+7 widened to fp32
+__device__ __forceinline__ void load_centroid8(const float* c, int h, float (&e)[8]) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(c) + 2 * h), b = __ldg(reinterpret_cast<const float4*>(c) + 2 * h + 1);
+    e[0] = a.x; e[1] = a.y; e[2] = a.z; e[3] = a.w; e[4] = b.x; e[5] = b.y; e[6] = b.z; e[7] = b.w;
 }
-__device__ __forceinline__ float4 load_centroid4(const __half* c, int lane) {
-    const uint2 raw = __ldg(reinterpret_cast<const uint2*>(c) + lane);
-    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&raw.x));
-    const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
-    return make_float4(a.x, a.y, b.x, b.y);
+__device__ __forceinline__ void load_centroid8(const __half* c, int h, float (&e)[8]) {
+    const uint4 raw = __ldg(reinterpret_cast<const uint4*>(c) + h);   // one 128-bit load = 8 fp16
+    const uint32_t u[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&u[i]));
+        e[2 * i] = f.x;
+        e[2 * i + 1] = f.y;
+    }
 }
 
 // Decompress the tokens of ONE passage (codes/residual rows [tok0, tok0+len)) with the warps of a CTA.
-// emit(j, v, lane) receives the fp32 values of dims 4*lane..4*lane+3 of token j.
+// A warp pulls 512 B of packed residuals per step (one 128-bit load per lane) into shared memory and then
+// emits TWO tokens per iteration: each half-warp owns one token, lane h of the half its dims 8h..8h+7.
+// emit(j, v, h, valid) is called by all 32 lanes (it may shuffle); v = the 8 fp32 values, valid = j < len.
 template <int NBITS, typename CT, typename Emit>
 __device__ __forceinline__ void decompress_passage(int64_t tok0, int len, const uint8_t* __restrict__ residuals,
                                                    const int32_t* __restrict__ codes, const CT* __restrict__ centroids,
@@ -72,6 +90,7 @@ __device__ __forceinline__ void decompress_passage(int64_t tok0, int len, const 
     constexpr int PB = 16 * NBITS;   // packed bytes per token
     constexpr int TB = 512 / PB;     // tokens per 512-byte warp batch
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int h = lane & 15, half = lane >> 4;
     uint8_t* stage = s_stage + warp * 512;
     for (int t0 = warp * TB; t0 < len; t0 += nw * TB) {
         const int nt = min(TB, len - t0);
@@ -79,13 +98,16 @@ __device__ __forceinline__ void decompress_passage(int64_t tok0, int len, const 
             reinterpret_cast<int4*>(stage)[lane] = ld_stream_v4(residuals + (tok0 + t0) * PB + lane * 16);
         int code = (lane < nt) ? ld_stream_s32(codes + tok0 + t0 + lane) : 0;
         __syncwarp();
-#pragma unroll 4
-        for (int j = 0; j < nt; j++) {
+        for (int j0 = 0; j0 < nt; j0 += 2) {
+            const int j = min(j0 + half, nt - 1);           // the odd tail re-does the last token, masked out below
             int c = __shfl_sync(0xffffffffu, code, j);
             c = min(max(c, 0), C - 1);
-            const float4 w = token_weights<NBITS>(stage + j * PB, sW, lane);
-            const float4 e = load_centroid4(centroids + (size_t)c * kDim, lane);
-            emit(t0 + j, make_float4(w.x + e.x, w.y + e.y, w.z + e.z, w.w + e.w), lane);
+            float w[8], e[8], v[8];
+            token_weights8<NBITS>(stage + j * PB, sW, h, w);
+            load_centroid8(centroids + (size_t)c * kDim, h, e);
+#pragma unroll
+            for (int i = 0; i < 8; i++) v[i] = w[i] + e[i];
+            emit(t0 + j, v, h, j0 + half < nt);
         }
         __syncwarp();
     }
@@ -114,8 +136,11 @@ decompress_packed_kernel(const int32_t* __restrict__ pids, int npids, const int6
         const int len = (int)(offsets[pid + 1] - tok0);
         float* dst = out + out_offsets[i] * kDim;
         decompress_passage<NBITS, CT>(tok0, len, residuals, codes, centroids, C, sW, s_stage,
-                                      [&](int j, float4 v, int lane) {
-                                          reinterpret_cast<float4*>(dst + (size_t)j * kDim)[lane] = v;
+                                      [&](int j, const float (&v)[8], int h, bool valid) {
+                                          if (!valid) return;
+                                          float4* o = reinterpret_cast<float4*>(dst + (size_t)j * kDim) + 2 * h;
+                                          o[0] = make_float4(v[0], v[1], v[2], v[3]);
+                                          o[1] = make_float4(v[4], v[5], v[6], v[7]);
                                       });
     }
 }
@@ -140,16 +165,23 @@ decompress_normalize_kernel(const int32_t* __restrict__ pids, const int32_t* __r
         const int len = (int)(offsets[pid + 1] - tok0);
         __nv_bfloat16* dst = D + ((size_t)b * tok_stride + tok_offsets[(size_t)b * (pid_stride + 1) + i]) * kDim;
         decompress_passage<NBITS, CT>(tok0, len, residuals, codes, centroids, C, sW, s_stage,
-                                      [&](int j, float4 v, int lane) {
-                                          float ss = v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+                                      [&](int j, const float (&v)[8], int h, bool valid) {
+                                          float ss = 0.f;
 #pragma unroll
-                                          for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-                                          // F.normalize: x / max(||x||_2, 1e-12)  (index_storage.py:175)
-                                          const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
-                                          __nv_bfloat162 lo = __floats2bfloat162_rn(v.x * inv, v.y * inv);
-                                          __nv_bfloat162 hi = __floats2bfloat162_rn(v.z * inv, v.w * inv);
-                                          reinterpret_cast<uint2*>(dst + (size_t)j * kDim)[lane] =
-                                              make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+                                          for (int i = 0; i < 8; i++) ss = fmaf(v[i], v[i], ss);
+#pragma unroll
+                                          for (int o = 8; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+                                          // F.normalize: x / max(||x||_2, 1e-12) = x * rsqrt(max(||x||^2, 1e-24))
+                                          // (index_storage.py:175)
+                                          const float inv = rsqrtf(fmaxf(ss, 1e-24f));
+                                          uint32_t pk[4];
+#pragma unroll
+                                          for (int i = 0; i < 4; i++) {
+                                              __nv_bfloat162 t = __floats2bfloat162_rn(v[2 * i] * inv, v[2 * i + 1] * inv);
+                                              pk[i] = *reinterpret_cast<uint32_t*>(&t);
+                                          }
+                                          if (valid)
+                                              reinterpret_cast<uint4*>(dst + (size_t)j * kDim)[h] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                                       });
         // aligned layout: rows between this passage's last token and the next passage's first are zero
         const int span = tok_offsets[(size_t)b * (pid_stride + 1) + i + 1] - tok_offsets[(size_t)b * (pid_stride + 1) + i];

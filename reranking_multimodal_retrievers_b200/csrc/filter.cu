@@ -16,31 +16,33 @@
 namespace plaid {
 
 static constexpr int kApproxWarps = 8;        // warps per CTA
-static constexpr int kApproxDocsPerWarp = 4;  // passages each warp walks through, one after the other
-static constexpr int kApproxDocs = kApproxWarps * kApproxDocsPerWarp;  // = 32 passages per CTA
 
-// A CTA scores 32 consecutive candidate passages of one query.  Warp w handles passages 4w..4w+3:
+// A CTA scores 8*DPW consecutive candidate passages of one query; warp w walks passages DPW*w.. one
+// after the other.  Stage 1 (pruned, almost no S reads) uses DPW = 4; stage 2 (every code reads an S
+// row) uses DPW = 1 so that the CTAs resident at any moment belong to few queries and their S tables
+// (4*C*32 bytes each) stay in L2.  Within a warp:
 // lane = query token; codes are pulled 128 at a time (one 128-bit load per lane), probed against the
 // query's pruning bitmap, and every surviving code costs one coalesced 128 B read of its S row.
 // The 32 per-token maxima of each passage are parked in shared memory; afterwards lane j of warp 0
 // adds up passage j's row left to right, which is exactly the sequential fp32 sum of
 // filter_pids.cpp:59-63 at 1/32 of the shuffle traffic of doing it inside every warp.
-template <bool USE_IDX>
+template <bool USE_IDX, int DPW>
 __global__ void __launch_bounds__(kApproxWarps * 32)
 approx_scores_kernel(const int32_t* __restrict__ pids, const int32_t* __restrict__ counts, int pid_stride,
                      const float* __restrict__ S, const int32_t* __restrict__ qlens,
                      const uint32_t* __restrict__ idx_bits, int C, const int32_t* __restrict__ codes,
                      const int64_t* __restrict__ offsets, float* __restrict__ out) {
-    __shared__ float s_max[kApproxDocs][33];
+    constexpr int kDocs = kApproxWarps * DPW;
+    __shared__ float s_max[kDocs][33];
     const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int n = min(counts[b], pid_stride);
-    const int i0 = blockIdx.x * kApproxDocs;
+    const int i0 = blockIdx.x * kDocs;
     if (i0 >= n) return;  // whole CTA past the end of this query's list
     const float* Sb = S + (size_t)b * C * PLAID_NQ_MAX + lane;
     const uint32_t* bits = USE_IDX ? idx_bits + (size_t)b * (C >> 5) : nullptr;
 #pragma unroll 1
-    for (int d = 0; d < kApproxDocsPerWarp; d++) {
-        const int slot = warp * kApproxDocsPerWarp + d;
+    for (int d = 0; d < DPW; d++) {
+        const int slot = warp * DPW + d;
         const int i = i0 + slot;
         float m = -9999.0f;  // filter_pids.cpp:30-33
         if (i < n) {
@@ -87,7 +89,7 @@ approx_scores_kernel(const int32_t* __restrict__ pids, const int32_t* __restrict
         s_max[slot][lane] = m;
     }
     __syncthreads();
-    if (warp == 0) {
+    if (warp == 0 && lane < kDocs) {
         const int i = i0 + lane;
         if (i < n) {
             const int nq = min(qlens[b], PLAID_NQ_MAX);
@@ -251,13 +253,15 @@ static int next_pow2(int v) {
 static int launch_approx(const int32_t* pids, const int32_t* counts, int B, int pid_stride, const float* S,
                          const int32_t* qlens, const uint32_t* idx_bits, int C, const int32_t* codes,
                          const int64_t* offsets, float* out, cudaStream_t st) {
-    dim3 grid((pid_stride + kApproxDocs - 1) / kApproxDocs, B);
-    if (idx_bits)
-        approx_scores_kernel<true><<<grid, kApproxWarps * 32, 0, st>>>(pids, counts, pid_stride, S, qlens, idx_bits, C,
-                                                                       codes, offsets, out);
-    else
-        approx_scores_kernel<false><<<grid, kApproxWarps * 32, 0, st>>>(pids, counts, pid_stride, S, qlens, nullptr, C,
-                                                                        codes, offsets, out);
+    if (idx_bits) {
+        dim3 grid((pid_stride + kApproxWarps * 4 - 1) / (kApproxWarps * 4), B);
+        approx_scores_kernel<true, 4><<<grid, kApproxWarps * 32, 0, st>>>(pids, counts, pid_stride, S, qlens, idx_bits, C,
+                                                                          codes, offsets, out);
+    } else {
+        dim3 grid((pid_stride + kApproxWarps - 1) / kApproxWarps, B);
+        approx_scores_kernel<false, 1><<<grid, kApproxWarps * 32, 0, st>>>(pids, counts, pid_stride, S, qlens, nullptr, C,
+                                                                           codes, offsets, out);
+    }
     PLAID_LAUNCH_OK("approx_scores_kernel");
     return PLAID_OK;
 }

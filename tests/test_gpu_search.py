@@ -89,12 +89,17 @@ def test_pipeline_stagewise_bit_exact_with_injected_table(pkg, golden):
         assert torch.equal(t.stage1_scores[b, :n1].cpu(), r["stage1_scores"])
         assert torch.equal(t.stage2_pids[b, :n2].cpu(), r["stage2_pids"])
         assert torch.equal(t.stage2_scores[b, :n2].cpu(), r["stage2_scores"])
-        # decompressed + normalised passages (bf16): within one bf16 ulp of the oracle's fp32 rows
+        # decompressed + normalised passages (bf16): within one bf16 ulp of the oracle's fp32 rows.
+        # In D every passage starts on a 32-token boundary; the rows in between are zero.
         lens = ix.doclens[r["stage2_pids"].long()]
-        to = t.tok_offsets[b, :n2 + 1].cpu()
-        assert torch.equal(to[1:] - to[:-1], lens.to(torch.int32))
-        T = int(to[-1])
-        D = t.D[b * t.tok_stride: b * t.tok_stride + T].float().cpu()
+        to = t.tok_offsets[b, :n2 + 1].cpu().long()
+        assert torch.equal(to[1:] - to[:-1], (lens + 31) // 32 * 32) and int(to[0]) == 0
+        Dq = t.D[b * t.tok_stride: b * t.tok_stride + int(to[-1])].float().cpu()
+        rows = torch.cat([torch.arange(int(o), int(o) + int(l)) for o, l in zip(to[:-1], lens)])
+        pad = torch.ones(Dq.shape[0], dtype=torch.bool)
+        pad[rows] = False
+        assert torch.count_nonzero(Dq[pad]) == 0
+        D = Dq[rows]
         assert (D - r["D"]).abs().max() <= 2 ** -8
         assert (D != r["D"].bfloat16().float()).float().mean() < 2e-3
         # exact MaxSim: (a) same bf16 operands -> only summation order differs; (b) fp32 oracle within 1e-3
