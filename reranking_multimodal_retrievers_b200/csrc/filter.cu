@@ -16,13 +16,37 @@
 namespace plaid {
 
 static constexpr int kApproxWarps = 8;        // warps per CTA
+static constexpr int kStage1Dpw = 16;         // stage 1: 128 passages per CTA (amortises the bitmap load)
+static constexpr int kStage2Dpw = 1;          // stage 2: 8 passages per CTA (few queries resident -> S stays in L2)
+
+// Gather the S rows of the codes selected by `mask` (bit l = lane l's `code`), G rows in flight per step.
+template <int G>
+__device__ __forceinline__ float gather_rows(unsigned mask, int code, const float* __restrict__ Sb, float m) {
+    while (mask) {
+        int src[G];
+        float v[G];
+#pragma unroll
+        for (int t = 0; t < G; t++) {
+            src[t] = mask ? (__ffs(mask) - 1) : -1;
+            if (mask) mask &= mask - 1;
+        }
+#pragma unroll
+        for (int t = 0; t < G; t++) {
+            const int c = __shfl_sync(0xffffffffu, code, src[t] < 0 ? 0 : src[t]);
+            v[t] = (src[t] >= 0) ? __ldg(Sb + (size_t)(unsigned)c * PLAID_NQ_MAX) : -9999.0f;
+        }
+#pragma unroll
+        for (int t = 0; t < G; t++) m = fmaxf(m, v[t]);
+    }
+    return m;
+}
 
 // A CTA scores 8*DPW consecutive candidate passages of one query; warp w walks passages DPW*w.. one
-// after the other.  Stage 1 (pruned, almost no S reads) uses DPW = 4; stage 2 (every code reads an S
-// row) uses DPW = 1 so that the CTAs resident at any moment belong to few queries and their S tables
-// (4*C*32 bytes each) stay in L2.  Within a warp:
-// lane = query token; codes are pulled 128 at a time (one 128-bit load per lane), probed against the
-// query's pruning bitmap, and every surviving code costs one coalesced 128 B read of its S row.
+// after the other, lane = query token.  Codes are pulled 128 at a time (one 128-bit load per lane).
+//   stage 1 (USE_IDX): the query's pruning bitmap (C bits) sits in shared memory; each lane probes its
+//     four codes, ONE warp vote per 128 codes tells whether anything survived, and only then the
+//     surviving codes' S rows are read (one coalesced 128 B request each);
+//   stage 2: every code reads its S row, eight rows in flight per warp.
 // The 32 per-token maxima of each passage are parked in shared memory; afterwards lane j of warp 0
 // adds up passage j's row left to right, which is exactly the sequential fp32 sum of
 // filter_pids.cpp:59-63 at 1/32 of the shuffle traffic of doing it inside every warp.
@@ -33,13 +57,21 @@ approx_scores_kernel(const int32_t* __restrict__ pids, const int32_t* __restrict
                      const uint32_t* __restrict__ idx_bits, int C, const int32_t* __restrict__ codes,
                      const int64_t* __restrict__ offsets, float* __restrict__ out) {
     constexpr int kDocs = kApproxWarps * DPW;
-    __shared__ float s_max[kDocs][33];
+    extern __shared__ __align__(16) uint32_t s_dyn[];
+    float (*s_max)[33] = reinterpret_cast<float (*)[33]>(s_dyn);      // [kDocs][33]
+    uint32_t* s_bits = s_dyn + kDocs * 33;                            // [C/32] (stage 1 only)
     const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int n = min(counts[b], pid_stride);
     const int i0 = blockIdx.x * kDocs;
     if (i0 >= n) return;  // whole CTA past the end of this query's list
     const float* Sb = S + (size_t)b * C * PLAID_NQ_MAX + lane;
-    const uint32_t* bits = USE_IDX ? idx_bits + (size_t)b * (C >> 5) : nullptr;
+    if (USE_IDX) {
+        const uint4* src = reinterpret_cast<const uint4*>(idx_bits + (size_t)b * (C >> 5));
+        for (int i = threadIdx.x; i < (C >> 7); i += blockDim.x) reinterpret_cast<uint4*>(s_bits)[i] = __ldg(src + i);
+        for (int i = (C >> 7) * 4 + threadIdx.x; i < (C >> 5); i += blockDim.x)
+            s_bits[i] = __ldg(idx_bits + (size_t)b * (C >> 5) + i);
+        __syncthreads();
+    }
 #pragma unroll 1
     for (int d = 0; d < DPW; d++) {
         const int slot = warp * DPW + d;
@@ -49,52 +81,51 @@ approx_scores_kernel(const int32_t* __restrict__ pids, const int32_t* __restrict
             const int pid = pids[(size_t)b * pid_stride + i];
             const int64_t off = offsets[pid];
             const int len = (int)(offsets[pid + 1] - off);
-            const int64_t base = off & ~(int64_t)3;            // 16-byte aligned start of the code stream
-            const int head = (int)(off - base);
-            for (int e0 = 0; e0 < head + len; e0 += 128) {
-                const int e = e0 + lane * 4;                    // element index relative to `base`
+            const int head = (int)(off & 3);                    // codes is 16-byte aligned: align the stream down
+            const int32_t* cp = codes + (off - head) + lane * 4;
+            const int end = head + len;
+            for (int e0 = 0; e0 < end; e0 += 128) {
+                const int e = e0 + lane * 4;                    // element index relative to the aligned start
                 int c4[4] = {-1, -1, -1, -1};
-                if (e >= head && e + 3 < head + len) {
-                    const int4 v = ld_stream_v4(codes + base + e);
-                    c4[0] = v.x; c4[1] = v.y; c4[2] = v.z; c4[3] = v.w;
+                if (e + 3 < end) {                              // whole vector inside [aligned start, passage end)
+                    const int4 v = ld_stream_v4(cp + e0);
+                    c4[0] = e >= head ? v.x : -1;               // elements before the passage belong to its neighbour
+                    c4[1] = e + 1 >= head ? v.y : -1;
+                    c4[2] = e + 2 >= head ? v.z : -1;
+                    c4[3] = v.w;
+                } else if (e < end) {                           // the passage's last, partial vector
+#pragma unroll
+                    for (int u = 0; u < 3; u++)
+                        if (e + u >= head && e + u < end) c4[u] = ld_stream_s32(cp + e0 + u);
+                }
+                if (USE_IDX) {
+                    bool hit[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        const unsigned code = (unsigned)c4[u];
+                        hit[u] = code < (unsigned)C && ((s_bits[code >> 5] >> (code & 31)) & 1u);
+                    }
+                    if (__any_sync(0xffffffffu, hit[0] | hit[1] | hit[2] | hit[3])) {
+#pragma unroll
+                        for (int u = 0; u < 4; u++)
+                            m = gather_rows<4>(__ballot_sync(0xffffffffu, hit[u]), c4[u], Sb, m);
+                    }
                 } else {
 #pragma unroll
                     for (int u = 0; u < 4; u++)
-                        if (e + u >= head && e + u < head + len) c4[u] = ld_stream_s32(codes + base + e + u);
-                }
-#pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    const int code = c4[u];
-                    bool keep = (unsigned)code < (unsigned)C;
-                    if (USE_IDX) keep = keep && ((__ldg(bits + (code >> 5)) >> (code & 31)) & 1u);
-                    unsigned mask = __ballot_sync(0xffffffffu, keep);
-                    while (mask) {  // four S rows in flight per step
-                        int src[4];
-                        float v[4];
-#pragma unroll
-                        for (int t = 0; t < 4; t++) {
-                            src[t] = mask ? (__ffs(mask) - 1) : -1;
-                            if (mask) mask &= mask - 1;
-                        }
-#pragma unroll
-                        for (int t = 0; t < 4; t++) {
-                            const int c = __shfl_sync(0xffffffffu, code, src[t] < 0 ? 0 : src[t]);
-                            v[t] = (src[t] >= 0) ? __ldg(Sb + (size_t)c * PLAID_NQ_MAX) : -9999.0f;
-                        }
-                        m = fmaxf(fmaxf(m, fmaxf(v[0], v[1])), fmaxf(v[2], v[3]));
-                    }
+                        m = gather_rows<8>(__ballot_sync(0xffffffffu, (unsigned)c4[u] < (unsigned)C), c4[u], Sb, m);
                 }
             }
         }
         s_max[slot][lane] = m;
     }
     __syncthreads();
-    if (warp == 0 && lane < kDocs) {
-        const int i = i0 + lane;
+    const int nq = min(qlens[b], PLAID_NQ_MAX);
+    for (int j = threadIdx.x; j < kDocs; j += blockDim.x) {
+        const int i = i0 + j;
         if (i < n) {
-            const int nq = min(qlens[b], PLAID_NQ_MAX);
             float s = 0.0f;  // sequential fp32 sum in token order (filter_pids.cpp:59-63)
-            for (int k = 0; k < nq; k++) s += s_max[lane][k];
+            for (int k = 0; k < nq; k++) s += s_max[j][k];
             out[(size_t)b * pid_stride + i] = s;
         }
     }
@@ -253,14 +284,27 @@ static int next_pow2(int v) {
 static int launch_approx(const int32_t* pids, const int32_t* counts, int B, int pid_stride, const float* S,
                          const int32_t* qlens, const uint32_t* idx_bits, int C, const int32_t* codes,
                          const int64_t* offsets, float* out, cudaStream_t st) {
+    PLAID_CHECK_ARG((reinterpret_cast<uintptr_t>(codes) & 15) == 0, PLAID_ERR_ARG, "approx_scores: codes must be 16-byte aligned");
     if (idx_bits) {
-        dim3 grid((pid_stride + kApproxWarps * 4 - 1) / (kApproxWarps * 4), B);
-        approx_scores_kernel<true, 4><<<grid, kApproxWarps * 32, 0, st>>>(pids, counts, pid_stride, S, qlens, idx_bits, C,
-                                                                          codes, offsets, out);
+        constexpr int kDocs = kApproxWarps * kStage1Dpw;
+        const size_t smem = (size_t)kDocs * 33 * 4 + (size_t)(C >> 5) * 4;
+        PLAID_CHECK_ARG(smem <= 200 * 1024, PLAID_ERR_UNSUPPORTED, "approx_scores: C=%d pruning bitmap exceeds shared memory", C);
+        PLAID_CHECK_ARG((reinterpret_cast<uintptr_t>(idx_bits) & 15) == 0 && (C % 128) == 0, PLAID_ERR_ARG,
+                        "approx_scores: idx_bits must be 16-byte aligned and C a multiple of 128");
+        static size_t configured = 0;
+        if (smem > 48 * 1024 && smem > configured) {
+            PLAID_CUDA_OK(cudaFuncSetAttribute(approx_scores_kernel<true, kStage1Dpw>,
+                                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            configured = smem;
+        }
+        dim3 grid((pid_stride + kDocs - 1) / kDocs, B);
+        approx_scores_kernel<true, kStage1Dpw><<<grid, kApproxWarps * 32, smem, st>>>(pids, counts, pid_stride, S, qlens,
+                                                                                     idx_bits, C, codes, offsets, out);
     } else {
-        dim3 grid((pid_stride + kApproxWarps - 1) / kApproxWarps, B);
-        approx_scores_kernel<false, 1><<<grid, kApproxWarps * 32, 0, st>>>(pids, counts, pid_stride, S, qlens, nullptr, C,
-                                                                           codes, offsets, out);
+        constexpr int kDocs = kApproxWarps * kStage2Dpw;
+        dim3 grid((pid_stride + kDocs - 1) / kDocs, B);
+        approx_scores_kernel<false, kStage2Dpw><<<grid, kApproxWarps * 32, kDocs * 33 * 4, st>>>(
+            pids, counts, pid_stride, S, qlens, nullptr, C, codes, offsets, out);
     }
     PLAID_LAUNCH_OK("approx_scores_kernel");
     return PLAID_OK;
@@ -292,8 +336,8 @@ extern "C" int plaid_approx_scores(const int32_t* pids, const int32_t* counts, i
     using namespace plaid;
     PLAID_CHECK_ARG(pids && counts && S && qlens && codes && offsets && out_scores, PLAID_ERR_ARG,
                     "plaid_approx_scores: null pointer");
-    PLAID_CHECK_ARG(B >= 0 && pid_stride >= 0 && C > 0 && (C % 32) == 0, PLAID_ERR_ARG,
-                    "plaid_approx_scores: bad sizes (B=%d stride=%d C=%d; C must be a multiple of 32)", B, pid_stride, C);
+    PLAID_CHECK_ARG(B >= 0 && pid_stride >= 0 && C > 0 && (C % 128) == 0, PLAID_ERR_ARG,
+                    "plaid_approx_scores: bad sizes (B=%d stride=%d C=%d; C must be a multiple of 128)", B, pid_stride, C);
     if (B == 0 || pid_stride == 0) return PLAID_OK;
     PLAID_CHECK_ARG(B <= 65535, PLAID_ERR_UNSUPPORTED, "plaid_approx_scores: B=%d > 65535 per call", B);
     return launch_approx(pids, counts, B, pid_stride, S, qlens, idx_bits, C, codes, offsets, out_scores,
@@ -320,7 +364,7 @@ extern "C" int plaid_filter_pids(const int32_t* pids, const int32_t* counts, int
     PLAID_CHECK_ARG(pids && counts && S && qlens && idx_bits && codes && offsets && ws_scores && ws_keys && stage1_pids &&
                         stage1_scores && stage1_counts && stage2_pids && stage2_scores && stage2_counts,
                     PLAID_ERR_ARG, "plaid_filter_pids: null pointer");
-    PLAID_CHECK_ARG(ndocs >= 4 && B >= 0 && pid_stride >= 0 && C > 0 && (C % 32) == 0, PLAID_ERR_ARG,
+    PLAID_CHECK_ARG(ndocs >= 4 && B >= 0 && pid_stride >= 0 && C > 0 && (C % 128) == 0, PLAID_ERR_ARG,
                     "plaid_filter_pids: bad sizes (ndocs=%d B=%d stride=%d C=%d)", ndocs, B, pid_stride, C);
     if (B == 0) return PLAID_OK;
     PLAID_CHECK_ARG(B <= 65535, PLAID_ERR_UNSUPPORTED, "plaid_filter_pids: B=%d > 65535 per call", B);

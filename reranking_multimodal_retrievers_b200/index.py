@@ -160,8 +160,8 @@ class DeviceIndex:
             self.residuals = res[: self.num_embeddings * pd].view(self.num_embeddings, pd)
             self.centroids_f16 = host.centroids.to(dev, torch.float16).contiguous()
             self.num_centroids = int(self.centroids_f16.shape[0])
-            if self.num_centroids % 32:
-                raise ValueError("number of centroids must be a multiple of 32")
+            if self.num_centroids % 128:
+                raise ValueError("number of centroids must be a multiple of 128")
             self.centroids_f32 = self.centroids_f16.float()
             self.centroids_bf16 = ops.to_bf16(self.centroids_f32)
             self.bucket_weights = host.bucket_weights.to(dev, torch.float32).contiguous()

@@ -32,9 +32,12 @@ def _dev():
 
 
 def _cu(t: torch.Tensor, dtype=None) -> torch.Tensor:
-    """contiguous tensor on the current CUDA device (optionally cast)."""
+    """contiguous, 16-byte aligned tensor on the current CUDA device (optionally cast)."""
     t = t.to(device=_dev(), dtype=dtype if dtype is not None else t.dtype, non_blocking=True)
-    return t.contiguous()
+    t = t.contiguous()
+    if t.data_ptr() % 16:   # a view into the middle of a buffer: the kernels use 128-bit loads
+        t = t.clone()
+    return t
 
 
 def _p(t):
