@@ -72,52 +72,89 @@ approx_scores_kernel(const int32_t* __restrict__ pids, const int32_t* __restrict
             s_bits[i] = __ldg(idx_bits + (size_t)b * (C >> 5) + i);
         __syncthreads();
     }
-#pragma unroll 1
-    for (int d = 0; d < DPW; d++) {
-        const int slot = warp * DPW + d;
-        const int i = i0 + slot;
-        float m = -9999.0f;  // filter_pids.cpp:30-33
+    // Passage descriptors of this warp's DPW passages, fetched in one parallel step (lane l <- passage l)
+    // so that the scan below has no pid -> offsets -> codes pointer chase per passage.
+    int64_t my_off = 0;
+    int my_len = 0;
+    if (lane < DPW) {
+        const int i = i0 + warp * DPW + lane;
         if (i < n) {
             const int pid = pids[(size_t)b * pid_stride + i];
-            const int64_t off = offsets[pid];
-            const int len = (int)(offsets[pid + 1] - off);
-            const int head = (int)(off & 3);                    // codes is 16-byte aligned: align the stream down
-            const int32_t* cp = codes + (off - head) + lane * 4;
-            const int end = head + len;
-            for (int e0 = 0; e0 < end; e0 += 128) {
-                const int e = e0 + lane * 4;                    // element index relative to the aligned start
-                int c4[4] = {-1, -1, -1, -1};
-                if (e + 3 < end) {                              // whole vector inside [aligned start, passage end)
-                    const int4 v = ld_stream_v4(cp + e0);
-                    c4[0] = e >= head ? v.x : -1;               // elements before the passage belong to its neighbour
-                    c4[1] = e + 1 >= head ? v.y : -1;
-                    c4[2] = e + 2 >= head ? v.z : -1;
-                    c4[3] = v.w;
-                } else if (e < end) {                           // the passage's last, partial vector
+            my_off = offsets[pid];
+            my_len = (int)(offsets[pid + 1] - my_off);
+        }
+    }
+    constexpr int kVec = 4;  // 128-code vectors fetched up front per passage (covers 512 tokens = doc_maxlen)
+    int cur[kVec][4], nxt[kVec][4];
+    // issue the loads of passage d (codes [off, off+len)) into r; returns its aligned-stream geometry
+    auto fetch = [&](int d, int (&r)[kVec][4], const int32_t*& cp, int& head, int& end) {
+        const int64_t off = __shfl_sync(0xffffffffu, my_off, d);
+        const int len = __shfl_sync(0xffffffffu, my_len, d);
+        head = (int)(off & 3);                              // codes is 16-byte aligned: align the stream down
+        cp = codes + (off - head) + lane * 4;
+        end = len > 0 ? head + len : 0;
 #pragma unroll
-                    for (int u = 0; u < 3; u++)
-                        if (e + u >= head && e + u < end) c4[u] = ld_stream_s32(cp + e0 + u);
-                }
-                if (USE_IDX) {
-                    bool hit[4];
+        for (int v = 0; v < kVec; v++) {
+            const int e = v * 128 + lane * 4;               // element index relative to the aligned start
+            r[v][0] = r[v][1] = r[v][2] = r[v][3] = -1;
+            if (e + 3 < end) {                              // whole vector inside [aligned start, passage end)
+                const int4 x = ld_stream_v4(cp + v * 128);
+                r[v][0] = e >= head ? x.x : -1;             // elements before the passage belong to its neighbour
+                r[v][1] = e + 1 >= head ? x.y : -1;
+                r[v][2] = e + 2 >= head ? x.z : -1;
+                r[v][3] = x.w;
+            } else if (e < end) {                           // the passage's last, partial vector
 #pragma unroll
-                    for (int u = 0; u < 4; u++) {
-                        const unsigned code = (unsigned)c4[u];
-                        hit[u] = code < (unsigned)C && ((s_bits[code >> 5] >> (code & 31)) & 1u);
-                    }
-                    if (__any_sync(0xffffffffu, hit[0] | hit[1] | hit[2] | hit[3])) {
-#pragma unroll
-                        for (int u = 0; u < 4; u++)
-                            m = gather_rows<4>(__ballot_sync(0xffffffffu, hit[u]), c4[u], Sb, m);
-                    }
-                } else {
-#pragma unroll
-                    for (int u = 0; u < 4; u++)
-                        m = gather_rows<8>(__ballot_sync(0xffffffffu, (unsigned)c4[u] < (unsigned)C), c4[u], Sb, m);
-                }
+                for (int u = 0; u < 3; u++)
+                    if (e + u >= head && e + u < end) r[v][u] = ld_stream_s32(cp + v * 128 + u);
             }
         }
-        s_max[slot][lane] = m;
+    };
+    auto scan4 = [&](const int (&c4)[4], float m) -> float {
+        if (USE_IDX) {
+            bool hit[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const unsigned code = (unsigned)c4[u];
+                hit[u] = code < (unsigned)C && ((s_bits[code >> 5] >> (code & 31)) & 1u);
+            }
+            if (__any_sync(0xffffffffu, hit[0] | hit[1] | hit[2] | hit[3])) {
+#pragma unroll
+                for (int u = 0; u < 4; u++) m = gather_rows<4>(__ballot_sync(0xffffffffu, hit[u]), c4[u], Sb, m);
+            }
+        } else {
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+                m = gather_rows<8>(__ballot_sync(0xffffffffu, (unsigned)c4[u] < (unsigned)C), c4[u], Sb, m);
+        }
+        return m;
+    };
+    const int32_t *cp_cur, *cp_nxt;
+    int head_cur, end_cur, head_nxt, end_nxt;
+    fetch(0, cur, cp_cur, head_cur, end_cur);
+#pragma unroll 1
+    for (int d = 0; d < DPW; d++) {
+        if (d + 1 < DPW) fetch(d + 1, nxt, cp_nxt, head_nxt, end_nxt);   // next passage's codes are in flight
+        float m = -9999.0f;  // filter_pids.cpp:30-33
+#pragma unroll
+        for (int v = 0; v < kVec; v++)
+            if (v * 128 < end_cur) m = scan4(cur[v], m);
+        for (int e0 = kVec * 128; e0 < end_cur; e0 += 128) {           // passages longer than 512 tokens
+            const int e = e0 + lane * 4;
+            int c4[4] = {-1, -1, -1, -1};
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+                if (e + u >= head_cur && e + u < end_cur) c4[u] = ld_stream_s32(cp_cur + e0 + u);
+            m = scan4(c4, m);
+        }
+        s_max[warp * DPW + d][lane] = m;
+        if (d + 1 < DPW) {
+#pragma unroll
+            for (int v = 0; v < kVec; v++)
+#pragma unroll
+                for (int u = 0; u < 4; u++) cur[v][u] = nxt[v][u];
+            cp_cur = cp_nxt; head_cur = head_nxt; end_cur = end_nxt;
+        }
     }
     __syncthreads();
     const int nq = min(qlens[b], PLAID_NQ_MAX);
