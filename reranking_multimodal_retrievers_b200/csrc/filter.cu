@@ -84,43 +84,22 @@ approx_scores_kernel(const int32_t* __restrict__ pids, const int32_t* __restrict
             my_len = (int)(offsets[pid + 1] - my_off);
         }
     }
-    constexpr int kVec = 4;  // 128-code vectors fetched up front per passage (covers 512 tokens = doc_maxlen)
-    int cur[kVec][4], nxt[kVec][4];
-    // issue the loads of passage d (codes [off, off+len)) into r; returns its aligned-stream geometry
-    auto fetch = [&](int d, int (&r)[kVec][4], const int32_t*& cp, int& head, int& end) {
-        const int64_t off = __shfl_sync(0xffffffffu, my_off, d);
-        const int len = __shfl_sync(0xffffffffu, my_len, d);
-        head = (int)(off & 3);                              // codes is 16-byte aligned: align the stream down
-        cp = codes + (off - head) + lane * 4;
-        end = len > 0 ? head + len : 0;
-#pragma unroll
-        for (int v = 0; v < kVec; v++) {
-            const int e = v * 128 + lane * 4;               // element index relative to the aligned start
-            r[v][0] = r[v][1] = r[v][2] = r[v][3] = -1;
-            if (e + 3 < end) {                              // whole vector inside [aligned start, passage end)
-                const int4 x = ld_stream_v4(cp + v * 128);
-                r[v][0] = e >= head ? x.x : -1;             // elements before the passage belong to its neighbour
-                r[v][1] = e + 1 >= head ? x.y : -1;
-                r[v][2] = e + 2 >= head ? x.z : -1;
-                r[v][3] = x.w;
-            } else if (e < end) {                           // the passage's last, partial vector
-#pragma unroll
-                for (int u = 0; u < 3; u++)
-                    if (e + u >= head && e + u < end) r[v][u] = ld_stream_s32(cp + v * 128 + u);
-            }
-        }
-    };
+    const uint32_t sbits = smem_u32(s_bits);
+    const unsigned last_word = (unsigned)(C >> 5) - 1u;
+    // four codes of this lane -> survivors' S rows folded into m
     auto scan4 = [&](const int (&c4)[4], float m) -> float {
         if (USE_IDX) {
-            bool hit[4];
+            unsigned hit[4];
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
+            for (int u = 0; u < 4; u++) {   // branch-free probe of the shared-memory bitmap
                 const unsigned code = (unsigned)c4[u];
-                hit[u] = code < (unsigned)C && ((s_bits[code >> 5] >> (code & 31)) & 1u);
+                unsigned w;
+                asm("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(sbits + (min(code >> 5, last_word) << 2)));
+                hit[u] = (code < (unsigned)C ? 1u : 0u) & (w >> (code & 31));
             }
-            if (__any_sync(0xffffffffu, hit[0] | hit[1] | hit[2] | hit[3])) {
+            if (__any_sync(0xffffffffu, (hit[0] | hit[1] | hit[2] | hit[3]) & 1u)) {
 #pragma unroll
-                for (int u = 0; u < 4; u++) m = gather_rows<4>(__ballot_sync(0xffffffffu, hit[u]), c4[u], Sb, m);
+                for (int u = 0; u < 4; u++) m = gather_rows<4>(__ballot_sync(0xffffffffu, hit[u] & 1u), c4[u], Sb, m);
             }
         } else {
 #pragma unroll
@@ -129,32 +108,38 @@ approx_scores_kernel(const int32_t* __restrict__ pids, const int32_t* __restrict
         }
         return m;
     };
-    const int32_t *cp_cur, *cp_nxt;
-    int head_cur, end_cur, head_nxt, end_nxt;
-    fetch(0, cur, cp_cur, head_cur, end_cur);
+    // one 128-code vector of the aligned stream starting at element e0 (lane covers e0+4*lane .. +3)
+    auto load4 = [&](const int32_t* cp, int e0, int head, int end, int (&c4)[4]) {
+        const int e = e0 + lane * 4;
+        c4[0] = c4[1] = c4[2] = c4[3] = -1;
+        if (e + 3 < end) {                              // whole vector inside [aligned start, passage end)
+            const int4 x = ld_stream_v4(cp + e0);
+            c4[0] = e >= head ? x.x : -1;               // elements before the passage belong to its neighbour
+            c4[1] = e + 1 >= head ? x.y : -1;
+            c4[2] = e + 2 >= head ? x.z : -1;
+            c4[3] = x.w;
+        } else if (e < end) {                           // the passage's last, partial vector
+#pragma unroll
+            for (int u = 0; u < 3; u++)
+                if (e + u >= head && e + u < end) c4[u] = ld_stream_s32(cp + e0 + u);
+        }
+    };
 #pragma unroll 1
     for (int d = 0; d < DPW; d++) {
-        if (d + 1 < DPW) fetch(d + 1, nxt, cp_nxt, head_nxt, end_nxt);   // next passage's codes are in flight
+        const int64_t off = __shfl_sync(0xffffffffu, my_off, d);
+        const int len = __shfl_sync(0xffffffffu, my_len, d);
+        const int head = (int)(off & 3);                    // codes is 16-byte aligned: align the stream down
+        const int32_t* cp = codes + (off - head) + lane * 4;
+        const int end = len > 0 ? head + len : 0;
         float m = -9999.0f;  // filter_pids.cpp:30-33
-#pragma unroll
-        for (int v = 0; v < kVec; v++)
-            if (v * 128 < end_cur) m = scan4(cur[v], m);
-        for (int e0 = kVec * 128; e0 < end_cur; e0 += 128) {           // passages longer than 512 tokens
-            const int e = e0 + lane * 4;
-            int c4[4] = {-1, -1, -1, -1};
-#pragma unroll
-            for (int u = 0; u < 4; u++)
-                if (e + u >= head_cur && e + u < end_cur) c4[u] = ld_stream_s32(cp_cur + e0 + u);
-            m = scan4(c4, m);
+        for (int e0 = 0; e0 < end; e0 += 256) {             // two vectors (256 codes) in flight per step
+            int ca[4], cb[4];
+            load4(cp, e0, head, end, ca);
+            load4(cp, e0 + 128, head, end, cb);
+            m = scan4(ca, m);
+            if (e0 + 128 < end) m = scan4(cb, m);
         }
         s_max[warp * DPW + d][lane] = m;
-        if (d + 1 < DPW) {
-#pragma unroll
-            for (int v = 0; v < kVec; v++)
-#pragma unroll
-                for (int u = 0; u < 4; u++) cur[v][u] = nxt[v][u];
-            cp_cur = cp_nxt; head_cur = head_nxt; end_cur = end_nxt;
-        }
     }
     __syncthreads();
     const int nq = min(qlens[b], PLAID_NQ_MAX);
