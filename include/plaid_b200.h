@@ -162,6 +162,17 @@ int plaid_maxsim_packed(const void* Qb_bf16, const int32_t* qlens, int B, int B_
                         const void* D_bf16, const int32_t* tok_offsets, const int32_t* counts, int pid_stride,
                         int tok_stride, int clamp_zero, int aligned32, float* scores, int* watchdog, void* stream);
 
+/* a6 + a7 + a8 fused, the form the search pipeline runs: the passages listed in pids [B, pid_stride]
+ * (counts[b] valid) are decompressed, normalised, rounded to bf16 and contracted with the query on
+ * tcgen05 without the passage embeddings ever existing in HBM (decompressor warps write the B operand
+ * straight into the swizzled shared-memory layout of the UMMA descriptor).  tok_offsets is what
+ * plaid_doc_token_offsets(align = 32) produced for the same pids.  centroids_f16 [C,128] fp16 as stored in
+ * centroids.pt.  scores[b, i] as in plaid_maxsim_packed(clamp_zero = 1). */
+int plaid_maxsim_fused(const void* Qb_bf16, const int32_t* qlens, int B, int B_pad, int Lq_pad,
+                       const int32_t* pids, const int32_t* counts, int pid_stride, const int32_t* tok_offsets,
+                       const int64_t* offsets, const float* W, const uint8_t* residuals, const int32_t* codes,
+                       const void* centroids_f16, int C, int nbits, float* scores, int* watchdog, void* stream);
+
 /* The operator the reference binds as ColBERT.segmented_maxsim (colbert.py:60): scores f32 [T, nq]
  * already computed, lengths i64 [ndocs] -> f32 [ndocs]; zero-initialised running max, then a
  * left-to-right fp32 sum over the nq columns. */

@@ -18,6 +18,7 @@
 // query changes.  B tiles (passage tokens, bf16 [NT x 128]) stream through an NS-stage TMA ring;
 // accumulators are double-buffered in TMEM.
 #include "common.cuh"
+#include "decompress.cuh"
 
 namespace plaid {
 
@@ -41,6 +42,14 @@ struct MsParams {
     int Ld, docs_per_query;
     float* scores_raw;           // optional [n, Ld, Lq_out]
     int Lq_out;
+    // fused decompression (packed + aligned only): the B tiles are produced from the compressed index
+    const int32_t* pids;         // [B, pid_stride] passages to score (local pids)
+    const int64_t* doc_offsets;  // [N+1] token offsets of the index
+    const int32_t* codes;        // [NE]
+    const uint8_t* residuals;    // [NE, 16*nbits]
+    const __half* centroids;     // [C, 128] fp16, exactly centroids.pt
+    const float* wtable;         // [256, 8/nbits]
+    int C;
     // common
     float* scores;
     int groups_per_query, num_items, items_per_cta;
@@ -117,11 +126,203 @@ __device__ __forceinline__ float max32(const uint32_t (&r)[32], float seed) {
 
 __device__ __noinline__ void store_raw(float* dst, float v) { *dst = v; }
 
+// ===================== MMA issuer (one thread) =====================
+// Walks the CTA's work items in order; for every B tile: wait for the stage to be full and for an
+// accumulator buffer to be drained, issue MT x 8 tcgen05.mma (K = 128), commit the stage back to its
+// producer and the accumulator to the epilogue.  The A operand (query) is swapped when the query changes.
+__device__ __forceinline__ void ms_mma_issue(const MsParams& p, MsShared* sh, uint8_t* sA, uint8_t* sB, int b_bytes,
+                                             uint32_t tmem_base, int item_begin, int item_end, int lane) {
+    const int acc_cols = p.MT * p.NT;
+    if (lane == 0) {
+        const uint32_t idesc = umma_idesc_bf16(128, p.NT);
+        int cur_q = -1, a_loads = 0, it_tile = 0;
+        bool ok = true;
+        for (int w = item_begin; ok && w < item_end; w++) {
+            const MsItem it = ms_item(p, w);
+            if (it.nd == 0) continue;
+            if (it.q != cur_q) {
+                if (a_loads > 0) umma_commit(&sh->a_empty);  // every MMA that read the old A has retired
+                if (!mbar_wait(&sh->a_full, a_loads & 1, p.watchdog)) break;
+                cur_q = it.q;
+                a_loads++;
+            }
+            const int ntiles = (it.ntok + p.NT - 1) / p.NT;
+            for (int t = 0; t < ntiles; t++, it_tile++) {
+                const int s = it_tile % p.NS, acc = it_tile & 1;
+                if (!mbar_wait(&sh->tmem_empty[acc], ((it_tile >> 1) & 1) ^ 1, p.watchdog)) { ok = false; break; }
+                if (!mbar_wait(&sh->full[s], (it_tile / p.NS) & 1, p.watchdog)) { ok = false; break; }
+                tc_fence_after();
+                const uint32_t b0 = smem_u32(sB + s * b_bytes);
+                for (int m = 0; m < p.MT; m++) {
+                    const uint32_t a0 = smem_u32(sA + m * 2 * (128 * 128));
+                    const uint32_t d_tmem = tmem_base + acc * acc_cols + m * p.NT;
+#pragma unroll
+                    for (int k = 0; k < 8; k++) {
+                        const uint64_t da = umma_smem_desc_sw128(a0 + (k >> 2) * (128 * 128) + (k & 3) * 32);
+                        const uint64_t db = umma_smem_desc_sw128(b0 + (k >> 2) * (p.NT * 128) + (k & 3) * 32);
+                        umma_bf16(d_tmem, da, db, idesc, k > 0);
+                    }
+                }
+                umma_commit(&sh->empty[s]);
+                umma_commit(&sh->tmem_full[acc]);
+            }
+        }
+    }
+}
+
+// ===================== epilogue: 4 warps, warp = TMEM lane quadrant =====================
 // MODE 0: packed + aligned (the search pipeline: every passage starts on a 32-token boundary of D and its
 //         pad rows are zero, so a 32-column chunk never straddles two passages and -- with the clamp at
 //         0 -- pad columns cannot change a maximum);
 // MODE 1: packed, arbitrary passage boundaries (colbert_score_packed operator);
 // MODE 2: padded with mask (colbert_score operator), optional masked-matrix output.
+template <int MODE>
+__device__ __forceinline__ void ms_epilogue(const MsParams& p, MsShared* sh, uint32_t tmem_base, int item_begin,
+                                            int item_end, int warp, int lane) {
+    const int acc_cols = p.MT * p.NT;
+    const int quad = warp;
+    const float init = p.clamp_zero ? 0.0f : -INFINITY;
+    const uint32_t tmem_lane = tmem_base + ((uint32_t)(quad * 32) << 16);
+    int it_tile = 0, parity = 0;
+    bool ok = true;
+    for (int w = item_begin; ok && w < item_end; w++) {
+        const MsItem it = ms_item(p, w);
+        if (it.nd == 0) continue;
+        const int lq = p.qlens[it.q];
+        float* part = sh->part[parity][quad];
+        if (MODE != 0) {
+            if (lane < kMsGD) part[lane] = 0.0f;
+            __syncwarp();
+        }
+        float runmax[kMsMaxMT];
+        bool rowok[kMsMaxMT], live[kMsMaxMT];
+#pragma unroll
+        for (int m = 0; m < kMsMaxMT; m++) {
+            runmax[m] = init;
+            rowok[m] = (m * 128 + quad * 32 + lane) < lq;
+            live[m] = m < p.MT && (m * 128 + quad * 32) < lq;   // warp-uniform: some lane has a real query token
+        }
+        // passage ends of the item (relative to its first token) held one per lane: lane d+1 = end of passage d
+        int ends_reg = 0x7fffffff;
+        if (lane <= it.nd) ends_reg = it.ends ? (it.ends[lane] - it.ends[0]) : lane * p.Ld;
+        auto doc_end = [&](int d) -> int { return __shfl_sync(0xffffffffu, ends_reg, d + 1); };
+        int doc = 0;
+        int next_end = doc_end(0);
+
+        auto flush_all = [&](int d) {   // MODE 0: one write per passage, all m-tiles folded in
+            float v = 0.0f;
+#pragma unroll
+            for (int m = 0; m < kMsMaxMT; m++) {
+                if (m < p.MT && rowok[m]) v += p.clamp_zero ? fmaxf(runmax[m], 0.0f) : runmax[m];
+                runmax[m] = init;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0) part[d] = v;
+        };
+        auto flush_one = [&](int m, int d) {
+            float v = rowok[m] ? (p.clamp_zero ? fmaxf(runmax[m], 0.0f) : runmax[m]) : 0.0f;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0) part[d] += v;
+            runmax[m] = init;
+        };
+
+        const int ntiles = (it.ntok + p.NT - 1) / p.NT;
+        const int nchunks = p.NT >> 5;
+        for (int t = 0; t < ntiles; t++, it_tile++) {
+            const int acc = it_tile & 1;
+            if (!mbar_wait(&sh->tmem_full[acc], (it_tile >> 1) & 1, p.watchdog)) { ok = false; break; }
+            tc_fence_after();
+            const uint32_t tmem_acc = tmem_lane + acc * acc_cols;
+            for (int ch = 0; ch < nchunks; ch++) {
+                const int tk0 = t * p.NT + ch * 32;       // item-relative token of column 0
+                if (tk0 >= it.ntok) break;
+                if (MODE == 0) {
+                    while (tk0 == next_end && doc + 1 < it.nd) {   // this chunk opens the next passage
+                        flush_all(doc);
+                        doc++;
+                        next_end = doc_end(doc);
+                    }
+#pragma unroll
+                    for (int m = 0; m < kMsMaxMT; m++) {
+                        if (!live[m]) continue;
+                        uint32_t r[32];
+                        tmem_ld_32x32(tmem_acc + m * p.NT + ch * 32, r);
+                        tc_wait_ld();
+                        runmax[m] = max32(r, runmax[m]);
+                    }
+                } else {
+                    const int nv = min(32, it.ntok - tk0);    // valid columns in this chunk
+                    uint32_t mword = 0xffffffffu;
+                    if (MODE == 2) {
+                        const int mb = (lane < nv) ? p.mask[it.row0 + tk0 + lane] : 0;
+                        mword = __ballot_sync(0xffffffffu, mb != 0);
+                    }
+                    const bool fast = (nv == 32) && (next_end >= tk0 + 32) && (mword == 0xffffffffu) &&
+                                      (MODE != 2 || p.scores_raw == nullptr);
+                    int doc_after = doc, end_after = next_end;
+#pragma unroll
+                    for (int m = 0; m < kMsMaxMT; m++) {
+                        if (m >= p.MT) break;
+                        if (fast && !live[m]) continue;
+                        uint32_t r[32];
+                        tmem_ld_32x32(tmem_acc + m * p.NT + ch * 32, r);
+                        tc_wait_ld();
+                        if (fast) {
+                            runmax[m] = max32(r, runmax[m]);
+                        } else {
+                            int d = doc, e = next_end;
+                            const int krow = m * 128 + quad * 32 + lane;
+                            const bool raw = (MODE == 2) && p.scores_raw != nullptr && krow < p.Lq_out;
+#pragma unroll
+                            for (int j = 0; j < 32; j++) {
+                                if (j < nv) {
+                                    while (tk0 + j == e && d + 1 < it.nd) {  // passage d ends before this token
+                                        flush_one(m, d);
+                                        d++;
+                                        e = doc_end(d);
+                                    }
+                                    float v = __uint_as_float(r[j]);
+                                    if (MODE == 2 && !((mword >> j) & 1u)) v = -9999.0f;  // colbert.py:240-241
+                                    if (raw) store_raw(p.scores_raw + (size_t)(it.row0 + tk0 + j) * p.Lq_out + krow, v);
+                                    runmax[m] = fmaxf(runmax[m], v);
+                                }
+                            }
+                            doc_after = d;
+                            end_after = e;
+                        }
+                    }
+                    doc = doc_after;
+                    next_end = end_after;
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sh->tmem_empty[acc]);
+        }
+        // close the passages still open (the last one, plus trailing empty ones)
+        if (MODE == 0) {
+            for (int d = doc; d < it.nd; d++) flush_all(d);
+        } else {
+#pragma unroll
+            for (int m = 0; m < kMsMaxMT; m++) {
+                if (m >= p.MT) break;
+                for (int d = doc; d < it.nd; d++) flush_one(m, d);
+            }
+        }
+        __syncwarp();
+        if (epi_bar_or(!ok)) ok = false;
+        const int te = threadIdx.x;  // 0..127 among the epilogue threads
+        if (te < it.nd) {
+            const float s = ((sh->part[parity][0][te] + sh->part[parity][1][te]) + sh->part[parity][2][te]) +
+                            sh->part[parity][3][te];
+            p.scores[it.out0 + te] = s;
+        }
+        parity ^= 1;
+    }
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(kMsThreads, 1)
 maxsim_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_d, const MsParams p) {
@@ -190,190 +391,165 @@ maxsim_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
             }
         }
     } else if (warp == 7) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
-            const uint32_t idesc = umma_idesc_bf16(128, p.NT);
-            int cur_q = -1, a_loads = 0, it_tile = 0;
-            bool ok = true;
-            for (int w = item_begin; ok && w < item_end; w++) {
-                const MsItem it = ms_item(p, w);
-                if (it.nd == 0) continue;
-                if (it.q != cur_q) {
-                    if (a_loads > 0) umma_commit(&sh->a_empty);  // every MMA that read the old A has retired
-                    if (!mbar_wait(&sh->a_full, a_loads & 1, p.watchdog)) break;
-                    cur_q = it.q;
-                    a_loads++;
-                }
-                const int ntiles = (it.ntok + p.NT - 1) / p.NT;
-                for (int t = 0; t < ntiles; t++, it_tile++) {
-                    const int s = it_tile % p.NS, acc = it_tile & 1;
-                    if (!mbar_wait(&sh->tmem_empty[acc], ((it_tile >> 1) & 1) ^ 1, p.watchdog)) { ok = false; break; }
-                    if (!mbar_wait(&sh->full[s], (it_tile / p.NS) & 1, p.watchdog)) { ok = false; break; }
-                    tc_fence_after();
-                    const uint32_t b0 = smem_u32(sB + s * b_bytes);
-                    for (int m = 0; m < p.MT; m++) {
-                        const uint32_t a0 = smem_u32(sA + m * 2 * (128 * 128));
-                        const uint32_t d_tmem = tmem_base + acc * acc_cols + m * p.NT;
-#pragma unroll
-                        for (int k = 0; k < 8; k++) {
-                            const uint64_t da = umma_smem_desc_sw128(a0 + (k >> 2) * (128 * 128) + (k & 3) * 32);
-                            const uint64_t db = umma_smem_desc_sw128(b0 + (k >> 2) * (p.NT * 128) + (k & 3) * 32);
-                            umma_bf16(d_tmem, da, db, idesc, k > 0);
-                        }
-                    }
-                    umma_commit(&sh->empty[s]);
-                    umma_commit(&sh->tmem_full[acc]);
-                }
-            }
-        }
+        ms_mma_issue(p, sh, sA, sB, b_bytes, tmem_base, item_begin, item_end, lane);
     } else if (warp < 4) {
-        // ===================== epilogue: 4 warps, warp = TMEM lane quadrant =====================
-        const int quad = warp;
-        const float init = p.clamp_zero ? 0.0f : -INFINITY;
-        const uint32_t tmem_lane = tmem_base + ((uint32_t)(quad * 32) << 16);
-        int it_tile = 0, parity = 0;
-        bool ok = true;
-        for (int w = item_begin; ok && w < item_end; w++) {
-            const MsItem it = ms_item(p, w);
-            if (it.nd == 0) continue;
-            const int lq = p.qlens[it.q];
-            float* part = sh->part[parity][quad];
-            if (MODE != 0) {
-                if (lane < kMsGD) part[lane] = 0.0f;
-                __syncwarp();
-            }
-            float runmax[kMsMaxMT];
-            bool rowok[kMsMaxMT], live[kMsMaxMT];
-#pragma unroll
-            for (int m = 0; m < kMsMaxMT; m++) {
-                runmax[m] = init;
-                rowok[m] = (m * 128 + quad * 32 + lane) < lq;
-                live[m] = m < p.MT && (m * 128 + quad * 32) < lq;   // warp-uniform: some lane has a real query token
-            }
-            // passage ends of the item (relative to its first token) held one per lane: lane d+1 = end of passage d
-            int ends_reg = 0x7fffffff;
-            if (lane <= it.nd) ends_reg = it.ends ? (it.ends[lane] - it.ends[0]) : lane * p.Ld;
-            auto doc_end = [&](int d) -> int { return __shfl_sync(0xffffffffu, ends_reg, d + 1); };
-            int doc = 0;
-            int next_end = doc_end(0);
-
-            auto flush_all = [&](int d) {   // MODE 0: one write per passage, all m-tiles folded in
-                float v = 0.0f;
-#pragma unroll
-                for (int m = 0; m < kMsMaxMT; m++) {
-                    if (m < p.MT && rowok[m]) v += p.clamp_zero ? fmaxf(runmax[m], 0.0f) : runmax[m];
-                    runmax[m] = init;
-                }
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-                if (lane == 0) part[d] = v;
-            };
-            auto flush_one = [&](int m, int d) {
-                float v = rowok[m] ? (p.clamp_zero ? fmaxf(runmax[m], 0.0f) : runmax[m]) : 0.0f;
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-                if (lane == 0) part[d] += v;
-                runmax[m] = init;
-            };
-
-            const int ntiles = (it.ntok + p.NT - 1) / p.NT;
-            const int nchunks = p.NT >> 5;
-            for (int t = 0; t < ntiles; t++, it_tile++) {
-                const int acc = it_tile & 1;
-                if (!mbar_wait(&sh->tmem_full[acc], (it_tile >> 1) & 1, p.watchdog)) { ok = false; break; }
-                tc_fence_after();
-                const uint32_t tmem_acc = tmem_lane + acc * acc_cols;
-                for (int ch = 0; ch < nchunks; ch++) {
-                    const int tk0 = t * p.NT + ch * 32;       // item-relative token of column 0
-                    if (tk0 >= it.ntok) break;
-                    if (MODE == 0) {
-                        while (tk0 == next_end && doc + 1 < it.nd) {   // this chunk opens the next passage
-                            flush_all(doc);
-                            doc++;
-                            next_end = doc_end(doc);
-                        }
-#pragma unroll
-                        for (int m = 0; m < kMsMaxMT; m++) {
-                            if (!live[m]) continue;
-                            uint32_t r[32];
-                            tmem_ld_32x32(tmem_acc + m * p.NT + ch * 32, r);
-                            tc_wait_ld();
-                            runmax[m] = max32(r, runmax[m]);
-                        }
-                    } else {
-                        const int nv = min(32, it.ntok - tk0);    // valid columns in this chunk
-                        uint32_t mword = 0xffffffffu;
-                        if (MODE == 2) {
-                            const int mb = (lane < nv) ? p.mask[it.row0 + tk0 + lane] : 0;
-                            mword = __ballot_sync(0xffffffffu, mb != 0);
-                        }
-                        const bool fast = (nv == 32) && (next_end >= tk0 + 32) && (mword == 0xffffffffu) &&
-                                          (MODE != 2 || p.scores_raw == nullptr);
-                        int doc_after = doc, end_after = next_end;
-#pragma unroll
-                        for (int m = 0; m < kMsMaxMT; m++) {
-                            if (m >= p.MT) break;
-                            if (fast && !live[m]) continue;
-                            uint32_t r[32];
-                            tmem_ld_32x32(tmem_acc + m * p.NT + ch * 32, r);
-                            tc_wait_ld();
-                            if (fast) {
-                                runmax[m] = max32(r, runmax[m]);
-                            } else {
-                                int d = doc, e = next_end;
-                                const int krow = m * 128 + quad * 32 + lane;
-                                const bool raw = (MODE == 2) && p.scores_raw != nullptr && krow < p.Lq_out;
-#pragma unroll
-                                for (int j = 0; j < 32; j++) {
-                                    if (j < nv) {
-                                        while (tk0 + j == e && d + 1 < it.nd) {  // passage d ends before this token
-                                            flush_one(m, d);
-                                            d++;
-                                            e = doc_end(d);
-                                        }
-                                        float v = __uint_as_float(r[j]);
-                                        if (MODE == 2 && !((mword >> j) & 1u)) v = -9999.0f;  // colbert.py:240-241
-                                        if (raw) store_raw(p.scores_raw + (size_t)(it.row0 + tk0 + j) * p.Lq_out + krow, v);
-                                        runmax[m] = fmaxf(runmax[m], v);
-                                    }
-                                }
-                                doc_after = d;
-                                end_after = e;
-                            }
-                        }
-                        doc = doc_after;
-                        next_end = end_after;
-                    }
-                }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&sh->tmem_empty[acc]);
-            }
-            // close the passages still open (the last one, plus trailing empty ones)
-            if (MODE == 0) {
-                for (int d = doc; d < it.nd; d++) flush_all(d);
-            } else {
-#pragma unroll
-                for (int m = 0; m < kMsMaxMT; m++) {
-                    if (m >= p.MT) break;
-                    for (int d = doc; d < it.nd; d++) flush_one(m, d);
-                }
-            }
-            __syncwarp();
-            if (epi_bar_or(!ok)) ok = false;
-            const int te = threadIdx.x;  // 0..127 among the epilogue threads
-            if (te < it.nd) {
-                const float s = ((sh->part[parity][0][te] + sh->part[parity][1][te]) + sh->part[parity][2][te]) +
-                                sh->part[parity][3][te];
-                p.scores[it.out0 + te] = s;
-            }
-            parity ^= 1;
-        }
+        ms_epilogue<MODE>(p, sh, tmem_base, item_begin, item_end, warp, lane);
     }
 
     tc_fence_before();
     __syncthreads();
     if (warp == 7) tmem_dealloc(tmem_base, 512);
+}
+
+// =============================================================================================
+// Fused form for the search pipeline: decompress -> normalise -> bf16 -> swizzled smem -> tcgen05.
+// The B operand never exists in HBM.  12 decompressor warps replace the TMA producer: a tile of NT
+// passage tokens is built by NT/32 warps (one 32-row chunk each -- passages are 32-row aligned, so a
+// chunk belongs to one passage and its rows past the passage's end are zero), written straight into the
+// K-major 128B-swizzled layout the UMMA descriptor expects (16-byte chunk c of row r lands at chunk
+// c ^ (r & 7); rows 128 B apart; the two 64-dim k-halves NT*128 B apart), fenced into the async proxy
+// and handed to the MMA thread through the stage's mbarrier.  Each group of NT/32 warps owns one stage.
+// Per token (half-warp, 8 dims per lane): packed residual byte(s) -> weight table (smem) + fp16 centroid
+// row (one 128-bit L2 load) in fp32, sum of squares over the half-warp, rsqrt, bf16 pack, one 128-bit
+// shared-memory store.  Epilogue = MODE 0 (aligned).
+static constexpr int kFusedDecWarps = 12;
+static constexpr int kFusedThreads = (6 + kFusedDecWarps) * 32;   // warps 0-3 epilogue, 4 Q TMA, 5 MMA, 6.. decompress
+
+template <int NBITS>
+__global__ void __launch_bounds__(kFusedThreads, 1)
+maxsim_fused_kernel(const __grid_constant__ CUtensorMap map_q, const MsParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    constexpr int PB = 16 * NBITS;                  // packed residual bytes per token
+    const int a_bytes = p.MT * 128 * kDim * 2;
+    const int b_bytes = p.NT * kDim * 2;
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + a_bytes;                   // [NS][2 k-halves][NT rows][128 B]
+    MsShared* sh = reinterpret_cast<MsShared*>(sB + p.NS * b_bytes);
+    float* sW = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(sh) + ((sizeof(MsShared) + 15) & ~size_t(15)));
+    uint8_t* s_stage = reinterpret_cast<uint8_t*>(sW + 256 * (8 / NBITS));   // [12 warps][32 tokens * PB]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int item_begin = blockIdx.x * p.items_per_cta;
+    const int item_end = min(p.num_items, item_begin + p.items_per_cta);
+    const int wpt = p.NT >> 5;                      // decompressor warps per tile
+
+    if (threadIdx.x == 0) {
+        mbar_init(&sh->a_full, 1);
+        mbar_init(&sh->a_empty, 1);
+        for (int s = 0; s < p.NS; s++) { mbar_init(&sh->full[s], wpt); mbar_init(&sh->empty[s], 1); }
+        for (int a = 0; a < 2; a++) { mbar_init(&sh->tmem_full[a], 1); mbar_init(&sh->tmem_empty[a], 4); }
+        fence_mbar_init();
+    }
+    if (warp == 5) {
+        tmem_alloc(&sh->tmem_base, 512);
+        tmem_relinquish();
+    }
+    for (int i = threadIdx.x; i < 256 * (8 / NBITS); i += blockDim.x) sW[i] = p.wtable[i];
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = sh->tmem_base;
+
+    if (warp < 4) {
+        ms_epilogue<0>(p, sh, tmem_base, item_begin, item_end, warp, lane);
+    } else if (warp == 4) {
+        // ===================== query (A operand) TMA producer =====================
+        if (lane == 0) {
+            tma_prefetch_desc(&map_q);
+            int cur_q = -1, a_loads = 0;
+            for (int w = item_begin; w < item_end; w++) {
+                const MsItem it = ms_item(p, w);
+                if (it.nd == 0 || it.q == cur_q) continue;
+                if (a_loads > 0 && !mbar_wait(&sh->a_empty, (a_loads - 1) & 1, p.watchdog)) break;
+                mbar_expect_tx(&sh->a_full, a_bytes);
+                for (int m = 0; m < p.MT; m++)
+                    for (int h = 0; h < 2; h++)
+                        tma_load_2d(sA + (m * 2 + h) * (128 * 128), &map_q, &sh->a_full, h * 64, it.q * p.Lq_pad + m * 128);
+                cur_q = it.q;
+                a_loads++;
+            }
+        }
+    } else if (warp == 5) {
+        ms_mma_issue(p, sh, sA, sB, b_bytes, tmem_base, item_begin, item_end, lane);
+    } else {
+        // ===================== decompressor warps =====================
+        const int dw = warp - 6;
+        const int group = dw / wpt, cit = dw - group * wpt;   // stage owned by this warp's group, chunk inside the tile
+        const int h = lane & 15, half = lane >> 4;
+        uint8_t* stage_bytes = s_stage + dw * (32 * PB);
+        // byte offset of this lane's 16-byte chunk inside a tile row pair: k-half (h>>3), chunk (h&7) xor (row&7)
+        int it_tile = 0;
+        bool ok = true;
+        for (int w = item_begin; ok && w < item_end; w++) {
+            const MsItem it = ms_item(p, w);
+            if (it.nd == 0) continue;
+            // passage descriptors of the item, one per lane (lane d <- passage d)
+            int64_t my_off = 0;
+            int my_len = 0;
+            if (lane < it.nd) {
+                const int pid = p.pids[it.out0 + lane];
+                my_off = p.doc_offsets[pid];
+                my_len = (int)(p.doc_offsets[pid + 1] - my_off);
+            }
+            int ends_reg = 0x7fffffff;   // aligned start of passage `lane` relative to the item (lane nd = item end)
+            if (lane <= it.nd) ends_reg = it.ends[lane] - it.ends[0];
+            const int ntiles = (it.ntok + p.NT - 1) / p.NT;
+            for (int t = 0; t < ntiles; t++, it_tile++) {
+                if (it_tile % p.NS != group) continue;
+                if (!mbar_wait(&sh->empty[group], ((it_tile / p.NS) & 1) ^ 1, p.watchdog)) { ok = false; break; }
+                const int tk0 = t * p.NT + cit * 32;            // item-relative first row of this warp's chunk
+                if (tk0 < it.ntok) {
+                    const int d = __popc(__ballot_sync(0xffffffffu, ends_reg <= tk0)) - 1;
+                    const int seg = tk0 - __shfl_sync(0xffffffffu, ends_reg, d);
+                    const int64_t tok0 = __shfl_sync(0xffffffffu, my_off, d) + seg;
+                    const int valid = max(0, min(32, __shfl_sync(0xffffffffu, my_len, d) - seg));
+                    // pull the chunk's packed residuals (valid*PB bytes, 128-bit loads) and codes
+#pragma unroll
+                    for (int v = 0; v < NBITS; v++) {
+                        const int byte = v * 512 + lane * 16;
+                        if (byte < valid * PB)
+                            *reinterpret_cast<int4*>(stage_bytes + byte) = ld_stream_v4(p.residuals + tok0 * PB + byte);
+                    }
+                    const int code = (lane < valid) ? ld_stream_s32(p.codes + tok0 + lane) : 0;
+                    __syncwarp();
+                    uint8_t* tile = sB + group * b_bytes + (h >> 3) * (p.NT * 128);
+#pragma unroll 2
+                    for (int j0 = 0; j0 < 32; j0 += 2) {
+                        const int j = j0 + half;
+                        const int jc = min(j, max(valid - 1, 0));
+                        int c = __shfl_sync(0xffffffffu, code, jc);
+                        c = min(max(c, 0), p.C - 1);
+                        float wv[8], ev[8], v[8];
+                        token_weights8<NBITS>(stage_bytes + jc * PB, sW, h, wv);
+                        load_centroid8(p.centroids + (size_t)c * kDim, h, ev);
+                        float ss = 0.f;
+#pragma unroll
+                        for (int i = 0; i < 8; i++) { v[i] = wv[i] + ev[i]; ss = fmaf(v[i], v[i], ss); }
+#pragma unroll
+                        for (int o = 8; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+                        const float inv = (j < valid) ? rsqrtf(fmaxf(ss, 1e-24f)) : 0.0f;   // pad rows are zero
+                        uint32_t pk[4];
+#pragma unroll
+                        for (int i = 0; i < 4; i++) {
+                            __nv_bfloat162 t2 = __floats2bfloat162_rn(v[2 * i] * inv, v[2 * i + 1] * inv);
+                            pk[i] = *reinterpret_cast<uint32_t*>(&t2);
+                        }
+                        const int row = cit * 32 + j;
+                        *reinterpret_cast<uint4*>(tile + row * 128 + (((h & 7) ^ (row & 7)) << 4)) =
+                            make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                    }
+                }
+                fence_proxy_async_smem();      // generic-proxy writes -> visible to the tensor core's async proxy
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sh->full[group]);
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 5) tmem_dealloc(tmem_base, 512);
 }
 
 static int ms_configure(MsParams& p, int Lq_pad) {
@@ -413,7 +589,77 @@ static int ms_launch(const void* Qb, int q_rows, const void* D, uint64_t d_rows,
     return PLAID_OK;
 }
 
+static int ms_launch_fused(const void* Qb, int q_rows, int nbits, MsParams& p, cudaStream_t st) {
+    CUtensorMap map_q;
+    int rc;
+    if ((rc = make_bf16_2d_map(&map_q, Qb, (uint64_t)q_rows, kDim, 128)) != PLAID_OK) return rc;
+    p.NS = kFusedDecWarps / (p.NT >> 5);        // one stage per group of NT/32 decompressor warps
+    const int keys = 8 / nbits;
+    const int smem = 1024 + p.MT * 128 * kDim * 2 + p.NS * p.NT * kDim * 2 + (int)sizeof(MsShared) + 16 + 256 * keys * 4 +
+                     kFusedDecWarps * 32 * 16 * nbits + 64;
+    PLAID_CHECK_ARG(smem <= 227 * 1024, PLAID_ERR_UNSUPPORTED, "maxsim_fused: %d bytes of shared memory needed", smem);
+    const void* fn = nbits == 1 ? (const void*)maxsim_fused_kernel<1> : nbits == 2 ? (const void*)maxsim_fused_kernel<2>
+                   : nbits == 4 ? (const void*)maxsim_fused_kernel<4> : (const void*)maxsim_fused_kernel<8>;
+    static int configured[9] = {0};
+    if (smem > configured[nbits]) {
+        PLAID_CUDA_OK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured[nbits] = smem;
+    }
+    int grid = sm_count();
+    if (grid > p.num_items) grid = p.num_items;
+    p.items_per_cta = (p.num_items + grid - 1) / grid;
+    grid = (p.num_items + p.items_per_cta - 1) / p.items_per_cta;
+    switch (nbits) {
+        case 1: maxsim_fused_kernel<1><<<grid, kFusedThreads, smem, st>>>(map_q, p); break;
+        case 2: maxsim_fused_kernel<2><<<grid, kFusedThreads, smem, st>>>(map_q, p); break;
+        case 4: maxsim_fused_kernel<4><<<grid, kFusedThreads, smem, st>>>(map_q, p); break;
+        default: maxsim_fused_kernel<8><<<grid, kFusedThreads, smem, st>>>(map_q, p); break;
+    }
+    PLAID_LAUNCH_OK("maxsim_fused_kernel");
+    return PLAID_OK;
+}
+
 }  // namespace plaid
+
+extern "C" int plaid_maxsim_fused(const void* Qb_bf16, const int32_t* qlens, int B, int B_pad, int Lq_pad,
+                                  const int32_t* pids, const int32_t* counts, int pid_stride, const int32_t* tok_offsets,
+                                  const int64_t* offsets, const float* W, const uint8_t* residuals, const int32_t* codes,
+                                  const void* centroids_f16, int C, int nbits, float* scores, int* watchdog, void* stream) {
+    using namespace plaid;
+    PLAID_CHECK_ARG(Qb_bf16 && qlens && pids && counts && tok_offsets && offsets && W && residuals && codes && centroids_f16 &&
+                        scores,
+                    PLAID_ERR_ARG, "plaid_maxsim_fused: null pointer");
+    PLAID_CHECK_ARG(B >= 0 && B_pad >= B && pid_stride >= 1 && C > 0 && Lq_pad >= 32 && (Lq_pad % 32) == 0, PLAID_ERR_ARG,
+                    "plaid_maxsim_fused: bad sizes");
+    PLAID_CHECK_ARG(nbits == 1 || nbits == 2 || nbits == 4 || nbits == 8, PLAID_ERR_UNSUPPORTED,
+                    "plaid_maxsim_fused: nbits=%d not in {1,2,4,8}", nbits);
+    PLAID_CHECK_ARG((reinterpret_cast<uintptr_t>(residuals) & 15) == 0 && (reinterpret_cast<uintptr_t>(centroids_f16) & 15) == 0,
+                    PLAID_ERR_ARG, "plaid_maxsim_fused: residuals/centroids must be 16-byte aligned");
+    if (B == 0) return PLAID_OK;
+    MsParams p{};
+    int rc;
+    if ((rc = ms_configure(p, Lq_pad)) != PLAID_OK) return rc;
+    p.qlens = qlens;
+    p.padded = 0;
+    p.aligned = 1;
+    p.tok_offsets = tok_offsets;
+    p.counts = counts;
+    p.pid_stride = pid_stride;
+    p.tok_stride = 0;
+    p.scores = scores;
+    p.clamp_zero = 1;
+    p.watchdog = watchdog;
+    p.pids = pids;
+    p.doc_offsets = offsets;
+    p.codes = codes;
+    p.residuals = residuals;
+    p.centroids = reinterpret_cast<const __half*>(centroids_f16);
+    p.wtable = W;
+    p.C = C;
+    p.groups_per_query = (pid_stride + kMsGD - 1) / kMsGD;
+    p.num_items = B * p.groups_per_query;
+    return ms_launch_fused(Qb_bf16, B_pad * Lq_pad, nbits, p, (cudaStream_t)stream);
+}
 
 extern "C" int plaid_maxsim_packed(const void* Qb_bf16, const int32_t* qlens, int B, int B_pad, int Lq_pad,
                                    const void* D_bf16, const int32_t* tok_offsets, const int32_t* counts, int pid_stride,

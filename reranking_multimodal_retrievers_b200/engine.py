@@ -55,8 +55,11 @@ class StageTaps:
 
 
 class SearchEngine:
-    def __init__(self, index: DeviceIndex, s_budget_bytes: int = 6 << 30, max_chunk: int = 512):
+    def __init__(self, index: DeviceIndex, s_budget_bytes: int = 6 << 30, max_chunk: int = 512, fused: bool = True):
         self.index = index
+        # fused = decompression feeds the tensor cores through shared memory (no passage embeddings in HBM);
+        # the unfused pair of kernels materialises D (bf16) and is what the stage-wise parity taps read
+        self.fused = bool(fused)
         self.s_budget_bytes = int(s_budget_bytes)
         self.max_chunk = int(max_chunk)
         self._ws_key = None
@@ -106,13 +109,18 @@ class SearchEngine:
             s2_pids=e(Bc, nd4, dtype=torch.int32), s2_scores=e(Bc, nd4, dtype=torch.float32),
             s2_counts=e(Bc, dtype=torch.int32),
             tok_offsets=e(Bc, nd4 + 1, dtype=torch.int32),
-            D=e(Bc * tok_stride, 128, dtype=torch.bfloat16),
+            D=None,   # bf16 [Bc * tok_stride, 128], allocated on first use by the unfused path
             scores=e(Bc, nd4, dtype=torch.float32),
             out_pids=e(Bc, k, dtype=torch.int32), out_scores=e(Bc, k, dtype=torch.float32),
             out_counts=e(Bc, dtype=torch.int32),
         )
         self._ws_key, self._ws = key, ws
         return ws
+
+    def _dense_buffer(self, ws, Bc):
+        if ws["D"] is None:
+            ws["D"] = torch.empty(Bc * ws["tok_stride"], 128, device=self.index.device, dtype=torch.bfloat16)
+        return ws["D"]
 
     # ----------------------------------------------------------------------------------- one chunk
     def _flag_ptrs(self):
@@ -121,6 +129,7 @@ class SearchEngine:
     # kernels launched by each C-ABI entry point (memsets are not kernels)
     _LAUNCHES = {"plaid_prepare_queries": 1, "plaid_centroid_scores": 1, "plaid_candidates": 3, "plaid_approx_scores": 1,
                  "plaid_doc_token_offsets": 1, "plaid_decompress_normalize_bf16": 1, "plaid_maxsim_packed": 1,
+                 "plaid_maxsim_fused": 1,
                  "plaid_select_top": 1}
 
     def _call(self, stage, name, *args):
@@ -171,11 +180,17 @@ class SearchEngine:
         nd4 = ws["nd4"]
         call("doc_offsets", "plaid_doc_token_offsets", _p(ws["s2_pids"]), _p(ws["s2_counts"]), b, nd4, _p(ix.offsets),
              32, _p(ws["tok_offsets"]), st)
-        call("decompress", "plaid_decompress_normalize_bf16", _p(ws["s2_pids"]), _p(ws["s2_counts"]), b, nd4, _p(ws["tok_offsets"]),
-             ws["tok_stride"], _p(ix.offsets), _p(ix.weight_table), _p(ix.residuals), _p(ix.codes),
-             _p(ix.centroids_f16), 1, C, ix.nbits, _p(ws["D"]), st)
-        call("maxsim", "plaid_maxsim_packed", _p(ws["Qb"]), _p(ws["qlens"]), b, Bc, Lq_pad, _p(ws["D"]), _p(ws["tok_offsets"]),
-             _p(ws["s2_counts"]), nd4, ws["tok_stride"], 1, 1, _p(ws["scores"]), wd, st)
+        if self.fused and Lq_pad <= 384:
+            call("maxsim_fused", "plaid_maxsim_fused", _p(ws["Qb"]), _p(ws["qlens"]), b, Bc, Lq_pad, _p(ws["s2_pids"]),
+                 _p(ws["s2_counts"]), nd4, _p(ws["tok_offsets"]), _p(ix.offsets), _p(ix.weight_table), _p(ix.residuals),
+                 _p(ix.codes), _p(ix.centroids_f16), C, ix.nbits, _p(ws["scores"]), wd, st)
+        else:
+            D = self._dense_buffer(ws, Bc)
+            call("decompress", "plaid_decompress_normalize_bf16", _p(ws["s2_pids"]), _p(ws["s2_counts"]), b, nd4,
+                 _p(ws["tok_offsets"]), ws["tok_stride"], _p(ix.offsets), _p(ix.weight_table), _p(ix.residuals),
+                 _p(ix.codes), _p(ix.centroids_f16), 1, C, ix.nbits, _p(D), st)
+            call("maxsim", "plaid_maxsim_packed", _p(ws["Qb"]), _p(ws["qlens"]), b, Bc, Lq_pad, _p(D), _p(ws["tok_offsets"]),
+                 _p(ws["s2_counts"]), nd4, ws["tok_stride"], 1, 1, _p(ws["scores"]), wd, st)
         call("topk", "plaid_select_top", _p(ws["s2_pids"]), _p(ws["scores"]), _p(ws["s2_counts"]), b, nd4, k, _p(ws["out_pids"]),
              _p(ws["out_scores"]), _p(ws["out_counts"]), k, _p(ws["ws_keys"]), st)
 

@@ -25,10 +25,10 @@ def pkg():
     return p
 
 
-def _engine(g):
+def _engine(g, fused=True):
     from reranking_multimodal_retrievers_b200.engine import SearchEngine
     from reranking_multimodal_retrievers_b200.index import DeviceIndex
-    return SearchEngine(DeviceIndex(golden_host_index(g)))
+    return SearchEngine(DeviceIndex(golden_host_index(g)), fused=fused)
 
 
 def test_centroid_scores_tcgen05(pkg, golden):
@@ -68,7 +68,7 @@ def test_centroid_scores_tcgen05(pkg, golden):
 def test_pipeline_stagewise_bit_exact_with_injected_table(pkg, golden):
     from reranking_multimodal_retrievers_b200 import ops
     g = golden
-    eng = _engine(g)
+    eng = _engine(g, fused=False)      # the unfused kernel pair materialises D, which this test inspects
     ix = golden_oracle_index(g)
     Q = torch.from_numpy(g["Q"])
     B = Q.shape[0]
@@ -77,6 +77,16 @@ def test_pipeline_stagewise_bit_exact_with_injected_table(pkg, golden):
                                             remove_zero_rows=True, keep_taps=True)
     eng.check_flags()
     t = eng.last_taps
+    # the fused kernel (decompression feeding the tensor cores through shared memory) builds the very same
+    # bf16 operand tiles, so its scores and ranking are bit-identical to the unfused pair's
+    engf = _engine(g, fused=True)
+    pf, sf, cf = engf.search_batch(Q, k=k, ncells=ncells, centroid_score_threshold=thr, ndocs=ndocs,
+                                   remove_zero_rows=True, keep_taps=True)
+    engf.check_flags()
+    assert torch.equal(pf, pids) and torch.equal(sf, scores) and torch.equal(cf, counts)
+    for b in range(B):
+        n2 = int(t.stage2_counts[b])
+        assert torch.equal(engf.last_taps.scores[b, :n2], t.scores[b, :n2])
     for b in range(B):
         q = nonzero_rows(Q[b])
         nq = min(32, q.shape[0])
@@ -116,6 +126,44 @@ def test_pipeline_stagewise_bit_exact_with_injected_table(pkg, golden):
         assert int(pids[b, 0]) == int(g[f"rank_pids_{b}"][0])
         gs = torch.from_numpy(g[f"rank_scores_{b}"])
         assert ((scores[b, :m].cpu() - gs[:m]).abs() <= SCORE_REL_TOL * gs[:m].abs() + 1e-6).all()
+
+
+@pytest.mark.parametrize("nbits,Lq,lo,hi,zero_rows", [(4, 320, 128, 512, 0), (2, 64, 1, 40, 0), (1, 96, 1, 70, 9),
+                                                       (8, 33, 5, 300, 0), (2, 200, 100, 239, 60)])
+def test_search_all_bit_widths_and_query_lengths(pkg, nbits, Lq, lo, hi, zero_rows):
+    """Fused decompress+MaxSim over 1/2/4/8-bit residuals, 1-3 query m-tiles (PreFLMR's 320 tokens),
+    passages of 1..512 tokens, masked (all-zero) query rows -- against the oracle with our table injected."""
+    from reranking_multimodal_retrievers_b200.engine import SearchEngine
+    from reranking_multimodal_retrievers_b200.index import DeviceIndex
+    from reranking_multimodal_retrievers_b200 import synthetic
+    sx = synthetic.make_synthetic_index(1500, lo, hi, nbits, seed=7 * nbits + Lq, num_centroids=512, mode="codes")
+    Q = synthetic.make_queries(sx, 6, Lq, seed=3, zero_rows=zero_rows)
+    ix = po.OracleIndex(centroids=sx.centroids, bucket_weights=sx.bucket_weights, codes=sx.codes, residuals=sx.residuals,
+                        doclens=sx.doclens, ivf=sx.ivf, ivf_lengths=sx.ivf_lengths, nbits=nbits)
+    k, ndocs, ncells, thr = 20, 256, 2, 0.45
+    res = {}
+    for fused in (True, False):
+        eng = SearchEngine(DeviceIndex(sx), fused=fused)
+        res[fused] = eng.search_batch(Q, k=k, ncells=ncells, centroid_score_threshold=thr, ndocs=ndocs,
+                                      remove_zero_rows=True, keep_taps=True)
+        eng.check_flags()
+        t = eng.last_taps
+    for a, c in zip(res[True], res[False]):
+        assert torch.equal(a, c)
+    pids, scores, counts = res[True]
+    for b in range(Q.shape[0]):
+        q = nonzero_rows(Q[b])
+        nq = min(32, q.shape[0])
+        S = t.S[b, :, :nq].cpu().contiguous()
+        r = po.rank(ix, q, ncells, thr, ndocs, S_override=S, taps=True)
+        n2 = int(t.stage2_counts[b])
+        assert torch.equal(t.stage2_pids[b, :n2].cpu(), r["stage2_pids"])
+        sc = t.scores[b, :n2].cpu()
+        assert ((sc - r["scores_unsorted"]).abs() <= SCORE_REL_TOL * r["scores_unsorted"].abs() + 1e-5).all()
+        m = int(counts[b])
+        rp, rs = po.select_top(r["stage2_pids"], sc, k)
+        assert torch.equal(pids[b, :m].cpu(), rp) and torch.equal(scores[b, :m].cpu(), rs)
+        assert int(pids[b, 0]) == int(r["pids"][0])
 
 
 def test_colbert_score_padded_vs_reference(pkg, golden):
