@@ -495,49 +495,95 @@ maxsim_fused_kernel(const __grid_constant__ CUtensorMap map_q, const MsParams p)
             int ends_reg = 0x7fffffff;   // aligned start of passage `lane` relative to the item (lane nd = item end)
             if (lane <= it.nd) ends_reg = it.ends[lane] - it.ends[0];
             const int ntiles = (it.ntok + p.NT - 1) / p.NT;
-            for (int t = 0; t < ntiles; t++, it_tile++) {
-                if (it_tile % p.NS != group) continue;
-                if (!mbar_wait(&sh->empty[group], ((it_tile / p.NS) & 1) ^ 1, p.watchdog)) { ok = false; break; }
-                const int tk0 = t * p.NT + cit * 32;            // item-relative first row of this warp's chunk
+            // geometry of this warp's chunk in tile t: first token in the index arrays and number of real rows
+            auto geom = [&](int t, int64_t& tok0, int& valid) {
+                const int tk0 = t * p.NT + cit * 32;            // item-relative first row of the chunk
+                valid = 0;
+                tok0 = 0;
                 if (tk0 < it.ntok) {
                     const int d = __popc(__ballot_sync(0xffffffffu, ends_reg <= tk0)) - 1;
                     const int seg = tk0 - __shfl_sync(0xffffffffu, ends_reg, d);
-                    const int64_t tok0 = __shfl_sync(0xffffffffu, my_off, d) + seg;
-                    const int valid = max(0, min(32, __shfl_sync(0xffffffffu, my_len, d) - seg));
-                    // pull the chunk's packed residuals (valid*PB bytes, 128-bit loads) and codes
+                    tok0 = __shfl_sync(0xffffffffu, my_off, d) + seg;
+                    valid = max(0, min(32, __shfl_sync(0xffffffffu, my_len, d) - seg));
+                }
+            };
+            // packed residuals (valid*PB bytes, 128-bit loads) and codes of a chunk, into registers
+            auto fetch = [&](int64_t tok0, int valid, int4 (&res)[NBITS], int& code) {
 #pragma unroll
-                    for (int v = 0; v < NBITS; v++) {
-                        const int byte = v * 512 + lane * 16;
-                        if (byte < valid * PB)
-                            *reinterpret_cast<int4*>(stage_bytes + byte) = ld_stream_v4(p.residuals + tok0 * PB + byte);
-                    }
-                    const int code = (lane < valid) ? ld_stream_s32(p.codes + tok0 + lane) : 0;
+                for (int v = 0; v < NBITS; v++) {
+                    const int byte = v * 512 + lane * 16;
+                    res[v] = make_int4(0, 0, 0, 0);
+                    if (byte < valid * PB) res[v] = ld_stream_v4(p.residuals + tok0 * PB + byte);
+                }
+                code = (lane < valid) ? ld_stream_s32(p.codes + tok0 + lane) : 0;
+            };
+            int4 pres[NBITS];
+            int pcode = 0, pvalid = 0, ptile = -1;
+            for (int t = 0; t < ntiles; t++, it_tile++) {
+                if (it_tile % p.NS != group) continue;
+                int4 res[NBITS];
+                int code, valid;
+                if (ptile == t) {                               // prefetched while the previous tile was being built
+#pragma unroll
+                    for (int v = 0; v < NBITS; v++) res[v] = pres[v];
+                    code = pcode;
+                    valid = pvalid;
+                } else {
+                    int64_t tok0;
+                    geom(t, tok0, valid);
+                    fetch(tok0, valid, res, code);
+                }
+                if (t + p.NS < ntiles) {                        // this warp's next chunk of the item: loads in flight now
+                    int64_t ntok0;
+                    geom(t + p.NS, ntok0, pvalid);
+                    fetch(ntok0, pvalid, pres, pcode);
+                    ptile = t + p.NS;
+                }
+                if (!mbar_wait(&sh->empty[group], ((it_tile / p.NS) & 1) ^ 1, p.watchdog)) { ok = false; break; }
+                if (valid > 0) {
+#pragma unroll
+                    for (int v = 0; v < NBITS; v++) *reinterpret_cast<int4*>(stage_bytes + v * 512 + lane * 16) = res[v];
                     __syncwarp();
                     uint8_t* tile = sB + group * b_bytes + (h >> 3) * (p.NT * 128);
-#pragma unroll 2
-                    for (int j0 = 0; j0 < 32; j0 += 2) {
-                        const int j = j0 + half;
-                        const int jc = min(j, max(valid - 1, 0));
-                        int c = __shfl_sync(0xffffffffu, code, jc);
-                        c = min(max(c, 0), p.C - 1);
-                        float wv[8], ev[8], v[8];
-                        token_weights8<NBITS>(stage_bytes + jc * PB, sW, h, wv);
-                        load_centroid8(p.centroids + (size_t)c * kDim, h, ev);
-                        float ss = 0.f;
+#pragma unroll 1
+                    for (int jb = 0; jb < 32; jb += 16) {       // 8 token pairs per batch: 8 centroid rows in flight
+                        uint4 cent[8];
 #pragma unroll
-                        for (int i = 0; i < 8; i++) { v[i] = wv[i] + ev[i]; ss = fmaf(v[i], v[i], ss); }
-#pragma unroll
-                        for (int o = 8; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-                        const float inv = (j < valid) ? rsqrtf(fmaxf(ss, 1e-24f)) : 0.0f;   // pad rows are zero
-                        uint32_t pk[4];
-#pragma unroll
-                        for (int i = 0; i < 4; i++) {
-                            __nv_bfloat162 t2 = __floats2bfloat162_rn(v[2 * i] * inv, v[2 * i + 1] * inv);
-                            pk[i] = *reinterpret_cast<uint32_t*>(&t2);
+                        for (int u = 0; u < 8; u++) {
+                            const int jc = min(jb + 2 * u + half, valid - 1);
+                            int c = __shfl_sync(0xffffffffu, code, jc);
+                            c = min(max(c, 0), p.C - 1);
+                            cent[u] = __ldg(reinterpret_cast<const uint4*>(p.centroids + (size_t)c * kDim) + h);
                         }
-                        const int row = cit * 32 + j;
-                        *reinterpret_cast<uint4*>(tile + row * 128 + (((h & 7) ^ (row & 7)) << 4)) =
-                            make_uint4(pk[0], pk[1], pk[2], pk[3]);
+#pragma unroll
+                        for (int u = 0; u < 8; u++) {
+                            const int j = jb + 2 * u + half;
+                            const int jc = min(j, valid - 1);
+                            float wv[8], v[8];
+                            token_weights8<NBITS>(stage_bytes + jc * PB, sW, h, wv);
+                            const uint32_t cu[4] = {cent[u].x, cent[u].y, cent[u].z, cent[u].w};
+                            float ss = 0.f;
+#pragma unroll
+                            for (int i = 0; i < 4; i++) {
+                                const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&cu[i]));
+                                v[2 * i] = wv[2 * i] + f.x;
+                                v[2 * i + 1] = wv[2 * i + 1] + f.y;
+                            }
+#pragma unroll
+                            for (int i = 0; i < 8; i++) ss = fmaf(v[i], v[i], ss);
+#pragma unroll
+                            for (int o = 8; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+                            const float inv = (j < valid) ? rsqrtf(fmaxf(ss, 1e-24f)) : 0.0f;   // pad rows are zero
+                            uint32_t pk[4];
+#pragma unroll
+                            for (int i = 0; i < 4; i++) {
+                                __nv_bfloat162 t2 = __floats2bfloat162_rn(v[2 * i] * inv, v[2 * i + 1] * inv);
+                                pk[i] = *reinterpret_cast<uint32_t*>(&t2);
+                            }
+                            const int row = cit * 32 + j;
+                            *reinterpret_cast<uint4*>(tile + row * 128 + (((h & 7) ^ (row & 7)) << 4)) =
+                                make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                        }
                     }
                 }
                 fence_proxy_async_smem();      // generic-proxy writes -> visible to the tensor core's async proxy
