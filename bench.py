@@ -144,6 +144,7 @@ def main():
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--cpu-budget-s", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-fused", action="store_true", help="materialise bf16 passage embeddings (unfused decompress + MaxSim)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -199,7 +200,7 @@ def main():
     sx, Qdev = build_workload(w, rank, dev)
     index = DeviceIndex(sx, dev)
     index.pid_base = rank * w["N"]                      # this rank's shard of the N*world passage collection
-    eng = SearchEngine(index)
+    eng = SearchEngine(index, fused=not args.no_fused)
     B, Lq, k = w["B"], w["Lq"], w["k"]
     Qhost = Qdev.cpu().pin_memory()
     out_host = (torch.empty(B, k, dtype=torch.int32).pin_memory(), torch.empty(B, k, dtype=torch.float32).pin_memory(),
@@ -295,6 +296,7 @@ def main():
         "filter_stage2": dict(bytes=4.0 * T2 + 16.0 * 1024 * B + 128.0 * T2, flops=0.0),
         "decompress": dict(bytes=(4.0 + 16 * nbits + 256.0 + 256.0) * T3, flops=0.0),   # codes+residual+f16 centroid row in, bf16 out
         "maxsim": dict(bytes=256.0 * T3, flops=2.0 * Lq * 128 * T3),
+        "maxsim_fused": dict(bytes=(4.0 + 16 * nbits) * T3, flops=2.0 * Lq * 128 * T3),    # K4' of SURVEY 8d
     }
     kernels = {}
     for stage, v in stage_ms.items():

@@ -61,7 +61,7 @@ __device__ __forceinline__ void decompress_passage(int64_t tok0, int len, const 
             int c = __shfl_sync(0xffffffffu, code, j);
             c = min(max(c, 0), C - 1);
             float w[8], e[8], v[8];
-            token_weights8<NBITS>(stage + j * PB, sW, h, w);
+            token_weights8<NBITS>(smem_u32(stage) + j * PB, smem_u32(sW), h, w);
             load_centroid8(centroids + (size_t)c * kDim, h, e);
 #pragma unroll
             for (int i = 0; i < 8; i++) v[i] = w[i] + e[i];

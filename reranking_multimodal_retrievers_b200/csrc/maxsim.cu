@@ -477,7 +477,8 @@ maxsim_fused_kernel(const __grid_constant__ CUtensorMap map_q, const MsParams p)
         const int dw = warp - 6;
         const int group = dw / wpt, cit = dw - group * wpt;   // stage owned by this warp's group, chunk inside the tile
         const int h = lane & 15, half = lane >> 4;
-        uint8_t* stage_bytes = s_stage + dw * (32 * PB);
+        const uint32_t stage_sa = smem_u32(s_stage + dw * (32 * PB));   // this warp's residual staging area
+        const uint32_t sW_sa = smem_u32(sW);
         // byte offset of this lane's 16-byte chunk inside a tile row pair: k-half (h>>3), chunk (h&7) xor (row&7)
         int it_tile = 0;
         bool ok = true;
@@ -542,9 +543,10 @@ maxsim_fused_kernel(const __grid_constant__ CUtensorMap map_q, const MsParams p)
                 if (!mbar_wait(&sh->empty[group], ((it_tile / p.NS) & 1) ^ 1, p.watchdog)) { ok = false; break; }
                 if (valid > 0) {
 #pragma unroll
-                    for (int v = 0; v < NBITS; v++) *reinterpret_cast<int4*>(stage_bytes + v * 512 + lane * 16) = res[v];
+                    for (int v = 0; v < NBITS; v++)
+                        sts_v4u32(stage_sa + v * 512 + lane * 16, res[v].x, res[v].y, res[v].z, res[v].w);
                     __syncwarp();
-                    uint8_t* tile = sB + group * b_bytes + (h >> 3) * (p.NT * 128);
+                    const uint32_t tile_sa = smem_u32(sB + group * b_bytes + (h >> 3) * (p.NT * 128));
 #pragma unroll 1
                     for (int jb = 0; jb < 32; jb += 16) {       // 8 token pairs per batch: 8 centroid rows in flight
                         uint4 cent[8];
@@ -560,7 +562,7 @@ maxsim_fused_kernel(const __grid_constant__ CUtensorMap map_q, const MsParams p)
                             const int j = jb + 2 * u + half;
                             const int jc = min(j, valid - 1);
                             float wv[8], v[8];
-                            token_weights8<NBITS>(stage_bytes + jc * PB, sW, h, wv);
+                            token_weights8<NBITS>(stage_sa + jc * PB, sW_sa, h, wv);
                             const uint32_t cu[4] = {cent[u].x, cent[u].y, cent[u].z, cent[u].w};
                             float ss = 0.f;
 #pragma unroll
@@ -581,8 +583,7 @@ maxsim_fused_kernel(const __grid_constant__ CUtensorMap map_q, const MsParams p)
                                 pk[i] = *reinterpret_cast<uint32_t*>(&t2);
                             }
                             const int row = cit * 32 + j;
-                            *reinterpret_cast<uint4*>(tile + row * 128 + (((h & 7) ^ (row & 7)) << 4)) =
-                                make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                            sts_v4u32(tile_sa + row * 128 + (((h & 7) ^ (row & 7)) << 4), pk[0], pk[1], pk[2], pk[3]);
                         }
                     }
                 }
