@@ -403,7 +403,7 @@ maxsim_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
 
 // =============================================================================================
 // Fused form for the search pipeline: decompress -> normalise -> bf16 -> swizzled smem -> tcgen05.
-// The B operand never exists in HBM.  12 decompressor warps replace the TMA producer: a tile of NT
+// The B operand never exists in HBM.  16 decompressor warps replace the TMA producer: a tile of NT
 // passage tokens is built by NT/32 warps (one 32-row chunk each -- passages are 32-row aligned, so a
 // chunk belongs to one passage and its rows past the passage's end are zero), written straight into the
 // K-major 128B-swizzled layout the UMMA descriptor expects (16-byte chunk c of row r lands at chunk
@@ -412,7 +412,7 @@ maxsim_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
 // Per token (half-warp, 8 dims per lane): packed residual byte(s) -> weight table (smem) + fp16 centroid
 // row (one 128-bit L2 load) in fp32, sum of squares over the half-warp, rsqrt, bf16 pack, one 128-bit
 // shared-memory store.  Epilogue = MODE 0 (aligned).
-static constexpr int kFusedDecWarps = 12;
+static constexpr int kFusedDecWarps = 16;
 static constexpr int kFusedThreads = (6 + kFusedDecWarps) * 32;   // warps 0-3 epilogue, 4 Q TMA, 5 MMA, 6.. decompress
 
 template <int NBITS>
@@ -427,7 +427,7 @@ maxsim_fused_kernel(const __grid_constant__ CUtensorMap map_q, const MsParams p)
     uint8_t* sB = smem + a_bytes;                   // [NS][2 k-halves][NT rows][128 B]
     MsShared* sh = reinterpret_cast<MsShared*>(sB + p.NS * b_bytes);
     float* sW = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(sh) + ((sizeof(MsShared) + 15) & ~size_t(15)));
-    uint8_t* s_stage = reinterpret_cast<uint8_t*>(sW + 256 * (8 / NBITS));   // [12 warps][32 tokens * PB]
+    uint8_t* s_stage = reinterpret_cast<uint8_t*>(sW + 256 * (8 / NBITS));   // [kFusedDecWarps][32 tokens * PB]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int item_begin = blockIdx.x * p.items_per_cta;
@@ -476,6 +476,7 @@ maxsim_fused_kernel(const __grid_constant__ CUtensorMap map_q, const MsParams p)
         // ===================== decompressor warps =====================
         const int dw = warp - 6;
         const int group = dw / wpt, cit = dw - group * wpt;   // stage owned by this warp's group, chunk inside the tile
+        if (group >= p.NS) goto done;                          // more warps than stages fit in shared memory: idle
         const int h = lane & 15, half = lane >> 4;
         const uint32_t stage_sa = smem_u32(s_stage + dw * (32 * PB));   // this warp's residual staging area
         const uint32_t sW_sa = smem_u32(sW);
@@ -594,6 +595,7 @@ maxsim_fused_kernel(const __grid_constant__ CUtensorMap map_q, const MsParams p)
         }
     }
 
+done:
     tc_fence_before();
     __syncthreads();
     if (warp == 5) tmem_dealloc(tmem_base, 512);
@@ -640,11 +642,15 @@ static int ms_launch_fused(const void* Qb, int q_rows, int nbits, MsParams& p, c
     CUtensorMap map_q;
     int rc;
     if ((rc = make_bf16_2d_map(&map_q, Qb, (uint64_t)q_rows, kDim, 128)) != PLAID_OK) return rc;
-    p.NS = kFusedDecWarps / (p.NT >> 5);        // one stage per group of NT/32 decompressor warps
-    const int keys = 8 / nbits;
-    const int smem = 1024 + p.MT * 128 * kDim * 2 + p.NS * p.NT * kDim * 2 + (int)sizeof(MsShared) + 16 + 256 * keys * 4 +
-                     kFusedDecWarps * 32 * 16 * nbits + 64;
-    PLAID_CHECK_ARG(smem <= 227 * 1024, PLAID_ERR_UNSUPPORTED, "maxsim_fused: %d bytes of shared memory needed", smem);
+    // one stage per group of NT/32 decompressor warps; as many groups as shared memory allows (spare warps idle)
+    const int keys = 8 / nbits, wpt = p.NT >> 5;
+    const int fixed = 1024 + p.MT * 128 * kDim * 2 + (int)sizeof(MsShared) + 16 + 256 * keys * 4 + 64;
+    const int per_stage = p.NT * kDim * 2 + wpt * 32 * 16 * nbits;
+    p.NS = (227 * 1024 - fixed) / per_stage;
+    if (p.NS > kFusedDecWarps / wpt) p.NS = kFusedDecWarps / wpt;
+    if (p.NS > kMsMaxStages) p.NS = kMsMaxStages;
+    PLAID_CHECK_ARG(p.NS >= 2, PLAID_ERR_UNSUPPORTED, "maxsim_fused: shared memory too small for Lq_pad=%d, nbits=%d", p.Lq_pad, nbits);
+    const int smem = fixed + p.NS * per_stage;
     const void* fn = nbits == 1 ? (const void*)maxsim_fused_kernel<1> : nbits == 2 ? (const void*)maxsim_fused_kernel<2>
                    : nbits == 4 ? (const void*)maxsim_fused_kernel<4> : (const void*)maxsim_fused_kernel<8>;
     static int configured[9] = {0};
