@@ -59,7 +59,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -138,7 +138,7 @@ def run_cpu_sample(cs, Q, k, budget_s, max_queries, warm=True):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
@@ -188,6 +188,10 @@ def main():
 
     # ------------------------------------------------------------------ our arm
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback)"
+    # stdout carries exactly ONE JSON line: anything libraries print there (NCCL's version banner) goes to stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     import torch.distributed as dist
@@ -268,7 +272,8 @@ def main():
     eng.events = []
     l0 = eng.launch_count
     sampler = ClockSampler(local_rank)
-    ms_total, clocks = timed(lambda: step(Qdev), args.steps, sampler)
+    sampler.start()                                     # runs through both timed regions
+    ms_total, _ = timed(lambda: step(Qdev), args.steps)
     launches = eng.launch_count - l0
     events, eng.events = eng.events, None
     stage_ms = {}
@@ -279,6 +284,7 @@ def main():
     for _ in range(2):
         step_e2e()
     ms_e2e, _ = timed(step_e2e, args.steps)
+    clocks = sampler.stop()
 
     if rank != 0:
         if world > 1:
@@ -340,7 +346,9 @@ def main():
                                 "kind": r["kind"], "queries_per_s": r["queries"] / r["seconds"],
                                 "sample": f"first {r['queries']} of the step's {B} queries, same index, {r['seconds']:.1f} s",
                                 "stage_share": r["stage_share"]}
-    print(json.dumps(line))
+    sys.stdout.flush()
+    os.dup2(real_stdout, 1)
+    print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
