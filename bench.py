@@ -33,6 +33,9 @@ WORKLOADS = {
     "cfg2": dict(N=112_000, lo=120, hi=239, nbits=2, B=1024, Lq=64, k=100,
                  desc="OK-VQA GS-112K-shaped synthetic index (112k passages, ~180 tok/passage, nbits=2), "
                       "1024 FLMR queries (32+32 tokens), k=100"),
+    "cfg4shard": dict(N=1_250_000, lo=120, hi=239, nbits=2, B=1024, Lq=64, k=100, C=524_288,
+                      desc="one 1/8 shard (1.25M passages) of the 10M-passage index, C=524288 centroids of the full index, "
+                           "nbits=2, 1024 FLMR queries, k=100"),
     "cfg3": dict(N=100_000, lo=128, hi=512, nbits=4, B=256, Lq=320, k=100,
                  desc="E-VQA/InfoSeek-shaped 100k-passage index, nbits=4, 256 PreFLMR 320-token queries, k=100"),
 }
@@ -100,7 +103,7 @@ def build_workload(w, rank, device):
     import torch
     from reranking_multimodal_retrievers_b200 import synthetic
     sx = synthetic.make_synthetic_index(w["N"], w["lo"], w["hi"], w["nbits"], seed=1234 + 17 * rank, mode="codes",
-                                        device=device)
+                                        device=device, num_centroids=w.get("C"))
     Q = synthetic.make_queries(sx, w["B"], w["Lq"], seed=99)      # same queries on every rank
     return sx, Q.to(torch.float32)
 
@@ -300,6 +303,7 @@ def main():
         "centroid_scores": dict(bytes=4.0 * C * 32 * B + 2.0 * C * 128 * chunks, flops=2.0 * C * 128 * 32 * B),
         "filter_stage1": dict(bytes=4.0 * T1 + 16.0 * ncand, flops=0.0),
         "filter_stage2": dict(bytes=4.0 * T2 + 16.0 * 1024 * B + 128.0 * T2, flops=0.0),
+        "candidates": dict(bytes=4.0 * ncand + (w["N"] / 8.0) * B * 2, flops=0.0),
         "decompress": dict(bytes=(4.0 + 16 * nbits + 256.0 + 256.0) * T3, flops=0.0),   # codes+residual+f16 centroid row in, bf16 out
         "maxsim": dict(bytes=256.0 * T3, flops=2.0 * Lq * 128 * T3),
         "maxsim_fused": dict(bytes=(4.0 + 16 * nbits) * T3, flops=2.0 * Lq * 128 * T3),    # K4' of SURVEY 8d
@@ -318,10 +322,20 @@ def main():
     dom = max((s for s in kernels if s in alg), key=lambda s: kernels[s]["ms_per_step"])
     nl = kernels[dom]["launches_per_step"]
     per_launch_s = kernels[dom]["ms_per_step"] * 1e-3 / nl
-    roofline = {"kernel": dom, "bound": "hbm", "achieved": round(alg[dom]["bytes"] / nl / per_launch_s / 1e9, 1),
-                "peak": peaks["hbm"], "unit": "GB/s", "peak_source": peaks["source"] + " (sustained: timed inside the step)",
-                "traffic": None, "algorithmic_bytes_per_launch": alg[dom]["bytes"] / nl,
-                "avg_launch_ms": round(per_launch_s * 1e3, 4)}
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")        # dram bytes per launch from `ncu --set full`
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get(args.workload, {}).get(dom)
+    if dom == "maxsim_fused":    # intensity 2*Lq*128/(4+16*nbits) flop/B >> ridge: tensor roofline
+        roofline = {"kernel": dom, "bound": "tensor", "achieved": round(alg[dom]["flops"] / nl / per_launch_s / 1e12, 2),
+                    "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
+                    "peak_source": peaks["source"] + " (sustained: timed inside the step)", "traffic": traffic,
+                    "algorithmic_flops_per_launch": alg[dom]["flops"] / nl, "avg_launch_ms": round(per_launch_s * 1e3, 4)}
+    else:
+        roofline = {"kernel": dom, "bound": "hbm", "achieved": round(alg[dom]["bytes"] / nl / per_launch_s / 1e9, 1),
+                    "peak": peaks["hbm"], "unit": "GB/s",
+                    "peak_source": peaks["source"] + " (sustained: timed inside the step)", "traffic": traffic,
+                    "algorithmic_bytes_per_launch": alg[dom]["bytes"] / nl, "avg_launch_ms": round(per_launch_s * 1e3, 4)}
     roofline["frac"] = round(roofline["achieved"] / roofline["peak"], 4)
 
     tok_s = world * T3 / (ms_step * 1e-3)               # every rank exact-scores ~T3 tokens of its own shard

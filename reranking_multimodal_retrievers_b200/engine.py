@@ -85,7 +85,7 @@ class SearchEngine:
         dev = ix.device
         C, N = ix.num_centroids, ix.num_passages
         tiles = (C + 255) // 256
-        csplit = max(1, min(tiles, -(-2 * 148 // (Bc // 4))))
+        csplit = max(1, min(tiles, 32, -(-2 * 148 // (Bc // 4))))   # ~2 CTAs per SM; at most 64 partial cell lists
         nlists = 2 * csplit
         nd4 = ndocs // 4
         cand_stride = max(ndocs, min(N, NQ_MAX * ncells * max(ix.max_ivf_len, 1)))
