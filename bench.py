@@ -39,6 +39,8 @@ WORKLOADS = {
     "cfg5": dict(B=4096, dpq=100, Ld=240, lo=120, hi=239, Lq=64, rerank=True,
                  desc="exhaustive uncompressed MaxSim rerank of top-100 candidates per query, 4096 queries, bf16 passage "
                       "embeddings [409600, 240, 128] (lengths U{120..239}), Lq=64"),
+    "cfg5small": dict(B=512, dpq=100, Ld=240, lo=120, hi=239, Lq=64, rerank=True,
+                      desc="cfg5 shape at 512 queries (profiling size)"),
     "cfg3": dict(N=100_000, lo=128, hi=512, nbits=4, B=256, Lq=320, k=100,
                  desc="E-VQA/InfoSeek-shaped 100k-passage index, nbits=4, 256 PreFLMR 320-token queries, k=100"),
 }

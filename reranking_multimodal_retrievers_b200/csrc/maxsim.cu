@@ -232,6 +232,16 @@ __device__ __forceinline__ void ms_epilogue(const MsParams& p, MsShared* sh, uin
         const int nchunks = p.NT >> 5;
         for (int t = 0; t < ntiles; t++, it_tile++) {
             const int acc = it_tile & 1;
+            // padded form: the tile's mask bytes (lane <- token 32*ch + lane of each chunk) are requested before
+            // the wait on the accumulator, so their latency hides behind the MMA
+            int mbyte[4] = {0, 0, 0, 0};
+            if (MODE == 2) {
+#pragma unroll
+                for (int ch = 0; ch < 4; ch++) {
+                    const int tk = t * p.NT + ch * 32 + lane;
+                    if (ch * 32 < p.NT && tk < it.ntok) mbyte[ch] = p.mask[it.row0 + tk];
+                }
+            }
             if (!mbar_wait(&sh->tmem_full[acc], (it_tile >> 1) & 1, p.watchdog)) { ok = false; break; }
             tc_fence_after();
             const uint32_t tmem_acc = tmem_lane + acc * acc_cols;
@@ -256,21 +266,34 @@ __device__ __forceinline__ void ms_epilogue(const MsParams& p, MsShared* sh, uin
                     const int nv = min(32, it.ntok - tk0);    // valid columns in this chunk
                     uint32_t mword = 0xffffffffu;
                     if (MODE == 2) {
-                        const int mb = (lane < nv) ? p.mask[it.row0 + tk0 + lane] : 0;
+                        const int mb = ch == 0 ? mbyte[0] : ch == 1 ? mbyte[1] : ch == 2 ? mbyte[2] : mbyte[3];
                         mword = __ballot_sync(0xffffffffu, mb != 0);
                     }
-                    const bool fast = (nv == 32) && (next_end >= tk0 + 32) && (mword == 0xffffffffu) &&
-                                      (MODE != 2 || p.scores_raw == nullptr);
+                    // whole chunk inside the current passage and no per-element side effects wanted
+                    const bool plain = (nv == 32) && (next_end >= tk0 + 32) && (MODE != 2 || p.scores_raw == nullptr);
+                    const bool fast = plain && (mword == 0xffffffffu);
+                    if (plain && mword == 0u) {           // a fully padded chunk: every column counts as -9999
+#pragma unroll
+                        for (int m = 0; m < kMsMaxMT; m++)
+                            if (live[m]) runmax[m] = fmaxf(runmax[m], -9999.0f);
+                        continue;
+                    }
                     int doc_after = doc, end_after = next_end;
 #pragma unroll
                     for (int m = 0; m < kMsMaxMT; m++) {
                         if (m >= p.MT) break;
-                        if (fast && !live[m]) continue;
+                        if (plain && !live[m]) continue;
                         uint32_t r[32];
                         tmem_ld_32x32(tmem_acc + m * p.NT + ch * 32, r);
                         tc_wait_ld();
                         if (fast) {
                             runmax[m] = max32(r, runmax[m]);
+                        } else if (plain) {               // partially padded chunk: select, then max
+                            float a = runmax[m];
+#pragma unroll
+                            for (int j = 0; j < 32; j++)
+                                a = fmaxf(a, ((mword >> j) & 1u) ? __uint_as_float(r[j]) : -9999.0f);
+                            runmax[m] = a;
                         } else {
                             int d = doc, e = next_end;
                             const int krow = m * 128 + quad * 32 + lane;
