@@ -124,8 +124,6 @@ __device__ __forceinline__ float max32(const uint32_t (&r)[32], float seed) {
     return a;
 }
 
-__device__ __noinline__ void store_raw(float* dst, float v) { *dst = v; }
-
 // ===================== MMA issuer (one thread) =====================
 // Walks the CTA's work items in order; for every B tile: wait for the stage to be full and for an
 // accumulator buffer to be drained, issue MT x 8 tcgen05.mma (K = 128), commit the stage back to its
@@ -190,10 +188,6 @@ __device__ __forceinline__ void ms_epilogue(const MsParams& p, MsShared* sh, uin
         if (it.nd == 0) continue;
         const int lq = p.qlens[it.q];
         float* part = sh->part[parity][quad];
-        if (MODE != 0) {
-            if (lane < kMsGD) part[lane] = 0.0f;
-            __syncwarp();
-        }
         float runmax[kMsMaxMT];
         bool rowok[kMsMaxMT], live[kMsMaxMT];
 #pragma unroll
@@ -209,7 +203,7 @@ __device__ __forceinline__ void ms_epilogue(const MsParams& p, MsShared* sh, uin
         int doc = 0;
         int next_end = doc_end(0);
 
-        auto flush_all = [&](int d) {   // MODE 0: one write per passage, all m-tiles folded in
+        auto flush_all = [&](int d) {   // one write per passage, all m-tiles folded in
             float v = 0.0f;
 #pragma unroll
             for (int m = 0; m < kMsMaxMT; m++) {
@@ -219,13 +213,6 @@ __device__ __forceinline__ void ms_epilogue(const MsParams& p, MsShared* sh, uin
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
             if (lane == 0) part[d] = v;
-        };
-        auto flush_one = [&](int m, int d) {
-            float v = rowok[m] ? (p.clamp_zero ? fmaxf(runmax[m], 0.0f) : runmax[m]) : 0.0f;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            if (lane == 0) part[d] += v;
-            runmax[m] = init;
         };
 
         const int ntiles = (it.ntok + p.NT - 1) / p.NT;
@@ -278,62 +265,55 @@ __device__ __forceinline__ void ms_epilogue(const MsParams& p, MsShared* sh, uin
                             if (live[m]) runmax[m] = fmaxf(runmax[m], -9999.0f);
                         continue;
                     }
-                    int doc_after = doc, end_after = next_end;
+                    if (plain) {
 #pragma unroll
                     for (int m = 0; m < kMsMaxMT; m++) {
-                        if (m >= p.MT) break;
-                        if (plain && !live[m]) continue;
+                        if (!live[m]) continue;
                         uint32_t r[32];
                         tmem_ld_32x32(tmem_acc + m * p.NT + ch * 32, r);
                         tc_wait_ld();
                         if (fast) {
                             runmax[m] = max32(r, runmax[m]);
-                        } else if (plain) {               // partially padded chunk: select, then max
+                        } else {                          // partially padded chunk: select, then max
                             float a = runmax[m];
 #pragma unroll
                             for (int j = 0; j < 32; j++)
                                 a = fmaxf(a, ((mword >> j) & 1u) ? __uint_as_float(r[j]) : -9999.0f);
                             runmax[m] = a;
-                        } else {
-                            int d = doc, e = next_end;
-                            const int krow = m * 128 + quad * 32 + lane;
-                            const bool raw = (MODE == 2) && p.scores_raw != nullptr && krow < p.Lq_out;
-#pragma unroll
-                            for (int j = 0; j < 32; j++) {
-                                if (j < nv) {
-                                    while (tk0 + j == e && d + 1 < it.nd) {  // passage d ends before this token
-                                        flush_one(m, d);
-                                        d++;
-                                        e = doc_end(d);
-                                    }
-                                    float v = __uint_as_float(r[j]);
-                                    if (MODE == 2 && !((mword >> j) & 1u)) v = -9999.0f;  // colbert.py:240-241
-                                    if (raw) store_raw(p.scores_raw + (size_t)(it.row0 + tk0 + j) * p.Lq_out + krow, v);
-                                    runmax[m] = fmaxf(runmax[m], v);
-                                }
-                            }
-                            doc_after = d;
-                            end_after = e;
                         }
                     }
-                    doc = doc_after;
-                    next_end = end_after;
+                } else {
+                    // generic chunk (a passage ends inside it, the item ends inside it, or the masked matrix is
+                    // wanted): one column at a time straight from TMEM -- a compact runtime loop, so the rare
+                    // path does not bloat the instruction stream of the common one
+#pragma unroll 1
+                    for (int j = 0; j < nv; j++) {
+                        while (tk0 + j == next_end && doc + 1 < it.nd) {     // passage `doc` ends before this token
+                            flush_all(doc);
+                            doc++;
+                            next_end = doc_end(doc);
+                        }
+                        const bool on = (mword >> j) & 1u;
+#pragma unroll
+                        for (int m = 0; m < kMsMaxMT; m++) {
+                            if (m >= p.MT) break;
+                            float v = __uint_as_float(tmem_ld_32x1(tmem_acc + m * p.NT + ch * 32 + j));
+                            if (MODE == 2 && !on) v = -9999.0f;              // colbert.py:240-241
+                            const int krow = m * 128 + quad * 32 + lane;
+                            if (MODE == 2 && p.scores_raw != nullptr && krow < p.Lq_out)
+                                p.scores_raw[(size_t)(it.row0 + tk0 + j) * p.Lq_out + krow] = v;
+                            runmax[m] = fmaxf(runmax[m], v);
+                        }
+                    }
                 }
             }
+        }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&sh->tmem_empty[acc]);
         }
         // close the passages still open (the last one, plus trailing empty ones)
-        if (MODE == 0) {
-            for (int d = doc; d < it.nd; d++) flush_all(d);
-        } else {
-#pragma unroll
-            for (int m = 0; m < kMsMaxMT; m++) {
-                if (m >= p.MT) break;
-                for (int d = doc; d < it.nd; d++) flush_one(m, d);
-            }
-        }
+        for (int d = doc; d < it.nd; d++) flush_all(d);
         __syncwarp();
         if (epi_bar_or(!ok)) ok = false;
         const int te = threadIdx.x;  // 0..127 among the epilogue threads
