@@ -217,16 +217,25 @@ __device__ __forceinline__ void ms_epilogue(const MsParams& p, MsShared* sh, uin
 
         const int ntiles = (it.ntok + p.NT - 1) / p.NT;
         const int nchunks = p.NT >> 5;
+        int mnext[4] = {0, 0, 0, 0};
         for (int t = 0; t < ntiles; t++, it_tile++) {
             const int acc = it_tile & 1;
-            // padded form: the tile's mask bytes (lane <- token 32*ch + lane of each chunk) are requested before
-            // the wait on the accumulator, so their latency hides behind the MMA
-            int mbyte[4] = {0, 0, 0, 0};
+            // padded form: mask bytes of the tile (lane <- token 32*ch + lane of each chunk).  The epilogue is the
+            // slowest role, so the accumulator is usually ready already: the bytes of tile t+1 are requested
+            // now and consumed one tile later, keeping their latency off the critical path.
+            int mbyte[4] = {mnext[0], mnext[1], mnext[2], mnext[3]};
             if (MODE == 2) {
+                if (t == 0) {
+#pragma unroll
+                    for (int ch = 0; ch < 4; ch++) {
+                        const int tk = ch * 32 + lane;
+                        mbyte[ch] = (ch * 32 < p.NT && tk < it.ntok) ? p.mask[it.row0 + tk] : 0;
+                    }
+                }
 #pragma unroll
                 for (int ch = 0; ch < 4; ch++) {
-                    const int tk = t * p.NT + ch * 32 + lane;
-                    if (ch * 32 < p.NT && tk < it.ntok) mbyte[ch] = p.mask[it.row0 + tk];
+                    const int tk = (t + 1) * p.NT + ch * 32 + lane;
+                    mnext[ch] = (ch * 32 < p.NT && tk < it.ntok) ? p.mask[it.row0 + tk] : 0;
                 }
             }
             if (!mbar_wait(&sh->tmem_full[acc], (it_tile >> 1) & 1, p.watchdog)) { ok = false; break; }
@@ -251,6 +260,11 @@ __device__ __forceinline__ void ms_epilogue(const MsParams& p, MsShared* sh, uin
                     }
                 } else {
                     const int nv = min(32, it.ntok - tk0);    // valid columns in this chunk
+                    while (tk0 == next_end && doc + 1 < it.nd) {     // the previous passage ended exactly at this chunk
+                        flush_all(doc);
+                        doc++;
+                        next_end = doc_end(doc);
+                    }
                     uint32_t mword = 0xffffffffu;
                     if (MODE == 2) {
                         const int mb = ch == 0 ? mbyte[0] : ch == 1 ? mbyte[1] : ch == 2 ? mbyte[2] : mbyte[3];
