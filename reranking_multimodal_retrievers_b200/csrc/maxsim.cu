@@ -296,8 +296,35 @@ __device__ __forceinline__ void ms_epilogue(const MsParams& p, MsShared* sh, uin
                             runmax[m] = a;
                         }
                     }
+                } else if (nv == 32 && (MODE != 2 || p.scores_raw == nullptr) && doc + 1 < it.nd &&
+                           doc_end(doc + 1) >= tk0 + 32) {
+                    // exactly one passage boundary inside the chunk, at column s: columns [0, s) close passage `doc`,
+                    // columns [s, 32) open passage doc+1.  Two predicated maxima per m-tile, no loop.
+                    const int s = next_end - tk0;
+                    float open_max[kMsMaxMT];
+#pragma unroll
+                    for (int m = 0; m < kMsMaxMT; m++) {
+                        open_max[m] = init;
+                        if (!live[m]) continue;
+                        uint32_t r[32];
+                        tmem_ld_32x32(tmem_acc + m * p.NT + ch * 32, r);
+                        tc_wait_ld();
+                        float a = runmax[m], b = init;
+#pragma unroll
+                        for (int j = 0; j < 32; j++) {
+                            const float v = ((mword >> j) & 1u) ? __uint_as_float(r[j]) : -9999.0f;
+                            if (j < s) a = fmaxf(a, v); else b = fmaxf(b, v);
+                        }
+                        runmax[m] = a;
+                        open_max[m] = b;
+                    }
+                    flush_all(doc);
+                    doc++;
+                    next_end = doc_end(doc);
+#pragma unroll
+                    for (int m = 0; m < kMsMaxMT; m++) runmax[m] = open_max[m];
                 } else {
-                    // generic chunk (a passage ends inside it, the item ends inside it, or the masked matrix is
+                    // generic chunk (several passages end inside it, the item ends inside it, or the masked matrix is
                     // wanted): one column at a time straight from TMEM -- a compact runtime loop, so the rare
                     // path does not bloat the instruction stream of the common one
 #pragma unroll 1
