@@ -177,3 +177,26 @@ def test_merge_topk_matches_cpu_merge(P):
     msg = sharded.pack_lists(pids[0].cuda(), scores[0].cuda(), counts[0].cuda())
     p, s, c = sharded.unpack_lists(msg.unsqueeze(0), k)
     assert torch.equal(p[0].cpu(), pids[0]) and torch.equal(s[0].cpu(), scores[0]) and torch.equal(c[0].cpu(), counts[0])
+
+
+def test_strided_tensor_lookup_and_padding(P, golden):
+    """StridedTensor (strided_tensor.py:77-99, strided_tensor_core.py:85-96): the IVF and the code stream."""
+    pkg, _ = P
+    ix = golden_oracle_index(golden)
+    ivf = pkg.StridedTensor(ix.ivf, ix.ivf_lengths)
+    cells = torch.tensor([7, 0, 1023, 7, 512])
+    pids, lens = ivf.lookup(cells)
+    ref = torch.cat([ix.ivf[ix.ivf_offsets[c]:ix.ivf_offsets[c + 1]] for c in cells.tolist()])
+    assert torch.equal(pids.cpu(), ref) and torch.equal(lens.cpu(), ix.ivf_lengths[cells])
+    codes = pkg.StridedTensor(ix.codes, ix.doclens)
+    docs = torch.tensor([3, 999, 0])
+    padded, mask = codes.lookup(docs, output="padded")
+    assert padded.shape == (3, int(ix.doclens[docs].max())) and mask.shape == padded.shape
+    for i, d in enumerate(docs.tolist()):
+        L = int(ix.doclens[d])
+        assert torch.equal(padded[i, :L].cpu(), ix.codes[ix.offsets[d]:ix.offsets[d] + L])
+        assert not bool(mask[i, L:].any()) and bool(mask[i, :L].all()) and int(padded[i, L:].abs().sum()) == 0
+    res = pkg.StridedTensor(ix.residuals, ix.doclens)
+    full, fmask = res.as_padded_tensor()
+    assert full.shape == (ix.doclens.numel(), int(ix.doclens.max()), ix.residuals.shape[1]) and fmask.dim() == 3
+    assert torch.equal(full[5, :int(ix.doclens[5])].cpu(), ix.residuals[ix.offsets[5]:ix.offsets[6]])
