@@ -87,7 +87,8 @@ int plaid_candidates(const float* cell_val, const int32_t* cell_idx, const int32
  * Approximate score of every listed passage: sum over k < nq_b (sequential fp32, in k order) of
  * max over the passage's codes with idx bit set (all codes when idx_bits == NULL) of S[b, code, k],
  * each per-token max initialised to -9999.  pids [B, pid_stride] with counts[b] valid entries;
- * scores written to the same slots of out_scores.  A CTA takes 32 passages of one query; lane = query token. */
+ * scores written to the same slots of out_scores.  Lane = query token.  codes must lie in [0, C) (unchecked,
+ * as in the reference, which asserts it); C a multiple of 128, codes / idx_bits 16-byte aligned. */
 int plaid_approx_scores(const int32_t* pids, const int32_t* counts, int B, int pid_stride, const float* S,
                         const int32_t* qlens, const uint32_t* idx_bits, int C, const int32_t* codes,
                         const int64_t* offsets, float* out_scores, void* stream);

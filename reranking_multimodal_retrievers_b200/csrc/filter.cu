@@ -43,10 +43,11 @@ __device__ __forceinline__ float gather_rows(unsigned mask, int code, const floa
 
 // A CTA scores 8*DPW consecutive candidate passages of one query; warp w walks passages DPW*w.. one
 // after the other, lane = query token.  Codes are pulled 128 at a time (one 128-bit load per lane).
-//   stage 1 (USE_IDX): the query's pruning bitmap (C bits) sits in shared memory; each lane probes its
-//     four codes, ONE warp vote per 128 codes tells whether anything survived, and only then the
-//     surviving codes' S rows are read (one coalesced 128 B request each);
-//   stage 2: every code reads its S row, eight rows in flight per warp.
+//   stage 1 (USE_IDX): the query's pruning bitmap (C bits + one zero word for the sentinel code C) sits in
+//     shared memory; each lane probes its four codes (4 instructions each), ONE warp vote per 128 codes
+//     tells whether anything survived, and only then the surviving codes' S rows are read;
+//   stage 2: every code reads its S row (one coalesced 128 B request), eight rows in flight per warp.
+// Codes must be < C (the reference asserts the same, filter_pids.cpp:47).
 // The 32 per-token maxima of each passage are parked in shared memory; afterwards lane j of warp 0
 // adds up passage j's row left to right, which is exactly the sequential fp32 sum of
 // filter_pids.cpp:59-63 at 1/32 of the shuffle traffic of doing it inside every warp.
@@ -68,8 +69,7 @@ approx_scores_kernel(const int32_t* __restrict__ pids, const int32_t* __restrict
     if (USE_IDX) {
         const uint4* src = reinterpret_cast<const uint4*>(idx_bits + (size_t)b * (C >> 5));
         for (int i = threadIdx.x; i < (C >> 7); i += blockDim.x) reinterpret_cast<uint4*>(s_bits)[i] = __ldg(src + i);
-        for (int i = (C >> 7) * 4 + threadIdx.x; i < (C >> 5); i += blockDim.x)
-            s_bits[i] = __ldg(idx_bits + (size_t)b * (C >> 5) + i);
+        if (threadIdx.x == 0) s_bits[C >> 5] = 0u;   // word of the sentinel code C: "not a survivor"
         __syncthreads();
     }
     // Passage descriptors of this warp's DPW passages, fetched in one parallel step (lane l <- passage l)
@@ -85,59 +85,73 @@ approx_scores_kernel(const int32_t* __restrict__ pids, const int32_t* __restrict
         }
     }
     const uint32_t sbits = smem_u32(s_bits);
-    const unsigned last_word = (unsigned)(C >> 5) - 1u;
-    // four codes of this lane -> survivors' S rows folded into m
-    auto scan4 = [&](const int (&c4)[4], float m) -> float {
-        if (USE_IDX) {
-            unsigned hit[4];
-#pragma unroll
-            for (int u = 0; u < 4; u++) {   // branch-free probe of the shared-memory bitmap
-                const unsigned code = (unsigned)c4[u];
-                unsigned w;
-                asm("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(sbits + (min(code >> 5, last_word) << 2)));
-                hit[u] = (code < (unsigned)C ? 1u : 0u) & (w >> (code & 31));
-            }
-            if (__any_sync(0xffffffffu, (hit[0] | hit[1] | hit[2] | hit[3]) & 1u)) {
-#pragma unroll
-                for (int u = 0; u < 4; u++) m = gather_rows<4>(__ballot_sync(0xffffffffu, hit[u] & 1u), c4[u], Sb, m);
-            }
-        } else {
-#pragma unroll
-            for (int u = 0; u < 4; u++)
-                m = gather_rows<8>(__ballot_sync(0xffffffffu, (unsigned)c4[u] < (unsigned)C), c4[u], Sb, m);
-        }
-        return m;
-    };
-    // one 128-code vector of the aligned stream starting at element e0 (lane covers e0+4*lane .. +3)
-    auto load4 = [&](const int32_t* cp, int e0, int head, int end, int (&c4)[4]) {
-        const int e = e0 + lane * 4;
-        c4[0] = c4[1] = c4[2] = c4[3] = -1;
-        if (e + 3 < end) {                              // whole vector inside [aligned start, passage end)
-            const int4 x = ld_stream_v4(cp + e0);
-            c4[0] = e >= head ? x.x : -1;               // elements before the passage belong to its neighbour
-            c4[1] = e + 1 >= head ? x.y : -1;
-            c4[2] = e + 2 >= head ? x.z : -1;
-            c4[3] = x.w;
-        } else if (e < end) {                           // the passage's last, partial vector
-#pragma unroll
-            for (int u = 0; u < 3; u++)
-                if (e + u >= head && e + u < end) c4[u] = ld_stream_s32(cp + e0 + u);
-        }
-    };
 #pragma unroll 1
     for (int d = 0; d < DPW; d++) {
         const int64_t off = __shfl_sync(0xffffffffu, my_off, d);
         const int len = __shfl_sync(0xffffffffu, my_len, d);
-        const int head = (int)(off & 3);                    // codes is 16-byte aligned: align the stream down
-        const int32_t* cp = codes + (off - head) + lane * 4;
-        const int end = len > 0 ? head + len : 0;
         float m = -9999.0f;  // filter_pids.cpp:30-33
-        for (int e0 = 0; e0 < end; e0 += 256) {             // two vectors (256 codes) in flight per step
-            int ca[4], cb[4];
-            load4(cp, e0, head, end, ca);
-            load4(cp, e0 + 128, head, end, cb);
-            m = scan4(ca, m);
-            if (e0 + 128 < end) m = scan4(cb, m);
+        if (USE_IDX) {
+            // ---- stage 1: 128 codes per step (one 128-bit load per lane), bitmap probe, one vote ----
+            // Elements outside the passage become the sentinel code C, whose bitmap word is zero.
+            const int head = (int)(off & 3);                    // codes is 16-byte aligned: align the stream down
+            const int32_t* cp = codes + (off - head) + lane * 4;
+            const int end = len > 0 ? head + len : 0;
+            auto load4 = [&](int e0, int (&c4)[4]) {
+                const int e = e0 + lane * 4;                    // element index relative to the aligned start
+                c4[0] = c4[1] = c4[2] = c4[3] = C;
+                if (e + 3 < end) {                              // whole vector before the passage's end
+                    const int4 x = ld_stream_v4(cp + e0);
+                    c4[0] = e >= head ? x.x : C;                // elements before the passage belong to its neighbour
+                    c4[1] = e + 1 >= head ? x.y : C;
+                    c4[2] = e + 2 >= head ? x.z : C;
+                    c4[3] = x.w;
+                } else if (e < end) {                           // the passage's last, partial vector
+#pragma unroll
+                    for (int u = 0; u < 3; u++)
+                        if (e + u >= head && e + u < end) c4[u] = ld_stream_s32(cp + e0 + u);
+                }
+            };
+            auto scan4 = [&](const int (&c4)[4]) {
+                unsigned w[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {                   // codes are < C by contract (sentinel = C)
+                    asm("ld.shared.u32 %0, [%1];" : "=r"(w[u]) : "r"(sbits + (((unsigned)c4[u] >> 5) << 2)));
+                    w[u] >>= ((unsigned)c4[u] & 31u);
+                }
+                if (__any_sync(0xffffffffu, (w[0] | w[1] | w[2] | w[3]) & 1u)) {
+#pragma unroll
+                    for (int u = 0; u < 4; u++) m = gather_rows<4>(__ballot_sync(0xffffffffu, w[u] & 1u), c4[u], Sb, m);
+                }
+            };
+            for (int e0 = 0; e0 < end; e0 += 256) {             // two vectors (256 codes) in flight per step
+                int ca[4], cb[4];
+                load4(e0, ca);
+                load4(e0 + 128, cb);
+                scan4(ca);
+                if (e0 + 128 < end) scan4(cb);
+            }
+        } else {
+            // ---- stage 2: every code reads its S row (one coalesced 128 B request per token) ----
+            const int32_t* cp = codes + off;
+            for (int t0 = 0; t0 < len; t0 += 32) {
+                const int t = t0 + lane;
+                const int code = (t < len) ? ld_stream_s32(cp + t) : 0;
+                if (t0 + 32 <= len) {                           // full chunk: straight-line gather, 8 rows in flight
+#pragma unroll
+                    for (int g = 0; g < 32; g += 8) {
+                        float v[8];
+#pragma unroll
+                        for (int u = 0; u < 8; u++) {
+                            const unsigned c = (unsigned)__shfl_sync(0xffffffffu, code, g + u);
+                            v[u] = __ldg(Sb + (size_t)c * PLAID_NQ_MAX);
+                        }
+#pragma unroll
+                        for (int u = 0; u < 8; u++) m = fmaxf(m, v[u]);
+                    }
+                } else {
+                    m = gather_rows<8>(__ballot_sync(0xffffffffu, t < len), code, Sb, m);
+                }
+            }
         }
         s_max[warp * DPW + d][lane] = m;
     }
@@ -309,7 +323,7 @@ static int launch_approx(const int32_t* pids, const int32_t* counts, int B, int 
     PLAID_CHECK_ARG((reinterpret_cast<uintptr_t>(codes) & 15) == 0, PLAID_ERR_ARG, "approx_scores: codes must be 16-byte aligned");
     if (idx_bits) {
         constexpr int kDocs = kApproxWarps * kStage1Dpw;
-        const size_t smem = (size_t)kDocs * 33 * 4 + (size_t)(C >> 5) * 4;
+        const size_t smem = (size_t)kDocs * 33 * 4 + (size_t)(C >> 5) * 4 + 16;
         PLAID_CHECK_ARG(smem <= 200 * 1024, PLAID_ERR_UNSUPPORTED, "approx_scores: C=%d pruning bitmap exceeds shared memory", C);
         PLAID_CHECK_ARG((reinterpret_cast<uintptr_t>(idx_bits) & 15) == 0 && (C % 128) == 0, PLAID_ERR_ARG,
                         "approx_scores: idx_bits must be 16-byte aligned and C a multiple of 128");

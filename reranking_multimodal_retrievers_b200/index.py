@@ -162,6 +162,7 @@ class DeviceIndex:
             self.num_centroids = int(self.centroids_f16.shape[0])
             if self.num_centroids % 128:
                 raise ValueError("number of centroids must be a multiple of 128")
+            ops.check_codes(self.codes, self.num_centroids)   # the kernels trust codes < C from here on
             self.centroids_f32 = self.centroids_f16.float()
             self.centroids_bf16 = ops.to_bf16(self.centroids_f32)
             self.bucket_weights = host.bucket_weights.to(dev, torch.float32).contiguous()

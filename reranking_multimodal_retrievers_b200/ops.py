@@ -67,6 +67,13 @@ def unpack_idx_bits(words: torch.Tensor, C: int) -> torch.Tensor:
     return bits.reshape(*words.shape[:-1], -1)[..., :C].bool()
 
 
+def check_codes(codes: torch.Tensor, C: int):
+    """The filter kernels index the pruning bitmap and the S table with the codes unchecked (the reference
+    asserts `code < ncentroids` and aborts, filter_pids.cpp:47); validate once on the host side instead."""
+    if codes.numel() and (int(codes.max()) >= C or int(codes.min()) < 0):
+        raise _lib.PlaidError(f"centroid codes outside [0, {C})")
+
+
 def pad_centroid_scores(centroid_scores: torch.Tensor) -> torch.Tensor:
     """[C, nq] (nq <= 32) -> the kernels' [C, 32] row layout."""
     C, nq = centroid_scores.shape
@@ -92,6 +99,7 @@ def approx_scores(pids, centroid_scores, codes, offsets, idx=None):
     bits = pack_idx_bits(_cu(idx).bool()) if idx is not None else None
     out = torch.empty(max(n, 1), device=pids.device, dtype=torch.float32)
     codes, offsets = _cu(codes, torch.int32), _cu(offsets, torch.int64)   # named: must outlive the launch
+    check_codes(codes, C)
     _lib.call("plaid_approx_scores", _p(pids), _p(counts), 1, n, _p(S), _p(qlens), _p(bits), C,
               _p(codes), _p(offsets), _p(out), _stream())
     return out[:n]
@@ -138,6 +146,7 @@ def filter_pids(pids, centroid_scores, codes, doclens, offsets, idx, nfiltered_d
     s2s = torch.empty(ndocs // 4, device=dev, dtype=torch.float32)
     s2c = torch.empty(1, device=dev, dtype=torch.int32)
     codes, offsets = _cu(codes, torch.int32), _cu(offsets, torch.int64)   # named: must outlive the launch
+    check_codes(codes, C)
     _lib.call("plaid_filter_pids", _p(pid_buf), _p(counts), 1, stride, _p(S), _p(qlens), _p(bits), C,
               _p(codes), _p(offsets), ndocs, _p(ws_scores), _p(ws_keys),
               _p(s1p), _p(s1s), _p(s1c), _p(s2p), _p(s2s), _p(s2c), _stream())
