@@ -189,7 +189,7 @@ def test_strided_tensor_lookup_and_padding(P, golden):
     ref = torch.cat([ix.ivf[ix.ivf_offsets[c]:ix.ivf_offsets[c + 1]] for c in cells.tolist()])
     assert torch.equal(pids.cpu(), ref) and torch.equal(lens.cpu(), ix.ivf_lengths[cells])
     codes = pkg.StridedTensor(ix.codes, ix.doclens)
-    docs = torch.tensor([3, 999, 0])
+    docs = torch.tensor([3, ix.doclens.numel() - 1, 0])
     padded, mask = codes.lookup(docs, output="padded")
     assert padded.shape == (3, int(ix.doclens[docs].max())) and mask.shape == padded.shape
     for i, d in enumerate(docs.tolist()):
