@@ -62,13 +62,14 @@ int plaid_f32_to_bf16(const float* src, void* dst_bf16, int64_t n, void* stream)
  *                                   l-th of 2*csplit partial lists (csplit centroid ranges x two
  *                                   128-column halves), best first, ties -> lowest centroid id;
  *                                   cell_idx = -1 where there is no entry.
- * nq_b = min(qlens[b], 32).  S is laid out [B_pad, C, 32] fp32 -- per query exactly the reference's
- * `centroid_scores` [C, nq] tensor (row = centroid).  C must be a multiple of 32; the grid is
+ * nq_b = min(qlens[b], 32).  S is laid out [B_pad, C, 32] -- per query exactly the reference's
+ * `centroid_scores` [C, nq] tensor (row = centroid) -- in fp32, or with s_is_f16 != 0 rounded to fp16
+ * (the precision the reference's GPU branch computes S in); mask and cells are derived from the stored values.  C must be a multiple of 32; the grid is
  * (B_pad/4) x csplit CTAs.  Rows of Qb beyond qlens[b] must be zero (plaid_prepare_queries does it).
  * *watchdog (device int, may be NULL) is set to 1 if an in-kernel pipeline wait ever times out. */
 int plaid_centroid_scores(const void* centroids_bf16, int C, const void* Qb_bf16, const int32_t* qlens,
                           int B_pad, int Lq_pad, float threshold, int ncells, int csplit,
-                          float* S, uint32_t* idx_bits, float* cell_val, int32_t* cell_idx, int* watchdog,
+                          void* S, int s_is_f16, uint32_t* idx_bits, float* cell_val, int32_t* cell_idx, int* watchdog,
                           void* stream);
 
 /* ---- a3: candidate pids (candidate_generation.py:31-37,57-60; strided_tensor.py:77-99;
@@ -89,8 +90,8 @@ int plaid_candidates(const float* cell_val, const int32_t* cell_idx, const int32
  * each per-token max initialised to -9999.  pids [B, pid_stride] with counts[b] valid entries;
  * scores written to the same slots of out_scores.  Lane = query token.  codes must lie in [0, C) (unchecked,
  * as in the reference, which asserts it); C a multiple of 128, codes / idx_bits 16-byte aligned. */
-int plaid_approx_scores(const int32_t* pids, const int32_t* counts, int B, int pid_stride, const float* S,
-                        const int32_t* qlens, const uint32_t* idx_bits, int C, const int32_t* codes,
+int plaid_approx_scores(const int32_t* pids, const int32_t* counts, int B, int pid_stride, const void* S,
+                        int s_is_f16, const int32_t* qlens, const uint32_t* idx_bits, int C, const int32_t* codes,
                         const int64_t* offsets, float* out_scores, void* stream);
 
 /* Per query the `keep` largest (score, pid) pairs in descending (score, pid) order -- the order of
@@ -106,8 +107,8 @@ int plaid_select_top(const int32_t* pids, const float* scores, const int32_t* co
  * Workspaces: ws_scores f32 [B, max(pid_stride, ndocs)], ws_keys u64 [B, max(pid_stride, ndocs)],
  * stage1_pids i32 [B, ndocs] / stage1_scores f32 [B, ndocs] / stage1_counts [B] (outputs too, for
  * stage-wise parity), stage2_* likewise with ndocs/4. */
-int plaid_filter_pids(const int32_t* pids, const int32_t* counts, int B, int pid_stride, const float* S,
-                      const int32_t* qlens, const uint32_t* idx_bits, int C, const int32_t* codes,
+int plaid_filter_pids(const int32_t* pids, const int32_t* counts, int B, int pid_stride, const void* S,
+                      int s_is_f16, const int32_t* qlens, const uint32_t* idx_bits, int C, const int32_t* codes,
                       const int64_t* offsets, int ndocs, float* ws_scores, uint64_t* ws_keys,
                       int32_t* stage1_pids, float* stage1_scores, int32_t* stage1_counts,
                       int32_t* stage2_pids, float* stage2_scores, int32_t* stage2_counts, void* stream);

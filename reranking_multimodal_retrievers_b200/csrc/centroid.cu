@@ -19,6 +19,7 @@
 //     columns it sees -- partial per centroid range, merged in candidates.cu.
 // The kernel is bound by the S write (4*C*32 bytes per query), not by the tensor pipe.
 #include "common.cuh"
+#include <cuda_fp16.h>
 
 namespace plaid {
 
@@ -54,10 +55,12 @@ __device__ __noinline__ float topk_insert(float* bv, int* bi, int ncells, float 
     return bv[ncells - 1];
 }
 
+template <typename ST>   // float: S as the reference's fp32 table; __half: S rounded to fp16 (what the reference's GPU
+                         // branch computes in, candidate_generation.py:52) -- half the bytes to write and to gather
 __global__ void __launch_bounds__(kCsThreads, 1)
 centroid_scores_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_c,
                        const int32_t* __restrict__ qlens, int C, int Lq_pad, float threshold, int ncells, int csplit,
-                       float* __restrict__ S, uint32_t* __restrict__ idx_bits, float* __restrict__ cell_val,
+                       ST* __restrict__ S, uint32_t* __restrict__ idx_bits, float* __restrict__ cell_val,
                        int32_t* __restrict__ cell_idx, int* __restrict__ watchdog) {
     extern __shared__ uint8_t smem_raw[];
     // 1024-byte alignment: required by the 128B swizzle atoms the UMMA descriptors describe
@@ -138,7 +141,7 @@ centroid_scores_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
         const int bq = qgroup * 4 + quad;
         const int nq = min(qlens[bq], PLAID_NQ_MAX);
         const bool tok_valid = lane < nq;
-        float* Sq = S + (size_t)bq * C * PLAID_NQ_MAX + lane;
+        ST* Sq = S + (size_t)bq * C * PLAID_NQ_MAX + lane;
         uint32_t* bits_q = idx_bits + (size_t)bq * (C >> 5);
         float bv[PLAID_NCELLS_MAX];
         int bi[PLAID_NCELLS_MAX];
@@ -157,10 +160,24 @@ centroid_scores_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                 tc_wait_ld();
                 const int c0 = c_tile + ch * 32;
                 if (c0 >= C) break;  // C is a multiple of 32: a chunk is entirely inside or outside
-                // (1) the S rows: for each centroid the warp stores 32 consecutive floats (one 128 B line)
-                float* dst = Sq + (size_t)c0 * PLAID_NQ_MAX;
+                // (1) the S rows: for each centroid the warp stores 32 consecutive values (one 128 B / 64 B line).
+                //     With fp16 storage everything downstream (mask, cells) is computed from the ROUNDED values,
+                //     so that the table in memory is the one and only definition of S.
+                ST* dst = Sq + (size_t)c0 * PLAID_NQ_MAX;
+                if constexpr (sizeof(ST) == 2) {
 #pragma unroll
-                for (int j = 0; j < 32; j++) __stcs(dst + j * PLAID_NQ_MAX, __uint_as_float(r[j]));
+                    for (int j = 0; j < 32; j += 2) {
+                        const __half2 h2 = __floats2half2_rn(__uint_as_float(r[j]), __uint_as_float(r[j + 1]));
+                        __stcs(reinterpret_cast<unsigned short*>(dst + j * PLAID_NQ_MAX), __half_as_ushort(__low2half(h2)));
+                        __stcs(reinterpret_cast<unsigned short*>(dst + (j + 1) * PLAID_NQ_MAX), __half_as_ushort(__high2half(h2)));
+                        const float2 f2 = __half22float2(h2);
+                        r[j] = __float_as_uint(f2.x);
+                        r[j + 1] = __float_as_uint(f2.y);
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; j++) __stcs(dst + j * PLAID_NQ_MAX, __uint_as_float(r[j]));
+                }
                 // (2) this thread's best value in the chunk decides whether the rare paths run at all
                 float mx = __uint_as_float(r[0]);
 #pragma unroll
@@ -203,7 +220,7 @@ centroid_scores_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
 }  // namespace plaid
 
 extern "C" int plaid_centroid_scores(const void* centroids_bf16, int C, const void* Qb_bf16, const int32_t* qlens,
-                                     int B_pad, int Lq_pad, float threshold, int ncells, int csplit, float* S,
+                                     int B_pad, int Lq_pad, float threshold, int ncells, int csplit, void* S, int s_is_f16,
                                      uint32_t* idx_bits, float* cell_val, int32_t* cell_idx, int* watchdog,
                                      void* stream) {
     using namespace plaid;
@@ -221,12 +238,19 @@ extern "C" int plaid_centroid_scores(const void* centroids_bf16, int C, const vo
     if ((rc = make_bf16_2d_map(&map_c, centroids_bf16, (uint64_t)C, kDim, kCsN)) != PLAID_OK) return rc;
     static bool configured = false;
     if (!configured) {
-        PLAID_CUDA_OK(cudaFuncSetAttribute(centroid_scores_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCsSmemBytes));
+        PLAID_CUDA_OK(cudaFuncSetAttribute(centroid_scores_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCsSmemBytes));
+        PLAID_CUDA_OK(cudaFuncSetAttribute(centroid_scores_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCsSmemBytes));
         configured = true;
     }
     dim3 grid(B_pad / 4, csplit);
-    centroid_scores_kernel<<<grid, kCsThreads, kCsSmemBytes, (cudaStream_t)stream>>>(
-        map_q, map_c, qlens, C, Lq_pad, threshold, ncells, csplit, S, idx_bits, cell_val, cell_idx, watchdog);
+    if (s_is_f16)
+        centroid_scores_kernel<__half><<<grid, kCsThreads, kCsSmemBytes, (cudaStream_t)stream>>>(
+            map_q, map_c, qlens, C, Lq_pad, threshold, ncells, csplit, reinterpret_cast<__half*>(S), idx_bits, cell_val,
+            cell_idx, watchdog);
+    else
+        centroid_scores_kernel<float><<<grid, kCsThreads, kCsSmemBytes, (cudaStream_t)stream>>>(
+            map_q, map_c, qlens, C, Lq_pad, threshold, ncells, csplit, reinterpret_cast<float*>(S), idx_bits, cell_val,
+            cell_idx, watchdog);
     PLAID_LAUNCH_OK("centroid_scores_kernel");
     return PLAID_OK;
 }

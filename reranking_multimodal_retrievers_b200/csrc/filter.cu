@@ -12,16 +12,21 @@
 //   std::pair<float,int> ordering of filter_pids.cpp:24; an 8-pass MSB radix select finds the
 //   keep-th key, survivors are bitonic-sorted in shared memory.
 #include "common.cuh"
+#include <cuda_fp16.h>
 
 namespace plaid {
+
+// one element of the centroid-score table, fp32 or fp16 storage
+__device__ __forceinline__ float load_s(const float* p) { return __ldg(p); }
+__device__ __forceinline__ float load_s(const __half* p) { return __half2float(__ldg(p)); }
 
 static constexpr int kApproxWarps = 8;        // warps per CTA
 static constexpr int kStage1Dpw = 16;         // stage 1: 128 passages per CTA (amortises the bitmap load)
 static constexpr int kStage2Dpw = 1;          // stage 2: 8 passages per CTA (few queries resident -> S stays in L2)
 
 // Gather the S rows of the codes selected by `mask` (bit l = lane l's `code`), G rows in flight per step.
-template <int G>
-__device__ __forceinline__ float gather_rows(unsigned mask, int code, const float* __restrict__ Sb, float m) {
+template <int G, typename ST>
+__device__ __forceinline__ float gather_rows(unsigned mask, int code, const ST* __restrict__ Sb, float m) {
     while (mask) {
         int src[G];
         float v[G];
@@ -33,7 +38,7 @@ __device__ __forceinline__ float gather_rows(unsigned mask, int code, const floa
 #pragma unroll
         for (int t = 0; t < G; t++) {
             const int c = __shfl_sync(0xffffffffu, code, src[t] < 0 ? 0 : src[t]);
-            v[t] = (src[t] >= 0) ? __ldg(Sb + (size_t)(unsigned)c * PLAID_NQ_MAX) : -9999.0f;
+            v[t] = (src[t] >= 0) ? load_s(Sb + (size_t)(unsigned)c * PLAID_NQ_MAX) : -9999.0f;
         }
 #pragma unroll
         for (int t = 0; t < G; t++) m = fmaxf(m, v[t]);
@@ -51,10 +56,10 @@ __device__ __forceinline__ float gather_rows(unsigned mask, int code, const floa
 // The 32 per-token maxima of each passage are parked in shared memory; afterwards lane j of warp 0
 // adds up passage j's row left to right, which is exactly the sequential fp32 sum of
 // filter_pids.cpp:59-63 at 1/32 of the shuffle traffic of doing it inside every warp.
-template <bool USE_IDX, int DPW>
+template <bool USE_IDX, int DPW, typename ST>
 __global__ void __launch_bounds__(kApproxWarps * 32)
 approx_scores_kernel(const int32_t* __restrict__ pids, const int32_t* __restrict__ counts, int pid_stride,
-                     const float* __restrict__ S, const int32_t* __restrict__ qlens,
+                     const ST* __restrict__ S, const int32_t* __restrict__ qlens,
                      const uint32_t* __restrict__ idx_bits, int C, const int32_t* __restrict__ codes,
                      const int64_t* __restrict__ offsets, float* __restrict__ out) {
     constexpr int kDocs = kApproxWarps * DPW;
@@ -65,7 +70,7 @@ approx_scores_kernel(const int32_t* __restrict__ pids, const int32_t* __restrict
     const int n = min(counts[b], pid_stride);
     const int i0 = blockIdx.x * kDocs;
     if (i0 >= n) return;  // whole CTA past the end of this query's list
-    const float* Sb = S + (size_t)b * C * PLAID_NQ_MAX + lane;
+    const ST* Sb = S + (size_t)b * C * PLAID_NQ_MAX + lane;
     if (USE_IDX) {
         const uint4* src = reinterpret_cast<const uint4*>(idx_bits + (size_t)b * (C >> 5));
         for (int i = threadIdx.x; i < (C >> 7); i += blockDim.x) reinterpret_cast<uint4*>(s_bits)[i] = __ldg(src + i);
@@ -143,7 +148,7 @@ approx_scores_kernel(const int32_t* __restrict__ pids, const int32_t* __restrict
 #pragma unroll
                         for (int u = 0; u < 8; u++) {
                             const unsigned c = (unsigned)__shfl_sync(0xffffffffu, code, g + u);
-                            v[u] = __ldg(Sb + (size_t)c * PLAID_NQ_MAX);
+                            v[u] = load_s(Sb + (size_t)c * PLAID_NQ_MAX);
                         }
 #pragma unroll
                         for (int u = 0; u < 8; u++) m = fmaxf(m, v[u]);
@@ -317,9 +322,10 @@ static int next_pow2(int v) {
     return p;
 }
 
-static int launch_approx(const int32_t* pids, const int32_t* counts, int B, int pid_stride, const float* S,
-                         const int32_t* qlens, const uint32_t* idx_bits, int C, const int32_t* codes,
-                         const int64_t* offsets, float* out, cudaStream_t st) {
+template <typename ST>
+static int launch_approx_t(const int32_t* pids, const int32_t* counts, int B, int pid_stride, const ST* S,
+                           const int32_t* qlens, const uint32_t* idx_bits, int C, const int32_t* codes,
+                           const int64_t* offsets, float* out, cudaStream_t st) {
     PLAID_CHECK_ARG((reinterpret_cast<uintptr_t>(codes) & 15) == 0, PLAID_ERR_ARG, "approx_scores: codes must be 16-byte aligned");
     if (idx_bits) {
         constexpr int kDocs = kApproxWarps * kStage1Dpw;
@@ -329,21 +335,31 @@ static int launch_approx(const int32_t* pids, const int32_t* counts, int B, int 
                         "approx_scores: idx_bits must be 16-byte aligned and C a multiple of 128");
         static size_t configured = 0;
         if (smem > 48 * 1024 && smem > configured) {
-            PLAID_CUDA_OK(cudaFuncSetAttribute(approx_scores_kernel<true, kStage1Dpw>,
+            PLAID_CUDA_OK(cudaFuncSetAttribute(approx_scores_kernel<true, kStage1Dpw, ST>,
                                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             configured = smem;
         }
         dim3 grid((pid_stride + kDocs - 1) / kDocs, B);
-        approx_scores_kernel<true, kStage1Dpw><<<grid, kApproxWarps * 32, smem, st>>>(pids, counts, pid_stride, S, qlens,
-                                                                                     idx_bits, C, codes, offsets, out);
+        approx_scores_kernel<true, kStage1Dpw, ST><<<grid, kApproxWarps * 32, smem, st>>>(pids, counts, pid_stride, S, qlens,
+                                                                                         idx_bits, C, codes, offsets, out);
     } else {
         constexpr int kDocs = kApproxWarps * kStage2Dpw;
         dim3 grid((pid_stride + kDocs - 1) / kDocs, B);
-        approx_scores_kernel<false, kStage2Dpw><<<grid, kApproxWarps * 32, kDocs * 33 * 4, st>>>(
+        approx_scores_kernel<false, kStage2Dpw, ST><<<grid, kApproxWarps * 32, kDocs * 33 * 4, st>>>(
             pids, counts, pid_stride, S, qlens, nullptr, C, codes, offsets, out);
     }
     PLAID_LAUNCH_OK("approx_scores_kernel");
     return PLAID_OK;
+}
+
+static int launch_approx(const int32_t* pids, const int32_t* counts, int B, int pid_stride, const void* S, int s_is_f16,
+                         const int32_t* qlens, const uint32_t* idx_bits, int C, const int32_t* codes,
+                         const int64_t* offsets, float* out, cudaStream_t st) {
+    if (s_is_f16)
+        return launch_approx_t<__half>(pids, counts, B, pid_stride, reinterpret_cast<const __half*>(S), qlens, idx_bits, C,
+                                       codes, offsets, out, st);
+    return launch_approx_t<float>(pids, counts, B, pid_stride, reinterpret_cast<const float*>(S), qlens, idx_bits, C, codes,
+                                  offsets, out, st);
 }
 
 static int launch_select(const int32_t* pids, const float* scores, const int32_t* counts, int B, int in_stride, int keep,
@@ -366,8 +382,8 @@ static int launch_select(const int32_t* pids, const float* scores, const int32_t
 
 }  // namespace plaid
 
-extern "C" int plaid_approx_scores(const int32_t* pids, const int32_t* counts, int B, int pid_stride, const float* S,
-                                   const int32_t* qlens, const uint32_t* idx_bits, int C, const int32_t* codes,
+extern "C" int plaid_approx_scores(const int32_t* pids, const int32_t* counts, int B, int pid_stride, const void* S,
+                                   int s_is_f16, const int32_t* qlens, const uint32_t* idx_bits, int C, const int32_t* codes,
                                    const int64_t* offsets, float* out_scores, void* stream) {
     using namespace plaid;
     PLAID_CHECK_ARG(pids && counts && S && qlens && codes && offsets && out_scores, PLAID_ERR_ARG,
@@ -376,7 +392,7 @@ extern "C" int plaid_approx_scores(const int32_t* pids, const int32_t* counts, i
                     "plaid_approx_scores: bad sizes (B=%d stride=%d C=%d; C must be a multiple of 128)", B, pid_stride, C);
     if (B == 0 || pid_stride == 0) return PLAID_OK;
     PLAID_CHECK_ARG(B <= 65535, PLAID_ERR_UNSUPPORTED, "plaid_approx_scores: B=%d > 65535 per call", B);
-    return launch_approx(pids, counts, B, pid_stride, S, qlens, idx_bits, C, codes, offsets, out_scores,
+    return launch_approx(pids, counts, B, pid_stride, S, s_is_f16, qlens, idx_bits, C, codes, offsets, out_scores,
                          (cudaStream_t)stream);
 }
 
@@ -391,8 +407,8 @@ extern "C" int plaid_select_top(const int32_t* pids, const float* scores, const 
                          (cudaStream_t)stream);
 }
 
-extern "C" int plaid_filter_pids(const int32_t* pids, const int32_t* counts, int B, int pid_stride, const float* S,
-                                 const int32_t* qlens, const uint32_t* idx_bits, int C, const int32_t* codes,
+extern "C" int plaid_filter_pids(const int32_t* pids, const int32_t* counts, int B, int pid_stride, const void* S,
+                                 int s_is_f16, const int32_t* qlens, const uint32_t* idx_bits, int C, const int32_t* codes,
                                  const int64_t* offsets, int ndocs, float* ws_scores, uint64_t* ws_keys,
                                  int32_t* stage1_pids, float* stage1_scores, int32_t* stage1_counts,
                                  int32_t* stage2_pids, float* stage2_scores, int32_t* stage2_counts, void* stream) {
@@ -408,14 +424,16 @@ extern "C" int plaid_filter_pids(const int32_t* pids, const int32_t* counts, int
     int rc;
     // stage 1: pruned centroids only (filter_pids.cpp:139-146), keep ndocs
     if (pid_stride > 0 &&
-        (rc = launch_approx(pids, counts, B, pid_stride, S, qlens, idx_bits, C, codes, offsets, ws_scores, st)) != PLAID_OK)
+        (rc = launch_approx(pids, counts, B, pid_stride, S, s_is_f16, qlens, idx_bits, C, codes, offsets, ws_scores, st)) !=
+            PLAID_OK)
         return rc;
     if ((rc = launch_select(pids, ws_scores, counts, B, pid_stride, ndocs, stage1_pids, stage1_scores, stage1_counts, ndocs,
                             ws_keys, st)) != PLAID_OK)
         return rc;
     // stage 2: all centroids (filter_pids.cpp:148-157), keep ndocs/4.  ws_scores is free again (its content
     // was folded into the keys) and is reused with row stride ndocs.
-    if ((rc = launch_approx(stage1_pids, stage1_counts, B, ndocs, S, qlens, nullptr, C, codes, offsets, ws_scores, st)) !=
+    if ((rc = launch_approx(stage1_pids, stage1_counts, B, ndocs, S, s_is_f16, qlens, nullptr, C, codes, offsets, ws_scores,
+                            st)) !=
         PLAID_OK)
         return rc;
     return launch_select(stage1_pids, ws_scores, stage1_counts, B, ndocs, ndocs / 4, stage2_pids, stage2_scores,

@@ -55,8 +55,13 @@ class StageTaps:
 
 
 class SearchEngine:
-    def __init__(self, index: DeviceIndex, s_budget_bytes: int = 6 << 30, max_chunk: int = 512, fused: bool = True):
+    def __init__(self, index: DeviceIndex, s_budget_bytes: int = 6 << 30, max_chunk: int = 512, fused: bool = True,
+                 s_dtype: torch.dtype = torch.float16):
         self.index = index
+        # storage precision of the centroid-score table S: fp16 (what the reference's GPU branch computes S in,
+        # candidate_generation.py:52; half the bytes to write and to gather) or fp32 (the CPU branch's precision)
+        assert s_dtype in (torch.float16, torch.float32)
+        self.s_dtype = s_dtype
         # fused = decompression feeds the tensor cores through shared memory (no passage embeddings in HBM);
         # the unfused pair of kernels materialises D (bf16) and is what the stage-wise parity taps read
         self.fused = bool(fused)
@@ -72,7 +77,7 @@ class SearchEngine:
 
     # ----------------------------------------------------------------------------------- workspace
     def chunk_size(self, B: int) -> int:
-        per_query = self.index.num_centroids * NQ_MAX * 4
+        per_query = self.index.num_centroids * NQ_MAX * (2 if self.s_dtype == torch.float16 else 4)
         bc = max(4, min(self.max_chunk, self.s_budget_bytes // per_query))
         bc = min(bc, ((B + 3) // 4) * 4)
         return max(4, (bc // 4) * 4)
@@ -97,7 +102,7 @@ class SearchEngine:
         ws = dict(
             csplit=csplit, nlists=nlists, cand_stride=cand_stride, fstride=fstride, tok_stride=tok_stride, nd4=nd4,
             Qb=e(Bc, Lq_pad, 128, dtype=torch.bfloat16), qlens=e(Bc, dtype=torch.int32),
-            S=e(Bc, C, NQ_MAX, dtype=torch.float32), idx_bits=e(Bc, C // 32, dtype=torch.int32),
+            S=e(Bc, C, NQ_MAX, dtype=self.s_dtype), idx_bits=e(Bc, C // 32, dtype=torch.int32),
             cell_val=e(Bc, NQ_MAX, nlists, ncells, dtype=torch.float32),
             cell_idx=e(Bc, NQ_MAX, nlists, ncells, dtype=torch.int32),
             cells=e(Bc, NQ_MAX, ncells, dtype=torch.int32),
@@ -155,7 +160,7 @@ class SearchEngine:
         call = self._call
         call("prepare", "plaid_prepare_queries", _p(Qc), b, Lq, int(remove_zero_rows), Bc, Lq_pad, _p(ws["Qb"]), _p(ws["qlens"]), st)
         call("centroid_scores", "plaid_centroid_scores", _p(ix.centroids_bf16), C, _p(ws["Qb"]), _p(ws["qlens"]), Bc, Lq_pad, float(thr),
-             ncells, ws["csplit"], _p(ws["S"]), _p(ws["idx_bits"]), _p(ws["cell_val"]), _p(ws["cell_idx"]), wd, st)
+             ncells, ws["csplit"], _p(ws["S"]), int(self.s_dtype == torch.float16), _p(ws["idx_bits"]), _p(ws["cell_val"]), _p(ws["cell_idx"]), wd, st)
         call("candidates", "plaid_candidates", _p(ws["cell_val"]), _p(ws["cell_idx"]), _p(ws["qlens"]), b, ncells, ws["nlists"],
              _p(ix.ivf_pids), _p(ix.ivf_offsets), C, N, _p(ws["cells"]), _p(ws["bitmap"]), _p(ws["cand_pids"]),
              _p(ws["cand_counts"]), ws["cand_stride"], ovf, st)
@@ -169,11 +174,12 @@ class SearchEngine:
         call = self._call
         # plaid_filter_pids' four launches issued one by one so each can be timed on its own
         cs, fs, nd4_ = ws["cand_stride"], ws["fstride"], ndocs // 4
-        call("filter_stage1", "plaid_approx_scores", _p(ws["cand_pids"]), _p(ws["cand_counts"]), b, cs, _p(ws["S"]),
+        f16 = int(self.s_dtype == torch.float16)
+        call("filter_stage1", "plaid_approx_scores", _p(ws["cand_pids"]), _p(ws["cand_counts"]), b, cs, _p(ws["S"]), f16,
              _p(ws["qlens"]), _p(ws["idx_bits"]), C, _p(ix.codes), _p(ix.offsets), _p(ws["ws_scores"]), st)
         call("select1", "plaid_select_top", _p(ws["cand_pids"]), _p(ws["ws_scores"]), _p(ws["cand_counts"]), b, cs, ndocs,
              _p(ws["s1_pids"]), _p(ws["s1_scores"]), _p(ws["s1_counts"]), ndocs, _p(ws["ws_keys"]), st)
-        call("filter_stage2", "plaid_approx_scores", _p(ws["s1_pids"]), _p(ws["s1_counts"]), b, ndocs, _p(ws["S"]),
+        call("filter_stage2", "plaid_approx_scores", _p(ws["s1_pids"]), _p(ws["s1_counts"]), b, ndocs, _p(ws["S"]), f16,
              _p(ws["qlens"]), None, C, _p(ix.codes), _p(ix.offsets), _p(ws["ws_scores"]), st)
         call("select2", "plaid_select_top", _p(ws["s1_pids"]), _p(ws["ws_scores"]), _p(ws["s1_counts"]), b, ndocs, nd4_,
              _p(ws["s2_pids"]), _p(ws["s2_scores"]), _p(ws["s2_counts"]), nd4_, _p(ws["ws_keys"]), st)

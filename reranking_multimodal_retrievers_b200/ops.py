@@ -100,7 +100,7 @@ def approx_scores(pids, centroid_scores, codes, offsets, idx=None):
     out = torch.empty(max(n, 1), device=pids.device, dtype=torch.float32)
     codes, offsets = _cu(codes, torch.int32), _cu(offsets, torch.int64)   # named: must outlive the launch
     check_codes(codes, C)
-    _lib.call("plaid_approx_scores", _p(pids), _p(counts), 1, n, _p(S), _p(qlens), _p(bits), C,
+    _lib.call("plaid_approx_scores", _p(pids), _p(counts), 1, n, _p(S), 0, _p(qlens), _p(bits), C,
               _p(codes), _p(offsets), _p(out), _stream())
     return out[:n]
 
@@ -147,7 +147,7 @@ def filter_pids(pids, centroid_scores, codes, doclens, offsets, idx, nfiltered_d
     s2c = torch.empty(1, device=dev, dtype=torch.int32)
     codes, offsets = _cu(codes, torch.int32), _cu(offsets, torch.int64)   # named: must outlive the launch
     check_codes(codes, C)
-    _lib.call("plaid_filter_pids", _p(pid_buf), _p(counts), 1, stride, _p(S), _p(qlens), _p(bits), C,
+    _lib.call("plaid_filter_pids", _p(pid_buf), _p(counts), 1, stride, _p(S), 0, _p(qlens), _p(bits), C,
               _p(codes), _p(offsets), ndocs, _p(ws_scores), _p(ws_keys),
               _p(s1p), _p(s1s), _p(s1c), _p(s2p), _p(s2s), _p(s2c), _stream())
     n1, n2 = min(n, ndocs), min(n, ndocs // 4)

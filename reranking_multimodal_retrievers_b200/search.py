@@ -36,7 +36,8 @@ class IndexScorer:
             self.index_path = None
             host = index_path
         self.index = DeviceIndex(host, device)
-        self.engine = SearchEngine(self.index)
+        self.engine = SearchEngine(self.index)                              # batched path (Searcher.search_batch)
+        self.engine1 = SearchEngine(self.index, s_dtype=torch.float32)      # single-query API: fp32 centroid_scores
         self.doclens = self.index.doclens
         self.num_embeddings = self.index.num_embeddings
         self.num_partitions = self.index.num_centroids
@@ -51,14 +52,14 @@ class IndexScorer:
         thr = d[1] if thr is None else thr
         ndocs = d[2] if ndocs is None else ndocs
         Lq_pad = ((Q.shape[1] + 31) // 32) * 32
-        ws = self.engine._workspace(4, Lq_pad, int(ncells), int(ndocs), int(ndocs) // 4)
+        ws = self.engine1._workspace(4, Lq_pad, int(ncells), int(ndocs), int(ndocs) // 4)
         return Q, ws, int(ncells), float(thr), int(ndocs), Lq_pad
 
     def retrieve(self, config, Q):
         """(candidate pids i32 sorted unique, centroid_scores f32 [C, nq]) -- index_storage.py:67-80."""
         Q, ws, ncells, thr, ndocs, Lq_pad = self._prep(config, Q)
         Qd = ops._cu(Q, torch.float32)
-        self.engine.stage_candidates(ws, Qd, Lq_pad, ncells, thr, False, 4)
+        self.engine1.stage_candidates(ws, Qd, Lq_pad, ncells, thr, False, 4)
         n = int(ws["cand_counts"][0].item())
         nq = min(int(ws["qlens"][0].item()), int(getattr(config, "query_maxlen", 32) or 32), ops.NQ_MAX)
         self._last = (ws, Lq_pad, ndocs)
@@ -86,7 +87,7 @@ class IndexScorer:
         if pids.data_ptr() != ws["cand_pids"].data_ptr():
             ws["cand_pids"][0, :n] = pids
         ws["cand_counts"][0] = n
-        self.engine.stage_rank(ws, 1, Lq_pad, ndocs, ndocs // 4, 4)
+        self.engine1.stage_rank(ws, 1, Lq_pad, ndocs, ndocs // 4, 4)
         m = int(ws["s2_counts"][0].item())
         return ws["scores"][0, :m].clone(), ws["s2_pids"][0, :m].clone()
 

@@ -61,7 +61,7 @@ def test_fullsize_properties_and_oracle_sample(N, B):
     t = eng.last_taps
     Qc = Q.cpu()
     for b in (0, 3, 7):
-        S = t.S[b].cpu().contiguous()
+        S = t.S[b].float().cpu().contiguous()
         r = po.rank(ix, Qc[b], 2, 0.45, 1024, S_override=S, taps=True)
         assert torch.equal(t.cand_pids[b, :int(t.cand_counts[b])].cpu(), r["candidates"])
         assert torch.equal(t.stage1_pids[b, :1024].cpu(), r["stage1_pids"])

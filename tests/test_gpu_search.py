@@ -25,16 +25,20 @@ def pkg():
     return p
 
 
-def _engine(g, fused=True):
+def _engine(g, fused=True, s_dtype=torch.float16):
     from reranking_multimodal_retrievers_b200.engine import SearchEngine
     from reranking_multimodal_retrievers_b200.index import DeviceIndex
-    return SearchEngine(DeviceIndex(golden_host_index(g)), fused=fused)
+    return SearchEngine(DeviceIndex(golden_host_index(g)), fused=fused, s_dtype=s_dtype)
 
 
-def test_centroid_scores_tcgen05(pkg, golden):
+S_DTYPES = [torch.float32, torch.float16]
+
+
+@pytest.mark.parametrize("s_dtype", S_DTYPES)
+def test_centroid_scores_tcgen05(pkg, golden, s_dtype):
     from reranking_multimodal_retrievers_b200 import ops
     g = golden
-    eng = _engine(g)
+    eng = _engine(g, s_dtype=s_dtype)
     ix = golden_oracle_index(g)
     Q = torch.from_numpy(g["Q"])
     B = Q.shape[0]
@@ -48,15 +52,21 @@ def test_centroid_scores_tcgen05(pkg, golden):
         q = nonzero_rows(Q[b])
         nq = min(32, q.shape[0])
         assert int(t.qlens[b]) == q.shape[0]
-        S = t.S[b, :, :nq].cpu()
+        assert t.S.dtype == s_dtype
+        S = t.S[b, :, :nq].float().cpu()
         # (1) same bf16-rounded operands, fp32 accumulate: only the summation order differs
+        #     (fp16 storage: the stored value is that sum rounded to nearest fp16, |S| < 1 -> ulp <= 2^-11)
         S_ref_b = cent_b @ q[:nq].bfloat16().float().T
-        torch.testing.assert_close(S, S_ref_b, rtol=0, atol=2e-6)
+        if s_dtype == torch.float32:
+            torch.testing.assert_close(S, S_ref_b, rtol=0, atol=2e-6)
+        else:
+            assert (S - S_ref_b).abs().max() <= 2 ** -12 + 2e-6
+            assert (S != S_ref_b.half().float()).float().mean() < 1e-3
         # (2) against the fp32 reference table
         if f"S_{b}" in g:
             assert np.abs(S.numpy() - g[f"S_{b}"]).max() <= S_ABS_TOL
         # padded token lanes are exact zeros
-        assert torch.count_nonzero(t.S[b, :, nq:]) == 0
+        assert torch.count_nonzero(t.S[b, :, nq:].float()) == 0
         # pruning mask and cells are functions of OUR table: bit-exact
         idx = ops.unpack_idx_bits(t.idx_bits[b], S.shape[0]).cpu()
         assert torch.equal(idx, po.centroid_mask(S, thr))
@@ -65,10 +75,11 @@ def test_centroid_scores_tcgen05(pkg, golden):
         assert torch.all(t.cells[b, nq:] == -1)
 
 
-def test_pipeline_stagewise_bit_exact_with_injected_table(pkg, golden):
+@pytest.mark.parametrize("s_dtype", S_DTYPES)
+def test_pipeline_stagewise_bit_exact_with_injected_table(pkg, golden, s_dtype):
     from reranking_multimodal_retrievers_b200 import ops
     g = golden
-    eng = _engine(g, fused=False)      # the unfused kernel pair materialises D, which this test inspects
+    eng = _engine(g, fused=False, s_dtype=s_dtype)   # the unfused kernel pair materialises D, which this test inspects
     ix = golden_oracle_index(g)
     Q = torch.from_numpy(g["Q"])
     B = Q.shape[0]
@@ -79,7 +90,7 @@ def test_pipeline_stagewise_bit_exact_with_injected_table(pkg, golden):
     t = eng.last_taps
     # the fused kernel (decompression feeding the tensor cores through shared memory) builds the very same
     # bf16 operand tiles, so its scores and ranking are bit-identical to the unfused pair's
-    engf = _engine(g, fused=True)
+    engf = _engine(g, fused=True, s_dtype=s_dtype)
     pf, sf, cf = engf.search_batch(Q, k=k, ncells=ncells, centroid_score_threshold=thr, ndocs=ndocs,
                                    remove_zero_rows=True, keep_taps=True)
     engf.check_flags()
@@ -90,7 +101,7 @@ def test_pipeline_stagewise_bit_exact_with_injected_table(pkg, golden):
     for b in range(B):
         q = nonzero_rows(Q[b])
         nq = min(32, q.shape[0])
-        S = t.S[b, :, :nq].cpu().contiguous()
+        S = t.S[b, :, :nq].float().cpu().contiguous()
         r = po.rank(ix, q, ncells, thr, ndocs, S_override=S, taps=True)
         nc = int(t.cand_counts[b])
         assert torch.equal(t.cand_pids[b, :nc].cpu(), r["candidates"])                     # sorted unique pids
@@ -154,7 +165,7 @@ def test_search_all_bit_widths_and_query_lengths(pkg, nbits, Lq, lo, hi, zero_ro
     for b in range(Q.shape[0]):
         q = nonzero_rows(Q[b])
         nq = min(32, q.shape[0])
-        S = t.S[b, :, :nq].cpu().contiguous()
+        S = t.S[b, :, :nq].float().cpu().contiguous()
         r = po.rank(ix, q, ncells, thr, ndocs, S_override=S, taps=True)
         n2 = int(t.stage2_counts[b])
         assert torch.equal(t.stage2_pids[b, :n2].cpu(), r["stage2_pids"])
