@@ -78,11 +78,13 @@ int plaid_centroid_scores(const void* centroids_bf16, int C, const void* Qb_bf16
  * takes the union of their IVF pid lists and emits it sorted + unique through a per-query pid
  * bitmap: bitmap_ws [B, ceil(N/32)] u32 (zeroed by the call), cand_pids [B, cand_stride] i32
  * ascending, cand_counts[b].  If a query would need more than cand_stride slots the list is
- * truncated and *overflow is set to 1. */
+ * truncated and *overflow is set to 1.  wprefix (optional, may be NULL): i32 [B, ceil(N/32)], number of
+ * candidates before each bitmap word, so that rank(pid) = wprefix[pid/32] + popc(word & ((1 << pid%32) - 1))
+ * (used by plaid_filter_stage1_ivf). */
 int plaid_candidates(const float* cell_val, const int32_t* cell_idx, const int32_t* qlens, int B, int ncells,
                      int nlists, const int32_t* ivf_pids, const int64_t* ivf_offsets, int C, int N,
                      int32_t* cells, uint32_t* bitmap_ws, int32_t* cand_pids, int32_t* cand_counts,
-                     int cand_stride, int* overflow, void* stream);
+                     int cand_stride, int* overflow, int32_t* wprefix, void* stream);
 
 /* ---- a5: filter_pids (CB/search/filter_pids.cpp:27-164) ---------------------------------------
  * Approximate score of every listed passage: sum over k < nq_b (sequential fp32, in k order) of
@@ -93,6 +95,20 @@ int plaid_candidates(const float* cell_val, const int32_t* cell_idx, const int32
 int plaid_approx_scores(const int32_t* pids, const int32_t* counts, int B, int pid_stride, const void* S,
                         int s_is_f16, const int32_t* qlens, const uint32_t* idx_bits, int C, const int32_t* codes,
                         const int64_t* offsets, float* out_scores, void* stream);
+
+/* Stage 1 of the filter driven by the inverted file (same result as plaid_approx_scores with idx_bits, bit for
+ * bit): for every surviving centroid (idx bit set) its IVF list names the passages that contain it; the candidate
+ * bitmap / word-prefix counts (plaid_candidates) turn those into candidate slots; the (slot, centroid) pairs are
+ * counting-sorted per query in shared memory and reduced.  Queries whose mask is dense (more than cap_s
+ * survivors, more than 4*cap_p list entries to visit, more pairs than cap_p, or more candidates than fit the
+ * sort) are routed through the token scan instead -- decided per query on the device, no host round trip.
+ * Workspaces: ws_surv i32 [B, cap_s], ws_pair_slot / ws_pair_c / ws_sorted_c i32 [B, cap_p], ws_meta i32 [B, 4]. */
+int plaid_filter_stage1_ivf(const int32_t* pids, const int32_t* counts, int B, int pid_stride, const void* S,
+                            int s_is_f16, const int32_t* qlens, const uint32_t* idx_bits, int C,
+                            const int32_t* codes, const int64_t* offsets, const int32_t* ivf_pids,
+                            const int64_t* ivf_offsets, const uint32_t* bitmap, const int32_t* wprefix, int N,
+                            int32_t* ws_surv, int cap_s, int32_t* ws_pair_slot, int32_t* ws_pair_c,
+                            int32_t* ws_sorted_c, int cap_p, int32_t* ws_meta, float* out_scores, void* stream);
 
 /* Per query the `keep` largest (score, pid) pairs in descending (score, pid) order -- the order of
  * std::pair<float,int> in filter_pids.cpp:24,108-123.  Emits min(counts[b], keep) entries

@@ -25,8 +25,10 @@ _SIGNATURES = {
     "plaid_prepare_queries": [_P, _I, _I, _I, _I, _I, _P, _P, _P],
     "plaid_f32_to_bf16": [_P, _P, _I64, _P],
     "plaid_centroid_scores": [_P, _I, _P, _P, _I, _I, _F, _I, _I, _P, _I, _P, _P, _P, _P, _P],
-    "plaid_candidates": [_P, _P, _P, _I, _I, _I, _P, _P, _I, _I, _P, _P, _P, _P, _I, _P, _P],
+    "plaid_candidates": [_P, _P, _P, _I, _I, _I, _P, _P, _I, _I, _P, _P, _P, _P, _I, _P, _P, _P],
     "plaid_approx_scores": [_P, _P, _I, _I, _P, _I, _P, _P, _I, _P, _P, _P, _P],
+    "plaid_filter_stage1_ivf": [_P, _P, _I, _I, _P, _I, _P, _P, _I, _P, _P, _P, _P, _P, _P, _I, _P, _I, _P, _P, _P, _I, _P, _P,
+                                _P],
     "plaid_select_top": [_P, _P, _P, _I, _I, _I, _P, _P, _P, _I, _P, _P],
     "plaid_filter_pids": [_P, _P, _I, _I, _P, _I, _P, _P, _I, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "plaid_build_weight_table": [_P, _P, _P, _I, _P, _P],

@@ -72,7 +72,8 @@ mark_candidates_kernel(const int32_t* __restrict__ cells, int ncells, const int3
 // One CTA per query: scan the bitmap, emit set bits as ascending pids.
 __global__ void __launch_bounds__(1024)
 compact_candidates_kernel(const uint32_t* __restrict__ bitmap, int words, int32_t* __restrict__ cand_pids,
-                          int32_t* __restrict__ cand_counts, int cand_stride, int* __restrict__ overflow) {
+                          int32_t* __restrict__ cand_counts, int cand_stride, int* __restrict__ overflow,
+                          int32_t* __restrict__ wprefix) {
     __shared__ int s_warp[32];
     __shared__ int s_base;
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -104,6 +105,7 @@ compact_candidates_kernel(const uint32_t* __restrict__ bitmap, int words, int32_
         }
         __syncthreads();
         int pos = s_base + s_warp[warp] + incl - cnt;
+        if (wprefix && w < words) wprefix[(size_t)b * words + w] = pos;   // candidates before word w = rank base of its pids
         while (bits) {
             const int bit = __ffs(bits) - 1;
             bits &= bits - 1;
@@ -126,7 +128,7 @@ compact_candidates_kernel(const uint32_t* __restrict__ bitmap, int words, int32_
 extern "C" int plaid_candidates(const float* cell_val, const int32_t* cell_idx, const int32_t* qlens, int B, int ncells,
                                 int nlists, const int32_t* ivf_pids, const int64_t* ivf_offsets, int C, int N,
                                 int32_t* cells, uint32_t* bitmap_ws, int32_t* cand_pids, int32_t* cand_counts,
-                                int cand_stride, int* overflow, void* stream) {
+                                int cand_stride, int* overflow, int32_t* wprefix, void* stream) {
     using namespace plaid;
     PLAID_CHECK_ARG(cell_val && cell_idx && qlens && ivf_pids && ivf_offsets && cells && bitmap_ws && cand_pids &&
                         cand_counts,
@@ -146,7 +148,7 @@ extern "C" int plaid_candidates(const float* cell_val, const int32_t* cell_idx, 
     mark_candidates_kernel<<<dim3(PLAID_NQ_MAX * ncells, B), 256, 0, st>>>(cells, ncells, ivf_pids, ivf_offsets, C, N,
                                                                           words, bitmap_ws);
     PLAID_LAUNCH_OK("mark_candidates_kernel");
-    compact_candidates_kernel<<<B, 1024, 0, st>>>(bitmap_ws, words, cand_pids, cand_counts, cand_stride, overflow);
+    compact_candidates_kernel<<<B, 1024, 0, st>>>(bitmap_ws, words, cand_pids, cand_counts, cand_stride, overflow, wprefix);
     PLAID_LAUNCH_OK("compact_candidates_kernel");
     return PLAID_OK;
 }

@@ -61,8 +61,10 @@ __global__ void __launch_bounds__(kApproxWarps * 32)
 approx_scores_kernel(const int32_t* __restrict__ pids, const int32_t* __restrict__ counts, int pid_stride,
                      const ST* __restrict__ S, const int32_t* __restrict__ qlens,
                      const uint32_t* __restrict__ idx_bits, int C, const int32_t* __restrict__ codes,
-                     const int64_t* __restrict__ offsets, float* __restrict__ out) {
+                     const int64_t* __restrict__ offsets, float* __restrict__ out,
+                     const int32_t* __restrict__ only_flagged, int flag_stride) {
     constexpr int kDocs = kApproxWarps * DPW;
+    if (only_flagged && only_flagged[(size_t)blockIdx.y * flag_stride] == 0) return;   // hybrid stage 1: not this query
     extern __shared__ __align__(16) uint32_t s_dyn[];
     float (*s_max)[33] = reinterpret_cast<float (*)[33]>(s_dyn);      // [kDocs][33]
     uint32_t* s_bits = s_dyn + kDocs * 33;                            // [C/32] (stage 1 only)
@@ -325,7 +327,8 @@ static int next_pow2(int v) {
 template <typename ST>
 static int launch_approx_t(const int32_t* pids, const int32_t* counts, int B, int pid_stride, const ST* S,
                            const int32_t* qlens, const uint32_t* idx_bits, int C, const int32_t* codes,
-                           const int64_t* offsets, float* out, cudaStream_t st) {
+                           const int64_t* offsets, float* out, cudaStream_t st, const int32_t* only_flagged = nullptr,
+                           int flag_stride = 0) {
     PLAID_CHECK_ARG((reinterpret_cast<uintptr_t>(codes) & 15) == 0, PLAID_ERR_ARG, "approx_scores: codes must be 16-byte aligned");
     if (idx_bits) {
         constexpr int kDocs = kApproxWarps * kStage1Dpw;
@@ -340,13 +343,13 @@ static int launch_approx_t(const int32_t* pids, const int32_t* counts, int B, in
             configured = smem;
         }
         dim3 grid((pid_stride + kDocs - 1) / kDocs, B);
-        approx_scores_kernel<true, kStage1Dpw, ST><<<grid, kApproxWarps * 32, smem, st>>>(pids, counts, pid_stride, S, qlens,
-                                                                                         idx_bits, C, codes, offsets, out);
+        approx_scores_kernel<true, kStage1Dpw, ST><<<grid, kApproxWarps * 32, smem, st>>>(
+            pids, counts, pid_stride, S, qlens, idx_bits, C, codes, offsets, out, only_flagged, flag_stride);
     } else {
         constexpr int kDocs = kApproxWarps * kStage2Dpw;
         dim3 grid((pid_stride + kDocs - 1) / kDocs, B);
         approx_scores_kernel<false, kStage2Dpw, ST><<<grid, kApproxWarps * 32, kDocs * 33 * 4, st>>>(
-            pids, counts, pid_stride, S, qlens, nullptr, C, codes, offsets, out);
+            pids, counts, pid_stride, S, qlens, nullptr, C, codes, offsets, out, only_flagged, flag_stride);
     }
     PLAID_LAUNCH_OK("approx_scores_kernel");
     return PLAID_OK;
@@ -360,6 +363,154 @@ static int launch_approx(const int32_t* pids, const int32_t* counts, int B, int 
                                        codes, offsets, out, st);
     return launch_approx_t<float>(pids, counts, B, pid_stride, reinterpret_cast<const float*>(S), qlens, idx_bits, C, codes,
                                   offsets, out, st);
+}
+
+// ------------------------------------------------------------------------------------------ stage 1 via the IVF
+// Stage 1 only needs, for every candidate passage, the set of SURVIVING centroids (pruning mask set) it
+// contains.  Scanning every token of every candidate finds them the hard way; when the mask is sparse the
+// inverted file gives them directly: for each survivor c, ivf[c] lists the passages that contain c, the
+// candidate bitmap says which of them are candidates and the bitmap's word-prefix counts give their slot.
+//   ivf_survivors : per query, compact the mask into a survivor list; estimate the work (sum of list lengths)
+//                   and fall back to the token scan for this query when it is not clearly cheaper;
+//   ivf_pairs     : warp per survivor, emits (slot, centroid) pairs;
+//   ivf_scores    : per query, counting sort of the pairs by slot in shared memory, then per slot the
+//                   per-token max over its survivors' S rows and the sequential fp32 sum (filter_pids.cpp:59-63).
+// The per-token max is order-independent, so the result is bit-identical to the scan.
+static constexpr int kIvfMeta = 4;   // per query: [0] survivors, [1] pairs, [2] use-the-scan flag, [3] visits
+
+__global__ void __launch_bounds__(256)
+ivf_survivors_kernel(const uint32_t* __restrict__ idx_bits, int C, const int64_t* __restrict__ ivf_offsets,
+                     const int32_t* __restrict__ counts, int pid_stride, int max_bins, int cap_s, int max_visits,
+                     int32_t* __restrict__ surv, int32_t* __restrict__ meta) {
+    __shared__ int s_count, s_visits;
+    const int b = blockIdx.x;
+    if (threadIdx.x == 0) { s_count = 0; s_visits = 0; }
+    __syncthreads();
+    const uint32_t* bits = idx_bits + (size_t)b * (C >> 5);
+    int visits = 0;
+    for (int w = threadIdx.x; w < (C >> 5); w += blockDim.x) {
+        uint32_t x = bits[w];
+        while (x) {
+            const int c = (w << 5) + __ffs(x) - 1;
+            x &= x - 1;
+            const int slot = atomicAdd(&s_count, 1);
+            if (slot < cap_s) surv[(size_t)b * cap_s + slot] = c;
+            visits += (int)min((int64_t)(1 << 24), ivf_offsets[c + 1] - ivf_offsets[c]);
+        }
+    }
+    if (visits) atomicAdd(&s_visits, min(visits, 1 << 28));
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int n = min(counts[b], pid_stride);
+        int32_t* m = meta + (size_t)b * kIvfMeta;
+        m[0] = min(s_count, cap_s);
+        m[1] = 0;
+        m[2] = (s_count > cap_s || s_visits > max_visits || n > max_bins) ? 1 : 0;
+        m[3] = s_visits;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+ivf_pairs_kernel(const int32_t* __restrict__ surv, int cap_s, int32_t* __restrict__ meta,
+                 const int32_t* __restrict__ ivf_pids, const int64_t* __restrict__ ivf_offsets,
+                 const uint32_t* __restrict__ bitmap, const int32_t* __restrict__ wprefix, int words, int N,
+                 int32_t* __restrict__ pair_slot, int32_t* __restrict__ pair_c, int cap_p) {
+    const int b = blockIdx.y, lane = threadIdx.x & 31;
+    int32_t* m = meta + (size_t)b * kIvfMeta;
+    if (m[2]) return;
+    const int si = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (si >= m[0]) return;
+    const int c = surv[(size_t)b * cap_s + si];
+    const int64_t lo = ivf_offsets[c], hi = ivf_offsets[c + 1];
+    const uint32_t* bm = bitmap + (size_t)b * words;
+    const int32_t* wp = wprefix + (size_t)b * words;
+    for (int64_t i = lo + lane; i < hi; i += 32) {
+        const unsigned pid = (unsigned)ld_stream_s32(ivf_pids + i);
+        if (pid >= (unsigned)N) continue;
+        const uint32_t word = __ldg(bm + (pid >> 5));
+        if ((word >> (pid & 31)) & 1u) {
+            const int slot = __ldg(wp + (pid >> 5)) + __popc(word & ((1u << (pid & 31)) - 1u));
+            const int idx = atomicAdd(&m[1], 1);
+            if (idx < cap_p) {
+                pair_slot[(size_t)b * cap_p + idx] = slot;
+                pair_c[(size_t)b * cap_p + idx] = c;
+            } else {
+                m[2] = 1;   // too many pairs for the workspace: this query goes through the scan
+            }
+        }
+    }
+}
+
+template <typename ST>
+__global__ void __launch_bounds__(512)
+ivf_scores_kernel(const int32_t* __restrict__ counts, int pid_stride, const int32_t* __restrict__ meta,
+                  const int32_t* __restrict__ pair_slot, const int32_t* __restrict__ pair_c, int32_t* __restrict__ sorted_c,
+                  int cap_p, const ST* __restrict__ S, int C, const int32_t* __restrict__ qlens, float* __restrict__ out) {
+    extern __shared__ __align__(16) int s_bins[];          // [n + 1] then [16 warps][32][33] floats
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+    const int32_t* m = meta + (size_t)b * kIvfMeta;
+    if (m[2]) return;
+    const int n = min(counts[b], pid_stride);
+    const int np = min(m[1], cap_p);
+    float (*s_max)[33] = reinterpret_cast<float (*)[33]>(s_bins + ((n + 1 + 3) & ~3)) + warp * 32;
+    __shared__ int s_part[512];
+    const int32_t* ps = pair_slot + (size_t)b * cap_p;
+    const int32_t* pc = pair_c + (size_t)b * cap_p;
+    int32_t* sc = sorted_c + (size_t)b * cap_p;
+    for (int i = tid; i <= n; i += blockDim.x) s_bins[i] = 0;
+    __syncthreads();
+    for (int i = tid; i < np; i += blockDim.x) atomicAdd(&s_bins[ps[i] + 1], 1);   // count of slot s in bins[s + 1]
+    __syncthreads();
+    // exclusive scan over bins[0..n]: thread t owns a contiguous span
+    const int span = (n + 1 + blockDim.x - 1) / blockDim.x;
+    const int lo = min(tid * span, n + 1), hi = min(lo + span, n + 1);
+    int sum = 0;
+    for (int i = lo; i < hi; i++) sum += s_bins[i];
+    s_part[tid] = sum;
+    __syncthreads();
+    if (warp == 0) {   // scan the 512 partial sums: 16 per lane
+        int loc[16], tot = 0;
+#pragma unroll
+        for (int u = 0; u < 16; u++) { loc[u] = tot; tot += s_part[lane * 16 + u]; }
+        int incl = tot;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        const int base = incl - tot;
+#pragma unroll
+        for (int u = 0; u < 16; u++) s_part[lane * 16 + u] = base + loc[u];
+    }
+    __syncthreads();
+    int run = s_part[tid];
+    for (int i = lo; i < hi; i++) { const int v = s_bins[i]; s_bins[i] = run + v; run += v; }   // inclusive: bins[s+1]... see below
+    __syncthreads();
+    // now bins[i] = number of pairs with slot < i  (inclusive scan of the shifted counts); start(s) = bins[s]
+    // scatter: cursor = start(s); afterwards bins[s] = end(s) and start(s) = (s ? bins[s-1] : 0)
+    for (int i = tid; i < np; i += blockDim.x) sc[atomicAdd(&s_bins[ps[i]], 1)] = pc[i];
+    __syncthreads();
+    const int nq = min(qlens[b], PLAID_NQ_MAX);
+    const ST* Sb = S + (size_t)b * C * PLAID_NQ_MAX + lane;
+    for (int base = warp * 32; base < n; base += nw * 32) {
+        for (int j = 0; j < 32; j++) {
+            const int s = base + j;
+            float mx = -9999.0f;  // filter_pids.cpp:30-33
+            if (s < n) {
+                const int beg = s ? s_bins[s - 1] : 0, end = s_bins[s];
+                for (int i = beg; i < end; i++) mx = fmaxf(mx, load_s(Sb + (size_t)(unsigned)sc[i] * PLAID_NQ_MAX));
+            }
+            s_max[j][lane] = mx;
+        }
+        __syncwarp();
+        const int s = base + lane;
+        if (s < n) {
+            float acc = 0.0f;  // sequential fp32 sum in token order (filter_pids.cpp:59-63)
+            for (int k = 0; k < nq; k++) acc += s_max[lane][k];
+            out[(size_t)b * pid_stride + s] = acc;
+        }
+        __syncwarp();
+    }
 }
 
 static int launch_select(const int32_t* pids, const float* scores, const int32_t* counts, int B, int in_stride, int keep,
@@ -394,6 +545,57 @@ extern "C" int plaid_approx_scores(const int32_t* pids, const int32_t* counts, i
     PLAID_CHECK_ARG(B <= 65535, PLAID_ERR_UNSUPPORTED, "plaid_approx_scores: B=%d > 65535 per call", B);
     return launch_approx(pids, counts, B, pid_stride, S, s_is_f16, qlens, idx_bits, C, codes, offsets, out_scores,
                          (cudaStream_t)stream);
+}
+
+extern "C" int plaid_filter_stage1_ivf(const int32_t* pids, const int32_t* counts, int B, int pid_stride, const void* S,
+                                       int s_is_f16, const int32_t* qlens, const uint32_t* idx_bits, int C,
+                                       const int32_t* codes, const int64_t* offsets, const int32_t* ivf_pids,
+                                       const int64_t* ivf_offsets, const uint32_t* bitmap, const int32_t* wprefix, int N,
+                                       int32_t* ws_surv, int cap_s, int32_t* ws_pair_slot, int32_t* ws_pair_c,
+                                       int32_t* ws_sorted_c, int cap_p, int32_t* ws_meta, float* out_scores, void* stream) {
+    using namespace plaid;
+    PLAID_CHECK_ARG(pids && counts && S && qlens && idx_bits && codes && offsets && ivf_pids && ivf_offsets && bitmap &&
+                        wprefix && ws_surv && ws_pair_slot && ws_pair_c && ws_sorted_c && ws_meta && out_scores,
+                    PLAID_ERR_ARG, "plaid_filter_stage1_ivf: null pointer");
+    PLAID_CHECK_ARG(B >= 0 && pid_stride >= 1 && C > 0 && (C % 128) == 0 && N > 0 && cap_s >= 8 && cap_p >= 32, PLAID_ERR_ARG,
+                    "plaid_filter_stage1_ivf: bad sizes");
+    if (B == 0) return PLAID_OK;
+    PLAID_CHECK_ARG(B <= 65535, PLAID_ERR_UNSUPPORTED, "plaid_filter_stage1_ivf: B=%d > 65535 per call", B);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int words = (N + 31) / 32;
+    // shared memory of ivf_scores: bins [n+1] + 16 warps x 32 x 33 floats; passages beyond that use the scan
+    const int smem_cap = 200 * 1024;
+    const int smax_bytes = 16 * 32 * 33 * 4;
+    int max_bins = (smem_cap - smax_bytes) / 4 - 8;
+    if (max_bins > pid_stride) max_bins = pid_stride;
+    const int smem = ((max_bins + 1 + 3) & ~3) * 4 + smax_bytes;
+    // the scan costs ~4 bytes per candidate token; the IVF route pays ~12 bytes per list entry visited
+    const int max_visits = cap_p * 4;
+    ivf_survivors_kernel<<<B, 256, 0, st>>>(idx_bits, C, ivf_offsets, counts, pid_stride, max_bins, cap_s, max_visits,
+                                            ws_surv, ws_meta);
+    PLAID_LAUNCH_OK("ivf_survivors_kernel");
+    ivf_pairs_kernel<<<dim3((cap_s + 7) / 8, B), 256, 0, st>>>(ws_surv, cap_s, ws_meta, ivf_pids, ivf_offsets, bitmap,
+                                                                wprefix, words, N, ws_pair_slot, ws_pair_c, cap_p);
+    PLAID_LAUNCH_OK("ivf_pairs_kernel");
+    static int configured = 0;
+    if (smem > configured) {
+        PLAID_CUDA_OK(cudaFuncSetAttribute(ivf_scores_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        PLAID_CUDA_OK(cudaFuncSetAttribute(ivf_scores_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured = smem;
+    }
+    if (s_is_f16)
+        ivf_scores_kernel<__half><<<B, 512, smem, st>>>(counts, pid_stride, ws_meta, ws_pair_slot, ws_pair_c, ws_sorted_c,
+                                                        cap_p, reinterpret_cast<const __half*>(S), C, qlens, out_scores);
+    else
+        ivf_scores_kernel<float><<<B, 512, smem, st>>>(counts, pid_stride, ws_meta, ws_pair_slot, ws_pair_c, ws_sorted_c,
+                                                       cap_p, reinterpret_cast<const float*>(S), C, qlens, out_scores);
+    PLAID_LAUNCH_OK("ivf_scores_kernel");
+    // queries flagged for the scan (dense masks, oversized lists): the token-scan kernel, restricted to them
+    if (s_is_f16)
+        return launch_approx_t<__half>(pids, counts, B, pid_stride, reinterpret_cast<const __half*>(S), qlens, idx_bits, C,
+                                       codes, offsets, out_scores, st, ws_meta + 2, kIvfMeta);
+    return launch_approx_t<float>(pids, counts, B, pid_stride, reinterpret_cast<const float*>(S), qlens, idx_bits, C, codes,
+                                  offsets, out_scores, st, ws_meta + 2, kIvfMeta);
 }
 
 extern "C" int plaid_select_top(const int32_t* pids, const float* scores, const int32_t* counts, int B, int in_stride,

@@ -56,8 +56,11 @@ class StageTaps:
 
 class SearchEngine:
     def __init__(self, index: DeviceIndex, s_budget_bytes: int = 6 << 30, max_chunk: int = 512, fused: bool = True,
-                 s_dtype: torch.dtype = torch.float16):
+                 s_dtype: torch.dtype = torch.float16, ivf_stage1: bool = True):
         self.index = index
+        # stage 1 of the filter through the inverted file (falls back to the token scan per query on the device)
+        self.ivf_stage1 = bool(ivf_stage1)
+        self.cap_s, self.cap_p = 4096, 65536
         # storage precision of the centroid-score table S: fp16 (what the reference's GPU branch computes S in,
         # candidate_generation.py:52; half the bytes to write and to gather) or fp32 (the CPU branch's precision)
         assert s_dtype in (torch.float16, torch.float32)
@@ -106,7 +109,10 @@ class SearchEngine:
             cell_val=e(Bc, NQ_MAX, nlists, ncells, dtype=torch.float32),
             cell_idx=e(Bc, NQ_MAX, nlists, ncells, dtype=torch.int32),
             cells=e(Bc, NQ_MAX, ncells, dtype=torch.int32),
-            bitmap=e(Bc, (N + 31) // 32, dtype=torch.int32),
+            bitmap=e(Bc, (N + 31) // 32, dtype=torch.int32), wprefix=e(Bc, (N + 31) // 32, dtype=torch.int32),
+            surv=e(Bc, self.cap_s, dtype=torch.int32), pair_slot=e(Bc, self.cap_p, dtype=torch.int32),
+            pair_c=e(Bc, self.cap_p, dtype=torch.int32), sorted_c=e(Bc, self.cap_p, dtype=torch.int32),
+            ivf_meta=e(Bc, 4, dtype=torch.int32),
             cand_pids=e(Bc, cand_stride, dtype=torch.int32), cand_counts=e(Bc, dtype=torch.int32),
             ws_scores=e(Bc, fstride, dtype=torch.float32), ws_keys=e(Bc, fstride, dtype=torch.int64),
             s1_pids=e(Bc, ndocs, dtype=torch.int32), s1_scores=e(Bc, ndocs, dtype=torch.float32),
@@ -132,7 +138,7 @@ class SearchEngine:
         return ctypes.c_void_p(self.flags.data_ptr()), ctypes.c_void_p(self.flags.data_ptr() + 4)
 
     # kernels launched by each C-ABI entry point (memsets are not kernels)
-    _LAUNCHES = {"plaid_prepare_queries": 1, "plaid_centroid_scores": 1, "plaid_candidates": 3, "plaid_approx_scores": 1,
+    _LAUNCHES = {"plaid_prepare_queries": 1, "plaid_centroid_scores": 1, "plaid_candidates": 3, "plaid_approx_scores": 1, "plaid_filter_stage1_ivf": 4,
                  "plaid_doc_token_offsets": 1, "plaid_decompress_normalize_bf16": 1, "plaid_maxsim_packed": 1,
                  "plaid_maxsim_fused": 1,
                  "plaid_select_top": 1}
@@ -163,7 +169,7 @@ class SearchEngine:
              ncells, ws["csplit"], _p(ws["S"]), int(self.s_dtype == torch.float16), _p(ws["idx_bits"]), _p(ws["cell_val"]), _p(ws["cell_idx"]), wd, st)
         call("candidates", "plaid_candidates", _p(ws["cell_val"]), _p(ws["cell_idx"]), _p(ws["qlens"]), b, ncells, ws["nlists"],
              _p(ix.ivf_pids), _p(ix.ivf_offsets), C, N, _p(ws["cells"]), _p(ws["bitmap"]), _p(ws["cand_pids"]),
-             _p(ws["cand_counts"]), ws["cand_stride"], ovf, st)
+             _p(ws["cand_counts"]), ws["cand_stride"], ovf, _p(ws["wprefix"]), st)
 
     def stage_rank(self, ws, b: int, Lq_pad: int, ndocs: int, k: int, Bc: int):
         """a5-a10: two-stage filter, decompression, exact MaxSim, top-k -- on ws['cand_pids'/'S'/'idx_bits']."""
@@ -175,8 +181,15 @@ class SearchEngine:
         # plaid_filter_pids' four launches issued one by one so each can be timed on its own
         cs, fs, nd4_ = ws["cand_stride"], ws["fstride"], ndocs // 4
         f16 = int(self.s_dtype == torch.float16)
-        call("filter_stage1", "plaid_approx_scores", _p(ws["cand_pids"]), _p(ws["cand_counts"]), b, cs, _p(ws["S"]), f16,
-             _p(ws["qlens"]), _p(ws["idx_bits"]), C, _p(ix.codes), _p(ix.offsets), _p(ws["ws_scores"]), st)
+        if self.ivf_stage1:
+            call("filter_stage1", "plaid_filter_stage1_ivf", _p(ws["cand_pids"]), _p(ws["cand_counts"]), b, cs, _p(ws["S"]),
+                 f16, _p(ws["qlens"]), _p(ws["idx_bits"]), C, _p(ix.codes), _p(ix.offsets), _p(ix.ivf_pids),
+                 _p(ix.ivf_offsets), _p(ws["bitmap"]), _p(ws["wprefix"]), ix.num_passages, _p(ws["surv"]), self.cap_s,
+                 _p(ws["pair_slot"]), _p(ws["pair_c"]), _p(ws["sorted_c"]), self.cap_p, _p(ws["ivf_meta"]),
+                 _p(ws["ws_scores"]), st)
+        else:
+            call("filter_stage1", "plaid_approx_scores", _p(ws["cand_pids"]), _p(ws["cand_counts"]), b, cs, _p(ws["S"]), f16,
+                 _p(ws["qlens"]), _p(ws["idx_bits"]), C, _p(ix.codes), _p(ix.offsets), _p(ws["ws_scores"]), st)
         call("select1", "plaid_select_top", _p(ws["cand_pids"]), _p(ws["ws_scores"]), _p(ws["cand_counts"]), b, cs, ndocs,
              _p(ws["s1_pids"]), _p(ws["s1_scores"]), _p(ws["s1_counts"]), ndocs, _p(ws["ws_keys"]), st)
         call("filter_stage2", "plaid_approx_scores", _p(ws["s1_pids"]), _p(ws["s1_counts"]), b, ndocs, _p(ws["S"]), f16,

@@ -177,6 +177,39 @@ def test_search_all_bit_widths_and_query_lengths(pkg, nbits, Lq, lo, hi, zero_ro
         assert int(pids[b, 0]) == int(r["pids"][0])
 
 
+@pytest.mark.parametrize("thr,cap_s,cap_p", [(0.45, 4096, 65536), (0.45, 4096, 64), (0.45, 8, 65536), (0.1, 4096, 65536),
+                                             (0.25, 4096, 65536), (-1.0, 4096, 65536)])
+def test_stage1_ivf_route_equals_token_scan(pkg, golden, thr, cap_s, cap_p):
+    """Stage 1 through the inverted file vs the token scan: identical lists and scores, whichever route the device
+    picks per query (sparse masks -> IVF pairs; dense masks / workspace overflow -> scan)."""
+    from reranking_multimodal_retrievers_b200.engine import SearchEngine
+    from reranking_multimodal_retrievers_b200.index import DeviceIndex
+    g = golden
+    ix = DeviceIndex(golden_host_index(g))
+    Q = torch.from_numpy(g["Q"])
+    kw = dict(k=int(g["k"]), ncells=int(g["ncells"]), centroid_score_threshold=thr, ndocs=int(g["ndocs"]),
+              remove_zero_rows=True, keep_taps=True)
+    a = SearchEngine(ix, ivf_stage1=True)
+    a.cap_s, a.cap_p = cap_s, cap_p
+    b = SearchEngine(ix, ivf_stage1=False)
+    ra, rb = a.search_batch(Q, **kw), b.search_batch(Q, **kw)
+    a.check_flags(); b.check_flags()
+    ta, tb = a.last_taps, b.last_taps
+    for x, y in zip(ra, rb):
+        assert torch.equal(x, y)
+    B = Q.shape[0]
+    assert torch.equal(ta.stage1_counts[:B], tb.stage1_counts[:B])
+    for q in range(B):
+        n1 = int(ta.stage1_counts[q])
+        assert torch.equal(ta.stage1_pids[q, :n1], tb.stage1_pids[q, :n1])
+        assert torch.equal(ta.stage1_scores[q, :n1], tb.stage1_scores[q, :n1])
+    used_scan = a._ws["ivf_meta"][:B, 2].cpu()
+    if thr == 0.45 and cap_s == 4096 and cap_p == 65536:
+        assert int(used_scan.sum()) == 0            # sparse masks: every query went through the IVF
+    if cap_p == 64 or cap_s == 8 or thr <= 0.1:
+        assert int(used_scan.sum()) == B            # forced / dense: every query fell back to the scan
+
+
 def test_colbert_score_padded_vs_reference(pkg, golden):
     g = golden
     Q, D, mask = (torch.from_numpy(g[n]) for n in ("cs_Q", "cs_D", "cs_mask"))
