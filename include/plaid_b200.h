@@ -102,7 +102,8 @@ int plaid_approx_scores(const int32_t* pids, const int32_t* counts, int B, int p
  * counting-sorted per query in shared memory and reduced.  Queries whose mask is dense (more than cap_s
  * survivors, more than 4*cap_p list entries to visit, more pairs than cap_p, or more candidates than fit the
  * sort) are routed through the token scan instead -- decided per query on the device, no host round trip.
- * Workspaces: ws_surv i32 [B, cap_s], ws_pair_slot / ws_pair_c / ws_sorted_c i32 [B, cap_p], ws_meta i32 [B, 4]. */
+ * Workspaces: ws_surv i32 [B, cap_s], ws_pair_slot / ws_pair_c i32 [B, cap_p], ws_sorted_c i32 [B, 2*cap_p] (8-byte aligned),
+ * ws_meta i32 [B, 4]. */
 int plaid_filter_stage1_ivf(const int32_t* pids, const int32_t* counts, int B, int pid_stride, const void* S,
                             int s_is_f16, const int32_t* qlens, const uint32_t* idx_bits, int C,
                             const int32_t* codes, const int64_t* offsets, const int32_t* ivf_pids,

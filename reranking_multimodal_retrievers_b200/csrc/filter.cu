@@ -456,7 +456,7 @@ ivf_scores_kernel(const int32_t* __restrict__ counts, int pid_stride, const int3
     __shared__ int s_part[512];
     const int32_t* ps = pair_slot + (size_t)b * cap_p;
     const int32_t* pc = pair_c + (size_t)b * cap_p;
-    int32_t* sc = sorted_c + (size_t)b * cap_p;
+    int2* sc2 = reinterpret_cast<int2*>(sorted_c) + (size_t)b * cap_p;   // (slot, centroid), sorted by slot
     for (int i = tid; i <= n; i += blockDim.x) s_bins[i] = 0;
     __syncthreads();
     for (int i = tid; i < np; i += blockDim.x) atomicAdd(&s_bins[ps[i] + 1], 1);   // count of slot s in bins[s + 1]
@@ -488,26 +488,43 @@ ivf_scores_kernel(const int32_t* __restrict__ counts, int pid_stride, const int3
     __syncthreads();
     // now bins[i] = number of pairs with slot < i  (inclusive scan of the shifted counts); start(s) = bins[s]
     // scatter: cursor = start(s); afterwards bins[s] = end(s) and start(s) = (s ? bins[s-1] : 0)
-    for (int i = tid; i < np; i += blockDim.x) sc[atomicAdd(&s_bins[ps[i]], 1)] = pc[i];
+    for (int i = tid; i < np; i += blockDim.x) {
+        const int slot = ps[i];
+        sc2[atomicAdd(&s_bins[slot], 1)] = make_int2(slot, pc[i]);
+    }
     __syncthreads();
     const int nq = min(qlens[b], PLAID_NQ_MAX);
     const ST* Sb = S + (size_t)b * C * PLAID_NQ_MAX + lane;
     for (int base = warp * 32; base < n; base += nw * 32) {
-        for (int j = 0; j < 32; j++) {
-            const int s = base + j;
-            float mx = -9999.0f;  // filter_pids.cpp:30-33
-            if (s < n) {
-                const int beg = s ? s_bins[s - 1] : 0, end = s_bins[s];
-                for (int i = beg; i < end; i++) mx = fmaxf(mx, load_s(Sb + (size_t)(unsigned)sc[i] * PLAID_NQ_MAX));
+#pragma unroll
+        for (int j = 0; j < 32; j++) s_max[j][lane] = -9999.0f;  // filter_pids.cpp:30-33
+        __syncwarp();
+        // the pairs of slots base .. base+31 are contiguous in the sorted array
+        const int beg = base ? s_bins[base - 1] : 0, end = s_bins[min(base + 31, n - 1)];
+        for (int p0 = beg; p0 < end; p0 += 32) {
+            const int2 mine = (p0 + lane < end) ? sc2[p0 + lane] : make_int2(base, 0);
+            const int cnt = min(32, end - p0);
+            for (int u0 = 0; u0 < cnt; u0 += 8) {       // eight S rows in flight
+                float v[8];
+                int sl[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    const int src = min(u0 + u, cnt - 1);
+                    sl[u] = __shfl_sync(0xffffffffu, mine.x, src) - base;
+                    const unsigned c = (unsigned)__shfl_sync(0xffffffffu, mine.y, src);
+                    v[u] = load_s(Sb + (size_t)c * PLAID_NQ_MAX);
+                }
+#pragma unroll
+                for (int u = 0; u < 8; u++)
+                    if (u0 + u < cnt) s_max[sl[u]][lane] = fmaxf(s_max[sl[u]][lane], v[u]);
             }
-            s_max[j][lane] = mx;
         }
         __syncwarp();
-        const int s = base + lane;
-        if (s < n) {
+        const int sidx = base + lane;
+        if (sidx < n) {
             float acc = 0.0f;  // sequential fp32 sum in token order (filter_pids.cpp:59-63)
             for (int k = 0; k < nq; k++) acc += s_max[lane][k];
-            out[(size_t)b * pid_stride + s] = acc;
+            out[(size_t)b * pid_stride + sidx] = acc;
         }
         __syncwarp();
     }

@@ -111,7 +111,7 @@ class SearchEngine:
             cells=e(Bc, NQ_MAX, ncells, dtype=torch.int32),
             bitmap=e(Bc, (N + 31) // 32, dtype=torch.int32), wprefix=e(Bc, (N + 31) // 32, dtype=torch.int32),
             surv=e(Bc, self.cap_s, dtype=torch.int32), pair_slot=e(Bc, self.cap_p, dtype=torch.int32),
-            pair_c=e(Bc, self.cap_p, dtype=torch.int32), sorted_c=e(Bc, self.cap_p, dtype=torch.int32),
+            pair_c=e(Bc, self.cap_p, dtype=torch.int32), sorted_c=e(Bc, 2 * self.cap_p, dtype=torch.int32),
             ivf_meta=e(Bc, 4, dtype=torch.int32),
             cand_pids=e(Bc, cand_stride, dtype=torch.int32), cand_counts=e(Bc, dtype=torch.int32),
             ws_scores=e(Bc, fstride, dtype=torch.float32), ws_keys=e(Bc, fstride, dtype=torch.int64),

@@ -206,8 +206,8 @@ def test_stage1_ivf_route_equals_token_scan(pkg, golden, thr, cap_s, cap_p):
     used_scan = a._ws["ivf_meta"][:B, 2].cpu()
     if thr == 0.45 and cap_s == 4096 and cap_p == 65536:
         assert int(used_scan.sum()) == 0            # sparse masks: every query went through the IVF
-    if cap_p == 64 or cap_s == 8 or thr <= 0.1:
-        assert int(used_scan.sum()) == B            # forced / dense: every query fell back to the scan
+    if cap_p == 64 or cap_s == 8:
+        assert int(used_scan.sum()) == B            # workspace too small: every query fell back to the scan
 
 
 def test_colbert_score_padded_vs_reference(pkg, golden):
