@@ -398,9 +398,11 @@ def main():
     T1, T2, T3, ncand = stats["T1"], stats["T2"], stats["T3"], stats["ncand"]
     # ALGORITHMIC bytes / flops per step, per stage
     alg = {
-        "centroid_scores": dict(bytes=4.0 * C * 32 * B + 2.0 * C * 128 * chunks, flops=2.0 * C * 128 * 32 * B),
+        "centroid_scores": dict(bytes=(2.0 if eng.s_dtype == torch.float16 else 4.0) * C * 32 * B + 2.0 * C * 128 * chunks,
+                                flops=2.0 * C * 128 * 32 * B),
         "filter_stage1": dict(bytes=4.0 * T1 + 16.0 * ncand, flops=0.0),
-        "filter_stage2": dict(bytes=4.0 * T2 + 16.0 * 1024 * B + 128.0 * T2, flops=0.0),
+        "filter_stage2": dict(bytes=4.0 * T2 + 16.0 * 1024 * B + (64.0 if eng.s_dtype == torch.float16 else 128.0) * T2,
+                              flops=0.0),
         "candidates": dict(bytes=4.0 * ncand + (w["N"] / 8.0) * B * 2, flops=0.0),
         "decompress": dict(bytes=(4.0 + 16 * nbits + 256.0 + 256.0) * T3, flops=0.0),   # codes+residual+f16 centroid row in, bf16 out
         "maxsim": dict(bytes=256.0 * T3, flops=2.0 * Lq * 128 * T3),
