@@ -41,22 +41,10 @@ struct CsBarriers {
     int abort_flag;
 };
 
-// Insert (v, c) into the descending list bv/bi[0..ncells) (ties: lower centroid id first); returns the
-// new value of the last entry.  Called only with v > bv[ncells-1].  Deliberately out of line.
-__device__ __noinline__ float topk_insert(float* bv, int* bi, int ncells, float v, int c) {
-    int p = ncells - 1;
-    while (p > 0 && (v > bv[p - 1] || (v == bv[p - 1] && (unsigned)c < (unsigned)bi[p - 1]))) {
-        bv[p] = bv[p - 1];
-        bi[p] = bi[p - 1];
-        p--;
-    }
-    bv[p] = v;
-    bi[p] = c;
-    return bv[ncells - 1];
-}
-
-template <typename ST>   // float: S as the reference's fp32 table; __half: S rounded to fp16 (what the reference's GPU
-                         // branch computes in, candidate_generation.py:52) -- half the bytes to write and to gather
+// ST = float: S as the reference's fp32 table; __half: S rounded to fp16 (what the reference's GPU branch computes in,
+// candidate_generation.py:52) -- half the bytes to write and to gather.  NC = ncells rounded up to 1/2/4/8 (register-
+// resident running top-NC per thread).
+template <typename ST, int NC>
 __global__ void __launch_bounds__(kCsThreads, 1)
 centroid_scores_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_c,
                        const int32_t* __restrict__ qlens, int C, int Lq_pad, float threshold, int ncells, int csplit,
@@ -68,6 +56,7 @@ centroid_scores_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
     uint8_t* sA = smem;                          // [2 k-halves][128 rows][128 B]
     uint8_t* sB = smem + kCsABytes;              // [stage][2 k-halves][256 rows][128 B]
     CsBarriers* bar = reinterpret_cast<CsBarriers*>(smem + kCsABytes + kCsStages * kCsBBytes);
+    __shared__ float s_cut[4][32];   // per (query, token): best NC-th value any of the two column-half warps has seen
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int qgroup = blockIdx.x, split = blockIdx.y;
@@ -84,6 +73,7 @@ centroid_scores_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
         bar->abort_flag = 0;
         fence_mbar_init();
     }
+    if (threadIdx.x < 128) s_cut[threadIdx.x >> 5][threadIdx.x & 31] = -INFINITY;
     if (warp == 2) {
         tmem_alloc(&bar->tmem_base, 512);
         tmem_relinquish();
@@ -143,11 +133,11 @@ centroid_scores_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
         const bool tok_valid = lane < nq;
         ST* Sq = S + (size_t)bq * C * PLAID_NQ_MAX + lane;
         uint32_t* bits_q = idx_bits + (size_t)bq * (C >> 5);
-        float bv[PLAID_NCELLS_MAX];
-        int bi[PLAID_NCELLS_MAX];
+        float bv[NC];
+        int bi[NC];
 #pragma unroll
-        for (int p = 0; p < PLAID_NCELLS_MAX; p++) { bv[p] = -INFINITY; bi[p] = -1; }
-        float cut = -INFINITY;  // current ncells-th best value of this thread
+        for (int p = 0; p < NC; p++) { bv[p] = -INFINITY; bi[p] = -1; }
+        float cut = -INFINITY;  // current ncells-th best value of this thread's own list
         for (int it = 0; it < ntiles; it++) {
             const int acc = it & 1;
             if (!mbar_wait(&bar->tmem_full[acc], (it >> 1) & 1, watchdog)) break;
@@ -190,12 +180,31 @@ centroid_scores_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                         word |= (__any_sync(0xffffffffu, tok_valid && __uint_as_float(r[j]) >= threshold) ? 1u : 0u) << j;
                 }
                 if (lane == 0) bits_q[c0 >> 5] = word;
-                // (3) running top-ncells of this query token (score desc, centroid id asc); a thread gets
-                //     here only ~2 ln(C) times over the whole scan, so the list lives in local memory
-                if (tok_valid && mx > cut) {
+                // (3) running top-ncells of this query token (score desc, centroid id asc).  A value can only matter if
+                //     it beats this list's own ncells-th best AND is not below the ncells-th best the sibling warp (other
+                //     128-column half, same query token) has already seen -- that bound is shared through smem (racy
+                //     reads/writes only ever make the filter weaker, never wrong).
+                const float other = s_cut[quad][lane];
+                if (tok_valid && mx > cut && mx >= other) {
 #pragma unroll
-                    for (int j = 0; j < 32; j++)
-                        if (__uint_as_float(r[j]) > cut) cut = topk_insert(bv, bi, ncells, __uint_as_float(r[j]), c0 + j);
+                    for (int j = 0; j < 32; j++) {
+                        float cv = __uint_as_float(r[j]);
+                        if (cv > cut && cv >= other) {
+                            int ci = c0 + j;
+#pragma unroll
+                            for (int p = 0; p < NC; p++) {
+                                if (p < ncells) {
+                                    const bool ahead = cv > bv[p] || (cv == bv[p] && (unsigned)ci < (unsigned)bi[p]);
+                                    if (ahead) {
+                                        const float tv = bv[p]; bv[p] = cv; cv = tv;
+                                        const int ti = bi[p]; bi[p] = ci; ci = ti;
+                                    }
+                                    if (p == ncells - 1) cut = bv[p];
+                                }
+                            }
+                        }
+                    }
+                    if (cut > other) s_cut[quad][lane] = cut;
                 }
             }
             tc_fence_before();
@@ -205,7 +214,7 @@ centroid_scores_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
         // every (centroid range, column half) keeps its own partial list: slot = split*2 + half
         const size_t base = (((size_t)bq * PLAID_NQ_MAX + lane) * (csplit * 2) + (split * 2 + half)) * ncells;
 #pragma unroll
-        for (int p = 0; p < PLAID_NCELLS_MAX; p++)
+        for (int p = 0; p < NC; p++)
             if (p < ncells) {
                 cell_val[base + p] = bv[p];
                 cell_idx[base + p] = tok_valid ? bi[p] : -1;
@@ -236,21 +245,29 @@ extern "C" int plaid_centroid_scores(const void* centroids_bf16, int C, const vo
     int rc;
     if ((rc = make_bf16_2d_map(&map_q, Qb_bf16, (uint64_t)B_pad * Lq_pad, kDim, 32)) != PLAID_OK) return rc;
     if ((rc = make_bf16_2d_map(&map_c, centroids_bf16, (uint64_t)C, kDim, kCsN)) != PLAID_OK) return rc;
-    static bool configured = false;
-    if (!configured) {
-        PLAID_CUDA_OK(cudaFuncSetAttribute(centroid_scores_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCsSmemBytes));
-        PLAID_CUDA_OK(cudaFuncSetAttribute(centroid_scores_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCsSmemBytes));
-        configured = true;
-    }
     dim3 grid(B_pad / 4, csplit);
-    if (s_is_f16)
-        centroid_scores_kernel<__half><<<grid, kCsThreads, kCsSmemBytes, (cudaStream_t)stream>>>(
-            map_q, map_c, qlens, C, Lq_pad, threshold, ncells, csplit, reinterpret_cast<__half*>(S), idx_bits, cell_val,
-            cell_idx, watchdog);
-    else
-        centroid_scores_kernel<float><<<grid, kCsThreads, kCsSmemBytes, (cudaStream_t)stream>>>(
-            map_q, map_c, qlens, C, Lq_pad, threshold, ncells, csplit, reinterpret_cast<float*>(S), idx_bits, cell_val,
-            cell_idx, watchdog);
+    cudaStream_t st = (cudaStream_t)stream;
+#define PLAID_CS_LAUNCH(ST_, NC_)                                                                                       \
+    do {                                                                                                                \
+        static bool configured = false;                                                                                 \
+        if (!configured) {                                                                                              \
+            PLAID_CUDA_OK(cudaFuncSetAttribute(centroid_scores_kernel<ST_, NC_>,                                        \
+                                               cudaFuncAttributeMaxDynamicSharedMemorySize, kCsSmemBytes));             \
+            configured = true;                                                                                          \
+        }                                                                                                               \
+        centroid_scores_kernel<ST_, NC_><<<grid, kCsThreads, kCsSmemBytes, st>>>(                                       \
+            map_q, map_c, qlens, C, Lq_pad, threshold, ncells, csplit, reinterpret_cast<ST_*>(S), idx_bits, cell_val,   \
+            cell_idx, watchdog);                                                                                        \
+    } while (0)
+    const int nc = ncells <= 1 ? 1 : ncells <= 2 ? 2 : ncells <= 4 ? 4 : 8;
+    if (s_is_f16) {
+        if (nc == 1) PLAID_CS_LAUNCH(__half, 1); else if (nc == 2) PLAID_CS_LAUNCH(__half, 2);
+        else if (nc == 4) PLAID_CS_LAUNCH(__half, 4); else PLAID_CS_LAUNCH(__half, 8);
+    } else {
+        if (nc == 1) PLAID_CS_LAUNCH(float, 1); else if (nc == 2) PLAID_CS_LAUNCH(float, 2);
+        else if (nc == 4) PLAID_CS_LAUNCH(float, 4); else PLAID_CS_LAUNCH(float, 8);
+    }
+#undef PLAID_CS_LAUNCH
     PLAID_LAUNCH_OK("centroid_scores_kernel");
     return PLAID_OK;
 }

@@ -14,6 +14,7 @@ ties are ordered (score desc, pid desc).
 from __future__ import annotations
 
 import ctypes
+import os
 from dataclasses import dataclass
 
 import torch
@@ -94,6 +95,7 @@ class SearchEngine:
         C, N = ix.num_centroids, ix.num_passages
         tiles = (C + 255) // 256
         csplit = max(1, min(tiles, 32, -(-2 * 148 // (Bc // 4))))   # ~2 CTAs per SM; at most 64 partial cell lists
+        csplit = int(os.environ.get("PLAID_CSPLIT", csplit))
         nlists = 2 * csplit
         nd4 = ndocs // 4
         cand_stride = max(ndocs, min(N, NQ_MAX * ncells * max(ix.max_ivf_len, 1)))
