@@ -94,7 +94,9 @@ class SearchEngine:
         dev = ix.device
         C, N = ix.num_centroids, ix.num_passages
         tiles = (C + 255) // 256
-        csplit = max(1, min(tiles, 32, -(-2 * 148 // (Bc // 4))))   # ~2 CTAs per SM; at most 64 partial cell lists
+        groups = Bc // 4                                              # one CTA per 4 queries and centroid range
+        csplit = 1 if groups >= 111 else max(1, min(tiles, 32, -(-148 // groups)))   # fill the 148 SMs once; every extra
+        # range restarts its running top-ncells lists from scratch, which costs more than a partial last wave
         csplit = int(os.environ.get("PLAID_CSPLIT", csplit))
         nlists = 2 * csplit
         nd4 = ndocs // 4
