@@ -47,9 +47,11 @@ const char* plaid_arch(void);
  * Q fp32 [B, Lq, 128] -> per query: rows with sum(|q|) > 0 kept in order (remove_zero_rows != 0),
  * converted to bf16 into Qb [B_pad, Lq_pad, 128] (rows past the kept ones and queries >= B are zero),
  * qlens[b] = rows kept (0 for the padding queries b >= B; qlens has B_pad entries).  B_pad must be a
- * multiple of 4, Lq_pad a multiple of 32 and >= Lq. */
+ * multiple of 4, Lq_pad a multiple of 32 and >= Lq.  Qh_f16 (optional, may be NULL) receives the same
+ * rows rounded to fp16 -- the operand of the search pipeline's MaxSim, which like the reference's GPU
+ * branch (`Q.half()`, CB/search/index_storage.py:164-170) runs on fp16 passage embeddings. */
 int plaid_prepare_queries(const float* Q, int B, int Lq, int remove_zero_rows, int B_pad, int Lq_pad,
-                          void* Qb_bf16, int32_t* qlens, void* stream);
+                          void* Qb_bf16, void* Qh_f16, int32_t* qlens, void* stream);
 
 /* fp32 -> bf16 row conversion used when loading the codebook (round-to-nearest-even). */
 int plaid_f32_to_bf16(const float* src, void* dst_bf16, int64_t n, void* stream);
@@ -168,6 +170,15 @@ int plaid_decompress_normalize_bf16(const int32_t* pids, const int32_t* counts, 
                                     const void* centroids, int centroids_are_f16, int C, int nbits,
                                     void* D_bf16, void* stream);
 
+/* Same placement, in the fp16 arithmetic of the reference's GPU branch: half centroid + half bucket
+ * weight -> half (CB/indexing/codecs/decompress_residuals.cu:35-37), L2-normalised, fp16 rows
+ * (residual.py:273).  This is bit for bit what plaid_maxsim_fused builds in shared memory; the pair
+ * plaid_decompress_normalize_f16 + plaid_maxsim_packed(operands_f16 = 1) is the unfused form of it. */
+int plaid_decompress_normalize_f16(const int32_t* pids, const int32_t* counts, int B, int pid_stride,
+                                   const int32_t* tok_offsets, int tok_stride, const int64_t* offsets,
+                                   const float* W, const uint8_t* residuals, const int32_t* codes,
+                                   const void* centroids_f16, int C, int nbits, void* D_f16, void* stream);
+
 /* ---- a8: colbert_score_packed + segmented_maxsim (CB/modeling/colbert.py:289-311,
  *          CB/modeling/segmented_maxsim.cpp:22-93) ---------------------------------------------
  * scores[b, i] = sum_{k < qlens[b]} max(0, max_{t in passage i} <D[b, t], Qb[b, k]>): a tcgen05
@@ -175,19 +186,23 @@ int plaid_decompress_normalize_bf16(const int32_t* pids, const int32_t* counts, 
  * tokens done in the epilogue straight out of TMEM (the similarity matrix never reaches HBM).
  * clamp_zero = 1 reproduces the zero-initialised max buffer of segmented_maxsim.cpp:58-59.
  * aligned32 = 1 promises that every passage starts on a 32-token boundary of D and that its pad rows are
- * zero (what plaid_doc_token_offsets(align=32) + plaid_decompress_normalize_bf16 produce): with the clamp
- * a zero row cannot change a maximum, so the epilogue never has to split a 32-column chunk. */
-int plaid_maxsim_packed(const void* Qb_bf16, const int32_t* qlens, int B, int B_pad, int Lq_pad,
-                        const void* D_bf16, const int32_t* tok_offsets, const int32_t* counts, int pid_stride,
-                        int tok_stride, int clamp_zero, int aligned32, float* scores, int* watchdog, void* stream);
+ * zero (what plaid_doc_token_offsets(align=32) + plaid_decompress_normalize_* produce): with the clamp
+ * a zero row cannot change a maximum, so the epilogue never has to split a 32-column chunk.
+ * operands_f16 = 1: Q and D hold fp16 instead of bf16 values (same layout, same tensor-core rate). */
+int plaid_maxsim_packed(const void* Q16, const int32_t* qlens, int B, int B_pad, int Lq_pad,
+                        const void* D16, const int32_t* tok_offsets, const int32_t* counts, int pid_stride,
+                        int tok_stride, int clamp_zero, int aligned32, int operands_f16, float* scores,
+                        int* watchdog, void* stream);
 
 /* a6 + a7 + a8 fused, the form the search pipeline runs: the passages listed in pids [B, pid_stride]
- * (counts[b] valid) are decompressed, normalised, rounded to bf16 and contracted with the query on
- * tcgen05 without the passage embeddings ever existing in HBM (decompressor warps write the B operand
- * straight into the swizzled shared-memory layout of the UMMA descriptor).  tok_offsets is what
- * plaid_doc_token_offsets(align = 32) produced for the same pids.  centroids_f16 [C,128] fp16 as stored in
- * centroids.pt.  scores[b, i] as in plaid_maxsim_packed(clamp_zero = 1). */
-int plaid_maxsim_fused(const void* Qb_bf16, const int32_t* qlens, int B, int B_pad, int Lq_pad,
+ * (counts[b] valid) are decompressed and normalised in fp16 (see plaid_decompress_normalize_f16) and
+ * contracted with the fp16 query Qh [B_pad, Lq_pad, 128] on tcgen05 without the passage embeddings ever
+ * existing in HBM (decompressor warps write the B operand straight into the swizzled shared-memory
+ * layout of the UMMA descriptor).  tok_offsets is what plaid_doc_token_offsets(align = 32) produced for
+ * the same pids.  centroids_f16 [C,128] fp16 as stored in centroids.pt; W the fp32 table of
+ * plaid_build_weight_table (rounded to fp16 on load, as `bucket_weights.half()` does, residual.py:40).
+ * scores[b, i] as in plaid_maxsim_packed(clamp_zero = 1). */
+int plaid_maxsim_fused(const void* Qh_f16, const int32_t* qlens, int B, int B_pad, int Lq_pad,
                        const int32_t* pids, const int32_t* counts, int pid_stride, const int32_t* tok_offsets,
                        const int64_t* offsets, const float* W, const uint8_t* residuals, const int32_t* codes,
                        const void* centroids_f16, int C, int nbits, float* scores, int* watchdog, void* stream);

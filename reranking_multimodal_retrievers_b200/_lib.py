@@ -22,7 +22,7 @@ _SIGNATURES = {
     "plaid_abi_version": [],
     "plaid_last_error": [],
     "plaid_arch": [],
-    "plaid_prepare_queries": [_P, _I, _I, _I, _I, _I, _P, _P, _P],
+    "plaid_prepare_queries": [_P, _I, _I, _I, _I, _I, _P, _P, _P, _P],
     "plaid_f32_to_bf16": [_P, _P, _I64, _P],
     "plaid_centroid_scores": [_P, _I, _P, _P, _I, _I, _F, _I, _I, _P, _I, _P, _P, _P, _P, _P],
     "plaid_candidates": [_P, _P, _P, _I, _I, _I, _P, _P, _I, _I, _P, _P, _P, _P, _I, _P, _P, _P],
@@ -36,7 +36,8 @@ _SIGNATURES = {
     "plaid_unpack_residual_codes": [_P, _I64, _I, _P, _P, _P, _P],
     "plaid_doc_token_offsets": [_P, _P, _I, _I, _P, _I, _P, _P],
     "plaid_decompress_normalize_bf16": [_P, _P, _I, _I, _P, _I, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P],
-    "plaid_maxsim_packed": [_P, _P, _I, _I, _I, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P],
+    "plaid_decompress_normalize_f16": [_P, _P, _I, _I, _P, _I, _P, _P, _P, _P, _P, _I, _I, _P, _P],
+    "plaid_maxsim_packed": [_P, _P, _I, _I, _I, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P],
     "plaid_maxsim_fused": [_P, _P, _I, _I, _I, _P, _P, _I, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P, _P],
     "plaid_segmented_maxsim": [_P, _I, _P, _P, _I, _P, _P],
     "plaid_colbert_score_padded": [_P, _P, _I, _I, _I, _P, _P, _I64, _I, _I, _P, _P, _I, _P, _P],
@@ -69,7 +70,7 @@ _LIB = None
 def lib() -> ctypes.CDLL:
     global _LIB
     if _LIB is None:
-        path = _build.LIB_PATH
+        path = os.environ.get("PLAID_B200_LIB") or _build.LIB_PATH     # override: A/B timing of kernel variants
         if not os.path.exists(path):
             path = _build.build_library()  # raises if nvcc is unavailable: no silent fallback
         handle = ctypes.CDLL(path)

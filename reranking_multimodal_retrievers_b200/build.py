@@ -71,6 +71,34 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     return LIB_PATH
 
 
+def build_variant(name: str, defines: list[str], files=("maxsim.cu",)) -> str:
+    """Development aid for A/B timing: rebuilds `files` with extra -D flags and links them with the
+    regular objects into csrc/build/variants/libplaid_b200.<name>.so (select it with PLAID_B200_LIB)."""
+    build_library()
+    vdir = os.path.join(BUILD_DIR, "variants")
+    os.makedirs(vdir, exist_ok=True)
+    objs = []
+    for src in sources():
+        base = os.path.basename(src)
+        obj = os.path.join(BUILD_DIR, base[:-3] + ".o")
+        if base in files:
+            obj = os.path.join(vdir, f"{base[:-3]}.{name}.o")
+            cmd = [NVCC, *NVCC_FLAGS, *[f"-D{d}" for d in defines], "-c", src, "-o", obj]
+            res = subprocess.run(cmd, capture_output=True, text=True)
+            with open(obj + ".log", "w") as f:
+                f.write(" ".join(cmd) + "\n" + res.stdout + res.stderr)
+            if res.returncode != 0:
+                raise RuntimeError(res.stdout + res.stderr)
+        objs.append(obj)
+    out = os.path.join(vdir, f"libplaid_b200.{name}.so")
+    subprocess.check_call([NVCC, "-shared", "-o", out, *objs, "-cudart", "static"])
+    return out
+
+
 if __name__ == "__main__":
+    if "--variant" in sys.argv:
+        i = sys.argv.index("--variant")
+        print(build_variant(sys.argv[i + 1], sys.argv[i + 2:]))
+        sys.exit(0)
     path = build_library(force="--force" in sys.argv, verbose="--verbose" in sys.argv)
     print(path)

@@ -148,6 +148,61 @@ decompress_normalize_kernel(const int32_t* __restrict__ pids, const int32_t* __r
     }
 }
 
+
+// ---- pipeline form in fp16 (the arithmetic of the fused MaxSim kernel, bit for bit): centroid + weight in half,
+// L2 normalise, fp16 rows placed by per-query token offsets; pad rows of the aligned layout are zero ----
+template <int NBITS>
+__global__ void __launch_bounds__(kDecWarps * 32)
+decompress_normalize_f16_kernel(const int32_t* __restrict__ pids, const int32_t* __restrict__ counts, int pid_stride,
+                                const int32_t* __restrict__ tok_offsets, int tok_stride,
+                                const int64_t* __restrict__ offsets, const float* __restrict__ W,
+                                const uint8_t* __restrict__ residuals, const int32_t* __restrict__ codes,
+                                const __half* __restrict__ centroids, __half* __restrict__ D) {
+    __shared__ __align__(128) uint8_t sLUT[kLutBytes];
+    __shared__ __align__(16) uint8_t s_stage[kDecWarps * 512];
+    constexpr int PB = 16 * NBITS, TB = 512 / PB;
+    const int b = blockIdx.y;
+    const int n = min(counts[b], pid_stride);
+    if ((int)blockIdx.x >= n) return;
+    lut_fill_f16<NBITS>(W, sLUT);
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int h = lane & 15, half = lane >> 4;
+    const uint32_t lut_sa = lut_lane_base<NBITS>(smem_u32(sLUT), lane);
+    const uint32_t stage_sa = smem_u32(s_stage + warp * 512);
+    for (int i = blockIdx.x; i < n; i += gridDim.x) {
+        const int pid = pids[(size_t)b * pid_stride + i];
+        const int64_t tok0 = offsets[pid];
+        const int len = (int)(offsets[pid + 1] - tok0);
+        __half* dst = D + ((size_t)b * tok_stride + tok_offsets[(size_t)b * (pid_stride + 1) + i]) * kDim;
+        for (int t0 = warp * TB; t0 < len; t0 += nw * TB) {
+            const int nt = min(TB, len - t0);
+            int4 r = make_int4(0, 0, 0, 0);     // rows past nt stay zero: they decode to finite values nobody stores
+            if (lane * 16 < nt * PB) r = ld_stream_v4(residuals + (tok0 + t0) * PB + lane * 16);
+            sts_v4u32(stage_sa + lane * 16, r.x, r.y, r.z, r.w);
+            const int code = (lane < nt) ? ld_stream_s32(codes + tok0 + t0 + lane) : 0;
+            __syncwarp();
+            for (int j0 = 0; j0 < nt; j0 += 2) {
+                const int j = j0 + half;
+                const unsigned c = (unsigned)__shfl_sync(0xffffffffu, code, j);
+                const uint4 cent = __ldg(reinterpret_cast<const uint4*>(centroids + (size_t)c * kDim) + h);
+                uint32_t w[4], pk[4];
+                __half2 v[4];
+                token_weights_h8<NBITS>(stage_sa + j * PB, lut_sa, h, w);
+                float ss = token_sum_h8(cent, w, v);
+#pragma unroll
+                for (int o = 8; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+                token_scale_h8(v, ss, true, pk);
+                if (j < nt) reinterpret_cast<uint4*>(dst + (size_t)(t0 + j) * kDim)[h] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            }
+            __syncwarp();
+        }
+        const int span = tok_offsets[(size_t)b * (pid_stride + 1) + i + 1] - tok_offsets[(size_t)b * (pid_stride + 1) + i];
+        for (int r = len + (threadIdx.x >> 5); r < span; r += (blockDim.x >> 5))
+            reinterpret_cast<uint2*>(dst + (size_t)r * kDim)[threadIdx.x & 31] = make_uint2(0u, 0u);
+    }
+}
+
 // per query: exclusive prefix sums of passage lengths
 __global__ void __launch_bounds__(256)
 doc_token_offsets_kernel(const int32_t* __restrict__ pids, const int32_t* __restrict__ counts, int pid_stride,
@@ -305,4 +360,35 @@ extern "C" int plaid_decompress_normalize_bf16(const int32_t* pids, const int32_
                                         codes, reinterpret_cast<const __half*>(centroids), C, D, (cudaStream_t)stream);
     return launch_normalize<float>(nbits, pids, counts, B, pid_stride, tok_offsets, tok_stride, offsets, W, residuals, codes,
                                    reinterpret_cast<const float*>(centroids), C, D, (cudaStream_t)stream);
+}
+
+extern "C" int plaid_decompress_normalize_f16(const int32_t* pids, const int32_t* counts, int B, int pid_stride,
+                                              const int32_t* tok_offsets, int tok_stride, const int64_t* offsets,
+                                              const float* W, const uint8_t* residuals, const int32_t* codes,
+                                              const void* centroids_f16, int C, int nbits, void* D_f16, void* stream) {
+    using namespace plaid;
+    PLAID_CHECK_ARG(pids && counts && tok_offsets && offsets && W && residuals && codes && centroids_f16 && D_f16, PLAID_ERR_ARG,
+                    "plaid_decompress_normalize_f16: null pointer");
+    PLAID_CHECK_ARG(B >= 0 && pid_stride >= 1 && tok_stride >= 1 && C > 0, PLAID_ERR_ARG,
+                    "plaid_decompress_normalize_f16: bad sizes");
+    PLAID_CHECK_ARG((reinterpret_cast<uintptr_t>(residuals) & 15) == 0 && (reinterpret_cast<uintptr_t>(centroids_f16) & 15) == 0 &&
+                        (reinterpret_cast<uintptr_t>(D_f16) & 15) == 0,
+                    PLAID_ERR_ARG, "plaid_decompress_normalize_f16: residuals/centroids/D must be 16-byte aligned");
+    if (B == 0) return PLAID_OK;
+    PLAID_CHECK_ARG(B <= 65535, PLAID_ERR_UNSUPPORTED, "plaid_decompress_normalize_f16: B=%d > 65535 per call", B);
+    const __half* cent = reinterpret_cast<const __half*>(centroids_f16);
+    __half* D = reinterpret_cast<__half*>(D_f16);
+    dim3 grid(pid_stride, B);
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (nbits) {
+        case 1: decompress_normalize_f16_kernel<1><<<grid, kDecWarps * 32, 0, st>>>(pids, counts, pid_stride, tok_offsets, tok_stride, offsets, W, residuals, codes, cent, D); break;
+        case 2: decompress_normalize_f16_kernel<2><<<grid, kDecWarps * 32, 0, st>>>(pids, counts, pid_stride, tok_offsets, tok_stride, offsets, W, residuals, codes, cent, D); break;
+        case 4: decompress_normalize_f16_kernel<4><<<grid, kDecWarps * 32, 0, st>>>(pids, counts, pid_stride, tok_offsets, tok_stride, offsets, W, residuals, codes, cent, D); break;
+        case 8: decompress_normalize_f16_kernel<8><<<grid, kDecWarps * 32, 0, st>>>(pids, counts, pid_stride, tok_offsets, tok_stride, offsets, W, residuals, codes, cent, D); break;
+        default:
+            set_error("plaid_decompress_normalize_f16: nbits=%d not in {1,2,4,8}", nbits);
+            return PLAID_ERR_UNSUPPORTED;
+    }
+    PLAID_LAUNCH_OK("decompress_normalize_f16_kernel");
+    return PLAID_OK;
 }

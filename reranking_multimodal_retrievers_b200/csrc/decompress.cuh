@@ -20,8 +20,16 @@ __device__ __forceinline__ float2 lds_v2f32(uint32_t a) {
 __device__ __forceinline__ float4 lds_v4f32(uint32_t a) {
     float4 v; asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a)); return v;
 }
+__device__ __forceinline__ uint4 lds_v4u32(uint32_t a) {
+    uint4 v; asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a)); return v;
+}
 __device__ __forceinline__ void sts_v4u32(uint32_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
     asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" :: "r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+// Same store without the compiler-level memory barrier: ordered against the other volatile shared
+// accesses and the fences/barriers that publish it, but ordinary loads (centroid rows) may move across it.
+__device__ __forceinline__ void sts_v4u32_relaxed(uint32_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" :: "r"(a), "r"(x), "r"(y), "r"(z), "r"(w));
 }
 
 // Bucket weights of the 8 dimensions 8h..8h+7 (h = 0..15) of one token whose packed row sits at shared
@@ -65,6 +73,88 @@ __device__ __forceinline__ void load_centroid8(const __half* c, int h, float (&e
         e[2 * i] = f.x;
         e[2 * i + 1] = f.y;
     }
+}
+
+// ======================= fp16 decoding (search pipeline) =======================
+// The arithmetic of the reference's GPU branch: half centroid + half bucket weight -> half
+// (CB/indexing/codecs/decompress_residuals.cu:35-37), L2-normalised and kept in half
+// (CB/indexing/codecs/residual.py:273).  Used by both the fused MaxSim kernel and
+// plaid_decompress_normalize_f16, so the two produce the same bits.
+//
+// Weight table in shared memory: entry x (a packed residual byte) holds the 8/NBITS fp16 weights it
+// expands to.  Entries are 128 B apart and each is replicated across the 128-byte line, one copy per
+// lane slot: lane l reads copy l % (128 / ES), so the lanes of a wavefront never meet in a bank and the
+// random byte values cost no bank conflicts (the fp32 table of the first version spent ~60% of the
+// shared-memory load wavefronts on them).
+static constexpr int kLutBytes = 256 * 128;
+template <int NBITS> __host__ __device__ constexpr int lut_entry_bytes() { return NBITS == 8 ? 4 : 16 / NBITS; }
+
+template <int NBITS>
+__device__ __forceinline__ void lut_fill_f16(const float* __restrict__ W, uint8_t* lut) {
+    constexpr int ES = lut_entry_bytes<NBITS>(), KEYS = 8 / NBITS, SLOTS = 128 / ES;
+    for (int i = threadIdx.x; i < 256 * SLOTS; i += blockDim.x) {
+        const int e = i / SLOTS, sl = i - e * SLOTS;
+        __half* dst = reinterpret_cast<__half*>(lut + e * 128 + sl * ES);
+#pragma unroll
+        for (int k = 0; k < KEYS; k++) dst[k] = __float2half_rn(W[e * KEYS + k]);
+        if (NBITS == 8) dst[1] = __float2half_rn(0.0f);
+    }
+}
+// shared address of this lane's copy of entry 0
+template <int NBITS>
+__device__ __forceinline__ uint32_t lut_lane_base(uint32_t lut_sa, int lane) {
+    constexpr int ES = lut_entry_bytes<NBITS>();
+    return lut_sa + (uint32_t)(lane & (128 / ES - 1)) * ES;
+}
+// fp16 weights of dimensions 8h..8h+7 of the token whose packed row sits at shared address `row`, as 4 half2 words
+template <int NBITS>
+__device__ __forceinline__ void token_weights_h8(uint32_t row, uint32_t lut, int h, uint32_t (&w)[4]) {
+    if constexpr (NBITS == 2) {
+        const uint32_t x = lds_u16(row + 2 * h);
+        const uint2 a = lds_v2u32(lut + ((x & 0xffu) << 7)), b = lds_v2u32(lut + ((x >> 8) << 7));
+        w[0] = a.x; w[1] = a.y; w[2] = b.x; w[3] = b.y;
+    } else if constexpr (NBITS == 4) {
+        const uint32_t x = lds_u32(row + 4 * h);
+#pragma unroll
+        for (int i = 0; i < 4; i++) w[i] = lds_u32(lut + (((x >> (8 * i)) & 0xffu) << 7));
+    } else if constexpr (NBITS == 1) {
+        const uint32_t x = lds_u8(row + h);
+        const uint4 a = lds_v4u32(lut + (x << 7));
+        w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w;
+    } else {
+        const uint2 x = lds_v2u32(row + 8 * h);
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const uint32_t xx = i < 2 ? x.x : x.y;
+            const uint32_t lo = lds_u16(lut + (((xx >> (16 * (i & 1))) & 0xffu) << 7));
+            const uint32_t hi = lds_u16(lut + (((xx >> (16 * (i & 1) + 8)) & 0xffu) << 7));
+            w[i] = lo | (hi << 16);
+        }
+    }
+}
+
+__device__ __forceinline__ __half2 u32_as_h2(uint32_t u) { return *reinterpret_cast<__half2*>(&u); }
+__device__ __forceinline__ uint32_t h2_as_u32(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
+
+// v = centroid + weight (half2), partial sum of squares of the lane's 8 dims in fp32
+__device__ __forceinline__ float token_sum_h8(const uint4& cent, const uint32_t (&w)[4], __half2 (&v)[4]) {
+    v[0] = __hadd2(u32_as_h2(cent.x), u32_as_h2(w[0]));
+    v[1] = __hadd2(u32_as_h2(cent.y), u32_as_h2(w[1]));
+    v[2] = __hadd2(u32_as_h2(cent.z), u32_as_h2(w[2]));
+    v[3] = __hadd2(u32_as_h2(cent.w), u32_as_h2(w[3]));
+    __half2 s2 = __hmul2(v[0], v[0]);
+    s2 = __hfma2(v[1], v[1], s2);
+    s2 = __hfma2(v[2], v[2], s2);
+    s2 = __hfma2(v[3], v[3], s2);
+    const float2 f = __half22float2(s2);
+    return f.x + f.y;
+}
+// ss = the token's full sum of squares (already reduced over the 16 lanes); x / max(||x||, 1e-12), 0 for pad rows
+__device__ __forceinline__ void token_scale_h8(const __half2 (&v)[4], float ss, bool real, uint32_t (&pk)[4]) {
+    const float inv = real ? rsqrtf(fmaxf(ss, 1e-24f)) : 0.0f;
+    const __half2 i2 = __float2half2_rn(inv);
+#pragma unroll
+    for (int i = 0; i < 4; i++) pk[i] = h2_as_u32(__hmul2(v[i], i2));
 }
 
 }  // namespace plaid

@@ -20,6 +20,13 @@
 #include "common.cuh"
 #include "decompress.cuh"
 
+#ifndef MS_FUSED_CB
+#define MS_FUSED_CB 2      // fused kernel: centroid rows prefetched per batch (token pairs)
+#endif
+#ifndef MS_FUSED_U
+#define MS_FUSED_U 2       // fused kernel: token pairs decoded together
+#endif
+
 namespace plaid {
 
 static constexpr int kMsThreads = 256;   // warps 0-3 epilogue, 4-5 idle, 6 TMA producer, 7 TMEM alloc + MMA issue
@@ -30,6 +37,7 @@ static constexpr int kMsMaxMT = 4;       // Lq_pad <= 512
 struct MsParams {
     const int32_t* qlens;        // [nQ] valid rows per query
     int Lq_pad, MT, NT, NS;
+    int ab_f16;                  // operands (Q and D) are fp16 instead of bf16
     int padded;                  // 0 = packed search form, 1 = padded colbert_score form
     int aligned;                 // packed only: passages start on 32-token boundaries of D, pad rows are zero
     // packed
@@ -132,7 +140,7 @@ __device__ __forceinline__ void ms_mma_issue(const MsParams& p, MsShared* sh, ui
                                              uint32_t tmem_base, int item_begin, int item_end, int lane) {
     const int acc_cols = p.MT * p.NT;
     if (lane == 0) {
-        const uint32_t idesc = umma_idesc_bf16(128, p.NT);
+        const uint32_t idesc = p.ab_f16 ? umma_idesc_f16(128, p.NT) : umma_idesc_bf16(128, p.NT);
         int cur_q = -1, a_loads = 0, it_tile = 0;
         bool ok = true;
         for (int w = item_begin; ok && w < item_end; w++) {
@@ -453,9 +461,11 @@ maxsim_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
 // K-major 128B-swizzled layout the UMMA descriptor expects (16-byte chunk c of row r lands at chunk
 // c ^ (r & 7); rows 128 B apart; the two 64-dim k-halves NT*128 B apart), fenced into the async proxy
 // and handed to the MMA thread through the stage's mbarrier.  Each group of NT/32 warps owns one stage.
-// Per token (half-warp, 8 dims per lane): packed residual byte(s) -> weight table (smem) + fp16 centroid
-// row (one 128-bit L2 load) in fp32, sum of squares over the half-warp, rsqrt, bf16 pack, one 128-bit
-// shared-memory store.  Epilogue = MODE 0 (aligned).
+// Per token (half-warp, 8 dims per lane), in the fp16 arithmetic of the reference's GPU branch: packed
+// residual byte(s) -> fp16 weights from a bank-conflict-free table in shared memory, + fp16 centroid row (one
+// 128-bit L2 load), sum of squares over the half-warp, rsqrt, scale, one 128-bit store into the fp16 tile.
+// Tokens are handled in batches of 4 pairs whose shared loads / shuffles / stores are interleaved in program
+// order, with the centroid rows of the next batch already in flight.  Epilogue = MODE 0 (aligned).
 static constexpr int kFusedDecWarps = 16;
 static constexpr int kFusedThreads = (6 + kFusedDecWarps) * 32;   // warps 0-3 epilogue, 4 Q TMA, 5 MMA, 6.. decompress
 
@@ -469,9 +479,9 @@ maxsim_fused_kernel(const __grid_constant__ CUtensorMap map_q, const MsParams p)
     const int b_bytes = p.NT * kDim * 2;
     uint8_t* sA = smem;
     uint8_t* sB = smem + a_bytes;                   // [NS][2 k-halves][NT rows][128 B]
-    MsShared* sh = reinterpret_cast<MsShared*>(sB + p.NS * b_bytes);
-    float* sW = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(sh) + ((sizeof(MsShared) + 15) & ~size_t(15)));
-    uint8_t* s_stage = reinterpret_cast<uint8_t*>(sW + 256 * (8 / NBITS));   // [kFusedDecWarps][32 tokens * PB]
+    uint8_t* sLUT = sB + p.NS * b_bytes;            // fp16 weight table, 256 entries x 128 B (1024-aligned)
+    uint8_t* s_stage = sLUT + kLutBytes;            // [kFusedDecWarps][32 tokens * PB]
+    MsShared* sh = reinterpret_cast<MsShared*>(s_stage + kFusedDecWarps * 32 * PB);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int item_begin = blockIdx.x * p.items_per_cta;
@@ -489,7 +499,7 @@ maxsim_fused_kernel(const __grid_constant__ CUtensorMap map_q, const MsParams p)
         tmem_alloc(&sh->tmem_base, 512);
         tmem_relinquish();
     }
-    for (int i = threadIdx.x; i < 256 * (8 / NBITS); i += blockDim.x) sW[i] = p.wtable[i];
+    lut_fill_f16<NBITS>(p.wtable, sLUT);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -523,8 +533,7 @@ maxsim_fused_kernel(const __grid_constant__ CUtensorMap map_q, const MsParams p)
         if (group >= p.NS) goto done;                          // more warps than stages fit in shared memory: idle
         const int h = lane & 15, half = lane >> 4;
         const uint32_t stage_sa = smem_u32(s_stage + dw * (32 * PB));   // this warp's residual staging area
-        const uint32_t sW_sa = smem_u32(sW);
-        // byte offset of this lane's 16-byte chunk inside a tile row pair: k-half (h>>3), chunk (h&7) xor (row&7)
+        const uint32_t lut_sa = lut_lane_base<NBITS>(smem_u32(sLUT), lane);
         int it_tile = 0;
         bool ok = true;
         for (int w = item_begin; ok && w < item_end; w++) {
@@ -591,45 +600,56 @@ maxsim_fused_kernel(const __grid_constant__ CUtensorMap map_q, const MsParams p)
                     for (int v = 0; v < NBITS; v++)
                         sts_v4u32(stage_sa + v * 512 + lane * 16, res[v].x, res[v].y, res[v].z, res[v].w);
                     __syncwarp();
-                    const uint32_t tile_sa = smem_u32(sB + group * b_bytes + (h >> 3) * (p.NT * 128));
+                    // this lane's 16-byte slot in a tile row: k-half (h >> 3), chunk (h & 7) xor (row & 7); rows of the
+                    // chunk start at a multiple of 32, so row & 7 == j & 7 == (2u & 6) | half for token pair u
+                    const uint32_t tile_sa = smem_u32(sB + group * b_bytes + (h >> 3) * (p.NT * 128)) + cit * 32 * 128;
+                    const char* cent_h = reinterpret_cast<const char*>(p.centroids) + h * 16;
+                    const uint32_t xh = (uint32_t)((h & 7) ^ half);
+                    constexpr int CB = MS_FUSED_CB;               // token pairs per centroid batch (rows in flight: 2 * CB)
+                    constexpr int U = MS_FUSED_U;                 // token pairs decoded together (interleaved in program order)
+                    // Rows past `valid` need no clamping: their staged bytes and codes are zero, so they decode to
+                    // finite values that the scale step replaces by zeros.
+                    auto load_cents = [&](int jb, uint4 (&c4)[CB]) {
+#pragma unroll
+                        for (int u = 0; u < CB; u++) {
+                            const unsigned c = (unsigned)__shfl_sync(0xffffffffu, code, jb + 2 * u + half);
+                            c4[u] = __ldg(reinterpret_cast<const uint4*>(cent_h + (size_t)c * (kDim * 2)));
+                        }
+                    };
+                    auto process = [&](int jb, const uint4 (&c4)[CB]) {
+#pragma unroll
+                        for (int u0 = 0; u0 < CB; u0 += U) {
+                            uint32_t wt[U][4];
+                            __half2 v[U][4];
+                            float ss[U];
+#pragma unroll
+                            for (int u = 0; u < U; u++)
+                                token_weights_h8<NBITS>(stage_sa + (jb + 2 * (u0 + u) + half) * PB, lut_sa, h, wt[u]);
+#pragma unroll
+                            for (int u = 0; u < U; u++) ss[u] = token_sum_h8(c4[u0 + u], wt[u], v[u]);
+#pragma unroll
+                            for (int o = 8; o > 0; o >>= 1) {
+#pragma unroll
+                                for (int u = 0; u < U; u++) ss[u] += __shfl_xor_sync(0xffffffffu, ss[u], o);
+                            }
+#pragma unroll
+                            for (int u = 0; u < U; u++) {
+                                const int j = jb + 2 * (u0 + u) + half;
+                                uint32_t pk[4];
+                                token_scale_h8(v[u], ss[u], j < valid, pk);
+                                sts_v4u32_relaxed(tile_sa + j * 128 + ((xh ^ (uint32_t)((2 * (u0 + u)) & 6)) << 4), pk[0], pk[1], pk[2],
+                                                  pk[3]);
+                            }
+                        }
+                    };
+                    uint4 centA[CB], centB[CB];
+                    load_cents(0, centA);
 #pragma unroll 1
-                    for (int jb = 0; jb < 32; jb += 16) {       // 8 token pairs per batch: 8 centroid rows in flight
-                        uint4 cent[8];
-#pragma unroll
-                        for (int u = 0; u < 8; u++) {
-                            const int jc = min(jb + 2 * u + half, valid - 1);
-                            int c = __shfl_sync(0xffffffffu, code, jc);
-                            c = min(max(c, 0), p.C - 1);
-                            cent[u] = __ldg(reinterpret_cast<const uint4*>(p.centroids + (size_t)c * kDim) + h);
-                        }
-#pragma unroll
-                        for (int u = 0; u < 8; u++) {
-                            const int j = jb + 2 * u + half;
-                            const int jc = min(j, valid - 1);
-                            float wv[8], v[8];
-                            token_weights8<NBITS>(stage_sa + jc * PB, sW_sa, h, wv);
-                            const uint32_t cu[4] = {cent[u].x, cent[u].y, cent[u].z, cent[u].w};
-                            float ss = 0.f;
-#pragma unroll
-                            for (int i = 0; i < 4; i++) {
-                                const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&cu[i]));
-                                v[2 * i] = wv[2 * i] + f.x;
-                                v[2 * i + 1] = wv[2 * i + 1] + f.y;
-                            }
-#pragma unroll
-                            for (int i = 0; i < 8; i++) ss = fmaf(v[i], v[i], ss);
-#pragma unroll
-                            for (int o = 8; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-                            const float inv = (j < valid) ? rsqrtf(fmaxf(ss, 1e-24f)) : 0.0f;   // pad rows are zero
-                            uint32_t pk[4];
-#pragma unroll
-                            for (int i = 0; i < 4; i++) {
-                                __nv_bfloat162 t2 = __floats2bfloat162_rn(v[2 * i] * inv, v[2 * i + 1] * inv);
-                                pk[i] = *reinterpret_cast<uint32_t*>(&t2);
-                            }
-                            const int row = cit * 32 + j;
-                            sts_v4u32(tile_sa + row * 128 + (((h & 7) ^ (row & 7)) << 4), pk[0], pk[1], pk[2], pk[3]);
-                        }
+                    for (int jb = 0; jb < 32; jb += 4 * CB) {     // two batches per trip: A at jb, B at jb + 2 CB
+                        load_cents(jb + 2 * CB, centB);
+                        process(jb, centA);
+                        if (jb + 4 * CB < 32) load_cents(jb + 4 * CB, centA);
+                        process(jb + 2 * CB, centB);
                     }
                 }
                 fence_proxy_async_smem();      // generic-proxy writes -> visible to the tensor core's async proxy
@@ -687,9 +707,9 @@ static int ms_launch_fused(const void* Qb, int q_rows, int nbits, MsParams& p, c
     int rc;
     if ((rc = make_bf16_2d_map(&map_q, Qb, (uint64_t)q_rows, kDim, 128)) != PLAID_OK) return rc;
     // one stage per group of NT/32 decompressor warps; as many groups as shared memory allows (spare warps idle)
-    const int keys = 8 / nbits, wpt = p.NT >> 5;
-    const int fixed = 1024 + p.MT * 128 * kDim * 2 + (int)sizeof(MsShared) + 16 + 256 * keys * 4 + 64;
-    const int per_stage = p.NT * kDim * 2 + wpt * 32 * 16 * nbits;
+    const int wpt = p.NT >> 5;
+    const int fixed = 1024 + p.MT * 128 * kDim * 2 + kLutBytes + kFusedDecWarps * 32 * 16 * nbits + (int)sizeof(MsShared) + 64;
+    const int per_stage = p.NT * kDim * 2;
     p.NS = (227 * 1024 - fixed) / per_stage;
     if (p.NS > kFusedDecWarps / wpt) p.NS = kFusedDecWarps / wpt;
     if (p.NS > kMsMaxStages) p.NS = kMsMaxStages;
@@ -718,12 +738,12 @@ static int ms_launch_fused(const void* Qb, int q_rows, int nbits, MsParams& p, c
 
 }  // namespace plaid
 
-extern "C" int plaid_maxsim_fused(const void* Qb_bf16, const int32_t* qlens, int B, int B_pad, int Lq_pad,
+extern "C" int plaid_maxsim_fused(const void* Qh_f16, const int32_t* qlens, int B, int B_pad, int Lq_pad,
                                   const int32_t* pids, const int32_t* counts, int pid_stride, const int32_t* tok_offsets,
                                   const int64_t* offsets, const float* W, const uint8_t* residuals, const int32_t* codes,
                                   const void* centroids_f16, int C, int nbits, float* scores, int* watchdog, void* stream) {
     using namespace plaid;
-    PLAID_CHECK_ARG(Qb_bf16 && qlens && pids && counts && tok_offsets && offsets && W && residuals && codes && centroids_f16 &&
+    PLAID_CHECK_ARG(Qh_f16 && qlens && pids && counts && tok_offsets && offsets && W && residuals && codes && centroids_f16 &&
                         scores,
                     PLAID_ERR_ARG, "plaid_maxsim_fused: null pointer");
     PLAID_CHECK_ARG(B >= 0 && B_pad >= B && pid_stride >= 1 && C > 0 && Lq_pad >= 32 && (Lq_pad % 32) == 0, PLAID_ERR_ARG,
@@ -753,15 +773,16 @@ extern "C" int plaid_maxsim_fused(const void* Qb_bf16, const int32_t* qlens, int
     p.centroids = reinterpret_cast<const __half*>(centroids_f16);
     p.wtable = W;
     p.C = C;
+    p.ab_f16 = 1;
     p.groups_per_query = (pid_stride + kMsGD - 1) / kMsGD;
     p.num_items = B * p.groups_per_query;
-    return ms_launch_fused(Qb_bf16, B_pad * Lq_pad, nbits, p, (cudaStream_t)stream);
+    return ms_launch_fused(Qh_f16, B_pad * Lq_pad, nbits, p, (cudaStream_t)stream);
 }
 
 extern "C" int plaid_maxsim_packed(const void* Qb_bf16, const int32_t* qlens, int B, int B_pad, int Lq_pad,
                                    const void* D_bf16, const int32_t* tok_offsets, const int32_t* counts, int pid_stride,
-                                   int tok_stride, int clamp_zero, int aligned32, float* scores, int* watchdog,
-                                   void* stream) {
+                                   int tok_stride, int clamp_zero, int aligned32, int operands_f16, float* scores,
+                                   int* watchdog, void* stream) {
     using namespace plaid;
     PLAID_CHECK_ARG(Qb_bf16 && qlens && D_bf16 && tok_offsets && counts && scores, PLAID_ERR_ARG,
                     "plaid_maxsim_packed: null pointer");
@@ -784,6 +805,7 @@ extern "C" int plaid_maxsim_packed(const void* Qb_bf16, const int32_t* qlens, in
     PLAID_CHECK_ARG(!aligned32 || clamp_zero, PLAID_ERR_ARG,
                     "plaid_maxsim_packed: the aligned layout relies on the clamp at 0 to ignore its zero pad rows");
     p.aligned = aligned32 ? 1 : 0;
+    p.ab_f16 = operands_f16 ? 1 : 0;
     p.watchdog = watchdog;
     p.groups_per_query = (pid_stride + kMsGD - 1) / kMsGD;
     p.num_items = B * p.groups_per_query;

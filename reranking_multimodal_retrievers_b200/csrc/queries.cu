@@ -1,6 +1,7 @@
 // queries.cu -- query preparation: zero-row removal (CB/searcher.py:124-130), bf16 conversion,
 // padding to the tile shapes of the tensor-core kernels.
 #include "common.cuh"
+#include <cuda_fp16.h>
 
 namespace plaid {
 
@@ -10,14 +11,17 @@ namespace plaid {
 __global__ void __launch_bounds__(256) prepare_queries_kernel(const float* __restrict__ Q, int B, int Lq,
                                                               int remove_zero, int Lq_pad,
                                                               __nv_bfloat16* __restrict__ Qb,
-                                                              int32_t* __restrict__ qlens) {
+                                                              __half* __restrict__ Qh, int32_t* __restrict__ qlens) {
     extern __shared__ int s_flag[];  // [Lq] keep flags, then [Lq] destination rows
     int* s_dst = s_flag + Lq;
     const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
     __nv_bfloat16* out = Qb + (size_t)b * Lq_pad * kDim;
+    __half* outh = Qh ? Qh + (size_t)b * Lq_pad * kDim : nullptr;      // optional fp16 twin (MaxSim operand)
     if (b >= B) {
-        for (int i = threadIdx.x; i < Lq_pad * kDim / 8; i += blockDim.x)
+        for (int i = threadIdx.x; i < Lq_pad * kDim / 8; i += blockDim.x) {
             reinterpret_cast<int4*>(out)[i] = make_int4(0, 0, 0, 0);
+            if (outh) reinterpret_cast<int4*>(outh)[i] = make_int4(0, 0, 0, 0);
+        }
         if (threadIdx.x == 0) qlens[b] = 0;
         return;
     }
@@ -53,9 +57,16 @@ __global__ void __launch_bounds__(256) prepare_queries_kernel(const float* __res
         __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
         uint2 pk = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
         reinterpret_cast<uint2*>(out + (size_t)d * kDim)[lane] = pk;
+        if (outh) {
+            __half2 hl = __floats2half2_rn(v.x, v.y), hh = __floats2half2_rn(v.z, v.w);
+            reinterpret_cast<uint2*>(outh + (size_t)d * kDim)[lane] =
+                make_uint2(*reinterpret_cast<uint32_t*>(&hl), *reinterpret_cast<uint32_t*>(&hh));
+        }
     }
-    for (int r = kept + warp; r < Lq_pad; r += nw)
+    for (int r = kept + warp; r < Lq_pad; r += nw) {
         reinterpret_cast<uint2*>(out + (size_t)r * kDim)[lane] = make_uint2(0, 0);
+        if (outh) reinterpret_cast<uint2*>(outh + (size_t)r * kDim)[lane] = make_uint2(0, 0);
+    }
 }
 
 __global__ void f32_to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int64_t n) {
@@ -75,7 +86,7 @@ __global__ void f32_to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16*
 }  // namespace plaid
 
 extern "C" int plaid_prepare_queries(const float* Q, int B, int Lq, int remove_zero_rows, int B_pad, int Lq_pad,
-                                     void* Qb_bf16, int32_t* qlens, void* stream) {
+                                     void* Qb_bf16, void* Qh_f16, int32_t* qlens, void* stream) {
     using namespace plaid;
     PLAID_CHECK_ARG(Q && Qb_bf16 && qlens, PLAID_ERR_ARG, "plaid_prepare_queries: null pointer");
     PLAID_CHECK_ARG(B >= 0 && B_pad >= B && (B_pad % 4) == 0, PLAID_ERR_ARG,
@@ -84,7 +95,7 @@ extern "C" int plaid_prepare_queries(const float* Q, int B, int Lq, int remove_z
                     "plaid_prepare_queries: Lq_pad=%d must be a multiple of 32 and >= Lq=%d (<= 4096)", Lq_pad, Lq);
     if (B_pad == 0) return PLAID_OK;
     prepare_queries_kernel<<<B_pad, 256, 2 * Lq * sizeof(int), (cudaStream_t)stream>>>(
-        Q, B, Lq, remove_zero_rows, Lq_pad, reinterpret_cast<__nv_bfloat16*>(Qb_bf16), qlens);
+        Q, B, Lq, remove_zero_rows, Lq_pad, reinterpret_cast<__nv_bfloat16*>(Qb_bf16), reinterpret_cast<__half*>(Qh_f16), qlens);
     PLAID_LAUNCH_OK("prepare_queries_kernel");
     return PLAID_OK;
 }

@@ -108,7 +108,8 @@ class SearchEngine:
         e = lambda *shape, dtype: torch.empty(*shape, device=dev, dtype=dtype)
         ws = dict(
             csplit=csplit, nlists=nlists, cand_stride=cand_stride, fstride=fstride, tok_stride=tok_stride, nd4=nd4,
-            Qb=e(Bc, Lq_pad, 128, dtype=torch.bfloat16), qlens=e(Bc, dtype=torch.int32),
+            Qb=e(Bc, Lq_pad, 128, dtype=torch.bfloat16), Qh=e(Bc, Lq_pad, 128, dtype=torch.float16),
+            qlens=e(Bc, dtype=torch.int32),
             S=e(Bc, C, NQ_MAX, dtype=self.s_dtype), idx_bits=e(Bc, C // 32, dtype=torch.int32),
             cell_val=e(Bc, NQ_MAX, nlists, ncells, dtype=torch.float32),
             cell_idx=e(Bc, NQ_MAX, nlists, ncells, dtype=torch.int32),
@@ -124,7 +125,7 @@ class SearchEngine:
             s2_pids=e(Bc, nd4, dtype=torch.int32), s2_scores=e(Bc, nd4, dtype=torch.float32),
             s2_counts=e(Bc, dtype=torch.int32),
             tok_offsets=e(Bc, nd4 + 1, dtype=torch.int32),
-            D=None,   # bf16 [Bc * tok_stride, 128], allocated on first use by the unfused path
+            D=None,   # fp16 [Bc * tok_stride, 128], allocated on first use by the unfused path
             scores=e(Bc, nd4, dtype=torch.float32),
             out_pids=e(Bc, k, dtype=torch.int32), out_scores=e(Bc, k, dtype=torch.float32),
             out_counts=e(Bc, dtype=torch.int32),
@@ -134,7 +135,7 @@ class SearchEngine:
 
     def _dense_buffer(self, ws, Bc):
         if ws["D"] is None:
-            ws["D"] = torch.empty(Bc * ws["tok_stride"], 128, device=self.index.device, dtype=torch.bfloat16)
+            ws["D"] = torch.empty(Bc * ws["tok_stride"], 128, device=self.index.device, dtype=torch.float16)
         return ws["D"]
 
     # ----------------------------------------------------------------------------------- one chunk
@@ -143,7 +144,7 @@ class SearchEngine:
 
     # kernels launched by each C-ABI entry point (memsets are not kernels)
     _LAUNCHES = {"plaid_prepare_queries": 1, "plaid_centroid_scores": 1, "plaid_candidates": 3, "plaid_approx_scores": 1, "plaid_filter_stage1_ivf": 4,
-                 "plaid_doc_token_offsets": 1, "plaid_decompress_normalize_bf16": 1, "plaid_maxsim_packed": 1,
+                 "plaid_doc_token_offsets": 1, "plaid_decompress_normalize_f16": 1, "plaid_maxsim_packed": 1,
                  "plaid_maxsim_fused": 1,
                  "plaid_select_top": 1}
 
@@ -168,7 +169,8 @@ class SearchEngine:
         C, N = ix.num_centroids, ix.num_passages
         wd, ovf = self._flag_ptrs()
         call = self._call
-        call("prepare", "plaid_prepare_queries", _p(Qc), b, Lq, int(remove_zero_rows), Bc, Lq_pad, _p(ws["Qb"]), _p(ws["qlens"]), st)
+        call("prepare", "plaid_prepare_queries", _p(Qc), b, Lq, int(remove_zero_rows), Bc, Lq_pad, _p(ws["Qb"]), _p(ws["Qh"]),
+             _p(ws["qlens"]), st)
         call("centroid_scores", "plaid_centroid_scores", _p(ix.centroids_bf16), C, _p(ws["Qb"]), _p(ws["qlens"]), Bc, Lq_pad, float(thr),
              ncells, ws["csplit"], _p(ws["S"]), int(self.s_dtype == torch.float16), _p(ws["idx_bits"]), _p(ws["cell_val"]), _p(ws["cell_idx"]), wd, st)
         call("candidates", "plaid_candidates", _p(ws["cell_val"]), _p(ws["cell_idx"]), _p(ws["qlens"]), b, ncells, ws["nlists"],
@@ -204,16 +206,16 @@ class SearchEngine:
         call("doc_offsets", "plaid_doc_token_offsets", _p(ws["s2_pids"]), _p(ws["s2_counts"]), b, nd4, _p(ix.offsets),
              32, _p(ws["tok_offsets"]), st)
         if self.fused and Lq_pad <= 384:
-            call("maxsim_fused", "plaid_maxsim_fused", _p(ws["Qb"]), _p(ws["qlens"]), b, Bc, Lq_pad, _p(ws["s2_pids"]),
+            call("maxsim_fused", "plaid_maxsim_fused", _p(ws["Qh"]), _p(ws["qlens"]), b, Bc, Lq_pad, _p(ws["s2_pids"]),
                  _p(ws["s2_counts"]), nd4, _p(ws["tok_offsets"]), _p(ix.offsets), _p(ix.weight_table), _p(ix.residuals),
                  _p(ix.codes), _p(ix.centroids_f16), C, ix.nbits, _p(ws["scores"]), wd, st)
         else:
             D = self._dense_buffer(ws, Bc)
-            call("decompress", "plaid_decompress_normalize_bf16", _p(ws["s2_pids"]), _p(ws["s2_counts"]), b, nd4,
+            call("decompress", "plaid_decompress_normalize_f16", _p(ws["s2_pids"]), _p(ws["s2_counts"]), b, nd4,
                  _p(ws["tok_offsets"]), ws["tok_stride"], _p(ix.offsets), _p(ix.weight_table), _p(ix.residuals),
-                 _p(ix.codes), _p(ix.centroids_f16), 1, C, ix.nbits, _p(D), st)
-            call("maxsim", "plaid_maxsim_packed", _p(ws["Qb"]), _p(ws["qlens"]), b, Bc, Lq_pad, _p(D), _p(ws["tok_offsets"]),
-                 _p(ws["s2_counts"]), nd4, ws["tok_stride"], 1, 1, _p(ws["scores"]), wd, st)
+                 _p(ix.codes), _p(ix.centroids_f16), C, ix.nbits, _p(D), st)
+            call("maxsim", "plaid_maxsim_packed", _p(ws["Qh"]), _p(ws["qlens"]), b, Bc, Lq_pad, _p(D), _p(ws["tok_offsets"]),
+                 _p(ws["s2_counts"]), nd4, ws["tok_stride"], 1, 1, 1, _p(ws["scores"]), wd, st)
         call("topk", "plaid_select_top", _p(ws["s2_pids"]), _p(ws["scores"]), _p(ws["s2_counts"]), b, nd4, k, _p(ws["out_pids"]),
              _p(ws["out_scores"]), _p(ws["out_counts"]), k, _p(ws["ws_keys"]), st)
 

@@ -108,7 +108,7 @@ def colbert_score_packed(Q, D_packed, D_lengths, config=None):
         return scores[:nd]
     wd = _watchdog(dev)
     _lib.call("plaid_maxsim_packed", _p(Qb), _p(qlens), 1, Qb.shape[0], Qb.shape[1], _p(Db), _p(tok_offsets), _p(counts),
-              max(nd, 1), max(T, 1), 1, 0, _p(scores), _p(wd), _stream())
+              max(nd, 1), max(T, 1), 1, 0, 0, _p(scores), _p(wd), _stream())
     return scores[:nd]
 
 

@@ -237,8 +237,10 @@ def segmented_lookup(input, pids, lengths, offsets):
 
 
 # --------------------------------------------------------------------------------------------- query prep
-def prepare_queries(Q: torch.Tensor, remove_zero_rows: bool, Lq_pad: int | None = None, B_pad: int | None = None):
-    """Q f32 [B, Lq, 128] -> (Qb bf16 [B_pad, Lq_pad, 128], qlens i32 [B_pad])."""
+def prepare_queries(Q: torch.Tensor, remove_zero_rows: bool, Lq_pad: int | None = None, B_pad: int | None = None,
+                    with_f16: bool = False):
+    """Q f32 [B, Lq, 128] -> (Qb bf16 [B_pad, Lq_pad, 128], qlens i32 [B_pad]); with_f16 adds the fp16 twin
+    (Qb, qlens, Qh)."""
     Q = _cu(Q, torch.float32)
     B, Lq, dim = Q.shape
     if dim != DIM:
@@ -247,9 +249,10 @@ def prepare_queries(Q: torch.Tensor, remove_zero_rows: bool, Lq_pad: int | None 
     B_pad = B_pad or ((B + 3) // 4) * 4
     Qb = torch.empty(B_pad, Lq_pad, DIM, device=Q.device, dtype=torch.bfloat16)
     qlens = torch.empty(B_pad, device=Q.device, dtype=torch.int32)
-    _lib.call("plaid_prepare_queries", _p(Q), B, Lq, int(bool(remove_zero_rows)), B_pad, Lq_pad, _p(Qb), _p(qlens),
-              _stream())
-    return Qb, qlens
+    Qh = torch.empty(B_pad, Lq_pad, DIM, device=Q.device, dtype=torch.float16) if with_f16 else None
+    _lib.call("plaid_prepare_queries", _p(Q), B, Lq, int(bool(remove_zero_rows)), B_pad, Lq_pad, _p(Qb),
+              _p(Qh) if with_f16 else None, _p(qlens), _stream())
+    return (Qb, qlens, Qh) if with_f16 else (Qb, qlens)
 
 
 def to_bf16(x: torch.Tensor) -> torch.Tensor:

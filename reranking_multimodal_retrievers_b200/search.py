@@ -73,8 +73,9 @@ class IndexScorer:
         nq = centroid_scores.shape[1]
         if centroid_scores.data_ptr() != S_ws.data_ptr():
             # foreign table: install it and rebuild the pruning mask (index_storage.py:115)
-            Qb, qlens = ops.prepare_queries(ops._cu(Q, torch.float32), False, Lq_pad, 4)
+            Qb, qlens, Qh = ops.prepare_queries(ops._cu(Q, torch.float32), False, Lq_pad, 4, with_f16=True)
             ws["Qb"].copy_(Qb)
+            ws["Qh"].copy_(Qh)
             ws["qlens"].copy_(qlens)
             S_ws.zero_()
             S_ws[:, :nq] = ops._cu(centroid_scores, torch.float32)

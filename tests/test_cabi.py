@@ -43,7 +43,7 @@ def test_errors_are_reported_not_fatal():
     """A bad argument returns PLAID_ERR_ARG and sets plaid_last_error (no abort / exit like
     filter_pids.cpp:47,98-101); argument validation happens before any CUDA call."""
     handle = _lib.lib()
-    rc = handle.plaid_prepare_queries(None, 1, 32, 0, 4, 32, None, None, None)
+    rc = handle.plaid_prepare_queries(None, 1, 32, 0, 4, 32, None, None, None, None)
     assert rc == -1
     assert b"null pointer" in handle.plaid_last_error()
     try:

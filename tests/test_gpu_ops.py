@@ -34,9 +34,11 @@ def test_prepare_queries_zero_rows_and_bf16(P):
         assert torch.equal(Qb[b, :kept.shape[0]].cpu(), kept.bfloat16())       # RNE rounding, order preserved
         assert torch.count_nonzero(Qb[b, kept.shape[0]:]) == 0
     assert qlens[5:].tolist() == [0, 0, 0] and torch.count_nonzero(Qb[5:]) == 0
-    Qb2, qlens2 = ops.prepare_queries(Q, remove_zero_rows=False)
+    Qb2, qlens2, Qh2 = ops.prepare_queries(Q, remove_zero_rows=False, with_f16=True)
     assert qlens2[:5].tolist() == [40] * 5
     assert torch.equal(Qb2[:5, :40].cpu(), Q.bfloat16())
+    assert torch.equal(Qh2[:5, :40].cpu(), Q.half()) and torch.count_nonzero(Qh2[5:]) == 0      # fp16 twin, same rows
+    assert torch.count_nonzero(Qh2[:5, 40:]) == 0
 
 
 def test_decompress_residuals_bit_exact_vs_golden(P, golden):

@@ -89,7 +89,7 @@ def test_pipeline_stagewise_bit_exact_with_injected_table(pkg, golden, s_dtype):
     eng.check_flags()
     t = eng.last_taps
     # the fused kernel (decompression feeding the tensor cores through shared memory) builds the very same
-    # bf16 operand tiles, so its scores and ranking are bit-identical to the unfused pair's
+    # fp16 operand tiles, so its scores and ranking are bit-identical to the unfused pair's
     engf = _engine(g, fused=True, s_dtype=s_dtype)
     pf, sf, cf = engf.search_batch(Q, k=k, ncells=ncells, centroid_score_threshold=thr, ndocs=ndocs,
                                    remove_zero_rows=True, keep_taps=True)
@@ -110,7 +110,8 @@ def test_pipeline_stagewise_bit_exact_with_injected_table(pkg, golden, s_dtype):
         assert torch.equal(t.stage1_scores[b, :n1].cpu(), r["stage1_scores"])
         assert torch.equal(t.stage2_pids[b, :n2].cpu(), r["stage2_pids"])
         assert torch.equal(t.stage2_scores[b, :n2].cpu(), r["stage2_scores"])
-        # decompressed + normalised passages (bf16): within one bf16 ulp of the oracle's fp32 rows.
+        # decompressed + normalised passages (fp16 arithmetic, as the reference's GPU branch): a few fp16 ulps
+        # from the oracle's fp32 rows.
         # In D every passage starts on a 32-token boundary; the rows in between are zero.
         lens = ix.doclens[r["stage2_pids"].long()]
         to = t.tok_offsets[b, :n2 + 1].cpu().long()
@@ -121,11 +122,12 @@ def test_pipeline_stagewise_bit_exact_with_injected_table(pkg, golden, s_dtype):
         pad[rows] = False
         assert torch.count_nonzero(Dq[pad]) == 0
         D = Dq[rows]
-        assert (D - r["D"]).abs().max() <= 2 ** -8
-        assert (D != r["D"].bfloat16().float()).float().mean() < 2e-3
-        # exact MaxSim: (a) same bf16 operands -> only summation order differs; (b) fp32 oracle within 1e-3
+        assert (D - r["D"]).abs().max() <= 2 ** -10
+        assert (D - r["D"]).abs().mean() <= 1e-4
+        assert ((D.norm(dim=-1) - 1).abs() <= 1e-3).all()
+        # exact MaxSim: (a) same fp16 operands -> only summation order differs; (b) fp32 oracle within 1e-3
         sc = t.scores[b, :n2].cpu()
-        ref_same = po.colbert_score_packed(q.bfloat16().float(), D, lens)
+        ref_same = po.colbert_score_packed(q.half().float(), D, lens)
         torch.testing.assert_close(sc, ref_same, rtol=2e-5, atol=2e-5)
         assert ((sc - r["scores_unsorted"]).abs() <= SCORE_REL_TOL * r["scores_unsorted"].abs() + 1e-6).all()
         # final order: (score desc, pid desc) of our own scores, exactly
