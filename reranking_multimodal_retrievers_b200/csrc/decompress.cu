@@ -167,9 +167,10 @@ decompress_normalize_f16_kernel(const int32_t* __restrict__ pids, const int32_t*
     lut_fill_f16<NBITS>(W, sLUT);
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    const int h = lane & 15, half = lane >> 4;
+    const int q = lane & 7, tsub = lane >> 3;            // quarter warp per token, lane q <- chunk q of both k-halves
     const uint32_t lut_sa = lut_lane_base<NBITS>(smem_u32(sLUT), lane);
     const uint32_t stage_sa = smem_u32(s_stage + warp * 512);
+    const char* cent_q = reinterpret_cast<const char*>(centroids) + q * 16;
     for (int i = blockIdx.x; i < n; i += gridDim.x) {
         const int pid = pids[(size_t)b * pid_stride + i];
         const int64_t tok0 = offsets[pid];
@@ -182,18 +183,23 @@ decompress_normalize_f16_kernel(const int32_t* __restrict__ pids, const int32_t*
             sts_v4u32(stage_sa + lane * 16, r.x, r.y, r.z, r.w);
             const int code = (lane < nt) ? ld_stream_s32(codes + tok0 + t0 + lane) : 0;
             __syncwarp();
-            for (int j0 = 0; j0 < nt; j0 += 2) {
-                const int j = j0 + half;
+            for (int j0 = 0; j0 < nt; j0 += 4) {
+                const int j = j0 + tsub;
                 const unsigned c = (unsigned)__shfl_sync(0xffffffffu, code, j);
-                const uint4 cent = __ldg(reinterpret_cast<const uint4*>(centroids + (size_t)c * kDim) + h);
-                uint32_t w[4], pk[4];
-                __half2 v[4];
-                token_weights_h8<NBITS>(stage_sa + j * PB, lut_sa, h, w);
-                float ss = token_sum_h8(cent, w, v);
-#pragma unroll
-                for (int o = 8; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-                token_scale_h8(v, ss, true, pk);
-                if (j < nt) reinterpret_cast<uint4*>(dst + (size_t)(t0 + j) * kDim)[h] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                const uint4* crow = centroid_row(cent_q, c);
+                const uint4 clo = __ldg(crow), chi = __ldg(crow + 8);
+                uint32_t wlo[4], whi[4];
+                __half2 v[8];
+                token_weights_h8<NBITS>(stage_sa + j * PB, lut_sa, q, wlo);
+                token_weights_h8<NBITS>(stage_sa + j * PB, lut_sa, q + 8, whi);
+                const float ss = quarter_sum(token_sum_h16(clo, chi, wlo, whi, v));
+                uint4 olo, ohi;
+                token_scale_h16(v, ss, true, olo, ohi);
+                if (j < nt) {
+                    uint4* o = reinterpret_cast<uint4*>(dst + (size_t)(t0 + j) * kDim);
+                    o[q] = olo;
+                    o[q + 8] = ohi;
+                }
             }
             __syncwarp();
         }

@@ -107,27 +107,30 @@ __device__ __forceinline__ uint32_t lut_lane_base(uint32_t lut_sa, int lane) {
     return lut_sa + (uint32_t)(lane & (128 / ES - 1)) * ES;
 }
 // fp16 weights of dimensions 8h..8h+7 of the token whose packed row sits at shared address `row`, as 4 half2 words
+// (byte extraction with PRMT, entry address with one multiply-add)
 template <int NBITS>
 __device__ __forceinline__ void token_weights_h8(uint32_t row, uint32_t lut, int h, uint32_t (&w)[4]) {
     if constexpr (NBITS == 2) {
         const uint32_t x = lds_u16(row + 2 * h);
-        const uint2 a = lds_v2u32(lut + ((x & 0xffu) << 7)), b = lds_v2u32(lut + ((x >> 8) << 7));
+        const uint2 a = lds_v2u32(__byte_perm(x, 0, 0x4440) * 128u + lut), b = lds_v2u32(__byte_perm(x, 0, 0x4441) * 128u + lut);
         w[0] = a.x; w[1] = a.y; w[2] = b.x; w[3] = b.y;
     } else if constexpr (NBITS == 4) {
         const uint32_t x = lds_u32(row + 4 * h);
-#pragma unroll
-        for (int i = 0; i < 4; i++) w[i] = lds_u32(lut + (((x >> (8 * i)) & 0xffu) << 7));
+        w[0] = lds_u32(__byte_perm(x, 0, 0x4440) * 128u + lut);
+        w[1] = lds_u32(__byte_perm(x, 0, 0x4441) * 128u + lut);
+        w[2] = lds_u32(__byte_perm(x, 0, 0x4442) * 128u + lut);
+        w[3] = lds_u32(__byte_perm(x, 0, 0x4443) * 128u + lut);
     } else if constexpr (NBITS == 1) {
         const uint32_t x = lds_u8(row + h);
-        const uint4 a = lds_v4u32(lut + (x << 7));
+        const uint4 a = lds_v4u32(x * 128u + lut);
         w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w;
     } else {
         const uint2 x = lds_v2u32(row + 8 * h);
 #pragma unroll
         for (int i = 0; i < 4; i++) {
             const uint32_t xx = i < 2 ? x.x : x.y;
-            const uint32_t lo = lds_u16(lut + (((xx >> (16 * (i & 1))) & 0xffu) << 7));
-            const uint32_t hi = lds_u16(lut + (((xx >> (16 * (i & 1) + 8)) & 0xffu) << 7));
+            const uint32_t lo = lds_u16(__byte_perm(xx, 0, 0x4440 + 2 * (i & 1)) * 128u + lut);
+            const uint32_t hi = lds_u16(__byte_perm(xx, 0, 0x4441 + 2 * (i & 1)) * 128u + lut);
             w[i] = lo | (hi << 16);
         }
     }
@@ -135,26 +138,52 @@ __device__ __forceinline__ void token_weights_h8(uint32_t row, uint32_t lut, int
 
 __device__ __forceinline__ __half2 u32_as_h2(uint32_t u) { return *reinterpret_cast<__half2*>(&u); }
 __device__ __forceinline__ uint32_t h2_as_u32(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
+__device__ __forceinline__ float rsqrt_ftz(float x) { float y; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
-// v = centroid + weight (half2), partial sum of squares of the lane's 8 dims in fp32
-__device__ __forceinline__ float token_sum_h8(const uint4& cent, const uint32_t (&w)[4], __half2 (&v)[4]) {
-    v[0] = __hadd2(u32_as_h2(cent.x), u32_as_h2(w[0]));
-    v[1] = __hadd2(u32_as_h2(cent.y), u32_as_h2(w[1]));
-    v[2] = __hadd2(u32_as_h2(cent.z), u32_as_h2(w[2]));
-    v[3] = __hadd2(u32_as_h2(cent.w), u32_as_h2(w[3]));
-    __half2 s2 = __hmul2(v[0], v[0]);
-    s2 = __hfma2(v[1], v[1], s2);
-    s2 = __hfma2(v[2], v[2], s2);
-    s2 = __hfma2(v[3], v[3], s2);
-    const float2 f = __half22float2(s2);
-    return f.x + f.y;
+// A token is decoded by 8 lanes (a quarter warp); lane q of the quarter owns dimensions 8q..8q+7 (`lo`) and
+// 64+8q..64+8q+7 (`hi`), i.e. 16-byte chunk q of both 64-dim k-halves of the operand tile.
+// centroid row address: base + code * 256 bytes in one 64-bit multiply-add
+__device__ __forceinline__ const uint4* centroid_row(const void* base_q, uint32_t code) {
+    uint64_t a;
+    asm("mad.wide.u32 %0, %1, 256, %2;" : "=l"(a) : "r"(code), "l"(reinterpret_cast<uint64_t>(base_q)));
+    return reinterpret_cast<const uint4*>(a);
 }
-// ss = the token's full sum of squares (already reduced over the 16 lanes); x / max(||x||, 1e-12), 0 for pad rows
-__device__ __forceinline__ void token_scale_h8(const __half2 (&v)[4], float ss, bool real, uint32_t (&pk)[4]) {
-    const float inv = real ? rsqrtf(fmaxf(ss, 1e-24f)) : 0.0f;
-    const __half2 i2 = __float2half2_rn(inv);
+// v = centroid + weight (half2); returns the lane's partial sum of squares (two fp16 accumulators of 4 products
+// each per half2 component, combined in fp32)
+__device__ __forceinline__ float token_sum_h16(const uint4& clo, const uint4& chi, const uint32_t (&wlo)[4],
+                                               const uint32_t (&whi)[4], __half2 (&v)[8]) {
+    v[0] = __hadd2(u32_as_h2(clo.x), u32_as_h2(wlo[0]));
+    v[1] = __hadd2(u32_as_h2(clo.y), u32_as_h2(wlo[1]));
+    v[2] = __hadd2(u32_as_h2(clo.z), u32_as_h2(wlo[2]));
+    v[3] = __hadd2(u32_as_h2(clo.w), u32_as_h2(wlo[3]));
+    v[4] = __hadd2(u32_as_h2(chi.x), u32_as_h2(whi[0]));
+    v[5] = __hadd2(u32_as_h2(chi.y), u32_as_h2(whi[1]));
+    v[6] = __hadd2(u32_as_h2(chi.z), u32_as_h2(whi[2]));
+    v[7] = __hadd2(u32_as_h2(chi.w), u32_as_h2(whi[3]));
+    __half2 a = __hmul2(v[0], v[0]), b = __hmul2(v[4], v[4]);
 #pragma unroll
-    for (int i = 0; i < 4; i++) pk[i] = h2_as_u32(__hmul2(v[i], i2));
+    for (int i = 1; i < 4; i++) {
+        a = __hfma2(v[i], v[i], a);
+        b = __hfma2(v[4 + i], v[4 + i], b);
+    }
+    const float2 fa = __half22float2(a), fb = __half22float2(b);
+    return (fa.x + fa.y) + (fb.x + fb.y);
+}
+// sum over the 8 lanes of the quarter warp
+__device__ __forceinline__ float quarter_sum(float ss) {
+    ss += __shfl_xor_sync(0xffffffffu, ss, 4);
+    ss += __shfl_xor_sync(0xffffffffu, ss, 2);
+    ss += __shfl_xor_sync(0xffffffffu, ss, 1);
+    return ss;
+}
+// x / max(||x||, 1e-12) = x * rsqrt(max(||x||^2, 1e-24)) (index_storage.py:175); pad rows become zeros
+__device__ __forceinline__ void token_scale_h16(const __half2 (&v)[8], float ss, bool real, uint4& lo, uint4& hi) {
+    const float inv = real ? rsqrt_ftz(fmaxf(ss, 1e-24f)) : 0.0f;
+    const __half2 i2 = __float2half2_rn(inv);
+    lo = make_uint4(h2_as_u32(__hmul2(v[0], i2)), h2_as_u32(__hmul2(v[1], i2)), h2_as_u32(__hmul2(v[2], i2)),
+                    h2_as_u32(__hmul2(v[3], i2)));
+    hi = make_uint4(h2_as_u32(__hmul2(v[4], i2)), h2_as_u32(__hmul2(v[5], i2)), h2_as_u32(__hmul2(v[6], i2)),
+                    h2_as_u32(__hmul2(v[7], i2)));
 }
 
 }  // namespace plaid

@@ -21,10 +21,7 @@
 #include "decompress.cuh"
 
 #ifndef MS_FUSED_CB
-#define MS_FUSED_CB 2      // fused kernel: centroid rows prefetched per batch (token pairs)
-#endif
-#ifndef MS_FUSED_U
-#define MS_FUSED_U 2       // fused kernel: token pairs decoded together
+#define MS_FUSED_CB 2      // fused kernel: steps (of 4 tokens) per centroid batch; two batches are in flight
 #endif
 
 namespace plaid {
@@ -375,6 +372,106 @@ __device__ __forceinline__ void ms_epilogue(const MsParams& p, MsShared* sh, uin
     }
 }
 
+// Barrier over the first `nthreads` epilogue threads (whole warps), ORing a predicate like epi_bar_or.
+__device__ __forceinline__ bool epi_bar_or_n(bool pred, int nthreads) {
+    uint32_t r;
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t"
+        "setp.ne.u32 p, %1, 0;\n\t"
+        "bar.red.or.pred q, 1, %2, p;\n\t"
+        "selp.u32 %0, 1, 0, q;\n\t}"
+        : "=r"(r) : "r"((uint32_t)pred), "r"(nthreads) : "memory");
+    return r != 0;
+}
+
+// max(seed, 16 values) as three levels of 3-input maxima instead of one 16-deep chain
+__device__ __forceinline__ float max16(const uint32_t (&r)[16], float seed) {
+    auto f = [&](int i) { return __uint_as_float(r[i]); };
+    const float a0 = fmaxf(fmaxf(seed, f(0)), f(1)), a1 = fmaxf(fmaxf(f(2), f(3)), f(4));
+    const float a2 = fmaxf(fmaxf(f(5), f(6)), f(7)), a3 = fmaxf(fmaxf(f(8), f(9)), f(10));
+    const float a4 = fmaxf(fmaxf(f(11), f(12)), f(13)), a5 = fmaxf(f(14), f(15));
+    return fmaxf(fmaxf(fmaxf(a0, a1), a2), fmaxf(fmaxf(a3, a4), a5));
+}
+
+// ===================== epilogue of the search pipeline: aligned passages, one m-tile, NT = 128 =====================
+// The common case (Lq_pad <= 128, e.g. FLMR's 32 + 32 query tokens) gets its own lean loop: the only
+// epilogue warps that exist for the barriers are the ones whose TMEM lanes can hold query rows
+// (n_epi = Lq_pad / 32), the accumulator is read in 16-column pieces with the load of the next piece in flight
+// while the current one is reduced, and passage boundaries are looked at once per 32 columns.  With the clamp
+// at 0 the running maximum simply starts at 0.
+__device__ __forceinline__ void ms_epilogue_a1(const MsParams& p, MsShared* sh, uint32_t tmem_base, int item_begin,
+                                               int item_end, int warp, int lane, int n_epi) {
+    const int quad = warp;
+    const uint32_t tmem_lane = tmem_base + ((uint32_t)(quad * 32) << 16);
+    int it_tile = 0, parity = 0;
+    bool ok = true;
+    for (int w = item_begin; ok && w < item_end; w++) {
+        const MsItem it = ms_item(p, w);
+        if (it.nd == 0) continue;
+        const int lq = p.qlens[it.q];
+        const bool rowok = (quad * 32 + lane) < lq;
+        const bool live = quad * 32 < lq;               // warp-uniform: some lane holds a real query token
+        float* part = sh->part[parity][quad];
+        // passage ends of the item (relative to its first token) held one per lane: lane d+1 = end of passage d
+        int ends_reg = 0x7fffffff;
+        if (lane <= it.nd) ends_reg = it.ends[lane] - it.ends[0];
+        int doc = 0;
+        int next_end = __shfl_sync(0xffffffffu, ends_reg, 1);
+        float runmax = 0.0f;
+        auto flush = [&](int d) {
+            float v = rowok ? runmax : 0.0f;
+            runmax = 0.0f;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0) part[d] = v;
+        };
+        const int ntiles = (it.ntok + 127) >> 7;
+        for (int t = 0; t < ntiles; t++, it_tile++) {
+            const int acc = it_tile & 1;
+            if (!mbar_wait(&sh->tmem_full[acc], (it_tile >> 1) & 1, p.watchdog)) { ok = false; break; }
+            tc_fence_after();
+            if (live) {
+                const uint32_t tmem_acc = tmem_lane + acc * 128;
+                const int nch = min(4, (it.ntok - t * 128) >> 5);     // 32-column chunks of this tile that hold tokens
+                uint32_t ra[16], rb[16];
+                tmem_ld_32x16(tmem_acc, ra);
+                tc_wait_ld16(ra);
+#pragma unroll
+                for (int ch = 0; ch < 4; ch++) {
+                    if (ch < nch) {
+                        const int tk0 = t * 128 + ch * 32;
+                        while (tk0 == next_end && doc + 1 < it.nd) {   // this chunk opens the next passage
+                            flush(doc);
+                            doc++;
+                            next_end = __shfl_sync(0xffffffffu, ends_reg, doc + 1);
+                        }
+                        tmem_ld_32x16(tmem_acc + ch * 32 + 16, rb);    // second half in flight ...
+                        runmax = max16(ra, runmax);                    // ... while the first is reduced
+                        tc_wait_ld16(rb);
+                        if (ch + 1 < nch) tmem_ld_32x16(tmem_acc + ch * 32 + 32, ra);
+                        runmax = max16(rb, runmax);
+                        if (ch + 1 < nch) tc_wait_ld16(ra);
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sh->tmem_empty[acc]);
+        }
+        for (int d = doc; d < it.nd; d++) flush(d);     // the last passage, plus trailing empty ones
+        __syncwarp();
+        if (epi_bar_or_n(!ok, n_epi * 32)) ok = false;
+        const int te = threadIdx.x;
+        if (te < it.nd) {
+            float s = sh->part[parity][0][te];
+            for (int qd = 1; qd < n_epi; qd++) s += sh->part[parity][qd][te];
+            p.scores[it.out0 + te] = s;
+        }
+        parity ^= 1;
+    }
+}
+
+
 template <int MODE>
 __global__ void __launch_bounds__(kMsThreads, 1)
 maxsim_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_d, const MsParams p) {
@@ -390,6 +487,10 @@ maxsim_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
     // The two single-thread roles sit on SM sub-partitions 2/3, away from the epilogue warps of the first
     // 64 query tokens (the common Lq = 64 case leaves quadrants 2/3 without live rows).
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // the search pipeline's common shape gets the lean epilogue (ms_epilogue_a1), run by the Lq_pad/32 warps whose
+    // TMEM lanes can hold query rows
+    const bool lean = (MODE == 0) && p.MT == 1 && p.NT == 128;
+    const int n_epi = lean ? min(4, p.Lq_pad >> 5) : 4;
     const int item_begin = blockIdx.x * p.items_per_cta;
     const int item_end = min(p.num_items, item_begin + p.items_per_cta);
 
@@ -397,7 +498,7 @@ maxsim_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
         mbar_init(&sh->a_full, 1);
         mbar_init(&sh->a_empty, 1);
         for (int s = 0; s < p.NS; s++) { mbar_init(&sh->full[s], 1); mbar_init(&sh->empty[s], 1); }
-        for (int a = 0; a < 2; a++) { mbar_init(&sh->tmem_full[a], 1); mbar_init(&sh->tmem_empty[a], 4); }
+        for (int a = 0; a < 2; a++) { mbar_init(&sh->tmem_full[a], 1); mbar_init(&sh->tmem_empty[a], n_epi); }
         fence_mbar_init();
     }
     if (warp == 7) {
@@ -445,7 +546,11 @@ maxsim_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
     } else if (warp == 7) {
         ms_mma_issue(p, sh, sA, sB, b_bytes, tmem_base, item_begin, item_end, lane);
     } else if (warp < 4) {
-        ms_epilogue<MODE>(p, sh, tmem_base, item_begin, item_end, warp, lane);
+        if (lean) {
+            if (warp < n_epi) ms_epilogue_a1(p, sh, tmem_base, item_begin, item_end, warp, lane, n_epi);
+        } else {
+            ms_epilogue<MODE>(p, sh, tmem_base, item_begin, item_end, warp, lane);
+        }
     }
 
     tc_fence_before();
@@ -461,12 +566,16 @@ maxsim_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
 // K-major 128B-swizzled layout the UMMA descriptor expects (16-byte chunk c of row r lands at chunk
 // c ^ (r & 7); rows 128 B apart; the two 64-dim k-halves NT*128 B apart), fenced into the async proxy
 // and handed to the MMA thread through the stage's mbarrier.  Each group of NT/32 warps owns one stage.
-// Per token (half-warp, 8 dims per lane), in the fp16 arithmetic of the reference's GPU branch: packed
-// residual byte(s) -> fp16 weights from a bank-conflict-free table in shared memory, + fp16 centroid row (one
-// 128-bit L2 load), sum of squares over the half-warp, rsqrt, scale, one 128-bit store into the fp16 tile.
-// Tokens are handled in batches of 4 pairs whose shared loads / shuffles / stores are interleaved in program
-// order, with the centroid rows of the next batch already in flight.  Epilogue = MODE 0 (aligned).
+// Per token (quarter warp, 16 dims per lane), in the fp16 arithmetic of the reference's GPU branch: packed
+// residual bytes -> fp16 weights from a bank-conflict-free table in shared memory, + fp16 centroid row (two
+// 128-bit L2 loads per lane), sum of squares over the 8 lanes, rsqrt, scale, two 128-bit stores into the fp16
+// tile.  Centroid rows are requested one batch (8 tokens) ahead, across chunk boundaries too; the shared loads
+// of the next 4 tokens are issued before the shuffles of the current ones.  Epilogue = MODE 0 (aligned).
 static constexpr int kFusedDecWarps = 16;
+// 1- and 2-bit residuals: the packed rows of the next chunk travel global -> shared with per-lane asynchronous
+// copies into a second staging buffer (no registers held across the chunk); 4 and 8 bits keep one buffer and
+// carry the next chunk in registers, because their staging areas are 2-4x larger.
+template <int NBITS> constexpr bool kFusedAsyncStage = (NBITS <= 2);
 static constexpr int kFusedThreads = (6 + kFusedDecWarps) * 32;   // warps 0-3 epilogue, 4 Q TMA, 5 MMA, 6.. decompress
 
 template <int NBITS>
@@ -480,10 +589,12 @@ maxsim_fused_kernel(const __grid_constant__ CUtensorMap map_q, const MsParams p)
     uint8_t* sA = smem;
     uint8_t* sB = smem + a_bytes;                   // [NS][2 k-halves][NT rows][128 B]
     uint8_t* sLUT = sB + p.NS * b_bytes;            // fp16 weight table, 256 entries x 128 B (1024-aligned)
-    uint8_t* s_stage = sLUT + kLutBytes;            // [kFusedDecWarps][32 tokens * PB]
-    MsShared* sh = reinterpret_cast<MsShared*>(s_stage + kFusedDecWarps * 32 * PB);
+    uint8_t* s_stage = sLUT + kLutBytes;            // [kFusedDecWarps][1 or 2 buffers][32 tokens * PB]
+    MsShared* sh = reinterpret_cast<MsShared*>(s_stage + kFusedDecWarps * (kFusedAsyncStage<NBITS> ? 2 : 1) * 32 * PB);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool lean = p.MT == 1 && p.NT == 128;      // see maxsim_kernel
+    const int n_epi = lean ? min(4, p.Lq_pad >> 5) : 4;
     const int item_begin = blockIdx.x * p.items_per_cta;
     const int item_end = min(p.num_items, item_begin + p.items_per_cta);
     const int wpt = p.NT >> 5;                      // decompressor warps per tile
@@ -492,7 +603,7 @@ maxsim_fused_kernel(const __grid_constant__ CUtensorMap map_q, const MsParams p)
         mbar_init(&sh->a_full, 1);
         mbar_init(&sh->a_empty, 1);
         for (int s = 0; s < p.NS; s++) { mbar_init(&sh->full[s], wpt); mbar_init(&sh->empty[s], 1); }
-        for (int a = 0; a < 2; a++) { mbar_init(&sh->tmem_full[a], 1); mbar_init(&sh->tmem_empty[a], 4); }
+        for (int a = 0; a < 2; a++) { mbar_init(&sh->tmem_full[a], 1); mbar_init(&sh->tmem_empty[a], n_epi); }
         fence_mbar_init();
     }
     if (warp == 5) {
@@ -506,7 +617,11 @@ maxsim_fused_kernel(const __grid_constant__ CUtensorMap map_q, const MsParams p)
     const uint32_t tmem_base = sh->tmem_base;
 
     if (warp < 4) {
-        ms_epilogue<0>(p, sh, tmem_base, item_begin, item_end, warp, lane);
+        if (lean) {
+            if (warp < n_epi) ms_epilogue_a1(p, sh, tmem_base, item_begin, item_end, warp, lane, n_epi);
+        } else {
+            ms_epilogue<0>(p, sh, tmem_base, item_begin, item_end, warp, lane);
+        }
     } else if (warp == 4) {
         // ===================== query (A operand) TMA producer =====================
         if (lane == 0) {
@@ -531,10 +646,22 @@ maxsim_fused_kernel(const __grid_constant__ CUtensorMap map_q, const MsParams p)
         const int dw = warp - 6;
         const int group = dw / wpt, cit = dw - group * wpt;   // stage owned by this warp's group, chunk inside the tile
         if (group >= p.NS) goto done;                          // more warps than stages fit in shared memory: idle
-        const int h = lane & 15, half = lane >> 4;
-        const uint32_t stage_sa = smem_u32(s_stage + dw * (32 * PB));   // this warp's residual staging area
+        // A quarter warp decodes one token: lane q of the quarter owns 16-byte chunk q of both k-halves of the row
+        // (dims 8q..8q+7 and 64+8q..64+8q+7); one step of the warp = the 4 tokens 4*step + tsub.
+        const int q = lane & 7, tsub = lane >> 3;
+        constexpr int CB = kFusedAsyncStage<NBITS> ? MS_FUSED_CB : 1;   // steps per centroid batch (4*CB tokens, 4*CB registers)
+        constexpr int NBATCH = 8 / CB;
+        constexpr int kStageBufs = kFusedAsyncStage<NBITS> ? 2 : 1;
+        const uint32_t stage0_sa = smem_u32(s_stage + dw * (kStageBufs * 32 * PB));   // this warp's residual staging area(s)
+        int buf = 0;
         const uint32_t lut_sa = lut_lane_base<NBITS>(smem_u32(sLUT), lane);
-        int it_tile = 0;
+        const char* cent_q = reinterpret_cast<const char*>(p.centroids) + q * 16;
+        // Row j = 4*step + tsub of the chunk; chunk q of a row sits at 16-byte slot q ^ (j & 7) = (q ^ tsub) ^ 4*(step & 1).
+        const uint32_t tile_lane = smem_u32(sB + group * b_bytes) + (cit * 32 + tsub) * 128;
+        const uint32_t slot_even = tile_lane + ((uint32_t)(q ^ tsub) << 4), slot_odd = tile_lane + ((uint32_t)(q ^ tsub ^ 4) << 4);
+        const uint32_t khalf = (uint32_t)p.NT * 128;          // the second k-half of the tile
+        int base_mod = 0;     // (tiles of the earlier items) % NS: tile t of this item uses stage (base_mod + t) % NS
+        int mine = 0;         // tiles this warp's group has built so far = phase counter of its stage barriers
         bool ok = true;
         for (int w = item_begin; ok && w < item_end; w++) {
             const MsItem it = ms_item(p, w);
@@ -562,94 +689,111 @@ maxsim_fused_kernel(const __grid_constant__ CUtensorMap map_q, const MsParams p)
                     valid = max(0, min(32, __shfl_sync(0xffffffffu, my_len, d) - seg));
                 }
             };
-            // packed residuals (valid*PB bytes, 128-bit loads) and codes of a chunk, into registers
-            auto fetch = [&](int64_t tok0, int valid, int4 (&res)[NBITS], int& code) {
+            // packed residuals (valid*PB bytes, 16 per lane and pass) and codes of a chunk: rows past `valid` get zero
+            // bytes and code 0, so they decode to finite values that the scale step replaces by zeros
+            auto fetch = [&](int64_t tok0, int valid, uint32_t st_sa, int4 (&res)[NBITS], int& code) {
 #pragma unroll
                 for (int v = 0; v < NBITS; v++) {
                     const int byte = v * 512 + lane * 16;
-                    res[v] = make_int4(0, 0, 0, 0);
-                    if (byte < valid * PB) res[v] = ld_stream_v4(p.residuals + tok0 * PB + byte);
+                    const bool real = byte < valid * PB;
+                    if constexpr (kFusedAsyncStage<NBITS>) {
+                        cp_async_16(st_sa + byte, p.residuals + (real ? tok0 * PB + byte : 0), real ? 16 : 0);
+                    } else {
+                        res[v] = make_int4(0, 0, 0, 0);
+                        if (real) res[v] = ld_stream_v4(p.residuals + tok0 * PB + byte);
+                    }
                 }
+                if constexpr (kFusedAsyncStage<NBITS>) cp_async_commit();
                 code = (lane < valid) ? ld_stream_s32(p.codes + tok0 + lane) : 0;
+            };
+            // centroid rows of batch bt (steps bt*CB .. bt*CB+CB-1) of a chunk whose codes sit one per lane in `code`
+            auto load_cents = [&](int code, int bt, uint4 (&clo)[CB], uint4 (&chi)[CB]) {
+#pragma unroll
+                for (int u = 0; u < CB; u++) {
+                    const unsigned c = (unsigned)__shfl_sync(0xffffffffu, code, 4 * (bt * CB + u) + tsub);
+                    const uint4* row = centroid_row(cent_q, c);
+                    clo[u] = __ldg(row);
+                    chi[u] = __ldg(row + 8);
+                }
+            };
+            // decode batch bt into the tile: shared loads of step u+1 are issued before the shuffles of step u
+            auto process = [&](int bt, int valid, uint32_t stage_sa, const uint4 (&clo)[CB], const uint4 (&chi)[CB]) {
+                uint32_t wlo[4], whi[4];
+                token_weights_h8<NBITS>(stage_sa + (4 * bt * CB + tsub) * PB, lut_sa, q, wlo);
+                token_weights_h8<NBITS>(stage_sa + (4 * bt * CB + tsub) * PB, lut_sa, q + 8, whi);
+#pragma unroll
+                for (int u = 0; u < CB; u++) {
+                    const int step = bt * CB + u, j = 4 * step + tsub;
+                    __half2 v[8];
+                    float ss = token_sum_h16(clo[u], chi[u], wlo, whi, v);
+                    if (u + 1 < CB) {
+                        token_weights_h8<NBITS>(stage_sa + (j + 4) * PB, lut_sa, q, wlo);
+                        token_weights_h8<NBITS>(stage_sa + (j + 4) * PB, lut_sa, q + 8, whi);
+                    }
+                    ss = quarter_sum(ss);
+                    uint4 olo, ohi;
+                    token_scale_h16(v, ss, j < valid, olo, ohi);
+                    const uint32_t dst = (((CB & 1) ? (step & 1) : (u & 1)) ? slot_odd : slot_even) + step * 512;
+                    sts_v4u32_relaxed(dst, olo.x, olo.y, olo.z, olo.w);
+                    sts_v4u32_relaxed(dst + khalf, ohi.x, ohi.y, ohi.z, ohi.w);
+                }
             };
             int4 pres[NBITS];
             int pcode = 0, pvalid = 0, ptile = -1;
-            for (int t = 0; t < ntiles; t++, it_tile++) {
-                if (it_tile % p.NS != group) continue;
+            uint4 alo[CB], ahi[CB], blo[CB], bhi[CB];
+            bool a_ready = false;                               // batch 0 of the coming chunk is already in alo/ahi
+            int first = group - base_mod;                       // this group's first tile of the item
+            if (first < 0) first += p.NS;
+            base_mod = (base_mod + ntiles) % p.NS;
+            for (int t = first; t < ntiles; t += p.NS, mine++) {
+                const uint32_t stage_sa = stage0_sa + buf * (32 * PB);
                 int4 res[NBITS];
                 int code, valid;
-                if (ptile == t) {                               // prefetched while the previous tile was being built
+                if (ptile == t) {                               // requested while the previous tile was being built
+                    if constexpr (!kFusedAsyncStage<NBITS>) {
 #pragma unroll
-                    for (int v = 0; v < NBITS; v++) res[v] = pres[v];
+                        for (int v = 0; v < NBITS; v++) res[v] = pres[v];
+                    }
                     code = pcode;
                     valid = pvalid;
                 } else {
                     int64_t tok0;
                     geom(t, tok0, valid);
-                    fetch(tok0, valid, res, code);
+                    fetch(tok0, valid, stage_sa, res, code);
                 }
-                if (t + p.NS < ntiles) {                        // this warp's next chunk of the item: loads in flight now
+                if (!a_ready && valid > 0) load_cents(code, 0, alo, ahi);
+                a_ready = false;
+                const bool more = t + p.NS < ntiles;
+                if (more) {                                     // this warp's next chunk of the item: loads in flight now
                     int64_t ntok0;
                     geom(t + p.NS, ntok0, pvalid);
-                    fetch(ntok0, pvalid, pres, pcode);
+                    fetch(ntok0, pvalid, stage0_sa + (buf ^ 1) * (32 * PB), pres, pcode);
                     ptile = t + p.NS;
                 }
-                if (!mbar_wait(&sh->empty[group], ((it_tile / p.NS) & 1) ^ 1, p.watchdog)) { ok = false; break; }
-                if (valid > 0) {
-#pragma unroll
-                    for (int v = 0; v < NBITS; v++)
-                        sts_v4u32(stage_sa + v * 512 + lane * 16, res[v].x, res[v].y, res[v].z, res[v].w);
+                if (!mbar_wait(&sh->empty[group], (mine & 1) ^ 1, p.watchdog)) { ok = false; break; }
+                if constexpr (kFusedAsyncStage<NBITS>) {        // this chunk's rows have landed (the next chunk's may not)
+                    if (more) cp_async_wait<1>(); else cp_async_wait<0>();
                     __syncwarp();
-                    // this lane's 16-byte slot in a tile row: k-half (h >> 3), chunk (h & 7) xor (row & 7); rows of the
-                    // chunk start at a multiple of 32, so row & 7 == j & 7 == (2u & 6) | half for token pair u
-                    const uint32_t tile_sa = smem_u32(sB + group * b_bytes + (h >> 3) * (p.NT * 128)) + cit * 32 * 128;
-                    const char* cent_h = reinterpret_cast<const char*>(p.centroids) + h * 16;
-                    const uint32_t xh = (uint32_t)((h & 7) ^ half);
-                    constexpr int CB = MS_FUSED_CB;               // token pairs per centroid batch (rows in flight: 2 * CB)
-                    constexpr int U = MS_FUSED_U;                 // token pairs decoded together (interleaved in program order)
-                    // Rows past `valid` need no clamping: their staged bytes and codes are zero, so they decode to
-                    // finite values that the scale step replaces by zeros.
-                    auto load_cents = [&](int jb, uint4 (&c4)[CB]) {
+                    buf ^= 1;
+                }
+                if (valid > 0) {
+                    if constexpr (!kFusedAsyncStage<NBITS>) {
 #pragma unroll
-                        for (int u = 0; u < CB; u++) {
-                            const unsigned c = (unsigned)__shfl_sync(0xffffffffu, code, jb + 2 * u + half);
-                            c4[u] = __ldg(reinterpret_cast<const uint4*>(cent_h + (size_t)c * (kDim * 2)));
-                        }
-                    };
-                    auto process = [&](int jb, const uint4 (&c4)[CB]) {
-#pragma unroll
-                        for (int u0 = 0; u0 < CB; u0 += U) {
-                            uint32_t wt[U][4];
-                            __half2 v[U][4];
-                            float ss[U];
-#pragma unroll
-                            for (int u = 0; u < U; u++)
-                                token_weights_h8<NBITS>(stage_sa + (jb + 2 * (u0 + u) + half) * PB, lut_sa, h, wt[u]);
-#pragma unroll
-                            for (int u = 0; u < U; u++) ss[u] = token_sum_h8(c4[u0 + u], wt[u], v[u]);
-#pragma unroll
-                            for (int o = 8; o > 0; o >>= 1) {
-#pragma unroll
-                                for (int u = 0; u < U; u++) ss[u] += __shfl_xor_sync(0xffffffffu, ss[u], o);
-                            }
-#pragma unroll
-                            for (int u = 0; u < U; u++) {
-                                const int j = jb + 2 * (u0 + u) + half;
-                                uint32_t pk[4];
-                                token_scale_h8(v[u], ss[u], j < valid, pk);
-                                sts_v4u32_relaxed(tile_sa + j * 128 + ((xh ^ (uint32_t)((2 * (u0 + u)) & 6)) << 4), pk[0], pk[1], pk[2],
-                                                  pk[3]);
-                            }
-                        }
-                    };
-                    uint4 centA[CB], centB[CB];
-                    load_cents(0, centA);
+                        for (int v = 0; v < NBITS; v++)
+                            sts_v4u32(stage_sa + v * 512 + lane * 16, res[v].x, res[v].y, res[v].z, res[v].w);
+                        __syncwarp();
+                    }
 #pragma unroll 1
-                    for (int jb = 0; jb < 32; jb += 4 * CB) {     // two batches per trip: A at jb, B at jb + 2 CB
-                        load_cents(jb + 2 * CB, centB);
-                        process(jb, centA);
-                        if (jb + 4 * CB < 32) load_cents(jb + 4 * CB, centA);
-                        process(jb + 2 * CB, centB);
+                    for (int bt = 0; bt < NBATCH; bt += 2) {    // two batches per trip: A = bt, B = bt + 1
+                        load_cents(code, bt + 1, blo, bhi);
+                        process(bt, valid, stage_sa, alo, ahi);
+                        if (bt + 2 < NBATCH) {
+                            load_cents(code, bt + 2, alo, ahi);
+                        } else if (more && pvalid > 0) {        // batch 0 of the next chunk (its codes arrived long ago)
+                            load_cents(pcode, 0, alo, ahi);
+                            a_ready = true;
+                        }
+                        process(bt + 1, valid, stage_sa, blo, bhi);
                     }
                 }
                 fence_proxy_async_smem();      // generic-proxy writes -> visible to the tensor core's async proxy
@@ -708,7 +852,9 @@ static int ms_launch_fused(const void* Qb, int q_rows, int nbits, MsParams& p, c
     if ((rc = make_bf16_2d_map(&map_q, Qb, (uint64_t)q_rows, kDim, 128)) != PLAID_OK) return rc;
     // one stage per group of NT/32 decompressor warps; as many groups as shared memory allows (spare warps idle)
     const int wpt = p.NT >> 5;
-    const int fixed = 1024 + p.MT * 128 * kDim * 2 + kLutBytes + kFusedDecWarps * 32 * 16 * nbits + (int)sizeof(MsShared) + 64;
+    const int stage_bufs = nbits <= 2 ? 2 : 1;       // kFusedAsyncStage
+    const int fixed = 1024 + p.MT * 128 * kDim * 2 + kLutBytes + kFusedDecWarps * stage_bufs * 32 * 16 * nbits +
+                      (int)sizeof(MsShared) + 64;
     const int per_stage = p.NT * kDim * 2;
     p.NS = (227 * 1024 - fixed) / per_stage;
     if (p.NS > kFusedDecWarps / wpt) p.NS = kFusedDecWarps / wpt;
