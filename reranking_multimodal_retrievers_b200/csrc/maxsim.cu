@@ -27,13 +27,17 @@
 namespace plaid {
 
 static constexpr int kMsThreads = 256;   // warps 0-3 epilogue, 4-5 idle, 6 TMA producer, 7 TMEM alloc + MMA issue
-static constexpr int kMsGD = 16;         // passages per work item
+#ifndef MS_GD
+#define MS_GD 32
+#endif
+static constexpr int kMsGD = MS_GD;      // passages per work item (<= 32: one lane per passage)
 static constexpr int kMsMaxStages = 8;
 static constexpr int kMsMaxMT = 4;       // Lq_pad <= 512
 
 struct MsParams {
     const int32_t* qlens;        // [nQ] valid rows per query
     int Lq_pad, MT, NT, NS;
+    int na_shift;                // log2 of the accumulator buffers in TMEM (4 when 4 x MT x NT <= 512 columns, else 2)
     int ab_f16;                  // operands (Q and D) are fp16 instead of bf16
     int padded;                  // 0 = packed search form, 1 = padded colbert_score form
     int aligned;                 // packed only: passages start on 32-token boundaries of D, pad rows are zero
@@ -102,8 +106,8 @@ struct MsShared {
     uint64_t a_full, a_empty;
     uint64_t full[kMsMaxStages];
     uint64_t empty[kMsMaxStages];
-    uint64_t tmem_full[2];
-    uint64_t tmem_empty[2];
+    uint64_t tmem_full[4];
+    uint64_t tmem_empty[4];
     uint32_t tmem_base;
     float part[2][4][kMsGD];
 };
@@ -129,46 +133,62 @@ __device__ __forceinline__ float max32(const uint32_t (&r)[32], float seed) {
     return a;
 }
 
-// ===================== MMA issuer (one thread) =====================
+// ===================== MMA issuer (one warp, one issuing lane) =====================
 // Walks the CTA's work items in order; for every B tile: wait for the stage to be full and for an
 // accumulator buffer to be drained, issue MT x 8 tcgen05.mma (K = 128), commit the stage back to its
 // producer and the accumulator to the epilogue.  The A operand (query) is swapped when the query changes.
+// The whole warp runs the loop so that its state lives in uniform registers (a loop under `lane == 0` makes
+// the compiler re-broadcast every tcgen05 operand, ~300 instructions per tile on the kernel's critical path);
+// only lane 0 issues.  Stage / phase counters advance incrementally (no division), and the shared-memory
+// descriptors are the base descriptor plus a 16-byte-unit offset.
 __device__ __forceinline__ void ms_mma_issue(const MsParams& p, MsShared* sh, uint8_t* sA, uint8_t* sB, int b_bytes,
-                                             uint32_t tmem_base, int item_begin, int item_end, int lane) {
+                                             uint32_t tmem_base_in, int item_begin, int item_end, int lane) {
+    // everything the tcgen05 operands derive from is made provably warp-uniform (lane-0 broadcasts), otherwise the
+    // compiler wraps every instruction in an elect/broadcast loop
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, tmem_base_in, 0);
     const int acc_cols = p.MT * p.NT;
-    if (lane == 0) {
-        const uint32_t idesc = p.ab_f16 ? umma_idesc_f16(128, p.NT) : umma_idesc_bf16(128, p.NT);
-        int cur_q = -1, a_loads = 0, it_tile = 0;
-        bool ok = true;
-        for (int w = item_begin; ok && w < item_end; w++) {
-            const MsItem it = ms_item(p, w);
-            if (it.nd == 0) continue;
-            if (it.q != cur_q) {
-                if (a_loads > 0) umma_commit(&sh->a_empty);  // every MMA that read the old A has retired
-                if (!mbar_wait(&sh->a_full, a_loads & 1, p.watchdog)) break;
-                cur_q = it.q;
-                a_loads++;
-            }
-            const int ntiles = (it.ntok + p.NT - 1) / p.NT;
-            for (int t = 0; t < ntiles; t++, it_tile++) {
-                const int s = it_tile % p.NS, acc = it_tile & 1;
-                if (!mbar_wait(&sh->tmem_empty[acc], ((it_tile >> 1) & 1) ^ 1, p.watchdog)) { ok = false; break; }
-                if (!mbar_wait(&sh->full[s], (it_tile / p.NS) & 1, p.watchdog)) { ok = false; break; }
-                tc_fence_after();
-                const uint32_t b0 = smem_u32(sB + s * b_bytes);
+    const uint32_t idesc = p.ab_f16 ? umma_idesc_f16(128, p.NT) : umma_idesc_bf16(128, p.NT);
+    const uint64_t da_base = umma_smem_desc_sw128(smem_u32(sA)), db_base = umma_smem_desc_sw128(smem_u32(sB));
+    const uint32_t b_khalf = (uint32_t)(p.NT * 128) >> 4, b_stage = (uint32_t)b_bytes >> 4;
+    constexpr uint32_t a_khalf = (128 * 128) >> 4, a_mtile = (2 * 128 * 128) >> 4;
+    int cur_q = -1, a_loads = 0, it_tile = 0;
+    int s = 0;                  // stage of the next tile, and the parity its `full` barrier completes with
+    uint32_t full_par = 0;
+    bool ok = true;
+    for (int w = item_begin; ok && w < item_end; w++) {
+        const MsItem it = ms_item(p, w);
+        const int nd = __shfl_sync(0xffffffffu, it.nd, 0), q = __shfl_sync(0xffffffffu, it.q, 0);
+        const int ntok = __shfl_sync(0xffffffffu, it.ntok, 0);
+        if (nd == 0) continue;
+        if (q != cur_q) {
+            if (a_loads > 0 && elect_one()) umma_commit(&sh->a_empty);  // every MMA that read the old A has retired
+            if (!__all_sync(0xffffffffu, mbar_wait(&sh->a_full, a_loads & 1, p.watchdog))) break;
+            cur_q = q;
+            a_loads++;
+        }
+        const int ntiles = (ntok + p.NT - 1) / p.NT;
+        for (int t = 0; t < ntiles; t++, it_tile++) {
+            const int acc = it_tile & ((1 << p.na_shift) - 1);
+            bool got = mbar_wait(&sh->tmem_empty[acc], ((it_tile >> p.na_shift) & 1) ^ 1, p.watchdog);
+            got = got && mbar_wait(&sh->full[s], full_par, p.watchdog);
+            if (!__all_sync(0xffffffffu, got)) { ok = false; break; }
+            tc_fence_after();
+            if (elect_one()) {
+                const uint64_t db0 = db_base + (uint64_t)(s * b_stage);
+#pragma unroll 1
                 for (int m = 0; m < p.MT; m++) {
-                    const uint32_t a0 = smem_u32(sA + m * 2 * (128 * 128));
+                    const uint64_t da0 = da_base + (uint64_t)(m * a_mtile);
                     const uint32_t d_tmem = tmem_base + acc * acc_cols + m * p.NT;
 #pragma unroll
-                    for (int k = 0; k < 8; k++) {
-                        const uint64_t da = umma_smem_desc_sw128(a0 + (k >> 2) * (128 * 128) + (k & 3) * 32);
-                        const uint64_t db = umma_smem_desc_sw128(b0 + (k >> 2) * (p.NT * 128) + (k & 3) * 32);
-                        umma_bf16(d_tmem, da, db, idesc, k > 0);
-                    }
+                    for (int k = 0; k < 8; k++)
+                        umma_bf16(d_tmem, da0 + (uint64_t)((k >> 2) * a_khalf + (k & 3) * 2),
+                                  db0 + (uint64_t)((k >> 2) * b_khalf + (k & 3) * 2), idesc, k > 0);
                 }
                 umma_commit(&sh->empty[s]);
                 umma_commit(&sh->tmem_full[acc]);
             }
+            __syncwarp();
+            if (++s == p.NS) { s = 0; full_par ^= 1; }
         }
     }
 }
@@ -204,7 +224,11 @@ __device__ __forceinline__ void ms_epilogue(const MsParams& p, MsShared* sh, uin
         // passage ends of the item (relative to its first token) held one per lane: lane d+1 = end of passage d
         int ends_reg = 0x7fffffff;
         if (lane <= it.nd) ends_reg = it.ends ? (it.ends[lane] - it.ends[0]) : lane * p.Ld;
-        auto doc_end = [&](int d) -> int { return __shfl_sync(0xffffffffu, ends_reg, d + 1); };
+        // (with 32 passages there is no lane 32 for the item's end: it is it.ntok)
+        auto doc_end = [&](int d) -> int {
+            const int v = __shfl_sync(0xffffffffu, ends_reg, min(d + 1, 31));
+            return d + 1 < 32 ? v : it.ntok;
+        };
         int doc = 0;
         int next_end = doc_end(0);
 
@@ -224,7 +248,7 @@ __device__ __forceinline__ void ms_epilogue(const MsParams& p, MsShared* sh, uin
         const int nchunks = p.NT >> 5;
         int mnext[4] = {0, 0, 0, 0};
         for (int t = 0; t < ntiles; t++, it_tile++) {
-            const int acc = it_tile & 1;
+            const int acc = it_tile & ((1 << p.na_shift) - 1);
             // padded form: mask bytes of the tile (lane <- token 32*ch + lane of each chunk).  The epilogue is the
             // slowest role, so the accumulator is usually ready already: the bytes of tile t+1 are requested
             // now and consumed one tile later, keeping their latency off the critical path.
@@ -243,7 +267,7 @@ __device__ __forceinline__ void ms_epilogue(const MsParams& p, MsShared* sh, uin
                     mnext[ch] = (ch * 32 < p.NT && tk < it.ntok) ? p.mask[it.row0 + tk] : 0;
                 }
             }
-            if (!mbar_wait(&sh->tmem_full[acc], (it_tile >> 1) & 1, p.watchdog)) { ok = false; break; }
+            if (!mbar_wait(&sh->tmem_full[acc], (it_tile >> p.na_shift) & 1, p.watchdog)) { ok = false; break; }
             tc_fence_after();
             const uint32_t tmem_acc = tmem_lane + acc * acc_cols;
             for (int ch = 0; ch < nchunks; ch++) {
@@ -427,8 +451,8 @@ __device__ __forceinline__ void ms_epilogue_a1(const MsParams& p, MsShared* sh, 
         };
         const int ntiles = (it.ntok + 127) >> 7;
         for (int t = 0; t < ntiles; t++, it_tile++) {
-            const int acc = it_tile & 1;
-            if (!mbar_wait(&sh->tmem_full[acc], (it_tile >> 1) & 1, p.watchdog)) { ok = false; break; }
+            const int acc = it_tile & ((1 << p.na_shift) - 1);
+            if (!mbar_wait(&sh->tmem_full[acc], (it_tile >> p.na_shift) & 1, p.watchdog)) { ok = false; break; }
             tc_fence_after();
             if (live) {
                 const uint32_t tmem_acc = tmem_lane + acc * 128;
@@ -443,7 +467,8 @@ __device__ __forceinline__ void ms_epilogue_a1(const MsParams& p, MsShared* sh, 
                         while (tk0 == next_end && doc + 1 < it.nd) {   // this chunk opens the next passage
                             flush(doc);
                             doc++;
-                            next_end = __shfl_sync(0xffffffffu, ends_reg, doc + 1);
+                            const int nx = __shfl_sync(0xffffffffu, ends_reg, min(doc + 1, 31));
+                            next_end = doc + 1 < 32 ? nx : it.ntok;     // no lane 32: the 32nd passage ends with the item
                         }
                         tmem_ld_32x16(tmem_acc + ch * 32 + 16, rb);    // second half in flight ...
                         runmax = max16(ra, runmax);                    // ... while the first is reduced
@@ -498,7 +523,7 @@ maxsim_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
         mbar_init(&sh->a_full, 1);
         mbar_init(&sh->a_empty, 1);
         for (int s = 0; s < p.NS; s++) { mbar_init(&sh->full[s], 1); mbar_init(&sh->empty[s], 1); }
-        for (int a = 0; a < 2; a++) { mbar_init(&sh->tmem_full[a], 1); mbar_init(&sh->tmem_empty[a], n_epi); }
+        for (int a = 0; a < 4; a++) { mbar_init(&sh->tmem_full[a], 1); mbar_init(&sh->tmem_empty[a], n_epi); }
         fence_mbar_init();
     }
     if (warp == 7) {
@@ -603,7 +628,7 @@ maxsim_fused_kernel(const __grid_constant__ CUtensorMap map_q, const MsParams p)
         mbar_init(&sh->a_full, 1);
         mbar_init(&sh->a_empty, 1);
         for (int s = 0; s < p.NS; s++) { mbar_init(&sh->full[s], wpt); mbar_init(&sh->empty[s], 1); }
-        for (int a = 0; a < 2; a++) { mbar_init(&sh->tmem_full[a], 1); mbar_init(&sh->tmem_empty[a], n_epi); }
+        for (int a = 0; a < 4; a++) { mbar_init(&sh->tmem_full[a], 1); mbar_init(&sh->tmem_empty[a], n_epi); }
         fence_mbar_init();
     }
     if (warp == 5) {
@@ -814,6 +839,7 @@ static int ms_configure(MsParams& p, int Lq_pad) {
     p.MT = (Lq_pad + 127) / 128;
     PLAID_CHECK_ARG(p.MT >= 1 && p.MT <= kMsMaxMT, PLAID_ERR_UNSUPPORTED, "maxsim: Lq_pad=%d > 512 query tokens", Lq_pad);
     p.NT = (p.MT <= 2) ? 128 : 64;   // 2 accumulator buffers x MT x NT <= 512 TMEM columns
+    p.na_shift = (4 * p.MT * p.NT <= 512) ? 2 : 1;
     const int a_bytes = p.MT * 128 * kDim * 2, b_bytes = p.NT * kDim * 2;
     int ns = (200 * 1024 - a_bytes) / b_bytes;
     p.NS = ns > kMsMaxStages ? kMsMaxStages : ns;
