@@ -141,8 +141,11 @@ __device__ __forceinline__ float max32(const uint32_t (&r)[32], float seed) {
 // the compiler re-broadcast every tcgen05 operand, ~300 instructions per tile on the kernel's critical path);
 // only lane 0 issues.  Stage / phase counters advance incrementally (no division), and the shared-memory
 // descriptors are the base descriptor plus a 16-byte-unit offset.
+// With map_q != nullptr the warp also loads the query tile itself (no separate TMA producer warp): it lets the
+// MMAs that read the old query retire, issues the TMA and waits for it -- a drain of a few tiles once per query.
 __device__ __forceinline__ void ms_mma_issue(const MsParams& p, MsShared* sh, uint8_t* sA, uint8_t* sB, int b_bytes,
-                                             uint32_t tmem_base_in, int item_begin, int item_end, int lane) {
+                                             uint32_t tmem_base_in, int item_begin, int item_end, int lane,
+                                             const CUtensorMap* map_q = nullptr) {
     // everything the tcgen05 operands derive from is made provably warp-uniform (lane-0 broadcasts), otherwise the
     // compiler wraps every instruction in an elect/broadcast loop
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, tmem_base_in, 0);
@@ -162,6 +165,16 @@ __device__ __forceinline__ void ms_mma_issue(const MsParams& p, MsShared* sh, ui
         if (nd == 0) continue;
         if (q != cur_q) {
             if (a_loads > 0 && elect_one()) umma_commit(&sh->a_empty);  // every MMA that read the old A has retired
+            if (map_q != nullptr) {
+                if (a_loads > 0 && !__all_sync(0xffffffffu, mbar_wait(&sh->a_empty, (a_loads - 1) & 1, p.watchdog))) break;
+                if (elect_one()) {
+                    mbar_expect_tx(&sh->a_full, p.MT * 128 * kDim * 2);
+                    for (int m = 0; m < p.MT; m++)
+                        for (int h = 0; h < 2; h++)
+                            tma_load_2d(sA + (m * 2 + h) * (128 * 128), map_q, &sh->a_full, h * 64, q * p.Lq_pad + m * 128);
+                }
+                __syncwarp();
+            }
             if (!__all_sync(0xffffffffu, mbar_wait(&sh->a_full, a_loads & 1, p.watchdog))) break;
             cur_q = q;
             a_loads++;
@@ -601,10 +614,19 @@ static constexpr int kFusedDecWarps = 16;
 // copies into a second staging buffer (no registers held across the chunk); 4 and 8 bits keep one buffer and
 // carry the next chunk in registers, because their staging areas are 2-4x larger.
 template <int NBITS> constexpr bool kFusedAsyncStage = (NBITS <= 2);
-static constexpr int kFusedThreads = (6 + kFusedDecWarps) * 32;   // warps 0-3 epilogue, 4 Q TMA, 5 MMA, 6.. decompress
+#ifndef MS_FUSED_UT
+#define MS_FUSED_UT 32
+#endif
+static constexpr int kFusedUnit = MS_FUSED_UT;   // rows of a tile built by one decompressor warp (16 or 32)
+// Two role layouts.  Regular: warps 0-3 epilogue, 4 Q TMA, 5 MMA, 6-21 decompress (704 threads, 80 registers).
+// SLIM (one m-tile and Lq_pad <= 96, i.e. at most three TMEM lane quadrants hold query rows): warps 0-2 epilogue,
+// warp 3 -- whose quadrant is empty -- issues the MMAs and loads the queries, 4-19 decompress: 640 threads, which
+// lifts the register cap from 80 to 96 per thread for the decompressors (they spill at 80).
+static constexpr int kFusedThreads = (6 + kFusedDecWarps) * 32;
+static constexpr int kFusedThreadsSlim = (4 + kFusedDecWarps) * 32;
 
-template <int NBITS>
-__global__ void __launch_bounds__(kFusedThreads, 1)
+template <int NBITS, bool SLIM>
+__global__ void __launch_bounds__(SLIM ? kFusedThreadsSlim : kFusedThreads, 1)
 maxsim_fused_kernel(const __grid_constant__ CUtensorMap map_q, const MsParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -614,15 +636,15 @@ maxsim_fused_kernel(const __grid_constant__ CUtensorMap map_q, const MsParams p)
     uint8_t* sA = smem;
     uint8_t* sB = smem + a_bytes;                   // [NS][2 k-halves][NT rows][128 B]
     uint8_t* sLUT = sB + p.NS * b_bytes;            // fp16 weight table, 256 entries x 128 B (1024-aligned)
-    uint8_t* s_stage = sLUT + kLutBytes;            // [kFusedDecWarps][1 or 2 buffers][32 tokens * PB]
-    MsShared* sh = reinterpret_cast<MsShared*>(s_stage + kFusedDecWarps * (kFusedAsyncStage<NBITS> ? 2 : 1) * 32 * PB);
+    uint8_t* s_stage = sLUT + kLutBytes;            // [kFusedDecWarps][1 or 2 buffers][kFusedUnit tokens * PB]
+    MsShared* sh = reinterpret_cast<MsShared*>(s_stage + kFusedDecWarps * (kFusedAsyncStage<NBITS> ? 2 : 1) * kFusedUnit * PB);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const bool lean = p.MT == 1 && p.NT == 128;      // see maxsim_kernel
     const int n_epi = lean ? min(4, p.Lq_pad >> 5) : 4;
     const int item_begin = blockIdx.x * p.items_per_cta;
     const int item_end = min(p.num_items, item_begin + p.items_per_cta);
-    const int wpt = p.NT >> 5;                      // decompressor warps per tile
+    const int wpt = p.NT / kFusedUnit;              // decompressor warps per tile
 
     if (threadIdx.x == 0) {
         mbar_init(&sh->a_full, 1);
@@ -631,7 +653,8 @@ maxsim_fused_kernel(const __grid_constant__ CUtensorMap map_q, const MsParams p)
         for (int a = 0; a < 4; a++) { mbar_init(&sh->tmem_full[a], 1); mbar_init(&sh->tmem_empty[a], n_epi); }
         fence_mbar_init();
     }
-    if (warp == 5) {
+    constexpr int kMmaWarp = SLIM ? 3 : 5, kFirstDecWarp = SLIM ? 4 : 6;
+    if (warp == kMmaWarp) {
         tmem_alloc(&sh->tmem_base, 512);
         tmem_relinquish();
     }
@@ -641,13 +664,15 @@ maxsim_fused_kernel(const __grid_constant__ CUtensorMap map_q, const MsParams p)
     tc_fence_after();
     const uint32_t tmem_base = sh->tmem_base;
 
-    if (warp < 4) {
+    if (SLIM && warp == kMmaWarp) {
+        ms_mma_issue(p, sh, sA, sB, b_bytes, tmem_base, item_begin, item_end, lane, &map_q);
+    } else if (warp < 4) {
         if (lean) {
             if (warp < n_epi) ms_epilogue_a1(p, sh, tmem_base, item_begin, item_end, warp, lane, n_epi);
         } else {
             ms_epilogue<0>(p, sh, tmem_base, item_begin, item_end, warp, lane);
         }
-    } else if (warp == 4) {
+    } else if (!SLIM && warp == 4) {
         // ===================== query (A operand) TMA producer =====================
         if (lane == 0) {
             tma_prefetch_desc(&map_q);
@@ -664,29 +689,41 @@ maxsim_fused_kernel(const __grid_constant__ CUtensorMap map_q, const MsParams p)
                 a_loads++;
             }
         }
-    } else if (warp == 5) {
+    } else if (!SLIM && warp == 5) {
         ms_mma_issue(p, sh, sA, sB, b_bytes, tmem_base, item_begin, item_end, lane);
     } else {
         // ===================== decompressor warps =====================
-        const int dw = warp - 6;
-        const int group = dw / wpt, cit = dw - group * wpt;   // stage owned by this warp's group, chunk inside the tile
-        if (group >= p.NS) goto done;                          // more warps than stages fit in shared memory: idle
+        // A tile of NT rows is built by wpt = NT / UT warps (one UT-row unit each; passages are 32-row aligned, so
+        // a unit belongs to one passage); the 16 warps form G = 16 / wpt groups and group g builds the tiles
+        // g, g + G, g + 2G, ... of the CTA's tile sequence, tile i into stage i % NS.  With UT = 16 there are two
+        // groups for four stages: a warp that finishes its unit moves straight on to its unit of the group's next
+        // tile instead of waiting for the slowest of the 16 warps and for the tensor core (with UT = 32 every
+        // stage always has a tile under construction and the whole CTA runs in lock step).
+        const int dw = warp - kFirstDecWarp;
+        const int group = dw / wpt, cit = dw - group * wpt;   // this warp's group, its unit inside the tile
+        const int G = kFusedDecWarps / wpt;                    // power of two
         // A quarter warp decodes one token: lane q of the quarter owns 16-byte chunk q of both k-halves of the row
         // (dims 8q..8q+7 and 64+8q..64+8q+7); one step of the warp = the 4 tokens 4*step + tsub.
         const int q = lane & 7, tsub = lane >> 3;
+        constexpr int UT = kFusedUnit;
         constexpr int CB = kFusedAsyncStage<NBITS> ? MS_FUSED_CB : 1;   // steps per centroid batch (4*CB tokens, 4*CB registers)
-        constexpr int NBATCH = 8 / CB;
+        constexpr int NBATCH = (UT / 4) / CB;
+        static_assert(NBATCH >= 2 && (NBATCH % 2) == 0, "a unit is an even number of centroid batches");
         constexpr int kStageBufs = kFusedAsyncStage<NBITS> ? 2 : 1;
-        const uint32_t stage0_sa = smem_u32(s_stage + dw * (kStageBufs * 32 * PB));   // this warp's residual staging area(s)
+        constexpr int NPASS = (UT * PB + 511) / 512;           // 512-byte passes (16 B per lane) over a unit's packed rows
+        const uint32_t stage0_sa = smem_u32(s_stage + dw * (kStageBufs * UT * PB));   // this warp's residual staging area(s)
         int buf = 0;
         const uint32_t lut_sa = lut_lane_base<NBITS>(smem_u32(sLUT), lane);
         const char* cent_q = reinterpret_cast<const char*>(p.centroids) + q * 16;
-        // Row j = 4*step + tsub of the chunk; chunk q of a row sits at 16-byte slot q ^ (j & 7) = (q ^ tsub) ^ 4*(step & 1).
-        const uint32_t tile_lane = smem_u32(sB + group * b_bytes) + (cit * 32 + tsub) * 128;
-        const uint32_t slot_even = tile_lane + ((uint32_t)(q ^ tsub) << 4), slot_odd = tile_lane + ((uint32_t)(q ^ tsub ^ 4) << 4);
+        // Row j = 4*step + tsub of the unit; chunk q of a row sits at 16-byte slot q ^ (row & 7) = (q ^ tsub) ^ 4*(step & 1)
+        // (units start on multiples of 16 rows).
+        const uint32_t tile_lane0 = smem_u32(sB) + (cit * UT + tsub) * 128;
+        const uint32_t slot_even = (uint32_t)(q ^ tsub) << 4, slot_odd = (uint32_t)(q ^ tsub ^ 4) << 4;
         const uint32_t khalf = (uint32_t)p.NT * 128;          // the second k-half of the tile
-        int base_mod = 0;     // (tiles of the earlier items) % NS: tile t of this item uses stage (base_mod + t) % NS
-        int mine = 0;         // tiles this warp's group has built so far = phase counter of its stage barriers
+        int base_g = 0;       // (tiles of the earlier items) % G
+        int st = group;       // stage of this group's next tile and the parity of that use of the stage
+        uint32_t st_par = 0;
+        while (st >= p.NS) { st -= p.NS; st_par ^= 1; }
         bool ok = true;
         for (int w = item_begin; ok && w < item_end; w++) {
             const MsItem it = ms_item(p, w);
@@ -702,27 +739,27 @@ maxsim_fused_kernel(const __grid_constant__ CUtensorMap map_q, const MsParams p)
             int ends_reg = 0x7fffffff;   // aligned start of passage `lane` relative to the item (lane nd = item end)
             if (lane <= it.nd) ends_reg = it.ends[lane] - it.ends[0];
             const int ntiles = (it.ntok + p.NT - 1) / p.NT;
-            // geometry of this warp's chunk in tile t: first token in the index arrays and number of real rows
+            // geometry of this warp's unit in tile t: first token in the index arrays and number of real rows
             auto geom = [&](int t, int64_t& tok0, int& valid) {
-                const int tk0 = t * p.NT + cit * 32;            // item-relative first row of the chunk
+                const int tk0 = t * p.NT + cit * UT;            // item-relative first row of the unit
                 valid = 0;
                 tok0 = 0;
                 if (tk0 < it.ntok) {
                     const int d = __popc(__ballot_sync(0xffffffffu, ends_reg <= tk0)) - 1;
                     const int seg = tk0 - __shfl_sync(0xffffffffu, ends_reg, d);
                     tok0 = __shfl_sync(0xffffffffu, my_off, d) + seg;
-                    valid = max(0, min(32, __shfl_sync(0xffffffffu, my_len, d) - seg));
+                    valid = max(0, min(UT, __shfl_sync(0xffffffffu, my_len, d) - seg));
                 }
             };
-            // packed residuals (valid*PB bytes, 16 per lane and pass) and codes of a chunk: rows past `valid` get zero
+            // packed residuals (valid*PB bytes, 16 per lane and pass) and codes of a unit: rows past `valid` get zero
             // bytes and code 0, so they decode to finite values that the scale step replaces by zeros
-            auto fetch = [&](int64_t tok0, int valid, uint32_t st_sa, int4 (&res)[NBITS], int& code) {
+            auto fetch = [&](int64_t tok0, int valid, uint32_t st_sa, int4 (&res)[NPASS], int& code) {
 #pragma unroll
-                for (int v = 0; v < NBITS; v++) {
+                for (int v = 0; v < NPASS; v++) {
                     const int byte = v * 512 + lane * 16;
                     const bool real = byte < valid * PB;
                     if constexpr (kFusedAsyncStage<NBITS>) {
-                        cp_async_16(st_sa + byte, p.residuals + (real ? tok0 * PB + byte : 0), real ? 16 : 0);
+                        if (byte < UT * PB) cp_async_16(st_sa + byte, p.residuals + (real ? tok0 * PB + byte : 0), real ? 16 : 0);
                     } else {
                         res[v] = make_int4(0, 0, 0, 0);
                         if (real) res[v] = ld_stream_v4(p.residuals + tok0 * PB + byte);
@@ -731,7 +768,7 @@ maxsim_fused_kernel(const __grid_constant__ CUtensorMap map_q, const MsParams p)
                 if constexpr (kFusedAsyncStage<NBITS>) cp_async_commit();
                 code = (lane < valid) ? ld_stream_s32(p.codes + tok0 + lane) : 0;
             };
-            // centroid rows of batch bt (steps bt*CB .. bt*CB+CB-1) of a chunk whose codes sit one per lane in `code`
+            // centroid rows of batch bt (steps bt*CB .. bt*CB+CB-1) of a unit whose codes sit one per lane in `code`
             auto load_cents = [&](int code, int bt, uint4 (&clo)[CB], uint4 (&chi)[CB]) {
 #pragma unroll
                 for (int u = 0; u < CB; u++) {
@@ -742,7 +779,8 @@ maxsim_fused_kernel(const __grid_constant__ CUtensorMap map_q, const MsParams p)
                 }
             };
             // decode batch bt into the tile: shared loads of step u+1 are issued before the shuffles of step u
-            auto process = [&](int bt, int valid, uint32_t stage_sa, const uint4 (&clo)[CB], const uint4 (&chi)[CB]) {
+            auto process = [&](int bt, int valid, uint32_t stage_sa, uint32_t tile_sa, const uint4 (&clo)[CB],
+                               const uint4 (&chi)[CB]) {
                 uint32_t wlo[4], whi[4];
                 token_weights_h8<NBITS>(stage_sa + (4 * bt * CB + tsub) * PB, lut_sa, q, wlo);
                 token_weights_h8<NBITS>(stage_sa + (4 * bt * CB + tsub) * PB, lut_sa, q + 8, whi);
@@ -758,26 +796,26 @@ maxsim_fused_kernel(const __grid_constant__ CUtensorMap map_q, const MsParams p)
                     ss = quarter_sum(ss);
                     uint4 olo, ohi;
                     token_scale_h16(v, ss, j < valid, olo, ohi);
-                    const uint32_t dst = (((CB & 1) ? (step & 1) : (u & 1)) ? slot_odd : slot_even) + step * 512;
+                    const uint32_t dst = tile_sa + (((CB & 1) ? (step & 1) : (u & 1)) ? slot_odd : slot_even) + step * 512;
                     sts_v4u32_relaxed(dst, olo.x, olo.y, olo.z, olo.w);
                     sts_v4u32_relaxed(dst + khalf, ohi.x, ohi.y, ohi.z, ohi.w);
                 }
             };
-            int4 pres[NBITS];
+            int4 pres[NPASS];
             int pcode = 0, pvalid = 0, ptile = -1;
             uint4 alo[CB], ahi[CB], blo[CB], bhi[CB];
-            bool a_ready = false;                               // batch 0 of the coming chunk is already in alo/ahi
-            int first = group - base_mod;                       // this group's first tile of the item
-            if (first < 0) first += p.NS;
-            base_mod = (base_mod + ntiles) % p.NS;
-            for (int t = first; t < ntiles; t += p.NS, mine++) {
-                const uint32_t stage_sa = stage0_sa + buf * (32 * PB);
-                int4 res[NBITS];
+            bool a_ready = false;                               // batch 0 of the coming unit is already in alo/ahi
+            const int first = (group - base_g) & (G - 1);       // this group's first tile of the item
+            base_g = (base_g + ntiles) & (G - 1);
+            for (int t = first; t < ntiles; t += G) {
+                const uint32_t stage_sa = stage0_sa + buf * (UT * PB);
+                const uint32_t tile_sa = tile_lane0 + st * b_bytes;
+                int4 res[NPASS];
                 int code, valid;
-                if (ptile == t) {                               // requested while the previous tile was being built
+                if (ptile == t) {                               // requested while the previous unit was being built
                     if constexpr (!kFusedAsyncStage<NBITS>) {
 #pragma unroll
-                        for (int v = 0; v < NBITS; v++) res[v] = pres[v];
+                        for (int v = 0; v < NPASS; v++) res[v] = pres[v];
                     }
                     code = pcode;
                     valid = pvalid;
@@ -788,42 +826,54 @@ maxsim_fused_kernel(const __grid_constant__ CUtensorMap map_q, const MsParams p)
                 }
                 if (!a_ready && valid > 0) load_cents(code, 0, alo, ahi);
                 a_ready = false;
-                const bool more = t + p.NS < ntiles;
-                if (more) {                                     // this warp's next chunk of the item: loads in flight now
+                const bool more = t + G < ntiles;
+                if (more) {                                     // this warp's next unit of the item: loads in flight now
                     int64_t ntok0;
-                    geom(t + p.NS, ntok0, pvalid);
-                    fetch(ntok0, pvalid, stage0_sa + (buf ^ 1) * (32 * PB), pres, pcode);
-                    ptile = t + p.NS;
+                    geom(t + G, ntok0, pvalid);
+                    fetch(ntok0, pvalid, stage0_sa + (buf ^ 1) * (UT * PB), pres, pcode);
+                    ptile = t + G;
                 }
-                if (!mbar_wait(&sh->empty[group], (mine & 1) ^ 1, p.watchdog)) { ok = false; break; }
-                if constexpr (kFusedAsyncStage<NBITS>) {        // this chunk's rows have landed (the next chunk's may not)
+                if (!mbar_wait(&sh->empty[st], st_par ^ 1, p.watchdog)) { ok = false; break; }
+                if constexpr (kFusedAsyncStage<NBITS>) {        // this unit's rows have landed (the next unit's may not)
                     if (more) cp_async_wait<1>(); else cp_async_wait<0>();
                     __syncwarp();
                     buf ^= 1;
                 }
+                if (valid == 0 && t * p.NT + cit * UT < it.ntok) {
+                    // the unit lies entirely in the alignment padding of a passage (UT = 16 only): its rows must be zero
+#pragma unroll
+                    for (int step = 0; step < UT / 4; step++) {
+                        const uint32_t dst = tile_sa + ((step & 1) ? slot_odd : slot_even) + step * 512;
+                        sts_v4u32_relaxed(dst, 0u, 0u, 0u, 0u);
+                        sts_v4u32_relaxed(dst + khalf, 0u, 0u, 0u, 0u);
+                    }
+                }
                 if (valid > 0) {
                     if constexpr (!kFusedAsyncStage<NBITS>) {
 #pragma unroll
-                        for (int v = 0; v < NBITS; v++)
-                            sts_v4u32(stage_sa + v * 512 + lane * 16, res[v].x, res[v].y, res[v].z, res[v].w);
+                        for (int v = 0; v < NPASS; v++)
+                            if (v * 512 + lane * 16 < UT * PB)
+                                sts_v4u32(stage_sa + v * 512 + lane * 16, res[v].x, res[v].y, res[v].z, res[v].w);
                         __syncwarp();
                     }
 #pragma unroll 1
                     for (int bt = 0; bt < NBATCH; bt += 2) {    // two batches per trip: A = bt, B = bt + 1
                         load_cents(code, bt + 1, blo, bhi);
-                        process(bt, valid, stage_sa, alo, ahi);
+                        process(bt, valid, stage_sa, tile_sa, alo, ahi);
                         if (bt + 2 < NBATCH) {
                             load_cents(code, bt + 2, alo, ahi);
-                        } else if (more && pvalid > 0) {        // batch 0 of the next chunk (its codes arrived long ago)
+                        } else if (more && pvalid > 0) {        // batch 0 of the next unit (its codes arrived long ago)
                             load_cents(pcode, 0, alo, ahi);
                             a_ready = true;
                         }
-                        process(bt + 1, valid, stage_sa, blo, bhi);
+                        process(bt + 1, valid, stage_sa, tile_sa, blo, bhi);
                     }
                 }
                 fence_proxy_async_smem();      // generic-proxy writes -> visible to the tensor core's async proxy
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&sh->full[group]);
+                if (lane == 0) mbar_arrive(&sh->full[st]);
+                st += G;                       // the group's next tile
+                while (st >= p.NS) { st -= p.NS; st_par ^= 1; }
             }
         }
     }
@@ -831,7 +881,7 @@ maxsim_fused_kernel(const __grid_constant__ CUtensorMap map_q, const MsParams p)
 done:
     tc_fence_before();
     __syncthreads();
-    if (warp == 5) tmem_dealloc(tmem_base, 512);
+    if (warp == kMmaWarp) tmem_dealloc(tmem_base, 512);
 }
 
 static int ms_configure(MsParams& p, int Lq_pad) {
@@ -876,34 +926,30 @@ static int ms_launch_fused(const void* Qb, int q_rows, int nbits, MsParams& p, c
     CUtensorMap map_q;
     int rc;
     if ((rc = make_bf16_2d_map(&map_q, Qb, (uint64_t)q_rows, kDim, 128)) != PLAID_OK) return rc;
-    // one stage per group of NT/32 decompressor warps; as many groups as shared memory allows (spare warps idle)
-    const int wpt = p.NT >> 5;
+    // as many B stages as shared memory allows; the decompressor groups share them in tile order
     const int stage_bufs = nbits <= 2 ? 2 : 1;       // kFusedAsyncStage
-    const int fixed = 1024 + p.MT * 128 * kDim * 2 + kLutBytes + kFusedDecWarps * stage_bufs * 32 * 16 * nbits +
+    const int fixed = 1024 + p.MT * 128 * kDim * 2 + kLutBytes + kFusedDecWarps * stage_bufs * kFusedUnit * 16 * nbits +
                       (int)sizeof(MsShared) + 64;
     const int per_stage = p.NT * kDim * 2;
     p.NS = (227 * 1024 - fixed) / per_stage;
-    if (p.NS > kFusedDecWarps / wpt) p.NS = kFusedDecWarps / wpt;
     if (p.NS > kMsMaxStages) p.NS = kMsMaxStages;
     PLAID_CHECK_ARG(p.NS >= 2, PLAID_ERR_UNSUPPORTED, "maxsim_fused: shared memory too small for Lq_pad=%d, nbits=%d", p.Lq_pad, nbits);
     const int smem = fixed + p.NS * per_stage;
-    const void* fn = nbits == 1 ? (const void*)maxsim_fused_kernel<1> : nbits == 2 ? (const void*)maxsim_fused_kernel<2>
-                   : nbits == 4 ? (const void*)maxsim_fused_kernel<4> : (const void*)maxsim_fused_kernel<8>;
-    static int configured[9] = {0};
-    if (smem > configured[nbits]) {
+    const bool slim = p.MT == 1 && p.NT == 128 && p.Lq_pad <= 96;
+#define PLAID_FUSED_FN(NB) (slim ? (const void*)maxsim_fused_kernel<NB, true> : (const void*)maxsim_fused_kernel<NB, false>)
+    const void* fn = nbits == 1 ? PLAID_FUSED_FN(1) : nbits == 2 ? PLAID_FUSED_FN(2) : nbits == 4 ? PLAID_FUSED_FN(4) : PLAID_FUSED_FN(8);
+#undef PLAID_FUSED_FN
+    static int configured[2][9] = {{0}, {0}};
+    if (smem > configured[slim][nbits]) {
         PLAID_CUDA_OK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        configured[nbits] = smem;
+        configured[slim][nbits] = smem;
     }
     int grid = sm_count();
     if (grid > p.num_items) grid = p.num_items;
     p.items_per_cta = (p.num_items + grid - 1) / grid;
     grid = (p.num_items + p.items_per_cta - 1) / p.items_per_cta;
-    switch (nbits) {
-        case 1: maxsim_fused_kernel<1><<<grid, kFusedThreads, smem, st>>>(map_q, p); break;
-        case 2: maxsim_fused_kernel<2><<<grid, kFusedThreads, smem, st>>>(map_q, p); break;
-        case 4: maxsim_fused_kernel<4><<<grid, kFusedThreads, smem, st>>>(map_q, p); break;
-        default: maxsim_fused_kernel<8><<<grid, kFusedThreads, smem, st>>>(map_q, p); break;
-    }
+    void* args[] = {(void*)&map_q, (void*)&p};
+    PLAID_CUDA_OK(cudaLaunchKernel(fn, dim3(grid), dim3(slim ? kFusedThreadsSlim : kFusedThreads), args, (size_t)smem, st));
     PLAID_LAUNCH_OK("maxsim_fused_kernel");
     return PLAID_OK;
 }
