@@ -404,7 +404,7 @@ def main():
         "filter_stage2": dict(bytes=4.0 * T2 + 16.0 * 1024 * B + (64.0 if eng.s_dtype == torch.float16 else 128.0) * T2,
                               flops=0.0),
         "candidates": dict(bytes=4.0 * ncand + (w["N"] / 8.0) * B * 2, flops=0.0),
-        "decompress": dict(bytes=(4.0 + 16 * nbits + 256.0 + 256.0) * T3, flops=0.0),   # codes+residual+f16 centroid row in, bf16 out
+        "decompress": dict(bytes=(4.0 + 16 * nbits + 256.0 + 256.0) * T3, flops=0.0),   # codes+residual+f16 centroid row in, fp16 out
         "maxsim": dict(bytes=256.0 * T3, flops=2.0 * Lq * 128 * T3),
         "maxsim_fused": dict(bytes=(4.0 + 16 * nbits) * T3, flops=2.0 * Lq * 128 * T3),    # K4' of SURVEY 8d
     }
@@ -443,8 +443,8 @@ def main():
     line = {
         "metric": "scored_doc_tokens_per_s", "value": tok_s, "unit": "doc-tokens/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "queries_per_s": B / (ms_step * 1e-3),
+        "vs_baseline": None, "dtype": "bf16 (centroid contraction) / fp16 (MaxSim operands), fp32 accumulate",
+        "data": "synthetic", "queries_per_s": B / (ms_step * 1e-3),
         "config": {"workload": f"{args.workload}: {w['desc']}", "passages_per_gpu": w["N"], "tokens_per_gpu": index.num_embeddings,
                    "centroids": C, "queries_per_step": B, "parallelism": f"pid-range shards x{world}, all-gather top-k merge",
                    "l2": "inputs larger than L2 (index + centroid-score table >> 126 MB), no explicit flush",

@@ -701,7 +701,12 @@ maxsim_fused_kernel(const __grid_constant__ CUtensorMap map_q, const MsParams p)
         // stage always has a tile under construction and the whole CTA runs in lock step).
         const int dw = warp - kFirstDecWarp;
         const int group = dw / wpt, cit = dw - group * wpt;   // this warp's group, its unit inside the tile
-        const int G = kFusedDecWarps / wpt;                    // power of two
+        // Groups in use: a power of two, at most the number of stages -- a stage's successive users must stay within
+        // one mbarrier phase of each other, which a group revisiting a stage after another group's turn would not
+        // (with fewer stages than groups the spare warps idle).
+        int G = kFusedDecWarps / wpt;
+        while (G > p.NS) G >>= 1;
+        if (group >= G) goto done;
         // A quarter warp decodes one token: lane q of the quarter owns 16-byte chunk q of both k-halves of the row
         // (dims 8q..8q+7 and 64+8q..64+8q+7); one step of the warp = the 4 tokens 4*step + tsub.
         const int q = lane & 7, tsub = lane >> 3;
