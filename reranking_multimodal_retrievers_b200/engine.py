@@ -95,8 +95,10 @@ class SearchEngine:
         C, N = ix.num_centroids, ix.num_passages
         tiles = (C + 255) // 256
         groups = Bc // 4                                              # one CTA per 4 queries and centroid range
-        csplit = 1 if groups >= 111 else max(1, min(tiles, 32, -(-148 // groups)))   # fill the 148 SMs once; every extra
-        # range restarts its running top-ncells lists from scratch, which costs more than a partial last wave
+        # centroid ranges per query group: as many as still fit the 148 SMs in ONE wave.  Measured (cfg4 shard,
+        # 44 groups): 3 ranges 9.7 ms, 4 ranges (176 CTAs, a second wave of 28) 14.3 ms, 6: 10.6, 10: 13.2 --
+        # every extra range re-streams the queries' accumulator setup and adds partial top-ncells lists to merge.
+        csplit = max(1, min(tiles, 32, 148 // max(groups, 1)))
         csplit = int(os.environ.get("PLAID_CSPLIT", csplit))
         nlists = 2 * csplit
         nd4 = ndocs // 4
