@@ -61,14 +61,15 @@ int plaid_f32_to_bf16(const float* src, void* dst_bf16, int64_t n, void* stream)
  * tcgen05; operands fed by TMA).  Fused epilogue products:
  *   idx_bits[b, c/32] bit (c%32)  = max_{k < nq_b} S[b,c,k] >= threshold      (centroid pruning mask)
  *   cell_val/cell_idx[b, k, l, j] = the ncells best (score, centroid) of query token k inside the
- *                                   l-th of 2*csplit partial lists (csplit centroid ranges x two
- *                                   128-column halves), best first, ties -> lowest centroid id;
+ *                                   l-th of PLAID_CELL_LISTS_PER_RANGE*csplit partial lists (csplit centroid
+ *                                   ranges x the column parts of a tile), best first, ties -> lowest centroid id;
  *                                   cell_idx = -1 where there is no entry.
  * nq_b = min(qlens[b], 32).  S is laid out [B_pad, C, 32] -- per query exactly the reference's
  * `centroid_scores` [C, nq] tensor (row = centroid) -- in fp32, or with s_is_f16 != 0 rounded to fp16
  * (the precision the reference's GPU branch computes S in); mask and cells are derived from the stored values.  C must be a multiple of 32; the grid is
  * (B_pad/4) x csplit CTAs.  Rows of Qb beyond qlens[b] must be zero (plaid_prepare_queries does it).
  * *watchdog (device int, may be NULL) is set to 1 if an in-kernel pipeline wait ever times out. */
+#define PLAID_CELL_LISTS_PER_RANGE 4
 int plaid_centroid_scores(const void* centroids_bf16, int C, const void* Qb_bf16, const int32_t* qlens,
                           int B_pad, int Lq_pad, float threshold, int ncells, int csplit,
                           void* S, int s_is_f16, uint32_t* idx_bits, float* cell_val, int32_t* cell_idx, int* watchdog,

@@ -10,7 +10,8 @@
 // and streams a contiguous range of centroid tiles through a 2-stage TMA ring; two 256-column fp32
 // accumulators in TMEM (all 512 columns) let the MMA of tile i+1 overlap the epilogue of tile i.
 //
-// Epilogue (8 warps; warp = (lane quadrant, 128-column half)), straight out of TMEM:
+// Epilogue (16 warps; warp = (lane quadrant, 64-column quarter) -- one warp per scheduler is latency-bound on its
+// TMEM load -> convert -> store chain, four hide it), straight out of TMEM:
 //   * S[b, c, 0..31] -- for one centroid the warp's 32 lanes write 32 consecutive floats, i.e. one
 //     full 128-byte line of the reference's [C, nq] layout;
 //   * idx bit (b, c) = max over the query's tokens >= threshold, as a warp vote (any token >= threshold),
@@ -26,7 +27,9 @@ namespace plaid {
 static constexpr int kCsM = 128;            // accumulator rows: 4 queries x 32 tokens
 static constexpr int kCsN = 256;            // centroids per tile
 static constexpr int kCsStages = 2;         // B-operand ring depth
-static constexpr int kCsThreads = 384;      // warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4..11 epilogue
+static constexpr int kCsParts = PLAID_CELL_LISTS_PER_RANGE;   // column parts of a tile, one epilogue warp per (quadrant, part)
+static constexpr int kCsPartCols = kCsN / kCsParts;
+static constexpr int kCsThreads = (4 + 4 * kCsParts) * 32;    // warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4.. epilogue
 static constexpr int kCsABytes = kCsM * kDim * 2;        // 32 KB
 static constexpr int kCsBBytes = kCsN * kDim * 2;        // 64 KB per stage
 static constexpr int kCsSmemBytes = 1024 + kCsABytes + kCsStages * kCsBBytes + 256;
@@ -56,7 +59,7 @@ centroid_scores_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
     uint8_t* sA = smem;                          // [2 k-halves][128 rows][128 B]
     uint8_t* sB = smem + kCsABytes;              // [stage][2 k-halves][256 rows][128 B]
     CsBarriers* bar = reinterpret_cast<CsBarriers*>(smem + kCsABytes + kCsStages * kCsBBytes);
-    __shared__ float s_cut[4][32];   // per (query, token): best NC-th value any of the two column-half warps has seen
+    __shared__ float s_cut[4][32];   // per (query, token): best NC-th value any of the column-part warps has seen
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int qgroup = blockIdx.x, split = blockIdx.y;
@@ -69,7 +72,7 @@ centroid_scores_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
     if (threadIdx.x == 0) {
         mbar_init(&bar->a_full, 1);
         for (int s = 0; s < kCsStages; s++) { mbar_init(&bar->full[s], 1); mbar_init(&bar->empty[s], 1); }
-        for (int a = 0; a < 2; a++) { mbar_init(&bar->tmem_full[a], 1); mbar_init(&bar->tmem_empty[a], 8); }
+        for (int a = 0; a < 2; a++) { mbar_init(&bar->tmem_full[a], 1); mbar_init(&bar->tmem_empty[a], 4 * kCsParts); }
         bar->abort_flag = 0;
         fence_mbar_init();
     }
@@ -127,7 +130,7 @@ centroid_scores_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
         }
     } else if (warp >= 4) {
         // ===================== epilogue =====================
-        const int quad = warp & 3, half = (warp - 4) >> 2;
+        const int quad = warp & 3, part = (warp - 4) >> 2;
         const int bq = qgroup * 4 + quad;
         const int nq = min(qlens[bq], PLAID_NQ_MAX);
         const bool tok_valid = lane < nq;
@@ -142,11 +145,11 @@ centroid_scores_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
             const int acc = it & 1;
             if (!mbar_wait(&bar->tmem_full[acc], (it >> 1) & 1, watchdog)) break;
             tc_fence_after();
-            const int c_tile = (tile_begin + it) * kCsN + half * 128;
+            const int c_tile = (tile_begin + it) * kCsN + part * kCsPartCols;
 #pragma unroll 1
-            for (int ch = 0; ch < 4; ch++) {
+            for (int ch = 0; ch < kCsPartCols / 32; ch++) {
                 uint32_t r[32];
-                tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + acc * kCsN + half * 128 + ch * 32, r);
+                tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + acc * kCsN + part * kCsPartCols + ch * 32, r);
                 tc_wait_ld();
                 const int c0 = c_tile + ch * 32;
                 if (c0 >= C) break;  // C is a multiple of 32: a chunk is entirely inside or outside
@@ -211,8 +214,8 @@ centroid_scores_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar->tmem_empty[acc]);
         }
-        // every (centroid range, column half) keeps its own partial list: slot = split*2 + half
-        const size_t base = (((size_t)bq * PLAID_NQ_MAX + lane) * (csplit * 2) + (split * 2 + half)) * ncells;
+        // every (centroid range, column part) keeps its own partial list: slot = split*kCsParts + part
+        const size_t base = (((size_t)bq * PLAID_NQ_MAX + lane) * (csplit * kCsParts) + (split * kCsParts + part)) * ncells;
 #pragma unroll
         for (int p = 0; p < NC; p++)
             if (p < ncells) {

@@ -23,6 +23,7 @@ from . import _lib, ops
 from .index import DeviceIndex
 from .ops import _p, _stream
 
+CELL_LISTS_PER_RANGE = 4      # PLAID_CELL_LISTS_PER_RANGE (include/plaid_b200.h)
 NQ_MAX = ops.NQ_MAX
 
 
@@ -100,7 +101,7 @@ class SearchEngine:
         # every extra range re-streams the queries' accumulator setup and adds partial top-ncells lists to merge.
         csplit = max(1, min(tiles, 32, 148 // max(groups, 1)))
         csplit = int(os.environ.get("PLAID_CSPLIT", csplit))
-        nlists = 2 * csplit
+        nlists = CELL_LISTS_PER_RANGE * csplit
         nd4 = ndocs // 4
         cand_stride = max(ndocs, min(N, NQ_MAX * ncells * max(ix.max_ivf_len, 1)))
         cand_stride = ((cand_stride + 63) // 64) * 64
