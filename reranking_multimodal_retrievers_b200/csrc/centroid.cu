@@ -157,30 +157,38 @@ centroid_scores_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                 //     With fp16 storage everything downstream (mask, cells) is computed from the ROUNDED values,
                 //     so that the table in memory is the one and only definition of S.
                 ST* dst = Sq + (size_t)c0 * PLAID_NQ_MAX;
+                // (2) this thread's best value in the chunk decides whether the rare paths run at all; with fp16 storage
+                //     it is a packed maximum of the rounded pairs (no unpacking on the common path)
+                __half2 h[sizeof(ST) == 2 ? 16 : 1];
+                float mx;
                 if constexpr (sizeof(ST) == 2) {
 #pragma unroll
-                    for (int j = 0; j < 32; j += 2) {
-                        const __half2 h2 = __floats2half2_rn(__uint_as_float(r[j]), __uint_as_float(r[j + 1]));
-                        __stcs(reinterpret_cast<unsigned short*>(dst + j * PLAID_NQ_MAX), __half_as_ushort(__low2half(h2)));
-                        __stcs(reinterpret_cast<unsigned short*>(dst + (j + 1) * PLAID_NQ_MAX), __half_as_ushort(__high2half(h2)));
-                        const float2 f2 = __half22float2(h2);
-                        r[j] = __float_as_uint(f2.x);
-                        r[j + 1] = __float_as_uint(f2.y);
+                    for (int j = 0; j < 16; j++) {
+                        h[j] = __floats2half2_rn(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
+                        __stcs(reinterpret_cast<unsigned short*>(dst + (2 * j) * PLAID_NQ_MAX), __half_as_ushort(__low2half(h[j])));
+                        __stcs(reinterpret_cast<unsigned short*>(dst + (2 * j + 1) * PLAID_NQ_MAX), __half_as_ushort(__high2half(h[j])));
                     }
+                    __half2 m2 = h[0];
+#pragma unroll
+                    for (int j = 1; j < 16; j++) m2 = __hmax2(m2, h[j]);
+                    mx = fmaxf(__low2float(m2), __high2float(m2));
                 } else {
 #pragma unroll
                     for (int j = 0; j < 32; j++) __stcs(dst + j * PLAID_NQ_MAX, __uint_as_float(r[j]));
-                }
-                // (2) this thread's best value in the chunk decides whether the rare paths run at all
-                float mx = __uint_as_float(r[0]);
+                    mx = __uint_as_float(r[0]);
 #pragma unroll
-                for (int j = 1; j < 32; j++) mx = fmaxf(mx, __uint_as_float(r[j]));
+                    for (int j = 1; j < 32; j++) mx = fmaxf(mx, __uint_as_float(r[j]));
+                }
+                auto val = [&](int j) -> float {     // the stored (rounded) value of column j
+                    if constexpr (sizeof(ST) == 2) return (j & 1) ? __high2float(h[j >> 1]) : __low2float(h[j >> 1]);
+                    else return __uint_as_float(r[j]);
+                };
                 // pruning mask: max_k S[c,k] >= thr  <=>  any valid token has S[c,k] >= thr
                 uint32_t word = 0;
                 if (__any_sync(0xffffffffu, tok_valid && mx >= threshold)) {
 #pragma unroll
                     for (int j = 0; j < 32; j++)
-                        word |= (__any_sync(0xffffffffu, tok_valid && __uint_as_float(r[j]) >= threshold) ? 1u : 0u) << j;
+                        word |= (__any_sync(0xffffffffu, tok_valid && val(j) >= threshold) ? 1u : 0u) << j;
                 }
                 if (lane == 0) bits_q[c0 >> 5] = word;
                 // (3) running top-ncells of this query token (score desc, centroid id asc).  A value can only matter if
@@ -191,7 +199,7 @@ centroid_scores_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                 if (tok_valid && mx > cut && mx >= other) {
 #pragma unroll
                     for (int j = 0; j < 32; j++) {
-                        float cv = __uint_as_float(r[j]);
+                        float cv = val(j);
                         if (cv > cut && cv >= other) {
                             int ci = c0 + j;
 #pragma unroll
