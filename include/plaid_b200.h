@@ -49,7 +49,7 @@ const char* plaid_arch(void);
  * qlens[b] = rows kept (0 for the padding queries b >= B; qlens has B_pad entries).  B_pad must be a
  * multiple of 4, Lq_pad a multiple of 32 and >= Lq.  Qh_f16 (optional, may be NULL) receives the same
  * rows rounded to fp16 -- the operand of the search pipeline's MaxSim, which like the reference's GPU
- * branch (`Q.half()`, CB/search/index_storage.py:164-170) runs on fp16 passage embeddings. */
+ * branch (`Q.cuda().half()`, CB/search/candidate_generation.py:52; half D, CB/indexing/codecs/residual.py:273) runs in fp16. */
 int plaid_prepare_queries(const float* Q, int B, int Lq, int remove_zero_rows, int B_pad, int Lq_pad,
                           void* Qb_bf16, void* Qh_f16, int32_t* qlens, void* stream);
 
