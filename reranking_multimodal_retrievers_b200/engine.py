@@ -56,6 +56,47 @@ class StageTaps:
     scores: torch.Tensor
 
 
+class _HostFeed:
+    """Double-buffered H2D of query chunks: chunk i+1 travels while chunk i is searched.  Only the query
+    preparation kernel reads the staging buffer, so it is released right after the chunk is enqueued."""
+
+    def __init__(self, Qh: torch.Tensor, Bc: int, dev, stream):
+        self.Qh, self.Bc, self.dev, self.stream = Qh, Bc, dev, stream
+        B, Lq, dim = Qh.shape
+        self.n_chunks = (B + Bc - 1) // Bc
+        self.bufs = [torch.empty(min(Bc, B), Lq, dim, device=dev, dtype=torch.float32) for _ in range(min(2, self.n_chunks))]
+        self.ready = [torch.cuda.Event() for _ in self.bufs]
+        self.free = [None for _ in self.bufs]
+        self._issue(0)
+
+    def _issue(self, ci: int):
+        if ci >= self.n_chunks:
+            return
+        slot = ci % len(self.bufs)
+        b0, b1 = ci * self.Bc, min(self.Qh.shape[0], (ci + 1) * self.Bc)
+        if self.free[slot] is not None:
+            self.stream.wait_event(self.free[slot])          # the chunk that used this buffer has been prepared
+        else:
+            self.stream.wait_stream(torch.cuda.current_stream(self.dev))   # buffers allocated on the compute stream
+        with torch.cuda.stream(self.stream):
+            self.bufs[slot][: b1 - b0].copy_(self.Qh[b0:b1], non_blocking=True)
+            self.ready[slot].record(self.stream)
+
+    def chunk(self, ci: int) -> torch.Tensor:
+        slot = ci % len(self.bufs)
+        if ci + 1 < self.n_chunks and len(self.bufs) > 1:
+            self._issue(ci + 1)
+        torch.cuda.current_stream(self.dev).wait_event(self.ready[slot])
+        b0, b1 = ci * self.Bc, min(self.Qh.shape[0], (ci + 1) * self.Bc)
+        return self.bufs[slot][: b1 - b0]
+
+    def release(self, ci: int):
+        slot = ci % len(self.bufs)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.dev))
+        self.free[slot] = ev
+
+
 class SearchEngine:
     def __init__(self, index: DeviceIndex, s_budget_bytes: int = 6 << 30, max_chunk: int = 512, fused: bool = True,
                  s_dtype: torch.dtype = torch.float16, ivf_stage1: bool = True):
@@ -73,6 +114,7 @@ class SearchEngine:
         self.s_budget_bytes = int(s_budget_bytes)
         self.max_chunk = int(max_chunk)
         self._ws_key = None
+        self._copy_stream = None
         self._ws = None
         self.last_taps: StageTaps | None = None
         self.launch_count = 0      # kernels of libplaid_b200 launched so far (bench.py reports the delta)
@@ -254,11 +296,14 @@ class SearchEngine:
         if B == 0 or ix.num_passages == 0:
             return out_p, out_s, out_c
         Bc = self.chunk_size(B)
-        Qd = Q if Q.is_cuda else Q.pin_memory().to(dev, non_blocking=True)
-        Qd = Qd.to(torch.float32).contiguous()
-        for b0 in range(0, B, Bc):
+        feed = self._host_feed(Q, Bc) if not Q.is_cuda else None
+        Qd = Q.to(torch.float32).contiguous() if Q.is_cuda else None
+        for ci, b0 in enumerate(range(0, B, Bc)):
             b1 = min(B, b0 + Bc)
-            ws = self._run_chunk(Qd[b0:b1], Lq_pad, ncells, thr, ndocs, kk, remove_zero_rows, Bc)
+            Qc = Qd[b0:b1] if feed is None else feed.chunk(ci)
+            ws = self._run_chunk(Qc, Lq_pad, ncells, thr, ndocs, kk, remove_zero_rows, Bc)
+            if feed is not None:
+                feed.release(ci)
             n = b1 - b0
             out_p[b0:b1, :kk] = ws["out_pids"][:n]
             out_s[b0:b1, :kk] = ws["out_scores"][:n]
@@ -275,6 +320,15 @@ class SearchEngine:
         if global_pids and ix.pid_base:
             out_p = torch.where(out_p >= 0, out_p + ix.pid_base, out_p)
         return out_p, out_s, out_c
+
+    def _host_feed(self, Q: torch.Tensor, Bc: int):
+        """Host query embeddings -> device, one chunk ahead of the compute on a copy stream."""
+        Qh = Q.to(torch.float32).contiguous()
+        if not Qh.is_pinned():
+            Qh = Qh.pin_memory()
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=self.index.device)
+        return _HostFeed(Qh, Bc, self.index.device, self._copy_stream)
 
     def check_flags(self):
         """Host-side check (synchronises): raises if a kernel watchdog fired or candidates overflowed."""
