@@ -10,12 +10,13 @@ from .modeling import (colbert_score, colbert_score_packed, colbert_score_reduce
                        flmr_colbert_score, flmr_colbert_score_reduce)
 from .ops import (decompress_residuals, filter_pids, segmented_lookup, segmented_maxsim)  # noqa: F401
 from .search import IndexScorer, Searcher  # noqa: F401
-from .searching import create_searcher, search_custom_collection  # noqa: F401
+from .searching import (create_searcher, exhaustive_search, ranking_to_batch_results,  # noqa: F401
+                        search_custom_collection)
 from .strided import StridedTensor  # noqa: F401
 
 __all__ = [
     "ColBERTConfig", "Queries", "Ranking", "Run", "RunConfig", "Searcher", "IndexScorer",
     "colbert_score", "colbert_score_packed", "colbert_score_reduce", "flmr_colbert_score",
     "flmr_colbert_score_reduce", "filter_pids", "decompress_residuals", "segmented_maxsim", "segmented_lookup",
-    "create_searcher", "search_custom_collection", "StridedTensor",
+    "create_searcher", "search_custom_collection", "exhaustive_search", "ranking_to_batch_results", "StridedTensor",
 ]

@@ -340,3 +340,26 @@ def test_sharded_search_equals_reference_per_shard_merge(pkg, golden):
         rp, rs = po.select_top(allp, alls, k)
         assert torch.equal(mp[b, :int(mc[b])].cpu(), rp) and torch.equal(ms[b, :int(mc[b])].cpu(), rs)
         assert int(mp[b, 0]) == int(g[f"rank_pids_{b}"][0])                # the planted passage still leads
+
+
+def test_exhaustive_search_matches_padded_scores(pkg):
+    """The executor's index-free branch (FLMR_base_executor.py:918-990): all queries x all items, best K."""
+    g = torch.Generator().manual_seed(11)
+    nQ, n_items, Ld, Lq, K = 5, 37, 50, 64, 10
+    Q = torch.nn.functional.normalize(torch.randn(nQ, Lq, 128, generator=g), dim=-1)
+    D = torch.nn.functional.normalize(torch.randn(n_items, Ld, 128, generator=g), dim=-1)
+    lens = torch.randint(5, Ld + 1, (n_items,), generator=g)
+    mask = (torch.arange(Ld).unsqueeze(0) < lens.unsqueeze(1)).unsqueeze(-1)
+    out = pkg.exhaustive_search(Q, D, mask, K, truncate_scores=False)
+    assert sorted(out.keys()) == list(range(nQ))
+    for qi in range(nQ):
+        ref = po.colbert_score(Q[qi:qi + 1].bfloat16().float().expand(n_items, -1, -1), D.bfloat16().float(), mask.squeeze(-1))
+        rp, rs = po.select_top(torch.arange(n_items, dtype=torch.int32), ref, K)
+        got = out[qi]
+        assert [r for _, r, _ in got] == list(range(K))
+        gs = torch.tensor([s for _, _, s in got])
+        torch.testing.assert_close(gs, rs, rtol=2e-5, atol=2e-4)
+        # same items unless two reference scores are closer than the summation-order noise
+        assert [i for i, _, _ in got] == rp.tolist() or (rs[:-1] - rs[1:]).min() < 1e-4
+    trunc = pkg.exhaustive_search(Q[:1], D, mask, 3)
+    assert all(isinstance(s, int) for _, _, s in trunc[0])          # the reference stores int(score) here

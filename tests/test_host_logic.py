@@ -154,3 +154,19 @@ def test_two_rank_exchange_gloo(tmp_path):
         assert torch.equal(pa, pb) and torch.equal(sa, sb)
     assert a[3][2][0].numel() == 0                       # the query nobody found anything for
     assert a[3][0][0].numel() == 6 and int(a[3][0][0].max()) >= 500   # pids from both shards' ranges compete
+
+
+def test_ranking_to_batch_results_pads_like_the_reference():
+    """FLMR_base_executor.py:992-1033: records per question, last entry repeated up to max_K."""
+    from reranking_multimodal_retrievers_b200.searching import ranking_to_batch_results
+    ranking = {0: [(5, 1, 9.5), (2, 2, 7.25)], 1: [(1, 1, 3.0), (0, 2, 2.0), (4, 3, 1.0)]}
+    idx2id = {i: f"doc{i}" for i in range(6)}
+    contents = {i: f"text {i}" for i in range(6)}
+    res = ranking_to_batch_results(ranking, ["qa", "qb"], idx2id, contents, 3, pos_item_ids=[["doc5"], ["doc1"]],
+                                   neg_item_ids=[[], ["doc3"]])
+    assert [r["question_id"] for r in res] == ["qa", "qb"]
+    top = res[0]["top_ranking_passages"]
+    assert [t["passage_index"] for t in top] == [5, 2, 2] and [t["score"] for t in top] == [9.5, 7.25, 7.25]
+    assert top[0] == {"passage_index": 5, "passage_id": "doc5", "content": "text 5", "score": 9.5}
+    assert [t["passage_id"] for t in res[1]["top_ranking_passages"]] == ["doc1", "doc0", "doc4"]
+    assert res[1]["pos_item_ids"] == ["doc1"] and res[1]["neg_item_ids"] == ["doc3"]
