@@ -38,6 +38,7 @@ struct MsParams {
     const int32_t* qlens;        // [nQ] valid rows per query
     int Lq_pad, MT, NT, NS;
     int na_shift;                // log2 of the accumulator buffers in TMEM (4 when 4 x MT x NT <= 512 columns, else 2)
+    int tmem_cols;               // TMEM columns this CTA allocates (256 when two CTAs share an SM, else 512)
     int ab_f16;                  // operands (Q and D) are fp16 instead of bf16
     int padded;                  // 0 = packed search form, 1 = padded colbert_score form
     int aligned;                 // packed only: passages start on 32-token boundaries of D, pad rows are zero
@@ -511,7 +512,7 @@ __device__ __forceinline__ void ms_epilogue_a1(const MsParams& p, MsShared* sh, 
 
 
 template <int MODE>
-__global__ void __launch_bounds__(kMsThreads, 1)
+__global__ void __launch_bounds__(kMsThreads, 2)    // <= 128 registers: two CTAs fit an SM (see ms_launch)
 maxsim_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_d, const MsParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -540,7 +541,7 @@ maxsim_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
         fence_mbar_init();
     }
     if (warp == 7) {
-        tmem_alloc(&sh->tmem_base, 512);
+        tmem_alloc(&sh->tmem_base, p.tmem_cols);
         tmem_relinquish();
     }
     tc_fence_before();
@@ -593,7 +594,7 @@ maxsim_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 7) tmem_dealloc(tmem_base, 512);
+    if (warp == 7) tmem_dealloc(tmem_base, p.tmem_cols);
 }
 
 // =============================================================================================
@@ -895,6 +896,7 @@ static int ms_configure(MsParams& p, int Lq_pad) {
     PLAID_CHECK_ARG(p.MT >= 1 && p.MT <= kMsMaxMT, PLAID_ERR_UNSUPPORTED, "maxsim: Lq_pad=%d > 512 query tokens", Lq_pad);
     p.NT = (p.MT <= 2) ? 128 : 64;   // 2 accumulator buffers x MT x NT <= 512 TMEM columns
     p.na_shift = (4 * p.MT * p.NT <= 512) ? 2 : 1;
+    p.tmem_cols = 512;
     const int a_bytes = p.MT * 128 * kDim * 2, b_bytes = p.NT * kDim * 2;
     int ns = (200 * 1024 - a_bytes) / b_bytes;
     p.NS = ns > kMsMaxStages ? kMsMaxStages : ns;
@@ -907,16 +909,26 @@ static int ms_launch(const void* Qb, int q_rows, const void* D, uint64_t d_rows,
     int rc;
     if ((rc = make_bf16_2d_map(&map_q, Qb, (uint64_t)q_rows, kDim, 128)) != PLAID_OK) return rc;
     if ((rc = make_bf16_2d_map(&map_d, D, d_rows, kDim, p.NT)) != PLAID_OK) return rc;
+    // One m-tile (Lq_pad <= 128): TWO CTAs per SM, each with 2 B stages, 2 accumulators (256 TMEM columns) and its
+    // own TMA / MMA / epilogue warps.  With HBM-resident operands the epilogue warps of one CTA (only Lq_pad/32 of
+    // the four hold query rows) cannot keep up with the stream; two independent pipelines double them.
+    const bool dual = p.MT == 1;
+    if (dual) {
+        p.NS = 2;
+        p.na_shift = 1;
+        p.tmem_cols = 256;
+    }
     const int smem = 1024 + p.MT * 128 * kDim * 2 + p.NS * p.NT * kDim * 2 + (int)sizeof(MsShared) + 64;
     const int mode = p.padded ? 2 : (p.aligned ? 0 : 1);
     static int configured[3] = {0, 0, 0};
+    const void* fn = mode == 0 ? (const void*)maxsim_kernel<0> : mode == 1 ? (const void*)maxsim_kernel<1>
+                                                                           : (const void*)maxsim_kernel<2>;
     if (smem > configured[mode]) {
-        const void* fn = mode == 0 ? (const void*)maxsim_kernel<0> : mode == 1 ? (const void*)maxsim_kernel<1>
-                                                                               : (const void*)maxsim_kernel<2>;
         PLAID_CUDA_OK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        PLAID_CUDA_OK(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         configured[mode] = smem;
     }
-    int grid = sm_count();
+    int grid = sm_count() * (dual ? 2 : 1);
     if (grid > p.num_items) grid = p.num_items;
     p.items_per_cta = (p.num_items + grid - 1) / grid;
     grid = (p.num_items + p.items_per_cta - 1) / p.items_per_cta;
