@@ -201,23 +201,47 @@ __device__ int select_sorted_desc(const uint64_t* __restrict__ keys, int n, int 
                 if ((k & prefix_mask) == prefix) atomicAdd(&s_hist[(int)((k >> shift) & 0xff)], 1);
             }
             __syncthreads();
-            if (tid == 0) {
-                int acc = 0, d = 255;
-                for (; d > 0; d--) {
-                    if (acc + s_hist[d] >= remaining) break;
-                    acc += s_hist[d];
+            if (tid < 32) {
+                // bucket of the `remaining`-th largest key: warp-parallel scan of the 256 bins from the top
+                // (lane l owns bins 8l..8l+7; a serial scan by one thread cost ~2500 cycles per pass)
+                int mine = 0;
+#pragma unroll
+                for (int j = 0; j < 8; j++) mine += s_hist[8 * tid + j];
+                int incl = mine;                              // sum over lanes >= tid
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int v = __shfl_down_sync(0xffffffffu, incl, o);
+                    if (tid + o < 32) incl += v;
                 }
-                s_misc[0] = d;
-                s_misc[1] = remaining - acc;
+                const unsigned reach = __ballot_sync(0xffffffffu, incl >= remaining);   // lanes 0..L
+                const int L = reach ? 31 - __clz(reach) : 0;
+                if (tid == L) {
+                    int acc = incl - mine, d = 8 * L + 7;
+                    for (; d > 0; d--) {
+                        if (acc + s_hist[d] >= remaining) break;
+                        acc += s_hist[d];
+                    }
+                    s_misc[0] = d;
+                    s_misc[1] = remaining - acc;
+                    s_misc[3] = s_hist[d];                    // size of that bucket
+                }
             }
             __syncthreads();
             prefix |= (uint64_t)s_misc[0] << shift;
             prefix_mask |= (uint64_t)0xff << shift;
             remaining = s_misc[1];
+            const int bucket = s_misc[3];
             __syncthreads();
+            if (bucket == remaining) {     // the whole bucket belongs to the selection: no need to split it further
+                remaining = 0;
+                break;
+            }
         }
-        thresh = prefix;              // the keep-th largest key
-        n_greater_needed = remaining; // how many copies of `thresh` itself belong to the selection
+        thresh = prefix;              // the keep-th largest key, or (early exit) the smallest key value of its bucket
+        n_greater_needed = remaining; // how many copies of `thresh` itself belong to the selection (0 after an early exit)
+        if (remaining == 0) {         // every key >= thresh is selected: exactly `keep` of them
+            thresh -= 1;              // (prefix > 0 here: bucket 0 of the first pass taken whole would mean n == keep)
+        }
     }
     for (int i = tid; i < sel_cap; i += blockDim.x) s_sel[i] = 0;
     if (tid == 0) { s_misc[2] = 0; s_misc[3] = 0; }
