@@ -615,10 +615,9 @@ static constexpr int kFusedDecWarps = 16;
 // copies into a second staging buffer (no registers held across the chunk); 4 and 8 bits keep one buffer and
 // carry the next chunk in registers, because their staging areas are 2-4x larger.
 template <int NBITS> constexpr bool kFusedAsyncStage = (NBITS <= 2);
-#ifndef MS_FUSED_UT
-#define MS_FUSED_UT 32
-#endif
-static constexpr int kFusedUnit = MS_FUSED_UT;   // rows of a tile built by one decompressor warp (16 or 32)
+// Rows of a tile built by one decompressor warp (template parameter UT): 32 for 128-row tiles (4 warps per tile,
+// 4 groups, 4 stages); 16 for the 64-row tiles of long queries (Lq_pad > 256: 4 warps per tile again, so that all
+// 16 warps have a group -- with 32-row units only half of them would, there being fewer stages than groups).
 // Two role layouts.  Regular: warps 0-3 epilogue, 4 Q TMA, 5 MMA, 6-21 decompress (704 threads, 80 registers).
 // SLIM (one m-tile and Lq_pad <= 96, i.e. at most three TMEM lane quadrants hold query rows): warps 0-2 epilogue,
 // warp 3 -- whose quadrant is empty -- issues the MMAs and loads the queries, 4-19 decompress: 640 threads, which
@@ -626,7 +625,7 @@ static constexpr int kFusedUnit = MS_FUSED_UT;   // rows of a tile built by one 
 static constexpr int kFusedThreads = (6 + kFusedDecWarps) * 32;
 static constexpr int kFusedThreadsSlim = (4 + kFusedDecWarps) * 32;
 
-template <int NBITS, bool SLIM>
+template <int NBITS, bool SLIM, int kFusedUnit>
 __global__ void __launch_bounds__(SLIM ? kFusedThreadsSlim : kFusedThreads, 1)
 maxsim_fused_kernel(const __grid_constant__ CUtensorMap map_q, const MsParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -945,7 +944,8 @@ static int ms_launch_fused(const void* Qb, int q_rows, int nbits, MsParams& p, c
     if ((rc = make_bf16_2d_map(&map_q, Qb, (uint64_t)q_rows, kDim, 128)) != PLAID_OK) return rc;
     // as many B stages as shared memory allows; the decompressor groups share them in tile order
     const int stage_bufs = nbits <= 2 ? 2 : 1;       // kFusedAsyncStage
-    const int fixed = 1024 + p.MT * 128 * kDim * 2 + kLutBytes + kFusedDecWarps * stage_bufs * kFusedUnit * 16 * nbits +
+    const int unit = p.NT == 64 ? 16 : 32;           // rows per decompressor warp (template parameter UT)
+    const int fixed = 1024 + p.MT * 128 * kDim * 2 + kLutBytes + kFusedDecWarps * stage_bufs * unit * 16 * nbits +
                       (int)sizeof(MsShared) + 64;
     const int per_stage = p.NT * kDim * 2;
     p.NS = (227 * 1024 - fixed) / per_stage;
@@ -953,13 +953,16 @@ static int ms_launch_fused(const void* Qb, int q_rows, int nbits, MsParams& p, c
     PLAID_CHECK_ARG(p.NS >= 2, PLAID_ERR_UNSUPPORTED, "maxsim_fused: shared memory too small for Lq_pad=%d, nbits=%d", p.Lq_pad, nbits);
     const int smem = fixed + p.NS * per_stage;
     const bool slim = p.MT == 1 && p.NT == 128 && p.Lq_pad <= 96;
-#define PLAID_FUSED_FN(NB) (slim ? (const void*)maxsim_fused_kernel<NB, true> : (const void*)maxsim_fused_kernel<NB, false>)
+#define PLAID_FUSED_FN(NB)                                                                              \
+    (slim ? (const void*)maxsim_fused_kernel<NB, true, 32>                                              \
+          : unit == 16 ? (const void*)maxsim_fused_kernel<NB, false, 16> : (const void*)maxsim_fused_kernel<NB, false, 32>)
     const void* fn = nbits == 1 ? PLAID_FUSED_FN(1) : nbits == 2 ? PLAID_FUSED_FN(2) : nbits == 4 ? PLAID_FUSED_FN(4) : PLAID_FUSED_FN(8);
 #undef PLAID_FUSED_FN
-    static int configured[2][9] = {{0}, {0}};
-    if (smem > configured[slim][nbits]) {
+    static int configured[3][9] = {{0}, {0}, {0}};
+    const int variant = slim ? 1 : unit == 16 ? 2 : 0;
+    if (smem > configured[variant][nbits]) {
         PLAID_CUDA_OK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        configured[slim][nbits] = smem;
+        configured[variant][nbits] = smem;
     }
     int grid = sm_count();
     if (grid > p.num_items) grid = p.num_items;
