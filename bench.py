@@ -78,6 +78,18 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
+    def stop_after_min_samples(self, step, min_samples=3, max_seconds=1.0):
+        """A very short timed region can end before nvidia-smi has delivered a few samples: keep the same load
+        running (untimed) until it has, and say so."""
+        extra, t0 = 0, time.time()
+        while self.proc is not None and len(self.lines) < min_samples and time.time() - t0 < max_seconds:
+            step()
+            extra += 1
+        out = self.stop()
+        if extra:
+            out["note"] = f"{extra} extra untimed steps of the same load were run to collect the samples"
+        return out
+
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -183,15 +195,15 @@ def bench_rerank(args, w, peaks, rank, world, local_rank):
         torch.cuda.synchronize()
         return e0.elapsed_time(e1)
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()                                     # before the warm-up (nvidia-smi needs ~100 ms for its first sample)
     for _ in range(args.warmup):
         step(Q)
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     ms = timed(lambda: step(Q), args.steps) / args.steps
     for _ in range(2):
         step_e2e()
     ms_e2e = timed(step_e2e, args.steps) / args.steps
-    clocks = sampler.stop()
+    clocks = sampler.stop_after_min_samples(lambda: step(Q))
     # check a slice against the CPU restatement of the reference's colbert_score (same bf16 operands)
     got = step(Q)[:dpq].cpu()
     ref = po.colbert_score(Q[:1].cpu().bfloat16().float(), D[:dpq].cpu().float(), mask[:dpq].cpu())
@@ -386,7 +398,7 @@ def main():
     for _ in range(2):
         step_e2e()
     ms_e2e, _ = timed(step_e2e, args.steps)
-    clocks = sampler.stop()
+    clocks = sampler.stop_after_min_samples(lambda: step(Qdev))
 
     if rank != 0:
         if world > 1:
