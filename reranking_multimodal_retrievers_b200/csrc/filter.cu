@@ -22,6 +22,10 @@ __device__ __forceinline__ float load_s(const __half* p) { return __half2float(_
 
 static constexpr int kApproxWarps = 8;        // warps per CTA
 static constexpr int kStage1Dpw = 16;         // stage 1: 128 passages per CTA (amortises the bitmap load)
+#ifndef PLAID_S2_ROWS
+#define PLAID_S2_ROWS 16
+#endif
+static constexpr int kS2Rows = PLAID_S2_ROWS;   // stage 2: S rows a warp keeps in flight
 static constexpr int kStage2Dpw = 1;          // stage 2: 8 passages per CTA (few queries resident -> S stays in L2)
 
 // Gather the S rows of the codes selected by `mask` (bit l = lane l's `code`), G rows in flight per step.
@@ -70,8 +74,7 @@ approx_scores_kernel(const int32_t* __restrict__ pids, const int32_t* __restrict
     uint32_t* s_bits = s_dyn + kDocs * 33;                            // [C/32] (stage 1 only)
     const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int n = min(counts[b], pid_stride);
-    const int i0 = blockIdx.x * kDocs;
-    if (i0 >= n) return;  // whole CTA past the end of this query's list
+    if ((int)blockIdx.x * kDocs >= n) return;  // whole CTA past the end of this query's list
     const ST* Sb = S + (size_t)b * C * PLAID_NQ_MAX + lane;
     if (USE_IDX) {
         const uint4* src = reinterpret_cast<const uint4*>(idx_bits + (size_t)b * (C >> 5));
@@ -79,6 +82,10 @@ approx_scores_kernel(const int32_t* __restrict__ pids, const int32_t* __restrict
         if (threadIdx.x == 0) s_bits[C >> 5] = 0u;   // word of the sentinel code C: "not a survivor"
         __syncthreads();
     }
+    // A CTA takes the passage groups blockIdx.x, blockIdx.x + gridDim.x, ... of its query (the regular launches have
+    // one group per CTA; the flagged-only fallback launch of the hybrid stage 1 uses a thin grid, because 100 k CTAs
+    // that all exit at once still cost 56 us of block scheduling).
+  for (int i0 = blockIdx.x * kDocs; i0 < n; i0 += gridDim.x * kDocs) {
     // Passage descriptors of this warp's DPW passages, fetched in one parallel step (lane l <- passage l)
     // so that the scan below has no pid -> offsets -> codes pointer chase per passage.
     int64_t my_off = 0;
@@ -143,17 +150,17 @@ approx_scores_kernel(const int32_t* __restrict__ pids, const int32_t* __restrict
             for (int t0 = 0; t0 < len; t0 += 32) {
                 const int t = t0 + lane;
                 const int code = (t < len) ? ld_stream_s32(cp + t) : 0;
-                if (t0 + 32 <= len) {                           // full chunk: straight-line gather, 8 rows in flight
+                if (t0 + 32 <= len) {                           // full chunk: straight-line gather, kS2Rows rows in flight
 #pragma unroll
-                    for (int g = 0; g < 32; g += 8) {
-                        float v[8];
+                    for (int g = 0; g < 32; g += kS2Rows) {
+                        float v[kS2Rows];
 #pragma unroll
-                        for (int u = 0; u < 8; u++) {
+                        for (int u = 0; u < kS2Rows; u++) {
                             const unsigned c = (unsigned)__shfl_sync(0xffffffffu, code, g + u);
                             v[u] = load_s(Sb + (size_t)c * PLAID_NQ_MAX);
                         }
 #pragma unroll
-                        for (int u = 0; u < 8; u++) m = fmaxf(m, v[u]);
+                        for (int u = 0; u < kS2Rows; u++) m = fmaxf(m, v[u]);
                     }
                 } else {
                     m = gather_rows<8>(__ballot_sync(0xffffffffu, t < len), code, Sb, m);
@@ -172,6 +179,8 @@ approx_scores_kernel(const int32_t* __restrict__ pids, const int32_t* __restrict
             out[(size_t)b * pid_stride + i] = s;
         }
     }
+    __syncthreads();     // s_max is reused by the next group
+  }
 }
 
 // ------------------------------------------------------------------------------------------ select
@@ -367,6 +376,7 @@ static int launch_approx_t(const int32_t* pids, const int32_t* counts, int B, in
             configured = smem;
         }
         dim3 grid((pid_stride + kDocs - 1) / kDocs, B);
+        if (only_flagged && grid.x > 8) grid.x = 8;     // rarely-taken fallback: few CTAs per query, each walks its groups
         approx_scores_kernel<true, kStage1Dpw, ST><<<grid, kApproxWarps * 32, smem, st>>>(
             pids, counts, pid_stride, S, qlens, idx_bits, C, codes, offsets, out, only_flagged, flag_stride);
     } else {
