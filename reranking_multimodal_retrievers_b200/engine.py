@@ -126,6 +126,15 @@ class SearchEngine:
     def chunk_size(self, B: int) -> int:
         per_query = self.index.num_centroids * NQ_MAX * (2 if self.s_dtype == torch.float16 else 4)
         bc = max(4, min(self.max_chunk, self.s_budget_bytes // per_query))
+        if per_query >= (16 << 20) and B > bc:
+            # Large codebooks (C >= 2^18): centroid scoring dominates the step and its throughput is queries x centroid
+            # ranges per wave, so take the chunk that fills the 148 SMs exactly (4 * floor(148 / ranges) queries).
+            best, best_rate = bc, bc * max(1, 148 // max(bc // 4, 1))
+            for cs in range(1, 9):
+                cand = 4 * (148 // cs)
+                if cand <= bc and cand * cs > best_rate:
+                    best, best_rate = cand, cand * cs
+            bc = best
         bc = min(bc, ((B + 3) // 4) * 4)
         return max(4, (bc // 4) * 4)
 
