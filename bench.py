@@ -41,6 +41,8 @@ WORKLOADS = {
                       "embeddings [409600, 240, 128] (lengths U{120..239}), Lq=64"),
     "cfg5small": dict(B=512, dpq=100, Ld=240, lo=120, hi=239, Lq=64, rerank=True,
                       desc="cfg5 shape at 512 queries (profiling size)"),
+    "codec": dict(n=4_000_000, C=65_536, nbits=2, codec=True,
+                  desc="index build (next row 8f-3): ResidualCodec.compress of 4M token embeddings against 65536 centroids, nbits=2"),
     "cfg3": dict(N=100_000, lo=128, hi=512, nbits=4, B=256, Lq=320, k=100,
                  desc="E-VQA/InfoSeek-shaped 100k-passage index, nbits=4, 256 PreFLMR 320-token queries, k=100"),
 }
@@ -153,6 +155,74 @@ def run_cpu_sample(cs, Q, k, budget_s, max_queries, warm=True):
     dt = time.perf_counter() - t0
     return dict(queries=n, seconds=dt, tokens=toks, kind=cs.kind, cores=cs.cores,
                 stage_share={s: round(v / max(dt, 1e-9), 3) for s, v in cs.stage_s.items()})
+
+
+def bench_codec(args, w, peaks, rank, world, local_rank):
+    """Index-build codec: argmax over the centroids on tcgen05 (no score table) + residual/bucketize/pack kernel."""
+    import torch
+    from reranking_multimodal_retrievers_b200 import codec
+    from oracle import plaid_oracle as po
+    dev = torch.device("cuda", local_rank)
+    n, C, nbits = w["n"], w["C"], w["nbits"]
+    g = torch.Generator(device=dev)
+    g.manual_seed(777 + rank)
+    cent = torch.nn.functional.normalize(torch.randn(C, 128, generator=g, device=dev), dim=-1).half()
+    assign = torch.randint(0, C, (n,), generator=g, device=dev)
+    embs = torch.empty(n, 128, device=dev)
+    for i in range(0, n, 1 << 20):
+        a = assign[i:i + (1 << 20)]
+        embs[i:i + a.numel()] = torch.nn.functional.normalize(
+            cent[a].float() + 0.05 * torch.randn(a.numel(), 128, generator=g, device=dev), dim=-1)
+    cut = torch.tensor([-0.0304, 0.0, 0.0302], device=dev) if nbits == 2 else torch.linspace(-0.06, 0.06, (1 << nbits) - 1, device=dev)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+
+    def timed(fn, steps):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            out = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / steps, out
+
+    for _ in range(args.warmup):
+        codes = codec.compress_into_codes(embs, cent)
+        codec.compress_residuals(embs, codes, cent, cut, nbits)
+    ms_codes, codes = timed(lambda: codec.compress_into_codes(embs, cent), args.steps)
+    ms_res, res = timed(lambda: codec.compress_residuals(embs, codes, cent, cut, nbits), args.steps)
+    clocks = sampler.stop_after_min_samples(lambda: codec.compress_residuals(embs, codes, cent, cut, nbits))
+    assert float((codes == assign.to(torch.int32)).float().mean()) > 0.999
+    m = 4096                                              # parity on a slice: bit-exact vs the oracle given the codes
+    _, want = po.codec_compress(cent[:].cpu(), cut.cpu(), nbits, embs[:m].cpu(), codes=codes[:m].cpu())
+    assert torch.equal(res[:m].cpu(), want), "compress_residuals differs from the oracle"
+    torch.set_num_threads(os.cpu_count() or 1)
+    mc = 20000
+    t0 = time.perf_counter()
+    po.codec_compress(cent.cpu(), cut.cpu(), nbits, embs[:mc].cpu())
+    dt = time.perf_counter() - t0
+    ms = ms_codes + ms_res
+    flops = 2.0 * C * 128 * n
+    res_bytes = (512.0 + 4 + 16 * nbits) * n
+    return {
+        "metric": "compressed_tokens_per_s", "value": world * n / (ms * 1e-3), "unit": "tokens/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16 argmax (fp32 accumulate), fp32 residual", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {w['desc']}", "tokens_per_step": n, "centroids": C},
+        "e2e": {"value": world * n / (ms * 1e-3), "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                "note": "index build works on device-resident encoder output"},
+        "gpu_launches": None, "clocks": clocks,
+        "kernels": {"compress_into_codes": {"ms_per_step": round(ms_codes, 3), "achieved_TFLOPs": round(flops / (ms_codes * 1e-3) / 1e12, 1),
+                                            "frac_tensor": round(flops / (ms_codes * 1e-3) / 1e12 / peaks["tf_sustained"], 4)},
+                    "compress_residuals": {"ms_per_step": round(ms_res, 3), "achieved_GBps": round(res_bytes / (ms_res * 1e-3) / 1e9, 1),
+                                           "frac_hbm": round(res_bytes / (ms_res * 1e-3) / 1e9 / peaks["hbm"], 4)}},
+        "roofline": {"kernel": "centroid_scores_kernel (argmax only)", "bound": "tensor", "achieved": round(flops / (ms_codes * 1e-3) / 1e12, 1),
+                     "peak": peaks["tf_sustained"], "unit": "TFLOP/s", "peak_source": peaks["source"],
+                     "frac": round(flops / (ms_codes * 1e-3) / 1e12 / peaks["tf_sustained"], 4), "traffic": None},
+        "cpu_baseline": {"value": mc / dt, "unit": "tokens/s", "cores": os.cpu_count(), "kind": "port",
+                         "sample": f"{mc} tokens, torch CPU ops as residual.py:169-222 (fp32 matmul + argmax, bucketize, packbits)"},
+    }
 
 
 def bench_rerank(args, w, peaks, rank, world, local_rank):
@@ -301,8 +371,8 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     import torch.distributed as dist
-    if w.get("rerank"):
-        line = bench_rerank(args, w, peaks, rank, world, local_rank)
+    if w.get("rerank") or w.get("codec"):
+        line = (bench_codec if w.get("codec") else bench_rerank)(args, w, peaks, rank, world, local_rank)
         sys.stdout.flush()
         os.dup2(real_stdout, 1)
         if rank == 0:

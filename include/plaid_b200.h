@@ -180,6 +180,22 @@ int plaid_decompress_normalize_f16(const int32_t* pids, const int32_t* counts, i
                                    const float* W, const uint8_t* residuals, const int32_t* codes,
                                    const void* centroids_f16, int C, int nbits, void* D_f16, void* stream);
 
+/* ---- f3 (next row): index-build side of the codec (CB/indexing/codecs/residual.py:169-222) -------------------
+ * plaid_merge_cells: the partial top-ncells lists of plaid_centroid_scores -> cells[b, k, 0..ncells) (the first step
+ * of plaid_candidates on its own).  With ncells = 1 and S = idx_bits = NULL in plaid_centroid_scores this is
+ * ResidualCodec.compress_into_codes (`(centroids @ batch.T).max(dim=0).indices`, residual.py:204-222): 32 embeddings
+ * play the role of one query's tokens; ties go to the lowest centroid id, as torch's max does. */
+int plaid_merge_cells(const float* cell_val, const int32_t* cell_idx, const int32_t* qlens, int B, int ncells,
+                      int nlists, int32_t* cells, void* stream);
+
+/* ResidualCodec.compress minus the argmax (residual.py:176-203): residual = embs[t] - centroids[codes[t]] in fp32,
+ * bucket = number of cutoffs strictly below it (torch.bucketize), nbits bits per dimension LSB first, packed MSB
+ * first into residuals u8 [n, 16*nbits] -- the byte layout the search path decodes.  *bad_code_flag is set to 1 if
+ * a code is outside [0, C). */
+int plaid_compress_residuals(const float* embs, const int32_t* codes, const void* centroids_f16,
+                             const float* bucket_cutoffs, int64_t n, int C, int nbits, uint8_t* residuals,
+                             int* bad_code_flag, void* stream);
+
 /* ---- a8: colbert_score_packed + segmented_maxsim (CB/modeling/colbert.py:289-311,
  *          CB/modeling/segmented_maxsim.cpp:22-93) ---------------------------------------------
  * scores[b, i] = sum_{k < qlens[b]} max(0, max_{t in passage i} <D[b, t], Qb[b, k]>): a tcgen05

@@ -279,3 +279,30 @@ def search_all(index: OracleIndex, Q: torch.Tensor, k: int, remove_zero_tensors:
         r = rank(index, q, ncells, thr, ndocs)
         res.append((r["pids"][:k], r["scores"][:k]))
     return res
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Index-build codec: numpy/torch restatement of ResidualCodec.compress (CPU branch),
+# CB/indexing/codecs/residual.py:169-222.  Pinned by tests/golden/codec_nbits{2,4}.npz (recorded from the reference).
+def codec_compress_into_codes(centroids: torch.Tensor, embs: torch.Tensor) -> torch.Tensor:
+    """`(centroids @ batch.T).max(dim=0).indices` in fp32 (residual.py:204-222): first maximum = lowest id."""
+    return (centroids.float() @ embs.float().T).max(dim=0).indices.to(torch.int32)
+
+
+def codec_binarize(residuals: torch.Tensor, bucket_cutoffs: torch.Tensor, nbits: int) -> torch.Tensor:
+    """residual.py:188-203: bucketize, nbits bits per dimension LSB first, packed MSB first."""
+    import numpy as np
+    b = torch.bucketize(residuals.float(), bucket_cutoffs.float()).to(torch.uint8)           # [n, dim]
+    bits = (b.unsqueeze(-1) >> torch.arange(nbits, dtype=torch.uint8)) & 1                    # [n, dim, nbits]
+    packed = np.packbits(np.asarray(bits.contiguous().flatten()))
+    return torch.as_tensor(packed, dtype=torch.uint8).reshape(residuals.size(0), residuals.size(1) // 8 * nbits)
+
+
+def codec_compress(centroids_f16: torch.Tensor, bucket_cutoffs: torch.Tensor, nbits: int, embs: torch.Tensor,
+                   codes: torch.Tensor = None):
+    """(codes, residual bytes) of residual.py:169-186; `codes` may be injected."""
+    cent = centroids_f16.float()
+    if codes is None:
+        codes = codec_compress_into_codes(cent, embs)
+    res = embs.float() - cent[codes.long()]
+    return codes, codec_binarize(res, bucket_cutoffs, nbits)

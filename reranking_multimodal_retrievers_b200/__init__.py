@@ -5,6 +5,7 @@ the filter_pids / decompress_residuals / segmented_maxsim / segmented_lookup ope
 FLMR glue create_searcher / search_custom_collection.  All arithmetic runs in libplaid_b200.so
 (hand-written CUDA, C ABI in include/plaid_b200.h); there is no CPU fallback.
 """
+from . import codec  # noqa: F401
 from .infra import ColBERTConfig, Queries, Ranking, Run, RunConfig  # noqa: F401
 from .modeling import (colbert_score, colbert_score_packed, colbert_score_reduce,  # noqa: F401
                        flmr_colbert_score, flmr_colbert_score_reduce)
@@ -18,5 +19,5 @@ __all__ = [
     "ColBERTConfig", "Queries", "Ranking", "Run", "RunConfig", "Searcher", "IndexScorer",
     "colbert_score", "colbert_score_packed", "colbert_score_reduce", "flmr_colbert_score",
     "flmr_colbert_score_reduce", "filter_pids", "decompress_residuals", "segmented_maxsim", "segmented_lookup",
-    "create_searcher", "search_custom_collection", "exhaustive_search", "ranking_to_batch_results", "StridedTensor",
+    "create_searcher", "search_custom_collection", "exhaustive_search", "ranking_to_batch_results", "StridedTensor", "codec",
 ]

@@ -22,6 +22,8 @@ _SIGNATURES = {
     "plaid_abi_version": [],
     "plaid_last_error": [],
     "plaid_arch": [],
+    "plaid_merge_cells": [_P, _P, _P, _I, _I, _I, _P, _P],
+    "plaid_compress_residuals": [_P, _P, _P, _P, ctypes.c_int64, _I, _I, _P, _P, _P],
     "plaid_prepare_queries": [_P, _I, _I, _I, _I, _I, _P, _P, _P, _P],
     "plaid_f32_to_bf16": [_P, _P, _I64, _P],
     "plaid_centroid_scores": [_P, _I, _P, _P, _I, _I, _F, _I, _I, _P, _I, _P, _P, _P, _P, _P],

@@ -152,3 +152,16 @@ extern "C" int plaid_candidates(const float* cell_val, const int32_t* cell_idx, 
     PLAID_LAUNCH_OK("compact_candidates_kernel");
     return PLAID_OK;
 }
+
+extern "C" int plaid_merge_cells(const float* cell_val, const int32_t* cell_idx, const int32_t* qlens, int B, int ncells,
+                                 int nlists, int32_t* cells, void* stream) {
+    using namespace plaid;
+    PLAID_CHECK_ARG(cell_val && cell_idx && qlens && cells, PLAID_ERR_ARG, "plaid_merge_cells: null pointer");
+    PLAID_CHECK_ARG(B >= 0 && ncells >= 1 && ncells <= PLAID_NCELLS_MAX && nlists >= 1, PLAID_ERR_ARG,
+                    "plaid_merge_cells: bad sizes (B=%d ncells=%d nlists=%d)", B, ncells, nlists);
+    if (B == 0) return PLAID_OK;
+    const int nt = B * PLAID_NQ_MAX;
+    merge_cells_kernel<<<(nt + 127) / 128, 128, 0, (cudaStream_t)stream>>>(cell_val, cell_idx, qlens, B, ncells, nlists, cells);
+    PLAID_LAUNCH_OK("merge_cells_kernel");
+    return PLAID_OK;
+}

@@ -157,6 +157,7 @@ centroid_scores_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                 //     With fp16 storage everything downstream (mask, cells) is computed from the ROUNDED values,
                 //     so that the table in memory is the one and only definition of S.
                 ST* dst = Sq + (size_t)c0 * PLAID_NQ_MAX;
+                const bool store = S != nullptr;     // S == NULL: only the top-ncells lists are wanted (index build: argmax)
                 // (2) this thread's best value in the chunk decides whether the rare paths run at all; with fp16 storage
                 //     it is a packed maximum of the rounded pairs (no unpacking on the common path)
                 __half2 h[sizeof(ST) == 2 ? 16 : 1];
@@ -165,8 +166,10 @@ centroid_scores_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
 #pragma unroll
                     for (int j = 0; j < 16; j++) {
                         h[j] = __floats2half2_rn(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
-                        __stcs(reinterpret_cast<unsigned short*>(dst + (2 * j) * PLAID_NQ_MAX), __half_as_ushort(__low2half(h[j])));
-                        __stcs(reinterpret_cast<unsigned short*>(dst + (2 * j + 1) * PLAID_NQ_MAX), __half_as_ushort(__high2half(h[j])));
+                        if (store) {
+                            __stcs(reinterpret_cast<unsigned short*>(dst + (2 * j) * PLAID_NQ_MAX), __half_as_ushort(__low2half(h[j])));
+                            __stcs(reinterpret_cast<unsigned short*>(dst + (2 * j + 1) * PLAID_NQ_MAX), __half_as_ushort(__high2half(h[j])));
+                        }
                     }
                     __half2 m2 = h[0];
 #pragma unroll
@@ -174,7 +177,8 @@ centroid_scores_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                     mx = fmaxf(__low2float(m2), __high2float(m2));
                 } else {
 #pragma unroll
-                    for (int j = 0; j < 32; j++) __stcs(dst + j * PLAID_NQ_MAX, __uint_as_float(r[j]));
+                    for (int j = 0; j < 32; j++)
+                        if (store) __stcs(dst + j * PLAID_NQ_MAX, __uint_as_float(r[j]));
                     mx = __uint_as_float(r[0]);
 #pragma unroll
                     for (int j = 1; j < 32; j++) mx = fmaxf(mx, __uint_as_float(r[j]));
@@ -190,7 +194,7 @@ centroid_scores_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                     for (int j = 0; j < 32; j++)
                         word |= (__any_sync(0xffffffffu, tok_valid && val(j) >= threshold) ? 1u : 0u) << j;
                 }
-                if (lane == 0) bits_q[c0 >> 5] = word;
+                if (lane == 0 && idx_bits != nullptr) bits_q[c0 >> 5] = word;
                 // (3) running top-ncells of this query token (score desc, centroid id asc).  A value can only matter if
                 //     it beats this list's own ncells-th best AND is not below the ncells-th best the sibling warp (other
                 //     128-column half, same query token) has already seen -- that bound is shared through smem (racy
@@ -244,8 +248,8 @@ extern "C" int plaid_centroid_scores(const void* centroids_bf16, int C, const vo
                                      uint32_t* idx_bits, float* cell_val, int32_t* cell_idx, int* watchdog,
                                      void* stream) {
     using namespace plaid;
-    PLAID_CHECK_ARG(centroids_bf16 && Qb_bf16 && qlens && S && idx_bits && cell_val && cell_idx, PLAID_ERR_ARG,
-                    "plaid_centroid_scores: null pointer");
+    PLAID_CHECK_ARG(centroids_bf16 && Qb_bf16 && qlens && cell_val && cell_idx, PLAID_ERR_ARG,
+                    "plaid_centroid_scores: null pointer");      // S and idx_bits may be NULL (lists only)
     PLAID_CHECK_ARG(C >= 32 && (C % 32) == 0, PLAID_ERR_UNSUPPORTED, "plaid_centroid_scores: C=%d must be a multiple of 32", C);
     PLAID_CHECK_ARG(B_pad >= 0 && (B_pad % 4) == 0 && Lq_pad >= 32 && (Lq_pad % 32) == 0, PLAID_ERR_ARG,
                     "plaid_centroid_scores: B_pad=%d must be a multiple of 4, Lq_pad=%d a multiple of 32", B_pad, Lq_pad);

@@ -202,3 +202,75 @@ def test_strided_tensor_lookup_and_padding(P, golden):
     full, fmask = res.as_padded_tensor()
     assert full.shape == (ix.doclens.numel(), int(ix.doclens.max()), ix.residuals.shape[1]) and fmask.dim() == 3
     assert torch.equal(full[5, :int(ix.doclens[5])].cpu(), ix.residuals[ix.offsets[5]:ix.offsets[6]])
+
+
+@pytest.mark.parametrize("name", ["codec_nbits2", "codec_nbits4"])
+def test_codec_compress_bit_exact_vs_reference_golden(P, name):
+    """Index-build codec kernels (8f-3) against vectors recorded from the reference's ResidualCodec.compress."""
+    import os
+    import numpy as np
+    from reranking_multimodal_retrievers_b200 import codec
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", f"{name}.npz"))
+    nbits = int(g["nbits"])
+    embs = torch.from_numpy(g["embs"]).cuda()
+    cent = torch.from_numpy(g["centroids_f16"]).cuda()
+    cut = torch.from_numpy(g["bucket_cutoffs"]).cuda()
+    ref_codes = torch.from_numpy(g["codes"])
+    ref_res = torch.from_numpy(g["residuals"])
+    # residual / bucketize / pack given the reference's codes: bit-exact
+    res = codec.compress_residuals(embs, ref_codes.cuda(), cent, cut, nbits)
+    assert torch.equal(res.cpu(), ref_res)
+    # argmax on the tensor cores: these embeddings sit next to their centroid, the codes are unambiguous
+    codes, res2 = codec.compress(embs, cent, cut, nbits)
+    assert torch.equal(codes.cpu(), ref_codes) and torch.equal(res2.cpu(), ref_res)
+
+
+@pytest.mark.parametrize("nbits,n,C", [(1, 77, 64), (2, 1000, 1024), (8, 130, 32)])
+def test_codec_all_bit_widths_and_argmax_vs_oracle(P, nbits, n, C):
+    from reranking_multimodal_retrievers_b200 import codec
+    g = torch.Generator().manual_seed(100 + nbits)
+    cent = torch.nn.functional.normalize(torch.randn(C, 128, generator=g), dim=-1).half()
+    embs = torch.nn.functional.normalize(torch.randn(n, 128, generator=g), dim=-1)       # far from any centroid: near-ties
+    res_all = embs - cent.float()[torch.randint(0, C, (n,), generator=g)]
+    if nbits < 8:
+        cut = res_all.flatten().quantile(torch.linspace(0, 1, 2 ** nbits + 1)[1:-1])
+    else:
+        cut = torch.linspace(-0.3, 0.3, 255)
+    codes = codec.compress_into_codes(embs.cuda(), cent.cuda()).cpu()
+    # oracle on the same bf16-rounded operands; a different pick is only allowed where the two best are a near-tie
+    S = cent.float().bfloat16().float() @ embs.bfloat16().float().T
+    ref = S.max(dim=0).indices.to(torch.int32)
+    diff = codes != ref
+    if diff.any():
+        top2 = S.topk(2, dim=0).values
+        assert ((top2[0] - top2[1])[diff] < 1e-5).all()
+        assert (S.gather(0, codes.long().unsqueeze(0))[0][diff] >= top2[1][diff] - 1e-6).all()
+    _, want = po.codec_compress(cent, cut, nbits, embs, codes=codes)
+    got = codec.compress_residuals(embs.cuda(), codes.cuda(), cent.cuda(), cut.cuda(), nbits)
+    assert torch.equal(got.cpu(), want)
+
+
+def test_codec_build_index_is_searchable(P):
+    """Embeddings -> codes/residuals/IVF on the device -> the planted passage is found."""
+    from reranking_multimodal_retrievers_b200 import codec
+    from reranking_multimodal_retrievers_b200.engine import SearchEngine
+    from reranking_multimodal_retrievers_b200.index import DeviceIndex
+    g = torch.Generator().manual_seed(5)
+    C, N, nbits = 256, 300, 2
+    cent = torch.nn.functional.normalize(torch.randn(C, 128, generator=g), dim=-1).half()
+    doclens = torch.randint(8, 40, (N,), generator=g)
+    assign = torch.randint(0, C, (int(doclens.sum()),), generator=g)
+    embs = torch.nn.functional.normalize(cent.float()[assign] + 0.05 * torch.randn(assign.numel(), 128, generator=g), dim=-1)
+    res = embs - cent.float()[assign]
+    cut = res.flatten().quantile(torch.tensor([0.25, 0.5, 0.75]))
+    w = res.flatten().quantile(torch.tensor([0.125, 0.375, 0.625, 0.875]))
+    hx = codec.build_index(embs.cuda(), doclens, cent.cuda(), cut.cuda(), w.cuda(), nbits)
+    assert torch.equal(hx.codes.cpu(), assign.to(torch.int32))
+    eng = SearchEngine(DeviceIndex(hx))
+    off = torch.cat([torch.zeros(1, dtype=torch.int64), doclens.cumsum(0)])
+    gold = torch.tensor([7, 123, 299])
+    Q = torch.stack([torch.nn.functional.normalize(
+        embs[off[p]: off[p] + 8].repeat(4, 1) + 0.02 * torch.randn(32, 128, generator=g), dim=-1) for p in gold.tolist()])
+    pids, scores, counts = eng.search_batch(Q, k=5, ndocs=64)
+    eng.check_flags()
+    assert pids[:, 0].cpu().tolist() == gold.tolist()

@@ -1,6 +1,7 @@
 """The CPU oracle (oracle/) pinned against golden vectors recorded from the UNMODIFIED reference
 Searcher (tests/golden/make_golden.py ran /root/reference in the authoring container)."""
 import numpy as np
+import pytest
 import torch
 
 from plaid_test_helpers import golden_oracle_index, nonzero_rows
@@ -52,3 +53,16 @@ def test_filter_handles_fewer_candidates_than_ndocs(golden):
     assert p1.numel() == 50 and p2.numel() == 32
     assert set(p2.tolist()) <= set(cand.tolist())
     assert torch.all(s2[:-1] >= s2[1:])
+
+
+@pytest.mark.parametrize("name", ["codec_nbits2", "codec_nbits4"])
+def test_codec_oracle_matches_reference_compress(name):
+    """Index-build codec (8f-3): the restatement reproduces ResidualCodec.compress bit for bit."""
+    import os
+    import numpy as np
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", f"{name}.npz"))
+    embs = torch.from_numpy(g["embs"])
+    cent = torch.from_numpy(g["centroids_f16"])
+    codes, res = po.codec_compress(cent, torch.from_numpy(g["bucket_cutoffs"]), int(g["nbits"]), embs)
+    assert torch.equal(codes, torch.from_numpy(g["codes"]))
+    assert torch.equal(res, torch.from_numpy(g["residuals"]))
