@@ -20,6 +20,9 @@
 #include "common.cuh"
 #include "decompress.cuh"
 
+#ifndef MS_FUSED_ATMEM
+#define MS_FUSED_ATMEM 1    // slim fused kernel: the query (A operand) lives in tensor memory, not in shared memory
+#endif
 #ifndef MS_FUSED_CB
 #define MS_FUSED_CB 2      // fused kernel: steps (of 4 tokens) per centroid batch; two batches are in flight
 #endif
@@ -39,6 +42,8 @@ struct MsParams {
     int Lq_pad, MT, NT, NS;
     int na_shift;                // log2 of the accumulator buffers in TMEM (4 when 4 x MT x NT <= 512 columns, else 2)
     int tmem_cols;               // TMEM columns this CTA allocates (256 when two CTAs share an SM, else 512)
+    int a_tmem_col;              // > 0: the A operand sits in TMEM from this column on (64 columns); rows written by the epilogue warps
+    const void* q_rows;          // fp16 query rows [B_pad * Lq_pad, 128] (A-in-TMEM only)
     int ab_f16;                  // operands (Q and D) are fp16 instead of bf16
     int padded;                  // 0 = packed search form, 1 = padded colbert_score form
     int aligned;                 // packed only: passages start on 32-token boundaries of D, pad rows are zero
@@ -166,7 +171,7 @@ __device__ __forceinline__ void ms_mma_issue(const MsParams& p, MsShared* sh, ui
         if (nd == 0) continue;
         if (q != cur_q) {
             if (a_loads > 0 && elect_one()) umma_commit(&sh->a_empty);  // every MMA that read the old A has retired
-            if (map_q != nullptr) {
+            if (map_q != nullptr && p.a_tmem_col == 0) {
                 if (a_loads > 0 && !__all_sync(0xffffffffu, mbar_wait(&sh->a_empty, (a_loads - 1) & 1, p.watchdog))) break;
                 if (elect_one()) {
                     mbar_expect_tx(&sh->a_full, p.MT * 128 * kDim * 2);
@@ -193,10 +198,17 @@ __device__ __forceinline__ void ms_mma_issue(const MsParams& p, MsShared* sh, ui
                 for (int m = 0; m < p.MT; m++) {
                     const uint64_t da0 = da_base + (uint64_t)(m * a_mtile);
                     const uint32_t d_tmem = tmem_base + acc * acc_cols + m * p.NT;
+                    if (p.a_tmem_col > 0) {
 #pragma unroll
-                    for (int k = 0; k < 8; k++)
-                        umma_bf16(d_tmem, da0 + (uint64_t)((k >> 2) * a_khalf + (k & 3) * 2),
-                                  db0 + (uint64_t)((k >> 2) * b_khalf + (k & 3) * 2), idesc, k > 0);
+                        for (int k = 0; k < 8; k++)
+                            umma_f16_ts(d_tmem, tmem_base + p.a_tmem_col + k * 8,
+                                        db0 + (uint64_t)((k >> 2) * b_khalf + (k & 3) * 2), idesc, k > 0);
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 8; k++)
+                            umma_bf16(d_tmem, da0 + (uint64_t)((k >> 2) * a_khalf + (k & 3) * 2),
+                                      db0 + (uint64_t)((k >> 2) * b_khalf + (k & 3) * 2), idesc, k > 0);
+                    }
                 }
                 umma_commit(&sh->empty[s]);
                 umma_commit(&sh->tmem_full[acc]);
@@ -441,11 +453,32 @@ __device__ __forceinline__ void ms_epilogue_a1(const MsParams& p, MsShared* sh, 
                                                int item_end, int warp, int lane, int n_epi) {
     const int quad = warp;
     const uint32_t tmem_lane = tmem_base + ((uint32_t)(quad * 32) << 16);
-    int it_tile = 0, parity = 0;
+    int it_tile = 0, parity = 0, cur_q = -1;
     bool ok = true;
     for (int w = item_begin; ok && w < item_end; w++) {
         const MsItem it = ms_item(p, w);
         if (it.nd == 0) continue;
+        if (p.a_tmem_col > 0 && it.q != cur_q) {
+            // A operand in tensor memory: this warp's 32 query rows (lane = row, 64 columns = 128 fp16).  The MMAs of
+            // the previous query have all completed -- this warp has consumed their last accumulator.
+            const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(p.q_rows) +
+                                                              ((size_t)it.q * p.Lq_pad + quad * 32 + lane) * kDim);
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                uint32_t r[16];
+#pragma unroll
+                for (int v = 0; v < 4; v++) {
+                    const uint4 x = __ldg(src + c * 4 + v);
+                    r[4 * v] = x.x; r[4 * v + 1] = x.y; r[4 * v + 2] = x.z; r[4 * v + 3] = x.w;
+                }
+                tmem_st_32x16(tmem_lane + p.a_tmem_col + c * 16, r);
+            }
+            tc_wait_st();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sh->a_full);
+            cur_q = it.q;
+        }
         const int lq = p.qlens[it.q];
         const bool rowok = (quad * 32 + lane) < lq;
         const bool live = quad * 32 < lq;               // warp-uniform: some lane holds a real query token
@@ -631,7 +664,7 @@ maxsim_fused_kernel(const __grid_constant__ CUtensorMap map_q, const MsParams p)
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     constexpr int PB = 16 * NBITS;                  // packed residual bytes per token
-    const int a_bytes = p.MT * 128 * kDim * 2;
+    const int a_bytes = p.a_tmem_col > 0 ? 0 : p.MT * 128 * kDim * 2;   // A operand in TMEM: no shared-memory copy
     const int b_bytes = p.NT * kDim * 2;
     uint8_t* sA = smem;
     uint8_t* sB = smem + a_bytes;                   // [NS][2 k-halves][NT rows][128 B]
@@ -647,7 +680,7 @@ maxsim_fused_kernel(const __grid_constant__ CUtensorMap map_q, const MsParams p)
     const int wpt = p.NT / kFusedUnit;              // decompressor warps per tile
 
     if (threadIdx.x == 0) {
-        mbar_init(&sh->a_full, 1);
+        mbar_init(&sh->a_full, p.a_tmem_col > 0 ? n_epi : 1);
         mbar_init(&sh->a_empty, 1);
         for (int s = 0; s < p.NS; s++) { mbar_init(&sh->full[s], wpt); mbar_init(&sh->empty[s], 1); }
         for (int a = 0; a < 4; a++) { mbar_init(&sh->tmem_full[a], 1); mbar_init(&sh->tmem_empty[a], n_epi); }
@@ -663,6 +696,20 @@ maxsim_fused_kernel(const __grid_constant__ CUtensorMap map_q, const MsParams p)
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = sh->tmem_base;
+    if (p.a_tmem_col > 0) {
+        // query rows no TMEM quadrant of a live epilogue warp holds are zero for the whole kernel: written once here
+        if (warp < 4 && warp >= n_epi) {
+            uint32_t z[16];
+#pragma unroll
+            for (int i = 0; i < 16; i++) z[i] = 0u;
+#pragma unroll
+            for (int c = 0; c < 4; c++) tmem_st_32x16(tmem_base + ((uint32_t)(warp * 32) << 16) + p.a_tmem_col + c * 16, z);
+            tc_wait_st();
+        }
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+    }
 
     if (SLIM && warp == kMmaWarp) {
         ms_mma_issue(p, sh, sA, sB, b_bytes, tmem_base, item_begin, item_end, lane, &map_q);
@@ -945,14 +992,21 @@ static int ms_launch_fused(const void* Qb, int q_rows, int nbits, MsParams& p, c
     // as many B stages as shared memory allows; the decompressor groups share them in tile order
     const int stage_bufs = nbits <= 2 ? 2 : 1;       // kFusedAsyncStage
     const int unit = p.NT == 64 ? 16 : 32;           // rows per decompressor warp (template parameter UT)
-    const int fixed = 1024 + p.MT * 128 * kDim * 2 + kLutBytes + kFusedDecWarps * stage_bufs * unit * 16 * nbits +
+    const bool slim = p.MT == 1 && p.NT == 128 && p.Lq_pad <= 96;
+#if MS_FUSED_ATMEM
+    if (slim) {                                      // A operand in tensor memory: 2 accumulators (256 columns) + 64 columns of A
+        p.na_shift = 1;
+        p.a_tmem_col = 256;
+        p.q_rows = Qb;
+    }
+#endif
+    const int fixed = 1024 + (p.a_tmem_col > 0 ? 0 : p.MT * 128 * kDim * 2) + kLutBytes + kFusedDecWarps * stage_bufs * unit * 16 * nbits +
                       (int)sizeof(MsShared) + 64;
     const int per_stage = p.NT * kDim * 2;
     p.NS = (227 * 1024 - fixed) / per_stage;
     if (p.NS > kMsMaxStages) p.NS = kMsMaxStages;
     PLAID_CHECK_ARG(p.NS >= 2, PLAID_ERR_UNSUPPORTED, "maxsim_fused: shared memory too small for Lq_pad=%d, nbits=%d", p.Lq_pad, nbits);
     const int smem = fixed + p.NS * per_stage;
-    const bool slim = p.MT == 1 && p.NT == 128 && p.Lq_pad <= 96;
 #define PLAID_FUSED_FN(NB)                                                                              \
     (slim ? (const void*)maxsim_fused_kernel<NB, true, 32>                                              \
           : unit == 16 ? (const void*)maxsim_fused_kernel<NB, false, 16> : (const void*)maxsim_fused_kernel<NB, false, 32>)
