@@ -149,6 +149,8 @@ __device__ __forceinline__ float max32(const uint32_t (&r)[32], float seed) {
 // descriptors are the base descriptor plus a 16-byte-unit offset.
 // With map_q != nullptr the warp also loads the query tile itself (no separate TMA producer warp): it lets the
 // MMAs that read the old query retire, issues the TMA and waits for it -- a drain of a few tiles once per query.
+// ATMEM (compile time, slim fused kernel only): the A operand is read from tensor memory (p.a_tmem_col).
+template <bool ATMEM>
 __device__ __forceinline__ void ms_mma_issue(const MsParams& p, MsShared* sh, uint8_t* sA, uint8_t* sB, int b_bytes,
                                              uint32_t tmem_base_in, int item_begin, int item_end, int lane,
                                              const CUtensorMap* map_q = nullptr) {
@@ -171,7 +173,7 @@ __device__ __forceinline__ void ms_mma_issue(const MsParams& p, MsShared* sh, ui
         if (nd == 0) continue;
         if (q != cur_q) {
             if (a_loads > 0 && elect_one()) umma_commit(&sh->a_empty);  // every MMA that read the old A has retired
-            if (map_q != nullptr && p.a_tmem_col == 0) {
+            if (map_q != nullptr && !ATMEM) {
                 if (a_loads > 0 && !__all_sync(0xffffffffu, mbar_wait(&sh->a_empty, (a_loads - 1) & 1, p.watchdog))) break;
                 if (elect_one()) {
                     mbar_expect_tx(&sh->a_full, p.MT * 128 * kDim * 2);
@@ -198,7 +200,7 @@ __device__ __forceinline__ void ms_mma_issue(const MsParams& p, MsShared* sh, ui
                 for (int m = 0; m < p.MT; m++) {
                     const uint64_t da0 = da_base + (uint64_t)(m * a_mtile);
                     const uint32_t d_tmem = tmem_base + acc * acc_cols + m * p.NT;
-                    if (p.a_tmem_col > 0) {
+                    if constexpr (ATMEM) {
 #pragma unroll
                         for (int k = 0; k < 8; k++)
                             umma_f16_ts(d_tmem, tmem_base + p.a_tmem_col + k * 8,
@@ -449,6 +451,7 @@ __device__ __forceinline__ float max16(const uint32_t (&r)[16], float seed) {
 // (n_epi = Lq_pad / 32), the accumulator is read in 16-column pieces with the load of the next piece in flight
 // while the current one is reduced, and passage boundaries are looked at once per 32 columns.  With the clamp
 // at 0 the running maximum simply starts at 0.
+template <bool ATMEM>
 __device__ __forceinline__ void ms_epilogue_a1(const MsParams& p, MsShared* sh, uint32_t tmem_base, int item_begin,
                                                int item_end, int warp, int lane, int n_epi) {
     const int quad = warp;
@@ -458,7 +461,7 @@ __device__ __forceinline__ void ms_epilogue_a1(const MsParams& p, MsShared* sh, 
     for (int w = item_begin; ok && w < item_end; w++) {
         const MsItem it = ms_item(p, w);
         if (it.nd == 0) continue;
-        if (p.a_tmem_col > 0 && it.q != cur_q) {
+        if (ATMEM && it.q != cur_q) {
             // A operand in tensor memory: this warp's 32 query rows (lane = row, 64 columns = 128 fp16).  The MMAs of
             // the previous query have all completed -- this warp has consumed their last accumulator.
             const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(p.q_rows) +
@@ -616,10 +619,10 @@ maxsim_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
             }
         }
     } else if (warp == 7) {
-        ms_mma_issue(p, sh, sA, sB, b_bytes, tmem_base, item_begin, item_end, lane);
+        ms_mma_issue<false>(p, sh, sA, sB, b_bytes, tmem_base, item_begin, item_end, lane);
     } else if (warp < 4) {
         if (lean) {
-            if (warp < n_epi) ms_epilogue_a1(p, sh, tmem_base, item_begin, item_end, warp, lane, n_epi);
+            if (warp < n_epi) ms_epilogue_a1<false>(p, sh, tmem_base, item_begin, item_end, warp, lane, n_epi);
         } else {
             ms_epilogue<MODE>(p, sh, tmem_base, item_begin, item_end, warp, lane);
         }
@@ -687,6 +690,7 @@ maxsim_fused_kernel(const __grid_constant__ CUtensorMap map_q, const MsParams p)
         fence_mbar_init();
     }
     constexpr int kMmaWarp = SLIM ? 3 : 5, kFirstDecWarp = SLIM ? 4 : 6;
+    constexpr bool kATmem = SLIM && (MS_FUSED_ATMEM != 0);     // the host sets p.a_tmem_col exactly for this layout
     if (warp == kMmaWarp) {
         tmem_alloc(&sh->tmem_base, 512);
         tmem_relinquish();
@@ -696,7 +700,7 @@ maxsim_fused_kernel(const __grid_constant__ CUtensorMap map_q, const MsParams p)
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = sh->tmem_base;
-    if (p.a_tmem_col > 0) {
+    if constexpr (SLIM && (MS_FUSED_ATMEM != 0)) {
         // query rows no TMEM quadrant of a live epilogue warp holds are zero for the whole kernel: written once here
         if (warp < 4 && warp >= n_epi) {
             uint32_t z[16];
@@ -712,10 +716,10 @@ maxsim_fused_kernel(const __grid_constant__ CUtensorMap map_q, const MsParams p)
     }
 
     if (SLIM && warp == kMmaWarp) {
-        ms_mma_issue(p, sh, sA, sB, b_bytes, tmem_base, item_begin, item_end, lane, &map_q);
+        ms_mma_issue<kATmem>(p, sh, sA, sB, b_bytes, tmem_base, item_begin, item_end, lane, &map_q);
     } else if (warp < 4) {
         if (lean) {
-            if (warp < n_epi) ms_epilogue_a1(p, sh, tmem_base, item_begin, item_end, warp, lane, n_epi);
+            if (warp < n_epi) ms_epilogue_a1<kATmem>(p, sh, tmem_base, item_begin, item_end, warp, lane, n_epi);
         } else {
             ms_epilogue<0>(p, sh, tmem_base, item_begin, item_end, warp, lane);
         }
@@ -737,7 +741,7 @@ maxsim_fused_kernel(const __grid_constant__ CUtensorMap map_q, const MsParams p)
             }
         }
     } else if (!SLIM && warp == 5) {
-        ms_mma_issue(p, sh, sA, sB, b_bytes, tmem_base, item_begin, item_end, lane);
+        ms_mma_issue<false>(p, sh, sA, sB, b_bytes, tmem_base, item_begin, item_end, lane);
     } else {
         // ===================== decompressor warps =====================
         // A tile of NT rows is built by wpt = NT / UT warps (one UT-row unit each; passages are 32-row aligned, so
