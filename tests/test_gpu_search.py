@@ -363,3 +363,20 @@ def test_exhaustive_search_matches_padded_scores(pkg):
         assert [i for i, _, _ in got] == rp.tolist() or (rs[:-1] - rs[1:]).min() < 1e-4
     trunc = pkg.exhaustive_search(Q[:1], D, mask, 3)
     assert all(isinstance(s, int) for _, _, s in trunc[0])          # the reference stores int(score) here
+
+
+def test_host_queries_are_fed_chunk_by_chunk(pkg, golden):
+    """search_batch on HOST query embeddings (pinned or not): the copy-stream feed over several chunks returns
+    exactly what the device-resident call returns."""
+    from reranking_multimodal_retrievers_b200 import synthetic
+    from reranking_multimodal_retrievers_b200.engine import SearchEngine
+    from reranking_multimodal_retrievers_b200.index import DeviceIndex
+    sx = synthetic.make_synthetic_index(1500, 10, 50, 2, seed=21, num_centroids=512, mode="codes", device="cuda")
+    Q = synthetic.make_queries(sx, 37, 64, seed=22)
+    eng = SearchEngine(DeviceIndex(sx), max_chunk=8)              # 5 chunks, the last one ragged
+    want = eng.search_batch(Q.cuda(), k=20, ndocs=128)
+    for host in (Q.cpu(), Q.cpu().pin_memory(), Q.cpu().double()):
+        got = eng.search_batch(host, k=20, ndocs=128)
+        torch.cuda.synchronize()
+        assert all(torch.equal(a, b) for a, b in zip(got, want))
+    eng.check_flags()
