@@ -444,6 +444,11 @@ ivf_survivors_kernel(const uint32_t* __restrict__ idx_bits, int C, const int64_t
     }
 }
 
+#ifndef PLAID_PAIRS_GRIDX
+#define PLAID_PAIRS_GRIDX 32
+#endif
+constexpr int kPairsGridX = PLAID_PAIRS_GRIDX;
+
 __global__ void __launch_bounds__(256)
 ivf_pairs_kernel(const int32_t* __restrict__ surv, int cap_s, int32_t* __restrict__ meta,
                  const int32_t* __restrict__ ivf_pids, const int64_t* __restrict__ ivf_offsets,
@@ -452,24 +457,36 @@ ivf_pairs_kernel(const int32_t* __restrict__ surv, int cap_s, int32_t* __restric
     const int b = blockIdx.y, lane = threadIdx.x & 31;
     int32_t* m = meta + (size_t)b * kIvfMeta;
     if (m[2]) return;
-    const int si = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (si >= m[0]) return;
-    const int c = surv[(size_t)b * cap_s + si];
-    const int64_t lo = ivf_offsets[c], hi = ivf_offsets[c + 1];
+    const int wpb = blockDim.x >> 5, ns = min(m[0], cap_s);
     const uint32_t* bm = bitmap + (size_t)b * words;
     const int32_t* wp = wprefix + (size_t)b * words;
-    for (int64_t i = lo + lane; i < hi; i += 32) {
-        const unsigned pid = (unsigned)ld_stream_s32(ivf_pids + i);
-        if (pid >= (unsigned)N) continue;
-        const uint32_t word = __ldg(bm + (pid >> 5));
-        if ((word >> (pid & 31)) & 1u) {
-            const int slot = __ldg(wp + (pid >> 5)) + __popc(word & ((1u << (pid & 31)) - 1u));
-            const int idx = atomicAdd(&m[1], 1);
-            if (idx < cap_p) {
-                pair_slot[(size_t)b * cap_p + idx] = slot;
-                pair_c[(size_t)b * cap_p + idx] = c;
-            } else {
-                m[2] = 1;   // too many pairs for the workspace: this query goes through the scan
+    // one warp per surviving centroid, grid-strided so the grid need not cover the cap_s worst case
+    for (int si = blockIdx.x * wpb + (threadIdx.x >> 5); si < ns; si += gridDim.x * wpb) {
+        const int c = surv[(size_t)b * cap_s + si];
+        const int64_t lo = ivf_offsets[c], hi = ivf_offsets[c + 1];
+        for (int64_t i0 = lo; i0 < hi; i0 += 32) {       // warp-uniform trip count: one atomic per warp and pass
+            const int64_t i = i0 + lane;
+            const unsigned pid = i < hi ? (unsigned)ld_stream_s32(ivf_pids + i) : 0xFFFFFFFFu;
+            uint32_t word = 0;
+            bool hit = false;
+            if (pid < (unsigned)N) {
+                word = __ldg(bm + (pid >> 5));
+                hit = (word >> (pid & 31)) & 1u;
+            }
+            const unsigned hits = __ballot_sync(0xFFFFFFFFu, hit);
+            if (hits == 0) continue;
+            int base = 0;
+            if (lane == 0) base = atomicAdd(&m[1], __popc(hits));
+            base = __shfl_sync(0xFFFFFFFFu, base, 0);
+            if (hit) {
+                const int idx = base + __popc(hits & ((1u << lane) - 1u));
+                if (idx < cap_p) {
+                    const int slot = __ldg(wp + (pid >> 5)) + __popc(word & ((1u << (pid & 31)) - 1u));
+                    pair_slot[(size_t)b * cap_p + idx] = slot;
+                    pair_c[(size_t)b * cap_p + idx] = c;
+                } else {
+                    m[2] = 1;   // too many pairs for the workspace: this query goes through the scan
+                }
             }
         }
     }
@@ -625,7 +642,7 @@ extern "C" int plaid_filter_stage1_ivf(const int32_t* pids, const int32_t* count
     ivf_survivors_kernel<<<B, 256, 0, st>>>(idx_bits, C, ivf_offsets, counts, pid_stride, max_bins, cap_s, max_visits,
                                             ws_surv, ws_meta);
     PLAID_LAUNCH_OK("ivf_survivors_kernel");
-    ivf_pairs_kernel<<<dim3((cap_s + 7) / 8, B), 256, 0, st>>>(ws_surv, cap_s, ws_meta, ivf_pids, ivf_offsets, bitmap,
+    ivf_pairs_kernel<<<dim3(min((cap_s + 7) / 8, kPairsGridX), B), 256, 0, st>>>(ws_surv, cap_s, ws_meta, ivf_pids, ivf_offsets, bitmap,
                                                                 wprefix, words, N, ws_pair_slot, ws_pair_c, cap_p);
     PLAID_LAUNCH_OK("ivf_pairs_kernel");
     static int configured = 0;
