@@ -11,6 +11,8 @@
 // select_top: one CTA per query; 64-bit keys (orderable(score) << 32 | pid) reproduce the
 //   std::pair<float,int> ordering of filter_pids.cpp:24; an 8-pass MSB radix select finds the
 //   keep-th key, survivors are bitonic-sorted in shared memory.
+#include <type_traits>
+
 #include "common.cuh"
 #include <cuda_fp16.h>
 
@@ -145,8 +147,50 @@ approx_scores_kernel(const int32_t* __restrict__ pids, const int32_t* __restrict
                 if (e0 + 128 < end) scan4(cb);
             }
         } else {
-            // ---- stage 2: every code reads its S row (one coalesced 128 B request per token) ----
+            // ---- stage 2: every code reads its S row ----
             const int32_t* cp = codes + off;
+            if constexpr (std::is_same<ST, __half>::value) {
+                // fp16 table: a row is 64 bytes, so one warp-wide 32-bit load fetches the rows of two tokens (lanes 0-15
+                // the even one, 16-31 the odd one) and a lane keeps the running maximum of two query tokens as a half2,
+                // exact in fp16.  16 loads = 32 rows in flight per warp; the walk is bound by gather latency.
+                const __half2* Sb2 = reinterpret_cast<const __half2*>(S + (size_t)b * C * PLAID_NQ_MAX) + (lane & 15);
+                const int hi = lane >> 4;
+                __half2 m2 = __half2half2(__ushort_as_half((unsigned short)0xFC00u));   // -inf: "no token yet"
+                for (int t0 = 0; t0 < len; t0 += 32) {
+                    const int t = t0 + lane;
+                    const int code = (t < len) ? ld_stream_s32(cp + t) : 0;
+                    const int cnt = min(32, len - t0);
+                    if (cnt == 32) {
+                        __half2 v[16];
+#pragma unroll
+                        for (int u = 0; u < 16; u++) {
+                            const unsigned c = (unsigned)__shfl_sync(0xffffffffu, code, 2 * u + hi);
+                            v[u] = __ldg(Sb2 + (size_t)c * (PLAID_NQ_MAX / 2));
+                        }
+#pragma unroll
+                        for (int u = 0; u < 16; u++) m2 = __hmax2(m2, v[u]);
+                    } else {
+                        // the passage's last, partial chunk: sources past the end repeat its last token (max is idempotent)
+                        for (int u0 = 0; 2 * u0 < cnt; u0 += 4) {
+                            __half2 v[4];
+#pragma unroll
+                            for (int u = 0; u < 4; u++) {
+                                const unsigned c = (unsigned)__shfl_sync(0xffffffffu, code, min(2 * (u0 + u) + hi, cnt - 1));
+                                v[u] = __ldg(Sb2 + (size_t)c * (PLAID_NQ_MAX / 2));
+                            }
+#pragma unroll
+                            for (int u = 0; u < 4; u++) m2 = __hmax2(m2, v[u]);
+                        }
+                    }
+                }
+                const unsigned other = __shfl_xor_sync(0xffffffffu, *reinterpret_cast<unsigned*>(&m2), 16);
+                m2 = __hmax2(m2, *reinterpret_cast<const __half2*>(&other));
+                if (lane < 16) {   // an empty passage keeps the reference's -9999 per query token (filter_pids.cpp:30-33)
+                    s_max[warp * DPW + d][2 * lane] = len > 0 ? __low2float(m2) : -9999.0f;
+                    s_max[warp * DPW + d][2 * lane + 1] = len > 0 ? __high2float(m2) : -9999.0f;
+                }
+                continue;
+            }
             for (int t0 = 0; t0 < len; t0 += 32) {
                 const int t = t0 + lane;
                 const int code = (t < len) ? ld_stream_s32(cp + t) : 0;
@@ -492,19 +536,40 @@ ivf_pairs_kernel(const int32_t* __restrict__ surv, int cap_s, int32_t* __restric
     }
 }
 
+// Per-warp tile of running maxima in ivf_scores_kernel: [32 passages][32 query tokens] in the table's own precision (the
+// maximum of stored values is exact in it).  The fp16 tile marks "no surviving centroid" with -inf and turns it into the
+// reference's -9999 (filter_pids.cpp:30-33), which fp16 cannot hold, when the row is summed.
+template <typename ST> struct IvfTile;
+template <> struct IvfTile<float> {
+    static constexpr int kThreads = 512, kPitch = 33;
+    __device__ static float empty() { return -9999.0f; }
+    __device__ static float load(const float* p) { return __ldg(p); }
+    __device__ static float vmax(float a, float b) { return fmaxf(a, b); }
+    __device__ static float term(float v) { return v; }
+};
+template <> struct IvfTile<__half> {
+    static constexpr int kThreads = 1024, kPitch = 34;     // 17 words: the transposed read of the sum is conflict-free
+    __device__ static __half empty() { return __ushort_as_half((unsigned short)0xFC00u); }
+    __device__ static __half load(const __half* p) { return __ldg(p); }
+    __device__ static __half vmax(__half a, __half b) { return __hmax(a, b); }
+    __device__ static float term(__half v) { return __half_as_ushort(v) == 0xFC00u ? -9999.0f : __half2float(v); }
+};
+
 template <typename ST>
-__global__ void __launch_bounds__(512)
+__global__ void __launch_bounds__(IvfTile<ST>::kThreads)
 ivf_scores_kernel(const int32_t* __restrict__ counts, int pid_stride, const int32_t* __restrict__ meta,
                   const int32_t* __restrict__ pair_slot, const int32_t* __restrict__ pair_c, int32_t* __restrict__ sorted_c,
                   int cap_p, const ST* __restrict__ S, int C, const int32_t* __restrict__ qlens, float* __restrict__ out) {
-    extern __shared__ __align__(16) int s_bins[];          // [n + 1] then [16 warps][32][33] floats
+    using Tile = IvfTile<ST>;
+    constexpr int kPitch = Tile::kPitch, kScan = 512, kInFlight = 16;
+    extern __shared__ __align__(16) int s_bins[];          // [n + 1] then one tile per warp
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
     const int32_t* m = meta + (size_t)b * kIvfMeta;
     if (m[2]) return;
     const int n = min(counts[b], pid_stride);
     const int np = min(m[1], cap_p);
-    float (*s_max)[33] = reinterpret_cast<float (*)[33]>(s_bins + ((n + 1 + 3) & ~3)) + warp * 32;
-    __shared__ int s_part[512];
+    ST* s_max = reinterpret_cast<ST*>(s_bins + ((n + 1 + 3) & ~3)) + (size_t)warp * 32 * kPitch;
+    __shared__ int s_part[kScan];
     const int32_t* ps = pair_slot + (size_t)b * cap_p;
     const int32_t* pc = pair_c + (size_t)b * cap_p;
     int2* sc2 = reinterpret_cast<int2*>(sorted_c) + (size_t)b * cap_p;   // (slot, centroid), sorted by slot
@@ -512,12 +577,12 @@ ivf_scores_kernel(const int32_t* __restrict__ counts, int pid_stride, const int3
     __syncthreads();
     for (int i = tid; i < np; i += blockDim.x) atomicAdd(&s_bins[ps[i] + 1], 1);   // count of slot s in bins[s + 1]
     __syncthreads();
-    // exclusive scan over bins[0..n]: thread t owns a contiguous span
-    const int span = (n + 1 + blockDim.x - 1) / blockDim.x;
-    const int lo = min(tid * span, n + 1), hi = min(lo + span, n + 1);
+    // exclusive scan over bins[0..n] by the first 512 threads: thread t owns a contiguous span
+    const int span = (n + 1 + kScan - 1) / kScan;
+    const int lo = tid < kScan ? min(tid * span, n + 1) : n + 1, hi = min(lo + span, n + 1);
     int sum = 0;
     for (int i = lo; i < hi; i++) sum += s_bins[i];
-    s_part[tid] = sum;
+    if (tid < kScan) s_part[tid] = sum;
     __syncthreads();
     if (warp == 0) {   // scan the 512 partial sums: 16 per lane
         int loc[16], tot = 0;
@@ -534,8 +599,8 @@ ivf_scores_kernel(const int32_t* __restrict__ counts, int pid_stride, const int3
         for (int u = 0; u < 16; u++) s_part[lane * 16 + u] = base + loc[u];
     }
     __syncthreads();
-    int run = s_part[tid];
-    for (int i = lo; i < hi; i++) { const int v = s_bins[i]; s_bins[i] = run + v; run += v; }   // inclusive: bins[s+1]... see below
+    int run = tid < kScan ? s_part[tid] : 0;
+    for (int i = lo; i < hi; i++) { const int v = s_bins[i]; s_bins[i] = run + v; run += v; }
     __syncthreads();
     // now bins[i] = number of pairs with slot < i  (inclusive scan of the shifted counts); start(s) = bins[s]
     // scatter: cursor = start(s); afterwards bins[s] = end(s) and start(s) = (s ? bins[s-1] : 0)
@@ -546,38 +611,57 @@ ivf_scores_kernel(const int32_t* __restrict__ counts, int pid_stride, const int3
     __syncthreads();
     const int nq = min(qlens[b], PLAID_NQ_MAX);
     const ST* Sb = S + (size_t)b * C * PLAID_NQ_MAX + lane;
-    for (int base = warp * 32; base < n; base += nw * 32) {
+    // a warp takes 32 passages at a time; their pairs are contiguous in the sorted array.  A group holds ~half a pair per
+    // passage on the headline workload, so the walk is a chain of dependent L2 round trips: the first 32 pairs of the
+    // next group are fetched while this one is reduced, and 16 score rows are in flight per pass.
+    int base = warp * 32, beg = 0, end = 0;
+    int2 mine = make_int2(base, 0);
+    if (base < n) {
+        beg = base ? s_bins[base - 1] : 0;
+        end = s_bins[min(base + 31, n - 1)];
+        if (beg + lane < end) mine = sc2[beg + lane];
+    }
+    while (base < n) {
+        const int nbase = base + nw * 32;
+        int nbeg = 0, nend = 0;
+        int2 nmine = make_int2(nbase, 0);
+        if (nbase < n) {
+            nbeg = s_bins[nbase - 1];
+            nend = s_bins[min(nbase + 31, n - 1)];
+            if (nbeg + lane < nend) nmine = sc2[nbeg + lane];
+        }
 #pragma unroll
-        for (int j = 0; j < 32; j++) s_max[j][lane] = -9999.0f;  // filter_pids.cpp:30-33
+        for (int j = 0; j < 32; j++) s_max[j * kPitch + lane] = Tile::empty();
         __syncwarp();
-        // the pairs of slots base .. base+31 are contiguous in the sorted array
-        const int beg = base ? s_bins[base - 1] : 0, end = s_bins[min(base + 31, n - 1)];
         for (int p0 = beg; p0 < end; p0 += 32) {
-            const int2 mine = (p0 + lane < end) ? sc2[p0 + lane] : make_int2(base, 0);
+            if (p0 != beg) mine = (p0 + lane < end) ? sc2[p0 + lane] : make_int2(base, 0);
             const int cnt = min(32, end - p0);
-            for (int u0 = 0; u0 < cnt; u0 += 8) {       // eight S rows in flight
-                float v[8];
-                int sl[8];
+            for (int u0 = 0; u0 < cnt; u0 += kInFlight) {
+                ST v[kInFlight];
 #pragma unroll
-                for (int u = 0; u < 8; u++) {
-                    const int src = min(u0 + u, cnt - 1);
-                    sl[u] = __shfl_sync(0xffffffffu, mine.x, src) - base;
-                    const unsigned c = (unsigned)__shfl_sync(0xffffffffu, mine.y, src);
-                    v[u] = load_s(Sb + (size_t)c * PLAID_NQ_MAX);
+                for (int u = 0; u < kInFlight; u++) {
+                    const unsigned c = (unsigned)__shfl_sync(0xffffffffu, mine.y, min(u0 + u, cnt - 1));
+                    v[u] = Tile::load(Sb + (size_t)c * PLAID_NQ_MAX);
                 }
 #pragma unroll
-                for (int u = 0; u < 8; u++)
-                    if (u0 + u < cnt) s_max[sl[u]][lane] = fmaxf(s_max[sl[u]][lane], v[u]);
+                for (int u = 0; u < kInFlight; u++) {
+                    const int sl = __shfl_sync(0xffffffffu, mine.x, min(u0 + u, cnt - 1)) - base;
+                    if (u0 + u < cnt) {
+                        ST* cell = s_max + sl * kPitch + lane;
+                        *cell = Tile::vmax(*cell, v[u]);
+                    }
+                }
             }
         }
         __syncwarp();
         const int sidx = base + lane;
         if (sidx < n) {
             float acc = 0.0f;  // sequential fp32 sum in token order (filter_pids.cpp:59-63)
-            for (int k = 0; k < nq; k++) acc += s_max[lane][k];
+            for (int k = 0; k < nq; k++) acc += Tile::term(s_max[lane * kPitch + k]);
             out[(size_t)b * pid_stride + sidx] = acc;
         }
         __syncwarp();
+        base = nbase; beg = nbeg; end = nend; mine = nmine;
     }
 }
 
@@ -631,9 +715,10 @@ extern "C" int plaid_filter_stage1_ivf(const int32_t* pids, const int32_t* count
     PLAID_CHECK_ARG(B <= 65535, PLAID_ERR_UNSUPPORTED, "plaid_filter_stage1_ivf: B=%d > 65535 per call", B);
     cudaStream_t st = (cudaStream_t)stream;
     const int words = (N + 31) / 32;
-    // shared memory of ivf_scores: bins [n+1] + 16 warps x 32 x 33 floats; passages beyond that use the scan
+    // shared memory of ivf_scores: bins [n+1] + one 32 x 32 tile of maxima per warp; passages beyond that use the scan
     const int smem_cap = 200 * 1024;
-    const int smax_bytes = 16 * 32 * 33 * 4;
+    const int smax_bytes = s_is_f16 ? (IvfTile<__half>::kThreads / 32) * 32 * IvfTile<__half>::kPitch * 2
+                                    : (IvfTile<float>::kThreads / 32) * 32 * IvfTile<float>::kPitch * 4;
     int max_bins = (smem_cap - smax_bytes) / 4 - 8;
     if (max_bins > pid_stride) max_bins = pid_stride;
     const int smem = ((max_bins + 1 + 3) & ~3) * 4 + smax_bytes;
@@ -652,10 +737,10 @@ extern "C" int plaid_filter_stage1_ivf(const int32_t* pids, const int32_t* count
         configured = smem;
     }
     if (s_is_f16)
-        ivf_scores_kernel<__half><<<B, 512, smem, st>>>(counts, pid_stride, ws_meta, ws_pair_slot, ws_pair_c, ws_sorted_c,
+        ivf_scores_kernel<__half><<<B, IvfTile<__half>::kThreads, smem, st>>>(counts, pid_stride, ws_meta, ws_pair_slot, ws_pair_c, ws_sorted_c,
                                                         cap_p, reinterpret_cast<const __half*>(S), C, qlens, out_scores);
     else
-        ivf_scores_kernel<float><<<B, 512, smem, st>>>(counts, pid_stride, ws_meta, ws_pair_slot, ws_pair_c, ws_sorted_c,
+        ivf_scores_kernel<float><<<B, IvfTile<float>::kThreads, smem, st>>>(counts, pid_stride, ws_meta, ws_pair_slot, ws_pair_c, ws_sorted_c,
                                                        cap_p, reinterpret_cast<const float*>(S), C, qlens, out_scores);
     PLAID_LAUNCH_OK("ivf_scores_kernel");
     // queries flagged for the scan (dense masks, oversized lists): the token-scan kernel, restricted to them
