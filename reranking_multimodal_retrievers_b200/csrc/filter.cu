@@ -541,18 +541,85 @@ ivf_pairs_kernel(const int32_t* __restrict__ surv, int cap_s, int32_t* __restric
 // reference's -9999 (filter_pids.cpp:30-33), which fp16 cannot hold, when the row is summed.
 template <typename ST> struct IvfTile;
 template <> struct IvfTile<float> {
-    static constexpr int kThreads = 512, kPitch = 33;
-    __device__ static float empty() { return -9999.0f; }
-    __device__ static float load(const float* p) { return __ldg(p); }
-    __device__ static float vmax(float a, float b) { return fmaxf(a, b); }
-    __device__ static float term(float v) { return v; }
+    static constexpr int kThreads = 512, kBytes = 32 * 33 * 4;
+    using Cell = float;                                     // [32][33]
+    __device__ static void clear(Cell* t, int lane) {
+#pragma unroll
+        for (int j = 0; j < 32; j++) t[j * 33 + lane] = -9999.0f;
+    }
+    // up to 32 (slot, centroid) pairs held one per lane in `mine`; Srow = the query's table
+    __device__ static void gather(Cell* t, int2 mine, int cnt, int base, const float* Srow, int lane) {
+        const float* Sb = Srow + lane;
+        for (int u0 = 0; u0 < cnt; u0 += 16) {
+            float v[16];
+#pragma unroll
+            for (int u = 0; u < 16; u++) {
+                const unsigned c = (unsigned)__shfl_sync(0xffffffffu, mine.y, min(u0 + u, cnt - 1));
+                v[u] = __ldg(Sb + (size_t)c * PLAID_NQ_MAX);
+            }
+#pragma unroll
+            for (int u = 0; u < 16; u++) {
+                const int sl = __shfl_sync(0xffffffffu, mine.x, min(u0 + u, cnt - 1)) - base;
+                if (u0 + u < cnt) t[sl * 33 + lane] = fmaxf(t[sl * 33 + lane], v[u]);
+            }
+        }
+    }
+    __device__ static float sum(const Cell* t, int lane, int nq) {
+        float acc = 0.0f;  // sequential fp32 sum in token order (filter_pids.cpp:59-63)
+        for (int k = 0; k < nq; k++) acc += t[lane * 33 + k];
+        return acc;
+    }
 };
 template <> struct IvfTile<__half> {
-    static constexpr int kThreads = 1024, kPitch = 34;     // 17 words: the transposed read of the sum is conflict-free
-    __device__ static __half empty() { return __ushort_as_half((unsigned short)0xFC00u); }
-    __device__ static __half load(const __half* p) { return __ldg(p); }
-    __device__ static __half vmax(__half a, __half b) { return __hmax(a, b); }
+    // Two query tokens per cell; a 64-byte table row is half a warp's load, so one load instruction fetches the rows of
+    // two pairs (lanes 0-15 the even pair, 16-31 the odd one).  Pitch 17 words: the transposed read of sum() is
+    // conflict-free.
+    static constexpr int kThreads = 1024, kBytes = 32 * 17 * 4;
+    using Cell = __half2;                                   // [32][17]
+    __device__ static __half2 ninf2() { return __half2half2(__ushort_as_half((unsigned short)0xFC00u)); }
+    __device__ static void clear(Cell* t, int lane) {
+#pragma unroll
+        for (int j = 0; j < 17; j++) t[j * 32 + lane] = ninf2();
+    }
+    __device__ static void gather(Cell* t, int2 mine, int cnt, int base, const __half* Srow, int lane) {
+        const __half2* Sb2 = reinterpret_cast<const __half2*>(Srow) + (lane & 15);
+        const int hi = lane >> 4;
+        __half2 v[16];
+#pragma unroll
+        for (int u = 0; u < 16; u++) {
+            if (2 * u < cnt) {     // an odd count's last load repeats the last pair in the upper half warp
+                const unsigned c = (unsigned)__shfl_sync(0xffffffffu, mine.y, min(2 * u + hi, cnt - 1));
+                v[u] = __ldg(Sb2 + (size_t)c * (PLAID_NQ_MAX / 2));
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 16; u++) {
+            if (2 * u < cnt) {
+                const int sl = __shfl_sync(0xffffffffu, mine.x, min(2 * u + hi, cnt - 1)) - base;
+                const int osl = __shfl_xor_sync(0xffffffffu, sl, 16);
+                const unsigned ov = __shfl_xor_sync(0xffffffffu, *reinterpret_cast<unsigned*>(&v[u]), 16);
+                Cell* cell = t + sl * 17 + (lane & 15);
+                if (sl != osl) {
+                    *cell = __hmax2(*cell, v[u]);
+                } else if (!hi) {  // both pairs belong to one passage: one half warp folds them, the other stays out
+                    *cell = __hmax2(*cell, __hmax2(v[u], *reinterpret_cast<const __half2*>(&ov)));
+                }
+                __syncwarp();      // lanes l and l + 16 share a column of the tile
+            }
+        }
+    }
+    // -inf marks "no surviving centroid": the reference's -9999 (filter_pids.cpp:30-33), which fp16 cannot hold
     __device__ static float term(__half v) { return __half_as_ushort(v) == 0xFC00u ? -9999.0f : __half2float(v); }
+    __device__ static float sum(const Cell* t, int lane, int nq) {
+        float acc = 0.0f;  // sequential fp32 sum in token order (filter_pids.cpp:59-63)
+#pragma unroll
+        for (int k2 = 0; k2 < PLAID_NQ_MAX / 2; k2++) {
+            const __half2 h = t[lane * 17 + k2];
+            if (2 * k2 < nq) acc += term(__low2half(h));
+            if (2 * k2 + 1 < nq) acc += term(__high2half(h));
+        }
+        return acc;
+    }
 };
 
 template <typename ST>
@@ -561,14 +628,15 @@ ivf_scores_kernel(const int32_t* __restrict__ counts, int pid_stride, const int3
                   const int32_t* __restrict__ pair_slot, const int32_t* __restrict__ pair_c, int32_t* __restrict__ sorted_c,
                   int cap_p, const ST* __restrict__ S, int C, const int32_t* __restrict__ qlens, float* __restrict__ out) {
     using Tile = IvfTile<ST>;
-    constexpr int kPitch = Tile::kPitch, kScan = 512, kInFlight = 16;
+    constexpr int kScan = 512;
     extern __shared__ __align__(16) int s_bins[];          // [n + 1] then one tile per warp
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
     const int32_t* m = meta + (size_t)b * kIvfMeta;
     if (m[2]) return;
     const int n = min(counts[b], pid_stride);
     const int np = min(m[1], cap_p);
-    ST* s_max = reinterpret_cast<ST*>(s_bins + ((n + 1 + 3) & ~3)) + (size_t)warp * 32 * kPitch;
+    typename Tile::Cell* s_max = reinterpret_cast<typename Tile::Cell*>(
+        reinterpret_cast<char*>(s_bins + ((n + 1 + 3) & ~3)) + (size_t)warp * Tile::kBytes);
     __shared__ int s_part[kScan];
     const int32_t* ps = pair_slot + (size_t)b * cap_p;
     const int32_t* pc = pair_c + (size_t)b * cap_p;
@@ -610,10 +678,10 @@ ivf_scores_kernel(const int32_t* __restrict__ counts, int pid_stride, const int3
     }
     __syncthreads();
     const int nq = min(qlens[b], PLAID_NQ_MAX);
-    const ST* Sb = S + (size_t)b * C * PLAID_NQ_MAX + lane;
+    const ST* Srow = S + (size_t)b * C * PLAID_NQ_MAX;
     // a warp takes 32 passages at a time; their pairs are contiguous in the sorted array.  A group holds ~half a pair per
     // passage on the headline workload, so the walk is a chain of dependent L2 round trips: the first 32 pairs of the
-    // next group are fetched while this one is reduced, and 16 score rows are in flight per pass.
+    // next group are fetched while this one is reduced, and 16 loads are in flight per pass.
     int base = warp * 32, beg = 0, end = 0;
     int2 mine = make_int2(base, 0);
     if (base < n) {
@@ -630,36 +698,16 @@ ivf_scores_kernel(const int32_t* __restrict__ counts, int pid_stride, const int3
             nend = s_bins[min(nbase + 31, n - 1)];
             if (nbeg + lane < nend) nmine = sc2[nbeg + lane];
         }
-#pragma unroll
-        for (int j = 0; j < 32; j++) s_max[j * kPitch + lane] = Tile::empty();
+        Tile::clear(s_max, lane);
         __syncwarp();
         for (int p0 = beg; p0 < end; p0 += 32) {
             if (p0 != beg) mine = (p0 + lane < end) ? sc2[p0 + lane] : make_int2(base, 0);
-            const int cnt = min(32, end - p0);
-            for (int u0 = 0; u0 < cnt; u0 += kInFlight) {
-                ST v[kInFlight];
-#pragma unroll
-                for (int u = 0; u < kInFlight; u++) {
-                    const unsigned c = (unsigned)__shfl_sync(0xffffffffu, mine.y, min(u0 + u, cnt - 1));
-                    v[u] = Tile::load(Sb + (size_t)c * PLAID_NQ_MAX);
-                }
-#pragma unroll
-                for (int u = 0; u < kInFlight; u++) {
-                    const int sl = __shfl_sync(0xffffffffu, mine.x, min(u0 + u, cnt - 1)) - base;
-                    if (u0 + u < cnt) {
-                        ST* cell = s_max + sl * kPitch + lane;
-                        *cell = Tile::vmax(*cell, v[u]);
-                    }
-                }
-            }
+            Tile::gather(s_max, mine, min(32, end - p0), base, Srow, lane);
+            __syncwarp();
         }
         __syncwarp();
         const int sidx = base + lane;
-        if (sidx < n) {
-            float acc = 0.0f;  // sequential fp32 sum in token order (filter_pids.cpp:59-63)
-            for (int k = 0; k < nq; k++) acc += Tile::term(s_max[lane * kPitch + k]);
-            out[(size_t)b * pid_stride + sidx] = acc;
-        }
+        if (sidx < n) out[(size_t)b * pid_stride + sidx] = Tile::sum(s_max, lane, nq);
         __syncwarp();
         base = nbase; beg = nbeg; end = nend; mine = nmine;
     }
@@ -717,8 +765,8 @@ extern "C" int plaid_filter_stage1_ivf(const int32_t* pids, const int32_t* count
     const int words = (N + 31) / 32;
     // shared memory of ivf_scores: bins [n+1] + one 32 x 32 tile of maxima per warp; passages beyond that use the scan
     const int smem_cap = 200 * 1024;
-    const int smax_bytes = s_is_f16 ? (IvfTile<__half>::kThreads / 32) * 32 * IvfTile<__half>::kPitch * 2
-                                    : (IvfTile<float>::kThreads / 32) * 32 * IvfTile<float>::kPitch * 4;
+    const int smax_bytes = s_is_f16 ? (IvfTile<__half>::kThreads / 32) * IvfTile<__half>::kBytes
+                                    : (IvfTile<float>::kThreads / 32) * IvfTile<float>::kBytes;
     int max_bins = (smem_cap - smax_bytes) / 4 - 8;
     if (max_bins > pid_stride) max_bins = pid_stride;
     const int smem = ((max_bins + 1 + 3) & ~3) * 4 + smax_bytes;
