@@ -480,14 +480,19 @@ def main():
     chunks = (B + eng.chunk_size(B) - 1) // eng.chunk_size(B)
     T1, T2, T3, ncand = stats["T1"], stats["T2"], stats["T3"], stats["ncand"]
     # ALGORITHMIC bytes / flops per step, per stage
+    s_row = 64.0 if eng.s_dtype == torch.float16 else 128.0
     alg = {
         "centroid_scores": dict(bytes=(2.0 if eng.s_dtype == torch.float16 else 4.0) * C * 32 * B + 2.0 * C * 128 * chunks,
                                 flops=2.0 * C * 128 * 32 * B),
+        # the token scan's bytes; the inverted-file route stage 1 normally takes reads far less, so this stage can show
+        # more than the scan's roofline
         "filter_stage1": dict(bytes=4.0 * T1 + 16.0 * ncand, flops=0.0),
-        "filter_stage2": dict(bytes=4.0 * T2 + 16.0 * 1024 * B + (64.0 if eng.s_dtype == torch.float16 else 128.0) * T2,
-                              flops=0.0),
+        # every token gathers one score row, but a query has only C distinct rows and re-reads are L2 hits: the
+        # compulsory HBM traffic is each touched row once
+        "filter_stage2": dict(bytes=4.0 * T2 + 16.0 * 1024 * B + s_row * min(T2, float(C) * B), flops=0.0),
         "candidates": dict(bytes=4.0 * ncand + (w["N"] / 8.0) * B * 2, flops=0.0),
-        "decompress": dict(bytes=(4.0 + 16 * nbits + 256.0 + 256.0) * T3, flops=0.0),   # codes+residual+f16 centroid row in, fp16 out
+        # codes + residual in, fp16 row out, and the fp16 centroid table once per launch (it stays in L2)
+        "decompress": dict(bytes=(4.0 + 16 * nbits + 256.0) * T3 + 256.0 * min(T3, float(C) * chunks), flops=0.0),
         "maxsim": dict(bytes=256.0 * T3, flops=2.0 * Lq * 128 * T3),
         "maxsim_fused": dict(bytes=(4.0 + 16 * nbits) * T3, flops=2.0 * Lq * 128 * T3),    # K4' of SURVEY 8d
     }

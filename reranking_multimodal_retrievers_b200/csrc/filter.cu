@@ -564,7 +564,7 @@ template <> struct IvfTile<float> {
             }
         }
     }
-    __device__ static float sum(const Cell* t, int lane, int nq) {
+    __device__ static float sum(const Cell* t, int lane, int nq, float) {
         float acc = 0.0f;  // sequential fp32 sum in token order (filter_pids.cpp:59-63)
         for (int k = 0; k < nq; k++) acc += t[lane * 33 + k];
         return acc;
@@ -584,39 +584,55 @@ template <> struct IvfTile<__half> {
     __device__ static void gather(Cell* t, int2 mine, int cnt, int base, const __half* Srow, int lane) {
         const __half2* Sb2 = reinterpret_cast<const __half2*>(Srow) + (lane & 15);
         const int hi = lane >> 4;
-        __half2 v[16];
+        // Split the (slot-sorted) pairs between the half warps at a slot boundary at or past the middle: the halves then
+        // never update the same row of the tile, so no exchange or ordering between them is needed.
+        const int prev = __shfl_up_sync(0xffffffffu, mine.x, 1);
+        const unsigned starts = __ballot_sync(0xffffffffu, lane > 0 && lane < cnt && mine.x != prev);
+        const int half = (cnt + 1) >> 1;
+        const unsigned above = (starts >> half) << half;
+        const int m = above ? __ffs(above) - 1 : cnt;
+        const int first = hi ? m : 0, last = hi ? cnt : m;           // this half warp's pairs
+        const int steps = max(m, cnt - m);
+        const bool active = first < last;                             // the upper half idles when one slot owns the tail
+        for (int u0 = 0; u0 < steps; u0 += 16) {
+            __half2 v[16];
 #pragma unroll
-        for (int u = 0; u < 16; u++) {
-            if (2 * u < cnt) {     // an odd count's last load repeats the last pair in the upper half warp
-                const unsigned c = (unsigned)__shfl_sync(0xffffffffu, mine.y, min(2 * u + hi, cnt - 1));
-                v[u] = __ldg(Sb2 + (size_t)c * (PLAID_NQ_MAX / 2));
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < 16; u++) {
-            if (2 * u < cnt) {
-                const int sl = __shfl_sync(0xffffffffu, mine.x, min(2 * u + hi, cnt - 1)) - base;
-                const int osl = __shfl_xor_sync(0xffffffffu, sl, 16);
-                const unsigned ov = __shfl_xor_sync(0xffffffffu, *reinterpret_cast<unsigned*>(&v[u]), 16);
-                Cell* cell = t + sl * 17 + (lane & 15);
-                if (sl != osl) {
-                    *cell = __hmax2(*cell, v[u]);
-                } else if (!hi) {  // both pairs belong to one passage: one half warp folds them, the other stays out
-                    *cell = __hmax2(*cell, __hmax2(v[u], *reinterpret_cast<const __half2*>(&ov)));
+            for (int u = 0; u < 16; u++) {
+                if (u0 + u < steps) {  // past its last pair a half warp repeats it: max is idempotent
+                    const unsigned c = (unsigned)__shfl_sync(0xffffffffu, mine.y, min(first + u0 + u, last - 1));
+                    v[u] = __ldg(Sb2 + (size_t)c * (PLAID_NQ_MAX / 2));
                 }
-                __syncwarp();      // lanes l and l + 16 share a column of the tile
+            }
+#pragma unroll
+            for (int u = 0; u < 16; u++) {
+                if (u0 + u < steps) {
+                    const int sl = __shfl_sync(0xffffffffu, mine.x, min(first + u0 + u, last - 1)) - base;
+                    if (active) {
+                        Cell* cell = t + sl * 17 + (lane & 15);
+                        *cell = __hmax2(*cell, v[u]);
+                    }
+                }
             }
         }
     }
-    // -inf marks "no surviving centroid": the reference's -9999 (filter_pids.cpp:30-33), which fp16 cannot hold
-    __device__ static float term(__half v) { return __half_as_ushort(v) == 0xFC00u ? -9999.0f : __half2float(v); }
-    __device__ static float sum(const Cell* t, int lane, int nq) {
+    // -inf marks "no surviving centroid": the reference's -9999 (filter_pids.cpp:30-33), which fp16 cannot hold.  A
+    // passage either has no pair at all (every cell empty) or a full table row for every query token.
+    __device__ static float sum(const Cell* t, int lane, int nq, float empty_sum) {
+        const Cell* row = t + lane * 17;
+        if (__half_as_ushort(__low2half(row[0])) == 0xFC00u) return empty_sum;
         float acc = 0.0f;  // sequential fp32 sum in token order (filter_pids.cpp:59-63)
+        if (nq == PLAID_NQ_MAX) {
 #pragma unroll
-        for (int k2 = 0; k2 < PLAID_NQ_MAX / 2; k2++) {
-            const __half2 h = t[lane * 17 + k2];
-            if (2 * k2 < nq) acc += term(__low2half(h));
-            if (2 * k2 + 1 < nq) acc += term(__high2half(h));
+            for (int k2 = 0; k2 < PLAID_NQ_MAX / 2; k2++) {
+                const float2 f = __half22float2(row[k2]);
+                acc += f.x;
+                acc += f.y;
+            }
+        } else {
+            for (int k = 0; k < nq; k++) {
+                const __half2 h = row[k >> 1];
+                acc += __half2float((k & 1) ? __high2half(h) : __low2half(h));
+            }
         }
         return acc;
     }
@@ -679,6 +695,8 @@ ivf_scores_kernel(const int32_t* __restrict__ counts, int pid_stride, const int3
     __syncthreads();
     const int nq = min(qlens[b], PLAID_NQ_MAX);
     const ST* Srow = S + (size_t)b * C * PLAID_NQ_MAX;
+    float empty_sum = 0.0f;                 // score of a passage without any surviving centroid
+    for (int k = 0; k < nq; k++) empty_sum += -9999.0f;
     // a warp takes 32 passages at a time; their pairs are contiguous in the sorted array.  A group holds ~half a pair per
     // passage on the headline workload, so the walk is a chain of dependent L2 round trips: the first 32 pairs of the
     // next group are fetched while this one is reduced, and 16 loads are in flight per pass.
@@ -707,7 +725,7 @@ ivf_scores_kernel(const int32_t* __restrict__ counts, int pid_stride, const int3
         }
         __syncwarp();
         const int sidx = base + lane;
-        if (sidx < n) out[(size_t)b * pid_stride + sidx] = Tile::sum(s_max, lane, nq);
+        if (sidx < n) out[(size_t)b * pid_stride + sidx] = Tile::sum(s_max, lane, nq, empty_sum);
         __syncwarp();
         base = nbase; beg = nbeg; end = nend; mine = nmine;
     }
