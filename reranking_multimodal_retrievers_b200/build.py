@@ -98,7 +98,13 @@ def build_variant(name: str, defines: list[str], files=("maxsim.cu",)) -> str:
 if __name__ == "__main__":
     if "--variant" in sys.argv:
         i = sys.argv.index("--variant")
-        print(build_variant(sys.argv[i + 1], sys.argv[i + 2:]))
+        rest = sys.argv[i + 2:]
+        files = ("maxsim.cu",)
+        if "--files" in rest:                      # --variant NAME [--files a.cu,b.cu] DEFINE[=VALUE]...
+            j = rest.index("--files")
+            files = tuple(rest[j + 1].split(","))
+            rest = rest[:j] + rest[j + 2:]
+        print(build_variant(sys.argv[i + 1], [d[2:] if d.startswith("-D") else d for d in rest], files))
         sys.exit(0)
     path = build_library(force="--force" in sys.argv, verbose="--verbose" in sys.argv)
     print(path)
