@@ -156,9 +156,11 @@ approx_scores_kernel(const int32_t* __restrict__ pids, const int32_t* __restrict
                 const __half2* Sb2 = reinterpret_cast<const __half2*>(S + (size_t)b * C * PLAID_NQ_MAX) + (lane & 15);
                 const int hi = lane >> 4;
                 __half2 m2 = __half2half2(__ushort_as_half((unsigned short)0xFC00u));   // -inf: "no token yet"
+                // the codes of the next 32 tokens are requested before this chunk's rows: one round trip per chunk, not two
+                int code = (lane < len) ? ld_stream_s32(cp + lane) : 0;
                 for (int t0 = 0; t0 < len; t0 += 32) {
-                    const int t = t0 + lane;
-                    const int code = (t < len) ? ld_stream_s32(cp + t) : 0;
+                    const int tn = t0 + 32 + lane;
+                    const int ncode = (tn < len) ? ld_stream_s32(cp + tn) : 0;
                     const int cnt = min(32, len - t0);
                     if (cnt == 32) {
                         __half2 v[16];
@@ -182,6 +184,7 @@ approx_scores_kernel(const int32_t* __restrict__ pids, const int32_t* __restrict
                             for (int u = 0; u < 4; u++) m2 = __hmax2(m2, v[u]);
                         }
                     }
+                    code = ncode;
                 }
                 const unsigned other = __shfl_xor_sync(0xffffffffu, *reinterpret_cast<unsigned*>(&m2), 16);
                 m2 = __hmax2(m2, *reinterpret_cast<const __half2*>(&other));
