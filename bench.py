@@ -486,14 +486,16 @@ def main():
                                 flops=2.0 * C * 128 * 32 * B),
         # the token scan's bytes; the inverted-file route stage 1 normally takes reads far less, so this stage can show
         # more than the scan's roofline
-        "filter_stage1": dict(bytes=4.0 * T1 + 16.0 * ncand, flops=0.0),
+        "filter_stage1": dict(bytes=4.0 * T1 + 16.0 * ncand, flops=0.0,
+                              note="bytes = the token scan's model; the inverted-file route reads far less, so > 1 is expected"),
         # every token gathers one score row, but a query has only C distinct rows and re-reads are L2 hits: the
         # compulsory HBM traffic is each touched row once
         "filter_stage2": dict(bytes=4.0 * T2 + 16.0 * 1024 * B + s_row * min(T2, float(C) * B), flops=0.0),
         "candidates": dict(bytes=4.0 * ncand + (w["N"] / 8.0) * B * 2, flops=0.0),
         # codes + residual in, fp16 row out, and the fp16 centroid table once per launch (it stays in L2)
         "decompress": dict(bytes=(4.0 + 16 * nbits + 256.0) * T3 + 256.0 * min(T3, float(C) * chunks), flops=0.0),
-        "maxsim": dict(bytes=256.0 * T3, flops=2.0 * Lq * 128 * T3),
+        "maxsim": dict(bytes=256.0 * T3, flops=2.0 * Lq * 128 * T3,
+                       note="reads D right after decompress wrote it: part of it is still in L2"),
         "maxsim_fused": dict(bytes=(4.0 + 16 * nbits) * T3, flops=2.0 * Lq * 128 * T3),    # K4' of SURVEY 8d
     }
     kernels = {}
@@ -506,6 +508,8 @@ def main():
             if alg[stage]["flops"]:
                 d["achieved_TFLOPs"] = round(alg[stage]["flops"] / (per_step * 1e-3) / 1e12, 2)
                 d["frac_tensor"] = round(d["achieved_TFLOPs"] / peaks["tf_sustained"], 4)
+            if "note" in alg[stage]:
+                d["note"] = alg[stage]["note"]
         kernels[stage] = d
     dom = max((s for s in kernels if s in alg), key=lambda s: kernels[s]["ms_per_step"])
     nl = kernels[dom]["launches_per_step"]
