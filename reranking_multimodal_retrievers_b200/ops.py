@@ -88,10 +88,14 @@ def pad_centroid_scores(centroid_scores: torch.Tensor) -> torch.Tensor:
 
 
 # --------------------------------------------------------------------------------------------- filter_pids
-def approx_scores(pids, centroid_scores, codes, offsets, idx=None):
-    """Per-passage approximate score (filter_pids.cpp:27-72) for ONE query; idx=None = all centroids."""
+def approx_scores(pids, centroid_scores, codes, offsets, idx=None, table_f16=False):
+    """Per-passage approximate score (filter_pids.cpp:27-72) for ONE query; idx=None = all centroids.
+    table_f16: hand the kernel the table in fp16, the precision of the reference's GPU branch
+    (candidate_generation.py:52) and the engine's default; the sums stay sequential fp32."""
     pids = _cu(pids, torch.int32)
     S = pad_centroid_scores(_cu(centroid_scores))
+    if table_f16:
+        S = S.half()
     C, nq = centroid_scores.shape
     n = pids.numel()
     counts = torch.tensor([n], device=pids.device, dtype=torch.int32)
@@ -100,7 +104,7 @@ def approx_scores(pids, centroid_scores, codes, offsets, idx=None):
     out = torch.empty(max(n, 1), device=pids.device, dtype=torch.float32)
     codes, offsets = _cu(codes, torch.int32), _cu(offsets, torch.int64)   # named: must outlive the launch
     check_codes(codes, C)
-    _lib.call("plaid_approx_scores", _p(pids), _p(counts), 1, n, _p(S), 0, _p(qlens), _p(bits), C,
+    _lib.call("plaid_approx_scores", _p(pids), _p(counts), 1, n, _p(S), int(table_f16), _p(qlens), _p(bits), C,
               _p(codes), _p(offsets), _p(out), _stream())
     return out[:n]
 

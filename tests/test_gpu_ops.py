@@ -112,6 +112,30 @@ def test_filter_pids_fewer_candidates_than_ndocs_and_short_queries(P, golden):
     assert p2.numel() == 0
 
 
+@pytest.mark.parametrize("nq", [32, 7, 1])
+def test_approx_scores_fp16_table(P, nq):
+    """The fp16 score table (the engine's default, candidate_generation.py:52): stage 2 reads two rows per warp load and
+    keeps half2 maxima -- maxima of fp16 values are exact, so the scores equal the oracle's on the rounded table bit for
+    bit.  Passage lengths cover empty, < 32, multiples of 32 and odd tails."""
+    _, ops = P
+    gen = torch.Generator().manual_seed(7)
+    C = 384
+    doclens = torch.tensor([0, 1, 2, 31, 32, 33, 63, 64, 65, 96, 127, 180, 5, 0, 40, 17] * 3, dtype=torch.int64)
+    offsets = torch.cat([torch.zeros(1, dtype=torch.int64), doclens.cumsum(0)])
+    codes = torch.randint(0, C, (int(offsets[-1]),), generator=gen, dtype=torch.int32)
+    ix = po.OracleIndex(centroids=torch.zeros(C, 128), bucket_weights=torch.zeros(4), codes=codes,
+                        residuals=torch.zeros(codes.numel(), 32, dtype=torch.uint8), doclens=doclens,
+                        ivf=torch.zeros(1, dtype=torch.int32), ivf_lengths=torch.zeros(C, dtype=torch.int64), nbits=2)
+    S = torch.randn(C, nq, generator=gen)
+    Sr = S.half().float()
+    pids = torch.randperm(doclens.numel(), generator=gen).to(torch.int32)
+    a = ops.approx_scores(pids, S, ix.codes, ix.offsets, None, table_f16=True)
+    assert torch.equal(a.cpu(), po.approx_scores(ix, pids, Sr, None))
+    idx = Sr.max(-1).values >= 1.2                     # a sparse pruning mask: many tokens without a surviving centroid
+    a = ops.approx_scores(pids, S, ix.codes, ix.offsets, idx, table_f16=True)
+    assert torch.equal(a.cpu(), po.approx_scores(ix, pids, Sr, idx))
+
+
 def test_select_top_order_and_ties(P):
     _, ops = P
     g = torch.Generator().manual_seed(9)
