@@ -237,10 +237,94 @@ __device__ __forceinline__ uint64_t make_key(float score, int32_t pid) {
     return ((uint64_t)float_to_ordered(score) << 32) | (uint32_t)pid;
 }
 
-// Block-wide: among keys[0..n) pick the `keep` largest into s_sel (sorted descending), return count.
+// Key sources of the select: a key array in global memory (merge_topk compacts G lists into one), or the (score, pid)
+// arrays themselves -- a key is 8 bytes either way, so select_top builds keys on the fly instead of writing a key array
+// and reading it back on every pass (its key-building pass was 16 % of select1 on cfg2).
+struct KeyArray {
+    const uint64_t* __restrict__ k;
+    __device__ __forceinline__ uint64_t operator()(int i) const { return k[i]; }
+};
+struct ScorePidKeys {
+    const float* __restrict__ s;
+    const int32_t* __restrict__ p;
+    __device__ __forceinline__ uint64_t operator()(int i) const { return make_key(s[i], p[i]); }
+};
+
+// Block-strided walk over n keys.  (Measured and rejected on cfg2: 4 / 8 independent loads in flight per thread -- 0.23 /
+// 0.30 ms vs 0.23; warp-aggregating the histogram atomics with __match_any_sync -- 0.42 ms: same-address shared atomics
+// are not what bounds the passes.)
+template <typename L, typename F>
+__device__ __forceinline__ void for_each_key(const L& load, int n, F f) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) f(load(i));
+}
+
+static constexpr int kRankMax = 256;   // buckets up to this size are finished by rank counting instead of more radix passes
+
+// Descending bitonic sort of s_sel[0..sel_cap) (sel_cap a power of two).  Compare-exchange steps with a partner inside the
+// warp (stride < 32) run on registers through shuffles, so only strides >= 32 cost a shared-memory round and a barrier
+// (sel_cap = 1024: 21 barriers instead of 55).
+__device__ void bitonic_sort_desc(uint64_t* s_sel, int sel_cap) {
+    const int tid = threadIdx.x;
+    if (sel_cap < 32) {
+        for (int size = 2; size <= sel_cap; size <<= 1) {
+            for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                for (int t = tid; t < (sel_cap >> 1); t += blockDim.x) {
+                    const int lo = 2 * t - (t & (stride - 1));
+                    const int hi = lo + stride;
+                    const bool desc = ((lo & size) == 0);
+                    const uint64_t a = s_sel[lo], c = s_sel[hi];
+                    if ((a < c) == desc) { s_sel[lo] = c; s_sel[hi] = a; }
+                }
+                __syncthreads();
+            }
+        }
+        return;
+    }
+    // whole warps are in or out of every loop below: sel_cap and blockDim.x are multiples of 32
+    for (int idx = tid; idx < sel_cap; idx += blockDim.x) {          // sizes 2..32 entirely inside a warp
+        uint64_t v = s_sel[idx];
+#pragma unroll
+        for (int size = 2; size <= 32; size <<= 1) {
+#pragma unroll
+            for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                const uint64_t o = __shfl_xor_sync(0xffffffffu, v, stride);
+                const bool want_max = ((idx & stride) == 0) == ((idx & size) == 0);
+                v = want_max ? (v > o ? v : o) : (v < o ? v : o);
+            }
+        }
+        s_sel[idx] = v;
+    }
+    __syncthreads();
+    for (int size = 64; size <= sel_cap; size <<= 1) {
+        for (int stride = size >> 1; stride >= 32; stride >>= 1) {
+            for (int t = tid; t < (sel_cap >> 1); t += blockDim.x) {
+                const int lo = 2 * t - (t & (stride - 1));
+                const int hi = lo + stride;
+                const bool desc = ((lo & size) == 0);
+                const uint64_t a = s_sel[lo], c = s_sel[hi];
+                if ((a < c) == desc) { s_sel[lo] = c; s_sel[hi] = a; }
+            }
+            __syncthreads();
+        }
+        for (int idx = tid; idx < sel_cap; idx += blockDim.x) {
+            uint64_t v = s_sel[idx];
+            const bool desc = (idx & size) == 0;
+#pragma unroll
+            for (int stride = 16; stride > 0; stride >>= 1) {
+                const uint64_t o = __shfl_xor_sync(0xffffffffu, v, stride);
+                const bool want_max = ((idx & stride) == 0) == desc;
+                v = want_max ? (v > o ? v : o) : (v < o ? v : o);
+            }
+            s_sel[idx] = v;
+        }
+        __syncthreads();
+    }
+}
+
+// Block-wide: among the n keys of `load` pick the `keep` largest into s_sel (sorted descending), return count.
 // s_sel has room for sel_cap = next_pow2(keep) keys; s_hist is 256 ints; s_misc 4 ints.
-__device__ int select_sorted_desc(const uint64_t* __restrict__ keys, int n, int keep, uint64_t* s_sel, int sel_cap,
-                                  int* s_hist, int* s_misc) {
+template <typename L>
+__device__ int select_sorted_desc(const L& load, int n, int keep, uint64_t* s_sel, int sel_cap, int* s_hist, int* s_misc) {
     const int tid = threadIdx.x;
     const int m = min(n, keep);
     uint64_t thresh = 0;  // with n <= keep every key is selected
@@ -251,30 +335,19 @@ __device__ int select_sorted_desc(const uint64_t* __restrict__ keys, int n, int 
         int remaining = keep;  // rank (1-based, from the top) still to be located inside the prefix group
         // Once the bucket that holds the keep-th key fits s_sel (idle until the selection below), its members are
         // collected there and the remaining passes read shared memory instead of walking all n keys in L2 again
-        // (stage-1 scores tie heavily in fp32, so the select otherwise runs all 8 passes over the full list).
-        // (select1 on cfg2: 0.30 -> 0.24 ms per 1024 queries.)
-        const uint64_t* src = keys;
+        // (stage-1 scores tie heavily in fp32, so the select otherwise runs all 8 passes over the full list;
+        // select1 on cfg2: 0.30 -> 0.24 ms per 1024 queries).
+        bool in_smem = false;
         int src_n = n;
+        bool ranked = false;
         for (int shift = 56; shift >= 0; shift -= 8) {
             for (int i = tid; i < 256; i += blockDim.x) s_hist[i] = 0;
             __syncthreads();
-#ifdef PLAID_SELECT_WARP_AGG
-            // tied scores put most keys of a pass into ONE bin: lanes with equal bins elect a leader that adds their
-            // count (a 32-way same-address shared atomic serialises).  Trip count is block-uniform for the full-mask match.
-            for (int base = 0; base < src_n; base += blockDim.x) {
-                const int i = base + tid;
-                const uint64_t k = i < src_n ? src[i] : 0;
-                const bool ok = i < src_n && (k & prefix_mask) == prefix;
-                const unsigned bin = ok ? (unsigned)((k >> shift) & 0xff) : 256u + (tid & 31);
-                const unsigned peers = __match_any_sync(0xffffffffu, bin);
-                if (ok && (tid & 31) == __ffs(peers) - 1) atomicAdd(&s_hist[bin], __popc(peers));
-            }
-#else
-            for (int i = tid; i < src_n; i += blockDim.x) {
-                const uint64_t k = src[i];
+            auto count = [&](uint64_t k) {
                 if ((k & prefix_mask) == prefix) atomicAdd(&s_hist[(int)((k >> shift) & 0xff)], 1);
-            }
-#endif
+            };
+            if (in_smem) for_each_key(KeyArray{s_sel}, src_n, count);
+            else for_each_key(load, n, count);
             __syncthreads();
             if (tid < 32) {
                 // bucket of the `remaining`-th largest key: warp-parallel scan of the 256 bins from the top
@@ -311,31 +384,61 @@ __device__ int select_sorted_desc(const uint64_t* __restrict__ keys, int n, int 
                 remaining = 0;
                 break;
             }
-            if (src == keys && shift > 0 && bucket <= sel_cap && 2 * bucket <= n) {
+            if (shift == 0) break;
+            if (!in_smem && bucket <= sel_cap && 2 * bucket <= n) {
                 if (tid == 0) s_misc[2] = 0;
                 __syncthreads();
-#ifdef PLAID_SELECT_WARP_AGG
-                for (int base = 0; base < n; base += blockDim.x) {
-                    const int i = base + tid;
-                    const uint64_t k = i < n ? keys[i] : 0;
-                    const bool ok = i < n && (k & prefix_mask) == prefix;
-                    const unsigned peers = __ballot_sync(0xffffffffu, ok);
-                    int slot0 = 0;
-                    if (peers && (tid & 31) == __ffs(peers) - 1) slot0 = atomicAdd(&s_misc[2], __popc(peers));
-                    slot0 = __shfl_sync(0xffffffffu, slot0, peers ? __ffs(peers) - 1 : 0);
-                    if (ok) s_sel[slot0 + __popc(peers & ((1u << (tid & 31)) - 1))] = k;     // exactly `bucket` keys match
-                }
-#else
-                for (int i = tid; i < n; i += blockDim.x) {
-                    const uint64_t k = keys[i];
+                for_each_key(load, n, [&](uint64_t k) {
                     if ((k & prefix_mask) == prefix) s_sel[atomicAdd(&s_misc[2], 1)] = k;   // exactly `bucket` keys match
-                }
-#endif
+                });
                 __syncthreads();
-                src = s_sel;
+                in_smem = true;
                 src_n = bucket;
+            } else if (in_smem && bucket <= kRankMax) {
+                // the list in s_sel still holds keys outside the bucket: squeeze them out (in place, via registers)
+                uint64_t mine[(4096 + kSelThreads - 1) / kSelThreads];      // src_n <= sel_cap; lists > 4096 keep radix passes
+                if (src_n <= 4096) {
+                    if (tid == 0) s_misc[2] = 0;
+#pragma unroll
+                    for (int j = 0; j < (4096 + kSelThreads - 1) / kSelThreads; j++) {
+                        const int i = tid + j * kSelThreads;
+                        mine[j] = i < src_n ? s_sel[i] : 0;
+                    }
+                    __syncthreads();
+#pragma unroll
+                    for (int j = 0; j < (4096 + kSelThreads - 1) / kSelThreads; j++) {
+                        const int i = tid + j * kSelThreads;
+                        if (i < src_n && (mine[j] & prefix_mask) == prefix) s_sel[atomicAdd(&s_misc[2], 1)] = mine[j];
+                    }
+                    __syncthreads();
+                    src_n = bucket;
+                }
+            }
+            if (in_smem && src_n == bucket && bucket <= kRankMax) {
+                // s_sel[0..bucket) is exactly the bucket: the wanted key is the one with `remaining - 1` greater keys in it
+                if (tid < bucket) {
+                    const uint64_t my = s_sel[tid];
+                    int greater = 0, equal = 0;
+                    for (int j = 0; j < bucket; j++) {
+                        const uint64_t o = s_sel[j];
+                        greater += o > my;
+                        equal += o == my;
+                    }
+                    if (greater < remaining && greater + equal >= remaining) {   // duplicates all write the same values
+                        s_misc[0] = (int)(uint32_t)(my >> 32);
+                        s_misc[1] = (int)(uint32_t)my;
+                        s_misc[3] = remaining - greater;
+                    }
+                }
+                __syncthreads();
+                prefix = ((uint64_t)(uint32_t)s_misc[0] << 32) | (uint32_t)s_misc[1];
+                remaining = s_misc[3];
+                ranked = true;
+                __syncthreads();
+                break;
             }
         }
+        (void)ranked;
         thresh = prefix;              // the keep-th largest key, or (early exit) the smallest key value of its bucket
         n_greater_needed = remaining; // how many copies of `thresh` itself belong to the selection (0 after an early exit)
         if (remaining == 0) {         // every key >= thresh is selected: exactly `keep` of them
@@ -345,45 +448,18 @@ __device__ int select_sorted_desc(const uint64_t* __restrict__ keys, int n, int 
     for (int i = tid; i < sel_cap; i += blockDim.x) s_sel[i] = 0;
     if (tid == 0) { s_misc[2] = 0; s_misc[3] = 0; }
     __syncthreads();
-#ifdef PLAID_SELECT_WARP_AGG
-    for (int base = 0; base < n; base += blockDim.x) {
-        const int i = base + tid;
-        const uint64_t k = i < n ? keys[i] : 0;
-        bool take = i < n && ((n <= keep) || (k > thresh));
-        if (i < n && !take && k == thresh) take = atomicAdd(&s_misc[3], 1) < n_greater_needed;
-        const unsigned peers = __ballot_sync(0xffffffffu, take);
-        int slot0 = 0;
-        if (peers && (tid & 31) == __ffs(peers) - 1) slot0 = atomicAdd(&s_misc[2], __popc(peers));
-        slot0 = __shfl_sync(0xffffffffu, slot0, peers ? __ffs(peers) - 1 : 0);
-        const int slot = slot0 + __popc(peers & ((1u << (tid & 31)) - 1));
-        if (take && slot < sel_cap) s_sel[slot] = k;
-    }
-#else
-    for (int i = tid; i < n; i += blockDim.x) {
-        const uint64_t k = keys[i];
+    for_each_key(load, n, [&](uint64_t k) {
         bool take = (n <= keep) || (k > thresh);
         if (!take && k == thresh) take = atomicAdd(&s_misc[3], 1) < n_greater_needed;
         if (take) {
             const int slot = atomicAdd(&s_misc[2], 1);
             if (slot < sel_cap) s_sel[slot] = k;
         }
-    }
-#endif
+    });
     __syncthreads();
-    // bitonic sort, descending (zero padding sinks to the end; real keys are > 0 because the
-    // ordered-float transform never yields 0 in the high word for non-NaN scores)
-    for (int size = 2; size <= sel_cap; size <<= 1) {
-        for (int stride = size >> 1; stride > 0; stride >>= 1) {
-            for (int t = tid; t < (sel_cap >> 1); t += blockDim.x) {
-                const int lo = 2 * t - (t & (stride - 1));
-                const int hi = lo + stride;
-                const bool desc = ((lo & size) == 0);
-                const uint64_t a = s_sel[lo], c = s_sel[hi];
-                if ((a < c) == desc) { s_sel[lo] = c; s_sel[hi] = a; }
-            }
-            __syncthreads();
-        }
-    }
+    // descending (zero padding sinks to the end; real keys are > 0 because the ordered-float transform never yields 0
+    // in the high word for non-NaN scores)
+    bitonic_sort_desc(s_sel, sel_cap);
     return m;
 }
 
@@ -412,11 +488,9 @@ select_top_kernel(const int32_t* __restrict__ pids, const float* __restrict__ sc
     int* s_misc = s_hist + 256;
     const int b = blockIdx.x;
     const int n = min(counts[b], in_stride);
-    uint64_t* keys = ws_keys + (size_t)b * in_stride;
-    for (int i = threadIdx.x; i < n; i += blockDim.x)
-        keys[i] = make_key(scores[(size_t)b * in_stride + i], pids[(size_t)b * in_stride + i]);
-    __syncthreads();
-    const int m = select_sorted_desc(keys, n, keep, s_sel, sel_cap, s_hist, s_misc);
+    (void)ws_keys;    // keys are built on the fly from (score, pid); the workspace argument stays in the ABI
+    const ScorePidKeys load{scores + (size_t)b * in_stride, pids + (size_t)b * in_stride};
+    const int m = select_sorted_desc(load, n, keep, s_sel, sel_cap, s_hist, s_misc);
     write_selection(s_sel, m, out_stride, out_pids + (size_t)b * out_stride,
                     out_scores ? out_scores + (size_t)b * out_stride : nullptr, out_counts ? out_counts + b : nullptr);
 }
@@ -452,7 +526,7 @@ merge_topk_kernel(const float* __restrict__ scores, const int32_t* __restrict__ 
         }
     }
     __syncthreads();
-    const int m = select_sorted_desc(keys, n, k, s_sel, sel_cap, s_hist, s_misc);
+    const int m = select_sorted_desc(KeyArray{keys}, n, k, s_sel, sel_cap, s_hist, s_misc);
     write_selection(s_sel, m, k, out_pids + (size_t)b * k, out_scores + (size_t)b * k, out_counts ? out_counts + b : nullptr);
 }
 

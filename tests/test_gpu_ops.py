@@ -147,6 +147,16 @@ def test_select_top_order_and_ties(P):
         op, os_ = ops.select_top(pids, scores, keep)
         rp, rs = po.select_top(pids, scores, keep)
         assert torch.equal(op.cpu(), rp) and torch.equal(os_.cpu(), rs)
+    # longer lists: the bucket of the keep-th key is collected into shared memory, narrowed there by further radix
+    # passes, squeezed and finished by rank counting (tied scores push the decision into the pid bytes)
+    n = 20000
+    for levels, scale in ((40, 0.25), (3, 1.0), (20000, 1e-3)):
+        scores = torch.randint(0, levels, (n,), generator=g).float() * scale - 3.0
+        pids = torch.randperm(1 << 17, generator=g)[:n].to(torch.int32)
+        for keep in (100, 1024, 4096, 8192, 16384):
+            op, os_ = ops.select_top(pids, scores, keep)
+            rp, rs = po.select_top(pids, scores, keep)
+            assert torch.equal(op.cpu(), rp) and torch.equal(os_.cpu(), rs), (levels, keep)
 
 
 def test_segmented_maxsim_and_lookup(P, golden):
