@@ -321,32 +321,37 @@ __device__ void bitonic_sort_desc(uint64_t* s_sel, int sel_cap) {
     }
 }
 
+static constexpr int kBktCap = 2048;   // largest bucket (of the keep-th key) that is collected into shared memory
+
 // Block-wide: among the n keys of `load` pick the `keep` largest into s_sel (sorted descending), return count.
-// s_sel has room for sel_cap = next_pow2(keep) keys; s_hist is 256 ints; s_misc 4 ints.
+// s_sel has room for sel_cap = next_pow2(keep) keys, s_bkt for kBktCap + kRankMax; s_hist is 256 ints; s_misc 4 ints.
+//
+// MSB-first radix select of the keep-th largest key.  As soon as the bucket that holds it has at most kBktCap members, ONE
+// more walk over the keys finishes the global part: keys above the bucket are selected for certain and go straight to
+// s_sel, the bucket's members go to s_bkt, where the remaining digits are resolved from shared memory (radix passes,
+// then rank counting once <= kRankMax keys are left) and its top `remaining` keys are appended.  Stage-1 scores tie
+// heavily in fp32, so the plain select ran all 8 passes plus the selection walk over the full list (select1 on cfg2:
+// 0.30 ms per 1024 queries; 0.24 with the bucket in shared memory; this layout saves the separate selection walk).
 template <typename L>
-__device__ int select_sorted_desc(const L& load, int n, int keep, uint64_t* s_sel, int sel_cap, int* s_hist, int* s_misc) {
+__device__ int select_sorted_desc(const L& load, int n, int keep, uint64_t* s_sel, int sel_cap, uint64_t* s_bkt,
+                                  int* s_hist, int* s_misc) {
     const int tid = threadIdx.x;
     const int m = min(n, keep);
+    uint64_t* s_rank = s_bkt + kBktCap;
     uint64_t thresh = 0;  // with n <= keep every key is selected
     int n_greater_needed = m;
+    bool collected = false;   // s_bkt[0..list_n) = the bucket at collection time, s_sel[0..sure) = the keys above it
+    int list_n = 0, sure = 0;
     if (n > keep) {
-        // MSB-first radix select of the keep-th largest key.
         uint64_t prefix = 0, prefix_mask = 0;
         int remaining = keep;  // rank (1-based, from the top) still to be located inside the prefix group
-        // Once the bucket that holds the keep-th key fits s_sel (idle until the selection below), its members are
-        // collected there and the remaining passes read shared memory instead of walking all n keys in L2 again
-        // (stage-1 scores tie heavily in fp32, so the select otherwise runs all 8 passes over the full list;
-        // select1 on cfg2: 0.30 -> 0.24 ms per 1024 queries).
-        bool in_smem = false;
-        int src_n = n;
-        bool ranked = false;
         for (int shift = 56; shift >= 0; shift -= 8) {
             for (int i = tid; i < 256; i += blockDim.x) s_hist[i] = 0;
             __syncthreads();
             auto count = [&](uint64_t k) {
                 if ((k & prefix_mask) == prefix) atomicAdd(&s_hist[(int)((k >> shift) & 0xff)], 1);
             };
-            if (in_smem) for_each_key(KeyArray{s_sel}, src_n, count);
+            if (collected) for_each_key(KeyArray{s_bkt}, list_n, count);
             else for_each_key(load, n, count);
             __syncthreads();
             if (tid < 32) {
@@ -380,47 +385,42 @@ __device__ int select_sorted_desc(const L& load, int n, int keep, uint64_t* s_se
             remaining = s_misc[1];
             const int bucket = s_misc[3];
             __syncthreads();
+            if (!collected && bucket <= kBktCap) {
+                // the last walk over all keys: certain keys -> s_sel, bucket -> s_bkt
+                if (tid == 0) { s_misc[2] = 0; s_misc[3] = 0; }
+                __syncthreads();
+                for_each_key(load, n, [&](uint64_t k) {
+                    const uint64_t hi = k & prefix_mask;
+                    if (hi > prefix) {
+                        const int slot = atomicAdd(&s_misc[2], 1);
+                        if (slot < sel_cap) s_sel[slot] = k;
+                    } else if (hi == prefix) {
+                        s_bkt[atomicAdd(&s_misc[3], 1)] = k;                   // exactly `bucket` keys match
+                    }
+                });
+                __syncthreads();
+                collected = true;
+                list_n = bucket;
+                sure = keep - remaining;      // == s_misc[2]: the keys above the bucket
+            }
             if (bucket == remaining) {     // the whole bucket belongs to the selection: no need to split it further
                 remaining = 0;
                 break;
             }
             if (shift == 0) break;
-            if (!in_smem && bucket <= sel_cap && 2 * bucket <= n) {
+            if (collected && bucket <= kRankMax) {
+                // copy the (narrowed) bucket out of the list; the wanted key is the one with `remaining - 1` greater keys in it
                 if (tid == 0) s_misc[2] = 0;
                 __syncthreads();
-                for_each_key(load, n, [&](uint64_t k) {
-                    if ((k & prefix_mask) == prefix) s_sel[atomicAdd(&s_misc[2], 1)] = k;   // exactly `bucket` keys match
+                for_each_key(KeyArray{s_bkt}, list_n, [&](uint64_t k) {
+                    if ((k & prefix_mask) == prefix) s_rank[atomicAdd(&s_misc[2], 1)] = k;
                 });
                 __syncthreads();
-                in_smem = true;
-                src_n = bucket;
-            } else if (in_smem && bucket <= kRankMax) {
-                // the list in s_sel still holds keys outside the bucket: squeeze them out (in place, via registers)
-                uint64_t mine[(4096 + kSelThreads - 1) / kSelThreads];      // src_n <= sel_cap; lists > 4096 keep radix passes
-                if (src_n <= 4096) {
-                    if (tid == 0) s_misc[2] = 0;
-#pragma unroll
-                    for (int j = 0; j < (4096 + kSelThreads - 1) / kSelThreads; j++) {
-                        const int i = tid + j * kSelThreads;
-                        mine[j] = i < src_n ? s_sel[i] : 0;
-                    }
-                    __syncthreads();
-#pragma unroll
-                    for (int j = 0; j < (4096 + kSelThreads - 1) / kSelThreads; j++) {
-                        const int i = tid + j * kSelThreads;
-                        if (i < src_n && (mine[j] & prefix_mask) == prefix) s_sel[atomicAdd(&s_misc[2], 1)] = mine[j];
-                    }
-                    __syncthreads();
-                    src_n = bucket;
-                }
-            }
-            if (in_smem && src_n == bucket && bucket <= kRankMax) {
-                // s_sel[0..bucket) is exactly the bucket: the wanted key is the one with `remaining - 1` greater keys in it
                 if (tid < bucket) {
-                    const uint64_t my = s_sel[tid];
+                    const uint64_t my = s_rank[tid];
                     int greater = 0, equal = 0;
                     for (int j = 0; j < bucket; j++) {
-                        const uint64_t o = s_sel[j];
+                        const uint64_t o = s_rank[j];
                         greater += o > my;
                         equal += o == my;
                     }
@@ -433,29 +433,29 @@ __device__ int select_sorted_desc(const L& load, int n, int keep, uint64_t* s_se
                 __syncthreads();
                 prefix = ((uint64_t)(uint32_t)s_misc[0] << 32) | (uint32_t)s_misc[1];
                 remaining = s_misc[3];
-                ranked = true;
                 __syncthreads();
                 break;
             }
         }
-        (void)ranked;
         thresh = prefix;              // the keep-th largest key, or (early exit) the smallest key value of its bucket
         n_greater_needed = remaining; // how many copies of `thresh` itself belong to the selection (0 after an early exit)
         if (remaining == 0) {         // every key >= thresh is selected: exactly `keep` of them
             thresh -= 1;              // (prefix > 0 here: bucket 0 of the first pass taken whole would mean n == keep)
         }
     }
-    for (int i = tid; i < sel_cap; i += blockDim.x) s_sel[i] = 0;
-    if (tid == 0) { s_misc[2] = 0; s_misc[3] = 0; }
+    for (int i = tid + sure; i < sel_cap; i += blockDim.x) s_sel[i] = 0;
+    if (tid == 0) { s_misc[2] = sure; s_misc[3] = 0; }
     __syncthreads();
-    for_each_key(load, n, [&](uint64_t k) {
+    auto select = [&](uint64_t k) {
         bool take = (n <= keep) || (k > thresh);
         if (!take && k == thresh) take = atomicAdd(&s_misc[3], 1) < n_greater_needed;
         if (take) {
             const int slot = atomicAdd(&s_misc[2], 1);
             if (slot < sel_cap) s_sel[slot] = k;
         }
-    });
+    };
+    if (collected) for_each_key(KeyArray{s_bkt}, list_n, select);
+    else for_each_key(load, n, select);
     __syncthreads();
     // descending (zero padding sinks to the end; real keys are > 0 because the ordered-float transform never yields 0
     // in the high word for non-NaN scores)
@@ -484,13 +484,14 @@ select_top_kernel(const int32_t* __restrict__ pids, const float* __restrict__ sc
                   int32_t* __restrict__ out_counts, int out_stride, uint64_t* __restrict__ ws_keys) {
     extern __shared__ __align__(16) unsigned char s_raw[];
     uint64_t* s_sel = reinterpret_cast<uint64_t*>(s_raw);
-    int* s_hist = reinterpret_cast<int*>(s_sel + sel_cap);
+    uint64_t* s_bkt = s_sel + sel_cap;
+    int* s_hist = reinterpret_cast<int*>(s_bkt + kBktCap + kRankMax);
     int* s_misc = s_hist + 256;
     const int b = blockIdx.x;
     const int n = min(counts[b], in_stride);
     (void)ws_keys;    // keys are built on the fly from (score, pid); the workspace argument stays in the ABI
     const ScorePidKeys load{scores + (size_t)b * in_stride, pids + (size_t)b * in_stride};
-    const int m = select_sorted_desc(load, n, keep, s_sel, sel_cap, s_hist, s_misc);
+    const int m = select_sorted_desc(load, n, keep, s_sel, sel_cap, s_bkt, s_hist, s_misc);
     write_selection(s_sel, m, out_stride, out_pids + (size_t)b * out_stride,
                     out_scores ? out_scores + (size_t)b * out_stride : nullptr, out_counts ? out_counts + b : nullptr);
 }
@@ -502,7 +503,8 @@ merge_topk_kernel(const float* __restrict__ scores, const int32_t* __restrict__ 
                   int32_t* __restrict__ out_counts, uint64_t* __restrict__ ws_keys) {
     extern __shared__ __align__(16) unsigned char s_raw[];
     uint64_t* s_sel = reinterpret_cast<uint64_t*>(s_raw);
-    int* s_hist = reinterpret_cast<int*>(s_sel + sel_cap);
+    uint64_t* s_bkt = s_sel + sel_cap;
+    int* s_hist = reinterpret_cast<int*>(s_bkt + kBktCap + kRankMax);
     int* s_misc = s_hist + 256;
     const int b = blockIdx.x;
     uint64_t* keys = ws_keys + (size_t)b * G * k;
@@ -526,7 +528,7 @@ merge_topk_kernel(const float* __restrict__ scores, const int32_t* __restrict__ 
         }
     }
     __syncthreads();
-    const int m = select_sorted_desc(KeyArray{keys}, n, k, s_sel, sel_cap, s_hist, s_misc);
+    const int m = select_sorted_desc(KeyArray{keys}, n, k, s_sel, sel_cap, s_bkt, s_hist, s_misc);
     write_selection(s_sel, m, k, out_pids + (size_t)b * k, out_scores + (size_t)b * k, out_counts ? out_counts + b : nullptr);
 }
 
@@ -872,7 +874,7 @@ static int launch_select(const int32_t* pids, const float* scores, const int32_t
     PLAID_CHECK_ARG(keep >= 1 && keep <= 16384, PLAID_ERR_UNSUPPORTED, "select_top: keep=%d outside [1, 16384]", keep);
     PLAID_CHECK_ARG(out_stride >= keep, PLAID_ERR_ARG, "select_top: out_stride=%d < keep=%d", out_stride, keep);
     const int sel_cap = next_pow2(keep < 2 ? 2 : keep);
-    const size_t smem = (size_t)sel_cap * 8 + 256 * 4 + 16;
+    const size_t smem = (size_t)(sel_cap + kBktCap + kRankMax) * 8 + 256 * 4 + 16;
     static size_t configured = 0;
     if (smem > 48 * 1024 && smem > configured) {
         PLAID_CUDA_OK(cudaFuncSetAttribute(select_top_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1006,7 +1008,7 @@ extern "C" int plaid_merge_topk(const float* scores, const int32_t* pids, const 
                     "plaid_merge_topk: G=%d (1..64), k=%d (1..16384)", G, k);
     if (B == 0) return PLAID_OK;
     const int sel_cap = next_pow2(k < 2 ? 2 : k);
-    const size_t smem = (size_t)sel_cap * 8 + 256 * 4 + 16;
+    const size_t smem = (size_t)(sel_cap + kBktCap + kRankMax) * 8 + 256 * 4 + 16;
     static size_t configured = 0;
     if (smem > 48 * 1024 && smem > configured) {
         PLAID_CUDA_OK(cudaFuncSetAttribute(merge_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
