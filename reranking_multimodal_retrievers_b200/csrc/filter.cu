@@ -243,11 +243,13 @@ __device__ __forceinline__ uint64_t make_key(float score, int32_t pid) {
 struct KeyArray {
     const uint64_t* __restrict__ k;
     __device__ __forceinline__ uint64_t operator()(int i) const { return k[i]; }
+    __device__ __forceinline__ uint32_t hi(int i) const { return reinterpret_cast<const uint32_t*>(k)[2 * i + 1]; }
 };
 struct ScorePidKeys {
     const float* __restrict__ s;
     const int32_t* __restrict__ p;
     __device__ __forceinline__ uint64_t operator()(int i) const { return make_key(s[i], p[i]); }
+    __device__ __forceinline__ uint32_t hi(int i) const { return float_to_ordered(s[i]); }
 };
 
 // Block-strided walk over n keys.  (Measured and rejected on cfg2: 4 / 8 independent loads in flight per thread -- 0.23 /
@@ -351,8 +353,19 @@ __device__ int select_sorted_desc(const L& load, int n, int keep, uint64_t* s_se
             auto count = [&](uint64_t k) {
                 if ((k & prefix_mask) == prefix) atomicAdd(&s_hist[(int)((k >> shift) & 0xff)], 1);
             };
-            if (collected) for_each_key(KeyArray{s_bkt}, list_n, count);
-            else for_each_key(load, n, count);
+            if (collected) {
+                for_each_key(KeyArray{s_bkt}, list_n, count);
+            } else if (shift >= 32) {
+                // digits of the score word: the walk over all keys reads only the scores and works on 32 bits
+                const uint32_t p_hi = (uint32_t)(prefix >> 32), m_hi = (uint32_t)(prefix_mask >> 32);
+                const int sh = shift - 32;
+                for (int i = tid; i < n; i += blockDim.x) {
+                    const uint32_t h = load.hi(i);
+                    if ((h & m_hi) == p_hi) atomicAdd(&s_hist[(int)((h >> sh) & 0xff)], 1);
+                }
+            } else {
+                for_each_key(load, n, count);
+            }
             __syncthreads();
             if (tid < 32) {
                 // bucket of the `remaining`-th largest key: warp-parallel scan of the 256 bins from the top
