@@ -231,7 +231,10 @@ approx_scores_kernel(const int32_t* __restrict__ pids, const int32_t* __restrict
 }
 
 // ------------------------------------------------------------------------------------------ select
-static constexpr int kSelThreads = 1024;
+#ifndef PLAID_SEL_THREADS
+#define PLAID_SEL_THREADS 512
+#endif
+static constexpr int kSelThreads = PLAID_SEL_THREADS;
 
 __device__ __forceinline__ uint64_t make_key(float score, int32_t pid) {
     return ((uint64_t)float_to_ordered(score) << 32) | (uint32_t)pid;
