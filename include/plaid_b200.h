@@ -117,7 +117,8 @@ int plaid_filter_stage1_ivf(const int32_t* pids, const int32_t* counts, int B, i
 /* Per query the `keep` largest (score, pid) pairs in descending (score, pid) order -- the order of
  * std::pair<float,int> in filter_pids.cpp:24,108-123.  Emits min(counts[b], keep) entries
  * (the rule of the reference's GPU branch, index_storage.py:138-139; the C++ pops an empty heap).
- * Unused output slots get PLAID_NO_PID / -inf.  ws_keys: u64 workspace [B, in_stride]. */
+ * Unused output slots get PLAID_NO_PID / -inf.  ws_keys: u64 workspace [B, in_stride]; kept in the ABI and must be
+ * non-null, but no longer touched (keys are built on the fly from scores and pids). */
 int plaid_select_top(const int32_t* pids, const float* scores, const int32_t* counts, int B, int in_stride,
                      int keep, int32_t* out_pids, float* out_scores, int32_t* out_counts, int out_stride,
                      uint64_t* ws_keys, void* stream);
