@@ -153,6 +153,15 @@ int plaid_unpack_residual_codes(const uint8_t* residuals, int64_t ntokens, int n
                                 const uint8_t* reversed_bit_map, const uint8_t* lookup, uint8_t* out,
                                 void* stream);
 
+/* The operator the reference binds as ResidualCodec.decompress_residuals on its GPU branch
+ * (CB/indexing/codecs/residual.py:115,242-263; codecs/decompress_residuals.cu:8-75): token rows, no pid indirection.
+ * out[t, d] = half(W[residuals[t, byte]][l]) + centroids_f16[codes[t], d] -- one half add, bit-exact with the
+ * reference kernel -- as fp16 [n, 128].  normalize != 0 applies ResidualCodec.decompress's
+ * `F.normalize(x, p=2, dim=-1).half()` on top (residual.py:272-273).  W is plaid_build_weight_table's table. */
+int plaid_decompress_tokens_f16(const uint8_t* residuals, const int32_t* codes, int64_t n, const float* W,
+                                const void* centroids_f16, int C, int nbits, int normalize, void* out_f16,
+                                void* stream);
+
 /* Exclusive per-query prefix sums of the passage lengths of pids [B, pid_stride] (counts[b] valid), each
  * length rounded up to a multiple of `align` tokens (1 = packed back to back; 32 = the layout
  * plaid_maxsim_packed's aligned mode reads): tok_offsets [B, pid_stride+1] (i32, local to the query). */
@@ -196,6 +205,10 @@ int plaid_merge_cells(const float* cell_val, const int32_t* cell_idx, const int3
 int plaid_compress_residuals(const float* embs, const int32_t* codes, const void* centroids_f16,
                              const float* bucket_cutoffs, int64_t n, int C, int nbits, uint8_t* residuals,
                              int* bad_code_flag, void* stream);
+
+/* ResidualCodec.packbits (residual.py:130, codecs/packbits.cu:10-57): nflags u8 flags (non-zero = 1; nflags a
+ * multiple of 8, 8-byte aligned) -> nflags/8 bytes, first flag in the most significant bit (np.packbits order). */
+int plaid_packbits(const uint8_t* bits, int64_t nflags, uint8_t* packed, void* stream);
 
 /* ---- a8: colbert_score_packed + segmented_maxsim (CB/modeling/colbert.py:289-311,
  *          CB/modeling/segmented_maxsim.cpp:22-93) ---------------------------------------------

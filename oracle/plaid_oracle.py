@@ -306,3 +306,26 @@ def codec_compress(centroids_f16: torch.Tensor, bucket_cutoffs: torch.Tensor, nb
         codes = codec_compress_into_codes(cent, embs)
     res = embs.float() - cent[codes.long()]
     return codes, codec_binarize(res, bucket_cutoffs, nbits)
+
+
+def codec_decompress_gpu_form(bucket_weights, reversed_bit_map, lookup, binary_residuals, codes, centroids_f16,
+                              normalize: bool = False):
+    """Restatement of the reference's GPU-branch operator ResidualCodec.decompress_residuals
+    (CB/indexing/codecs/decompress_residuals.cu:8-75): per element `out = half(bucket_weight); out += half(centroid)`,
+    i.e. ONE half add (computed here as the fp32 sum of the two halves rounded to half: exact for |x| < 2, which
+    unit-norm centroids plus residual weights satisfy).  normalize=True adds ResidualCodec.decompress's
+    `F.normalize(x, p=2, dim=-1).half()` (residual.py:272-273) with torch's own CPU half kernels.
+    PARITY UNPINNED against the reference kernel itself (it needs a GPU the authoring container does not have);
+    pinned indirectly: the fp32 CPU operator on the same bytes (golden D_0) differs by one half rounding."""
+    w = bucket_weights.half()[lookup[reversed_bit_map[binary_residuals.long()].long()].long()]
+    w = w.reshape(binary_residuals.shape[0], -1)
+    out = (w.float() + centroids_f16.half()[codes.long()].float()).half()
+    if normalize:
+        out = torch.nn.functional.normalize(out.float(), p=2, dim=-1).half()
+    return out
+
+
+def codec_packbits(flags: torch.Tensor) -> torch.Tensor:
+    """ResidualCodec.packbits: the CPU branch's np.packbits (residual.py:200), which packbits.cu:10-57 reproduces
+    (ballot over 32 flags, bit-reversed, bytes emitted most significant first)."""
+    return torch.as_tensor(np.packbits(np.asarray(flags.contiguous().flatten().ne(0).to(torch.uint8))), dtype=torch.uint8)

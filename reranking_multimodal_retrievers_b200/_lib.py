@@ -36,6 +36,8 @@ _SIGNATURES = {
     "plaid_build_weight_table": [_P, _P, _P, _I, _P, _P],
     "plaid_decompress_residuals": [_P, _I, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P],
     "plaid_unpack_residual_codes": [_P, _I64, _I, _P, _P, _P, _P],
+    "plaid_decompress_tokens_f16": [_P, _P, _I64, _P, _P, _I, _I, _I, _P, _P],
+    "plaid_packbits": [_P, _I64, _P, _P],
     "plaid_doc_token_offsets": [_P, _P, _I, _I, _P, _I, _P, _P],
     "plaid_decompress_normalize_bf16": [_P, _P, _I, _I, _P, _I, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P],
     "plaid_decompress_normalize_f16": [_P, _P, _I, _I, _P, _I, _P, _P, _P, _P, _P, _I, _I, _P, _P],

@@ -98,3 +98,64 @@ def build_index(embs: torch.Tensor, doclens: torch.Tensor, centroids_f16: torch.
     return HostIndex(centroids=centroids_f16.to(torch.float16), bucket_cutoffs=bucket_cutoffs.float(),
                      bucket_weights=bucket_weights.float(), codes=codes, residuals=residuals, doclens=doclens, ivf=ivf,
                      ivf_lengths=ivf_lengths, nbits=int(nbits))
+
+
+class ResidualEmbeddings:
+    """(codes i32 [n], residuals u8 [n, 16*nbits]) pair (CB/indexing/codecs/residual_embeddings.py:12-24)."""
+
+    def __init__(self, codes, residuals):
+        assert codes.size(0) == residuals.size(0), (codes.size(), residuals.size())
+        assert codes.dim() == 1 and residuals.dim() == 2, (codes.size(), residuals.size())
+        assert residuals.dtype == torch.uint8
+        self.codes = codes.to(torch.int32)
+        self.residuals = residuals
+
+
+class ResidualCodec:
+    """The reference's codec object (CB/indexing/codecs/residual.py:17-278), GPU branch only: same constructor,
+    `compress_into_codes / lookup_centroids / compress / binarize / decompress`, and the two operators the reference
+    binds as class attributes (residual.py:115,130)."""
+
+    Embeddings = ResidualEmbeddings
+    decompress_residuals = staticmethod(ops.codec_decompress_residuals)
+    packbits = staticmethod(ops.packbits)
+
+    def __init__(self, config, centroids, avg_residual=None, bucket_cutoffs=None, bucket_weights=None):
+        if getattr(config, "total_visible_gpus", 1) == 0:
+            raise RuntimeError("ResidualCodec: total_visible_gpus=0 selects the reference's CPU branch, which this "
+                               "B200 implementation does not have")
+        self.use_gpu = True
+        self.dim, self.nbits = int(config.dim), int(config.nbits)
+        self.centroids = _cu(centroids, torch.float16)
+        self.avg_residual = avg_residual
+        self.bucket_cutoffs = None if bucket_cutoffs is None else _cu(bucket_cutoffs, torch.float32)
+        self.bucket_weights = None if bucket_weights is None else _cu(bucket_weights, torch.float16)
+        from .index import codec_tables
+        rbm, lut = codec_tables(self.nbits)
+        self.reversed_bit_map, self.decompression_lookup_table = _cu(rbm), _cu(lut)
+        self.arange_bits = torch.arange(0, self.nbits, device=self.centroids.device, dtype=torch.uint8)
+
+    def compress_into_codes(self, embs, out_device=None):
+        codes = compress_into_codes(embs.float(), self.centroids)
+        return codes if out_device is None else codes.to(out_device)
+
+    def lookup_centroids(self, codes, out_device=None):
+        out = self.centroids[_cu(codes).long()]
+        return out if out_device is None else out.to(out_device)
+
+    def compress(self, embs):
+        codes, residuals = compress(embs.float(), self.centroids, self.bucket_cutoffs, self.nbits)
+        return ResidualEmbeddings(codes, residuals)
+
+    def binarize(self, residuals):
+        """residual.py:188-203 on the device: bucketize, nbits flags per value LSB first, packbits."""
+        r = torch.bucketize(_cu(residuals).float(), self.bucket_cutoffs).to(torch.uint8)
+        flags = (r.unsqueeze(-1) >> self.arange_bits) & 1
+        packed = ResidualCodec.packbits(flags.contiguous().flatten())
+        return packed.reshape(r.size(0), self.dim // 8 * self.nbits)
+
+    def decompress(self, compressed_embs):
+        """fp16 [n, dim], L2-normalised (residual.py:242-278, GPU branch) -- one launch, no 2^15-row batching."""
+        return ResidualCodec.decompress_residuals(compressed_embs.residuals, self.bucket_weights, self.reversed_bit_map,
+                                                  self.decompression_lookup_table, compressed_embs.codes,
+                                                  self.centroids, self.dim, self.nbits, normalize=True)

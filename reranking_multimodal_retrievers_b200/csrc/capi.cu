@@ -15,17 +15,37 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 
+static int current_device_slot() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0) dev = 0;
+    return dev % kMaxDevices;
+}
+
 int sm_count() {
-    static int cached = 0;
-    if (cached == 0) {
+    static int cached[kMaxDevices] = {0};
+    const int slot = current_device_slot();
+    if (cached[slot] == 0) {
         int dev = 0, n = 0;
         if (cudaGetDevice(&dev) == cudaSuccess &&
             cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
-            cached = n;
+            cached[slot] = n;
         else
             return 148;  // B200
     }
-    return cached;
+    return cached[slot];
+}
+
+// Racing threads may both set the attribute; that is harmless (same value, idempotent call).
+int ensure_dynamic_smem(const void* fn, int bytes, int (&state)[kMaxDevices], bool full_carveout) {
+    const int slot = current_device_slot();
+    if (bytes <= state[slot]) return PLAID_OK;
+    if (bytes > 48 * 1024 || full_carveout) {
+        PLAID_CUDA_OK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        if (full_carveout)
+            PLAID_CUDA_OK(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    }
+    state[slot] = bytes;
+    return PLAID_OK;
 }
 
 EncodeTiledFn encode_tiled_fn() {

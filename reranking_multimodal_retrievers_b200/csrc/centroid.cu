@@ -264,12 +264,9 @@ extern "C" int plaid_centroid_scores(const void* centroids_bf16, int C, const vo
     cudaStream_t st = (cudaStream_t)stream;
 #define PLAID_CS_LAUNCH(ST_, NC_)                                                                                       \
     do {                                                                                                                \
-        static bool configured = false;                                                                                 \
-        if (!configured) {                                                                                              \
-            PLAID_CUDA_OK(cudaFuncSetAttribute(centroid_scores_kernel<ST_, NC_>,                                        \
-                                               cudaFuncAttributeMaxDynamicSharedMemorySize, kCsSmemBytes));             \
-            configured = true;                                                                                          \
-        }                                                                                                               \
+        static int configured[kMaxDevices] = {0};                                                                       \
+        if ((rc = ensure_dynamic_smem((const void*)centroid_scores_kernel<ST_, NC_>, kCsSmemBytes, configured)) != PLAID_OK) \
+            return rc;                                                                                                  \
         centroid_scores_kernel<ST_, NC_><<<grid, kCsThreads, kCsSmemBytes, st>>>(                                       \
             map_q, map_c, qlens, C, Lq_pad, threshold, ncells, csplit, reinterpret_cast<ST_*>(S), idx_bits, cell_val,   \
             cell_idx, watchdog);                                                                                        \

@@ -61,6 +61,23 @@ compress_residuals_kernel(const float* __restrict__ embs, const int32_t* __restr
     }
 }
 
+// ResidualCodec.packbits (CB/indexing/codecs/residual.py:130, codecs/packbits.cu:10-57): a flat u8 array of 0/1 flags
+// (any non-zero byte counts as 1, like the reference's __ballot_sync on the byte) -> one byte per 8 flags, first flag
+// in the most significant bit (np.packbits order).  A thread turns 8 flags (one 64-bit load) into one byte.
+__global__ void __launch_bounds__(256)
+packbits_kernel(const uint8_t* __restrict__ bits, int64_t nbytes_out, uint8_t* __restrict__ packed) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nbytes_out; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint2 w = __ldcs(reinterpret_cast<const uint2*>(bits) + i);
+        uint32_t o = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            o |= (((w.x >> (8 * j)) & 0xffu) ? 1u : 0u) << (7 - j);
+            o |= (((w.y >> (8 * j)) & 0xffu) ? 1u : 0u) << (3 - j);
+        }
+        packed[i] = (uint8_t)o;
+    }
+}
+
 }  // namespace plaid
 
 extern "C" int plaid_compress_residuals(const float* embs, const int32_t* codes, const void* centroids_f16,
@@ -86,5 +103,19 @@ extern "C" int plaid_compress_residuals(const float* embs, const int32_t* codes,
         default: compress_residuals_kernel<8><<<(int)blocks, 256, 0, st>>>(embs, codes, cent, bucket_cutoffs, n, C, residuals, bad_code_flag); break;
     }
     PLAID_LAUNCH_OK("compress_residuals_kernel");
+    return PLAID_OK;
+}
+
+extern "C" int plaid_packbits(const uint8_t* bits, int64_t nflags, uint8_t* packed, void* stream) {
+    using namespace plaid;
+    PLAID_CHECK_ARG(bits && packed && nflags >= 0, PLAID_ERR_ARG, "plaid_packbits: bad argument");
+    PLAID_CHECK_ARG((nflags % 8) == 0, PLAID_ERR_ARG, "plaid_packbits: %lld flags is not a multiple of 8", (long long)nflags);
+    PLAID_CHECK_ARG((reinterpret_cast<uintptr_t>(bits) & 7) == 0, PLAID_ERR_ARG, "plaid_packbits: bits must be 8-byte aligned");
+    if (nflags == 0) return PLAID_OK;
+    const int64_t nout = nflags / 8;
+    int64_t blocks = (nout + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    packbits_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(bits, nout, packed);
+    PLAID_LAUNCH_OK("packbits_kernel");
     return PLAID_OK;
 }

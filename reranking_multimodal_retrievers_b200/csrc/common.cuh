@@ -17,7 +17,12 @@
 namespace plaid {
 
 void set_error(const char* fmt, ...);   // capi.cu
-int  sm_count();                        // capi.cu (cached cudaDevAttrMultiProcessorCount)
+int  sm_count();                        // capi.cu (cudaDevAttrMultiProcessorCount of the CURRENT device, cached per device)
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device attribute: every launch site keeps one
+// `static int state[kMaxDevices]` (largest size configured so far on each device) and calls this before launching.
+static constexpr int kMaxDevices = 64;
+int  ensure_dynamic_smem(const void* fn, int bytes, int (&state)[kMaxDevices], bool full_carveout = false);   // capi.cu
 
 // Driver entry point for cuTensorMapEncodeTiled, fetched through the runtime so the library
 // does not link libcuda (it must dlopen on a CPU-only box for the symbol-export test).

@@ -209,6 +209,62 @@ decompress_normalize_f16_kernel(const int32_t* __restrict__ pids, const int32_t*
     }
 }
 
+// ---- token form (no pid indirection): the operator the reference binds as ResidualCodec.decompress_residuals
+// (CB/indexing/codecs/residual.py:115, codecs/decompress_residuals.cu:8-75): out[t, d] = half(weight) + half(centroid),
+// ONE half add per element like the reference kernel (`output = bucket_weights[..]; output += centroids[code][d]`).
+// Half a warp owns a token, lane h its dimensions 8h..8h+7 = NBITS whole residual bytes; one 128-bit centroid load
+// and one 128-bit store per lane.  normalize != 0 adds ResidualCodec.decompress's `F.normalize(..).half()` on top
+// (residual.py:272-273: fp32 sum of squares, the norm rounded to half, a half division per element).
+template <int NBITS>
+__global__ void __launch_bounds__(256)
+decompress_tokens_f16_kernel(const uint8_t* __restrict__ residuals, const int32_t* __restrict__ codes, int64_t n,
+                             const float* __restrict__ W, const __half* __restrict__ centroids, int C, int normalize,
+                             __half* __restrict__ out) {
+    constexpr int KEYS = 8 / NBITS;
+    __shared__ __half sW[256 * KEYS];
+    for (int i = threadIdx.x; i < 256 * KEYS; i += blockDim.x) sW[i] = __float2half_rn(W[i]);   // bucket_weights.half()
+    __syncthreads();
+    const int lane = threadIdx.x & 31, h = lane & 15, half = lane >> 4;
+    const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int64_t n_even = (n + 1) & ~int64_t(1);           // both halves of a warp run the same number of iterations
+    for (int64_t t = ((((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 2) + half; t < n_even; t += 2 * warps) {
+        const bool valid = t < n;
+        const int64_t tt = valid ? t : n - 1;
+        int code = codes[tt];
+        code = min(max(code, 0), C - 1);
+        const uint8_t* src = residuals + tt * (16 * NBITS) + h * NBITS;
+        uint8_t x[NBITS];
+#pragma unroll
+        for (int k = 0; k < NBITS; k++) x[k] = src[k];
+        const uint4 craw = __ldg(reinterpret_cast<const uint4*>(centroids + (size_t)code * kDim) + h);
+        const __half2* c2 = reinterpret_cast<const __half2*>(&craw);
+        __half v[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const __half w = sW[x[i / KEYS] * KEYS + (i % KEYS)];
+            const __half c = (i & 1) ? __high2half(c2[i >> 1]) : __low2half(c2[i >> 1]);
+            v[i] = __hadd(w, c);
+        }
+        if (normalize) {
+            float ss = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; i++) ss = fmaf(__half2float(v[i]), __half2float(v[i]), ss);
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+            const float nrm = __half2float(__float2half_rn(sqrtf(ss)));    // half norm; clamp_min(1e-12) is 0 in half
+#pragma unroll
+            for (int i = 0; i < 8; i++) v[i] = __float2half_rn(__half2float(v[i]) / nrm);
+        }
+        if (valid) {
+            uint4 o;
+            __half2* o2 = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+            for (int i = 0; i < 4; i++) o2[i] = __halves2half2(v[2 * i], v[2 * i + 1]);
+            reinterpret_cast<uint4*>(out + t * kDim)[h] = o;
+        }
+    }
+}
+
 // per query: exclusive prefix sums of passage lengths
 __global__ void __launch_bounds__(256)
 doc_token_offsets_kernel(const int32_t* __restrict__ pids, const int32_t* __restrict__ counts, int pid_stride,
@@ -396,5 +452,32 @@ extern "C" int plaid_decompress_normalize_f16(const int32_t* pids, const int32_t
             return PLAID_ERR_UNSUPPORTED;
     }
     PLAID_LAUNCH_OK("decompress_normalize_f16_kernel");
+    return PLAID_OK;
+}
+
+extern "C" int plaid_decompress_tokens_f16(const uint8_t* residuals, const int32_t* codes, int64_t n, const float* W,
+                                           const void* centroids_f16, int C, int nbits, int normalize, void* out_f16,
+                                           void* stream) {
+    using namespace plaid;
+    PLAID_CHECK_ARG(residuals && codes && W && centroids_f16 && out_f16, PLAID_ERR_ARG, "plaid_decompress_tokens_f16: null pointer");
+    PLAID_CHECK_ARG(n >= 0 && C > 0, PLAID_ERR_ARG, "plaid_decompress_tokens_f16: bad sizes");
+    PLAID_CHECK_ARG((reinterpret_cast<uintptr_t>(centroids_f16) & 15) == 0 && (reinterpret_cast<uintptr_t>(out_f16) & 15) == 0,
+                    PLAID_ERR_ARG, "plaid_decompress_tokens_f16: centroids/out must be 16-byte aligned");
+    if (n == 0) return PLAID_OK;
+    int64_t blocks = (n + 15) / 16;               // 8 warps x 2 tokens per CTA and pass
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    cudaStream_t st = (cudaStream_t)stream;
+    const __half* cent = reinterpret_cast<const __half*>(centroids_f16);
+    __half* out = reinterpret_cast<__half*>(out_f16);
+    switch (nbits) {
+        case 1: decompress_tokens_f16_kernel<1><<<(int)blocks, 256, 0, st>>>(residuals, codes, n, W, cent, C, normalize, out); break;
+        case 2: decompress_tokens_f16_kernel<2><<<(int)blocks, 256, 0, st>>>(residuals, codes, n, W, cent, C, normalize, out); break;
+        case 4: decompress_tokens_f16_kernel<4><<<(int)blocks, 256, 0, st>>>(residuals, codes, n, W, cent, C, normalize, out); break;
+        case 8: decompress_tokens_f16_kernel<8><<<(int)blocks, 256, 0, st>>>(residuals, codes, n, W, cent, C, normalize, out); break;
+        default:
+            set_error("plaid_decompress_tokens_f16: nbits=%d not in {1,2,4,8}", nbits);
+            return PLAID_ERR_UNSUPPORTED;
+    }
+    PLAID_LAUNCH_OK("decompress_tokens_f16_kernel");
     return PLAID_OK;
 }

@@ -566,12 +566,8 @@ static int launch_approx_t(const int32_t* pids, const int32_t* counts, int B, in
         PLAID_CHECK_ARG(smem <= 200 * 1024, PLAID_ERR_UNSUPPORTED, "approx_scores: C=%d pruning bitmap exceeds shared memory", C);
         PLAID_CHECK_ARG((reinterpret_cast<uintptr_t>(idx_bits) & 15) == 0 && (C % 128) == 0, PLAID_ERR_ARG,
                         "approx_scores: idx_bits must be 16-byte aligned and C a multiple of 128");
-        static size_t configured = 0;
-        if (smem > 48 * 1024 && smem > configured) {
-            PLAID_CUDA_OK(cudaFuncSetAttribute(approx_scores_kernel<true, kStage1Dpw, ST>,
-                                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            configured = smem;
-        }
+        static int configured[kMaxDevices] = {0};
+        if (int rc = ensure_dynamic_smem((const void*)approx_scores_kernel<true, kStage1Dpw, ST>, (int)smem, configured)) return rc;
         dim3 grid((pid_stride + kDocs - 1) / kDocs, B);
         if (only_flagged && grid.x > 8) grid.x = 8;     // rarely-taken fallback: few CTAs per query, each walks its groups
         approx_scores_kernel<true, kStage1Dpw, ST><<<grid, kApproxWarps * 32, smem, st>>>(
@@ -891,11 +887,8 @@ static int launch_select(const int32_t* pids, const float* scores, const int32_t
     PLAID_CHECK_ARG(out_stride >= keep, PLAID_ERR_ARG, "select_top: out_stride=%d < keep=%d", out_stride, keep);
     const int sel_cap = next_pow2(keep < 2 ? 2 : keep);
     const size_t smem = (size_t)(sel_cap + kBktCap + kRankMax) * 8 + 256 * 4 + 16;
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-        PLAID_CUDA_OK(cudaFuncSetAttribute(select_top_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+    static int configured[kMaxDevices] = {0};
+    if (int rc = ensure_dynamic_smem((const void*)select_top_kernel, (int)smem, configured)) return rc;
     select_top_kernel<<<B, kSelThreads, smem, st>>>(pids, scores, counts, in_stride, keep, sel_cap, out_pids, out_scores,
                                                     out_counts, out_stride, ws_keys);
     PLAID_LAUNCH_OK("select_top_kernel");
@@ -949,12 +942,9 @@ extern "C" int plaid_filter_stage1_ivf(const int32_t* pids, const int32_t* count
     ivf_pairs_kernel<<<dim3(min((cap_s + 7) / 8, kPairsGridX), B), 256, 0, st>>>(ws_surv, cap_s, ws_meta, ivf_pids, ivf_offsets, bitmap,
                                                                 wprefix, words, N, ws_pair_slot, ws_pair_c, cap_p);
     PLAID_LAUNCH_OK("ivf_pairs_kernel");
-    static int configured = 0;
-    if (smem > configured) {
-        PLAID_CUDA_OK(cudaFuncSetAttribute(ivf_scores_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        PLAID_CUDA_OK(cudaFuncSetAttribute(ivf_scores_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        configured = smem;
-    }
+    static int configured_f32[kMaxDevices] = {0}, configured_f16[kMaxDevices] = {0};
+    if (int rc = ensure_dynamic_smem((const void*)ivf_scores_kernel<float>, smem, configured_f32)) return rc;
+    if (int rc = ensure_dynamic_smem((const void*)ivf_scores_kernel<__half>, smem, configured_f16)) return rc;
     if (s_is_f16)
         ivf_scores_kernel<__half><<<B, IvfTile<__half>::kThreads, smem, st>>>(counts, pid_stride, ws_meta, ws_pair_slot, ws_pair_c, ws_sorted_c,
                                                         cap_p, reinterpret_cast<const __half*>(S), C, qlens, out_scores);
@@ -1025,11 +1015,8 @@ extern "C" int plaid_merge_topk(const float* scores, const int32_t* pids, const 
     if (B == 0) return PLAID_OK;
     const int sel_cap = next_pow2(k < 2 ? 2 : k);
     const size_t smem = (size_t)(sel_cap + kBktCap + kRankMax) * 8 + 256 * 4 + 16;
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-        PLAID_CUDA_OK(cudaFuncSetAttribute(merge_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+    static int configured[kMaxDevices] = {0};
+    if (int rc = ensure_dynamic_smem((const void*)merge_topk_kernel, (int)smem, configured)) return rc;
     merge_topk_kernel<<<B, kSelThreads, smem, (cudaStream_t)stream>>>(scores, pids, counts, G, B, k, sel_cap, out_pids,
                                                                       out_scores, out_counts, ws_keys);
     PLAID_LAUNCH_OK("merge_topk_kernel");

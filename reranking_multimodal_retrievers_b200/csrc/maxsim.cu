@@ -970,14 +970,10 @@ static int ms_launch(const void* Qb, int q_rows, const void* D, uint64_t d_rows,
     }
     const int smem = 1024 + p.MT * 128 * kDim * 2 + p.NS * p.NT * kDim * 2 + (int)sizeof(MsShared) + 64;
     const int mode = p.padded ? 2 : (p.aligned ? 0 : 1);
-    static int configured[3] = {0, 0, 0};
+    static int configured[3][kMaxDevices] = {{0}, {0}, {0}};
     const void* fn = mode == 0 ? (const void*)maxsim_kernel<0> : mode == 1 ? (const void*)maxsim_kernel<1>
                                                                            : (const void*)maxsim_kernel<2>;
-    if (smem > configured[mode]) {
-        PLAID_CUDA_OK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        PLAID_CUDA_OK(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        configured[mode] = smem;
-    }
+    if ((rc = ensure_dynamic_smem(fn, smem, configured[mode], true)) != PLAID_OK) return rc;
     int grid = sm_count() * (dual ? 2 : 1);
     if (grid > p.num_items) grid = p.num_items;
     p.items_per_cta = (p.num_items + grid - 1) / grid;
@@ -1016,12 +1012,9 @@ static int ms_launch_fused(const void* Qb, int q_rows, int nbits, MsParams& p, c
           : unit == 16 ? (const void*)maxsim_fused_kernel<NB, false, 16> : (const void*)maxsim_fused_kernel<NB, false, 32>)
     const void* fn = nbits == 1 ? PLAID_FUSED_FN(1) : nbits == 2 ? PLAID_FUSED_FN(2) : nbits == 4 ? PLAID_FUSED_FN(4) : PLAID_FUSED_FN(8);
 #undef PLAID_FUSED_FN
-    static int configured[3][9] = {{0}, {0}, {0}};
+    static int configured[3][9][kMaxDevices] = {{{0}}};
     const int variant = slim ? 1 : unit == 16 ? 2 : 0;
-    if (smem > configured[variant][nbits]) {
-        PLAID_CUDA_OK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        configured[variant][nbits] = smem;
-    }
+    if ((rc = ensure_dynamic_smem(fn, smem, configured[variant][nbits])) != PLAID_OK) return rc;
     int grid = sm_count();
     if (grid > p.num_items) grid = p.num_items;
     p.items_per_cta = (p.num_items + grid - 1) / grid;

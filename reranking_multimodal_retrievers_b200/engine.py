@@ -99,8 +99,13 @@ class _HostFeed:
 
 class SearchEngine:
     def __init__(self, index: DeviceIndex, s_budget_bytes: int = 6 << 30, max_chunk: int = 512, fused: bool = True,
-                 s_dtype: torch.dtype = torch.float16, ivf_stage1: bool = True):
+                 s_dtype: torch.dtype = torch.float16, ivf_stage1: bool = True, query_maxlen: int = NQ_MAX):
         self.index = index
+        # number of leading query tokens that drive candidate generation and the two filter stages
+        # (`Q[:, :config.query_maxlen]`, CB/search/index_storage.py:77); the kernels hold one token per lane
+        if not 1 <= int(query_maxlen) <= NQ_MAX:
+            raise _lib.PlaidError(f"query_maxlen={query_maxlen}: the candidate stage supports 1..{NQ_MAX} query tokens")
+        self.query_maxlen = int(query_maxlen)
         # stage 1 of the filter through the inverted file (falls back to the token scan per query on the device)
         self.ivf_stage1 = bool(ivf_stage1)
         self.cap_s, self.cap_p = 4096, 65536
@@ -163,7 +168,7 @@ class SearchEngine:
         ws = dict(
             csplit=csplit, nlists=nlists, cand_stride=cand_stride, fstride=fstride, tok_stride=tok_stride, nd4=nd4,
             Qb=e(Bc, Lq_pad, 128, dtype=torch.bfloat16), Qh=e(Bc, Lq_pad, 128, dtype=torch.float16),
-            qlens=e(Bc, dtype=torch.int32),
+            qlens=e(Bc, dtype=torch.int32), cqlens=e(Bc, dtype=torch.int32),
             S=e(Bc, C, NQ_MAX, dtype=self.s_dtype), idx_bits=e(Bc, C // 32, dtype=torch.int32),
             cell_val=e(Bc, NQ_MAX, nlists, ncells, dtype=torch.float32),
             cell_idx=e(Bc, NQ_MAX, nlists, ncells, dtype=torch.int32),
@@ -173,7 +178,8 @@ class SearchEngine:
             pair_c=e(Bc, self.cap_p, dtype=torch.int32), sorted_c=e(Bc, 2 * self.cap_p, dtype=torch.int32),
             ivf_meta=e(Bc, 4, dtype=torch.int32),
             cand_pids=e(Bc, cand_stride, dtype=torch.int32), cand_counts=e(Bc, dtype=torch.int32),
-            ws_scores=e(Bc, fstride, dtype=torch.float32), ws_keys=e(Bc, fstride, dtype=torch.int64),
+            ws_scores=e(Bc, fstride, dtype=torch.float32), ws_keys=e(2, dtype=torch.int64),   # ABI leftover of select_top: must be non-null, never touched
+
             s1_pids=e(Bc, ndocs, dtype=torch.int32), s1_scores=e(Bc, ndocs, dtype=torch.float32),
             s1_counts=e(Bc, dtype=torch.int32),
             s2_pids=e(Bc, nd4, dtype=torch.int32), s2_scores=e(Bc, nd4, dtype=torch.float32),
@@ -225,11 +231,21 @@ class SearchEngine:
         call = self._call
         call("prepare", "plaid_prepare_queries", _p(Qc), b, Lq, int(remove_zero_rows), Bc, Lq_pad, _p(ws["Qb"]), _p(ws["Qh"]),
              _p(ws["qlens"]), st)
-        call("centroid_scores", "plaid_centroid_scores", _p(ix.centroids_bf16), C, _p(ws["Qb"]), _p(ws["qlens"]), Bc, Lq_pad, float(thr),
+        cq = self._candidate_qlens(ws)
+        call("centroid_scores", "plaid_centroid_scores", _p(ix.centroids_bf16), C, _p(ws["Qb"]), _p(cq), Bc, Lq_pad, float(thr),
              ncells, ws["csplit"], _p(ws["S"]), int(self.s_dtype == torch.float16), _p(ws["idx_bits"]), _p(ws["cell_val"]), _p(ws["cell_idx"]), wd, st)
-        call("candidates", "plaid_candidates", _p(ws["cell_val"]), _p(ws["cell_idx"]), _p(ws["qlens"]), b, ncells, ws["nlists"],
+        call("candidates", "plaid_candidates", _p(ws["cell_val"]), _p(ws["cell_idx"]), _p(cq), b, ncells, ws["nlists"],
              _p(ix.ivf_pids), _p(ix.ivf_offsets), C, N, _p(ws["cells"]), _p(ws["bitmap"]), _p(ws["cand_pids"]),
              _p(ws["cand_counts"]), ws["cand_stride"], ovf, _p(ws["wprefix"]), st)
+
+    def _candidate_qlens(self, ws, refresh: bool = True):
+        """Per-query token count of the candidate stage: min(qlens, query_maxlen).  The kernels clamp to 32
+        themselves, so the plain qlens serve unless the index was built with a shorter query_maxlen."""
+        if self.query_maxlen >= NQ_MAX:
+            return ws["qlens"]
+        if refresh:
+            torch.clamp(ws["qlens"], max=self.query_maxlen, out=ws["cqlens"])
+        return ws["cqlens"]
 
     def stage_rank(self, ws, b: int, Lq_pad: int, ndocs: int, k: int, Bc: int):
         """a5-a10: two-stage filter, decompression, exact MaxSim, top-k -- on ws['cand_pids'/'S'/'idx_bits']."""
@@ -238,22 +254,23 @@ class SearchEngine:
         C = ix.num_centroids
         wd, _ = self._flag_ptrs()
         call = self._call
+        cq = self._candidate_qlens(ws)
         # plaid_filter_pids' four launches issued one by one so each can be timed on its own
         cs, fs, nd4_ = ws["cand_stride"], ws["fstride"], ndocs // 4
         f16 = int(self.s_dtype == torch.float16)
         if self.ivf_stage1:
             call("filter_stage1", "plaid_filter_stage1_ivf", _p(ws["cand_pids"]), _p(ws["cand_counts"]), b, cs, _p(ws["S"]),
-                 f16, _p(ws["qlens"]), _p(ws["idx_bits"]), C, _p(ix.codes), _p(ix.offsets), _p(ix.ivf_pids),
+                 f16, _p(cq), _p(ws["idx_bits"]), C, _p(ix.codes), _p(ix.offsets), _p(ix.ivf_pids),
                  _p(ix.ivf_offsets), _p(ws["bitmap"]), _p(ws["wprefix"]), ix.num_passages, _p(ws["surv"]), self.cap_s,
                  _p(ws["pair_slot"]), _p(ws["pair_c"]), _p(ws["sorted_c"]), self.cap_p, _p(ws["ivf_meta"]),
                  _p(ws["ws_scores"]), st)
         else:
             call("filter_stage1", "plaid_approx_scores", _p(ws["cand_pids"]), _p(ws["cand_counts"]), b, cs, _p(ws["S"]), f16,
-                 _p(ws["qlens"]), _p(ws["idx_bits"]), C, _p(ix.codes), _p(ix.offsets), _p(ws["ws_scores"]), st)
+                 _p(cq), _p(ws["idx_bits"]), C, _p(ix.codes), _p(ix.offsets), _p(ws["ws_scores"]), st)
         call("select1", "plaid_select_top", _p(ws["cand_pids"]), _p(ws["ws_scores"]), _p(ws["cand_counts"]), b, cs, ndocs,
              _p(ws["s1_pids"]), _p(ws["s1_scores"]), _p(ws["s1_counts"]), ndocs, _p(ws["ws_keys"]), st)
         call("filter_stage2", "plaid_approx_scores", _p(ws["s1_pids"]), _p(ws["s1_counts"]), b, ndocs, _p(ws["S"]), f16,
-             _p(ws["qlens"]), None, C, _p(ix.codes), _p(ix.offsets), _p(ws["ws_scores"]), st)
+             _p(cq), None, C, _p(ix.codes), _p(ix.offsets), _p(ws["ws_scores"]), st)
         call("select2", "plaid_select_top", _p(ws["s1_pids"]), _p(ws["ws_scores"]), _p(ws["s1_counts"]), b, ndocs, nd4_,
              _p(ws["s2_pids"]), _p(ws["s2_scores"]), _p(ws["s2_counts"]), nd4_, _p(ws["ws_keys"]), st)
         nd4 = ws["nd4"]
@@ -304,6 +321,10 @@ class SearchEngine:
         out_c = torch.zeros(B, device=dev, dtype=torch.int32)
         if B == 0 or ix.num_passages == 0:
             return out_p, out_s, out_c
+        if torch.cuda.current_device() != dev.index:
+            # launches go to the current device's stream: the caller must have selected the index's device
+            raise _lib.PlaidError(f"search_batch: current CUDA device {torch.cuda.current_device()} != index device {dev.index}; "
+                                  "wrap the call in torch.cuda.device(index.device)")
         Bc = self.chunk_size(B)
         feed = self._host_feed(Q, Bc) if not Q.is_cuda else None
         Qd = Q.to(torch.float32).contiguous() if Q.is_cuda else None

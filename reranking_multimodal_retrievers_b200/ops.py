@@ -7,6 +7,8 @@ These mirror, argument for argument, the native operators the reference binds as
   IndexScorer.decompress_residuals   <- decompress_residuals_cpp  (CB/search/decompress_residuals.cpp:80-155)
   ColBERT.segmented_maxsim           <- segmented_maxsim_cpp      (CB/modeling/segmented_maxsim.cpp:49-93)
   StridedTensor.segmented_lookup     <- segmented_lookup_cpp      (CB/search/segmented_lookup.cpp:51-125)
+  ResidualCodec.decompress_residuals <- decompress_residuals_cpp  (CB/indexing/codecs/decompress_residuals.cu:8-75, GPU form)
+  ResidualCodec.packbits             <- packbits_cpp              (CB/indexing/codecs/packbits.cu:10-57)
 
 Inputs are torch CUDA tensors (CPU tensors are moved to the current CUDA device first, since the
 reference calls these with CPU tensors); outputs are CUDA tensors.  torch is used only to own
@@ -194,6 +196,43 @@ def decompress_residuals(pids, lengths, offsets, bucket_weights, reversed_bit_ma
         _lib.call("plaid_decompress_residuals", _p(pids), pids.numel(), _p(offsets), _p(out_offsets), _p(W),
                   _p(res), _p(codes), _p(cent), cent.shape[0], int(nbits), _p(out), _stream())
     return out[:total]
+
+
+def codec_decompress_residuals(binary_residuals, bucket_weights, reversed_bit_map, bucket_weight_combinations, codes,
+                               centroids, dim, nbits, normalize=False):
+    """Drop-in for ``ResidualCodec.decompress_residuals`` -- the GPU-branch operator (residual.py:115,250-260;
+    decompress_residuals.cu:8-75): token rows without pid indirection, fp16 [n, dim] = half bucket weight + half
+    centroid (one half add per element, bit-exact with the reference kernel).  normalize=True applies
+    ``ResidualCodec.decompress``'s `F.normalize(..).half()` in the same launch (residual.py:272-273)."""
+    if dim != DIM:
+        raise _lib.PlaidError(f"decompress_residuals: dim={dim}, the kernels are built for dim={DIM}")
+    res = _cu(binary_residuals, torch.uint8)
+    if res.dim() != 2 or res.shape[1] != DIM * int(nbits) // 8:
+        raise _lib.PlaidError(f"decompress_residuals: binary_residuals must be [n, {DIM * int(nbits) // 8}] for nbits={nbits}")
+    codes = _cu(codes, torch.int32)
+    n = res.shape[0]
+    if codes.numel() != n:
+        raise _lib.PlaidError("decompress_residuals: codes and binary_residuals disagree on the number of tokens")
+    cent = _cu(centroids, torch.float16)
+    W = build_weight_table(_cu(bucket_weights).float(), reversed_bit_map, bucket_weight_combinations, nbits)
+    out = torch.empty(max(n, 1), DIM, device=res.device, dtype=torch.float16)
+    if n:
+        _lib.call("plaid_decompress_tokens_f16", _p(res), _p(codes), ctypes.c_int64(n), _p(W), _p(cent), cent.shape[0],
+                  int(nbits), int(bool(normalize)), _p(out), _stream())
+    return out[:n]
+
+
+def packbits(bits):
+    """Drop-in for ``ResidualCodec.packbits`` (residual.py:130,198; packbits.cu:10-57): flat u8 flags -> u8 [n/8],
+    first flag in the most significant bit."""
+    bits = _cu(bits, torch.uint8).reshape(-1)
+    n = bits.numel()
+    if n % 8:
+        raise _lib.PlaidError(f"packbits: {n} flags is not a multiple of 8")
+    out = torch.empty(max(n // 8, 1), device=bits.device, dtype=torch.uint8)
+    if n:
+        _lib.call("plaid_packbits", _p(bits), ctypes.c_int64(n), _p(out), _stream())
+    return out[: n // 8]
 
 
 def unpack_residual_codes(residuals, nbits, reversed_bit_map, lookup):

@@ -12,7 +12,7 @@ import os
 
 import torch
 
-from . import modeling, ops
+from . import _lib, modeling, ops
 from .engine import SearchEngine, search_defaults
 from .index import DeviceIndex, HostIndex, load_reference_index
 from .infra import ColBERTConfig, Queries, Ranking, Run
@@ -36,16 +36,32 @@ class IndexScorer:
             self.index_path = None
             host = index_path
         self.index = DeviceIndex(host, device)
-        self.engine = SearchEngine(self.index)                              # batched path (Searcher.search_batch)
-        self.engine1 = SearchEngine(self.index, s_dtype=torch.float32)      # single-query API: fp32 centroid_scores
+        qml = int((getattr(host, "config", None) or {}).get("query_maxlen", ops.NQ_MAX) or ops.NQ_MAX)
+        self.engine = SearchEngine(self.index, query_maxlen=qml)            # batched path (Searcher.search_batch)
+        # single-query API of the reference: fp32 centroid_scores, and stage 1 by the code scan -- `score_pids` takes ANY
+        # pid list / table (filter_fn, foreign callers), while the inverted-file route of the batched engine is only
+        # valid for exactly the candidate bitmap the preceding `stage_candidates` left in the workspace
+        self.engine1 = SearchEngine(self.index, s_dtype=torch.float32, ivf_stage1=False, query_maxlen=qml)
         self.doclens = self.index.doclens
         self.num_embeddings = self.index.num_embeddings
         self.num_partitions = self.index.num_centroids
+        self._emb2pid = None
+
+    def set_query_maxlen(self, query_maxlen):
+        """`config.query_maxlen` of the searcher (CB/search/index_storage.py:77: `Q[:, :config.query_maxlen]`)."""
+        if not 1 <= int(query_maxlen) <= ops.NQ_MAX:
+            raise _lib.PlaidError(f"query_maxlen={query_maxlen}: the candidate stage supports 1..{ops.NQ_MAX} query tokens "
+                                  "(one per lane); longer candidate-stage queries are not silently truncated")
+        for eng in (self.engine, self.engine1):
+            eng.query_maxlen = int(query_maxlen)
 
     # ---- single-query API of the reference -------------------------------------------------
     def _prep(self, config, Q, k_hint=None):
         Q = Q if Q.dim() == 3 else Q.unsqueeze(0)
         assert Q.size(0) == 1, "IndexScorer.rank/retrieve take one query [1, Lq, dim] (searcher.py:81)"
+        qml = getattr(config, "query_maxlen", None)
+        if qml:
+            self.set_query_maxlen(qml)
         ncells, thr, ndocs = config.ncells, config.centroid_score_threshold, config.ndocs
         d = search_defaults(k_hint or 10)
         ncells = d[0] if ncells is None else ncells
@@ -56,23 +72,27 @@ class IndexScorer:
         return Q, ws, int(ncells), float(thr), int(ndocs), Lq_pad
 
     def retrieve(self, config, Q):
-        """(candidate pids i32 sorted unique, centroid_scores f32 [C, nq]) -- index_storage.py:67-80."""
+        """(candidate pids i32 sorted unique, centroid_scores f32 [C, nq]) -- index_storage.py:67-80.
+        Independent tensors, like the reference's: a later retrieve/rank does not change them."""
         Q, ws, ncells, thr, ndocs, Lq_pad = self._prep(config, Q)
         Qd = ops._cu(Q, torch.float32)
-        self.engine1.stage_candidates(ws, Qd, Lq_pad, ncells, thr, False, 4)
+        with torch.cuda.device(self.index.device):
+            self.engine1.stage_candidates(ws, Qd, Lq_pad, ncells, thr, False, 4)
         n = int(ws["cand_counts"][0].item())
-        nq = min(int(ws["qlens"][0].item()), int(getattr(config, "query_maxlen", 32) or 32), ops.NQ_MAX)
-        self._last = (ws, Lq_pad, ndocs)
-        return ws["cand_pids"][0, :n], ws["S"][0, :, :nq]
+        nq = min(int(ws["qlens"][0].item()), self.engine1.query_maxlen)
+        return ws["cand_pids"][0, :n].clone(), ws["S"][0, :, :nq].clone()
 
     def score_pids(self, config, Q, pids, centroid_scores, batch_size=None):
         """(scores f32, pids i32) of the ndocs/4 passages surviving the two-stage filter
-        (index_storage.py:100-184).  `pids`/`centroid_scores` are normally what `retrieve` returned."""
+        (index_storage.py:100-184).  `pids` is ANY list of local pids (what `retrieve` returned, a `filter_fn`'s
+        subset of it, or the caller's own) and `centroid_scores` any f32 [C, nq] table: both are installed into
+        the workspace and the pruning mask is rebuilt from the table (index_storage.py:115)."""
         Q, ws, ncells, thr, ndocs, Lq_pad = self._prep(config, Q)
         S_ws = ws["S"][0]
         nq = centroid_scores.shape[1]
-        if centroid_scores.data_ptr() != S_ws.data_ptr():
-            # foreign table: install it and rebuild the pruning mask (index_storage.py:115)
+        if nq > ops.NQ_MAX:
+            raise _lib.PlaidError(f"score_pids: centroid_scores has {nq} query-token columns > {ops.NQ_MAX}")
+        with torch.cuda.device(self.index.device):
             Qb, qlens, Qh = ops.prepare_queries(ops._cu(Q, torch.float32), False, Lq_pad, 4, with_f16=True)
             ws["Qb"].copy_(Qb)
             ws["Qh"].copy_(Qh)
@@ -81,14 +101,21 @@ class IndexScorer:
             S_ws[:, :nq] = ops._cu(centroid_scores, torch.float32)
             idx = S_ws[:, :nq].max(-1).values >= thr
             ws["idx_bits"][0] = ops.pack_idx_bits(idx)
-        pids = ops._cu(pids, torch.int32)
-        n = pids.numel()
-        if n > ws["cand_stride"]:
-            raise ValueError(f"{n} candidate pids exceed the workspace ({ws['cand_stride']})")
-        if pids.data_ptr() != ws["cand_pids"].data_ptr():
+            pids = ops._cu(pids, torch.int32).reshape(-1)
+            n = pids.numel()
+            if n > ws["cand_stride"]:
+                raise ValueError(f"{n} candidate pids exceed the workspace ({ws['cand_stride']})")
+            if n and (int(pids.min()) < 0 or int(pids.max()) >= self.index.num_passages):
+                raise _lib.PlaidError("score_pids: pid outside this index shard")
             ws["cand_pids"][0, :n] = pids
-        ws["cand_counts"][0] = n
-        self.engine1.stage_rank(ws, 1, Lq_pad, ndocs, ndocs // 4, 4)
+            ws["cand_counts"][0] = n
+            # the candidate stage of the filter sees min(qlen, nq, query_maxlen) tokens, as the reference's table has nq columns
+            saved = self.engine1.query_maxlen
+            self.engine1.query_maxlen = min(saved, nq)
+            try:
+                self.engine1.stage_rank(ws, 1, Lq_pad, ndocs, ndocs // 4, 4)
+            finally:
+                self.engine1.query_maxlen = saved
         m = int(ws["s2_counts"][0].item())
         return ws["scores"][0, :m].clone(), ws["s2_pids"][0, :m].clone()
 
@@ -102,6 +129,26 @@ class IndexScorer:
             op, os_ = ops.select_top(pids, scores, max(int(pids.numel()), 1))
             op = op + self.index.pid_base
             return op.tolist(), os_.tolist()
+
+    def lookup_eids(self, embedding_ids, codes=None, out_device="cuda"):
+        """fp16 normalised embeddings [n, dim] of the listed token ids (index_storage.py:61-62 ->
+        residual_embeddings_strided.py:24-28 -> ResidualCodec.decompress, GPU branch)."""
+        ix = self.index
+        eids = ops._cu(embedding_ids, torch.int64).reshape(-1)
+        if eids.numel() and (int(eids.min()) < 0 or int(eids.max()) >= ix.num_embeddings):
+            raise _lib.PlaidError("lookup_eids: embedding id outside this index shard")
+        codes = ix.codes[eids] if codes is None else ops._cu(codes, torch.int32)
+        residuals = ix.residuals[eids]
+        return ops.codec_decompress_residuals(residuals, ix.bucket_weights.half(), ix.reversed_bit_map, ix.lookup_table,
+                                              codes, ix.centroids_f16, ix.dim, ix.nbits, normalize=True)
+
+    def embedding_ids_to_pids(self, embedding_ids):
+        """Unique passages owning the listed token ids (index_storage.py:82-84; LOCAL pids of this shard)."""
+        if self._emb2pid is None:
+            ix = self.index
+            self._emb2pid = torch.repeat_interleave(torch.arange(ix.num_passages, device=ix.device, dtype=torch.int32),
+                                                    ix.doclens)
+        return torch.unique(self._emb2pid[ops._cu(embedding_ids, torch.int64).reshape(-1)], sorted=False)
 
     def lookup_pids(self, passage_ids, out_device="cuda", return_mask=False):
         """(D_packed f32 normalised [sum len, dim], lengths) for local pids (index_storage.py:64-65)."""
@@ -165,6 +212,8 @@ class Searcher:
             self.configure(centroid_score_threshold=thr)
         if self.config.ndocs is None:
             self.configure(ndocs=ndocs)
+        # `Q[:, :config.query_maxlen]` drives candidate generation (index_storage.py:77); > 32 raises
+        self.ranker.set_query_maxlen(self.config.query_maxlen or ops.NQ_MAX)
 
     def search_batch(self, Q: torch.Tensor, k=10, remove_zero_tensors=False):
         """Q f32 [B, Lq, dim] -> (pids i32 [B, k], scores f32 [B, k], counts i32 [B]) device tensors."""

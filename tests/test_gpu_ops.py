@@ -308,3 +308,86 @@ def test_codec_build_index_is_searchable(P):
     pids, scores, counts = eng.search_batch(Q, k=5, ndocs=64)
     eng.check_flags()
     assert pids[:, 0].cpu().tolist() == gold.tolist()
+
+
+@pytest.mark.parametrize("nbits", [1, 2, 4, 8])
+def test_residual_codec_gpu_operators(P, nbits):
+    """ResidualCodec.decompress_residuals (GPU form: token rows, fp16) and ResidualCodec.packbits
+    (CB/indexing/codecs/residual.py:115,130): bit-exact against the oracle; decompress() within one half ulp."""
+    pkg, ops = P
+    from reranking_multimodal_retrievers_b200.synthetic import make_synthetic_index
+    sx = make_synthetic_index(200, 1, 60, nbits, seed=60 + nbits, num_centroids=256, mode="codes")
+    rbm, lut = po.codec_tables(nbits)
+    n = sx.num_embeddings
+    for m in (n, 1, 33):                                        # odd counts exercise the half-warp tail
+        res, codes = sx.residuals[:m], sx.codes[:m]
+        out = pkg.ResidualCodec.decompress_residuals(res, sx.bucket_weights.half(), rbm, lut, codes, sx.centroids, 128, nbits)
+        want = po.codec_decompress_gpu_form(sx.bucket_weights, rbm, lut, res, codes, sx.centroids)
+        assert out.dtype == torch.float16 and out.shape == (m, 128)
+        assert torch.equal(out.cpu(), want)
+    # one half rounding away from the fp32 CPU operator on the same bytes
+    ix = po.OracleIndex(centroids=sx.centroids, bucket_weights=sx.bucket_weights.half().float(), codes=sx.codes,
+                        residuals=sx.residuals, doclens=sx.doclens, ivf=sx.ivf, ivf_lengths=sx.ivf_lengths, nbits=nbits)
+    D32 = po.decompress_residuals(ix, torch.arange(sx.num_passages, dtype=torch.int32))
+    assert torch.equal(out.cpu(), D32.half())
+    # the codec object: decompress() = normalised half rows
+    cfg = pkg.ColBERTConfig(dim=128, nbits=nbits)
+    codec = pkg.ResidualCodec(cfg, sx.centroids, bucket_cutoffs=sx.bucket_cutoffs, bucket_weights=sx.bucket_weights)
+    Dn = codec.decompress(pkg.ResidualEmbeddings(sx.codes, sx.residuals)).cpu()
+    ref = po.codec_decompress_gpu_form(sx.bucket_weights, rbm, lut, sx.residuals, sx.codes, sx.centroids, normalize=True)
+    assert (Dn.float() - ref.float()).abs().max() <= 2 ** -10 and (Dn != ref).float().mean() < 0.01
+    # packbits / binarize
+    g = torch.Generator().manual_seed(nbits)
+    flags = torch.randint(0, 2, (8 * 1000,), generator=g, dtype=torch.uint8)
+    assert torch.equal(pkg.ResidualCodec.packbits(flags).cpu(), po.codec_packbits(flags))
+    flags[::7] *= 200                                           # any non-zero byte is a set flag
+    assert torch.equal(ops.packbits(flags).cpu(), po.codec_packbits(flags))
+    assert ops.packbits(torch.zeros(0, dtype=torch.uint8)).numel() == 0
+    with pytest.raises(pkg.PlaidError):
+        ops.packbits(torch.ones(12, dtype=torch.uint8))
+    r = 0.1 * torch.randn(50, 128, generator=g)
+    assert torch.equal(codec.binarize(r).cpu(), po.codec_binarize(r, sx.bucket_cutoffs, nbits))
+
+
+def test_lookup_eids_and_embedding_ids_to_pids(P, golden):
+    """IndexScorer.lookup_eids / embedding_ids_to_pids (CB/search/index_storage.py:61-62,82-84)."""
+    pkg, ops = P
+    from plaid_test_helpers import golden_host_index
+    g = golden
+    ix = golden_oracle_index(g)
+    scorer = pkg.IndexScorer(golden_host_index(g))
+    gen = torch.Generator().manual_seed(5)
+    eids = torch.randint(0, ix.codes.numel(), (257,), generator=gen)
+    D = scorer.lookup_eids(eids)
+    rbm, lut = po.codec_tables(ix.nbits)
+    want = po.codec_decompress_gpu_form(ix.bucket_weights, rbm, lut, ix.residuals[eids], ix.codes[eids],
+                                        ix.centroids.half(), normalize=True)
+    assert D.dtype == torch.float16 and (D.cpu().float() - want.float()).abs().max() <= 2 ** -10
+    # same rows as lookup_pids (fp32 path) up to half precision
+    tok2pid = torch.repeat_interleave(torch.arange(ix.doclens.numel()), ix.doclens)
+    pids = scorer.embedding_ids_to_pids(eids)
+    assert sorted(pids.cpu().tolist()) == sorted(set(tok2pid[eids].tolist()))
+    Dp, lens = scorer.lookup_pids(torch.tensor([3, 0]))
+    first = int(ix.offsets[3])
+    De = scorer.lookup_eids(torch.arange(first, first + int(lens[0])))
+    assert (Dp[: int(lens[0])].cpu() - De.cpu().float()).abs().max() <= 2 ** -9
+    with pytest.raises(pkg.PlaidError):
+        scorer.lookup_eids(torch.tensor([ix.codes.numel()]))
+
+
+def test_integration_md_level2_stub(P, golden):
+    """The ctypes stub INTEGRATION.md tells a maintainer to paste is executed verbatim: it must give the reference's
+    filter_pids output (golden, recorded from the unmodified reference) on the reference's own S."""
+    import os
+    import re
+    from reranking_multimodal_retrievers_b200 import build
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    text = open(os.path.join(root, "INTEGRATION.md")).read()
+    block = re.search(r"level2-stub-begin.*?```python\n(.*?)```\n<!-- level2-stub-end", text, re.S).group(1)
+    ns = {"PLAID_B200_LIB": build.LIB_PATH}
+    exec(compile(block, "INTEGRATION.md", "exec"), ns)
+    g = golden
+    ix = golden_oracle_index(g)
+    S, idx, cand = (torch.from_numpy(g[f"{n}_0"]) for n in ("S", "idx", "cand"))
+    out = ns["filter_pids_b200"](cand, S, ix.codes, ix.doclens, ix.offsets[:-1].contiguous(), idx, int(g["ndocs"]))
+    assert np.array_equal(out.cpu().numpy(), g["stage2_0"])

@@ -380,3 +380,73 @@ def test_host_queries_are_fed_chunk_by_chunk(pkg, golden):
         torch.cuda.synchronize()
         assert all(torch.equal(a, b) for a, b in zip(got, want))
     eng.check_flags()
+
+
+def _oracle_score_pids(ix, q, cand, S, thr, ndocs):
+    """IndexScorer.score_pids (index_storage.py:100-184) on an explicit candidate list."""
+    idx = po.centroid_mask(S, thr)
+    p2 = po.filter_pids(ix, cand, S, idx, ndocs)
+    D = po.normalize(po.decompress_residuals(ix, p2))
+    return p2, po.colbert_score_packed(q, D, ix.doclens[p2.long()])
+
+
+def test_rank_with_filter_fn_more_candidates_than_ndocs(pkg):
+    """IndexScorer.rank / score_pids with a filter_fn and with a caller-made pid list, n_candidates > ndocs (the
+    normal case on real indexes): stage-1 pruning must act on the FILTERED list.  Against the oracle fed the
+    centroid-score table `retrieve` returned."""
+    from reranking_multimodal_retrievers_b200 import synthetic
+    from reranking_multimodal_retrievers_b200.infra import ColBERTConfig
+    sx = synthetic.make_synthetic_index(3000, 8, 40, 2, seed=31, num_centroids=256, mode="codes")
+    Q = synthetic.make_queries(sx, 3, 48, seed=32)
+    ix = po.OracleIndex(centroids=sx.centroids, bucket_weights=sx.bucket_weights, codes=sx.codes, residuals=sx.residuals,
+                        doclens=sx.doclens, ivf=sx.ivf, ivf_lengths=sx.ivf_lengths, nbits=2)
+    scorer = pkg.IndexScorer(sx)
+    ndocs, thr = 64, 0.4
+    cfg = ColBERTConfig(ncells=2, centroid_score_threshold=thr, ndocs=ndocs)
+    keep_fn = lambda pids: pids[(pids % 3) != 1]                                   # noqa: E731
+    for b in range(Q.shape[0]):
+        q = Q[b]
+        cand, S = scorer.retrieve(cfg, q.unsqueeze(0))
+        cand2, S2 = scorer.retrieve(cfg, Q[(b + 1) % 3].unsqueeze(0))               # a later retrieve must not disturb ...
+        Sc = S.float().cpu().contiguous()
+        assert cand.numel() > 4 * ndocs                                             # ... the first one's tensors
+        assert torch.equal(cand.cpu(), po.candidate_pids(ix, po.get_cells(Sc, 2)))
+        for pid_list in (keep_fn(cand), cand, cand.flip(0)[: 3 * ndocs].contiguous()):
+            scores, pids = scorer.score_pids(cfg, q.unsqueeze(0), pid_list, S)
+            rp, rs = _oracle_score_pids(ix, q, pid_list.cpu(), Sc, thr, ndocs)
+            assert torch.equal(pids.cpu(), rp), "stage-2 pids of a filtered candidate list differ from the oracle"
+            assert ((scores.cpu() - rs).abs() <= SCORE_REL_TOL * rs.abs() + 1e-5).all()
+        p, s = scorer.rank(cfg, q.unsqueeze(0), filter_fn=keep_fn)
+        assert all(pid % 3 != 1 for pid in p) and s == sorted(s, reverse=True) and len(p) == ndocs // 4
+
+
+@pytest.mark.parametrize("qml", [16, 5])
+def test_query_maxlen_below_32(pkg, qml):
+    """An index / config with query_maxlen < 32: only the first query_maxlen tokens drive candidate generation and
+    the filter (`Q[:, :config.query_maxlen]`, index_storage.py:77), all tokens the exact MaxSim."""
+    from reranking_multimodal_retrievers_b200 import synthetic
+    from reranking_multimodal_retrievers_b200.engine import SearchEngine
+    from reranking_multimodal_retrievers_b200.index import DeviceIndex
+    sx = synthetic.make_synthetic_index(1500, 10, 60, 2, seed=41, num_centroids=512, mode="codes")
+    Q = synthetic.make_queries(sx, 5, 64, seed=42)
+    ix = po.OracleIndex(centroids=sx.centroids, bucket_weights=sx.bucket_weights, codes=sx.codes, residuals=sx.residuals,
+                        doclens=sx.doclens, ivf=sx.ivf, ivf_lengths=sx.ivf_lengths, nbits=2)
+    k, ndocs, ncells, thr = 20, 128, 2, 0.45
+    eng = SearchEngine(DeviceIndex(sx), query_maxlen=qml)
+    pids, scores, counts = eng.search_batch(Q, k=k, ncells=ncells, centroid_score_threshold=thr, ndocs=ndocs, keep_taps=True)
+    eng.check_flags()
+    t = eng.last_taps
+    full = SearchEngine(DeviceIndex(sx)).search_batch(Q, k=k, ncells=ncells, centroid_score_threshold=thr, ndocs=ndocs)
+    assert not torch.equal(full[0], pids)                      # the knob changes the outcome on this data
+    for b in range(Q.shape[0]):
+        S = t.S[b, :, :qml].float().cpu().contiguous()
+        r = po.rank(ix, Q[b], ncells, thr, ndocs, query_maxlen=qml, S_override=S, taps=True)
+        nc, n1, n2 = int(t.cand_counts[b]), int(t.stage1_counts[b]), int(t.stage2_counts[b])
+        assert torch.equal(t.cand_pids[b, :nc].cpu(), r["candidates"])
+        assert torch.equal(t.stage1_pids[b, :n1].cpu(), r["stage1_pids"])
+        assert torch.equal(t.stage1_scores[b, :n1].cpu(), r["stage1_scores"])
+        assert torch.equal(t.stage2_pids[b, :n2].cpu(), r["stage2_pids"])
+        sc = t.scores[b, :n2].cpu()
+        assert ((sc - r["scores_unsorted"]).abs() <= SCORE_REL_TOL * r["scores_unsorted"].abs() + 1e-5).all()
+    with pytest.raises(pkg.PlaidError):
+        SearchEngine(DeviceIndex(sx), query_maxlen=64)
