@@ -147,14 +147,49 @@ def run_cpu_sample(cs, Q, k, budget_s, max_queries, warm=True):
     for key in cs.stage_s:
         cs.stage_s[key] = 0.0
     t0 = time.perf_counter()
-    n, toks = 0, 0
+    n, toks, results = 0, 0, []
     while n < min(max_queries, Qc.shape[0]) and (time.perf_counter() - t0) < budget_s:
-        _, t3 = cs.search_all(Qc[n:n + 1], k)
+        res, t3 = cs.search_all(Qc[n:n + 1], k, remove_zero_tensors=True)
+        results.append(res[0])
         n += 1
         toks += t3
     dt = time.perf_counter() - t0
-    return dict(queries=n, seconds=dt, tokens=toks, kind=cs.kind, cores=cs.cores,
+    detail = ("the reference's compiled C++ operators (oracle/_ref: filter_pids / decompress_residuals / segmented_lookup / "
+              "segmented_maxsim .cpp, built from /root/reference) under a restatement of IndexScorer.rank's Python glue"
+              if cs.kind == "reference" else "single-thread C restatement of the reference operators (oracle/plaid_oracle.c)")
+    return dict(queries=n, seconds=dt, tokens=toks, kind=cs.kind, kind_detail=detail, cores=cs.cores, results=results,
                 stage_share={s: round(v / max(dt, 1e-9), 3) for s, v in cs.stage_s.items()})
+
+
+def agreement(ours, ref_results, k):
+    """End-to-end agreement when each side uses its OWN centroid-score table: ours = bf16 contraction, fp16
+    table, fp16 MaxSim operands; reference = fp32 throughout.  ours = (pids, scores, counts) tensors of the same queries."""
+    import torch
+    p, s, c = (t.cpu() for t in ours)
+    top1 = same_set = 0
+    overlap, max_rel, head = [], 0.0, 0
+    for b, (rp, rs) in enumerate(ref_results):
+        n = int(c[b])
+        mine = dict(zip(p[b, :n].tolist(), s[b, :n].tolist()))
+        theirs = dict(zip(rp, rs))
+        top1 += int(n > 0 and len(rp) > 0 and int(p[b, 0]) == rp[0])
+        common = set(mine) & set(theirs)
+        overlap.append(len(common) / max(len(rp), 1))
+        same_set += int(len(common) == len(rp) == n)
+        for pid in common:
+            max_rel = max(max_rel, abs(mine[pid] - theirs[pid]) / max(abs(theirs[pid]), 1e-6))
+        # rank identity on the well-separated head: reference entries whose gap to the next one exceeds 2e-3 * score
+        m = 0
+        while m < min(n, len(rp)) - 1 and rs[m] - rs[m + 1] > 2e-3 * abs(rs[m]) and int(p[b, m]) == rp[m]:
+            m += 1
+        head += m
+    nq = max(len(ref_results), 1)
+    return {"queries": len(ref_results), "k": k, "top1_agreement": top1 / nq, "overlap_at_k_mean": sum(overlap) / nq,
+            "overlap_at_k_min": min(overlap) if overlap else None, "identical_result_sets": same_set / nq,
+            "max_rel_score_err_common_pids": max_rel, "mean_identical_well_separated_head": head / nq,
+            "note": "each side uses its own centroid-score table (ours: bf16 operands, fp16 table; reference: fp32); integer "
+                    "stages are bit-exact only with an injected table (tests), so near-tie passages at the ndocs / ndocs/4 "
+                    "cut-offs may differ"}
 
 
 def bench_codec(args, w, peaks, rank, world, local_rank):
@@ -343,6 +378,7 @@ def main():
         for step in range(args.warmup + args.steps):
             lo = (step * sample_q) % max(1, Q.shape[0] - sample_q)
             r = run_cpu_sample(cs, Q[lo:lo + sample_q], w["k"], 1e9, sample_q, warm=(step == 0))
+            r.pop("results")
             info = r
             if step >= args.warmup:
                 tot_q += r["queries"]; tot_s += r["seconds"]; tot_tok += r["tokens"]
@@ -354,6 +390,7 @@ def main():
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{args.workload}: {w['desc']}", "step": f"{sample_q}-query sample of the batch"},
             "cpu_baseline": {"value": tok_s, "unit": "doc-tokens/s", "cores": info["cores"], "kind": info["kind"],
+                             "kind_detail": info["kind_detail"],
                              "sample": f"{tot_q} queries of the step's {w['B']} (reference CPU path, all host threads)",
                              "queries_per_s": tot_q / max(tot_s, 1e-9), "stage_share": info["stage_share"]},
             "e2e": {"value": tok_s, "unit": "doc-tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -387,28 +424,43 @@ def main():
     sx, Qdev = build_workload(w, rank, dev)
     index = DeviceIndex(sx, dev)
     index.pid_base = rank * w["N"]                      # this rank's shard of the N*world passage collection
-    eng = SearchEngine(index, fused=not args.no_fused)
+    # the reference-facing objects: Searcher over the resident shard, wrapped for the exchange when there are several
+    from reranking_multimodal_retrievers_b200 import Searcher, search_custom_collection
+    searcher = Searcher(index=index)
+    if args.no_fused:
+        searcher.ranker.engine.fused = False
+    eng = searcher.ranker.engine
+    ss = sharded.ShardedSearcher(searcher) if world > 1 else searcher
     B, Lq, k = w["B"], w["Lq"], w["k"]
     Qhost = Qdev.cpu().pin_memory()
+    queries = {i: f"question {i}" for i in range(B)}
     out_host = (torch.empty(B, k, dtype=torch.int32).pin_memory(), torch.empty(B, k, dtype=torch.float32).pin_memory(),
                 torch.empty(B, dtype=torch.int32).pin_memory())
 
     def step(q):
-        p, s, c = eng.search_batch(q, k=k)
+        # Searcher.search_batch: the whole path on one shard; with several ranks + one all-gather of the top-k blocks and
+        # the merge kernel (ShardedSearcher).  remove_zero_tensors=True as in the plugin call (src/models/flmr/searching.py:54-61)
+        out = ss.search_batch(q, k, True)
         if world > 1:
-            gathered = sharded.all_gather_lists(sharded.pack_lists(p, s, c), world)
-            gp, gs, gc = sharded.unpack_lists(gathered, k)
-            p, s, c = sharded.merge_topk(gs, gp, gc, k)
             eng.launch_count += 1
-        return p, s, c
+        return out
 
-    def step_e2e():
-        # the public call with HOST (pinned) query embeddings: the engine copies them chunk by chunk on a copy
+    def step_e2e_engine():
+        # HOST (pinned) query embeddings in, device lists out + D2H: the engine copies the queries chunk by chunk on a copy
         # stream, one chunk ahead of the search (H2D of this step's inputs is inside the timed region)
         p, s, c = step(Qhost)
         out_host[0].copy_(p, non_blocking=True); out_host[1].copy_(s, non_blocking=True)
         out_host[2].copy_(c, non_blocking=True)         # D2H of the step's result
         torch.cuda.current_stream().synchronize()
+
+    api_result = [None]
+
+    def step_api():
+        # the plugin call of the reference: search_custom_collection -> _search_all_Q -> Ranking
+        # (src/models/flmr/searching.py:43-63, CB/searcher.py:80-93), host embeddings in, Ranking object out
+        api_result[0] = search_custom_collection(ss, queries, Qhost, num_document_to_retrieve=k, remove_zero_tensors=True)
+        if world > 1:
+            eng.launch_count += 1
 
     def timed(fn, steps, sampler=None):
         if world > 1:
@@ -431,7 +483,7 @@ def main():
         return float(ms.item()), clocks
 
     # accounting pass (untimed): tokens entering each stage, summed over the batch
-    stats = dict(ncand=0, T1=0, T2=0, T3=0, found=0)
+    stats = dict(ncand=0, T1=0, T2=0, T3=0, T3_padded=0, found=0, ivf_visits=0, ivf_pairs=0, ivf_survivors=0, scan_queries=0)
 
     def account(ws, n):
         dl = index.doclens
@@ -443,10 +495,16 @@ def main():
         m1 = torch.arange(ws["s1_pids"].shape[1], device=dev).unsqueeze(0) < c1.unsqueeze(1)
         stats["T2"] += int(dl[torch.where(m1, ws["s1_pids"][:n], 0).long()].mul(m1).sum())
         c2 = ws["s2_counts"][:n].long()
-        stats["T3"] += int(ws["tok_offsets"][:n].gather(1, c2.unsqueeze(1)).sum())
-        stats["found"] += int(ws["out_counts"][:n].sum())
+        m2 = torch.arange(ws["s2_pids"].shape[1], device=dev).unsqueeze(0) < c2.unsqueeze(1)
+        stats["T3"] += int(dl[torch.where(m2, ws["s2_pids"][:n], 0).long()].mul(m2).sum())     # REAL passage tokens
+        stats["T3_padded"] += int(ws["tok_offsets"][:n].gather(1, c2.unsqueeze(1)).sum())       # + 32-token alignment rows
+        meta = ws["ivf_meta"][:n].long()                # per query: survivors, pairs, scan flag, list entries visited
+        use = meta[:, 2] == 0
+        stats["ivf_survivors"] += int(meta[use, 0].sum()); stats["ivf_pairs"] += int(meta[use, 1].sum())
+        stats["ivf_visits"] += int(meta[use, 3].sum()); stats["scan_queries"] += int((~use).sum())
 
-    eng.search_batch(Qdev, k=k, on_chunk=account)
+    acc_p, acc_s, acc_c = eng.search_batch(Qdev, k=k, remove_zero_rows=True, on_chunk=account)
+    stats["found"] = int(acc_c.sum())
     torch.cuda.synchronize()
     eng.check_flags()
 
@@ -464,11 +522,22 @@ def main():
     for stage, a, b in events:
         stage_ms.setdefault(stage, []).append(a.elapsed_time(b))
     eng.check_flags()
-    # timed region 2: end to end through host buffers
+    # timed region 2: end to end through the reference-facing plugin call (host embeddings in, Ranking out)
     for _ in range(2):
-        step_e2e()
-    ms_e2e, _ = timed(step_e2e, args.steps)
+        step_api()
+    l1 = eng.launch_count
+    ms_e2e, _ = timed(step_api, args.steps)
+    launches_api = eng.launch_count - l1
+    # timed region 3: the same with the engine-level call (device lists + D2H, no Ranking object)
+    for _ in range(2):
+        step_e2e_engine()
+    ms_e2e_engine, _ = timed(step_e2e_engine, args.steps)
     clocks = sampler.stop_after_min_samples(lambda: step(Qdev))
+    # what a consumer pays on top when it turns the whole Ranking into Python tuples (untimed extra, host only)
+    t0 = time.perf_counter()
+    rk_dict = api_result[0].todict()
+    todict_ms = (time.perf_counter() - t0) * 1e3
+    assert len(rk_dict) == B and (world > 1 or sum(len(v) for v in rk_dict.values()) == stats["found"])
 
     if rank != 0:
         if world > 1:
@@ -479,15 +548,20 @@ def main():
     C, nbits = index.num_centroids, index.nbits
     chunks = (B + eng.chunk_size(B) - 1) // eng.chunk_size(B)
     T1, T2, T3, ncand = stats["T1"], stats["T2"], stats["T3"], stats["ncand"]
+    T3p = stats["T3_padded"]
     # ALGORITHMIC bytes / flops per step, per stage
     s_row = 64.0 if eng.s_dtype == torch.float16 else 128.0
     alg = {
         "centroid_scores": dict(bytes=(2.0 if eng.s_dtype == torch.float16 else 4.0) * C * 32 * B + 2.0 * C * 128 * chunks,
                                 flops=2.0 * C * 128 * 32 * B),
-        # the token scan's bytes; the inverted-file route stage 1 normally takes reads far less, so this stage can show
-        # more than the scan's roofline
-        "filter_stage1": dict(bytes=4.0 * T1 + 16.0 * ncand, flops=0.0,
-                              note="bytes = the token scan's model; the inverted-file route reads far less, so > 1 is expected"),
+        # inverted-file route: every visited IVF entry costs its pid (4 B) + the candidate-bitmap word and
+        # the word-prefix count that turn it into a slot (4 + 4 B); every (slot, centroid) pair is written and read back
+        # (2 x 8 B) and gathers one S row; one score per candidate goes out.  Queries routed to the token scan instead
+        # read 4 B per candidate token.
+        "filter_stage1": dict(bytes=12.0 * stats["ivf_visits"] + (16.0 + s_row) * stats["ivf_pairs"] + 4.0 * ncand
+                              + (4.0 * T1 / max(B, 1)) * stats["scan_queries"], flops=0.0,
+                              note="issue / latency bound (warp-level list walks and a shared-memory counting sort); the byte "
+                                   "model is the inverted-file route's, not the token scan's"),
         # every token gathers one score row, but a query has only C distinct rows and re-reads are L2 hits: the
         # compulsory HBM traffic is each touched row once
         "filter_stage2": dict(bytes=4.0 * T2 + 16.0 * 1024 * B + s_row * min(T2, float(C) * B), flops=0.0),
@@ -496,7 +570,8 @@ def main():
         "decompress": dict(bytes=(4.0 + 16 * nbits + 256.0) * T3 + 256.0 * min(T3, float(C) * chunks), flops=0.0),
         "maxsim": dict(bytes=256.0 * T3, flops=2.0 * Lq * 128 * T3,
                        note="reads D right after decompress wrote it: part of it is still in L2"),
-        "maxsim_fused": dict(bytes=(4.0 + 16 * nbits) * T3, flops=2.0 * Lq * 128 * T3),    # K4' of SURVEY 8d
+        # K4' of SURVEY 8d on REAL passage tokens (the 32-token alignment rows the tiles also carry are not counted)
+        "maxsim_fused": dict(bytes=(4.0 + 16 * nbits) * T3, flops=2.0 * Lq * 128 * T3),
     }
     kernels = {}
     for stage, v in stage_ms.items():
@@ -530,8 +605,9 @@ def main():
                     "algorithmic_bytes_per_launch": alg[dom]["bytes"] / nl, "avg_launch_ms": round(per_launch_s * 1e3, 4)}
     roofline["frac"] = round(roofline["achieved"] / roofline["peak"], 4)
 
-    tok_s = world * T3 / (ms_step * 1e-3)               # every rank exact-scores ~T3 tokens of its own shard
+    tok_s = world * T3 / (ms_step * 1e-3)               # every rank exact-scores ~T3 (real) tokens of its own shard
     e2e_ms = ms_e2e / args.steps
+    e2e_engine_ms = ms_e2e_engine / args.steps
     line = {
         "metric": "scored_doc_tokens_per_s", "value": tok_s, "unit": "doc-tokens/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
@@ -541,15 +617,29 @@ def main():
                    "centroids": C, "queries_per_step": B, "parallelism": f"pid-range shards x{world}, all-gather top-k merge",
                    "l2": "inputs larger than L2 (index + centroid-score table >> 126 MB), no explicit flush",
                    "candidates_per_query": ncand / B, "T1_tokens_per_query": T1 / B, "T2_tokens_per_query": T2 / B,
-                   "T3_tokens_per_query": T3 / B, "results_per_query": stats["found"] / B},
+                   "T3_tokens_per_query": T3 / B, "T3_padded_tokens_per_query": T3p / B,
+                   "token_accounting": "T1/T2/T3 count real passage tokens (doclens of the listed pids), as the reference arm does; "
+                                       "T3_padded adds the 32-token alignment rows of the MaxSim tiles and is not used in any rate",
+                   "results_per_query": stats["found"] / B},
         "e2e": {"value": world * T3 / (e2e_ms * 1e-3), "unit": "doc-tokens/s", "queries_per_s": B / (e2e_ms * 1e-3),
-                "ms_per_step": e2e_ms, "h2d_bytes_per_step": B * Lq * 128 * 4, "d2h_bytes_per_step": B * k * 8 + B * 4},
+                "ms_per_step": e2e_ms, "h2d_bytes_per_step": B * Lq * 128 * 4, "d2h_bytes_per_step": B * k * 8 + B * 4,
+                "call": "search_custom_collection(searcher, queries, Q_host, k, remove_zero_tensors=True) -> Ranking "
+                        "(src/models/flmr/searching.py:43-63 -> CB/searcher.py:80-93); pinned host embeddings in, Ranking over "
+                        "host arrays out, rows become Python tuples on access",
+                "gpu_launches": launches_api,
+                "ranking_todict_ms": round(todict_ms, 3),
+                "ranking_todict_note": "host-only cost of turning all B x k results into Python tuples (Ranking.todict()), "
+                                       "outside the timed region; the reference pays the same per-query tolist/zip inside its loop",
+                "engine_level": {"ms_per_step": e2e_engine_ms, "queries_per_s": B / (e2e_engine_ms * 1e-3),
+                                 "value": world * T3 / (e2e_engine_ms * 1e-3),
+                                 "call": "Searcher.search_batch(Q_host) + D2H of (pids, scores, counts) into pinned buffers"}},
         "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "kernels": kernels,
     }
     if world == 1 and not args.no_cpu_baseline:
         r = run_cpu_sample(make_cpu_searcher(sx), Qdev, k, args.cpu_budget_s, 64)
+        line["agreement"] = agreement((acc_p, acc_s, acc_c), r["results"], k)
         line["cpu_baseline"] = {"value": r["tokens"] / r["seconds"], "unit": "doc-tokens/s", "cores": r["cores"],
-                                "kind": r["kind"], "queries_per_s": r["queries"] / r["seconds"],
+                                "kind": r["kind"], "kind_detail": r["kind_detail"], "queries_per_s": r["queries"] / r["seconds"],
                                 "sample": f"first {r['queries']} of the step's {B} queries, same index, {r['seconds']:.1f} s",
                                 "stage_share": r["stage_share"]}
     sys.stdout.flush()

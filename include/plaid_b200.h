@@ -267,6 +267,14 @@ int plaid_merge_topk(const float* scores, const int32_t* pids, const int32_t* co
                      int32_t* out_pids, float* out_scores, int32_t* out_counts, uint64_t* ws_keys,
                      void* stream);
 
+/* The same merge reading the all-gather's receive buffer IN PLACE: every rank's message is one i32 block
+ * [B*k pids | B*k score bit patterns | B counts] (what the final plaid_select_top of the rank wrote straight into
+ * its send buffer), gathered = [G] such blocks.  pid_bases (i32 [G], may be NULL) = first global pid of every
+ * rank's shard, added to the shard-local pids while the keys are built. */
+int plaid_merge_topk_msg(const int32_t* gathered, int G, int B, int k, const int32_t* pid_bases,
+                         int32_t* out_pids, float* out_scores, int32_t* out_counts, uint64_t* ws_keys,
+                         void* stream);
+
 /* ---- a11: ragged gather (CB/search/segmented_lookup.cpp:36-125) ------------------------------
  * out rows = concatenation over i of input[offsets[i] .. offsets[i]+lengths[i]) (row_bytes each);
  * out_offsets = exclusive prefix sum of lengths (device, n+1). */

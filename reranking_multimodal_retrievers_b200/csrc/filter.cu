@@ -512,9 +512,11 @@ select_top_kernel(const int32_t* __restrict__ pids, const float* __restrict__ sc
                     out_scores ? out_scores + (size_t)b * out_stride : nullptr, out_counts ? out_counts + b : nullptr);
 }
 
-// gathered layout [G, B, k] -> per query G*k keys
+// gathered lists of G ranks -> per query G*k keys.  List g of query b: scores/pids + g*sp_stride + b*k (k entries),
+// count at counts[g*c_stride + b]; pid_bases (optional) turns shard-local pids into global ones.
 __global__ void __launch_bounds__(kSelThreads)
 merge_topk_kernel(const float* __restrict__ scores, const int32_t* __restrict__ pids, const int32_t* __restrict__ counts,
+                  int64_t sp_stride, int64_t c_stride, const int32_t* __restrict__ pid_bases,
                   int G, int B, int k, int sel_cap, int32_t* __restrict__ out_pids, float* __restrict__ out_scores,
                   int32_t* __restrict__ out_counts, uint64_t* __restrict__ ws_keys) {
     extern __shared__ __align__(16) unsigned char s_raw[];
@@ -529,7 +531,7 @@ merge_topk_kernel(const float* __restrict__ scores, const int32_t* __restrict__ 
         int acc = 0;
         for (int g = 0; g < G; g++) {
             s_hist[g] = acc;
-            acc += min(max(counts[(size_t)g * B + b], 0), k);
+            acc += min(max(counts[(size_t)g * c_stride + b], 0), k);
         }
         s_hist[G] = acc;
     }
@@ -537,10 +539,10 @@ merge_topk_kernel(const float* __restrict__ scores, const int32_t* __restrict__ 
     const int n = s_hist[G];
     for (int t = threadIdx.x; t < G * k; t += blockDim.x) {
         const int g = t / k, i = t - g * k;
-        const int cnt = min(max(counts[(size_t)g * B + b], 0), k);
+        const int cnt = (g + 1 < G ? s_hist[g + 1] : n) - s_hist[g];
         if (i < cnt) {
-            const size_t src = ((size_t)g * B + b) * k + i;
-            keys[s_hist[g] + i] = make_key(scores[src], pids[src]);
+            const size_t src = (size_t)g * sp_stride + (size_t)b * k + i;
+            keys[s_hist[g] + i] = make_key(scores[src], pids[src] + (pid_bases ? pid_bases[g] : 0));
         }
     }
     __syncthreads();
@@ -1004,12 +1006,10 @@ extern "C" int plaid_filter_pids(const int32_t* pids, const int32_t* counts, int
                          stage2_counts, ndocs / 4, ws_keys, st);
 }
 
-extern "C" int plaid_merge_topk(const float* scores, const int32_t* pids, const int32_t* counts, int G, int B, int k,
-                                int32_t* out_pids, float* out_scores, int32_t* out_counts, uint64_t* ws_keys,
-                                void* stream) {
+static int launch_merge(const float* scores, const int32_t* pids, const int32_t* counts, int64_t sp_stride, int64_t c_stride,
+                        const int32_t* pid_bases, int G, int B, int k, int32_t* out_pids, float* out_scores,
+                        int32_t* out_counts, uint64_t* ws_keys, cudaStream_t st) {
     using namespace plaid;
-    PLAID_CHECK_ARG(scores && pids && counts && out_pids && out_scores && ws_keys, PLAID_ERR_ARG,
-                    "plaid_merge_topk: null pointer");
     PLAID_CHECK_ARG(G >= 1 && G <= 64 && B >= 0 && k >= 1 && k <= 16384, PLAID_ERR_UNSUPPORTED,
                     "plaid_merge_topk: G=%d (1..64), k=%d (1..16384)", G, k);
     if (B == 0) return PLAID_OK;
@@ -1017,8 +1017,27 @@ extern "C" int plaid_merge_topk(const float* scores, const int32_t* pids, const 
     const size_t smem = (size_t)(sel_cap + kBktCap + kRankMax) * 8 + 256 * 4 + 16;
     static int configured[kMaxDevices] = {0};
     if (int rc = ensure_dynamic_smem((const void*)merge_topk_kernel, (int)smem, configured)) return rc;
-    merge_topk_kernel<<<B, kSelThreads, smem, (cudaStream_t)stream>>>(scores, pids, counts, G, B, k, sel_cap, out_pids,
-                                                                      out_scores, out_counts, ws_keys);
+    merge_topk_kernel<<<B, kSelThreads, smem, st>>>(scores, pids, counts, sp_stride, c_stride, pid_bases, G, B, k, sel_cap,
+                                                    out_pids, out_scores, out_counts, ws_keys);
     PLAID_LAUNCH_OK("merge_topk_kernel");
     return PLAID_OK;
+}
+
+extern "C" int plaid_merge_topk(const float* scores, const int32_t* pids, const int32_t* counts, int G, int B, int k,
+                                int32_t* out_pids, float* out_scores, int32_t* out_counts, uint64_t* ws_keys,
+                                void* stream) {
+    PLAID_CHECK_ARG(scores && pids && counts && out_pids && out_scores && ws_keys, PLAID_ERR_ARG,
+                    "plaid_merge_topk: null pointer");
+    return launch_merge(scores, pids, counts, (int64_t)B * k, B, nullptr, G, B, k, out_pids, out_scores, out_counts, ws_keys,
+                        (cudaStream_t)stream);
+}
+
+extern "C" int plaid_merge_topk_msg(const int32_t* gathered, int G, int B, int k, const int32_t* pid_bases,
+                                    int32_t* out_pids, float* out_scores, int32_t* out_counts, uint64_t* ws_keys,
+                                    void* stream) {
+    PLAID_CHECK_ARG(gathered && out_pids && out_scores && ws_keys, PLAID_ERR_ARG, "plaid_merge_topk_msg: null pointer");
+    PLAID_CHECK_ARG(B >= 0 && k >= 1, PLAID_ERR_ARG, "plaid_merge_topk_msg: bad sizes");
+    const int64_t stride = 2 * (int64_t)B * k + B;     // one rank's message: pids | score bits | counts
+    return launch_merge(reinterpret_cast<const float*>(gathered + (int64_t)B * k), gathered, gathered + 2 * (int64_t)B * k,
+                        stride, stride, pid_bases, G, B, k, out_pids, out_scores, out_counts, ws_keys, (cudaStream_t)stream);
 }

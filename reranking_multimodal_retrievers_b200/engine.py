@@ -247,8 +247,10 @@ class SearchEngine:
             torch.clamp(ws["qlens"], max=self.query_maxlen, out=ws["cqlens"])
         return ws["cqlens"]
 
-    def stage_rank(self, ws, b: int, Lq_pad: int, ndocs: int, k: int, Bc: int):
-        """a5-a10: two-stage filter, decompression, exact MaxSim, top-k -- on ws['cand_pids'/'S'/'idx_bits']."""
+    def stage_rank(self, ws, b: int, Lq_pad: int, ndocs: int, k: int, Bc: int, out=None, out_stride=None):
+        """a5-a10: two-stage filter, decompression, exact MaxSim, top-k -- on ws['cand_pids'/'S'/'idx_bits'].
+        out = (pids, scores, counts) raw pointers of the rows the final top-k is written to (row stride out_stride);
+        default: the workspace's out_* buffers."""
         ix = self.index
         st = _stream()
         C = ix.num_centroids
@@ -287,24 +289,27 @@ class SearchEngine:
                  _p(ix.codes), _p(ix.centroids_f16), C, ix.nbits, _p(D), st)
             call("maxsim", "plaid_maxsim_packed", _p(ws["Qh"]), _p(ws["qlens"]), b, Bc, Lq_pad, _p(D), _p(ws["tok_offsets"]),
                  _p(ws["s2_counts"]), nd4, ws["tok_stride"], 1, 1, 1, _p(ws["scores"]), wd, st)
-        call("topk", "plaid_select_top", _p(ws["s2_pids"]), _p(ws["scores"]), _p(ws["s2_counts"]), b, nd4, k, _p(ws["out_pids"]),
-             _p(ws["out_scores"]), _p(ws["out_counts"]), k, _p(ws["ws_keys"]), st)
+        op, os_, oc = out if out is not None else (_p(ws["out_pids"]), _p(ws["out_scores"]), _p(ws["out_counts"]))
+        call("topk", "plaid_select_top", _p(ws["s2_pids"]), _p(ws["scores"]), _p(ws["s2_counts"]), b, nd4, k, op, os_, oc,
+             out_stride or k, _p(ws["ws_keys"]), st)
 
     def _run_chunk(self, Qc: torch.Tensor, Lq_pad: int, ncells: int, thr: float, ndocs: int, k: int,
-                   remove_zero_rows: bool, Bc: int):
+                   remove_zero_rows: bool, Bc: int, out=None, out_stride=None):
         """Qc f32 [b, Lq, 128] on device, b <= Bc.  Enqueues the whole pipeline; returns the workspace."""
         ws = self._workspace(Bc, Lq_pad, ncells, ndocs, k)
         self.stage_candidates(ws, Qc, Lq_pad, ncells, thr, remove_zero_rows, Bc)
-        self.stage_rank(ws, Qc.shape[0], Lq_pad, ndocs, k, Bc)
+        self.stage_rank(ws, Qc.shape[0], Lq_pad, ndocs, k, Bc, out, out_stride)
         return ws
 
     # ----------------------------------------------------------------------------------- public
     def search_batch(self, Q: torch.Tensor, k: int = 100, ncells: int | None = None,
                      centroid_score_threshold: float | None = None, ndocs: int | None = None,
                      remove_zero_rows: bool = False, global_pids: bool = True, keep_taps: bool = False,
-                     on_chunk=None):
+                     on_chunk=None, out=None):
         """Q f32 [B, Lq, 128] (host or device) -> (pids i32 [B, k], scores f32 [B, k], counts i32 [B]) on
-        the device.  Slots past counts[b] hold pid -1 / score -inf."""
+        the device.  Slots past counts[b] hold pid -1 / score -inf.  `out` = preallocated contiguous result tensors
+        (the sharded search passes views of its all-gather send buffer); the last kernel of every chunk writes its
+        rows straight into them."""
         d_ncells, d_thr, d_ndocs = search_defaults(k)
         ncells = d_ncells if ncells is None else int(ncells)
         thr = d_thr if centroid_score_threshold is None else float(centroid_score_threshold)
@@ -316,9 +321,19 @@ class SearchEngine:
         B, Lq, dim = Q.shape
         Lq_pad = ((Lq + 31) // 32) * 32
         kk = min(k, ndocs // 4)
-        out_p = torch.full((B, k), -1, device=dev, dtype=torch.int32)
-        out_s = torch.full((B, k), float("-inf"), device=dev, dtype=torch.float32)
-        out_c = torch.zeros(B, device=dev, dtype=torch.int32)
+        if out is not None:
+            out_p, out_s, out_c = out
+            assert out_p.shape == (B, k) and out_s.shape == (B, k) and out_c.shape == (B,)
+            assert out_p.is_contiguous() and out_s.is_contiguous() and out_c.is_contiguous()
+            assert out_p.dtype == torch.int32 and out_s.dtype == torch.float32 and out_c.dtype == torch.int32
+        else:
+            out_p = torch.empty((B, k), device=dev, dtype=torch.int32)
+            out_s = torch.empty((B, k), device=dev, dtype=torch.float32)
+            out_c = torch.empty(B, device=dev, dtype=torch.int32)
+        if B == 0 or ix.num_passages == 0 or kk < k:       # the kernels fill exactly kk columns of every row
+            out_p.fill_(-1)
+            out_s.fill_(float("-inf"))
+            out_c.zero_()
         if B == 0 or ix.num_passages == 0:
             return out_p, out_s, out_c
         if torch.cuda.current_device() != dev.index:
@@ -331,13 +346,12 @@ class SearchEngine:
         for ci, b0 in enumerate(range(0, B, Bc)):
             b1 = min(B, b0 + Bc)
             Qc = Qd[b0:b1] if feed is None else feed.chunk(ci)
-            ws = self._run_chunk(Qc, Lq_pad, ncells, thr, ndocs, kk, remove_zero_rows, Bc)
+            rows = (ctypes.c_void_p(out_p.data_ptr() + b0 * k * 4), ctypes.c_void_p(out_s.data_ptr() + b0 * k * 4),
+                    ctypes.c_void_p(out_c.data_ptr() + b0 * 4))
+            ws = self._run_chunk(Qc, Lq_pad, ncells, thr, ndocs, kk, remove_zero_rows, Bc, rows, k)
             if feed is not None:
                 feed.release(ci)
             n = b1 - b0
-            out_p[b0:b1, :kk] = ws["out_pids"][:n]
-            out_s[b0:b1, :kk] = ws["out_scores"][:n]
-            out_c[b0:b1] = ws["out_counts"][:n]
             if on_chunk is not None:
                 on_chunk(ws, n)
             if keep_taps:
@@ -348,7 +362,7 @@ class SearchEngine:
                     stage2_scores=ws["s2_scores"], stage2_counts=ws["s2_counts"], tok_offsets=ws["tok_offsets"],
                     D=ws["D"], tok_stride=ws["tok_stride"], scores=ws["scores"])
         if global_pids and ix.pid_base:
-            out_p = torch.where(out_p >= 0, out_p + ix.pid_base, out_p)
+            out_p.add_((out_p >= 0).to(torch.int32) * ix.pid_base)
         return out_p, out_s, out_c
 
     def _host_feed(self, Q: torch.Tensor, Bc: int):

@@ -145,6 +145,7 @@ class DeviceIndex:
         if self.dim != ops.DIM:
             raise ValueError(f"index dim {self.dim} != {ops.DIM}")
         self.pid_base = int(getattr(host, "pid_base", 0))
+        self.config = getattr(host, "config", None)
         with torch.cuda.device(dev):
             self.doclens = host.doclens.to(dev, torch.int64).contiguous()
             self.num_passages = int(self.doclens.numel())

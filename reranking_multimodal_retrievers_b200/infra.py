@@ -139,19 +139,81 @@ class Queries:
         return self.path
 
 
+class _LazyRows:
+    """Mapping qid -> [(pid, rank, score), ...] over the arrays a batched search returns.  Rows become Python tuples
+    only when they are looked at: building 1024 x 100 tuples costs several times the GPU search itself, and most
+    consumers (`ranking_to_batch_results`, metrics) touch each row once or work from `Ranking.arrays()`."""
+
+    def __init__(self, qids, pids, scores, counts):
+        self._qids = list(qids)
+        self._row_of = None
+        self._pids, self._scores, self._counts = pids, scores, counts
+        self._cache = {}
+
+    def _row(self, i):
+        row = self._cache.get(i)
+        if row is None:
+            n = int(self._counts[i])
+            row = list(zip(self._pids[i, :n].tolist(), range(1, n + 1), self._scores[i, :n].tolist()))
+            self._cache[i] = row
+        return row
+
+    def __getitem__(self, qid):
+        if self._row_of is None:
+            self._row_of = {q: i for i, q in enumerate(self._qids)}
+        return self._row(self._row_of[qid])
+
+    def __len__(self):
+        return len(self._qids)
+
+    def __iter__(self):
+        return iter(self._qids)
+
+    def __contains__(self, qid):
+        if self._row_of is None:
+            self._row_of = {q: i for i, q in enumerate(self._qids)}
+        return qid in self._row_of
+
+    def keys(self):
+        return list(self._qids)
+
+    def values(self):
+        return (self._row(i) for i in range(len(self._qids)))
+
+    def items(self):
+        return ((q, self._row(i)) for i, q in enumerate(self._qids))
+
+
 class Ranking:
-    """qid -> [(pid, rank, score), ...] (CB/data/ranking.py:25-80)."""
+    """qid -> [(pid, rank, score), ...] (CB/data/ranking.py:25-80).  `data` is either a plain dict (as in the
+    reference) or the lazy view over result arrays that `Searcher._search_all_Q` builds (`Ranking.from_arrays`)."""
 
     def __init__(self, data, provenance=None):
         self.data = data
         self._provenance = provenance
-        self.flat_ranking = [(qid, *rest) for qid, sub in data.items() for rest in sub]
+        self._flat = None
+
+    @classmethod
+    def from_arrays(cls, qids, pids, scores, counts, provenance=None):
+        """pids i32 / scores f32 numpy [B, k], counts [B]: rows are materialised on access."""
+        return cls(_LazyRows(qids, pids, scores, counts), provenance)
+
+    def arrays(self):
+        """(qids, pids [B, k], scores [B, k], counts [B]) when built from arrays, else None."""
+        d = self.data
+        return (d._qids, d._pids, d._scores, d._counts) if isinstance(d, _LazyRows) else None
+
+    @property
+    def flat_ranking(self):
+        if self._flat is None:
+            self._flat = [(qid, *rest) for qid, sub in self.data.items() for rest in sub]
+        return self._flat
 
     def provenance(self):
         return self._provenance
 
     def todict(self):
-        return dict(self.data)
+        return dict(self.data.items())
 
     def tolist(self):
         return list(self.flat_ranking)

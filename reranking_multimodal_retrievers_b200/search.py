@@ -32,10 +32,10 @@ class IndexScorer:
         if isinstance(index_path, (str, os.PathLike)):
             self.index_path = str(index_path)
             host = load_reference_index(self.index_path, pid_range)
-        else:  # an in-memory HostIndex / SyntheticIndex
+        else:  # an in-memory HostIndex / SyntheticIndex, or an index that is already resident (DeviceIndex)
             self.index_path = None
             host = index_path
-        self.index = DeviceIndex(host, device)
+        self.index = host if isinstance(host, DeviceIndex) else DeviceIndex(host, device)
         qml = int((getattr(host, "config", None) or {}).get("query_maxlen", ops.NQ_MAX) or ops.NQ_MAX)
         self.engine = SearchEngine(self.index, query_maxlen=qml)            # batched path (Searcher.search_batch)
         # single-query API of the reference: fp32 centroid_scores, and stage 1 by the code scan -- `score_pids` takes ANY
@@ -243,16 +243,30 @@ class Searcher:
                     for i in range(Q.size(0))]
         else:
             p, s, c = self.search_batch(Q, k, remove_zero_tensors)
+            hp, hs, hc = self._host_results(p, s, c)              # one pinned D2H + one synchronisation
             self.ranker.engine.check_flags()
-            p, s, c = p.cpu(), s.cpu(), c.cpu().tolist()
-            rows = []
-            for i in range(Q.size(0)):
-                n = c[i]
-                rows.append(list(zip(p[i, :n].tolist(), range(1, k + 1), s[i, :n].tolist())))
+            provenance = {"source": "Searcher::search_all", "queries": queries.provenance(),
+                          "config": self.config.export(), "k": k}
+            return Ranking.from_arrays(queries.keys(), hp, hs, hc, provenance)
         data = {qid: val for qid, val in zip(queries.keys(), rows)}
         provenance = {"source": "Searcher::search_all", "queries": queries.provenance(),
                       "config": self.config.export(), "k": k}
         return Ranking(data=data, provenance=provenance)
+
+    def _host_results(self, p, s, c):
+        """Device lists -> numpy arrays through pinned staging buffers (fresh numpy copies: the Ranking owns them)."""
+        B, k = p.shape
+        key = (B, k)
+        if getattr(self, "_pinned_key", None) != key:
+            self._pinned = (torch.empty(B, k, dtype=torch.int32).pin_memory(), torch.empty(B, k, dtype=torch.float32).pin_memory(),
+                            torch.empty(B, dtype=torch.int32).pin_memory())
+            self._pinned_key = key
+        hp, hs, hc = self._pinned
+        hp.copy_(p, non_blocking=True)
+        hs.copy_(s, non_blocking=True)
+        hc.copy_(c, non_blocking=True)
+        torch.cuda.current_stream(p.device).synchronize()
+        return hp.numpy().copy(), hs.numpy().copy(), hc.numpy().copy()
 
 
 # re-exported so `from ... import colbert_score` works like `colbert.modeling.colbert`

@@ -57,20 +57,83 @@ def all_gather_lists(msg: torch.Tensor, world_size: int, group=None) -> torch.Te
     return flat.view(world_size, msg.shape[0], msg.shape[1])
 
 
+class ListExchange:
+    """The exchange step with persistent buffers: every rank's final top-k kernel writes its (local pids | score bits |
+    counts) straight into the send block, ONE all_gather_into_tensor moves the blocks, and the merge kernel reads the
+    receive buffer in place (adding each rank's pid base).  No pack / unpack kernels, no per-step allocations."""
+
+    def __init__(self, B: int, k: int, device, group=None):
+        self.B, self.k, self.group = B, k, group
+        self.world_size = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        n = 2 * B * k + B
+        self.send = torch.empty(n, device=device, dtype=torch.int32)
+        self.recv = torch.empty(self.world_size * n, device=device, dtype=torch.int32)
+        self.out_p = torch.empty(B, k, device=device, dtype=torch.int32)
+        self.out_s = torch.empty(B, k, device=device, dtype=torch.float32)
+        self.out_c = torch.empty(B, device=device, dtype=torch.int32)
+        self.ws = torch.empty(max(B * self.world_size * k, 1), device=device, dtype=torch.int64)
+        self.pid_bases = None
+
+    def views(self):
+        """(pids [B,k] i32, scores [B,k] f32, counts [B] i32) views of the send block."""
+        B, k = self.B, self.k
+        return (self.send[: B * k].view(B, k), self.send[B * k: 2 * B * k].view(torch.float32).view(B, k),
+                self.send[2 * B * k:])
+
+    def set_pid_base(self, pid_base: int):
+        mine = torch.tensor([pid_base], device=self.send.device, dtype=torch.int32)
+        bases = torch.empty(self.world_size, device=self.send.device, dtype=torch.int32)
+        dist.all_gather_into_tensor(bases, mine, group=self.group)
+        self.pid_bases = bases
+
+    def exchange_and_merge(self):
+        """all-gather of the send blocks + merge; returns (pids, scores, counts) [B, k] (global pids)."""
+        dist.all_gather_into_tensor(self.recv, self.send, group=self.group)
+        _lib.call("plaid_merge_topk_msg", _p(self.recv), self.world_size, self.B, self.k, _p(self.pid_bases),
+                  _p(self.out_p), _p(self.out_s), _p(self.out_c), _p(self.ws), _stream())
+        return self.out_p, self.out_s, self.out_c
+
+
 class ShardedSearcher:
-    """Wraps a per-rank `Searcher` (built with pid_range = this rank's shard)."""
+    """Wraps a per-rank `Searcher` (built with pid_range = this rank's shard).  `search_batch` and `_search_all_Q`
+    have the single-GPU Searcher's signatures, so `search_custom_collection(sharded_searcher, ...)` works unchanged."""
 
     def __init__(self, searcher, group=None):
         self.searcher = searcher
         self.group = group
         self.world_size = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.config = searcher.config
+        self._xchg = None
+
+    def _exchange(self, B, k):
+        if self._xchg is None or (self._xchg.B, self._xchg.k) != (B, k):
+            ix = self.searcher.ranker.index
+            self._xchg = ListExchange(B, k, ix.device, self.group)
+            self._xchg.set_pid_base(ix.pid_base)
+        return self._xchg
 
     def search_batch(self, Q: torch.Tensor, k=100, remove_zero_tensors=False):
-        p, s, c = self.searcher.search_batch(Q, k, remove_zero_tensors)   # global pids already
+        """-> merged (pids, scores, counts) [B, k]; the returned tensors are reused by the next call."""
         if self.world_size == 1:
-            return p, s, c
-        msg = pack_lists(p, s, c)
-        gathered = all_gather_lists(msg, self.world_size, self.group)
-        gp, gs, gc = unpack_lists(gathered, k)
-        return merge_topk(gs, gp, gc, k)
+            return self.searcher.search_batch(Q, k, remove_zero_tensors)
+        s = self.searcher
+        s._defaults(k)
+        c = s.config
+        x = self._exchange(Q.shape[0], k)
+        s.ranker.engine.search_batch(Q, k=k, ncells=c.ncells, centroid_score_threshold=c.centroid_score_threshold,
+                                     ndocs=c.ndocs, remove_zero_rows=remove_zero_tensors, global_pids=False, out=x.views())
+        return x.exchange_and_merge()
+
+    def _search_all_Q(self, queries, Q, k, filter_fn=None, progress=True, remove_zero_tensors=False, batch_size=None):
+        from .infra import Queries, Ranking
+        if filter_fn is not None:
+            raise NotImplementedError("filter_fn acts on shard-local candidate lists; use the per-shard Searcher")
+        queries = Queries.cast(queries)
+        p, sc, c = self.search_batch(Q, k, remove_zero_tensors)
+        hp, hs, hc = self.searcher._host_results(p, sc, c)
+        self.searcher.ranker.engine.check_flags()
+        provenance = {"source": "ShardedSearcher::search_all", "queries": queries.provenance(),
+                      "config": self.config.export(), "k": k, "shards": self.world_size}
+        return Ranking.from_arrays(queries.keys(), hp, hs, hc, provenance)

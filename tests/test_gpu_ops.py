@@ -329,6 +329,7 @@ def test_residual_codec_gpu_operators(P, nbits):
     ix = po.OracleIndex(centroids=sx.centroids, bucket_weights=sx.bucket_weights.half().float(), codes=sx.codes,
                         residuals=sx.residuals, doclens=sx.doclens, ivf=sx.ivf, ivf_lengths=sx.ivf_lengths, nbits=nbits)
     D32 = po.decompress_residuals(ix, torch.arange(sx.num_passages, dtype=torch.int32))
+    out = ops.codec_decompress_residuals(sx.residuals, sx.bucket_weights.half(), rbm, lut, sx.codes, sx.centroids, 128, nbits)
     assert torch.equal(out.cpu(), D32.half())
     # the codec object: decompress() = normalised half rows
     cfg = pkg.ColBERTConfig(dim=128, nbits=nbits)

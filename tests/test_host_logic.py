@@ -138,6 +138,19 @@ def _gloo_worker(rank, world, port, tmpdir):
             allp = torch.cat([gp[r, b, :gc[r, b]] for r in range(world)])
             alls = torch.cat([gs[r, b, :gc[r, b]] for r in range(world)])
             merged.append(po.select_top(allp, alls, k) if allp.numel() else (allp, alls))
+        # the persistent-buffer exchange of the product path: views of the send block, one all-gather, and the
+        # receive buffer laid out [G] x (pids | score bits | counts) as plaid_merge_topk_msg reads it
+        x = sharded.ListExchange(B, k, torch.device("cpu"))
+        vp, vs, vc = x.views()
+        vp.copy_(pids - 500 * rank); vs.copy_(scores); vc.copy_(counts)          # shard-local pids in the message
+        x.set_pid_base(500 * rank)
+        dist.all_gather_into_tensor(x.recv, x.send)
+        blocks = x.recv.view(world, 2 * B * k + B)
+        assert x.pid_bases.tolist() == [500 * r for r in range(world)]
+        for r in range(world):
+            assert torch.equal(blocks[r, : B * k].view(B, k) + x.pid_bases[r], gp[r])
+            assert torch.equal(blocks[r, B * k: 2 * B * k].view(torch.float32).view(B, k), gs[r])
+            assert torch.equal(blocks[r, 2 * B * k:], gc[r])
         torch.save((gp, gs, gc, merged), os.path.join(tmpdir, f"r{rank}.pt"))
     finally:
         dist.destroy_process_group()
@@ -170,3 +183,21 @@ def test_ranking_to_batch_results_pads_like_the_reference():
     assert top[0] == {"passage_index": 5, "passage_id": "doc5", "content": "text 5", "score": 9.5}
     assert [t["passage_id"] for t in res[1]["top_ranking_passages"]] == ["doc1", "doc0", "doc4"]
     assert res[1]["pos_item_ids"] == ["doc1"] and res[1]["neg_item_ids"] == ["doc3"]
+
+
+def test_lazy_ranking_equals_eager_dict():
+    """Ranking.from_arrays (what the batched _search_all_Q returns) behaves like the reference's dict-backed Ranking."""
+    import numpy as np
+    from reranking_multimodal_retrievers_b200 import infra
+    pids = np.array([[5, 3, 9], [2, -1, -1]], dtype=np.int32)
+    scores = np.array([[3.5, 2.25, 1.0], [0.5, float("-inf"), float("-inf")]], dtype=np.float32)
+    counts = np.array([3, 1], dtype=np.int32)
+    rk = infra.Ranking.from_arrays(["a", "b"], pids, scores, counts, provenance={"k": 3})
+    eager = {"a": [(5, 1, 3.5), (3, 2, 2.25), (9, 3, 1.0)], "b": [(2, 1, 0.5)]}
+    assert rk.data["b"] == eager["b"] and "a" in rk.data and len(rk.data) == 2
+    assert rk.todict() == eager and dict(rk.items()) == eager
+    assert rk.tolist() == infra.Ranking(data=eager).tolist()
+    assert list(rk.data.keys()) == ["a", "b"] and list(rk.data.values()) == list(eager.values())
+    q, p, s, c = rk.arrays()
+    assert q == ["a", "b"] and p is pids and c is counts
+    assert all(isinstance(x, int) for x in rk.data["a"][0][:2]) and isinstance(rk.data["a"][0][2], float)
