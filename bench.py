@@ -356,6 +356,8 @@ def main():
     ap.add_argument("--cpu-budget-s", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fused", action="store_true", help="materialise bf16 passage embeddings (unfused decompress + MaxSim)")
+    ap.add_argument("--streams", type=int, default=None, help="query chunks in flight on separate streams (engine default if unset)")
+    ap.add_argument("--max-chunk", type=int, default=None, help="queries per chunk (engine default 512)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -430,6 +432,10 @@ def main():
     if args.no_fused:
         searcher.ranker.engine.fused = False
     eng = searcher.ranker.engine
+    if args.streams:
+        eng.streams = args.streams
+    if args.max_chunk:
+        eng.max_chunk = args.max_chunk
     ss = sharded.ShardedSearcher(searcher) if world > 1 else searcher
     B, Lq, k = w["B"], w["Lq"], w["k"]
     Qhost = Qdev.cpu().pin_memory()
@@ -615,6 +621,7 @@ def main():
         "data": "synthetic", "queries_per_s": B / (ms_step * 1e-3),
         "config": {"workload": f"{args.workload}: {w['desc']}", "passages_per_gpu": w["N"], "tokens_per_gpu": index.num_embeddings,
                    "centroids": C, "queries_per_step": B, "parallelism": f"pid-range shards x{world}, all-gather top-k merge",
+                   "queries_per_chunk": eng.chunk_size(B), "chunk_streams": eng.streams,
                    "l2": "inputs larger than L2 (index + centroid-score table >> 126 MB), no explicit flush",
                    "candidates_per_query": ncand / B, "T1_tokens_per_query": T1 / B, "T2_tokens_per_query": T2 / B,
                    "T3_tokens_per_query": T3 / B, "T3_padded_tokens_per_query": T3p / B,

@@ -314,14 +314,17 @@ def codec_decompress_gpu_form(bucket_weights, reversed_bit_map, lookup, binary_r
     (CB/indexing/codecs/decompress_residuals.cu:8-75): per element `out = half(bucket_weight); out += half(centroid)`,
     i.e. ONE half add (computed here as the fp32 sum of the two halves rounded to half: exact for |x| < 2, which
     unit-norm centroids plus residual weights satisfy).  normalize=True adds ResidualCodec.decompress's
-    `F.normalize(x, p=2, dim=-1).half()` (residual.py:272-273) with torch's own CPU half kernels.
+    `F.normalize(x, p=2, dim=-1).half()` (residual.py:272-273) in the arithmetic torch's CUDA kernels use for half.
     PARITY UNPINNED against the reference kernel itself (it needs a GPU the authoring container does not have);
     pinned indirectly: the fp32 CPU operator on the same bytes (golden D_0) differs by one half rounding."""
     w = bucket_weights.half()[lookup[reversed_bit_map[binary_residuals.long()].long()].long()]
     w = w.reshape(binary_residuals.shape[0], -1)
     out = (w.float() + centroids_f16.half()[codes.long()].float()).half()
     if normalize:
-        out = torch.nn.functional.normalize(out.float(), p=2, dim=-1).half()
+        # F.normalize on a CUDA half tensor: the norm is accumulated in fp32 and ROUNDED TO HALF, clamp_min(1e-12) is
+        # a no-op in half (1e-12 underflows to 0), then a half / half division (fp32 quotient rounded to half)
+        nrm = out.float().pow(2).sum(-1, keepdim=True).sqrt().half().float()
+        out = (out.float() / nrm).half()
     return out
 
 

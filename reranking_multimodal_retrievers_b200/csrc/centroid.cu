@@ -32,7 +32,32 @@ static constexpr int kCsPartCols = kCsN / kCsParts;
 static constexpr int kCsThreads = (4 + 4 * kCsParts) * 32;    // warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4.. epilogue
 static constexpr int kCsABytes = kCsM * kDim * 2;        // 32 KB
 static constexpr int kCsBBytes = kCsN * kDim * 2;        // 64 KB per stage
-static constexpr int kCsSmemBytes = 1024 + kCsABytes + kCsStages * kCsBBytes + 256;
+// S leaves through shared memory: every epilogue warp transposes its 32 tokens x 32 centroids block into the table's
+// [centroid][token] order in a private staging area (32 rows of 32 values = one contiguous 2 KB (fp16) / 4 KB (fp32)
+// run of the table) and one lane hands it to the bulk-copy engine (cp.async.bulk shared -> global), so the table is
+// written in full lines by the copy engine instead of 32 two-byte stores per lane and chunk.  fp16: two blocks per
+// warp (the copy of one drains while the next is built); fp32: one.
+#ifndef PLAID_CS_BULK
+#define PLAID_CS_BULK 1
+#endif
+static constexpr int kCsStagePerWarp = 4096;
+static constexpr int kCsStageBytes = PLAID_CS_BULK ? 4 * kCsParts * kCsStagePerWarp : 0;
+static constexpr int kCsSmemBytes = 1024 + kCsABytes + kCsStages * kCsBBytes + kCsStageBytes + 256;
+
+__device__ __forceinline__ void sts_b16(uint32_t addr, unsigned short v) {
+    asm volatile("st.shared.b16 [%0], %1;" :: "r"(addr), "h"(v) : "memory");
+}
+__device__ __forceinline__ void sts_b32(uint32_t addr, uint32_t v) {
+    asm volatile("st.shared.b32 [%0], %1;" :: "r"(addr), "r"(v) : "memory");
+}
+// shared -> global bulk copy (16-byte aligned, size a multiple of 16), tracked by the issuing thread's bulk groups
+__device__ __forceinline__ void bulk_store(void* gdst, uint32_t ssrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(gdst), "r"(ssrc), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" :: "n"(N) : "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 struct CsBarriers {
     uint64_t a_full;
@@ -58,7 +83,8 @@ centroid_scores_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sA = smem;                          // [2 k-halves][128 rows][128 B]
     uint8_t* sB = smem + kCsABytes;              // [stage][2 k-halves][256 rows][128 B]
-    CsBarriers* bar = reinterpret_cast<CsBarriers*>(smem + kCsABytes + kCsStages * kCsBBytes);
+    uint8_t* sStage = sB + kCsStages * kCsBBytes;   // [epilogue warp][kCsStagePerWarp]
+    CsBarriers* bar = reinterpret_cast<CsBarriers*>(smem + kCsABytes + kCsStages * kCsBBytes + kCsStageBytes);
     __shared__ float s_cut[4][32];   // per (query, token): best NC-th value any of the column-part warps has seen
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -141,23 +167,44 @@ centroid_scores_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
 #pragma unroll
         for (int p = 0; p < NC; p++) { bv[p] = -INFINITY; bi[p] = -1; }
         float cut = -INFINITY;  // current ncells-th best value of this thread's own list
+#if PLAID_CS_BULK
+        constexpr int kBlkBytes = 32 * PLAID_NQ_MAX * (int)sizeof(ST);          // one staged block: 32 centroids x 32 tokens
+        constexpr int kBlkPerCopy = kCsStagePerWarp / kBlkBytes;                // fp16: both blocks of a tile part leave as ONE 4 KB copy
+        const uint32_t stage_base = smem_u32(sStage) + (uint32_t)(warp - 4) * kCsStagePerWarp;
+        const uint32_t stage_sa = stage_base + lane * (uint32_t)sizeof(ST);
+        const bool store = S != nullptr;     // S == NULL: only the top-ncells lists are wanted (index build: argmax)
+        ST* Sblk = S + (size_t)bq * C * PLAID_NQ_MAX;
+#endif
         for (int it = 0; it < ntiles; it++) {
             const int acc = it & 1;
             if (!mbar_wait(&bar->tmem_full[acc], (it >> 1) & 1, watchdog)) break;
             tc_fence_after();
             const int c_tile = (tile_begin + it) * kCsN + part * kCsPartCols;
+#if PLAID_CS_BULK
+            int staged = 0;                  // blocks staged and not yet handed to the copy engine
+#endif
 #pragma unroll 1
             for (int ch = 0; ch < kCsPartCols / 32; ch++) {
                 uint32_t r[32];
-                tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + acc * kCsN + part * kCsPartCols + ch * 32, r);
+                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * kCsN + part * kCsPartCols + ch * 32;
+                tmem_ld_32x32(taddr, r);
                 tc_wait_ld();
                 const int c0 = c_tile + ch * 32;
                 if (c0 >= C) break;  // C is a multiple of 32: a chunk is entirely inside or outside
                 // (1) the S rows: for each centroid the warp stores 32 consecutive values (one 128 B / 64 B line).
                 //     With fp16 storage everything downstream (mask, cells) is computed from the ROUNDED values,
                 //     so that the table in memory is the one and only definition of S.
+#if PLAID_CS_BULK
+                const uint32_t blk_sa = stage_sa + staged * kBlkBytes;
+                if (store && staged == 0) {
+                    // the previous copy out of this warp's staging area must have finished reading it
+                    if (lane == 0) bulk_wait_read<0>();
+                    __syncwarp();
+                }
+#else
                 ST* dst = Sq + (size_t)c0 * PLAID_NQ_MAX;
                 const bool store = S != nullptr;     // S == NULL: only the top-ncells lists are wanted (index build: argmax)
+#endif
                 // (2) this thread's best value in the chunk decides whether the rare paths run at all; with fp16 storage
                 //     it is a packed maximum of the rounded pairs (no unpacking on the common path)
                 __half2 h[sizeof(ST) == 2 ? 16 : 1];
@@ -166,10 +213,17 @@ centroid_scores_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
 #pragma unroll
                     for (int j = 0; j < 16; j++) {
                         h[j] = __floats2half2_rn(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
+#if PLAID_CS_BULK
+                        if (store) {
+                            sts_b16(blk_sa + (2 * j) * (PLAID_NQ_MAX * 2), __half_as_ushort(__low2half(h[j])));
+                            sts_b16(blk_sa + (2 * j + 1) * (PLAID_NQ_MAX * 2), __half_as_ushort(__high2half(h[j])));
+                        }
+#else
                         if (store) {
                             __stcs(reinterpret_cast<unsigned short*>(dst + (2 * j) * PLAID_NQ_MAX), __half_as_ushort(__low2half(h[j])));
                             __stcs(reinterpret_cast<unsigned short*>(dst + (2 * j + 1) * PLAID_NQ_MAX), __half_as_ushort(__high2half(h[j])));
                         }
+#endif
                     }
                     __half2 m2 = h[0];
 #pragma unroll
@@ -177,12 +231,30 @@ centroid_scores_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                     mx = fmaxf(__low2float(m2), __high2float(m2));
                 } else {
 #pragma unroll
-                    for (int j = 0; j < 32; j++)
+                    for (int j = 0; j < 32; j++) {
+#if PLAID_CS_BULK
+                        if (store) sts_b32(blk_sa + j * (PLAID_NQ_MAX * 4), r[j]);
+#else
                         if (store) __stcs(dst + j * PLAID_NQ_MAX, __uint_as_float(r[j]));
+#endif
+                    }
                     mx = __uint_as_float(r[0]);
 #pragma unroll
                     for (int j = 1; j < 32; j++) mx = fmaxf(mx, __uint_as_float(r[j]));
                 }
+#if PLAID_CS_BULK
+                if (store) {
+                    staged++;
+                    // hand the staged run to the copy engine once the area is full or the part / the table ends
+                    if (staged == kBlkPerCopy || ch + 1 == kCsPartCols / 32 || c0 + 32 >= C) {
+                        fence_proxy_async_smem();    // staged blocks -> visible to the copy engine (async proxy)
+                        __syncwarp();
+                        if (lane == 0)
+                            bulk_store(Sblk + (size_t)(c0 - (staged - 1) * 32) * PLAID_NQ_MAX, stage_base, staged * kBlkBytes);
+                        staged = 0;
+                    }
+                }
+#endif
                 auto val = [&](int j) -> float {     // the stored (rounded) value of column j
                     if constexpr (sizeof(ST) == 2) return (j & 1) ? __high2float(h[j >> 1]) : __low2float(h[j >> 1]);
                     else return __uint_as_float(r[j]);
@@ -199,12 +271,41 @@ centroid_scores_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                 //     it beats this list's own ncells-th best AND is not below the ncells-th best the sibling warp (other
                 //     128-column half, same query token) has already seen -- that bound is shared through smem (racy
                 //     reads/writes only ever make the filter weaker, never wrong).
+                //     Few chunks hold such a value and then usually one: the lanes that want an update mark their
+                //     candidate columns, and the warp walks the UNION of those columns in ascending order, re-reading one
+                //     accumulator column per step (a lane whose own test fails on a column just sits the step out).
                 const float other = s_cut[quad][lane];
-                if (tok_valid && mx > cut && mx >= other) {
+                const bool want = tok_valid && mx > cut && mx >= other;
+                if (__any_sync(0xffffffffu, want)) {
+                    uint32_t cols = 0;               // bit j: column j of the chunk may enter this lane's list
+                    if (want) {
+                        if constexpr (sizeof(ST) == 2) {
+                            // packed compares; bit p <-> column 2p, bit 16+p <-> column 2p+1 (un-interleaved below)
+                            const __half2 cut2 = __float2half2_rn(cut), oth2 = __float2half2_rn(other);
 #pragma unroll
-                    for (int j = 0; j < 32; j++) {
-                        float cv = val(j);
-                        if (cv > cut && cv >= other) {
+                            for (int j = 0; j < 16; j++)
+                                cols |= __hgt2_mask(h[j], cut2) & __hge2_mask(h[j], oth2) & (0x00010001u << j);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; j++)
+                                cols |= (val(j) > cut && val(j) >= other ? 1u : 0u) << j;
+                        }
+                    }
+                    uint32_t all = __reduce_or_sync(0xffffffffu, cols);
+                    if constexpr (sizeof(ST) == 2) {     // Morton-interleave the two 16-bit halves into column order
+                        uint32_t x = all & 0xffffu, y = all >> 16;
+                        x = (x | (x << 8)) & 0x00ff00ffu; y = (y | (y << 8)) & 0x00ff00ffu;
+                        x = (x | (x << 4)) & 0x0f0f0f0fu; y = (y | (y << 4)) & 0x0f0f0f0fu;
+                        x = (x | (x << 2)) & 0x33333333u; y = (y | (y << 2)) & 0x33333333u;
+                        x = (x | (x << 1)) & 0x55555555u; y = (y | (y << 1)) & 0x55555555u;
+                        all = x | (y << 1);
+                    }
+                    while (all) {
+                        const int j = __ffs(all) - 1;
+                        all &= all - 1;
+                        float cv = __uint_as_float(tmem_ld_32x1(taddr + j));      // this lane's value of column j again
+                        if constexpr (sizeof(ST) == 2) cv = __half2float(__float2half_rn(cv));
+                        if (want && cv > cut && cv >= other) {
                             int ci = c0 + j;
 #pragma unroll
                             for (int p = 0; p < NC; p++) {
@@ -219,13 +320,16 @@ centroid_scores_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                             }
                         }
                     }
-                    if (cut > other) s_cut[quad][lane] = cut;
+                    if (want && cut > other) s_cut[quad][lane] = cut;
                 }
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar->tmem_empty[acc]);
         }
+#if PLAID_CS_BULK
+        if (store && lane == 0) bulk_wait_all();     // the staging area must outlive the copies that read it
+#endif
         // every (centroid range, column part) keeps its own partial list: slot = split*kCsParts + part
         const size_t base = (((size_t)bq * PLAID_NQ_MAX + lane) * (csplit * kCsParts) + (split * kCsParts + part)) * ncells;
 #pragma unroll

@@ -99,7 +99,8 @@ class _HostFeed:
 
 class SearchEngine:
     def __init__(self, index: DeviceIndex, s_budget_bytes: int = 6 << 30, max_chunk: int = 512, fused: bool = True,
-                 s_dtype: torch.dtype = torch.float16, ivf_stage1: bool = True, query_maxlen: int = NQ_MAX):
+                 s_dtype: torch.dtype = torch.float16, ivf_stage1: bool = True, query_maxlen: int = NQ_MAX,
+                 streams: int | None = None):
         self.index = index
         # number of leading query tokens that drive candidate generation and the two filter stages
         # (`Q[:, :config.query_maxlen]`, CB/search/index_storage.py:77); the kernels hold one token per lane
@@ -118,6 +119,12 @@ class SearchEngine:
         self.fused = bool(fused)
         self.s_budget_bytes = int(s_budget_bytes)
         self.max_chunk = int(max_chunk)
+        # Query chunks are independent: with streams > 1 chunk i runs on side stream i % streams with its own workspace,
+        # so the latency-bound kernels of one chunk (selects, candidate marking) and the tails of the big ones overlap
+        # with the other chunk's work
+        self.streams = max(1, int(os.environ.get("PLAID_STREAMS", streams or 1)))
+        self._side_streams = None
+        self._ws_slots = {}
         self._ws_key = None
         self._copy_stream = None
         self._ws = None
@@ -143,10 +150,14 @@ class SearchEngine:
         bc = min(bc, ((B + 3) // 4) * 4)
         return max(4, (bc // 4) * 4)
 
-    def _workspace(self, Bc: int, Lq_pad: int, ncells: int, ndocs: int, k: int):
+    def _workspace(self, Bc: int, Lq_pad: int, ncells: int, ndocs: int, k: int, slot: int = 0):
         ix = self.index
         key = (Bc, Lq_pad, ncells, ndocs, k)
-        if self._ws_key == key:
+        if slot:
+            hit = self._ws_slots.get(slot)
+            if hit is not None and hit[0] == key:
+                return hit[1]
+        elif self._ws_key == key:
             return self._ws
         dev = ix.device
         C, N = ix.num_centroids, ix.num_passages
@@ -190,7 +201,10 @@ class SearchEngine:
             out_pids=e(Bc, k, dtype=torch.int32), out_scores=e(Bc, k, dtype=torch.float32),
             out_counts=e(Bc, dtype=torch.int32),
         )
-        self._ws_key, self._ws = key, ws
+        if slot:
+            self._ws_slots[slot] = (key, ws)
+        else:
+            self._ws_key, self._ws = key, ws
         return ws
 
     def _dense_buffer(self, ws, Bc):
@@ -294,9 +308,9 @@ class SearchEngine:
              out_stride or k, _p(ws["ws_keys"]), st)
 
     def _run_chunk(self, Qc: torch.Tensor, Lq_pad: int, ncells: int, thr: float, ndocs: int, k: int,
-                   remove_zero_rows: bool, Bc: int, out=None, out_stride=None):
+                   remove_zero_rows: bool, Bc: int, out=None, out_stride=None, slot: int = 0):
         """Qc f32 [b, Lq, 128] on device, b <= Bc.  Enqueues the whole pipeline; returns the workspace."""
-        ws = self._workspace(Bc, Lq_pad, ncells, ndocs, k)
+        ws = self._workspace(Bc, Lq_pad, ncells, ndocs, k, slot)
         self.stage_candidates(ws, Qc, Lq_pad, ncells, thr, remove_zero_rows, Bc)
         self.stage_rank(ws, Qc.shape[0], Lq_pad, ndocs, k, Bc, out, out_stride)
         return ws
@@ -343,14 +357,24 @@ class SearchEngine:
         Bc = self.chunk_size(B)
         feed = self._host_feed(Q, Bc) if not Q.is_cuda else None
         Qd = Q.to(torch.float32).contiguous() if Q.is_cuda else None
+        n_chunks = (B + Bc - 1) // Bc
+        nstreams = min(self.streams, n_chunks) if not (keep_taps or on_chunk is not None) else 1
+        main = torch.cuda.current_stream(dev)
+        if nstreams > 1:
+            if self._side_streams is None or len(self._side_streams) < nstreams:
+                self._side_streams = [torch.cuda.Stream(device=dev) for _ in range(nstreams)]
+            for st in self._side_streams[:nstreams]:
+                st.wait_stream(main)                        # inputs, output buffers and the previous call's work
         for ci, b0 in enumerate(range(0, B, Bc)):
             b1 = min(B, b0 + Bc)
-            Qc = Qd[b0:b1] if feed is None else feed.chunk(ci)
+            slot = ci % nstreams if nstreams > 1 else 0
             rows = (ctypes.c_void_p(out_p.data_ptr() + b0 * k * 4), ctypes.c_void_p(out_s.data_ptr() + b0 * k * 4),
                     ctypes.c_void_p(out_c.data_ptr() + b0 * 4))
-            ws = self._run_chunk(Qc, Lq_pad, ncells, thr, ndocs, kk, remove_zero_rows, Bc, rows, k)
-            if feed is not None:
-                feed.release(ci)
+            with torch.cuda.stream(self._side_streams[slot] if nstreams > 1 else main):
+                Qc = Qd[b0:b1] if feed is None else feed.chunk(ci)
+                ws = self._run_chunk(Qc, Lq_pad, ncells, thr, ndocs, kk, remove_zero_rows, Bc, rows, k, slot)
+                if feed is not None:
+                    feed.release(ci)
             n = b1 - b0
             if on_chunk is not None:
                 on_chunk(ws, n)
@@ -361,6 +385,9 @@ class SearchEngine:
                     stage1_scores=ws["s1_scores"], stage1_counts=ws["s1_counts"], stage2_pids=ws["s2_pids"],
                     stage2_scores=ws["s2_scores"], stage2_counts=ws["s2_counts"], tok_offsets=ws["tok_offsets"],
                     D=ws["D"], tok_stride=ws["tok_stride"], scores=ws["scores"])
+        if nstreams > 1:
+            for st in self._side_streams[:nstreams]:
+                main.wait_stream(st)
         if global_pids and ix.pid_base:
             out_p.add_((out_p >= 0).to(torch.int32) * ix.pid_base)
         return out_p, out_s, out_c
