@@ -40,6 +40,9 @@ static constexpr int kCsBBytes = kCsN * kDim * 2;        // 64 KB per stage
 #ifndef PLAID_CS_BULK
 #define PLAID_CS_BULK 1
 #endif
+#ifndef PLAID_CS_PREFETCH
+#define PLAID_CS_PREFETCH 0
+#endif
 static constexpr int kCsStagePerWarp = 4096;
 static constexpr int kCsStageBytes = PLAID_CS_BULK ? 4 * kCsParts * kCsStagePerWarp : 0;
 static constexpr int kCsSmemBytes = 1024 + kCsABytes + kCsStages * kCsBBytes + kCsStageBytes + 256;
@@ -54,6 +57,15 @@ __device__ __forceinline__ void sts_b32(uint32_t addr, uint32_t v) {
 __device__ __forceinline__ void bulk_store(void* gdst, uint32_t ssrc, uint32_t bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(gdst), "r"(ssrc), "r"(bytes) : "memory");
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+// bit p of the low half -> bit 2p, bit p of the high half -> bit 2p+1 (packed half2 compares see columns 2p / 2p+1 there)
+__device__ __forceinline__ uint32_t interleave16(uint32_t v) {
+    uint32_t x = v & 0xffffu, y = v >> 16;
+    x = (x | (x << 8)) & 0x00ff00ffu; y = (y | (y << 8)) & 0x00ff00ffu;
+    x = (x | (x << 4)) & 0x0f0f0f0fu; y = (y | (y << 4)) & 0x0f0f0f0fu;
+    x = (x | (x << 2)) & 0x33333333u; y = (y | (y << 2)) & 0x33333333u;
+    x = (x | (x << 1)) & 0x55555555u; y = (y | (y << 1)) & 0x55555555u;
+    return x | (y << 1);
 }
 template <int N>
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" :: "n"(N) : "memory"); }
@@ -167,6 +179,7 @@ centroid_scores_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
 #pragma unroll
         for (int p = 0; p < NC; p++) { bv[p] = -INFINITY; bi[p] = -1; }
         float cut = -INFINITY;  // current ncells-th best value of this thread's own list
+        const __half2 thr2 = __half2half2(__float2half_ru(threshold));
 #if PLAID_CS_BULK
         constexpr int kBlkBytes = 32 * PLAID_NQ_MAX * (int)sizeof(ST);          // one staged block: 32 centroids x 32 tokens
         constexpr int kBlkPerCopy = kCsStagePerWarp / kBlkBytes;                // fp16: both blocks of a tile part leave as ONE 4 KB copy
@@ -183,12 +196,12 @@ centroid_scores_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
 #if PLAID_CS_BULK
             int staged = 0;                  // blocks staged and not yet handed to the copy engine
 #endif
+            uint32_t r[32];
 #pragma unroll 1
             for (int ch = 0; ch < kCsPartCols / 32; ch++) {
-                uint32_t r[32];
                 const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * kCsN + part * kCsPartCols + ch * 32;
-                tmem_ld_32x32(taddr, r);
-                tc_wait_ld();
+                if (!(PLAID_CS_BULK && PLAID_CS_PREFETCH && sizeof(ST) == 2) || ch == 0) tmem_ld_32x32(taddr, r);
+                tc_wait_ld32(r);
                 const int c0 = c_tile + ch * 32;
                 if (c0 >= C) break;  // C is a multiple of 32: a chunk is entirely inside or outside
                 // (1) the S rows: for each centroid the warp stores 32 consecutive values (one 128 B / 64 B line).
@@ -196,11 +209,13 @@ centroid_scores_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                 //     so that the table in memory is the one and only definition of S.
 #if PLAID_CS_BULK
                 const uint32_t blk_sa = stage_sa + staged * kBlkBytes;
-                if (store && staged == 0) {
-                    // the previous copy out of this warp's staging area must have finished reading it
-                    if (lane == 0) bulk_wait_read<0>();
-                    __syncwarp();
-                }
+                auto stage_ready = [&]() {
+                    if (store && staged == 0) {
+                        // the previous copy out of this warp's staging area must have finished reading it
+                        if (lane == 0) bulk_wait_read<0>();
+                        __syncwarp();
+                    }
+                };
 #else
                 ST* dst = Sq + (size_t)c0 * PLAID_NQ_MAX;
                 const bool store = S != nullptr;     // S == NULL: only the top-ncells lists are wanted (index build: argmax)
@@ -210,9 +225,19 @@ centroid_scores_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                 __half2 h[sizeof(ST) == 2 ? 16 : 1];
                 float mx;
                 if constexpr (sizeof(ST) == 2) {
+#if PLAID_CS_BULK
+#pragma unroll
+                    for (int j = 0; j < 16; j++) h[j] = __floats2half2_rn(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
+#if PLAID_CS_PREFETCH   // measured slower (1.09 vs 0.99 ms on cfg2): the early load holds 32 more registers through the tail
+                    if (ch + 1 < kCsPartCols / 32 && c0 + 32 < C) tmem_ld_32x32(taddr + 32, r);   // the next chunk, behind this one's tail
+#endif
+                    stage_ready();
+#endif
 #pragma unroll
                     for (int j = 0; j < 16; j++) {
+#if !PLAID_CS_BULK
                         h[j] = __floats2half2_rn(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
+#endif
 #if PLAID_CS_BULK
                         if (store) {
                             sts_b16(blk_sa + (2 * j) * (PLAID_NQ_MAX * 2), __half_as_ushort(__low2half(h[j])));
@@ -230,6 +255,9 @@ centroid_scores_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                     for (int j = 1; j < 16; j++) m2 = __hmax2(m2, h[j]);
                     mx = fmaxf(__low2float(m2), __high2float(m2));
                 } else {
+#if PLAID_CS_BULK
+                    stage_ready();
+#endif
 #pragma unroll
                     for (int j = 0; j < 32; j++) {
 #if PLAID_CS_BULK
@@ -262,9 +290,19 @@ centroid_scores_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                 // pruning mask: max_k S[c,k] >= thr  <=>  any valid token has S[c,k] >= thr
                 uint32_t word = 0;
                 if (__any_sync(0xffffffffu, tok_valid && mx >= threshold)) {
+                    uint32_t hit = 0;                // this lane's columns at or above the threshold
+                    if (tok_valid) {
+                        if constexpr (sizeof(ST) == 2) {
+                            // a stored value is a half: v >= thr  <=>  v >= the smallest half that is >= thr
 #pragma unroll
-                    for (int j = 0; j < 32; j++)
-                        word |= (__any_sync(0xffffffffu, tok_valid && val(j) >= threshold) ? 1u : 0u) << j;
+                            for (int j = 0; j < 16; j++) hit |= __hge2_mask(h[j], thr2) & (0x00010001u << j);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; j++) hit |= (val(j) >= threshold ? 1u : 0u) << j;
+                        }
+                    }
+                    word = __reduce_or_sync(0xffffffffu, hit);
+                    if constexpr (sizeof(ST) == 2) word = interleave16(word);
                 }
                 if (lane == 0 && idx_bits != nullptr) bits_q[c0 >> 5] = word;
                 // (3) running top-ncells of this query token (score desc, centroid id asc).  A value can only matter if
@@ -292,14 +330,7 @@ centroid_scores_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                         }
                     }
                     uint32_t all = __reduce_or_sync(0xffffffffu, cols);
-                    if constexpr (sizeof(ST) == 2) {     // Morton-interleave the two 16-bit halves into column order
-                        uint32_t x = all & 0xffffu, y = all >> 16;
-                        x = (x | (x << 8)) & 0x00ff00ffu; y = (y | (y << 8)) & 0x00ff00ffu;
-                        x = (x | (x << 4)) & 0x0f0f0f0fu; y = (y | (y << 4)) & 0x0f0f0f0fu;
-                        x = (x | (x << 2)) & 0x33333333u; y = (y | (y << 2)) & 0x33333333u;
-                        x = (x | (x << 1)) & 0x55555555u; y = (y | (y << 1)) & 0x55555555u;
-                        all = x | (y << 1);
-                    }
+                    if constexpr (sizeof(ST) == 2) all = interleave16(all);
                     while (all) {
                         const int j = __ffs(all) - 1;
                         all &= all - 1;
