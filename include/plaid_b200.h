@@ -232,11 +232,20 @@ int plaid_maxsim_packed(const void* Q16, const int32_t* qlens, int B, int B_pad,
  * layout of the UMMA descriptor).  tok_offsets is what plaid_doc_token_offsets(align = 32) produced for
  * the same pids.  centroids_f16 [C,128] fp16 as stored in centroids.pt; W the fp32 table of
  * plaid_build_weight_table (rounded to fp16 on load, as `bucket_weights.half()` does, residual.py:40).
- * scores[b, i] as in plaid_maxsim_packed(clamp_zero = 1). */
+ * scores[b, i] as in plaid_maxsim_packed(clamp_zero = 1).  inv_norms_f16: optional table of plaid_token_inv_norms. */
 int plaid_maxsim_fused(const void* Qh_f16, const int32_t* qlens, int B, int B_pad, int Lq_pad,
                        const int32_t* pids, const int32_t* counts, int pid_stride, const int32_t* tok_offsets,
                        const int64_t* offsets, const float* W, const uint8_t* residuals, const int32_t* codes,
-                       const void* centroids_f16, int C, int nbits, float* scores, int* watchdog, void* stream);
+                       const void* centroids_f16, int C, int nbits, const void* inv_norms_f16, float* scores,
+                       int* watchdog, void* stream);
+
+/* Per-token scale factors for plaid_maxsim_fused: inv[t] = half(1 / max(||centroid[code_t] + weights_t||, 1e-12)),
+ * computed in exactly the fp16 arithmetic and reduction order of plaid_decompress_normalize_f16, for all n tokens of
+ * an index (fp16 [n], 2 bytes per token; derived data, built once when the index is loaded).  Passing the table as
+ * inv_norms_f16 lets the fused kernel skip the per-token sum of squares / rsqrt and still build bit-identical
+ * operand tiles; NULL keeps the in-kernel normalisation. */
+int plaid_token_inv_norms(const uint8_t* residuals, const int32_t* codes, int64_t n, const float* W,
+                          const void* centroids_f16, int C, int nbits, void* inv_f16, void* stream);
 
 /* The operator the reference binds as ColBERT.segmented_maxsim (colbert.py:60): scores f32 [T, nq]
  * already computed, lengths i64 [ndocs] -> f32 [ndocs]; zero-initialised running max, then a

@@ -42,7 +42,8 @@ _SIGNATURES = {
     "plaid_decompress_normalize_bf16": [_P, _P, _I, _I, _P, _I, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P],
     "plaid_decompress_normalize_f16": [_P, _P, _I, _I, _P, _I, _P, _P, _P, _P, _P, _I, _I, _P, _P],
     "plaid_maxsim_packed": [_P, _P, _I, _I, _I, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P],
-    "plaid_maxsim_fused": [_P, _P, _I, _I, _I, _P, _P, _I, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P, _P],
+    "plaid_maxsim_fused": [_P, _P, _I, _I, _I, _P, _P, _I, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P],
+    "plaid_token_inv_norms": [_P, _P, _I64, _P, _P, _I, _I, _P, _P],
     "plaid_segmented_maxsim": [_P, _I, _P, _P, _I, _P, _P],
     "plaid_colbert_score_padded": [_P, _P, _I, _I, _I, _P, _P, _I64, _I, _I, _P, _P, _I, _P, _P],
     "plaid_colbert_score_reduce": [_P, _P, _I64, _I, _I, _P, _P],

@@ -80,7 +80,7 @@ int make_bf16_2d_map(CUtensorMap* map, const void* base, uint64_t rows, uint64_t
 
 extern "C" {
 
-int plaid_abi_version(void) { return 1; }
+int plaid_abi_version(void) { return 2; }
 
 const char* plaid_last_error(void) { return plaid::g_err; }
 

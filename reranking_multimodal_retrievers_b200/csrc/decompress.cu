@@ -265,6 +265,49 @@ decompress_tokens_f16_kernel(const uint8_t* __restrict__ residuals, const int32_
     }
 }
 
+// ---- per-token scale factors for the fused MaxSim: inv[t] = half(1 / max(||centroid + weights||, 1e-12)) in exactly the
+// arithmetic (and reduction order) of the fp16 pipeline above, computed ONCE when an index is loaded.  With the table
+// the fused kernel's decompressors skip the sum of squares, its three shuffles and the rsqrt per token and still
+// build bit-identical tiles.
+template <int NBITS>
+__global__ void __launch_bounds__(kDecWarps * 32)
+token_inv_norms_kernel(const uint8_t* __restrict__ residuals, const int32_t* __restrict__ codes, int64_t n,
+                       const float* __restrict__ W, const __half* __restrict__ centroids, int C, __half* __restrict__ inv) {
+    __shared__ __align__(128) uint8_t sLUT[kLutBytes];
+    __shared__ __align__(16) uint8_t s_stage[kDecWarps * 512];
+    constexpr int PB = 16 * NBITS, TB = 512 / PB;
+    lut_fill_f16<NBITS>(W, sLUT);
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int q = lane & 7, tsub = lane >> 3;
+    const uint32_t lut_sa = lut_lane_base<NBITS>(smem_u32(sLUT), lane);
+    const uint32_t stage_sa = smem_u32(s_stage + warp * 512);
+    const char* cent_q = reinterpret_cast<const char*>(centroids) + q * 16;
+    const int64_t stride = (int64_t)gridDim.x * nw * TB;
+    for (int64_t t0 = ((int64_t)blockIdx.x * nw + warp) * TB; t0 < n; t0 += stride) {
+        const int nt = (int)min((int64_t)TB, n - t0);
+        int4 r = make_int4(0, 0, 0, 0);
+        if (lane * 16 < nt * PB) r = ld_stream_v4(residuals + t0 * PB + lane * 16);
+        sts_v4u32(stage_sa + lane * 16, r.x, r.y, r.z, r.w);
+        int code = (lane < nt) ? ld_stream_s32(codes + t0 + lane) : 0;
+        code = min(max(code, 0), C - 1);
+        __syncwarp();
+        for (int j0 = 0; j0 < nt; j0 += 4) {
+            const int j = j0 + tsub;
+            const unsigned c = (unsigned)__shfl_sync(0xffffffffu, code, j);
+            const uint4* crow = centroid_row(cent_q, c);
+            const uint4 clo = __ldg(crow), chi = __ldg(crow + 8);
+            uint32_t wlo[4], whi[4];
+            __half2 v[8];
+            token_weights_h8<NBITS>(stage_sa + j * PB, lut_sa, q, wlo);
+            token_weights_h8<NBITS>(stage_sa + j * PB, lut_sa, q + 8, whi);
+            const float ss = quarter_sum(token_sum_h16(clo, chi, wlo, whi, v));
+            if (j < nt && q == 0) inv[t0 + j] = token_inv_h16(ss);
+        }
+        __syncwarp();
+    }
+}
+
 // per query: exclusive prefix sums of passage lengths
 __global__ void __launch_bounds__(256)
 doc_token_offsets_kernel(const int32_t* __restrict__ pids, const int32_t* __restrict__ counts, int pid_stride,
@@ -479,5 +522,30 @@ extern "C" int plaid_decompress_tokens_f16(const uint8_t* residuals, const int32
             return PLAID_ERR_UNSUPPORTED;
     }
     PLAID_LAUNCH_OK("decompress_tokens_f16_kernel");
+    return PLAID_OK;
+}
+
+extern "C" int plaid_token_inv_norms(const uint8_t* residuals, const int32_t* codes, int64_t n, const float* W,
+                                     const void* centroids_f16, int C, int nbits, void* inv_f16, void* stream) {
+    using namespace plaid;
+    PLAID_CHECK_ARG(residuals && codes && W && centroids_f16 && inv_f16, PLAID_ERR_ARG, "plaid_token_inv_norms: null pointer");
+    PLAID_CHECK_ARG(n >= 0 && C > 0, PLAID_ERR_ARG, "plaid_token_inv_norms: bad sizes");
+    PLAID_CHECK_ARG((reinterpret_cast<uintptr_t>(residuals) & 15) == 0 && (reinterpret_cast<uintptr_t>(centroids_f16) & 15) == 0,
+                    PLAID_ERR_ARG, "plaid_token_inv_norms: residuals/centroids must be 16-byte aligned");
+    if (n == 0) return PLAID_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const __half* cent = reinterpret_cast<const __half*>(centroids_f16);
+    __half* inv = reinterpret_cast<__half*>(inv_f16);
+    const int grid = 148 * 8;
+    switch (nbits) {
+        case 1: token_inv_norms_kernel<1><<<grid, kDecWarps * 32, 0, st>>>(residuals, codes, n, W, cent, C, inv); break;
+        case 2: token_inv_norms_kernel<2><<<grid, kDecWarps * 32, 0, st>>>(residuals, codes, n, W, cent, C, inv); break;
+        case 4: token_inv_norms_kernel<4><<<grid, kDecWarps * 32, 0, st>>>(residuals, codes, n, W, cent, C, inv); break;
+        case 8: token_inv_norms_kernel<8><<<grid, kDecWarps * 32, 0, st>>>(residuals, codes, n, W, cent, C, inv); break;
+        default:
+            set_error("plaid_token_inv_norms: nbits=%d not in {1,2,4,8}", nbits);
+            return PLAID_ERR_UNSUPPORTED;
+    }
+    PLAID_LAUNCH_OK("token_inv_norms_kernel");
     return PLAID_OK;
 }

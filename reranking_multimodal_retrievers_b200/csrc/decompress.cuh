@@ -176,6 +176,28 @@ __device__ __forceinline__ float quarter_sum(float ss) {
     ss += __shfl_xor_sync(0xffffffffu, ss, 1);
     return ss;
 }
+// v = centroid + weight only (the scale comes from the precomputed per-token table)
+__device__ __forceinline__ void token_add_h16(const uint4& clo, const uint4& chi, const uint32_t (&wlo)[4],
+                                              const uint32_t (&whi)[4], __half2 (&v)[8]) {
+    v[0] = __hadd2(u32_as_h2(clo.x), u32_as_h2(wlo[0]));
+    v[1] = __hadd2(u32_as_h2(clo.y), u32_as_h2(wlo[1]));
+    v[2] = __hadd2(u32_as_h2(clo.z), u32_as_h2(wlo[2]));
+    v[3] = __hadd2(u32_as_h2(clo.w), u32_as_h2(wlo[3]));
+    v[4] = __hadd2(u32_as_h2(chi.x), u32_as_h2(whi[0]));
+    v[5] = __hadd2(u32_as_h2(chi.y), u32_as_h2(whi[1]));
+    v[6] = __hadd2(u32_as_h2(chi.z), u32_as_h2(whi[2]));
+    v[7] = __hadd2(u32_as_h2(chi.w), u32_as_h2(whi[3]));
+}
+// 1 / max(||x||, 1e-12) rounded to half: the scale factor of a token, exactly as token_scale_h16 applies it
+__device__ __forceinline__ __half token_inv_h16(float ss) { return __float2half_rn(rsqrt_ftz(fmaxf(ss, 1e-24f))); }
+// scale by a precomputed half factor (0 for pad rows)
+__device__ __forceinline__ void token_scale_pre_h16(const __half2 (&v)[8], uint32_t inv_bits, uint4& lo, uint4& hi) {
+    const __half2 i2 = u32_as_h2(__byte_perm(inv_bits, 0, 0x1010));
+    lo = make_uint4(h2_as_u32(__hmul2(v[0], i2)), h2_as_u32(__hmul2(v[1], i2)), h2_as_u32(__hmul2(v[2], i2)),
+                    h2_as_u32(__hmul2(v[3], i2)));
+    hi = make_uint4(h2_as_u32(__hmul2(v[4], i2)), h2_as_u32(__hmul2(v[5], i2)), h2_as_u32(__hmul2(v[6], i2)),
+                    h2_as_u32(__hmul2(v[7], i2)));
+}
 // x / max(||x||, 1e-12) = x * rsqrt(max(||x||^2, 1e-24)) (index_storage.py:175); pad rows become zeros
 __device__ __forceinline__ void token_scale_h16(const __half2 (&v)[8], float ss, bool real, uint4& lo, uint4& hi) {
     const float inv = real ? rsqrt_ftz(fmaxf(ss, 1e-24f)) : 0.0f;

@@ -64,6 +64,7 @@ struct MsParams {
     const uint8_t* residuals;    // [NE, 16*nbits]
     const __half* centroids;     // [C, 128] fp16, exactly centroids.pt
     const float* wtable;         // [256, 8/nbits]
+    const __half* inv_norms;     // [NE] precomputed per-token scale factors (plaid_token_inv_norms), or NULL
     int C;
     // common
     float* scores;
@@ -507,12 +508,16 @@ __device__ __forceinline__ void ms_epilogue_a1(const MsParams& p, MsShared* sh, 
             if (live) {
                 const uint32_t tmem_acc = tmem_lane + acc * 128;
                 const int nch = min(4, (it.ntok - t * 128) >> 5);     // 32-column chunks of this tile that hold tokens
-                uint32_t ra[16], rb[16];
-                tmem_ld_32x16(tmem_acc, ra);
-                tc_wait_ld16(ra);
+                // A tcgen05.ld round trip costs ~200 cycles whatever its width, and this warp is the kernel's critical
+                // path when the decompressors are fast (ncu: 97 % busy with one round trip per 16 columns).  One
+                // 32-column load per passage chunk halves the round trips with the same 32 registers (deeper schemes
+                // -- four 16-column buffers, two 32-column ones -- push the whole kernel over its 96-register cap and
+                // spill in the decompressors: 4.5 ms instead of 2.9).
+                uint32_t r[32];
 #pragma unroll
                 for (int ch = 0; ch < 4; ch++) {
                     if (ch < nch) {
+                        tmem_ld_32x32(tmem_acc + ch * 32, r);
                         const int tk0 = t * 128 + ch * 32;
                         while (tk0 == next_end && doc + 1 < it.nd) {   // this chunk opens the next passage
                             flush(doc);
@@ -520,12 +525,8 @@ __device__ __forceinline__ void ms_epilogue_a1(const MsParams& p, MsShared* sh, 
                             const int nx = __shfl_sync(0xffffffffu, ends_reg, min(doc + 1, 31));
                             next_end = doc + 1 < 32 ? nx : it.ntok;     // no lane 32: the 32nd passage ends with the item
                         }
-                        tmem_ld_32x16(tmem_acc + ch * 32 + 16, rb);    // second half in flight ...
-                        runmax = max16(ra, runmax);                    // ... while the first is reduced
-                        tc_wait_ld16(rb);
-                        if (ch + 1 < nch) tmem_ld_32x16(tmem_acc + ch * 32 + 32, ra);
-                        runmax = max16(rb, runmax);
-                        if (ch + 1 < nch) tc_wait_ld16(ra);
+                        tc_wait_ld32(r);
+                        runmax = max32(r, runmax);
                     }
                 }
             }
@@ -661,7 +662,7 @@ template <int NBITS> constexpr bool kFusedAsyncStage = (NBITS <= 2);
 static constexpr int kFusedThreads = (6 + kFusedDecWarps) * 32;
 static constexpr int kFusedThreadsSlim = (4 + kFusedDecWarps) * 32;
 
-template <int NBITS, bool SLIM, int kFusedUnit>
+template <int NBITS, bool SLIM, int kFusedUnit, bool PRE>
 __global__ void __launch_bounds__(SLIM ? kFusedThreadsSlim : kFusedThreads, 1)
 maxsim_fused_kernel(const __grid_constant__ CUtensorMap map_q, const MsParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -809,7 +810,7 @@ maxsim_fused_kernel(const __grid_constant__ CUtensorMap map_q, const MsParams p)
             };
             // packed residuals (valid*PB bytes, 16 per lane and pass) and codes of a unit: rows past `valid` get zero
             // bytes and code 0, so they decode to finite values that the scale step replaces by zeros
-            auto fetch = [&](int64_t tok0, int valid, uint32_t st_sa, int4 (&res)[NPASS], int& code) {
+            auto fetch = [&](int64_t tok0, int valid, uint32_t st_sa, int4 (&res)[NPASS], int& code, uint32_t& inv) {
 #pragma unroll
                 for (int v = 0; v < NPASS; v++) {
                     const int byte = v * 512 + lane * 16;
@@ -823,6 +824,8 @@ maxsim_fused_kernel(const __grid_constant__ CUtensorMap map_q, const MsParams p)
                 }
                 if constexpr (kFusedAsyncStage<NBITS>) cp_async_commit();
                 code = (lane < valid) ? ld_stream_s32(p.codes + tok0 + lane) : 0;
+                // precomputed scale factor of row `lane` of the unit (0 for the rows past `valid`: they become zeros)
+                if constexpr (PRE) inv = (lane < valid) ? (uint32_t)__ldg(reinterpret_cast<const unsigned short*>(p.inv_norms) + tok0 + lane) : 0u;
             };
             // centroid rows of batch bt (steps bt*CB .. bt*CB+CB-1) of a unit whose codes sit one per lane in `code`
             auto load_cents = [&](int code, int bt, uint4 (&clo)[CB], uint4 (&chi)[CB]) {
@@ -835,7 +838,7 @@ maxsim_fused_kernel(const __grid_constant__ CUtensorMap map_q, const MsParams p)
                 }
             };
             // decode batch bt into the tile: shared loads of step u+1 are issued before the shuffles of step u
-            auto process = [&](int bt, int valid, uint32_t stage_sa, uint32_t tile_sa, const uint4 (&clo)[CB],
+            auto process = [&](int bt, int valid, uint32_t inv, uint32_t stage_sa, uint32_t tile_sa, const uint4 (&clo)[CB],
                                const uint4 (&chi)[CB]) {
                 uint32_t wlo[4], whi[4];
                 token_weights_h8<NBITS>(stage_sa + (4 * bt * CB + tsub) * PB, lut_sa, q, wlo);
@@ -844,14 +847,23 @@ maxsim_fused_kernel(const __grid_constant__ CUtensorMap map_q, const MsParams p)
                 for (int u = 0; u < CB; u++) {
                     const int step = bt * CB + u, j = 4 * step + tsub;
                     __half2 v[8];
-                    float ss = token_sum_h16(clo[u], chi[u], wlo, whi, v);
-                    if (u + 1 < CB) {
-                        token_weights_h8<NBITS>(stage_sa + (j + 4) * PB, lut_sa, q, wlo);
-                        token_weights_h8<NBITS>(stage_sa + (j + 4) * PB, lut_sa, q + 8, whi);
-                    }
-                    ss = quarter_sum(ss);
                     uint4 olo, ohi;
-                    token_scale_h16(v, ss, j < valid, olo, ohi);
+                    if constexpr (PRE) {
+                        token_add_h16(clo[u], chi[u], wlo, whi, v);
+                        if (u + 1 < CB) {
+                            token_weights_h8<NBITS>(stage_sa + (j + 4) * PB, lut_sa, q, wlo);
+                            token_weights_h8<NBITS>(stage_sa + (j + 4) * PB, lut_sa, q + 8, whi);
+                        }
+                        token_scale_pre_h16(v, __shfl_sync(0xffffffffu, inv, j), olo, ohi);
+                    } else {
+                        float ss = token_sum_h16(clo[u], chi[u], wlo, whi, v);
+                        if (u + 1 < CB) {
+                            token_weights_h8<NBITS>(stage_sa + (j + 4) * PB, lut_sa, q, wlo);
+                            token_weights_h8<NBITS>(stage_sa + (j + 4) * PB, lut_sa, q + 8, whi);
+                        }
+                        ss = quarter_sum(ss);
+                        token_scale_h16(v, ss, j < valid, olo, ohi);
+                    }
                     const uint32_t dst = tile_sa + (((CB & 1) ? (step & 1) : (u & 1)) ? slot_odd : slot_even) + step * 512;
                     sts_v4u32_relaxed(dst, olo.x, olo.y, olo.z, olo.w);
                     sts_v4u32_relaxed(dst + khalf, ohi.x, ohi.y, ohi.z, ohi.w);
@@ -859,6 +871,7 @@ maxsim_fused_kernel(const __grid_constant__ CUtensorMap map_q, const MsParams p)
             };
             int4 pres[NPASS];
             int pcode = 0, pvalid = 0, ptile = -1;
+            uint32_t pinv = 0;
             uint4 alo[CB], ahi[CB], blo[CB], bhi[CB];
             bool a_ready = false;                               // batch 0 of the coming unit is already in alo/ahi
             const int first = (group - base_g) & (G - 1);       // this group's first tile of the item
@@ -868,6 +881,7 @@ maxsim_fused_kernel(const __grid_constant__ CUtensorMap map_q, const MsParams p)
                 const uint32_t tile_sa = tile_lane0 + st * b_bytes;
                 int4 res[NPASS];
                 int code, valid;
+                uint32_t inv = 0;
                 if (ptile == t) {                               // requested while the previous unit was being built
                     if constexpr (!kFusedAsyncStage<NBITS>) {
 #pragma unroll
@@ -875,10 +889,11 @@ maxsim_fused_kernel(const __grid_constant__ CUtensorMap map_q, const MsParams p)
                     }
                     code = pcode;
                     valid = pvalid;
+                    inv = pinv;
                 } else {
                     int64_t tok0;
                     geom(t, tok0, valid);
-                    fetch(tok0, valid, stage_sa, res, code);
+                    fetch(tok0, valid, stage_sa, res, code, inv);
                 }
                 if (!a_ready && valid > 0) load_cents(code, 0, alo, ahi);
                 a_ready = false;
@@ -886,7 +901,7 @@ maxsim_fused_kernel(const __grid_constant__ CUtensorMap map_q, const MsParams p)
                 if (more) {                                     // this warp's next unit of the item: loads in flight now
                     int64_t ntok0;
                     geom(t + G, ntok0, pvalid);
-                    fetch(ntok0, pvalid, stage0_sa + (buf ^ 1) * (UT * PB), pres, pcode);
+                    fetch(ntok0, pvalid, stage0_sa + (buf ^ 1) * (UT * PB), pres, pcode, pinv);
                     ptile = t + G;
                 }
                 if (!mbar_wait(&sh->empty[st], st_par ^ 1, p.watchdog)) { ok = false; break; }
@@ -915,14 +930,14 @@ maxsim_fused_kernel(const __grid_constant__ CUtensorMap map_q, const MsParams p)
 #pragma unroll 1
                     for (int bt = 0; bt < NBATCH; bt += 2) {    // two batches per trip: A = bt, B = bt + 1
                         load_cents(code, bt + 1, blo, bhi);
-                        process(bt, valid, stage_sa, tile_sa, alo, ahi);
+                        process(bt, valid, inv, stage_sa, tile_sa, alo, ahi);
                         if (bt + 2 < NBATCH) {
                             load_cents(code, bt + 2, alo, ahi);
                         } else if (more && pvalid > 0) {        // batch 0 of the next unit (its codes arrived long ago)
                             load_cents(pcode, 0, alo, ahi);
                             a_ready = true;
                         }
-                        process(bt + 1, valid, stage_sa, tile_sa, blo, bhi);
+                        process(bt + 1, valid, inv, stage_sa, tile_sa, blo, bhi);
                     }
                 }
                 fence_proxy_async_smem();      // generic-proxy writes -> visible to the tensor core's async proxy
@@ -1007,13 +1022,16 @@ static int ms_launch_fused(const void* Qb, int q_rows, int nbits, MsParams& p, c
     if (p.NS > kMsMaxStages) p.NS = kMsMaxStages;
     PLAID_CHECK_ARG(p.NS >= 2, PLAID_ERR_UNSUPPORTED, "maxsim_fused: shared memory too small for Lq_pad=%d, nbits=%d", p.Lq_pad, nbits);
     const int smem = fixed + p.NS * per_stage;
-#define PLAID_FUSED_FN(NB)                                                                              \
-    (slim ? (const void*)maxsim_fused_kernel<NB, true, 32>                                              \
-          : unit == 16 ? (const void*)maxsim_fused_kernel<NB, false, 16> : (const void*)maxsim_fused_kernel<NB, false, 32>)
+    const bool pre = p.inv_norms != nullptr;
+#define PLAID_FUSED_FN2(NB, PRE_)                                                                       \
+    (slim ? (const void*)maxsim_fused_kernel<NB, true, 32, PRE_>                                        \
+          : unit == 16 ? (const void*)maxsim_fused_kernel<NB, false, 16, PRE_> : (const void*)maxsim_fused_kernel<NB, false, 32, PRE_>)
+#define PLAID_FUSED_FN(NB) (pre ? PLAID_FUSED_FN2(NB, true) : PLAID_FUSED_FN2(NB, false))
     const void* fn = nbits == 1 ? PLAID_FUSED_FN(1) : nbits == 2 ? PLAID_FUSED_FN(2) : nbits == 4 ? PLAID_FUSED_FN(4) : PLAID_FUSED_FN(8);
 #undef PLAID_FUSED_FN
-    static int configured[3][9][kMaxDevices] = {{{0}}};
-    const int variant = slim ? 1 : unit == 16 ? 2 : 0;
+#undef PLAID_FUSED_FN2
+    static int configured[6][9][kMaxDevices] = {{{0}}};
+    const int variant = (slim ? 1 : unit == 16 ? 2 : 0) + (pre ? 3 : 0);
     if ((rc = ensure_dynamic_smem(fn, smem, configured[variant][nbits])) != PLAID_OK) return rc;
     int grid = sm_count();
     if (grid > p.num_items) grid = p.num_items;
@@ -1030,7 +1048,8 @@ static int ms_launch_fused(const void* Qb, int q_rows, int nbits, MsParams& p, c
 extern "C" int plaid_maxsim_fused(const void* Qh_f16, const int32_t* qlens, int B, int B_pad, int Lq_pad,
                                   const int32_t* pids, const int32_t* counts, int pid_stride, const int32_t* tok_offsets,
                                   const int64_t* offsets, const float* W, const uint8_t* residuals, const int32_t* codes,
-                                  const void* centroids_f16, int C, int nbits, float* scores, int* watchdog, void* stream) {
+                                  const void* centroids_f16, int C, int nbits, const void* inv_norms_f16, float* scores,
+                                  int* watchdog, void* stream) {
     using namespace plaid;
     PLAID_CHECK_ARG(Qh_f16 && qlens && pids && counts && tok_offsets && offsets && W && residuals && codes && centroids_f16 &&
                         scores,
@@ -1061,6 +1080,7 @@ extern "C" int plaid_maxsim_fused(const void* Qh_f16, const int32_t* qlens, int 
     p.residuals = residuals;
     p.centroids = reinterpret_cast<const __half*>(centroids_f16);
     p.wtable = W;
+    p.inv_norms = reinterpret_cast<const __half*>(inv_norms_f16);
     p.C = C;
     p.ab_f16 = 1;
     p.groups_per_query = (pid_stride + kMsGD - 1) / kMsGD;

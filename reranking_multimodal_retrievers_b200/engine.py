@@ -117,6 +117,8 @@ class SearchEngine:
         # fused = decompression feeds the tensor cores through shared memory (no passage embeddings in HBM);
         # the unfused pair of kernels materialises D (bf16) and is what the stage-wise parity taps read
         self.fused = bool(fused)
+        # fused kernel reads the per-token scale factors the index computed at load (same bits, fewer instructions)
+        self.use_inv_norms = os.environ.get("PLAID_NO_INV_NORMS", "0") != "1" and getattr(index, "inv_norms", None) is not None
         self.s_budget_bytes = int(s_budget_bytes)
         self.max_chunk = int(max_chunk)
         # Query chunks are independent: with streams > 1 chunk i runs on side stream i % streams with its own workspace,
@@ -295,7 +297,8 @@ class SearchEngine:
         if self.fused and Lq_pad <= 384:
             call("maxsim_fused", "plaid_maxsim_fused", _p(ws["Qh"]), _p(ws["qlens"]), b, Bc, Lq_pad, _p(ws["s2_pids"]),
                  _p(ws["s2_counts"]), nd4, _p(ws["tok_offsets"]), _p(ix.offsets), _p(ix.weight_table), _p(ix.residuals),
-                 _p(ix.codes), _p(ix.centroids_f16), C, ix.nbits, _p(ws["scores"]), wd, st)
+                 _p(ix.codes), _p(ix.centroids_f16), C, ix.nbits, _p(ix.inv_norms) if self.use_inv_norms else None,
+                 _p(ws["scores"]), wd, st)
         else:
             D = self._dense_buffer(ws, Bc)
             call("decompress", "plaid_decompress_normalize_f16", _p(ws["s2_pids"]), _p(ws["s2_counts"]), b, nd4,

@@ -11,6 +11,7 @@ Layout in HBM (one shard):
   centroids_f16  f16 [C, 128]      exactly centroids.pt (gathered by the decompressor)
   centroids_bf16 bf16 [C, 128]     operand of the centroid-scoring contraction
   weight_table f32 [256, 8/nbits]  bucket_weights o lookup o reversed_bit_map (residual.py:54-89)
+  inv_norms    f16 [NE]            1 / ||centroid[code] + residual weights|| per token (derived at load time)
 """
 from __future__ import annotations
 
@@ -171,6 +172,9 @@ class DeviceIndex:
             self.reversed_bit_map, self.lookup_table = rbm.to(dev), lut.to(dev)
             self.weight_table = ops.build_weight_table(self.bucket_weights, self.reversed_bit_map, self.lookup_table,
                                                        self.nbits)
+            # per-token scale factors 1/||centroid + residual weights|| (fp16, 2 B/token; derived at load): the fused
+            # decompress + MaxSim kernel multiplies by them instead of normalising every token it decodes
+            self.inv_norms = ops.token_inv_norms(self.residuals, self.codes, self.weight_table, self.centroids_f16, self.nbits)
             if getattr(host, "ivf", None) is not None:
                 ivf, ivf_lengths = host.ivf.to(dev, torch.int32), host.ivf_lengths.to(dev, torch.int64)
             else:

@@ -235,6 +235,19 @@ def packbits(bits):
     return out[: n // 8]
 
 
+def token_inv_norms(residuals, codes, weight_table, centroids_f16, nbits):
+    """fp16 [n]: the scale factor 1 / max(||centroid + weights||, 1e-12) of every token, in the fused MaxSim kernel's
+    own arithmetic (plaid_token_inv_norms); derived data of a loaded index."""
+    res, codes = _cu(residuals, torch.uint8), _cu(codes, torch.int32)
+    W, cent = _cu(weight_table, torch.float32), _cu(centroids_f16, torch.float16)
+    n = codes.numel()
+    out = torch.empty(max(n, 1), device=codes.device, dtype=torch.float16)
+    if n:
+        _lib.call("plaid_token_inv_norms", _p(res), _p(codes), ctypes.c_int64(n), _p(W), _p(cent), cent.shape[0], int(nbits),
+                  _p(out), _stream())
+    return out[:n]
+
+
 def unpack_residual_codes(residuals, nbits, reversed_bit_map, lookup):
     """Integer parity tap: bucket index of every dimension, u8 [n, 128]."""
     residuals = _cu(residuals, torch.uint8)
