@@ -192,6 +192,128 @@ def agreement(ours, ref_results, k):
                     "cut-offs may differ"}
 
 
+CFG4 = dict(blocks=8, passages_per_block=1_250_000, lo=120, hi=239, nbits=2, C=524_288, B=1024, Lq=64, k=100,
+            desc="10M-passage synthetic PLAID index (8 blocks of 1.25M passages, ~180 tok/passage, 1.8G tokens, C=524288, nbits=2) "
+                 "pid-sharded over the ranks, 1024 FLMR queries, k=100")
+
+
+def bench_cfg4(args, rank, world, dev, peaks, steps=4, warmup=2):
+    """BASELINE.json configs[3]: ONE fixed 10M-passage collection, pid-range sharded over `world` ranks (strong scaling:
+    every rank holds 10M/world passages), the same 1024 queries on every rank, per-shard search + one all-gather of the
+    top-k blocks + merge (oracle (A)).  Returns the `cfg4` block of the bench line (rank 0) or None."""
+    import types
+    import torch
+    import torch.distributed as dist
+    from reranking_multimodal_retrievers_b200 import Searcher, sharded, synthetic
+    from reranking_multimodal_retrievers_b200.index import DeviceIndex
+    c = CFG4
+    if c["blocks"] % world:
+        return {"skipped": f"world size {world} does not divide the collection's {c['blocks']} blocks"}
+    free, _ = torch.cuda.mem_get_info(dev)
+    per_rank_tokens = c["blocks"] // world * c["passages_per_block"] * (c["lo"] + c["hi"]) / 2
+    need = per_rank_tokens * (4 + 16 * c["nbits"] + 2 + 4 + 8) + (24 << 30)      # index + derived arrays + IVF scratch + workspace
+    if free < need:
+        return {"skipped": f"needs ~{need / 2**30:.0f} GiB per rank, {free / 2**30:.0f} GiB free"}
+    t0 = time.perf_counter()
+    mine = range(rank * c["blocks"] // world, (rank + 1) * c["blocks"] // world)
+    shard = synthetic.make_collection_shard(mine, c["passages_per_block"], c["lo"], c["hi"], c["nbits"], c["C"], c["blocks"],
+                                            seed=4000, device=dev)
+    index = DeviceIndex(shard, dev)
+    B, Lq, k = c["B"], c["Lq"], c["k"]
+    Q = torch.empty(B, Lq, 128, device=dev, dtype=torch.float32)
+    if rank == 0:      # queries planted in block 0 (rank 0 holds it for every world size): the same queries for every N
+        ppb = c["passages_per_block"]
+        view = types.SimpleNamespace(codes=shard.codes, residuals=shard.residuals, doclens=shard.doclens[:ppb],
+                                     centroids=shard.centroids, bucket_weights=shard.bucket_weights, nbits=shard.nbits,
+                                     dim=shard.dim, num_passages=ppb)
+        Q.copy_(synthetic.make_queries(view, B, Lq, seed=199))
+    if world > 1:
+        dist.broadcast(Q, src=0)
+    del shard
+    torch.cuda.synchronize()
+    build_s = time.perf_counter() - t0
+    searcher = Searcher(index=index)
+    eng = searcher.ranker.engine
+    ss = sharded.ShardedSearcher(searcher) if world > 1 else searcher
+    Qhost = Q.cpu().pin_memory()
+    queries = {i: f"question {i}" for i in range(B)}
+    from reranking_multimodal_retrievers_b200 import search_custom_collection
+
+    def timed(fn, n):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()) / n
+
+    stats = dict(ncand=0, T1=0, T2=0, T3=0, scan_queries=0)
+
+    def account(ws, n):
+        dl = index.doclens
+        for key, pk, ck in (("T1", "cand_pids", "cand_counts"), ("T2", "s1_pids", "s1_counts"), ("T3", "s2_pids", "s2_counts")):
+            cnt = ws[ck][:n].long()
+            for b0 in range(0, n, 16):                       # bounded temporaries: candidate lists are long here
+                m = torch.arange(ws[pk].shape[1], device=dev).unsqueeze(0) < cnt[b0:b0 + 16].unsqueeze(1)
+                stats[key] += int(dl[torch.where(m, ws[pk][b0:min(n, b0 + 16)], 0).long()].mul(m).sum())
+        stats["ncand"] += int(ws["cand_counts"][:n].sum())
+        stats["scan_queries"] += int((ws["ivf_meta"][:n, 2] != 0).sum())
+
+    acc = eng.search_batch(Q, k=k, remove_zero_rows=True, on_chunk=account)
+    torch.cuda.synchronize()
+    eng.check_flags()
+    found = int((acc[0][:, 0] >= 0).sum())
+    for _ in range(warmup):
+        ss.search_batch(Q, k, True)
+    eng.events = []
+    ms = timed(lambda: ss.search_batch(Q, k, True), steps)
+    events, eng.events = eng.events, None
+    ms_api = timed(lambda: search_custom_collection(ss, queries, Qhost, num_document_to_retrieve=k, remove_zero_tensors=True), steps)
+    eng.check_flags()
+    tot = torch.tensor([stats["T1"], stats["T2"], stats["T3"], stats["ncand"], stats["scan_queries"]], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tot)                                 # tokens scored by ALL shards
+    if rank != 0:
+        return None
+    stage_ms = {}
+    for stage, a, b in events:
+        stage_ms[stage] = stage_ms.get(stage, 0.0) + a.elapsed_time(b) / steps
+    T1, T2, T3, ncand, scan_q = (float(x) for x in tot.tolist())
+    C = c["C"]
+    chunks = (B + eng.chunk_size(B) - 1) // eng.chunk_size(B)
+    cs_bytes = 2.0 * C * 32 * B + 2.0 * C * 128 * chunks
+    kernels = {s_: {"ms_per_step": round(v, 3), "share": round(v / ms, 4)} for s_, v in stage_ms.items()}
+    if "centroid_scores" in kernels:
+        kernels["centroid_scores"].update(achieved_GBps=round(cs_bytes / (stage_ms["centroid_scores"] * 1e-3) / 1e9, 1),
+                                          frac_hbm=round(cs_bytes / (stage_ms["centroid_scores"] * 1e-3) / 1e9 / peaks["hbm"], 4),
+                                          note="replicated on every rank: the codebook is global and every shard's filter needs "
+                                               "the whole score table of every query")
+    return {
+        "workload": "cfg4: " + c["desc"], "scaling": "strong", "n_gpus": world, "steps": steps, "warmup": warmup,
+        "passages_total": c["blocks"] * c["passages_per_block"], "passages_per_rank": index.num_passages,
+        "tokens_per_rank": index.num_embeddings, "index_bytes_per_rank": index.bytes(), "centroids": C,
+        "ms_per_step": ms, "queries_per_s": B / (ms * 1e-3), "doc_tokens_per_s": T3 / (ms * 1e-3),
+        "e2e": {"ms_per_step": ms_api, "queries_per_s": B / (ms_api * 1e-3),
+                "call": "search_custom_collection(ShardedSearcher, ...) -> Ranking, host embeddings in"},
+        "queries_per_chunk": eng.chunk_size(B),
+        "candidates_per_query_all_shards": ncand / B, "T1_tokens_per_query_all_shards": T1 / B,
+        "T2_tokens_per_query_all_shards": T2 / B, "T3_tokens_per_query_all_shards": T3 / B,
+        "stage1_scan_fallback_queries_all_shards": scan_q, "queries_with_results_rank0": found,
+        "semantics": "per-shard truncation to ndocs / ndocs/4 (SURVEY.md 8e, oracle (A)): every shard exact-scores its own 256 "
+                     "passages per query, so T2/T3 grow with the number of shards while T1 stays the collection's",
+        "kernels_rank0": kernels, "index_build_s": round(build_s, 1),
+    }
+
+
 def bench_codec(args, w, peaks, rank, world, local_rank):
     """Index-build codec: argmax over the centroids on tcgen05 (no score table) + residual/bucketize/pack kernel."""
     import torch
@@ -356,6 +478,7 @@ def main():
     ap.add_argument("--cpu-budget-s", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fused", action="store_true", help="materialise bf16 passage embeddings (unfused decompress + MaxSim)")
+    ap.add_argument("--no-cfg4", action="store_true", help="skip the 10M-passage strong-scaling block")
     ap.add_argument("--streams", type=int, default=None, help="query chunks in flight on separate streams (engine default if unset)")
     ap.add_argument("--max-chunk", type=int, default=None, help="queries per chunk (engine default 512)")
     args = ap.parse_args()
@@ -545,110 +668,124 @@ def main():
     todict_ms = (time.perf_counter() - t0) * 1e3
     assert len(rk_dict) == B and (world > 1 or sum(len(v) for v in rk_dict.values()) == stats["found"])
 
+    def build_line():
+        ms_step = ms_total / args.steps
+        C, nbits = index.num_centroids, index.nbits
+        chunks = (B + eng.chunk_size(B) - 1) // eng.chunk_size(B)
+        T1, T2, T3, ncand = stats["T1"], stats["T2"], stats["T3"], stats["ncand"]
+        T3p = stats["T3_padded"]
+        # ALGORITHMIC bytes / flops per step, per stage
+        s_row = 64.0 if eng.s_dtype == torch.float16 else 128.0
+        alg = {
+            "centroid_scores": dict(bytes=(2.0 if eng.s_dtype == torch.float16 else 4.0) * C * 32 * B + 2.0 * C * 128 * chunks,
+                                    flops=2.0 * C * 128 * 32 * B),
+            # inverted-file route: every visited IVF entry costs its pid (4 B) + the candidate-bitmap word and
+            # the word-prefix count that turn it into a slot (4 + 4 B); every (slot, centroid) pair is written and read back
+            # (2 x 8 B) and gathers one S row; one score per candidate goes out.  Queries routed to the token scan instead
+            # read 4 B per candidate token.
+            "filter_stage1": dict(bytes=12.0 * stats["ivf_visits"] + (16.0 + s_row) * stats["ivf_pairs"] + 4.0 * ncand
+                                  + (4.0 * T1 / max(B, 1)) * stats["scan_queries"], flops=0.0,
+                                  note="issue / latency bound (warp-level list walks and a shared-memory counting sort); the byte "
+                                       "model is the inverted-file route's, not the token scan's"),
+            # every token gathers one score row, but a query has only C distinct rows and re-reads are L2 hits: the
+            # compulsory HBM traffic is each touched row once
+            "filter_stage2": dict(bytes=4.0 * T2 + 16.0 * 1024 * B + s_row * min(T2, float(C) * B), flops=0.0),
+            "candidates": dict(bytes=4.0 * ncand + (w["N"] / 8.0) * B * 2, flops=0.0),
+            # codes + residual in, fp16 row out, and the fp16 centroid table once per launch (it stays in L2)
+            "decompress": dict(bytes=(4.0 + 16 * nbits + 256.0) * T3 + 256.0 * min(T3, float(C) * chunks), flops=0.0),
+            "maxsim": dict(bytes=256.0 * T3, flops=2.0 * Lq * 128 * T3,
+                           note="reads D right after decompress wrote it: part of it is still in L2"),
+            # K4' of SURVEY 8d on REAL passage tokens (the 32-token alignment rows the tiles also carry are not counted)
+            "maxsim_fused": dict(bytes=(4.0 + 16 * nbits) * T3, flops=2.0 * Lq * 128 * T3),
+        }
+        kernels = {}
+        for stage, v in stage_ms.items():
+            per_step = sum(v) / args.steps
+            d = {"ms_per_step": round(per_step, 4), "share": round(per_step / ms_step, 4), "launches_per_step": len(v) // args.steps}
+            if stage in alg:
+                d["achieved_GBps"] = round(alg[stage]["bytes"] / (per_step * 1e-3) / 1e9, 1)
+                d["frac_hbm"] = round(d["achieved_GBps"] / peaks["hbm"], 4)
+                if alg[stage]["flops"]:
+                    d["achieved_TFLOPs"] = round(alg[stage]["flops"] / (per_step * 1e-3) / 1e12, 2)
+                    d["frac_tensor"] = round(d["achieved_TFLOPs"] / peaks["tf_sustained"], 4)
+                if "note" in alg[stage]:
+                    d["note"] = alg[stage]["note"]
+            kernels[stage] = d
+        dom = max((s for s in kernels if s in alg), key=lambda s: kernels[s]["ms_per_step"])
+        nl = kernels[dom]["launches_per_step"]
+        per_launch_s = kernels[dom]["ms_per_step"] * 1e-3 / nl
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")        # dram bytes per launch from `ncu --set full`
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get(args.workload, {}).get(dom)
+        if dom == "maxsim_fused":    # intensity 2*Lq*128/(4+16*nbits) flop/B >> ridge: tensor roofline
+            roofline = {"kernel": dom, "bound": "tensor", "achieved": round(alg[dom]["flops"] / nl / per_launch_s / 1e12, 2),
+                        "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
+                        "peak_source": peaks["source"] + " (sustained: timed inside the step)", "traffic": traffic,
+                        "algorithmic_flops_per_launch": alg[dom]["flops"] / nl, "avg_launch_ms": round(per_launch_s * 1e3, 4)}
+        else:
+            roofline = {"kernel": dom, "bound": "hbm", "achieved": round(alg[dom]["bytes"] / nl / per_launch_s / 1e9, 1),
+                        "peak": peaks["hbm"], "unit": "GB/s",
+                        "peak_source": peaks["source"] + " (sustained: timed inside the step)", "traffic": traffic,
+                        "algorithmic_bytes_per_launch": alg[dom]["bytes"] / nl, "avg_launch_ms": round(per_launch_s * 1e3, 4)}
+        roofline["frac"] = round(roofline["achieved"] / roofline["peak"], 4)
+
+        tok_s = world * T3 / (ms_step * 1e-3)               # every rank exact-scores ~T3 (real) tokens of its own shard
+        e2e_ms = ms_e2e / args.steps
+        e2e_engine_ms = ms_e2e_engine / args.steps
+        line = {
+            "metric": "scored_doc_tokens_per_s", "value": tok_s, "unit": "doc-tokens/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16 (centroid contraction) / fp16 (MaxSim operands), fp32 accumulate",
+            "data": "synthetic", "queries_per_s": B / (ms_step * 1e-3),
+            "config": {"workload": f"{args.workload}: {w['desc']}", "passages_per_gpu": w["N"], "tokens_per_gpu": index.num_embeddings,
+                       "centroids": C, "queries_per_step": B, "parallelism": f"pid-range shards x{world}, all-gather top-k merge",
+                       "queries_per_chunk": eng.chunk_size(B), "chunk_streams": eng.streams,
+                       "l2": "inputs larger than L2 (index + centroid-score table >> 126 MB), no explicit flush",
+                       "candidates_per_query": ncand / B, "T1_tokens_per_query": T1 / B, "T2_tokens_per_query": T2 / B,
+                       "T3_tokens_per_query": T3 / B, "T3_padded_tokens_per_query": T3p / B,
+                       "token_accounting": "T1/T2/T3 count real passage tokens (doclens of the listed pids), as the reference arm does; "
+                                           "T3_padded adds the 32-token alignment rows of the MaxSim tiles and is not used in any rate",
+                       "results_per_query": stats["found"] / B},
+            "e2e": {"value": world * T3 / (e2e_ms * 1e-3), "unit": "doc-tokens/s", "queries_per_s": B / (e2e_ms * 1e-3),
+                    "ms_per_step": e2e_ms, "h2d_bytes_per_step": B * Lq * 128 * 4, "d2h_bytes_per_step": B * k * 8 + B * 4,
+                    "call": "search_custom_collection(searcher, queries, Q_host, k, remove_zero_tensors=True) -> Ranking "
+                            "(src/models/flmr/searching.py:43-63 -> CB/searcher.py:80-93); pinned host embeddings in, Ranking over "
+                            "host arrays out, rows become Python tuples on access",
+                    "gpu_launches": launches_api,
+                    "ranking_todict_ms": round(todict_ms, 3),
+                    "ranking_todict_note": "host-only cost of turning all B x k results into Python tuples (Ranking.todict()), "
+                                           "outside the timed region; the reference pays the same per-query tolist/zip inside its loop",
+                    "engine_level": {"ms_per_step": e2e_engine_ms, "queries_per_s": B / (e2e_engine_ms * 1e-3),
+                                     "value": world * T3 / (e2e_engine_ms * 1e-3),
+                                     "call": "Searcher.search_batch(Q_host) + D2H of (pids, scores, counts) into pinned buffers"}},
+            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "kernels": kernels,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            r = run_cpu_sample(make_cpu_searcher(sx), Qdev, k, args.cpu_budget_s, 64)
+            line["agreement"] = agreement((acc_p, acc_s, acc_c), r["results"], k)
+            line["cpu_baseline"] = {"value": r["tokens"] / r["seconds"], "unit": "doc-tokens/s", "cores": r["cores"],
+                                    "kind": r["kind"], "kind_detail": r["kind_detail"], "queries_per_s": r["queries"] / r["seconds"],
+                                    "sample": f"first {r['queries']} of the step's {B} queries, same index, {r['seconds']:.1f} s",
+                                    "stage_share": r["stage_share"]}
+        return line
+
+    line = build_line() if rank == 0 else None
+    # BASELINE.json configs[3] in the same run: the fixed 10M-passage collection sharded over the ranks (strong scaling)
+    if args.workload == "cfg2" and not args.no_cfg4:
+        del searcher, ss, eng, index, sx, rk_dict, acc_p, acc_s, acc_c, Qdev, Qhost, build_line, step, step_api, step_e2e_engine, account
+        api_result[0] = None
+        torch.cuda.empty_cache()
+        try:
+            cfg4 = bench_cfg4(args, rank, world, dev, peaks)
+        except Exception as e:          # the headline line must still come out
+            cfg4 = {"failed": f"{type(e).__name__}: {e}"[:300]}
+        if rank == 0:
+            line["cfg4"] = cfg4
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
-
-    ms_step = ms_total / args.steps
-    C, nbits = index.num_centroids, index.nbits
-    chunks = (B + eng.chunk_size(B) - 1) // eng.chunk_size(B)
-    T1, T2, T3, ncand = stats["T1"], stats["T2"], stats["T3"], stats["ncand"]
-    T3p = stats["T3_padded"]
-    # ALGORITHMIC bytes / flops per step, per stage
-    s_row = 64.0 if eng.s_dtype == torch.float16 else 128.0
-    alg = {
-        "centroid_scores": dict(bytes=(2.0 if eng.s_dtype == torch.float16 else 4.0) * C * 32 * B + 2.0 * C * 128 * chunks,
-                                flops=2.0 * C * 128 * 32 * B),
-        # inverted-file route: every visited IVF entry costs its pid (4 B) + the candidate-bitmap word and
-        # the word-prefix count that turn it into a slot (4 + 4 B); every (slot, centroid) pair is written and read back
-        # (2 x 8 B) and gathers one S row; one score per candidate goes out.  Queries routed to the token scan instead
-        # read 4 B per candidate token.
-        "filter_stage1": dict(bytes=12.0 * stats["ivf_visits"] + (16.0 + s_row) * stats["ivf_pairs"] + 4.0 * ncand
-                              + (4.0 * T1 / max(B, 1)) * stats["scan_queries"], flops=0.0,
-                              note="issue / latency bound (warp-level list walks and a shared-memory counting sort); the byte "
-                                   "model is the inverted-file route's, not the token scan's"),
-        # every token gathers one score row, but a query has only C distinct rows and re-reads are L2 hits: the
-        # compulsory HBM traffic is each touched row once
-        "filter_stage2": dict(bytes=4.0 * T2 + 16.0 * 1024 * B + s_row * min(T2, float(C) * B), flops=0.0),
-        "candidates": dict(bytes=4.0 * ncand + (w["N"] / 8.0) * B * 2, flops=0.0),
-        # codes + residual in, fp16 row out, and the fp16 centroid table once per launch (it stays in L2)
-        "decompress": dict(bytes=(4.0 + 16 * nbits + 256.0) * T3 + 256.0 * min(T3, float(C) * chunks), flops=0.0),
-        "maxsim": dict(bytes=256.0 * T3, flops=2.0 * Lq * 128 * T3,
-                       note="reads D right after decompress wrote it: part of it is still in L2"),
-        # K4' of SURVEY 8d on REAL passage tokens (the 32-token alignment rows the tiles also carry are not counted)
-        "maxsim_fused": dict(bytes=(4.0 + 16 * nbits) * T3, flops=2.0 * Lq * 128 * T3),
-    }
-    kernels = {}
-    for stage, v in stage_ms.items():
-        per_step = sum(v) / args.steps
-        d = {"ms_per_step": round(per_step, 4), "share": round(per_step / ms_step, 4), "launches_per_step": len(v) // args.steps}
-        if stage in alg:
-            d["achieved_GBps"] = round(alg[stage]["bytes"] / (per_step * 1e-3) / 1e9, 1)
-            d["frac_hbm"] = round(d["achieved_GBps"] / peaks["hbm"], 4)
-            if alg[stage]["flops"]:
-                d["achieved_TFLOPs"] = round(alg[stage]["flops"] / (per_step * 1e-3) / 1e12, 2)
-                d["frac_tensor"] = round(d["achieved_TFLOPs"] / peaks["tf_sustained"], 4)
-            if "note" in alg[stage]:
-                d["note"] = alg[stage]["note"]
-        kernels[stage] = d
-    dom = max((s for s in kernels if s in alg), key=lambda s: kernels[s]["ms_per_step"])
-    nl = kernels[dom]["launches_per_step"]
-    per_launch_s = kernels[dom]["ms_per_step"] * 1e-3 / nl
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")        # dram bytes per launch from `ncu --set full`
-    if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get(args.workload, {}).get(dom)
-    if dom == "maxsim_fused":    # intensity 2*Lq*128/(4+16*nbits) flop/B >> ridge: tensor roofline
-        roofline = {"kernel": dom, "bound": "tensor", "achieved": round(alg[dom]["flops"] / nl / per_launch_s / 1e12, 2),
-                    "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
-                    "peak_source": peaks["source"] + " (sustained: timed inside the step)", "traffic": traffic,
-                    "algorithmic_flops_per_launch": alg[dom]["flops"] / nl, "avg_launch_ms": round(per_launch_s * 1e3, 4)}
-    else:
-        roofline = {"kernel": dom, "bound": "hbm", "achieved": round(alg[dom]["bytes"] / nl / per_launch_s / 1e9, 1),
-                    "peak": peaks["hbm"], "unit": "GB/s",
-                    "peak_source": peaks["source"] + " (sustained: timed inside the step)", "traffic": traffic,
-                    "algorithmic_bytes_per_launch": alg[dom]["bytes"] / nl, "avg_launch_ms": round(per_launch_s * 1e3, 4)}
-    roofline["frac"] = round(roofline["achieved"] / roofline["peak"], 4)
-
-    tok_s = world * T3 / (ms_step * 1e-3)               # every rank exact-scores ~T3 (real) tokens of its own shard
-    e2e_ms = ms_e2e / args.steps
-    e2e_engine_ms = ms_e2e_engine / args.steps
-    line = {
-        "metric": "scored_doc_tokens_per_s", "value": tok_s, "unit": "doc-tokens/s", "n_gpus": world,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "bf16 (centroid contraction) / fp16 (MaxSim operands), fp32 accumulate",
-        "data": "synthetic", "queries_per_s": B / (ms_step * 1e-3),
-        "config": {"workload": f"{args.workload}: {w['desc']}", "passages_per_gpu": w["N"], "tokens_per_gpu": index.num_embeddings,
-                   "centroids": C, "queries_per_step": B, "parallelism": f"pid-range shards x{world}, all-gather top-k merge",
-                   "queries_per_chunk": eng.chunk_size(B), "chunk_streams": eng.streams,
-                   "l2": "inputs larger than L2 (index + centroid-score table >> 126 MB), no explicit flush",
-                   "candidates_per_query": ncand / B, "T1_tokens_per_query": T1 / B, "T2_tokens_per_query": T2 / B,
-                   "T3_tokens_per_query": T3 / B, "T3_padded_tokens_per_query": T3p / B,
-                   "token_accounting": "T1/T2/T3 count real passage tokens (doclens of the listed pids), as the reference arm does; "
-                                       "T3_padded adds the 32-token alignment rows of the MaxSim tiles and is not used in any rate",
-                   "results_per_query": stats["found"] / B},
-        "e2e": {"value": world * T3 / (e2e_ms * 1e-3), "unit": "doc-tokens/s", "queries_per_s": B / (e2e_ms * 1e-3),
-                "ms_per_step": e2e_ms, "h2d_bytes_per_step": B * Lq * 128 * 4, "d2h_bytes_per_step": B * k * 8 + B * 4,
-                "call": "search_custom_collection(searcher, queries, Q_host, k, remove_zero_tensors=True) -> Ranking "
-                        "(src/models/flmr/searching.py:43-63 -> CB/searcher.py:80-93); pinned host embeddings in, Ranking over "
-                        "host arrays out, rows become Python tuples on access",
-                "gpu_launches": launches_api,
-                "ranking_todict_ms": round(todict_ms, 3),
-                "ranking_todict_note": "host-only cost of turning all B x k results into Python tuples (Ranking.todict()), "
-                                       "outside the timed region; the reference pays the same per-query tolist/zip inside its loop",
-                "engine_level": {"ms_per_step": e2e_engine_ms, "queries_per_s": B / (e2e_engine_ms * 1e-3),
-                                 "value": world * T3 / (e2e_engine_ms * 1e-3),
-                                 "call": "Searcher.search_batch(Q_host) + D2H of (pids, scores, counts) into pinned buffers"}},
-        "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "kernels": kernels,
-    }
-    if world == 1 and not args.no_cpu_baseline:
-        r = run_cpu_sample(make_cpu_searcher(sx), Qdev, k, args.cpu_budget_s, 64)
-        line["agreement"] = agreement((acc_p, acc_s, acc_c), r["results"], k)
-        line["cpu_baseline"] = {"value": r["tokens"] / r["seconds"], "unit": "doc-tokens/s", "cores": r["cores"],
-                                "kind": r["kind"], "kind_detail": r["kind_detail"], "queries_per_s": r["queries"] / r["seconds"],
-                                "sample": f"first {r['queries']} of the step's {B} queries, same index, {r['seconds']:.1f} s",
-                                "stage_share": r["stage_share"]}
     sys.stdout.flush()
     os.dup2(real_stdout, 1)
     print(json.dumps(line), flush=True)

@@ -571,7 +571,13 @@ static int launch_approx_t(const int32_t* pids, const int32_t* counts, int B, in
         static int configured[kMaxDevices] = {0};
         if (int rc = ensure_dynamic_smem((const void*)approx_scores_kernel<true, kStage1Dpw, ST>, (int)smem, configured)) return rc;
         dim3 grid((pid_stride + kDocs - 1) / kDocs, B);
-        if (only_flagged && grid.x > 8) grid.x = 8;     // rarely-taken fallback: few CTAs per query, each walks its groups
+        // fallback launch (queries flagged for the scan only): few CTAs per query, each walks its groups -- about two
+        // waves of resident CTAs in total, so that a batch whose queries ALL take the scan (long inverted lists: the
+        // 10M-passage index on one GPU) still fills the machine while the usual nobody-flagged launch stays cheap
+        if (only_flagged) {
+            const unsigned cap = (unsigned)max(8, (2 * 8 * sm_count() + B - 1) / B);
+            if (grid.x > cap) grid.x = cap;
+        }
         approx_scores_kernel<true, kStage1Dpw, ST><<<grid, kApproxWarps * 32, smem, st>>>(
             pids, counts, pid_stride, S, qlens, idx_bits, C, codes, offsets, out, only_flagged, flag_stride);
     } else {

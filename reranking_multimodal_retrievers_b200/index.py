@@ -62,16 +62,45 @@ class HostIndex:
     config: dict | None = None
 
 
-def build_ivf(codes: torch.Tensor, doclens: torch.Tensor, num_centroids: int):
+def build_ivf(codes: torch.Tensor, doclens: torch.Tensor, num_centroids: int, block_tokens: int = 1 << 27):
     """Per centroid the sorted unique pids owning a token with that code
-    (CB/indexing/collection_indexer.py:393-431 + CB/indexing/utils.py:8-53)."""
+    (CB/indexing/collection_indexer.py:393-431 + CB/indexing/utils.py:8-53).  Works in passage blocks of at most
+    `block_tokens` tokens -- (code, pid) keys are sorted per block and the blocks' runs are scattered into place by
+    a counting pass -- so that a 1.8 G-token shard needs a few GB of scratch, not a 64-bit sort of all its tokens."""
     dev = codes.device
     n = doclens.numel()
-    tok2pid = torch.repeat_interleave(torch.arange(n, device=dev, dtype=torch.int64), doclens.to(dev))
-    key = torch.unique(codes.to(torch.int64) * n + tok2pid)
-    ivf_codes = torch.div(key, n, rounding_mode="floor")
-    ivf = (key - ivf_codes * n).to(torch.int32)
-    lengths = torch.bincount(ivf_codes, minlength=num_centroids).to(torch.int64)
+    doclens = doclens.to(dev, torch.int64)
+    offsets = torch.zeros(n + 1, device=dev, dtype=torch.int64)
+    offsets[1:] = torch.cumsum(doclens, 0)
+    lengths = torch.zeros(num_centroids, device=dev, dtype=torch.int64)
+    parts = []
+    p0 = 0
+    while p0 < n:
+        target = offsets[p0] + block_tokens
+        p1 = int(torch.searchsorted(offsets, target, right=True).item()) - 1
+        p1 = min(n, max(p1, p0 + 1))
+        e0, e1 = int(offsets[p0]), int(offsets[p1])
+        tok2pid = torch.repeat_interleave(torch.arange(p0, p1, device=dev, dtype=torch.int64), doclens[p0:p1])
+        key = torch.unique(codes[e0:e1].to(torch.int64) * n + tok2pid)       # sorted by (code, pid)
+        del tok2pid
+        c = torch.div(key, n, rounding_mode="floor")
+        pid = (key - c * n).to(torch.int32)
+        del key
+        cnt = torch.bincount(c, minlength=num_centroids)
+        lengths += cnt
+        parts.append((c.to(torch.int32), pid, cnt))
+        p0 = p1
+    if len(parts) == 1:
+        return parts[0][1].contiguous(), lengths.contiguous()
+    total = int(lengths.sum().item())
+    ivf = torch.empty(total, device=dev, dtype=torch.int32)
+    base = torch.cumsum(lengths, 0) - lengths                                 # start of every centroid's list
+    for c, pid, cnt in parts:                                                 # blocks are in pid order: lists stay sorted
+        cl = c.long()
+        start = torch.cumsum(cnt, 0) - cnt
+        pos = base[cl] + (torch.arange(cl.numel(), device=dev, dtype=torch.int64) - start[cl])
+        ivf[pos] = pid
+        base += cnt
     return ivf.contiguous(), lengths.contiguous()
 
 
@@ -156,8 +185,11 @@ class DeviceIndex:
             self.num_embeddings = int(self.codes.numel())
             pd = self.dim * self.nbits // 8
             # rows are read with 16-byte loads; keep 512 bytes of slack behind the last row
-            res = torch.zeros(self.num_embeddings * pd + 512, device=dev, dtype=torch.uint8)
-            res[: self.num_embeddings * pd] = host.residuals.to(dev).reshape(-1)
+            res = getattr(host, "residual_storage", None)        # a resident flat buffer that already has the slack
+            if not (res is not None and res.device == dev and res.dtype == torch.uint8 and res.dim() == 1
+                    and res.numel() >= self.num_embeddings * pd + 512 and res.data_ptr() % 16 == 0):
+                res = torch.zeros(self.num_embeddings * pd + 512, device=dev, dtype=torch.uint8)
+                res[: self.num_embeddings * pd] = host.residuals.to(dev).reshape(-1)
             self._res_storage = res
             self.residuals = res[: self.num_embeddings * pd].view(self.num_embeddings, pd)
             self.centroids_f16 = host.centroids.to(dev, torch.float16).contiguous()

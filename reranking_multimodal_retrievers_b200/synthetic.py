@@ -73,6 +73,66 @@ def build_ivf(codes: torch.Tensor, doclens: torch.Tensor, num_centroids: int):
     return ivf.contiguous(), ivf_lengths.contiguous()
 
 
+@dataclass
+class CollectionShard:
+    """A pid range of a large code-space collection, generated block by block straight into resident buffers
+    (`residual_storage` already carries the slack DeviceIndex wants, so nothing is copied); the IVF is left to
+    DeviceIndex (rebuilt from the shard's codes, as for any pid-range shard)."""
+    centroids: torch.Tensor
+    bucket_cutoffs: torch.Tensor
+    bucket_weights: torch.Tensor
+    codes: torch.Tensor
+    residuals: torch.Tensor
+    residual_storage: torch.Tensor
+    doclens: torch.Tensor
+    nbits: int
+    pid_base: int
+    num_passages_total: int
+    dim: int = 128
+    ivf: torch.Tensor | None = None
+    ivf_lengths: torch.Tensor | None = None
+    config: dict | None = None
+
+
+def make_collection_shard(blocks, passages_per_block: int, doclen_lo: int, doclen_hi: int, nbits: int, num_centroids: int,
+                          total_blocks: int, seed: int = 4000, device: str = "cuda", noise: float = 0.05, dim: int = 128):
+    """Blocks `blocks` (consecutive indices) of a collection of total_blocks x passages_per_block passages in code space
+    (mode="codes" of make_synthetic_index).  Block b is a function of (seed, b) alone and the codebook of `seed` alone,
+    so the collection is the same however many ranks share it."""
+    dev = torch.device(device)
+    blocks = list(blocks)
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    centroids = torch.nn.functional.normalize(torch.randn(num_centroids, dim, generator=g, device=dev), dim=-1).half()
+    nb = 2 ** nbits
+    sigma = noise * (1.0 - 1.0 / dim) ** 0.5
+    q = torch.arange(nb, device=dev, dtype=torch.float32) / nb
+    cutoffs = (sigma * _normal_icdf(q[1:])).float().cpu()
+    weights = (sigma * _normal_icdf(q + 0.5 / nb)).float().cpu()
+    doclens = []
+    for b in blocks:
+        g.manual_seed(seed + 1 + b)
+        doclens.append(torch.randint(doclen_lo, doclen_hi + 1, (passages_per_block,), generator=g, device=dev, dtype=torch.int64))
+    ne = [int(d.sum()) for d in doclens]
+    total = sum(ne)
+    pd = dim * nbits // 8
+    codes = torch.empty(total, device=dev, dtype=torch.int32)
+    storage = torch.zeros(total * pd + 512, device=dev, dtype=torch.uint8)
+    residuals = storage[: total * pd].view(total, pd)
+    e0 = 0
+    for b, n_b in zip(blocks, ne):
+        g.manual_seed(seed + 1000 + b)
+        step = 1 << 26                                   # bounded temporaries
+        for s0 in range(0, n_b, step):
+            m = min(step, n_b - s0)
+            codes[e0 + s0: e0 + s0 + m] = torch.randint(0, num_centroids, (m,), generator=g, device=dev, dtype=torch.int32)
+            residuals[e0 + s0: e0 + s0 + m] = torch.randint(0, 256, (m, pd), generator=g, device=dev, dtype=torch.uint8)
+        e0 += n_b
+    return CollectionShard(centroids=centroids, bucket_cutoffs=cutoffs, bucket_weights=weights, codes=codes, residuals=residuals,
+                           residual_storage=storage, doclens=torch.cat(doclens), nbits=nbits,
+                           pid_base=blocks[0] * passages_per_block, num_passages_total=total_blocks * passages_per_block, dim=dim)
+
+
 def binarize(bucket_idx: torch.Tensor, nbits: int) -> torch.Tensor:
     """u8 bucket indices [n, dim] -> packed residual bytes [n, dim*nbits/8].
     Bits are emitted LSB-first per value and packed MSB-first, exactly as

@@ -4,7 +4,7 @@
 mkdir -p gpurun_out
 for spec in "$@"; do
   IFS='|' read -r label bargs envs <<< "$spec"
-  env $envs python bench.py --steps 20 --warmup 5 --no-cpu-baseline $bargs > gpurun_out/ab_$label.json 2> gpurun_out/ab_$label.err || tail -5 gpurun_out/ab_$label.err
+  env $envs python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-cfg4 $bargs > gpurun_out/ab_$label.json 2> gpurun_out/ab_$label.err || tail -5 gpurun_out/ab_$label.err
   python - "$label" <<'PY'
 import json, sys
 lab = sys.argv[1]

@@ -201,3 +201,23 @@ def test_lazy_ranking_equals_eager_dict():
     q, p, s, c = rk.arrays()
     assert q == ["a", "b"] and p is pids and c is counts
     assert all(isinstance(x, int) for x in rk.data["a"][0][:2]) and isinstance(rk.data["a"][0][2], float)
+
+
+def test_blocked_ivf_build_and_collection_shards_are_block_consistent():
+    """The IVF built in passage blocks equals the one-shot build; a collection generated block by block is the same
+    collection whichever ranks hold which blocks (strong scaling of the 10 M-passage workload relies on it)."""
+    from reranking_multimodal_retrievers_b200 import index, synthetic
+    sx = synthetic.make_synthetic_index(3000, 5, 40, 2, seed=3, num_centroids=256, mode="codes")
+    for bt in (1 << 27, 5000, 41):
+        ivf, lens = index.build_ivf(sx.codes, sx.doclens, 256, block_tokens=bt)
+        assert torch.equal(ivf, sx.ivf) and torch.equal(lens, sx.ivf_lengths)
+    whole = synthetic.make_collection_shard(range(4), 300, 5, 40, 2, 256, 4, device="cpu")
+    off = 0
+    for b in range(4):
+        part = synthetic.make_collection_shard([b], 300, 5, 40, 2, 256, 4, device="cpu")
+        n = part.codes.numel()
+        assert part.pid_base == 300 * b and torch.equal(part.centroids, whole.centroids)
+        assert torch.equal(whole.codes[off:off + n], part.codes) and torch.equal(whole.residuals[off:off + n], part.residuals)
+        assert torch.equal(whole.doclens[300 * b:300 * (b + 1)], part.doclens)
+        off += n
+    assert whole.residual_storage.numel() == whole.codes.numel() * 32 + 512
