@@ -19,7 +19,7 @@ def _header_decls():
 def test_library_builds_and_loads():
     path = build.build_library()
     handle = ctypes.CDLL(path)
-    assert handle.plaid_abi_version() == 1
+    assert handle.plaid_abi_version() == 2
     handle.plaid_arch.restype = ctypes.c_char_p
     assert handle.plaid_arch() == b"sm_100a"
 
