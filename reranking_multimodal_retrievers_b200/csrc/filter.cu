@@ -22,8 +22,10 @@ namespace plaid {
 __device__ __forceinline__ float load_s(const float* p) { return __ldg(p); }
 __device__ __forceinline__ float load_s(const __half* p) { return __half2float(__ldg(p)); }
 
-static constexpr int kApproxWarps = 8;        // warps per CTA
-static constexpr int kStage1Dpw = 16;         // stage 1: 128 passages per CTA (amortises the bitmap load)
+static constexpr int kApproxWarps = 8;        // warps per CTA (stage 2)
+static constexpr int kStage1Warps = 16;       // stage-1 scan: 16 warps share one copy of the pruning bitmap (64 KB at C = 2^19, where
+                                              // 8-warp CTAs left an SM with 16 warps and ~1 KB of code loads in flight each)
+static constexpr int kStage1Dpw = 16;         // stage 1: 256 passages per CTA (amortises the bitmap load)
 #ifndef PLAID_S2_ROWS
 #define PLAID_S2_ROWS 16
 #endif
@@ -62,14 +64,14 @@ __device__ __forceinline__ float gather_rows(unsigned mask, int code, const ST* 
 // The 32 per-token maxima of each passage are parked in shared memory; afterwards lane j of warp 0
 // adds up passage j's row left to right, which is exactly the sequential fp32 sum of
 // filter_pids.cpp:59-63 at 1/32 of the shuffle traffic of doing it inside every warp.
-template <bool USE_IDX, int DPW, typename ST>
-__global__ void __launch_bounds__(kApproxWarps * 32)
+template <bool USE_IDX, int DPW, typename ST, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
 approx_scores_kernel(const int32_t* __restrict__ pids, const int32_t* __restrict__ counts, int pid_stride,
                      const ST* __restrict__ S, const int32_t* __restrict__ qlens,
                      const uint32_t* __restrict__ idx_bits, int C, const int32_t* __restrict__ codes,
                      const int64_t* __restrict__ offsets, float* __restrict__ out,
                      const int32_t* __restrict__ only_flagged, int flag_stride) {
-    constexpr int kDocs = kApproxWarps * DPW;
+    constexpr int kDocs = WARPS * DPW;
     if (only_flagged && only_flagged[(size_t)blockIdx.y * flag_stride] == 0) return;   // hybrid stage 1: not this query
     extern __shared__ __align__(16) uint32_t s_dyn[];
     float (*s_max)[33] = reinterpret_cast<float (*)[33]>(s_dyn);      // [kDocs][33]
@@ -101,6 +103,7 @@ approx_scores_kernel(const int32_t* __restrict__ pids, const int32_t* __restrict
         }
     }
     const uint32_t sbits = smem_u32(s_bits);
+    int pa[4], pb[4];         // stage 1: the first 256 codes of the next passage, requested one passage ahead
 #pragma unroll 1
     for (int d = 0; d < DPW; d++) {
         const int64_t off = __shfl_sync(0xffffffffu, my_off, d);
@@ -109,10 +112,10 @@ approx_scores_kernel(const int32_t* __restrict__ pids, const int32_t* __restrict
         if (USE_IDX) {
             // ---- stage 1: 128 codes per step (one 128-bit load per lane), bitmap probe, one vote ----
             // Elements outside the passage become the sentinel code C, whose bitmap word is zero.
-            const int head = (int)(off & 3);                    // codes is 16-byte aligned: align the stream down
-            const int32_t* cp = codes + (off - head) + lane * 4;
-            const int end = len > 0 ? head + len : 0;
-            auto load4 = [&](int e0, int (&c4)[4]) {
+            // The first 256 codes of passage d + 1 are requested before passage d is scanned: the passages of a
+            // candidate list are scattered over the index, so every one of them is a DRAM round trip of its own and
+            // the walk is bound by how many of them a warp keeps in flight.
+            auto load4 = [&](const int32_t* cp, int head, int end, int e0, int (&c4)[4]) {
                 const int e = e0 + lane * 4;                    // element index relative to the aligned start
                 c4[0] = c4[1] = c4[2] = c4[3] = C;
                 if (e + 3 < end) {                              // whole vector before the passage's end
@@ -139,10 +142,31 @@ approx_scores_kernel(const int32_t* __restrict__ pids, const int32_t* __restrict
                     for (int u = 0; u < 4; u++) m = gather_rows<4>(__ballot_sync(0xffffffffu, w[u] & 1u), c4[u], Sb, m);
                 }
             };
-            for (int e0 = 0; e0 < end; e0 += 256) {             // two vectors (256 codes) in flight per step
-                int ca[4], cb[4];
-                load4(e0, ca);
-                load4(e0 + 128, cb);
+            // codes is 16-byte aligned: align the stream down
+            const int head = (int)(off & 3);
+            const int32_t* cp = codes + (off - head) + lane * 4;
+            const int end = len > 0 ? head + len : 0;
+            if (d == 0) {
+                load4(cp, head, end, 0, pa);
+                load4(cp, head, end, 128, pb);
+            }
+            int ca[4], cb[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) { ca[u] = pa[u]; cb[u] = pb[u]; }
+            if (d + 1 < DPW) {                                  // next passage of this warp: its loads go out now
+                const int64_t noff = __shfl_sync(0xffffffffu, my_off, d + 1);
+                const int nlen = __shfl_sync(0xffffffffu, my_len, d + 1);
+                const int nhead = (int)(noff & 3);
+                const int32_t* ncp = codes + (noff - nhead) + lane * 4;
+                const int nend = nlen > 0 ? nhead + nlen : 0;
+                load4(ncp, nhead, nend, 0, pa);
+                load4(ncp, nhead, nend, 128, pb);
+            }
+            scan4(ca);
+            if (128 < end) scan4(cb);
+            for (int e0 = 256; e0 < end; e0 += 256) {           // passages longer than 256 tokens: two vectors per step
+                load4(cp, head, end, e0, ca);
+                load4(cp, head, end, e0 + 128, cb);
                 scan4(ca);
                 if (e0 + 128 < end) scan4(cb);
             }
@@ -563,27 +587,27 @@ static int launch_approx_t(const int32_t* pids, const int32_t* counts, int B, in
                            int flag_stride = 0) {
     PLAID_CHECK_ARG((reinterpret_cast<uintptr_t>(codes) & 15) == 0, PLAID_ERR_ARG, "approx_scores: codes must be 16-byte aligned");
     if (idx_bits) {
-        constexpr int kDocs = kApproxWarps * kStage1Dpw;
+        constexpr int kDocs = kStage1Warps * kStage1Dpw;
         const size_t smem = (size_t)kDocs * 33 * 4 + (size_t)(C >> 5) * 4 + 16;
         PLAID_CHECK_ARG(smem <= 200 * 1024, PLAID_ERR_UNSUPPORTED, "approx_scores: C=%d pruning bitmap exceeds shared memory", C);
         PLAID_CHECK_ARG((reinterpret_cast<uintptr_t>(idx_bits) & 15) == 0 && (C % 128) == 0, PLAID_ERR_ARG,
                         "approx_scores: idx_bits must be 16-byte aligned and C a multiple of 128");
         static int configured[kMaxDevices] = {0};
-        if (int rc = ensure_dynamic_smem((const void*)approx_scores_kernel<true, kStage1Dpw, ST>, (int)smem, configured)) return rc;
+        if (int rc = ensure_dynamic_smem((const void*)approx_scores_kernel<true, kStage1Dpw, ST, kStage1Warps>, (int)smem, configured)) return rc;
         dim3 grid((pid_stride + kDocs - 1) / kDocs, B);
         // fallback launch (queries flagged for the scan only): few CTAs per query, each walks its groups -- about two
         // waves of resident CTAs in total, so that a batch whose queries ALL take the scan (long inverted lists: the
         // 10M-passage index on one GPU) still fills the machine while the usual nobody-flagged launch stays cheap
         if (only_flagged) {
-            const unsigned cap = (unsigned)max(8, (2 * 8 * sm_count() + B - 1) / B);
+            const unsigned cap = (unsigned)max(4, (2 * 4 * sm_count() + B - 1) / B);
             if (grid.x > cap) grid.x = cap;
         }
-        approx_scores_kernel<true, kStage1Dpw, ST><<<grid, kApproxWarps * 32, smem, st>>>(
+        approx_scores_kernel<true, kStage1Dpw, ST, kStage1Warps><<<grid, kStage1Warps * 32, smem, st>>>(
             pids, counts, pid_stride, S, qlens, idx_bits, C, codes, offsets, out, only_flagged, flag_stride);
     } else {
         constexpr int kDocs = kApproxWarps * kStage2Dpw;
         dim3 grid((pid_stride + kDocs - 1) / kDocs, B);
-        approx_scores_kernel<false, kStage2Dpw, ST><<<grid, kApproxWarps * 32, kDocs * 33 * 4, st>>>(
+        approx_scores_kernel<false, kStage2Dpw, ST, kApproxWarps><<<grid, kApproxWarps * 32, kDocs * 33 * 4, st>>>(
             pids, counts, pid_stride, S, qlens, nullptr, C, codes, offsets, out, only_flagged, flag_stride);
     }
     PLAID_LAUNCH_OK("approx_scores_kernel");
