@@ -104,3 +104,70 @@ def test_fullsize_padded_rerank_linearity_and_permutation():
     ref_clamped = full.max(1).values.clamp(min=0).sum(-1)
     torch.testing.assert_close(sp, ref_clamped, rtol=2e-5, atol=2e-4)
     torch.testing.assert_close(s[:dpq], full.max(1).values.sum(-1), rtol=2e-5, atol=2e-4)
+
+
+def _oracle_check(eng, sx, Q, k, queries, ndocs=1024):
+    """Oracle fed OUR centroid-score table on a few queries: integer stages bit-exact, scores within 1e-3, final
+    order exactly (score desc, pid desc) of our scores."""
+    ix = _oracle_index(sx)
+    pids, scores, counts = eng.search_batch(Q[:max(queries) + 1], k=k, keep_taps=True)
+    eng.check_flags()
+    t = eng.last_taps
+    Qc = Q.cpu()
+    for b in queries:
+        S = t.S[b].float().cpu().contiguous()
+        r = po.rank(ix, Qc[b], 2, 0.45, ndocs, S_override=S, taps=True)
+        assert torch.equal(t.cand_pids[b, :int(t.cand_counts[b])].cpu(), r["candidates"])
+        n1, n2 = int(t.stage1_counts[b]), int(t.stage2_counts[b])
+        assert torch.equal(t.stage1_pids[b, :n1].cpu(), r["stage1_pids"])
+        assert torch.equal(t.stage1_scores[b, :n1].cpu(), r["stage1_scores"])
+        assert torch.equal(t.stage2_pids[b, :n2].cpu(), r["stage2_pids"])
+        assert torch.equal(t.stage2_scores[b, :n2].cpu(), r["stage2_scores"])
+        sc = t.scores[b, :n2].cpu()
+        assert ((sc - r["scores_unsorted"]).abs() <= 1e-3 * r["scores_unsorted"].abs() + 1e-6).all()
+        rp, rs = po.select_top(r["stage2_pids"], sc, k)
+        assert torch.equal(pids[b, :int(counts[b])].cpu(), rp) and torch.equal(scores[b, :int(counts[b])].cpu(), rs)
+
+
+def test_cfg3_at_size_long_queries_nbits4():
+    """BASELINE configs[2] at size: 100k passages of 128..512 tokens (32M tokens, C = 65536), 4-bit residuals, 320-token
+    PreFLMR queries (three query m-tiles in the fused MaxSim; candidate stage on the first 32 tokens)."""
+    k = 100
+    sx, Q, gold, eng = _build(100_000, 48, 320, nbits=4, lo=128, hi=512, seed=1237)
+    p1, s1, c1 = eng.search_batch(Q, k=k)
+    eng.check_flags()
+    assert torch.all(c1 == k) and torch.all(s1[:, :-1] >= s1[:, 1:])
+    srt = p1.sort(dim=1).values
+    assert torch.all(srt[:, 1:] != srt[:, :-1]) and int(p1.min()) >= 0 and int(p1.max()) < 100_000
+    assert float((p1[:, 0].cpu() == gold.cpu().to(torch.int32)).float().mean()) >= 0.99
+    eng.max_chunk = 16                                  # chunking independence
+    p2, s2, _ = eng.search_batch(Q, k=k)
+    assert torch.equal(p1, p2) and torch.equal(s1, s2)
+    eng.max_chunk = 512
+    unf = type(eng)(eng.index, fused=False)             # the unfused pair builds the same tiles: same bits
+    p3, s3, _ = unf.search_batch(Q[:16], k=k)
+    assert torch.equal(p1[:16], p3) and torch.equal(s1[:16], s3)
+    _oracle_check(eng, sx, Q, k, (0, 5, 11))
+
+
+def test_cfg4_shard_at_size_large_codebook():
+    """One 1/8 shard of BASELINE configs[3]: 1.25M passages (225M tokens) against the full collection's C = 524288
+    centroids -- the large-codebook chunking of the engine (148-query chunks, several centroid ranges per group) and
+    33 MB score tables per query."""
+    from reranking_multimodal_retrievers_b200 import synthetic
+    from reranking_multimodal_retrievers_b200.engine import SearchEngine
+    from reranking_multimodal_retrievers_b200.index import DeviceIndex
+    k, N, C = 100, 1_250_000, 524_288
+    sx = synthetic.make_synthetic_index(N, 120, 239, 2, seed=1238, mode="codes", device="cuda", num_centroids=C)
+    Q, gold = synthetic.make_queries(sx, 300, 64, seed=99, return_gold=True)
+    eng = SearchEngine(DeviceIndex(sx))
+    assert eng.chunk_size(300) < 300                     # several chunks, the last one ragged
+    p1, s1, c1 = eng.search_batch(Q, k=k)
+    eng.check_flags()
+    assert torch.all(c1 == k) and torch.all(s1[:, :-1] >= s1[:, 1:])
+    srt = p1.sort(dim=1).values
+    assert torch.all(srt[:, 1:] != srt[:, :-1]) and int(p1.min()) >= 0 and int(p1.max()) < N
+    assert float((p1[:, 0].cpu() == gold.cpu().to(torch.int32)).float().mean()) >= 0.99
+    sub = eng.search_batch(Q[37:61], k=k)                # a different chunking of the same queries
+    assert torch.equal(sub[0], p1[37:61]) and torch.equal(sub[1], s1[37:61])
+    _oracle_check(eng, sx, Q, k, (0, 2))
