@@ -264,6 +264,19 @@ int plaid_colbert_score_padded(const void* Qb_bf16, const int32_t* qlens, int nQ
                                int docs_per_query, float* scores, float* scores_raw, int Lq_out,
                                int* watchdog, void* stream);
 
+/* Gradient of the padded MaxSim for the training-time scoring (FLMRModelForRetrieval.score /
+ * compute_ib_loss_new, src/models/flmr/models/flmr/modeling_flmr.py:932-947,1089-1125, under autograd in the reference).
+ * For every pair p = (query q, passage d) with upstream gradient grad[p] and every query token k < qlens[q]:
+ * t* = first arg max_t of the masked similarity (masked positions count as -9999), dQ[q, k, :] += grad[p] * D[d, t*, :],
+ * dD[d, t*, :] += grad[p] * Q[q, k, :].  Pairing: all_pairs != 0: p = q * n + d over all nQ x n pairs (the [B, B*n_docs]
+ * in-batch score matrix); else passage d pairs with query d / docs_per_query and p = d (colbert_score).
+ * Qb / D are the bf16-rounded operands of the forward; ws_argmax i32 [pairs, Lq_pad] (also an output: t* per pair and
+ * query token); dQ f32 [nQ, Lq_pad, 128] and dD f32 [n, Ld, 128] are fully written (either may be NULL). */
+int plaid_colbert_score_backward(const void* Qb_bf16, const int32_t* qlens, int nQ, int Lq_pad,
+                                 const void* D_bf16, const uint8_t* D_mask, int64_t n, int Ld, int docs_per_query,
+                                 int all_pairs, const float* grad, int32_t* ws_argmax, float* dQ, float* dD,
+                                 void* stream);
+
 /* colbert_score_reduce on an existing fp32 scores_padded [n, Ld, Lq] + mask (colbert.py:237-263,
  * 'colbert' interaction): -9999 fill, max over Ld, sum over Lq (left to right). */
 int plaid_colbert_score_reduce(const float* scores_padded, const uint8_t* D_mask, int64_t n, int Ld, int Lq,

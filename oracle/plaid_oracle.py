@@ -332,3 +332,23 @@ def codec_packbits(flags: torch.Tensor) -> torch.Tensor:
     """ResidualCodec.packbits: the CPU branch's np.packbits (residual.py:200), which packbits.cu:10-57 reproduces
     (ballot over 32 flags, bit-reversed, bytes emitted most significant first)."""
     return torch.as_tensor(np.packbits(np.asarray(flags.contiguous().flatten().ne(0).to(torch.uint8))), dtype=torch.uint8)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Training-time in-batch-negative scoring (SURVEY.md 8f-4): restatement of FLMRModelForRetrieval.compute_ib_loss_new
+# (src/models/flmr/models/flmr/modeling_flmr.py:1089-1125) with flmr_utils.colbert_score_reduce (flmr_utils.py:22-30).
+# Pinned by tests/golden/ib_loss.npz, recorded by executing those two reference functions (tests/golden/make_ib_golden.py).
+def ib_scores(Q: torch.Tensor, D: torch.Tensor, D_mask: torch.Tensor) -> torch.Tensor:
+    """[B, B*n_docs] padded MaxSim of every query against every passage of the batch, fp32 (modeling_flmr.py:1098-1105)."""
+    scores = (D.float().unsqueeze(0) @ Q.float().permute(0, 2, 1).unsqueeze(1)).flatten(0, 1)      # query-major
+    pad = ~D_mask.repeat(Q.size(0), 1, 1).view(scores.size(0), scores.size(1)).bool()
+    scores = scores.masked_fill(pad.unsqueeze(-1), -9999.0)
+    return scores.max(1).values.sum(-1).reshape(Q.size(0), -1)
+
+
+def ib_loss(Q: torch.Tensor, D: torch.Tensor, D_mask: torch.Tensor):
+    """(loss, in_batch_scores, labels): cross entropy with the positive of query i at column i * (n_docs) (:1107-1123)."""
+    s = ib_scores(Q, D, D_mask)
+    step = D.shape[0] // Q.shape[0]
+    labels = torch.arange(Q.shape[0], device=s.device) * step
+    return torch.nn.functional.cross_entropy(s, labels), s, labels

@@ -5,7 +5,7 @@ the filter_pids / decompress_residuals / segmented_maxsim / segmented_lookup ope
 FLMR glue create_searcher / search_custom_collection.  All arithmetic runs in libplaid_b200.so
 (hand-written CUDA, C ABI in include/plaid_b200.h); there is no CPU fallback.
 """
-from . import codec  # noqa: F401
+from . import codec, training  # noqa: F401
 from ._lib import PlaidError  # noqa: F401
 from .codec import ResidualCodec, ResidualEmbeddings  # noqa: F401
 from .infra import ColBERTConfig, Queries, Ranking, Run, RunConfig  # noqa: F401
@@ -23,5 +23,5 @@ __all__ = [
     "colbert_score", "colbert_score_packed", "colbert_score_reduce", "flmr_colbert_score",
     "flmr_colbert_score_reduce", "filter_pids", "decompress_residuals", "segmented_maxsim", "segmented_lookup",
     "codec_decompress_residuals", "packbits", "ResidualCodec", "ResidualEmbeddings", "PlaidError",
-    "create_searcher", "search_custom_collection", "exhaustive_search", "ranking_to_batch_results", "StridedTensor", "codec",
+    "create_searcher", "search_custom_collection", "exhaustive_search", "ranking_to_batch_results", "StridedTensor", "codec", "training",
 ]

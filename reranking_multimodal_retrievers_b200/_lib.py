@@ -46,6 +46,7 @@ _SIGNATURES = {
     "plaid_token_inv_norms": [_P, _P, _I64, _P, _P, _I, _I, _P, _P],
     "plaid_segmented_maxsim": [_P, _I, _P, _P, _I, _P, _P],
     "plaid_colbert_score_padded": [_P, _P, _I, _I, _I, _P, _P, _I64, _I, _I, _P, _P, _I, _P, _P],
+    "plaid_colbert_score_backward": [_P, _P, _I, _I, _P, _P, _I64, _I, _I, _I, _P, _P, _P, _P, _P],
     "plaid_colbert_score_reduce": [_P, _P, _I64, _I, _I, _P, _P],
     "plaid_merge_topk": [_P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P],
     "plaid_merge_topk_msg": [_P, _I, _I, _I, _P, _P, _P, _P, _P, _P],

@@ -392,3 +392,46 @@ def test_integration_md_level2_stub(P, golden):
     S, idx, cand = (torch.from_numpy(g[f"{n}_0"]) for n in ("S", "idx", "cand"))
     out = ns["filter_pids_b200"](cand, S, ix.codes, ix.doclens, ix.offsets[:-1].contiguous(), idx, int(g["ndocs"]))
     assert np.array_equal(out.cpu().numpy(), g["stage2_0"])
+
+
+def test_training_scores_and_gradients(P):
+    """f4: in-batch-negative scores / loss and the MaxSim backward (modeling_flmr.py:932-947,1089-1125) -- forward within
+    the bf16 tolerance of the reference's recorded fp32 scores, tight against the oracle on the same bf16 operands;
+    gradients against autograd through the oracle on those operands."""
+    pkg, ops = P
+    from plaid_test_helpers import load_golden
+    g = load_golden("ib_loss")
+    Q, D, mask = (torch.from_numpy(g[k]).clone() for k in ("Q", "D", "mask"))
+    Qd, Dd = Q.cuda().requires_grad_(True), D.cuda().requires_grad_(True)
+    s = pkg.training.in_batch_scores(Qd, Dd, mask)
+    assert s.shape == (4, 12)
+    ref = torch.from_numpy(g["scores"])
+    assert ((s.detach().cpu() - ref).abs() <= 1e-3 * ref.abs() + 2e-2).all()            # vs the reference's fp32 scores
+    Qb = Q.bfloat16().float().requires_grad_(True)
+    Db = D.bfloat16().float().requires_grad_(True)
+    loss_ref, s_b, _ = po.ib_loss(Qb, Db, mask)
+    torch.testing.assert_close(s.detach().cpu(), s_b.detach(), rtol=2e-5, atol=2e-4)   # same operands: summation order only
+    loss = pkg.training.compute_ib_loss_new(Qd, Dd, mask)
+    torch.testing.assert_close(loss.detach().cpu(), loss_ref.detach(), rtol=1e-4, atol=1e-4)
+    loss.backward()
+    loss_ref.backward()
+    # an arg-max can only differ where two passage tokens tie to within the summation order: allow a few rows
+    for got, want in ((Qd.grad.cpu(), Qb.grad), (Dd.grad.cpu(), Db.grad)):
+        bad = ((got - want).abs() > 1e-4 * want.abs().max() + 1e-6).any(-1).float().mean()
+        assert float(bad) < 0.02, float(bad)
+    assert torch.count_nonzero(Dd.grad.cpu()[~mask.squeeze(-1).bool()]) == 0           # padding never wins a maximum here
+    # the paired form (FLMRModelForRetrieval.score: every query repeated for its n_docs passages)
+    n_docs = int(g["n_docs"])
+    Q2, D2 = Q.cuda().requires_grad_(True), D.cuda().requires_grad_(True)
+    sp = pkg.training.colbert_score(Q2, D2, mask, docs_per_query=n_docs)
+    torch.testing.assert_close(sp.detach().cpu(), s_b.detach().reshape(4, 4, n_docs)[torch.arange(4), torch.arange(4)].reshape(-1),
+                               rtol=2e-5, atol=2e-4)
+    w = torch.linspace(0.5, 1.5, sp.numel(), device="cuda")
+    (sp * w).sum().backward()
+    Qr = Q.bfloat16().float().requires_grad_(True)
+    Dr = D.bfloat16().float().requires_grad_(True)
+    sr = po.colbert_score(Qr.repeat_interleave(n_docs, dim=0), Dr, mask.squeeze(-1).bool())
+    (sr * w.cpu()).sum().backward()
+    for got, want in ((Q2.grad.cpu(), Qr.grad), (D2.grad.cpu(), Dr.grad)):
+        bad = ((got - want).abs() > 1e-4 * want.abs().max() + 1e-6).any(-1).float().mean()
+        assert float(bad) < 0.02, float(bad)

@@ -151,6 +151,18 @@ def _gloo_worker(rank, world, port, tmpdir):
             assert torch.equal(blocks[r, : B * k].view(B, k) + x.pid_bases[r], gp[r])
             assert torch.equal(blocks[r, B * k: 2 * B * k].view(torch.float32).view(B, k), gs[r])
             assert torch.equal(blocks[r, 2 * B * k:], gc[r])
+        # training-time gather of queries / passages / masks (modeling_flmr.py:1127-1194): rank-ordered concatenation,
+        # gradient only through the local blocks
+        from reranking_multimodal_retrievers_b200 import training
+        q = torch.full((2, 3, 4), float(rank + 1), requires_grad=True)
+        d = torch.full((4, 5, 4), float(10 * (rank + 1)), requires_grad=True)
+        m = torch.full((4, 5, 1), float(rank))
+        gq, gd, gm = training.gather_tensors_from_other_gpus(q, d, m)
+        assert gq.shape == (2 * world, 3, 4) and gd.shape == (4 * world, 5, 4) and gm.shape == (4 * world, 5, 1)
+        for r in range(world):
+            assert torch.all(gq[2 * r:2 * r + 2] == r + 1) and torch.all(gd[4 * r:4 * r + 4] == 10 * (r + 1)) and torch.all(gm[4 * r:4 * r + 4] == r)
+        (gq.sum() * 2 + gd.sum() * 3).backward()
+        assert torch.all(q.grad == 2) and torch.all(d.grad == 3)                 # nothing flows to the other ranks' blocks
         torch.save((gp, gs, gc, merged), os.path.join(tmpdir, f"r{rank}.pt"))
     finally:
         dist.destroy_process_group()

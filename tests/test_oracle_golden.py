@@ -66,3 +66,20 @@ def test_codec_oracle_matches_reference_compress(name):
     codes, res = po.codec_compress(cent, torch.from_numpy(g["bucket_cutoffs"]), int(g["nbits"]), embs)
     assert torch.equal(codes, torch.from_numpy(g["codes"]))
     assert torch.equal(res, torch.from_numpy(g["residuals"]))
+
+
+def test_ib_loss_oracle_equals_reference_golden():
+    """Training-time in-batch scoring: the restatement against vectors recorded by executing the reference's
+    compute_ib_loss_new / colbert_score_reduce (tests/golden/make_ib_golden.py), gradients included."""
+    from plaid_test_helpers import load_golden
+    g = load_golden("ib_loss")
+    Q, D, mask = (torch.from_numpy(g[k]).clone() for k in ("Q", "D", "mask"))
+    Q.requires_grad_(True)
+    D.requires_grad_(True)
+    loss, scores, labels = po.ib_loss(Q, D, mask)
+    assert labels.tolist() == g["labels"].tolist()
+    np.testing.assert_allclose(scores.detach().numpy(), g["scores"], rtol=1e-6, atol=1e-5)
+    np.testing.assert_allclose(float(loss), float(g["loss"]), rtol=1e-6)
+    loss.backward()
+    np.testing.assert_allclose(Q.grad.numpy(), g["dQ"], rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(D.grad.numpy(), g["dD"], rtol=1e-5, atol=1e-7)
