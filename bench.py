@@ -279,6 +279,40 @@ def bench_cfg4(args, rank, world, dev, peaks, steps=4, warmup=2):
     events, eng.events = eng.events, None
     ms_api = timed(lambda: search_custom_collection(ss, queries, Qhost, num_document_to_retrieve=k, remove_zero_tensors=True), steps)
     eng.check_flags()
+    # the same with the stage lists exchanged too (exact-global truncation: the result of ONE index holding the collection)
+    exact = None
+    if world > 1:
+        sx_ = sharded.ShardedSearcher(searcher, mode="exact")
+        st2 = dict(T2=0, T3=0)
+
+        def account2(ws, n):
+            dl = index.doclens
+            for key, pk, ck in (("T2", "s1_pids", "s1_counts"), ("T3", "s2_pids", "s2_counts")):
+                cnt = ws[ck][:n].long()
+                m = torch.arange(ws[pk].shape[1], device=dev).unsqueeze(0) < cnt.unsqueeze(1)
+                st2[key] += int(dl[torch.where(m, ws[pk][:n], 0).long()].mul(m).sum())
+
+        eng.search_batch(Q, k=k, remove_zero_rows=True, on_chunk=account2)
+        for _ in range(warmup):
+            sx_.search_batch(Q, k, True)
+        eng.events = []
+        ms_x = timed(lambda: sx_.search_batch(Q, k, True), steps)
+        ev_x, eng.events = eng.events, None
+        ms_x_api = timed(lambda: search_custom_collection(sx_, queries, Qhost, num_document_to_retrieve=k, remove_zero_tensors=True), steps)
+        eng.check_flags()
+        t2 = torch.tensor([st2["T2"], st2["T3"]], device=dev, dtype=torch.float64)
+        dist.all_reduce(t2)
+        kx = {}
+        for stage, a, b in ev_x:
+            kx[stage] = kx.get(stage, 0.0) + a.elapsed_time(b) / steps
+        exact = {"ms_per_step": ms_x, "queries_per_s": B / (ms_x * 1e-3), "doc_tokens_per_s": float(t2[1]) / (ms_x * 1e-3),
+                 "e2e": {"ms_per_step": ms_x_api, "queries_per_s": B / (ms_x_api * 1e-3)},
+                 "T2_tokens_per_query_all_shards": float(t2[0]) / B, "T3_tokens_per_query_all_shards": float(t2[1]) / B,
+                 "kernels_rank0": {s_: round(v, 3) for s_, v in kx.items()},
+                 "semantics": "ShardedSearcher(mode='exact'): two more all-gathers per query chunk (the shards' stage-1 and stage-2 "
+                              "(score, pid) lists), merge + keep-own-range kernels; returns exactly what one index holding all "
+                              "10M passages returns (tests/nccl_worker.py), and stage 2 / MaxSim shrink with the shard count"}
+        eng.exchange = None
     tot = torch.tensor([stats["T1"], stats["T2"], stats["T3"], stats["ncand"], stats["scan_queries"]], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(tot)                                 # tokens scored by ALL shards
@@ -310,7 +344,7 @@ def bench_cfg4(args, rank, world, dev, peaks, steps=4, warmup=2):
         "stage1_scan_fallback_queries_all_shards": scan_q, "queries_with_results_rank0": found,
         "semantics": "per-shard truncation to ndocs / ndocs/4 (SURVEY.md 8e, oracle (A)): every shard exact-scores its own 256 "
                      "passages per query, so T2/T3 grow with the number of shards while T1 stays the collection's",
-        "kernels_rank0": kernels, "index_build_s": round(build_s, 1),
+        "kernels_rank0": kernels, "exact_global": exact, "index_build_s": round(build_s, 1),
     }
 
 

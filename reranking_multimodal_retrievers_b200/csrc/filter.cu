@@ -574,6 +574,41 @@ merge_topk_kernel(const float* __restrict__ scores, const int32_t* __restrict__ 
     write_selection(s_sel, m, k, out_pids + (size_t)b * k, out_scores + (size_t)b * k, out_counts ? out_counts + b : nullptr);
 }
 
+// keep the entries of a global list that fall into this shard's pid range, in order, as shard-local pids
+__global__ void __launch_bounds__(256)
+localize_lists_kernel(const int32_t* __restrict__ pids, const int32_t* __restrict__ counts, int stride, int pid_lo, int pid_hi,
+                      int32_t* __restrict__ out_pids, int32_t* __restrict__ out_counts, int out_stride) {
+    __shared__ int s_warp[8];
+    __shared__ int s_base;
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n = min(max(counts[b], 0), stride);
+    const int32_t* src = pids + (size_t)b * stride;
+    int32_t* dst = out_pids + (size_t)b * out_stride;
+    if (tid == 0) s_base = 0;
+    __syncthreads();
+    for (int i0 = 0; i0 < n; i0 += 256) {
+        const int i = i0 + tid;
+        const int pid = i < n ? src[i] : -1;
+        const bool mine = pid >= pid_lo && pid < pid_hi;
+        const unsigned m = __ballot_sync(0xffffffffu, mine);
+        if (lane == 0) s_warp[warp] = __popc(m);
+        __syncthreads();
+        int before = s_base;
+        for (int w = 0; w < warp; w++) before += s_warp[w];
+        if (mine) dst[before + __popc(m & ((1u << lane) - 1u))] = pid - pid_lo;
+        __syncthreads();
+        if (tid == 0) {
+            int t = 0;
+            for (int w = 0; w < 8; w++) t += s_warp[w];
+            s_base += t;
+        }
+        __syncthreads();
+    }
+    const int kept = s_base;
+    for (int i = kept + tid; i < out_stride; i += 256) dst[i] = PLAID_NO_PID;
+    if (tid == 0) out_counts[b] = kept;
+}
+
 static int next_pow2(int v) {
     int p = 1;
     while (p < v) p <<= 1;
@@ -1038,17 +1073,19 @@ extern "C" int plaid_filter_pids(const int32_t* pids, const int32_t* counts, int
 
 static int launch_merge(const float* scores, const int32_t* pids, const int32_t* counts, int64_t sp_stride, int64_t c_stride,
                         const int32_t* pid_bases, int G, int B, int k, int32_t* out_pids, float* out_scores,
-                        int32_t* out_counts, uint64_t* ws_keys, cudaStream_t st) {
+                        int32_t* out_counts, uint64_t* ws_keys, cudaStream_t st, int rows = -1) {
     using namespace plaid;
     PLAID_CHECK_ARG(G >= 1 && G <= 64 && B >= 0 && k >= 1 && k <= 16384, PLAID_ERR_UNSUPPORTED,
                     "plaid_merge_topk: G=%d (1..64), k=%d (1..16384)", G, k);
-    if (B == 0) return PLAID_OK;
+    if (rows < 0) rows = B;
+    PLAID_CHECK_ARG(rows <= B, PLAID_ERR_ARG, "plaid_merge_topk: rows=%d > B=%d", rows, B);
+    if (rows == 0) return PLAID_OK;
     const int sel_cap = next_pow2(k < 2 ? 2 : k);
     const size_t smem = (size_t)(sel_cap + kBktCap + kRankMax) * 8 + 256 * 4 + 16;
     static int configured[kMaxDevices] = {0};
     if (int rc = ensure_dynamic_smem((const void*)merge_topk_kernel, (int)smem, configured)) return rc;
-    merge_topk_kernel<<<B, kSelThreads, smem, st>>>(scores, pids, counts, sp_stride, c_stride, pid_bases, G, B, k, sel_cap,
-                                                    out_pids, out_scores, out_counts, ws_keys);
+    merge_topk_kernel<<<rows, kSelThreads, smem, st>>>(scores, pids, counts, sp_stride, c_stride, pid_bases, G, B, k, sel_cap,
+                                                       out_pids, out_scores, out_counts, ws_keys);
     PLAID_LAUNCH_OK("merge_topk_kernel");
     return PLAID_OK;
 }
@@ -1070,4 +1107,25 @@ extern "C" int plaid_merge_topk_msg(const int32_t* gathered, int G, int B, int k
     const int64_t stride = 2 * (int64_t)B * k + B;     // one rank's message: pids | score bits | counts
     return launch_merge(reinterpret_cast<const float*>(gathered + (int64_t)B * k), gathered, gathered + 2 * (int64_t)B * k,
                         stride, stride, pid_bases, G, B, k, out_pids, out_scores, out_counts, ws_keys, (cudaStream_t)stream);
+}
+
+extern "C" int plaid_merge_lists_msg(const int32_t* gathered, int G, int B, int rows, int k, const int32_t* pid_bases,
+                                     int32_t* out_pids, float* out_scores, int32_t* out_counts, uint64_t* ws_keys,
+                                     void* stream) {
+    PLAID_CHECK_ARG(gathered && out_pids && out_scores && ws_keys, PLAID_ERR_ARG, "plaid_merge_lists_msg: null pointer");
+    PLAID_CHECK_ARG(B >= 0 && k >= 1 && rows >= 0, PLAID_ERR_ARG, "plaid_merge_lists_msg: bad sizes");
+    const int64_t stride = 2 * (int64_t)B * k + B;
+    return launch_merge(reinterpret_cast<const float*>(gathered + (int64_t)B * k), gathered, gathered + 2 * (int64_t)B * k,
+                        stride, stride, pid_bases, G, B, k, out_pids, out_scores, out_counts, ws_keys, (cudaStream_t)stream, rows);
+}
+
+extern "C" int plaid_localize_lists(const int32_t* pids, const int32_t* counts, int B, int stride, int pid_lo, int pid_hi,
+                                    int32_t* out_pids, int32_t* out_counts, int out_stride, void* stream) {
+    using namespace plaid;
+    PLAID_CHECK_ARG(pids && counts && out_pids && out_counts && B >= 0 && stride >= 1 && out_stride >= stride, PLAID_ERR_ARG,
+                    "plaid_localize_lists: bad argument");
+    if (B == 0) return PLAID_OK;
+    localize_lists_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(pids, counts, stride, pid_lo, pid_hi, out_pids, out_counts, out_stride);
+    PLAID_LAUNCH_OK("localize_lists_kernel");
+    return PLAID_OK;
 }

@@ -125,6 +125,8 @@ class SearchEngine:
         # so the latency-bound kernels of one chunk (selects, candidate marking) and the tails of the big ones overlap
         # with the other chunk's work
         self.streams = max(1, int(os.environ.get("PLAID_STREAMS", streams or 1)))
+        # set by sharded.ShardedSearcher(mode="exact"): exchanges the stage lists between the shards
+        self.exchange = None
         self._side_streams = None
         self._ws_slots = {}
         self._ws_key = None
@@ -178,6 +180,10 @@ class SearchEngine:
         tok_stride = nd4 * (((max(ix.max_doclen, 1) + 31) // 32) * 32)   # passages are 32-token aligned in D
         tok_stride = ((tok_stride + 127) // 128) * 128
         e = lambda *shape, dtype: torch.empty(*shape, device=dev, dtype=dtype)
+        # the two filter stages' result lists live in one i32 block each, laid out [pids | score bits | counts]: for the
+        # exact-global sharded search the block IS the all-gather send buffer (sharded.StageExchange)
+        s1_msg = torch.zeros(2 * Bc * ndocs + Bc, device=dev, dtype=torch.int32)
+        s2_msg = torch.zeros(2 * Bc * nd4 + Bc, device=dev, dtype=torch.int32)
         ws = dict(
             csplit=csplit, nlists=nlists, cand_stride=cand_stride, fstride=fstride, tok_stride=tok_stride, nd4=nd4,
             Qb=e(Bc, Lq_pad, 128, dtype=torch.bfloat16), Qh=e(Bc, Lq_pad, 128, dtype=torch.float16),
@@ -193,10 +199,10 @@ class SearchEngine:
             cand_pids=e(Bc, cand_stride, dtype=torch.int32), cand_counts=e(Bc, dtype=torch.int32),
             ws_scores=e(Bc, fstride, dtype=torch.float32), ws_keys=e(2, dtype=torch.int64),   # ABI leftover of select_top: must be non-null, never touched
 
-            s1_pids=e(Bc, ndocs, dtype=torch.int32), s1_scores=e(Bc, ndocs, dtype=torch.float32),
-            s1_counts=e(Bc, dtype=torch.int32),
-            s2_pids=e(Bc, nd4, dtype=torch.int32), s2_scores=e(Bc, nd4, dtype=torch.float32),
-            s2_counts=e(Bc, dtype=torch.int32),
+            s1_msg=s1_msg, s1_pids=s1_msg[: Bc * ndocs].view(Bc, ndocs),
+            s1_scores=s1_msg[Bc * ndocs: 2 * Bc * ndocs].view(torch.float32).view(Bc, ndocs), s1_counts=s1_msg[2 * Bc * ndocs:],
+            s2_msg=s2_msg, s2_pids=s2_msg[: Bc * nd4].view(Bc, nd4),
+            s2_scores=s2_msg[Bc * nd4: 2 * Bc * nd4].view(torch.float32).view(Bc, nd4), s2_counts=s2_msg[2 * Bc * nd4:],
             tok_offsets=e(Bc, nd4 + 1, dtype=torch.int32),
             D=None,   # fp16 [Bc * tok_stride, 128], allocated on first use by the unfused path
             scores=e(Bc, nd4, dtype=torch.float32),
@@ -287,11 +293,17 @@ class SearchEngine:
                  _p(cq), _p(ws["idx_bits"]), C, _p(ix.codes), _p(ix.offsets), _p(ws["ws_scores"]), st)
         call("select1", "plaid_select_top", _p(ws["cand_pids"]), _p(ws["ws_scores"]), _p(ws["cand_counts"]), b, cs, ndocs,
              _p(ws["s1_pids"]), _p(ws["s1_scores"]), _p(ws["s1_counts"]), ndocs, _p(ws["ws_keys"]), st)
+        if self.exchange is not None:     # exact-global sharding: the collection's ndocs best, then this shard's share of them
+            self.exchange.globalize(ws["s1_msg"], ws["s1_pids"], ws["s1_counts"], Bc, b, ndocs)
+            self.launch_count += 2
         call("filter_stage2", "plaid_approx_scores", _p(ws["s1_pids"]), _p(ws["s1_counts"]), b, ndocs, _p(ws["S"]), f16,
              _p(cq), None, C, _p(ix.codes), _p(ix.offsets), _p(ws["ws_scores"]), st)
         call("select2", "plaid_select_top", _p(ws["s1_pids"]), _p(ws["ws_scores"]), _p(ws["s1_counts"]), b, ndocs, nd4_,
              _p(ws["s2_pids"]), _p(ws["s2_scores"]), _p(ws["s2_counts"]), nd4_, _p(ws["ws_keys"]), st)
         nd4 = ws["nd4"]
+        if self.exchange is not None:
+            self.exchange.globalize(ws["s2_msg"], ws["s2_pids"], ws["s2_counts"], Bc, b, nd4)
+            self.launch_count += 2
         call("doc_offsets", "plaid_doc_token_offsets", _p(ws["s2_pids"]), _p(ws["s2_counts"]), b, nd4, _p(ix.offsets),
              32, _p(ws["tok_offsets"]), st)
         if self.fused and Lq_pad <= 384:

@@ -95,17 +95,67 @@ class ListExchange:
         return self.out_p, self.out_s, self.out_c
 
 
+class StageExchange:
+    """Exact-global truncation of the two filter stages across pid-range shards (oracle (B)).
+
+    The reference keeps the ndocs best stage-1 passages and the ndocs/4 best stage-2 passages of the WHOLE collection
+    (filter_pids.cpp:108-123,148-157).  A shard's own top list is a superset of its share of the global one, so after
+    each stage: every rank's list block ([pids | score bits | counts], written in place by the selection kernel) is
+    all-gathered, every rank merges the G lists into the collection's top list with the same (score, pid) selection, and
+    keeps the entries of its own pid range.  The sharded search then returns exactly what one index holding the whole
+    collection would -- and stage 2 / decompression / MaxSim work on 1/G of the passages per rank."""
+
+    def __init__(self, pid_base: int, num_passages: int, device, group=None):
+        self.group = group
+        self.world_size = dist.get_world_size(group)
+        self.lo, self.hi = int(pid_base), int(pid_base) + int(num_passages)
+        mine = torch.tensor([pid_base], device=device, dtype=torch.int32)
+        self.pid_bases = torch.empty(self.world_size, device=device, dtype=torch.int32)
+        dist.all_gather_into_tensor(self.pid_bases, mine, group=group)
+        self._bufs = {}
+
+    def _buffers(self, msg: torch.Tensor, Bc: int, keep: int):
+        key = (msg.numel(), Bc, keep)
+        b = self._bufs.get(key)
+        if b is None:
+            dev = msg.device
+            b = dict(recv=torch.empty(self.world_size * msg.numel(), device=dev, dtype=torch.int32),
+                     gp=torch.empty(Bc, keep, device=dev, dtype=torch.int32), gs=torch.empty(Bc, keep, device=dev, dtype=torch.float32),
+                     gc=torch.empty(Bc, device=dev, dtype=torch.int32),
+                     keys=torch.empty(Bc * self.world_size * keep, device=dev, dtype=torch.int64))
+            self._bufs[key] = b
+        return b
+
+    def globalize(self, msg, pids, counts, Bc: int, rows: int, keep: int):
+        """msg: this shard's list block of a stage (local pids); on return `pids` / `counts` (views of msg) hold the
+        shard's share of the collection's top-`keep` list, as local pids in global (score, pid) order."""
+        b = self._buffers(msg, Bc, keep)
+        dist.all_gather_into_tensor(b["recv"], msg, group=self.group)
+        _lib.call("plaid_merge_lists_msg", _p(b["recv"]), self.world_size, Bc, rows, keep, _p(self.pid_bases),
+                  _p(b["gp"]), _p(b["gs"]), _p(b["gc"]), _p(b["keys"]), _stream())
+        _lib.call("plaid_localize_lists", _p(b["gp"]), _p(b["gc"]), rows, keep, self.lo, self.hi, _p(pids), _p(counts), keep,
+                  _stream())
+
+
 class ShardedSearcher:
     """Wraps a per-rank `Searcher` (built with pid_range = this rank's shard).  `search_batch` and `_search_all_Q`
     have the single-GPU Searcher's signatures, so `search_custom_collection(sharded_searcher, ...)` works unchanged."""
 
-    def __init__(self, searcher, group=None):
+    def __init__(self, searcher, group=None, mode: str = "per_shard"):
+        """mode "per_shard": every shard truncates to ndocs / ndocs/4 on its own and only the final top-k lists are
+        exchanged (one all-gather; oracle (A) of SURVEY.md 8e).  mode "exact": the stage lists are exchanged too
+        (StageExchange), and the result equals the search of one index holding the whole collection."""
+        assert mode in ("per_shard", "exact")
         self.searcher = searcher
         self.group = group
+        self.mode = mode
         self.world_size = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.config = searcher.config
         self._xchg = None
+        ix = searcher.ranker.index
+        searcher.ranker.engine.exchange = (StageExchange(ix.pid_base, ix.num_passages, ix.device, group)
+                                           if mode == "exact" and self.world_size > 1 else None)
 
     def _exchange(self, B, k):
         if self._xchg is None or (self._xchg.B, self._xchg.k) != (B, k):

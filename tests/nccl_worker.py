@@ -3,7 +3,8 @@
 Every rank searches its shard through the product path (ShardedSearcher: per-shard pipeline, the final top-k written
 into the all-gather send block, one all_gather_into_tensor, merge kernel reading the receive buffer in place) and
 ALSO runs the oracle on its shard with the shard's own centroid-score table injected (oracle (A)).
-Rank 0 gathers the oracle's per-shard lists, merges them with the oracle's (score, pid) selection and compares."""
+Rank 0 gathers the oracle's per-shard lists, merges them with the oracle's (score, pid) selection and compares.
+The exact-global mode (stage lists exchanged too) is checked against the search of the unsharded index."""
 import os
 import sys
 
@@ -58,6 +59,20 @@ def main(out_path):
             op, os_ = po.select_top(r["stage2_pids"], sc, k)          # the oracle's order on OUR scores (exact compare)
             assert torch.equal(lp[b, :int(lc[b])].cpu(), op + p0) and torch.equal(ls[b, :int(lc[b])].cpu(), os_)
             mine.append((op + p0, os_))
+        # exact-global mode (oracle (B)): the stage lists are exchanged as well, and the sharded search must
+        # return EXACTLY what one index holding the whole collection returns -- pids, scores and counts, bit for bit
+        whole = pkg.Searcher(index=sx, device=dev)
+        whole.configure(ndocs=ndocs)
+        wp_, ws_, wc_ = whole.search_batch(Q, k, False)
+        wp_, ws_, wc_ = wp_.clone(), ws_.clone(), wc_.clone()
+        searcher_x = pkg.Searcher(index=host, device=dev)
+        searcher_x.configure(ndocs=ndocs)
+        sx_exact = sharded.ShardedSearcher(searcher_x, mode="exact")
+        for max_chunk in (512, 8):                      # one chunk, and three (the last one ragged)
+            searcher_x.ranker.engine.max_chunk = max_chunk
+            ep, es, ec = sx_exact.search_batch(Q, k, False)
+            assert torch.equal(ec, wc_) and torch.equal(ep, wp_) and torch.equal(es, ws_), "exact-global sharded search differs from the single index"
+        searcher_x.ranker.engine.check_flags()
         gathered = [None] * world
         dist.all_gather_object(gathered, mine)
         if rank == 0:
