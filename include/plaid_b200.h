@@ -298,16 +298,13 @@ int plaid_merge_topk_msg(const int32_t* gathered, int G, int B, int k, const int
                          void* stream);
 
 /* Exact-global sharded search (oracle (B)): the reference truncates to ndocs and ndocs/4 over the WHOLE
- * collection (filter_pids.cpp:108-123,148-157), so after each filter stage the shards exchange their (score, pid)
- * lists.  plaid_merge_lists_msg is plaid_merge_topk_msg for a chunk: the message layout is that of B queries
- * ([B*k pids | B*k score bits | B counts] per rank) but only the first `rows` queries are merged (the last chunk of a
- * batch is ragged).  plaid_localize_lists then keeps, per query and in order, the entries of the merged global list
- * that fall into this shard's pid range [pid_lo, pid_hi) as shard-local pids (unused slots PLAID_NO_PID). */
-int plaid_merge_lists_msg(const int32_t* gathered, int G, int B, int rows, int k, const int32_t* pid_bases,
-                          int32_t* out_pids, float* out_scores, int32_t* out_counts, uint64_t* ws_keys,
-                          void* stream);
-int plaid_localize_lists(const int32_t* pids, const int32_t* counts, int B, int stride, int pid_lo, int pid_hi,
-                         int32_t* out_pids, int32_t* out_counts, int out_stride, void* stream);
+ * collection (filter_pids.cpp:108-123,148-157), so after each filter stage the shards all-gather their list blocks
+ * ([B*k local pids | B*k score bits | B counts] per rank, each list sorted by (score, pid) descending -- what
+ * plaid_select_top wrote).  The collection's `keep` best keys take a prefix of every shard's list: out_counts[b] = length
+ * of THIS shard's prefix for the first `rows` queries (my_rank = index of this shard's block, pid_bases[g] = first global
+ * pid of shard g).  The shard's pid list itself stays as it is. */
+int plaid_prefix_share(const int32_t* gathered, int G, int B, int rows, int k, int keep, const int32_t* pid_bases,
+                       int my_rank, int32_t* out_counts, void* stream);
 
 /* ---- a11: ragged gather (CB/search/segmented_lookup.cpp:36-125) ------------------------------
  * out rows = concatenation over i of input[offsets[i] .. offsets[i]+lengths[i]) (row_bytes each);

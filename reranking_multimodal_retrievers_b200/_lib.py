@@ -50,8 +50,7 @@ _SIGNATURES = {
     "plaid_colbert_score_reduce": [_P, _P, _I64, _I, _I, _P, _P],
     "plaid_merge_topk": [_P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P],
     "plaid_merge_topk_msg": [_P, _I, _I, _I, _P, _P, _P, _P, _P, _P],
-    "plaid_merge_lists_msg": [_P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P],
-    "plaid_localize_lists": [_P, _P, _I, _I, _I, _I, _P, _P, _I, _P],
+    "plaid_prefix_share": [_P, _I, _I, _I, _I, _I, _P, _I, _P, _P],
     "plaid_segmented_lookup": [_P, _I64, _P, _P, _P, _I, _P, _P],
 }
 _RESTYPES = {"plaid_last_error": ctypes.c_char_p, "plaid_arch": ctypes.c_char_p}

@@ -574,39 +574,43 @@ merge_topk_kernel(const float* __restrict__ scores, const int32_t* __restrict__ 
     write_selection(s_sel, m, k, out_pids + (size_t)b * k, out_scores + (size_t)b * k, out_counts ? out_counts + b : nullptr);
 }
 
-// keep the entries of a global list that fall into this shard's pid range, in order, as shard-local pids
+// Exact-global truncation across shards without a merge: every shard's stage list is sorted by (score, global pid)
+// descending and the keys of different shards never tie, so the collection's `keep` best keys take a PREFIX of every
+// shard's list.  A warp per query finds the length of this shard's prefix by bisection: element i of my list has global
+// rank i + (number of keys of the other shards above it), the latter by one bisection per other list (lane g searches
+// list g of the all-gathered blocks).  ~100 dependent loads per query instead of a select over G * k keys.
 __global__ void __launch_bounds__(256)
-localize_lists_kernel(const int32_t* __restrict__ pids, const int32_t* __restrict__ counts, int stride, int pid_lo, int pid_hi,
-                      int32_t* __restrict__ out_pids, int32_t* __restrict__ out_counts, int out_stride) {
-    __shared__ int s_warp[8];
-    __shared__ int s_base;
-    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int n = min(max(counts[b], 0), stride);
-    const int32_t* src = pids + (size_t)b * stride;
-    int32_t* dst = out_pids + (size_t)b * out_stride;
-    if (tid == 0) s_base = 0;
-    __syncthreads();
-    for (int i0 = 0; i0 < n; i0 += 256) {
-        const int i = i0 + tid;
-        const int pid = i < n ? src[i] : -1;
-        const bool mine = pid >= pid_lo && pid < pid_hi;
-        const unsigned m = __ballot_sync(0xffffffffu, mine);
-        if (lane == 0) s_warp[warp] = __popc(m);
-        __syncthreads();
-        int before = s_base;
-        for (int w = 0; w < warp; w++) before += s_warp[w];
-        if (mine) dst[before + __popc(m & ((1u << lane) - 1u))] = pid - pid_lo;
-        __syncthreads();
-        if (tid == 0) {
-            int t = 0;
-            for (int w = 0; w < 8; w++) t += s_warp[w];
-            s_base += t;
+prefix_share_kernel(const int32_t* __restrict__ gathered, int G, int B, int rows, int k, int keep,
+                    const int32_t* __restrict__ pid_bases, int me, int32_t* __restrict__ out_counts) {
+    const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (b >= rows) return;
+    const int64_t stride = 2 * (int64_t)B * k + B;
+    auto key_of = [&](int g, int j) -> uint64_t {
+        const int32_t* blk = gathered + (int64_t)g * stride;
+        const uint32_t sbits = float_to_ordered(__int_as_float(blk[(int64_t)B * k + (int64_t)b * k + j]));
+        return ((uint64_t)sbits << 32) | (uint32_t)(blk[(int64_t)b * k + j] + pid_bases[g]);
+    };
+    auto len_of = [&](int g) { return min(max(gathered[(int64_t)g * stride + 2 * (int64_t)B * k + b], 0), k); };
+    const int n_me = len_of(me);
+    int lo = 0, hi = n_me;                       // the answer L lies in [lo, hi]: rank(L - 1) < keep
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        const uint64_t e = key_of(me, mid - 1);
+        int above = 0;
+        for (int g = lane; g < G; g += 32) {
+            if (g == me) continue;
+            int a = 0, z = len_of(g);            // first index of list g whose key is below e
+            while (a < z) {
+                const int m = (a + z) >> 1;
+                if (key_of(g, m) > e) a = m + 1; else z = m;
+            }
+            above += a;
         }
-        __syncthreads();
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) above += __shfl_xor_sync(0xffffffffu, above, o);
+        if (mid - 1 + above < keep) lo = mid; else hi = mid - 1;
     }
-    const int kept = s_base;
-    for (int i = kept + tid; i < out_stride; i += 256) dst[i] = PLAID_NO_PID;
-    if (tid == 0) out_counts[b] = kept;
+    if (lane == 0) out_counts[b] = lo;
 }
 
 static int next_pow2(int v) {
@@ -1109,23 +1113,14 @@ extern "C" int plaid_merge_topk_msg(const int32_t* gathered, int G, int B, int k
                         stride, stride, pid_bases, G, B, k, out_pids, out_scores, out_counts, ws_keys, (cudaStream_t)stream);
 }
 
-extern "C" int plaid_merge_lists_msg(const int32_t* gathered, int G, int B, int rows, int k, const int32_t* pid_bases,
-                                     int32_t* out_pids, float* out_scores, int32_t* out_counts, uint64_t* ws_keys,
-                                     void* stream) {
-    PLAID_CHECK_ARG(gathered && out_pids && out_scores && ws_keys, PLAID_ERR_ARG, "plaid_merge_lists_msg: null pointer");
-    PLAID_CHECK_ARG(B >= 0 && k >= 1 && rows >= 0, PLAID_ERR_ARG, "plaid_merge_lists_msg: bad sizes");
-    const int64_t stride = 2 * (int64_t)B * k + B;
-    return launch_merge(reinterpret_cast<const float*>(gathered + (int64_t)B * k), gathered, gathered + 2 * (int64_t)B * k,
-                        stride, stride, pid_bases, G, B, k, out_pids, out_scores, out_counts, ws_keys, (cudaStream_t)stream, rows);
-}
-
-extern "C" int plaid_localize_lists(const int32_t* pids, const int32_t* counts, int B, int stride, int pid_lo, int pid_hi,
-                                    int32_t* out_pids, int32_t* out_counts, int out_stride, void* stream) {
+extern "C" int plaid_prefix_share(const int32_t* gathered, int G, int B, int rows, int k, int keep, const int32_t* pid_bases,
+                                  int my_rank, int32_t* out_counts, void* stream) {
     using namespace plaid;
-    PLAID_CHECK_ARG(pids && counts && out_pids && out_counts && B >= 0 && stride >= 1 && out_stride >= stride, PLAID_ERR_ARG,
-                    "plaid_localize_lists: bad argument");
-    if (B == 0) return PLAID_OK;
-    localize_lists_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(pids, counts, stride, pid_lo, pid_hi, out_pids, out_counts, out_stride);
-    PLAID_LAUNCH_OK("localize_lists_kernel");
+    PLAID_CHECK_ARG(gathered && pid_bases && out_counts, PLAID_ERR_ARG, "plaid_prefix_share: null pointer");
+    PLAID_CHECK_ARG(G >= 1 && G <= 1024 && my_rank >= 0 && my_rank < G && B >= 0 && rows >= 0 && rows <= B && k >= 1 && keep >= 1,
+                    PLAID_ERR_ARG, "plaid_prefix_share: bad sizes");
+    if (rows == 0) return PLAID_OK;
+    prefix_share_kernel<<<(rows + 7) / 8, 256, 0, (cudaStream_t)stream>>>(gathered, G, B, rows, k, keep, pid_bases, my_rank, out_counts);
+    PLAID_LAUNCH_OK("prefix_share_kernel");
     return PLAID_OK;
 }

@@ -101,40 +101,30 @@ class StageExchange:
     The reference keeps the ndocs best stage-1 passages and the ndocs/4 best stage-2 passages of the WHOLE collection
     (filter_pids.cpp:108-123,148-157).  A shard's own top list is a superset of its share of the global one, so after
     each stage: every rank's list block ([pids | score bits | counts], written in place by the selection kernel) is
-    all-gathered, every rank merges the G lists into the collection's top list with the same (score, pid) selection, and
-    keeps the entries of its own pid range.  The sharded search then returns exactly what one index holding the whole
+    all-gathered and every rank finds how long a prefix of its own (sorted) list belongs to the collection's top list
+    (plaid_prefix_share: bisection against the other shards' lists; no merge, no copy).  The sharded search then returns exactly what one index holding the whole
     collection would -- and stage 2 / decompression / MaxSim work on 1/G of the passages per rank."""
 
     def __init__(self, pid_base: int, num_passages: int, device, group=None):
         self.group = group
         self.world_size = dist.get_world_size(group)
-        self.lo, self.hi = int(pid_base), int(pid_base) + int(num_passages)
+        self.rank = dist.get_rank(group)
         mine = torch.tensor([pid_base], device=device, dtype=torch.int32)
         self.pid_bases = torch.empty(self.world_size, device=device, dtype=torch.int32)
         dist.all_gather_into_tensor(self.pid_bases, mine, group=group)
-        self._bufs = {}
-
-    def _buffers(self, msg: torch.Tensor, Bc: int, keep: int):
-        key = (msg.numel(), Bc, keep)
-        b = self._bufs.get(key)
-        if b is None:
-            dev = msg.device
-            b = dict(recv=torch.empty(self.world_size * msg.numel(), device=dev, dtype=torch.int32),
-                     gp=torch.empty(Bc, keep, device=dev, dtype=torch.int32), gs=torch.empty(Bc, keep, device=dev, dtype=torch.float32),
-                     gc=torch.empty(Bc, device=dev, dtype=torch.int32),
-                     keys=torch.empty(Bc * self.world_size * keep, device=dev, dtype=torch.int64))
-            self._bufs[key] = b
-        return b
+        self._recv = {}
 
     def globalize(self, msg, pids, counts, Bc: int, rows: int, keep: int):
-        """msg: this shard's list block of a stage (local pids); on return `pids` / `counts` (views of msg) hold the
-        shard's share of the collection's top-`keep` list, as local pids in global (score, pid) order."""
-        b = self._buffers(msg, Bc, keep)
-        dist.all_gather_into_tensor(b["recv"], msg, group=self.group)
-        _lib.call("plaid_merge_lists_msg", _p(b["recv"]), self.world_size, Bc, rows, keep, _p(self.pid_bases),
-                  _p(b["gp"]), _p(b["gs"]), _p(b["gc"]), _p(b["keys"]), _stream())
-        _lib.call("plaid_localize_lists", _p(b["gp"]), _p(b["gc"]), rows, keep, self.lo, self.hi, _p(pids), _p(counts), keep,
-                  _stream())
+        """msg: this shard's list block of a stage ([pids | score bits | counts], lists sorted by (score, pid) descending).
+        On return counts[:rows] (a view of msg) is the length of the shard's share of the collection's top-`keep` list --
+        a prefix of its own list, so `pids` stays untouched."""
+        del pids
+        recv = self._recv.get(msg.numel())
+        if recv is None:
+            recv = self._recv[msg.numel()] = torch.empty(self.world_size * msg.numel(), device=msg.device, dtype=torch.int32)
+        dist.all_gather_into_tensor(recv, msg, group=self.group)
+        _lib.call("plaid_prefix_share", _p(recv), self.world_size, Bc, rows, keep, keep, _p(self.pid_bases), self.rank,
+                  _p(counts), _stream())
 
 
 class ShardedSearcher:

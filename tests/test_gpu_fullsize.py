@@ -160,14 +160,19 @@ def test_cfg4_shard_at_size_large_codebook():
     k, N, C = 100, 1_250_000, 524_288
     sx = synthetic.make_synthetic_index(N, 120, 239, 2, seed=1238, mode="codes", device="cuda", num_centroids=C)
     Q, gold = synthetic.make_queries(sx, 300, 64, seed=99, return_gold=True)
-    eng = SearchEngine(DeviceIndex(sx))
-    assert eng.chunk_size(300) < 300                     # several chunks, the last one ragged
+    eng = SearchEngine(DeviceIndex(sx), s_budget_bytes=6 << 30)
+    assert eng.chunk_size(300) == 148                    # 148-query chunks (4 centroid ranges per query group), the last one ragged
     p1, s1, c1 = eng.search_batch(Q, k=k)
     eng.check_flags()
     assert torch.all(c1 == k) and torch.all(s1[:, :-1] >= s1[:, 1:])
     srt = p1.sort(dim=1).values
     assert torch.all(srt[:, 1:] != srt[:, :-1]) and int(p1.min()) >= 0 and int(p1.max()) < N
     assert float((p1[:, 0].cpu() == gold.cpu().to(torch.int32)).float().mean()) >= 0.99
+    big = SearchEngine(eng.index)                        # default table budget: one chunk of 300 queries
+    assert big.chunk_size(300) == 300
+    pb, sb, _ = big.search_batch(Q, k=k)
+    assert torch.equal(pb, p1) and torch.equal(sb, s1)
+    del big
     sub = eng.search_batch(Q[37:61], k=k)                # a different chunking of the same queries
     assert torch.equal(sub[0], p1[37:61]) and torch.equal(sub[1], s1[37:61])
     _oracle_check(eng, sx, Q, k, (0, 2))
