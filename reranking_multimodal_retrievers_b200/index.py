@@ -60,6 +60,7 @@ class HostIndex:
     pid_base: int = 0              # global pid of local passage 0
     num_passages_total: int | None = None
     config: dict | None = None
+    residual_storage: torch.Tensor | None = None   # resident flat buffer behind `residuals` with 512 B of slack (device loads)
 
 
 def build_ivf(codes: torch.Tensor, doclens: torch.Tensor, num_centroids: int, block_tokens: int = 1 << 27):
@@ -104,9 +105,7 @@ def build_ivf(codes: torch.Tensor, doclens: torch.Tensor, num_centroids: int, bl
     return ivf.contiguous(), lengths.contiguous()
 
 
-def load_reference_index(index_path: str, pid_range: tuple[int, int] | None = None) -> HostIndex:
-    """Read a reference-format index directory; with pid_range=(p0, p1) only that passage slice
-    (only the chunk files that overlap it are opened)."""
+def _index_header(index_path: str, pid_range):
     with open(os.path.join(index_path, "metadata.json")) as f:
         meta = json.load(f)
     cfg = meta.get("config", {})
@@ -120,33 +119,81 @@ def load_reference_index(index_path: str, pid_range: tuple[int, int] | None = No
             chunk_doclens.append(torch.tensor(json.load(f), dtype=torch.int64))
     n_total = sum(int(d.numel()) for d in chunk_doclens)
     p0, p1 = (0, n_total) if pid_range is None else (max(0, pid_range[0]), min(n_total, pid_range[1]))
-    codes_parts, res_parts, dl_parts = [], [], []
-    base = 0
+    # the chunk files that overlap [p0, p1): (chunk index, first / last token of the slice inside the chunk, its doclens)
+    todo, base = [], 0
     for i, dl in enumerate(chunk_doclens):
         c0, c1 = base, base + dl.numel()
         base = c1
         lo, hi = max(p0, c0), min(p1, c1)
         if lo >= hi:
             continue
-        codes = torch.load(os.path.join(index_path, f"{i}.codes.pt"), map_location="cpu")
-        res = torch.load(os.path.join(index_path, f"{i}.residuals.pt"), map_location="cpu")
         off = torch.cat((torch.zeros(1, dtype=torch.int64), torch.cumsum(dl, 0)))
-        e0, e1 = int(off[lo - c0]), int(off[hi - c0])
-        codes_parts.append(codes[e0:e1].to(torch.int32))
-        res_parts.append(res[e0:e1])
-        dl_parts.append(dl[lo - c0:hi - c0])
-    doclens = torch.cat(dl_parts) if dl_parts else torch.zeros(0, dtype=torch.int64)
-    codes = torch.cat(codes_parts) if codes_parts else torch.zeros(0, dtype=torch.int32)
-    residuals = torch.cat(res_parts) if res_parts else torch.zeros(0, dim * nbits // 8, dtype=torch.uint8)
+        todo.append((i, int(off[lo - c0]), int(off[hi - c0]), dl[lo - c0:hi - c0]))
+    return cfg, nbits, dim, centroids, cutoffs, weights, n_total, p0, p1, todo
+
+
+def _load_chunk(index_path: str, i: int, e0: int, e1: int):
+    codes = torch.load(os.path.join(index_path, f"{i}.codes.pt"), map_location="cpu")
+    res = torch.load(os.path.join(index_path, f"{i}.residuals.pt"), map_location="cpu")
+    return codes[e0:e1].to(torch.int32).contiguous(), res[e0:e1].contiguous()
+
+
+def load_reference_index(index_path: str, pid_range: tuple[int, int] | None = None, device=None, workers: int = 4) -> HostIndex:
+    """Read a reference-format index directory; with pid_range=(p0, p1) only that passage slice
+    (only the chunk files that overlap it are opened).  The chunk files are read by `workers` threads.
+    device=None: CPU tensors, as the reference's IndexLoader holds them (CB/search/index_loader.py:24-61).
+    device=cuda: the codes / residuals go straight into their final device buffers -- every chunk is copied from a
+    pinned staging buffer on a copy stream while the next chunk files are still being read -- and the result feeds
+    DeviceIndex without another copy (the reference concatenates everything on the CPU first,
+    CB/indexing/codecs/residual_embeddings.py:27-52)."""
+    from concurrent.futures import ThreadPoolExecutor
+    cfg, nbits, dim, centroids, cutoffs, weights, n_total, p0, p1, todo = _index_header(index_path, pid_range)
+    pd = dim * nbits // 8
+    doclens = torch.cat([t[3] for t in todo]) if todo else torch.zeros(0, dtype=torch.int64)
+    total = sum(t[2] - t[1] for t in todo)
+    storage = None
+    with ThreadPoolExecutor(max_workers=max(1, workers)) as ex:
+        futures = [ex.submit(_load_chunk, index_path, i, e0, e1) for i, e0, e1, _ in todo]
+        if device is None:
+            parts = [f.result() for f in futures]
+            codes = torch.cat([c for c, _ in parts]) if parts else torch.zeros(0, dtype=torch.int32)
+            residuals = torch.cat([r for _, r in parts]) if parts else torch.zeros(0, pd, dtype=torch.uint8)
+        else:
+            dev = torch.device(device)
+            codes = torch.empty(total, device=dev, dtype=torch.int32)
+            storage = torch.zeros(total * pd + 512, device=dev, dtype=torch.uint8)     # 512 B of slack, as DeviceIndex wants
+            residuals = storage[: total * pd].view(total, pd)
+            copy_stream = torch.cuda.Stream(device=dev)
+            copy_stream.wait_stream(torch.cuda.current_stream(dev))
+            biggest = max((e1 - e0 for _, e0, e1, _ in todo), default=0)
+            stage = [(torch.empty(biggest, dtype=torch.int32).pin_memory(), torch.empty(biggest, pd, dtype=torch.uint8).pin_memory(),
+                      torch.cuda.Event()) for _ in range(2 if todo else 0)]
+            at = 0
+            for j, f in enumerate(futures):
+                c, r = f.result()
+                n = c.numel()
+                hc, hr, done = stage[j % 2]
+                if j >= 2:
+                    done.synchronize()                       # the copy that last used this staging pair has finished
+                hc[:n].copy_(c)
+                hr[:n].copy_(r)
+                with torch.cuda.stream(copy_stream):
+                    codes[at:at + n].copy_(hc[:n], non_blocking=True)
+                    residuals[at:at + n].copy_(hr[:n], non_blocking=True)
+                    done.record(copy_stream)
+                at += n
+            torch.cuda.current_stream(dev).wait_stream(copy_stream)
     ivf = ivf_lengths = None
     if pid_range is None or (p0 == 0 and p1 == n_total):
         ivf_path = os.path.join(index_path, "ivf.pid.pt")
         if os.path.exists(ivf_path):
             ivf, ivf_lengths = torch.load(ivf_path, map_location="cpu")
             ivf, ivf_lengths = ivf.to(torch.int32), ivf_lengths.to(torch.int64)
-    return HostIndex(centroids=centroids.half(), bucket_cutoffs=cutoffs.float(), bucket_weights=weights.float(),
+    host = HostIndex(centroids=centroids.half(), bucket_cutoffs=cutoffs.float(), bucket_weights=weights.float(),
                      codes=codes, residuals=residuals.contiguous(), doclens=doclens, ivf=ivf, ivf_lengths=ivf_lengths,
                      nbits=nbits, dim=dim, pid_base=p0, num_passages_total=n_total, config=cfg)
+    host.residual_storage = storage
+    return host
 
 
 def shard_bounds(num_passages: int, world_size: int, rank: int) -> tuple[int, int]:

@@ -31,7 +31,8 @@ class IndexScorer:
         self.use_gpu = True
         if isinstance(index_path, (str, os.PathLike)):
             self.index_path = str(index_path)
-            host = load_reference_index(self.index_path, pid_range)
+            dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+            host = load_reference_index(self.index_path, pid_range, device=dev)    # chunk files stream straight into HBM
         else:  # an in-memory HostIndex / SyntheticIndex, or an index that is already resident (DeviceIndex)
             self.index_path = None
             host = index_path

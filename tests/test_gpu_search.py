@@ -450,3 +450,21 @@ def test_query_maxlen_below_32(pkg, qml):
         assert ((sc - r["scores_unsorted"]).abs() <= SCORE_REL_TOL * r["scores_unsorted"].abs() + 1e-5).all()
     with pytest.raises(pkg.PlaidError):
         SearchEngine(DeviceIndex(sx), query_maxlen=64)
+
+
+def test_reference_format_index_streams_into_device_buffers(pkg, tmp_path):
+    """load_reference_index(device=cuda): chunk files read by worker threads and copied through pinned staging buffers
+    straight into the final device tensors (whole index and a pid-range shard) -- same bytes as the CPU loader."""
+    from reranking_multimodal_retrievers_b200 import synthetic
+    from reranking_multimodal_retrievers_b200.index import DeviceIndex, load_reference_index
+    sx = synthetic.make_synthetic_index(2500, 5, 60, 4, seed=51, num_centroids=256, mode="codes")
+    path = synthetic.write_reference_format(sx, str(tmp_path / "idx.nbits=4"), chunk_passages=333)   # 8 chunk files, ragged last
+    for rng in (None, (400, 1999)):
+        cpu = load_reference_index(path, rng)
+        dev = load_reference_index(path, rng, device="cuda", workers=3)
+        assert dev.codes.is_cuda and dev.residual_storage is not None
+        assert torch.equal(dev.codes.cpu(), cpu.codes) and torch.equal(dev.residuals.cpu(), cpu.residuals)
+        assert torch.equal(dev.doclens, cpu.doclens) and dev.pid_base == cpu.pid_base
+        ix = DeviceIndex(dev)
+        assert ix._res_storage.data_ptr() == dev.residual_storage.data_ptr()          # adopted, not copied
+        assert torch.count_nonzero(ix._res_storage[-512:]) == 0
