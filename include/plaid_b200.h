@@ -102,9 +102,10 @@ int plaid_approx_scores(const int32_t* pids, const int32_t* counts, int B, int p
 /* Stage 1 of the filter driven by the inverted file (same result as plaid_approx_scores with idx_bits, bit for
  * bit): for every surviving centroid (idx bit set) its IVF list names the passages that contain it; the candidate
  * bitmap / word-prefix counts (plaid_candidates) turn those into candidate slots; the (slot, centroid) pairs are
- * counting-sorted per query in shared memory and reduced.  Queries whose mask is dense (more than cap_s
- * survivors, more than 4*cap_p list entries to visit, more pairs than cap_p, or more candidates than fit the
- * sort) are routed through the token scan instead -- decided per query on the device, no host round trip.
+ * counting-sorted per query in shared memory and reduced (candidate lists longer than the ~33 k slots the bins
+ * hold -- shards of millions of passages -- in slot ranges, one CTA per query and range).  Queries whose mask is
+ * dense (more than cap_s survivors, more than 4*cap_p list entries to visit, more pairs than cap_p) are routed
+ * through the token scan instead -- decided per query on the device, no host round trip.
  * Workspaces: ws_surv i32 [B, cap_s], ws_pair_slot / ws_pair_c i32 [B, cap_p], ws_sorted_c i32 [B, 2*cap_p] (8-byte aligned),
  * ws_meta i32 [B, 4]. */
 int plaid_filter_stage1_ivf(const int32_t* pids, const int32_t* counts, int B, int pid_stride, const void* S,
@@ -113,6 +114,10 @@ int plaid_filter_stage1_ivf(const int32_t* pids, const int32_t* counts, int B, i
                             const int64_t* ivf_offsets, const uint32_t* bitmap, const int32_t* wprefix, int N,
                             int32_t* ws_surv, int cap_s, int32_t* ws_pair_slot, int32_t* ws_pair_c,
                             int32_t* ws_sorted_c, int cap_p, int32_t* ws_meta, float* out_scores, void* stream);
+
+/* Test hook: slots per range of plaid_filter_stage1_ivf's sort (0 = as many as shared memory holds, the default), so
+ * that the multi-range path can be exercised on small indexes.  Process-wide; returns the previous value. */
+int plaid_set_ivf_range_slots(int slots);
 
 /* Per query the `keep` largest (score, pid) pairs in descending (score, pid) order -- the order of
  * std::pair<float,int> in filter_pids.cpp:24,108-123.  Emits min(counts[b], keep) entries

@@ -31,6 +31,7 @@ _SIGNATURES = {
     "plaid_approx_scores": [_P, _P, _I, _I, _P, _I, _P, _P, _I, _P, _P, _P, _P],
     "plaid_filter_stage1_ivf": [_P, _P, _I, _I, _P, _I, _P, _P, _I, _P, _P, _P, _P, _P, _P, _I, _P, _I, _P, _P, _P, _I, _P, _P,
                                 _P],
+    "plaid_set_ivf_range_slots": [_I],
     "plaid_select_top": [_P, _P, _P, _I, _I, _I, _P, _P, _P, _I, _P, _P],
     "plaid_filter_pids": [_P, _P, _I, _I, _P, _I, _P, _P, _I, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "plaid_build_weight_table": [_P, _P, _P, _I, _P, _P],

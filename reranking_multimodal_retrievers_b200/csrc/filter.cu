@@ -675,6 +675,7 @@ static int launch_approx(const int32_t* pids, const int32_t* counts, int B, int 
 //                   per-token max over its survivors' S rows and the sequential fp32 sum (filter_pids.cpp:59-63).
 // The per-token max is order-independent, so the result is bit-identical to the scan.
 static constexpr int kIvfMeta = 4;   // per query: [0] survivors, [1] pairs, [2] use-the-scan flag, [3] visits
+static int g_ivf_range_slots = 0;    // plaid_set_ivf_range_slots (test hook): 0 = what shared memory holds
 
 __global__ void __launch_bounds__(256)
 ivf_survivors_kernel(const uint32_t* __restrict__ idx_bits, int C, const int64_t* __restrict__ ivf_offsets,
@@ -862,25 +863,43 @@ template <typename ST>
 __global__ void __launch_bounds__(IvfTile<ST>::kThreads)
 ivf_scores_kernel(const int32_t* __restrict__ counts, int pid_stride, const int32_t* __restrict__ meta,
                   const int32_t* __restrict__ pair_slot, const int32_t* __restrict__ pair_c, int32_t* __restrict__ sorted_c,
-                  int cap_p, const ST* __restrict__ S, int C, const int32_t* __restrict__ qlens, float* __restrict__ out) {
+                  int cap_p, const ST* __restrict__ S, int C, const int32_t* __restrict__ qlens, float* __restrict__ out,
+                  int range_slots) {
     using Tile = IvfTile<ST>;
     constexpr int kScan = 512;
     extern __shared__ __align__(16) int s_bins[];          // [n + 1] then one tile per warp
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
     const int32_t* m = meta + (size_t)b * kIvfMeta;
     if (m[2]) return;
-    const int n = min(counts[b], pid_stride);
+    // A CTA sorts and reduces the candidate slots [slot0, slot0 + n) of its query: the whole list when it fits the
+    // shared-memory bins (gridDim.y = 1, every workload but very large shards), else one range of range_slots slots.
+    const int n_all = min(counts[b], pid_stride);
+    const int slot0 = blockIdx.y * range_slots;
+    if (slot0 >= n_all) return;
+    const int n = min(range_slots, n_all - slot0);
     const int np = min(m[1], cap_p);
     typename Tile::Cell* s_max = reinterpret_cast<typename Tile::Cell*>(
         reinterpret_cast<char*>(s_bins + ((n + 1 + 3) & ~3)) + (size_t)warp * Tile::kBytes);
     __shared__ int s_part[kScan];
+    __shared__ int s_below;
     const int32_t* ps = pair_slot + (size_t)b * cap_p;
     const int32_t* pc = pair_c + (size_t)b * cap_p;
-    int2* sc2 = reinterpret_cast<int2*>(sorted_c) + (size_t)b * cap_p;   // (slot, centroid), sorted by slot
     for (int i = tid; i <= n; i += blockDim.x) s_bins[i] = 0;
+    if (tid == 0) s_below = 0;
     __syncthreads();
-    for (int i = tid; i < np; i += blockDim.x) atomicAdd(&s_bins[ps[i] + 1], 1);   // count of slot s in bins[s + 1]
+    int below = 0;                                          // pairs of the earlier ranges: this range's offset in sorted_c
+    for (int i = tid; i < np; i += blockDim.x) {
+        const int sl = ps[i] - slot0;
+        if ((unsigned)sl < (unsigned)n) atomicAdd(&s_bins[sl + 1], 1);   // count of slot s in bins[s + 1]
+        else if (sl < 0) below++;
+    }
+    if (gridDim.y > 1) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) below += __shfl_xor_sync(0xffffffffu, below, o);
+        if (lane == 0 && below) atomicAdd(&s_below, below);
+    }
     __syncthreads();
+    int2* sc2 = reinterpret_cast<int2*>(sorted_c) + (size_t)b * cap_p + s_below;   // (slot, centroid) of this range, sorted by slot
     // exclusive scan over bins[0..n] by the first 512 threads: thread t owns a contiguous span
     const int span = (n + 1 + kScan - 1) / kScan;
     const int lo = tid < kScan ? min(tid * span, n + 1) : n + 1, hi = min(lo + span, n + 1);
@@ -909,8 +928,8 @@ ivf_scores_kernel(const int32_t* __restrict__ counts, int pid_stride, const int3
     // now bins[i] = number of pairs with slot < i  (inclusive scan of the shifted counts); start(s) = bins[s]
     // scatter: cursor = start(s); afterwards bins[s] = end(s) and start(s) = (s ? bins[s-1] : 0)
     for (int i = tid; i < np; i += blockDim.x) {
-        const int slot = ps[i];
-        sc2[atomicAdd(&s_bins[slot], 1)] = make_int2(slot, pc[i]);
+        const int sl = ps[i] - slot0;                       // slots are range-relative from here on
+        if ((unsigned)sl < (unsigned)n) sc2[atomicAdd(&s_bins[sl], 1)] = make_int2(sl, pc[i]);
     }
     __syncthreads();
     const int nq = min(qlens[b], PLAID_NQ_MAX);
@@ -945,7 +964,7 @@ ivf_scores_kernel(const int32_t* __restrict__ counts, int pid_stride, const int3
         }
         __syncwarp();
         const int sidx = base + lane;
-        if (sidx < n) out[(size_t)b * pid_stride + sidx] = Tile::sum(s_max, lane, nq, empty_sum);
+        if (sidx < n) out[(size_t)b * pid_stride + slot0 + sidx] = Tile::sum(s_max, lane, nq, empty_sum);
         __syncwarp();
         base = nbase; beg = nbeg; end = nend; mine = nmine;
     }
@@ -1003,11 +1022,15 @@ extern "C" int plaid_filter_stage1_ivf(const int32_t* pids, const int32_t* count
     const int smax_bytes = s_is_f16 ? (IvfTile<__half>::kThreads / 32) * IvfTile<__half>::kBytes
                                     : (IvfTile<float>::kThreads / 32) * IvfTile<float>::kBytes;
     int max_bins = (smem_cap - smax_bytes) / 4 - 8;
+    if (g_ivf_range_slots > 0 && g_ivf_range_slots < max_bins) max_bins = g_ivf_range_slots;
     if (max_bins > pid_stride) max_bins = pid_stride;
     const int smem = ((max_bins + 1 + 3) & ~3) * 4 + smax_bytes;
+    // candidate lists longer than the bins (shards of millions of passages) are reduced in ranges of max_bins slots
+    const int nranges = (pid_stride + max_bins - 1) / max_bins;
+    PLAID_CHECK_ARG(nranges <= 65535, PLAID_ERR_UNSUPPORTED, "plaid_filter_stage1_ivf: pid_stride=%d too large", pid_stride);
     // the scan costs ~4 bytes per candidate token; the IVF route pays ~12 bytes per list entry visited
     const int max_visits = cap_p * 4;
-    ivf_survivors_kernel<<<B, 256, 0, st>>>(idx_bits, C, ivf_offsets, counts, pid_stride, max_bins, cap_s, max_visits,
+    ivf_survivors_kernel<<<B, 256, 0, st>>>(idx_bits, C, ivf_offsets, counts, pid_stride, pid_stride, cap_s, max_visits,
                                             ws_surv, ws_meta);
     PLAID_LAUNCH_OK("ivf_survivors_kernel");
     ivf_pairs_kernel<<<dim3(min((cap_s + 7) / 8, kPairsGridX), B), 256, 0, st>>>(ws_surv, cap_s, ws_meta, ivf_pids, ivf_offsets, bitmap,
@@ -1017,11 +1040,11 @@ extern "C" int plaid_filter_stage1_ivf(const int32_t* pids, const int32_t* count
     if (int rc = ensure_dynamic_smem((const void*)ivf_scores_kernel<float>, smem, configured_f32)) return rc;
     if (int rc = ensure_dynamic_smem((const void*)ivf_scores_kernel<__half>, smem, configured_f16)) return rc;
     if (s_is_f16)
-        ivf_scores_kernel<__half><<<B, IvfTile<__half>::kThreads, smem, st>>>(counts, pid_stride, ws_meta, ws_pair_slot, ws_pair_c, ws_sorted_c,
-                                                        cap_p, reinterpret_cast<const __half*>(S), C, qlens, out_scores);
+        ivf_scores_kernel<__half><<<dim3(B, nranges), IvfTile<__half>::kThreads, smem, st>>>(counts, pid_stride, ws_meta, ws_pair_slot, ws_pair_c, ws_sorted_c,
+                                                        cap_p, reinterpret_cast<const __half*>(S), C, qlens, out_scores, max_bins);
     else
-        ivf_scores_kernel<float><<<B, IvfTile<float>::kThreads, smem, st>>>(counts, pid_stride, ws_meta, ws_pair_slot, ws_pair_c, ws_sorted_c,
-                                                       cap_p, reinterpret_cast<const float*>(S), C, qlens, out_scores);
+        ivf_scores_kernel<float><<<dim3(B, nranges), IvfTile<float>::kThreads, smem, st>>>(counts, pid_stride, ws_meta, ws_pair_slot, ws_pair_c, ws_sorted_c,
+                                                       cap_p, reinterpret_cast<const float*>(S), C, qlens, out_scores, max_bins);
     PLAID_LAUNCH_OK("ivf_scores_kernel");
     // queries flagged for the scan (dense masks, oversized lists): the token-scan kernel, restricted to them
     if (s_is_f16)
@@ -1029,6 +1052,12 @@ extern "C" int plaid_filter_stage1_ivf(const int32_t* pids, const int32_t* count
                                        codes, offsets, out_scores, st, ws_meta + 2, kIvfMeta);
     return launch_approx_t<float>(pids, counts, B, pid_stride, reinterpret_cast<const float*>(S), qlens, idx_bits, C, codes,
                                   offsets, out_scores, st, ws_meta + 2, kIvfMeta);
+}
+
+extern "C" int plaid_set_ivf_range_slots(int slots) {
+    const int prev = plaid::g_ivf_range_slots;
+    plaid::g_ivf_range_slots = slots > 0 ? slots : 0;
+    return prev;
 }
 
 extern "C" int plaid_select_top(const int32_t* pids, const float* scores, const int32_t* counts, int B, int in_stride,

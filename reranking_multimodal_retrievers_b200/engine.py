@@ -109,7 +109,7 @@ class SearchEngine:
         self.query_maxlen = int(query_maxlen)
         # stage 1 of the filter through the inverted file (falls back to the token scan per query on the device)
         self.ivf_stage1 = bool(ivf_stage1)
-        self.cap_s, self.cap_p = 4096, 65536
+        self.cap_s, self.cap_p = 4096, None    # pair capacity: None = sized from the candidate stride (see _workspace)
         # storage precision of the centroid-score table S: fp16 (what the reference's GPU branch computes S in,
         # candidate_generation.py:52; half the bytes to write and to gather) or fp32 (the CPU branch's precision)
         assert s_dtype in (torch.float16, torch.float32)
@@ -184,6 +184,10 @@ class SearchEngine:
         cand_stride = max(ndocs, min(N, NQ_MAX * ncells * max(ix.max_ivf_len, 1)))
         cand_stride = ((cand_stride + 63) // 64) * 64
         fstride = max(cand_stride, ndocs)
+        # (slot, centroid) pairs of the inverted-file stage 1: about one per candidate on the bench workloads; twice the
+        # longest candidate list, so that shards of millions of passages stay on that route (a query that still
+        # overflows is flagged on the device and takes the code scan)
+        cap_p = self.cap_p or max(65536, min(1 << 20, 1 << (2 * cand_stride - 1).bit_length()))
         tok_stride = nd4 * (((max(ix.max_doclen, 1) + 31) // 32) * 32)   # passages are 32-token aligned in D
         tok_stride = ((tok_stride + 127) // 128) * 128
         e = lambda *shape, dtype: torch.empty(*shape, device=dev, dtype=dtype)
@@ -193,6 +197,7 @@ class SearchEngine:
         s2_msg = torch.zeros(2 * Bc * nd4 + Bc, device=dev, dtype=torch.int32)
         ws = dict(
             csplit=csplit, nlists=nlists, cand_stride=cand_stride, fstride=fstride, tok_stride=tok_stride, nd4=nd4,
+            cap_p=cap_p,
             Qb=e(Bc, Lq_pad, 128, dtype=torch.bfloat16), Qh=e(Bc, Lq_pad, 128, dtype=torch.float16),
             qlens=e(Bc, dtype=torch.int32), cqlens=e(Bc, dtype=torch.int32),
             S=e(Bc, C, NQ_MAX, dtype=self.s_dtype), idx_bits=e(Bc, C // 32, dtype=torch.int32),
@@ -200,8 +205,8 @@ class SearchEngine:
             cell_idx=e(Bc, NQ_MAX, nlists, ncells, dtype=torch.int32),
             cells=e(Bc, NQ_MAX, ncells, dtype=torch.int32),
             bitmap=e(Bc, (N + 31) // 32, dtype=torch.int32), wprefix=e(Bc, (N + 31) // 32, dtype=torch.int32),
-            surv=e(Bc, self.cap_s, dtype=torch.int32), pair_slot=e(Bc, self.cap_p, dtype=torch.int32),
-            pair_c=e(Bc, self.cap_p, dtype=torch.int32), sorted_c=e(Bc, 2 * self.cap_p, dtype=torch.int32),
+            surv=e(Bc, self.cap_s, dtype=torch.int32), pair_slot=e(Bc, cap_p, dtype=torch.int32),
+            pair_c=e(Bc, cap_p, dtype=torch.int32), sorted_c=e(Bc, 2 * cap_p, dtype=torch.int32),
             ivf_meta=e(Bc, 4, dtype=torch.int32),
             cand_pids=e(Bc, cand_stride, dtype=torch.int32), cand_counts=e(Bc, dtype=torch.int32),
             ws_scores=e(Bc, fstride, dtype=torch.float32), ws_keys=e(2, dtype=torch.int64),   # ABI leftover of select_top: must be non-null, never touched
@@ -305,7 +310,7 @@ class SearchEngine:
             call("filter_stage1", "plaid_filter_stage1_ivf", _p(ws["cand_pids"]), _p(ws["cand_counts"]), b, cs, _p(ws["S"]),
                  f16, _p(cq), _p(ws["idx_bits"]), C, _p(ix.codes), _p(ix.offsets), _p(ix.ivf_pids),
                  _p(ix.ivf_offsets), _p(ws["bitmap"]), _p(ws["wprefix"]), ix.num_passages, _p(ws["surv"]), self.cap_s,
-                 _p(ws["pair_slot"]), _p(ws["pair_c"]), _p(ws["sorted_c"]), self.cap_p, _p(ws["ivf_meta"]),
+                 _p(ws["pair_slot"]), _p(ws["pair_c"]), _p(ws["sorted_c"]), ws["cap_p"], _p(ws["ivf_meta"]),
                  _p(ws["ws_scores"]), st)
         else:
             call("filter_stage1", "plaid_approx_scores", _p(ws["cand_pids"]), _p(ws["cand_counts"]), b, cs, _p(ws["S"]), f16,

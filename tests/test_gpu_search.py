@@ -212,6 +212,40 @@ def test_stage1_ivf_route_equals_token_scan(pkg, golden, thr, cap_s, cap_p):
         assert int(used_scan.sum()) == B            # workspace too small: every query fell back to the scan
 
 
+@pytest.mark.parametrize("range_slots", [100, 1024])
+def test_stage1_ivf_route_in_slot_ranges(pkg, golden, range_slots):
+    """Candidate lists longer than the shared-memory bins of the inverted-file stage 1 (shards of millions of passages)
+    are sorted and reduced in slot ranges; forced here on the small index through the test hook: same lists, same bits."""
+    from reranking_multimodal_retrievers_b200 import _lib
+    from reranking_multimodal_retrievers_b200.engine import SearchEngine
+    from reranking_multimodal_retrievers_b200.index import DeviceIndex
+    g = golden
+    ix = DeviceIndex(golden_host_index(g))
+    Q = torch.from_numpy(g["Q"])
+    kw = dict(k=int(g["k"]), ncells=int(g["ncells"]), centroid_score_threshold=0.45, ndocs=int(g["ndocs"]),
+              remove_zero_rows=True, keep_taps=True)
+    a, b = SearchEngine(ix, ivf_stage1=True), SearchEngine(ix, ivf_stage1=False)
+    prev = _lib.lib().plaid_set_ivf_range_slots(range_slots)
+    try:
+        ra = a.search_batch(Q, **kw)
+        torch.cuda.synchronize()
+    finally:
+        _lib.lib().plaid_set_ivf_range_slots(prev)
+    rb = b.search_batch(Q, **kw)
+    a.check_flags(); b.check_flags()
+    B = Q.shape[0]
+    assert int(a._ws["cand_counts"][:B].max()) > 2 * range_slots or range_slots > 100   # several ranges per query
+    assert int(a._ws["ivf_meta"][:B, 2].sum()) == 0                                      # nobody took the scan
+    for x, y in zip(ra, rb):
+        assert torch.equal(x, y)
+    ta, tb = a.last_taps, b.last_taps
+    assert torch.equal(ta.stage1_counts[:B], tb.stage1_counts[:B])
+    for q in range(B):
+        n1 = int(ta.stage1_counts[q])
+        assert torch.equal(ta.stage1_pids[q, :n1], tb.stage1_pids[q, :n1])
+        assert torch.equal(ta.stage1_scores[q, :n1], tb.stage1_scores[q, :n1])
+
+
 def test_colbert_score_padded_vs_reference(pkg, golden):
     g = golden
     Q, D, mask = (torch.from_numpy(g[n]) for n in ("cs_Q", "cs_D", "cs_mask"))
