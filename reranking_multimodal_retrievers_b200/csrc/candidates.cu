@@ -74,58 +74,66 @@ mark_candidates_kernel(const int32_t* __restrict__ cells, int ncells, const int3
     }
 }
 
-// One CTA per query: scan the bitmap, emit set bits as ascending pids.
-// (512 threads per CTA measured the same as 1024 on cfg2.)
+// One CTA per query: scan the bitmap, emit set bits as ascending pids.  A warp takes 128 consecutive words per pass
+// (four coalesced loads, lane l the words l, 32 + l, 64 + l, 96 + l of the run) and every warp derives the warp-total
+// prefix itself from a double-buffered shared array: one barrier per 4096 words (a 10M-passage shard has 312 k
+// words per query; the first version -- one word per thread, four barriers per 1024 words -- spent 5 ms per 1024
+// queries there, most of it in barriers).
 __global__ void __launch_bounds__(1024)
 compact_candidates_kernel(const uint32_t* __restrict__ bitmap, int words, int32_t* __restrict__ cand_pids,
                           int32_t* __restrict__ cand_counts, int cand_stride, int* __restrict__ overflow,
                           int32_t* __restrict__ wprefix) {
-    __shared__ int s_warp[32];
-    __shared__ int s_base;
-    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    __shared__ int s_warp[2][32];
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
     const uint32_t* bm = bitmap + (size_t)b * words;
     int32_t* out = cand_pids + (size_t)b * cand_stride;
-    if (tid == 0) s_base = 0;
-    __syncthreads();
-    for (int w0 = 0; w0 < words; w0 += blockDim.x) {
-        const int w = w0 + tid;
-        uint32_t bits = (w < words) ? bm[w] : 0u;
-        const int cnt = __popc(bits);
-        int incl = cnt;  // inclusive warp scan
+    int32_t* wp = wprefix ? wprefix + (size_t)b * words : nullptr;
+    int base = 0, buf = 0;          // candidates before this pass: the same value in every thread
+    for (int w0 = 0; w0 < words; w0 += 128 * nw, buf ^= 1) {
+        const int wl = w0 + warp * 128 + lane;
+        uint32_t bits[4];
+        int before[4], run = 0;     // candidates of this warp's run before the lane's word j
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int v = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += v;
-        }
-        if (lane == 31) s_warp[warp] = incl;
-        __syncthreads();
-        if (warp == 0) {
-            int v = s_warp[lane];
-            int inc2 = v;
+        for (int j = 0; j < 4; j++) bits[j] = (wl + 32 * j < words) ? bm[wl + 32 * j] : 0u;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int cnt = __popc(bits[j]);
+            int incl = cnt;         // inclusive warp scan
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
-                const int u = __shfl_up_sync(0xffffffffu, inc2, o);
-                if (lane >= o) inc2 += u;
+                const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
             }
-            s_warp[lane] = inc2 - v;  // exclusive prefix of the warp totals
+            before[j] = run + incl - cnt;
+            run += __shfl_sync(0xffffffffu, incl, 31);
         }
+        if (lane == 0) s_warp[buf][warp] = run;
         __syncthreads();
-        int pos = s_base + s_warp[warp] + incl - cnt;
-        if (wprefix && w < words) wprefix[(size_t)b * words + w] = pos;   // candidates before word w = rank base of its pids
-        while (bits) {
-            const int bit = __ffs(bits) - 1;
-            bits &= bits - 1;
-            if (pos < cand_stride) out[pos] = (w << 5) + bit;
-            pos++;
+        int tot = lane < nw ? s_warp[buf][lane] : 0, inc2 = tot;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int u = __shfl_up_sync(0xffffffffu, inc2, o);
+            if (lane >= o) inc2 += u;
         }
-        __syncthreads();
-        if (tid == blockDim.x - 1) s_base = pos;  // last thread's end position = running total
-        __syncthreads();
+        const int warp_pos = base + __shfl_sync(0xffffffffu, inc2 - tot, warp);
+        base += __shfl_sync(0xffffffffu, inc2, 31);
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int w = wl + 32 * j;
+            int pos = warp_pos + before[j];
+            if (wp && w < words) wp[w] = pos;   // candidates before word w = rank base of its pids
+            uint32_t x = bits[j];
+            while (x) {
+                const int bit = __ffs(x) - 1;
+                x &= x - 1;
+                if (pos < cand_stride) out[pos] = (w << 5) + bit;
+                pos++;
+            }
+        }
     }
     if (tid == 0) {
-        const int total = s_base;
-        cand_counts[b] = min(total, cand_stride);
-        if (total > cand_stride && overflow) atomicExch(overflow, 1);
+        cand_counts[b] = min(base, cand_stride);
+        if (base > cand_stride && overflow) atomicExch(overflow, 1);
     }
 }
 

@@ -72,7 +72,7 @@ __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.w
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 struct CsBarriers {
-    uint64_t a_full;
+    uint64_t a_full, a_empty;
     uint64_t full[kCsStages];
     uint64_t empty[kCsStages];
     uint64_t tmem_full[2];
@@ -88,7 +88,7 @@ template <typename ST, int NC>
 __global__ void __launch_bounds__(kCsThreads, 1)
 centroid_scores_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_c,
                        const int32_t* __restrict__ qlens, int C, int Lq_pad, float threshold, int ncells, int csplit,
-                       ST* __restrict__ S, uint32_t* __restrict__ idx_bits, float* __restrict__ cell_val,
+                       int num_units, ST* __restrict__ S, uint32_t* __restrict__ idx_bits, float* __restrict__ cell_val,
                        int32_t* __restrict__ cell_idx, int* __restrict__ watchdog) {
     extern __shared__ uint8_t smem_raw[];
     // 1024-byte alignment: required by the 128B swizzle atoms the UMMA descriptors describe
@@ -100,15 +100,23 @@ centroid_scores_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
     __shared__ float s_cut[4][32];   // per (query, token): best NC-th value any of the column-part warps has seen
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int qgroup = blockIdx.x, split = blockIdx.y;
+    // Work unit = (group of 4 queries, centroid range), numbered group-major; the persistent CTAs split the unit
+    // sequence into contiguous, equally long runs (a run's units mostly share their queries, so the A operand is
+    // reloaded only when the group changes), which keeps all SMs busy whatever the number of query groups.
     const int tiles_total = (C + kCsN - 1) / kCsN;
     const int tiles_per_split = (tiles_total + csplit - 1) / csplit;
-    const int tile_begin = split * tiles_per_split;
-    const int tile_end = min(tiles_total, tile_begin + tiles_per_split);
-    const int ntiles = max(0, tile_end - tile_begin);
+    const int unit_begin = (int)((long long)blockIdx.x * num_units / gridDim.x);
+    const int unit_end = (int)((long long)(blockIdx.x + 1) * num_units / gridDim.x);
+    auto unit_tiles = [&](int u, int& qgroup, int& split, int& tile_begin) -> int {
+        qgroup = u / csplit;
+        split = u - qgroup * csplit;
+        tile_begin = split * tiles_per_split;
+        return max(0, min(tiles_total, tile_begin + tiles_per_split) - tile_begin);
+    };
 
     if (threadIdx.x == 0) {
         mbar_init(&bar->a_full, 1);
+        mbar_init(&bar->a_empty, 1);
         for (int s = 0; s < kCsStages; s++) { mbar_init(&bar->full[s], 1); mbar_init(&bar->empty[s], 1); }
         for (int a = 0; a < 2; a++) { mbar_init(&bar->tmem_full[a], 1); mbar_init(&bar->tmem_empty[a], 4 * kCsParts); }
         bar->abort_flag = 0;
@@ -129,56 +137,69 @@ centroid_scores_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
         if (lane == 0) {
             tma_prefetch_desc(&map_q);
             tma_prefetch_desc(&map_c);
-            mbar_expect_tx(&bar->a_full, kCsABytes);
-            for (int h = 0; h < 2; h++)
-                for (int q = 0; q < 4; q++)
-                    tma_load_2d(sA + h * (kCsM * 128) + q * (32 * 128), &map_q, &bar->a_full, h * 64,
-                                (qgroup * 4 + q) * Lq_pad);
-            for (int it = 0; it < ntiles; it++) {
-                const int s = it % kCsStages;
-                if (!mbar_wait(&bar->empty[s], ((it / kCsStages) & 1) ^ 1, watchdog)) break;
-                mbar_expect_tx(&bar->full[s], kCsBBytes);
-                uint8_t* dst = sB + s * kCsBBytes;
-                const int row = (tile_begin + it) * kCsN;
-                tma_load_2d(dst, &map_c, &bar->full[s], 0, row);
-                tma_load_2d(dst + kCsN * 128, &map_c, &bar->full[s], 64, row);
+            int cur_g = -1, a_loads = 0, it = 0;
+            bool ok = true;
+            for (int u = unit_begin; ok && u < unit_end; u++) {
+                int qgroup, split, tile_begin;
+                const int ntiles = unit_tiles(u, qgroup, split, tile_begin);
+                if (qgroup != cur_g) {
+                    // the MMAs that read the previous group's queries have retired (the issuer commits a_empty on the switch)
+                    if (a_loads > 0 && !mbar_wait(&bar->a_empty, (a_loads - 1) & 1, watchdog)) break;
+                    mbar_expect_tx(&bar->a_full, kCsABytes);
+                    for (int h = 0; h < 2; h++)
+                        for (int q = 0; q < 4; q++)
+                            tma_load_2d(sA + h * (kCsM * 128) + q * (32 * 128), &map_q, &bar->a_full, h * 64,
+                                        (qgroup * 4 + q) * Lq_pad);
+                    cur_g = qgroup;
+                    a_loads++;
+                }
+                for (int t = 0; t < ntiles; t++, it++) {
+                    const int s = it % kCsStages;
+                    if (!mbar_wait(&bar->empty[s], ((it / kCsStages) & 1) ^ 1, watchdog)) { ok = false; break; }
+                    mbar_expect_tx(&bar->full[s], kCsBBytes);
+                    uint8_t* dst = sB + s * kCsBBytes;
+                    const int row = (tile_begin + t) * kCsN;
+                    tma_load_2d(dst, &map_c, &bar->full[s], 0, row);
+                    tma_load_2d(dst + kCsN * 128, &map_c, &bar->full[s], 64, row);
+                }
             }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer (one thread) =====================
         if (lane == 0) {
             const uint32_t idesc = umma_idesc_bf16(kCsM, kCsN);
-            bool ok = mbar_wait(&bar->a_full, 0, watchdog);
-            for (int it = 0; ok && it < ntiles; it++) {
-                const int s = it % kCsStages, acc = it & 1;
-                if (!mbar_wait(&bar->tmem_empty[acc], ((it >> 1) & 1) ^ 1, watchdog)) break;
-                if (!mbar_wait(&bar->full[s], (it / kCsStages) & 1, watchdog)) break;
-                tc_fence_after();
-                const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB + s * kCsBBytes);
-#pragma unroll
-                for (int k = 0; k < 8; k++) {
-                    // k-step of 16 bf16 = 32 B inside a 128 B swizzle row; k >= 4 -> second k-half sub-tile
-                    const uint64_t da = umma_smem_desc_sw128(a0 + (k >> 2) * (kCsM * 128) + (k & 3) * 32);
-                    const uint64_t db = umma_smem_desc_sw128(b0 + (k >> 2) * (kCsN * 128) + (k & 3) * 32);
-                    umma_bf16(tmem_base + acc * kCsN, da, db, idesc, k > 0);
+            int cur_g = -1, a_loads = 0, it = 0;
+            bool ok = true;
+            for (int u = unit_begin; ok && u < unit_end; u++) {
+                int qgroup, split, tile_begin;
+                const int ntiles = unit_tiles(u, qgroup, split, tile_begin);
+                if (qgroup != cur_g) {
+                    if (a_loads > 0) umma_commit(&bar->a_empty);   // every MMA issued so far has read the old queries
+                    if (!mbar_wait(&bar->a_full, a_loads & 1, watchdog)) break;
+                    cur_g = qgroup;
+                    a_loads++;
                 }
-                umma_commit(&bar->empty[s]);        // smem stage reusable once these MMAs retire
-                umma_commit(&bar->tmem_full[acc]);  // accumulator ready for the epilogue
+                for (int t = 0; t < ntiles; t++, it++) {
+                    const int s = it % kCsStages, acc = it & 1;
+                    if (!mbar_wait(&bar->tmem_empty[acc], ((it >> 1) & 1) ^ 1, watchdog)) { ok = false; break; }
+                    if (!mbar_wait(&bar->full[s], (it / kCsStages) & 1, watchdog)) { ok = false; break; }
+                    tc_fence_after();
+                    const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB + s * kCsBBytes);
+#pragma unroll
+                    for (int k = 0; k < 8; k++) {
+                        // k-step of 16 bf16 = 32 B inside a 128 B swizzle row; k >= 4 -> second k-half sub-tile
+                        const uint64_t da = umma_smem_desc_sw128(a0 + (k >> 2) * (kCsM * 128) + (k & 3) * 32);
+                        const uint64_t db = umma_smem_desc_sw128(b0 + (k >> 2) * (kCsN * 128) + (k & 3) * 32);
+                        umma_bf16(tmem_base + acc * kCsN, da, db, idesc, k > 0);
+                    }
+                    umma_commit(&bar->empty[s]);        // smem stage reusable once these MMAs retire
+                    umma_commit(&bar->tmem_full[acc]);  // accumulator ready for the epilogue
+                }
             }
         }
     } else if (warp >= 4) {
         // ===================== epilogue =====================
         const int quad = warp & 3, part = (warp - 4) >> 2;
-        const int bq = qgroup * 4 + quad;
-        const int nq = min(qlens[bq], PLAID_NQ_MAX);
-        const bool tok_valid = lane < nq;
-        ST* Sq = S + (size_t)bq * C * PLAID_NQ_MAX + lane;
-        uint32_t* bits_q = idx_bits + (size_t)bq * (C >> 5);
-        float bv[NC];
-        int bi[NC];
-#pragma unroll
-        for (int p = 0; p < NC; p++) { bv[p] = -INFINITY; bi[p] = -1; }
-        float cut = -INFINITY;  // current ncells-th best value of this thread's own list
         const __half2 thr2 = __half2half2(__float2half_ru(threshold));
 #if PLAID_CS_BULK
         constexpr int kBlkBytes = 32 * PLAID_NQ_MAX * (int)sizeof(ST);          // one staged block: 32 centroids x 32 tokens
@@ -186,13 +207,43 @@ centroid_scores_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
         const uint32_t stage_base = smem_u32(sStage) + (uint32_t)(warp - 4) * kCsStagePerWarp;
         const uint32_t stage_sa = stage_base + lane * (uint32_t)sizeof(ST);
         const bool store = S != nullptr;     // S == NULL: only the top-ncells lists are wanted (index build: argmax)
+#endif
+        int cur_g = -1, it = 0;
+        bool ok = true;
+        for (int u = unit_begin; u < unit_end; u++) {
+        int qgroup, split, tile_begin;
+        const int ntiles = unit_tiles(u, qgroup, split, tile_begin);
+        if (qgroup != cur_g) {
+            // New queries: the bound the column-part warps share (s_cut) belongs to the old ones.  All 16 epilogue warps
+            // have left the old group before it is reset, and nobody reads it before the reset is done.  (A warp that gave
+            // up on a barrier wait still walks the units, so the named barrier always sees all of them.)
+            if (cur_g >= 0) {
+                asm volatile("bar.sync 1, %0;" :: "n"(4 * kCsParts * 32) : "memory");
+                if (part == 0) s_cut[quad][lane] = -INFINITY;
+                asm volatile("bar.sync 1, %0;" :: "n"(4 * kCsParts * 32) : "memory");
+            }
+            cur_g = qgroup;
+        }
+        const int bq = qgroup * 4 + quad;
+        const int nq = min(qlens[bq], PLAID_NQ_MAX);
+        const bool tok_valid = lane < nq;
+#if !PLAID_CS_BULK
+        ST* Sq = S + (size_t)bq * C * PLAID_NQ_MAX + lane;
+#endif
+        uint32_t* bits_q = idx_bits + (size_t)bq * (C >> 5);
+        float bv[NC];
+        int bi[NC];
+#pragma unroll
+        for (int p = 0; p < NC; p++) { bv[p] = -INFINITY; bi[p] = -1; }
+        float cut = -INFINITY;  // current ncells-th best value of this thread's own list
+#if PLAID_CS_BULK
         ST* Sblk = S + (size_t)bq * C * PLAID_NQ_MAX;
 #endif
-        for (int it = 0; it < ntiles; it++) {
+        for (int t = 0; ok && t < ntiles; t++, it++) {
             const int acc = it & 1;
-            if (!mbar_wait(&bar->tmem_full[acc], (it >> 1) & 1, watchdog)) break;
+            if (!mbar_wait(&bar->tmem_full[acc], (it >> 1) & 1, watchdog)) { ok = false; break; }
             tc_fence_after();
-            const int c_tile = (tile_begin + it) * kCsN + part * kCsPartCols;
+            const int c_tile = (tile_begin + t) * kCsN + part * kCsPartCols;
 #if PLAID_CS_BULK
             int staged = 0;                  // blocks staged and not yet handed to the copy engine
 #endif
@@ -358,9 +409,6 @@ centroid_scores_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar->tmem_empty[acc]);
         }
-#if PLAID_CS_BULK
-        if (store && lane == 0) bulk_wait_all();     // the staging area must outlive the copies that read it
-#endif
         // every (centroid range, column part) keeps its own partial list: slot = split*kCsParts + part
         const size_t base = (((size_t)bq * PLAID_NQ_MAX + lane) * (csplit * kCsParts) + (split * kCsParts + part)) * ncells;
 #pragma unroll
@@ -369,6 +417,10 @@ centroid_scores_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                 cell_val[base + p] = bv[p];
                 cell_idx[base + p] = tok_valid ? bi[p] : -1;
             }
+        }
+#if PLAID_CS_BULK
+        if (store && lane == 0) bulk_wait_all();     // the staging area must outlive the copies that read it
+#endif
     }
 
     tc_fence_before();
@@ -395,7 +447,8 @@ extern "C" int plaid_centroid_scores(const void* centroids_bf16, int C, const vo
     int rc;
     if ((rc = make_bf16_2d_map(&map_q, Qb_bf16, (uint64_t)B_pad * Lq_pad, kDim, 32)) != PLAID_OK) return rc;
     if ((rc = make_bf16_2d_map(&map_c, centroids_bf16, (uint64_t)C, kDim, kCsN)) != PLAID_OK) return rc;
-    dim3 grid(B_pad / 4, csplit);
+    const int num_units = (B_pad / 4) * csplit;          // (query group, centroid range), group-major
+    dim3 grid(min(num_units, sm_count()));
     cudaStream_t st = (cudaStream_t)stream;
 #define PLAID_CS_LAUNCH(ST_, NC_)                                                                                       \
     do {                                                                                                                \
@@ -403,7 +456,8 @@ extern "C" int plaid_centroid_scores(const void* centroids_bf16, int C, const vo
         if ((rc = ensure_dynamic_smem((const void*)centroid_scores_kernel<ST_, NC_>, kCsSmemBytes, configured)) != PLAID_OK) \
             return rc;                                                                                                  \
         centroid_scores_kernel<ST_, NC_><<<grid, kCsThreads, kCsSmemBytes, st>>>(                                       \
-            map_q, map_c, qlens, C, Lq_pad, threshold, ncells, csplit, reinterpret_cast<ST_*>(S), idx_bits, cell_val,   \
+            map_q, map_c, qlens, C, Lq_pad, threshold, ncells, csplit, num_units, reinterpret_cast<ST_*>(S), idx_bits,  \
+            cell_val,                                                                                                   \
             cell_idx, watchdog);                                                                                        \
     } while (0)
     const int nc = ncells <= 1 ? 1 : ncells <= 2 ? 2 : ncells <= 4 ? 4 : 8;

@@ -23,21 +23,6 @@
 #ifndef MS_FUSED_ATMEM
 #define MS_FUSED_ATMEM 1    // slim fused kernel: the query (A operand) lives in tensor memory, not in shared memory
 #endif
-#ifndef MS_EPI_WIDE
-#define MS_EPI_WIDE 1       // lean epilogue: 64 accumulator columns per tcgen05.ld round trip (two x32 loads, one wait)
-#endif
-#ifndef MS_FUSED_SH_FIRST
-#define MS_FUSED_SH_FIRST 1 // fused kernel: barriers at the start of shared memory, so their addresses are constants
-#endif
-#ifndef MS_EXP_DEC_DIV
-#define MS_EXP_DEC_DIV 1    // timing experiments only (wrong results): decode 1/DIV of every unit ...
-#endif
-#ifndef MS_EXP_EPI_CH
-#define MS_EXP_EPI_CH 4     // ... reduce only the first CH chunks of every tile
-#endif
-#ifndef MS_FUSED_SLIM_UT
-#define MS_FUSED_SLIM_UT 32 // slim fused kernel: rows of a tile built by one decompressor warp (16: eight warps per tile, two tiles under construction)
-#endif
 #ifndef MS_FUSED_CB
 #define MS_FUSED_CB 2      // fused kernel: steps (of 4 tokens) per centroid batch; two batches are in flight
 #endif
@@ -153,20 +138,6 @@ __device__ __forceinline__ float max32(const uint32_t (&r)[32], float seed) {
 #pragma unroll
     for (int j = 0; j < 32; j += 2) a = fmaxf(a, fmaxf(__uint_as_float(r[j]), __uint_as_float(r[j + 1])));
     return a;
-}
-
-// the same maximum as four independent chains of 3-input maxima (depth 6 instead of 16)
-__device__ __forceinline__ float max32_tree(const uint32_t (&r)[32], float seed) {
-    auto f = [&](int i) { return __uint_as_float(r[i]); };
-    float c[4];
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-        float x = fmaxf(fmaxf(f(8 * k), f(8 * k + 1)), f(8 * k + 2));
-        x = fmaxf(fmaxf(x, f(8 * k + 3)), f(8 * k + 4));
-        x = fmaxf(fmaxf(x, f(8 * k + 5)), f(8 * k + 6));
-        c[k] = fmaxf(x, f(8 * k + 7));
-    }
-    return fmaxf(fmaxf(fmaxf(c[0], c[1]), c[2]), fmaxf(c[3], seed));
 }
 
 // ===================== MMA issuer (one warp, one issuing lane) =====================
@@ -481,7 +452,7 @@ __device__ __forceinline__ float max16(const uint32_t (&r)[16], float seed) {
 // (n_epi = Lq_pad / 32), the accumulator is read in 16-column pieces with the load of the next piece in flight
 // while the current one is reduced, and passage boundaries are looked at once per 32 columns.  With the clamp
 // at 0 the running maximum simply starts at 0.
-template <bool ATMEM, bool WIDE>
+template <bool ATMEM>
 __device__ __forceinline__ void ms_epilogue_a1(const MsParams& p, MsShared* sh, uint32_t tmem_base, int item_begin,
                                                int item_end, int warp, int lane, int n_epi) {
     const int quad = warp;
@@ -536,45 +507,12 @@ __device__ __forceinline__ void ms_epilogue_a1(const MsParams& p, MsShared* sh, 
             tc_fence_after();
             if (live) {
                 const uint32_t tmem_acc = tmem_lane + acc * 128;
-                const int nch = min(MS_EXP_EPI_CH, (it.ntok - t * 128) >> 5);     // 32-column chunks of this tile that hold tokens
+                const int nch = min(4, (it.ntok - t * 128) >> 5);     // 32-column chunks of this tile that hold tokens
                 // A tcgen05.ld round trip costs ~200 cycles whatever its width, and this warp is the kernel's critical
                 // path when the decompressors are fast (ncu: 97 % busy with one round trip per 16 columns).  One
                 // 32-column load per passage chunk halves the round trips with the same 32 registers (deeper schemes
                 // -- four 16-column buffers, two 32-column ones -- push the whole kernel over its 96-register cap and
                 // spill in the decompressors: 4.5 ms instead of 2.9).
-                if constexpr (WIDE) {
-                // Two 32-column loads per round trip (64 registers): the load latency (~200 cycles whatever the width)
-                // is paid twice per tile instead of four times.  Passages are 32-token aligned, so the only place a
-                // boundary can fall inside the pair is between its halves.
-#pragma unroll
-                for (int hf = 0; hf < 2; hf++) {
-                    if (2 * hf < nch) {
-                        uint32_t r0[32], r1[32];
-                        const bool two = 2 * hf + 1 < nch;          // warp-uniform
-                        tmem_ld_32x32(tmem_acc + hf * 64, r0);
-                        if (two) tmem_ld_32x32(tmem_acc + hf * 64 + 32, r1);
-                        const int tk0 = t * 128 + hf * 64;
-                        while (tk0 == next_end && doc + 1 < it.nd) {   // this chunk opens the next passage
-                            flush(doc);
-                            doc++;
-                            const int nx = __shfl_sync(0xffffffffu, ends_reg, min(doc + 1, 31));
-                            next_end = doc + 1 < 32 ? nx : it.ntok;     // no lane 32: the 32nd passage ends with the item
-                        }
-                        tc_wait_ld32(r0);
-                        runmax = max32_tree(r0, runmax);
-                        if (two) {
-                            tc_wait_ld32(r1);                           // already complete: only pins the register uses
-                            while (tk0 + 32 == next_end && doc + 1 < it.nd) {
-                                flush(doc);
-                                doc++;
-                                const int nx = __shfl_sync(0xffffffffu, ends_reg, min(doc + 1, 31));
-                                next_end = doc + 1 < 32 ? nx : it.ntok;
-                            }
-                            runmax = max32_tree(r1, runmax);
-                        }
-                    }
-                }
-                } else {
                 uint32_t r[32];
 #pragma unroll
                 for (int ch = 0; ch < 4; ch++) {
@@ -590,7 +528,6 @@ __device__ __forceinline__ void ms_epilogue_a1(const MsParams& p, MsShared* sh, 
                         tc_wait_ld32(r);
                         runmax = max32(r, runmax);
                     }
-                }
                 }
             }
             tc_fence_before();
@@ -614,7 +551,7 @@ __device__ __forceinline__ void ms_epilogue_a1(const MsParams& p, MsShared* sh, 
 template <int MODE>
 __global__ void __launch_bounds__(kMsThreads, 2)    // <= 128 registers: two CTAs fit an SM (see ms_launch)
 maxsim_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_d, const MsParams p) {
-    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int a_bytes = p.MT * 128 * kDim * 2;
     const int b_bytes = p.NT * kDim * 2;
@@ -686,7 +623,7 @@ maxsim_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
         ms_mma_issue<false>(p, sh, sA, sB, b_bytes, tmem_base, item_begin, item_end, lane);
     } else if (warp < 4) {
         if (lean) {
-            if (warp < n_epi) ms_epilogue_a1<false, false>(p, sh, tmem_base, item_begin, item_end, warp, lane, n_epi);
+            if (warp < n_epi) ms_epilogue_a1<false>(p, sh, tmem_base, item_begin, item_end, warp, lane, n_epi);
         } else {
             ms_epilogue<MODE>(p, sh, tmem_base, item_begin, item_end, warp, lane);
         }
@@ -722,42 +659,27 @@ template <int NBITS> constexpr bool kFusedAsyncStage = (NBITS <= 2);
 // SLIM (one m-tile and Lq_pad <= 96, i.e. at most three TMEM lane quadrants hold query rows): warps 0-2 epilogue,
 // warp 3 -- whose quadrant is empty -- issues the MMAs and loads the queries, 4-19 decompress: 640 threads, which
 // lifts the register cap from 80 to 96 per thread for the decompressors (they spill at 80).
-static constexpr int kFusedShBytes = 2048;           // MS_FUSED_SH_FIRST: MsShared's slot at the start of shared memory
 static constexpr int kFusedThreads = (6 + kFusedDecWarps) * 32;
 static constexpr int kFusedThreadsSlim = (4 + kFusedDecWarps) * 32;
 
 template <int NBITS, bool SLIM, int kFusedUnit, bool PRE>
 __global__ void __launch_bounds__(SLIM ? kFusedThreadsSlim : kFusedThreads, 1)
 maxsim_fused_kernel(const __grid_constant__ CUtensorMap map_q, const MsParams p) {
-    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     constexpr int PB = 16 * NBITS;                  // packed residual bytes per token
     constexpr bool kATmem = SLIM && (MS_FUSED_ATMEM != 0);     // the host sets p.a_tmem_col exactly for this layout
-    const int NT = SLIM ? 128 : p.NT;               // the slim layout exists for 128-token tiles only
+    // The slim layout exists for 128-token tiles only: with the tile shape a constant the decompressors' stage and
+    // barrier addresses need fewer registers (spills of the headline variant: 44 B stored / 108 B loaded per thread,
+    // two of the loads once per 32-token unit in the decompressor loop -> 4 B / 8 B, none in that loop; -3 % time).
+    const int NT = SLIM ? 128 : p.NT;
     const int a_bytes = kATmem ? 0 : p.MT * 128 * kDim * 2;   // A operand in TMEM: no shared-memory copy
     const int b_bytes = NT * kDim * 2;
-#if MS_FUSED_SH_FIRST
-    // The barriers come first: with the declared alignment the dynamic shared memory needs no run-time rounding, so
-    // every barrier address (and, in the slim layout, every stage address) is a constant the decompressors need not
-    // keep in -- or, at the register cap, reload from local memory into -- a register.
-    uint8_t* smem = smem_raw;
-    MsShared* sh = reinterpret_cast<MsShared*>(smem);
-    static_assert(sizeof(MsShared) <= kFusedShBytes, "MsShared outgrew its slot");
-    uint8_t* sA = smem + kFusedShBytes;
-    uint8_t* sB = sA + a_bytes;                     // [NS][2 k-halves][NT rows][128 B]
-    uint8_t* sLUT = sB + p.NS * b_bytes;            // fp16 weight table, 256 entries x 128 B (1024-aligned)
-    uint8_t* s_stage = sLUT + kLutBytes;            // [kFusedDecWarps][1 or 2 buffers][kFusedUnit tokens * PB]
-    if ((smem_u32(smem_raw) & 1023u) != 0u) {       // the swizzled tiles need the alignment the declaration asks for
-        if (threadIdx.x == 0 && p.watchdog != nullptr) atomicExch(p.watchdog, 2);
-        return;
-    }
-#else
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sA = smem;
     uint8_t* sB = smem + a_bytes;                   // [NS][2 k-halves][NT rows][128 B]
     uint8_t* sLUT = sB + p.NS * b_bytes;            // fp16 weight table, 256 entries x 128 B (1024-aligned)
     uint8_t* s_stage = sLUT + kLutBytes;            // [kFusedDecWarps][1 or 2 buffers][kFusedUnit tokens * PB]
     MsShared* sh = reinterpret_cast<MsShared*>(s_stage + kFusedDecWarps * (kFusedAsyncStage<NBITS> ? 2 : 1) * kFusedUnit * PB);
-#endif
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const bool lean = SLIM || (p.MT == 1 && NT == 128);      // see maxsim_kernel
@@ -802,7 +724,7 @@ maxsim_fused_kernel(const __grid_constant__ CUtensorMap map_q, const MsParams p)
         ms_mma_issue<kATmem>(p, sh, sA, sB, b_bytes, tmem_base, item_begin, item_end, lane, &map_q);
     } else if (warp < 4) {
         if (lean) {
-            if (warp < n_epi) ms_epilogue_a1<kATmem, SLIM && (MS_EPI_WIDE != 0)>(p, sh, tmem_base, item_begin, item_end, warp, lane, n_epi);
+            if (warp < n_epi) ms_epilogue_a1<kATmem>(p, sh, tmem_base, item_begin, item_end, warp, lane, n_epi);
         } else {
             ms_epilogue<0>(p, sh, tmem_base, item_begin, item_end, warp, lane);
         }
@@ -1010,7 +932,7 @@ maxsim_fused_kernel(const __grid_constant__ CUtensorMap map_q, const MsParams p)
                         __syncwarp();
                     }
 #pragma unroll 1
-                    for (int bt = 0; bt < NBATCH / MS_EXP_DEC_DIV; bt += 2) {    // two batches per trip: A = bt, B = bt + 1
+                    for (int bt = 0; bt < NBATCH; bt += 2) {    // two batches per trip: A = bt, B = bt + 1
                         load_cents(code, bt + 1, blo, bhi);
                         process(bt, valid, inv, stage_sa, tile_sa, alo, ahi);
                         if (bt + 2 < NBATCH) {
@@ -1088,8 +1010,8 @@ static int ms_launch_fused(const void* Qb, int q_rows, int nbits, MsParams& p, c
     if ((rc = make_bf16_2d_map(&map_q, Qb, (uint64_t)q_rows, kDim, 128)) != PLAID_OK) return rc;
     // as many B stages as shared memory allows; the decompressor groups share them in tile order
     const int stage_bufs = nbits <= 2 ? 2 : 1;       // kFusedAsyncStage
+    const int unit = p.NT == 64 ? 16 : 32;           // rows per decompressor warp (template parameter UT)
     const bool slim = p.MT == 1 && p.NT == 128 && p.Lq_pad <= 96;
-    const int unit = slim ? MS_FUSED_SLIM_UT : p.NT == 64 ? 16 : 32;   // rows per decompressor warp (template parameter UT)
 #if MS_FUSED_ATMEM
     if (slim) {                                      // A operand in tensor memory: 2 accumulators (256 columns) + 64 columns of A
         p.na_shift = 1;
@@ -1097,12 +1019,8 @@ static int ms_launch_fused(const void* Qb, int q_rows, int nbits, MsParams& p, c
         p.q_rows = Qb;
     }
 #endif
-#if MS_FUSED_SH_FIRST
-    const int fixed = kFusedShBytes + (p.a_tmem_col > 0 ? 0 : p.MT * 128 * kDim * 2) + kLutBytes + kFusedDecWarps * stage_bufs * unit * 16 * nbits;
-#else
     const int fixed = 1024 + (p.a_tmem_col > 0 ? 0 : p.MT * 128 * kDim * 2) + kLutBytes + kFusedDecWarps * stage_bufs * unit * 16 * nbits +
                       (int)sizeof(MsShared) + 64;
-#endif
     const int per_stage = p.NT * kDim * 2;
     p.NS = (227 * 1024 - fixed) / per_stage;
     if (p.NS > kMsMaxStages) p.NS = kMsMaxStages;
@@ -1110,7 +1028,7 @@ static int ms_launch_fused(const void* Qb, int q_rows, int nbits, MsParams& p, c
     const int smem = fixed + p.NS * per_stage;
     const bool pre = p.inv_norms != nullptr;
 #define PLAID_FUSED_FN2(NB, PRE_)                                                                       \
-    (slim ? (const void*)maxsim_fused_kernel<NB, true, MS_FUSED_SLIM_UT, PRE_>                                        \
+    (slim ? (const void*)maxsim_fused_kernel<NB, true, 32, PRE_>                                        \
           : unit == 16 ? (const void*)maxsim_fused_kernel<NB, false, 16, PRE_> : (const void*)maxsim_fused_kernel<NB, false, 32, PRE_>)
 #define PLAID_FUSED_FN(NB) (pre ? PLAID_FUSED_FN2(NB, true) : PLAID_FUSED_FN2(NB, false))
     const void* fn = nbits == 1 ? PLAID_FUSED_FN(1) : nbits == 2 ? PLAID_FUSED_FN(2) : nbits == 4 ? PLAID_FUSED_FN(4) : PLAID_FUSED_FN(8);

@@ -97,6 +97,36 @@ class _HostFeed:
         self.free[slot] = ev
 
 
+def pick_csplit(groups: int, tiles: int, sms: int = 148, unit_overhead: float = 8.0) -> int:
+    """Centroid ranges per group of 4 queries for plaid_centroid_scores.  Its persistent CTAs take contiguous, equally
+    long runs of the (group, range) units, so the kernel's time is that of the longest run: ceil(units / CTAs) units of
+    ceil(tiles / ranges) tiles each, plus a per-unit cost (partial top-ncells lists to write and merge, a refill of the
+    queries when the group changes).  That cost is measured, and large: on cfg2 (128 groups x 256 tiles) 8 ranges -- runs
+    of 7 units x 32 tiles = 224 tile times on paper instead of the 256 of one range with 20 idle SMs -- ran 6 % SLOWER
+    (1.07 vs 1.00 ms: the kernel is within reach of the HBM write rate with 128 SMs already), hence ~8 tile times per
+    unit.  Where whole waves are at stake it pays: 108 groups x 2048 tiles (second chunk of 1024 queries at C = 2^19)
+    take 4 ranges, 3 units per CTA, 1536 tile times instead of 2048."""
+    groups, tiles = max(groups, 1), max(tiles, 1)
+    best, best_cost = 1, None
+    for cs in range(1, min(tiles, 64) + 1):
+        units = groups * cs
+        run = -(-units // min(sms, units))
+        cost = run * (-(-tiles // cs) + unit_overhead)
+        if best_cost is None or cost < best_cost - 1e-9:
+            best, best_cost = cs, cost
+    return best
+
+
+_SM_COUNTS = {}
+
+
+def _sm_count(dev) -> int:
+    idx = torch.device(dev).index or 0
+    if idx not in _SM_COUNTS:
+        _SM_COUNTS[idx] = torch.cuda.get_device_properties(idx).multi_processor_count if torch.cuda.is_available() else 148
+    return _SM_COUNTS[idx]
+
+
 class SearchEngine:
     def __init__(self, index: DeviceIndex, s_budget_bytes: int | None = None, max_chunk: int = 512, fused: bool = True,
                  s_dtype: torch.dtype = torch.float16, ivf_stage1: bool = True, query_maxlen: int = NQ_MAX,
@@ -121,10 +151,11 @@ class SearchEngine:
         self.use_inv_norms = os.environ.get("PLAID_NO_INV_NORMS", "0") != "1" and getattr(index, "inv_norms", None) is not None
         if s_budget_bytes is None:
             # room for the centroid-score table of one query chunk: a quarter of what is free next to the index, at most
-            # 24 GB (a 10M-passage shard's 33 MB-per-query tables then come in chunks of 592 queries instead of 148:
-            # fewer launches and, when the shards exchange their stage lists, fewer synchronisation points)
+            # 40 GB (the 33 MB-per-query tables of a 2^19-centroid codebook: 1024 queries in ONE chunk when the shard
+            # leaves the room -- fewer launches and, when the shards exchange their stage lists, half the
+            # synchronisation points -- else chunks of 592)
             free = torch.cuda.mem_get_info(index.device)[0] if torch.cuda.is_available() else 24 << 30
-            s_budget_bytes = max(2 << 30, min(24 << 30, free // 4))
+            s_budget_bytes = max(2 << 30, min(40 << 30, free // 4))
         self.s_budget_bytes = int(s_budget_bytes)
         self.max_chunk = int(max_chunk)
         # Query chunks are independent: with streams > 1 chunk i runs on side stream i % streams with its own workspace,
@@ -148,6 +179,8 @@ class SearchEngine:
     def chunk_size(self, B: int) -> int:
         per_query = self.index.num_centroids * NQ_MAX * (2 if self.s_dtype == torch.float16 else 4)
         large = per_query >= (16 << 20)
+        if large and self.max_chunk >= 512 and ((B + 3) // 4) * 4 * per_query <= self.s_budget_bytes and B <= 2048:
+            return max(4, ((B + 3) // 4) * 4)      # the whole batch at once: the centroid kernel balances any number of groups
         bc = max(4, min(max(self.max_chunk, 592) if large and self.max_chunk >= 512 else self.max_chunk, self.s_budget_bytes // per_query))
         if large and B > bc:
             # Large codebooks (C >= 2^18): centroid scoring dominates the step and its throughput is queries x centroid
@@ -174,11 +207,7 @@ class SearchEngine:
         C, N = ix.num_centroids, ix.num_passages
         tiles = (C + 255) // 256
         groups = Bc // 4                                              # one CTA per 4 queries and centroid range
-        # centroid ranges per query group: as many as still fit the 148 SMs in ONE wave.  Measured (cfg4 shard,
-        # 44 groups): 3 ranges 9.7 ms, 4 ranges (176 CTAs, a second wave of 28) 14.3 ms, 6: 10.6, 10: 13.2 --
-        # every extra range re-streams the queries' accumulator setup and adds partial top-ncells lists to merge.
-        csplit = max(1, min(tiles, 32, 148 // max(groups, 1)))
-        csplit = int(os.environ.get("PLAID_CSPLIT", csplit))
+        csplit = int(os.environ.get("PLAID_CSPLIT", pick_csplit(groups, tiles, _sm_count(dev))))
         nlists = CELL_LISTS_PER_RANGE * csplit
         nd4 = ndocs // 4
         cand_stride = max(ndocs, min(N, NQ_MAX * ncells * max(ix.max_ivf_len, 1)))
