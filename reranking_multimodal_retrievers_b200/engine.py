@@ -139,6 +139,8 @@ class SearchEngine:
         self.query_maxlen = int(query_maxlen)
         # stage 1 of the filter through the inverted file (falls back to the token scan per query on the device)
         self.ivf_stage1 = bool(ivf_stage1)
+        if os.environ.get("PLAID_IVF_RANGE_SLOTS"):   # development knob: slots per sort range of the inverted-file stage 1
+            _lib.lib().plaid_set_ivf_range_slots(int(os.environ["PLAID_IVF_RANGE_SLOTS"]))
         self.cap_s, self.cap_p = 4096, None    # pair capacity: None = sized from the candidate stride (see _workspace)
         # storage precision of the centroid-score table S: fp16 (what the reference's GPU branch computes S in,
         # candidate_generation.py:52; half the bytes to write and to gather) or fp32 (the CPU branch's precision)

@@ -157,6 +157,17 @@ def test_select_top_order_and_ties(P):
             op, os_ = ops.select_top(pids, scores, keep)
             rp, rs = po.select_top(pids, scores, keep)
             assert torch.equal(op.cpu(), rp) and torch.equal(os_.cpu(), rs), (levels, keep)
+    # lists of a multi-million-passage shard (>= 32768 keys: warp-aggregated histogram updates): most keys carry the
+    # "no surviving centroid" score of stage 1, a few thousand something better
+    n = 150000
+    scores = torch.full((n,), -9999.0 * 32)
+    live = torch.randperm(n, generator=g)[:6000]
+    scores[live] = torch.randint(0, 500, (6000,), generator=g).float() * 0.125 - 20.0
+    pids = torch.randperm(1 << 22, generator=g)[:n].to(torch.int32)
+    for keep in (1024, 4096, 8192):
+        op, os_ = ops.select_top(pids, scores, keep)
+        rp, rs = po.select_top(pids, scores, keep)
+        assert torch.equal(op.cpu(), rp) and torch.equal(os_.cpu(), rs), keep
 
 
 def test_segmented_maxsim_and_lookup(P, golden):
