@@ -56,6 +56,23 @@ def load_peaks():
     return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source="fallback")
 
 
+def write_only_peak(dev, nbytes=4 << 30, reps=5):
+    """GB/s of a write-only stream (torch fill of `nbytes`), CUDA events, best of `reps`."""
+    import torch
+    x = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    best = 0.0
+    for i in range(reps + 2):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        x.zero_()
+        e1.record()
+        torch.cuda.synchronize()
+        if i >= 2:
+            best = max(best, nbytes / (e0.elapsed_time(e1) * 1e-3) / 1e9)
+    del x
+    return best
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -305,6 +322,8 @@ def bench_cfg4(args, rank, world, dev, peaks, steps=4, warmup=2):
         kx = {}
         for stage, a, b in ev_x:
             kx[stage] = kx.get(stage, 0.0) + a.elapsed_time(b) / steps
+        if os.environ.get("PLAID_BENCH_ALLRANKS"):          # development aid: every rank's stage times (rank skew at the exchanges)
+            print(f"[rank {rank}] exact: " + " ".join(f"{s_}={v:.3f}" for s_, v in kx.items()), file=sys.stderr, flush=True)
         exact = {"ms_per_step": ms_x, "queries_per_s": B / (ms_x * 1e-3), "doc_tokens_per_s": float(t2[1]) / (ms_x * 1e-3),
                  "e2e": {"ms_per_step": ms_x_api, "queries_per_s": B / (ms_x_api * 1e-3)},
                  "T2_tokens_per_query_all_shards": float(t2[0]) / B, "T3_tokens_per_query_all_shards": float(t2[1]) / B,
@@ -329,6 +348,8 @@ def bench_cfg4(args, rank, world, dev, peaks, steps=4, warmup=2):
     if "centroid_scores" in kernels:
         kernels["centroid_scores"].update(achieved_GBps=round(cs_bytes / (stage_ms["centroid_scores"] * 1e-3) / 1e9, 1),
                                           frac_hbm=round(cs_bytes / (stage_ms["centroid_scores"] * 1e-3) / 1e9 / peaks["hbm"], 4),
+                                          write_only_peak_GBps=round(peaks.get("write_only", 0.0), 1),
+                                          frac_write_only_peak=round(cs_bytes / (stage_ms["centroid_scores"] * 1e-3) / 1e9 / max(peaks.get("write_only", 0.0), 1.0), 4),
                                           note="replicated on every rank: the codebook is global and every shard's filter needs "
                                                "the whole score table of every query")
     return {
@@ -580,6 +601,7 @@ def main():
     from reranking_multimodal_retrievers_b200.engine import SearchEngine
     from reranking_multimodal_retrievers_b200.index import DeviceIndex
 
+    peaks["write_only"] = write_only_peak(dev)          # before the index takes its memory
     sx, Qdev = build_workload(w, rank, dev)
     index = DeviceIndex(sx, dev)
     index.pid_base = rank * w["N"]                      # this rank's shard of the N*world passage collection
@@ -745,6 +767,14 @@ def main():
                 if "note" in alg[stage]:
                     d["note"] = alg[stage]["note"]
             kernels[stage] = d
+        if "centroid_scores" in kernels:
+            # centroid_scores only WRITES (4.2 GB of table per step on cfg2); MEASURED_PEAKS' figure is a copy (read + write).
+            # A write-only stream has its own, lower ceiling: measured here with a device fill of 4 GB.
+            wp = peaks["write_only"]
+            kernels["centroid_scores"].update(
+                write_only_peak_GBps=round(wp, 1), frac_write_only_peak=round(kernels["centroid_scores"]["achieved_GBps"] / wp, 4),
+                note="write-only kernel: frac_hbm is against the copy (read+write) peak of MEASURED_PEAKS.json, "
+                     "frac_write_only_peak against a fill of 4 GB timed in this run")
         dom = max((s for s in kernels if s in alg), key=lambda s: kernels[s]["ms_per_step"])
         nl = kernels[dom]["launches_per_step"]
         per_launch_s = kernels[dom]["ms_per_step"] * 1e-3 / nl
