@@ -54,7 +54,7 @@ mark_candidates_kernel(const int32_t* __restrict__ cells, int ncells, const int3
                        const int64_t* __restrict__ ivf_offsets, int C, int N, int words,
                        uint32_t* __restrict__ bitmap) {
     const int b = blockIdx.y, lane = threadIdx.x & 31;
-    const int e = blockIdx.x * kMarkWarps + (threadIdx.x >> 5);
+    const int e = blockIdx.x * kMarkWarps + warp_index();
     if (e >= PLAID_NQ_MAX * ncells) return;
     const int32_t* qc = cells + (size_t)b * PLAID_NQ_MAX * ncells;
     const int c = qc[e];
@@ -84,7 +84,7 @@ compact_candidates_kernel(const uint32_t* __restrict__ bitmap, int words, int32_
                           int32_t* __restrict__ cand_counts, int cand_stride, int* __restrict__ overflow,
                           int32_t* __restrict__ wprefix) {
     __shared__ int s_warp[2][32];
-    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = warp_index(), nw = blockDim.x >> 5;
     const uint32_t* bm = bitmap + (size_t)b * words;
     int32_t* out = cand_pids + (size_t)b * cand_stride;
     int32_t* wp = wprefix ? wprefix + (size_t)b * words : nullptr;

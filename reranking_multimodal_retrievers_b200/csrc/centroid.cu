@@ -99,7 +99,7 @@ centroid_scores_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
     CsBarriers* bar = reinterpret_cast<CsBarriers*>(smem + kCsABytes + kCsStages * kCsBBytes + kCsStageBytes);
     __shared__ float s_cut[4][32];   // per (query, token): best NC-th value any of the column-part warps has seen
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = warp_index(), lane = threadIdx.x & 31;
     // Work unit = (group of 4 queries, centroid range), numbered group-major; the persistent CTAs split the unit
     // sequence into contiguous, equally long runs (a run's units mostly share their queries, so the A operand is
     // reloaded only when the group changes), which keeps all SMs busy whatever the number of query groups.

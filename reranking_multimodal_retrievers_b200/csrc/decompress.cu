@@ -47,7 +47,7 @@ __device__ __forceinline__ void decompress_passage(int64_t tok0, int len, const 
                                                    int C, const float* sW, uint8_t* s_stage, Emit emit) {
     constexpr int PB = 16 * NBITS;   // packed bytes per token
     constexpr int TB = 512 / PB;     // tokens per 512-byte warp batch
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int lane = threadIdx.x & 31, warp = warp_index(), nw = blockDim.x >> 5;
     const int h = lane & 15, half = lane >> 4;
     uint8_t* stage = s_stage + warp * 512;
     for (int t0 = warp * TB; t0 < len; t0 += nw * TB) {
@@ -166,7 +166,7 @@ decompress_normalize_f16_kernel(const int32_t* __restrict__ pids, const int32_t*
     if ((int)blockIdx.x >= n) return;
     lut_fill_f16<NBITS>(W, sLUT);
     __syncthreads();
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int lane = threadIdx.x & 31, warp = warp_index(), nw = blockDim.x >> 5;
     const int q = lane & 7, tsub = lane >> 3;            // quarter warp per token, lane q <- chunk q of both k-halves
     const uint32_t lut_sa = lut_lane_base<NBITS>(smem_u32(sLUT), lane);
     const uint32_t stage_sa = smem_u32(s_stage + warp * 512);
@@ -278,7 +278,7 @@ token_inv_norms_kernel(const uint8_t* __restrict__ residuals, const int32_t* __r
     constexpr int PB = 16 * NBITS, TB = 512 / PB;
     lut_fill_f16<NBITS>(W, sLUT);
     __syncthreads();
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int lane = threadIdx.x & 31, warp = warp_index(), nw = blockDim.x >> 5;
     const int q = lane & 7, tsub = lane >> 3;
     const uint32_t lut_sa = lut_lane_base<NBITS>(smem_u32(sLUT), lane);
     const uint32_t stage_sa = smem_u32(s_stage + warp * 512);
@@ -314,7 +314,7 @@ doc_token_offsets_kernel(const int32_t* __restrict__ pids, const int32_t* __rest
                          const int64_t* __restrict__ offsets, int align, int32_t* __restrict__ tok_offsets) {
     __shared__ int s_warp[8];
     __shared__ int s_base;
-    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = warp_index();
     const int n = min(counts[b], pid_stride);
     int32_t* out = tok_offsets + (size_t)b * (pid_stride + 1);
     if (tid == 0) s_base = 0;

@@ -76,7 +76,7 @@ approx_scores_kernel(const int32_t* __restrict__ pids, const int32_t* __restrict
     extern __shared__ __align__(16) uint32_t s_dyn[];
     float (*s_max)[33] = reinterpret_cast<float (*)[33]>(s_dyn);      // [kDocs][33]
     uint32_t* s_bits = s_dyn + kDocs * 33;                            // [C/32] (stage 1 only)
-    const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int b = blockIdx.y, lane = threadIdx.x & 31, warp = warp_index();
     const int n = min(counts[b], pid_stride);
     if ((int)blockIdx.x * kDocs >= n) return;  // whole CTA past the end of this query's list
     const ST* Sb = S + (size_t)b * C * PLAID_NQ_MAX + lane;
@@ -726,7 +726,7 @@ ivf_pairs_kernel(const int32_t* __restrict__ surv, int cap_s, int32_t* __restric
     const uint32_t* bm = bitmap + (size_t)b * words;
     const int32_t* wp = wprefix + (size_t)b * words;
     // one warp per surviving centroid, grid-strided so the grid need not cover the cap_s worst case
-    for (int si = blockIdx.x * wpb + (threadIdx.x >> 5); si < ns; si += gridDim.x * wpb) {
+    for (int si = blockIdx.x * wpb + warp_index(); si < ns; si += gridDim.x * wpb) {
         const int c = surv[(size_t)b * cap_s + si];
         const int64_t lo = ivf_offsets[c], hi = ivf_offsets[c + 1];
         for (int64_t i0 = lo; i0 < hi; i0 += 32) {       // warp-uniform trip count: one atomic per warp and pass
@@ -868,7 +868,7 @@ ivf_scores_kernel(const int32_t* __restrict__ counts, int pid_stride, const int3
     using Tile = IvfTile<ST>;
     constexpr int kScan = 512;
     extern __shared__ __align__(16) int s_bins[];          // [n + 1] then one tile per warp
-    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = warp_index(), nw = blockDim.x >> 5;
     const int32_t* m = meta + (size_t)b * kIvfMeta;
     if (m[2]) return;
     // A CTA sorts and reduces the candidate slots [slot0, slot0 + n) of its query: the whole list when it fits the

@@ -23,6 +23,9 @@
 #ifndef MS_FUSED_ATMEM
 #define MS_FUSED_ATMEM 1    // slim fused kernel: the query (A operand) lives in tensor memory, not in shared memory
 #endif
+#ifndef MS_UNIFORM_WARP
+#define MS_UNIFORM_WARP 1
+#endif
 #ifndef MS_FUSED_CB
 #define MS_FUSED_CB 2      // fused kernel: steps (of 4 tokens) per centroid batch; two batches are in flight
 #endif
@@ -562,7 +565,7 @@ maxsim_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
     // warps 0-3: epilogue (warp = TMEM lane quadrant); 4-5: idle; 6: TMA producer; 7: TMEM alloc + MMA issue.
     // The two single-thread roles sit on SM sub-partitions 2/3, away from the epilogue warps of the first
     // 64 query tokens (the common Lq = 64 case leaves quadrants 2/3 without live rows).
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = warp_index(), lane = threadIdx.x & 31;
     // the search pipeline's common shape gets the lean epilogue (ms_epilogue_a1), run by the Lq_pad/32 warps whose
     // TMEM lanes can hold query rows
     const bool lean = (MODE == 0) && p.MT == 1 && p.NT == 128;
@@ -681,7 +684,11 @@ maxsim_fused_kernel(const __grid_constant__ CUtensorMap map_q, const MsParams p)
     uint8_t* s_stage = sLUT + kLutBytes;            // [kFusedDecWarps][1 or 2 buffers][kFusedUnit tokens * PB]
     MsShared* sh = reinterpret_cast<MsShared*>(s_stage + kFusedDecWarps * (kFusedAsyncStage<NBITS> ? 2 : 1) * kFusedUnit * PB);
 
+#if MS_UNIFORM_WARP
+    const int warp = warp_index(), lane = threadIdx.x & 31;   // provably warp-uniform role branches (common.cuh)
+#else
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#endif
     const bool lean = SLIM || (p.MT == 1 && NT == 128);      // see maxsim_kernel
     const int n_epi = lean ? min(4, p.Lq_pad >> 5) : 4;
     const int item_begin = blockIdx.x * p.items_per_cta;

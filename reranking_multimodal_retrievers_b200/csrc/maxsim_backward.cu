@@ -44,7 +44,7 @@ maxsim_argmax_kernel(const __nv_bfloat16* __restrict__ Qb, const int32_t* __rest
     extern __shared__ __align__(16) uint8_t s_raw[];
     __nv_bfloat16* sD = reinterpret_cast<__nv_bfloat16*>(s_raw);                 // [Ld][kBwRow]
     __nv_bfloat16* sQ = sD + (((size_t)Ld * kBwRow + 7) & ~size_t(7));           // [kBwWarps][kDim]: the warp's query row (16-byte aligned)
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31, warp = warp_index();
     for (long long p = blockIdx.x; p < pr.pairs(); p += gridDim.x) {
         int q; long long d;
         pr.split(p, q, d);
@@ -92,7 +92,7 @@ maxsim_argmax_kernel(const __nv_bfloat16* __restrict__ Qb, const int32_t* __rest
 __global__ void __launch_bounds__(kBwWarps * 32)
 maxsim_dq_kernel(const int32_t* __restrict__ qlens, int Lq_pad, const __nv_bfloat16* __restrict__ D, int Ld, BwPairing pr,
                  const int32_t* __restrict__ idx, const float* __restrict__ grad, float* __restrict__ dQ) {
-    const int q = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int q = blockIdx.x, lane = threadIdx.x & 31, warp = warp_index();
     const int lq = min(qlens[q], Lq_pad);
     long long p0, p1, dstep;          // the pairs of q: p = p0 + j, passage d = d0 + j
     long long d0;
@@ -123,7 +123,7 @@ maxsim_dd_kernel(const __nv_bfloat16* __restrict__ Qb, const int32_t* __restrict
     extern __shared__ __align__(16) uint8_t s_raw[];
     float* sAcc = reinterpret_cast<float*>(s_raw);            // [Ld][kDim]
     const long long d = blockIdx.x;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31, warp = warp_index();
     float* out = dD + (size_t)d * Ld * kDim;
     if (USE_SMEM) {
         for (int i = threadIdx.x; i < Ld * kDim; i += blockDim.x) sAcc[i] = 0.0f;

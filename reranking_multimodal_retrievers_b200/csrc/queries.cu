@@ -14,7 +14,7 @@ __global__ void __launch_bounds__(256) prepare_queries_kernel(const float* __res
                                                               __half* __restrict__ Qh, int32_t* __restrict__ qlens) {
     extern __shared__ int s_flag[];  // [Lq] keep flags, then [Lq] destination rows
     int* s_dst = s_flag + Lq;
-    const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int b = blockIdx.x, lane = threadIdx.x & 31, warp = warp_index(), nw = blockDim.x >> 5;
     __nv_bfloat16* out = Qb + (size_t)b * Lq_pad * kDim;
     __half* outh = Qh ? Qh + (size_t)b * Lq_pad * kDim : nullptr;      // optional fp16 twin (MaxSim operand)
     if (b >= B) {
