@@ -251,6 +251,21 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32])
           "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
         : "r"(taddr) : "memory");
 }
+// TMEM -> registers, 16 lanes x 64 consecutive fp32 columns (16x256b, 8 repetitions of 8 columns): the 16 lanes start at
+// the lane of `taddr` (a multiple of 16 inside the warp's quadrant).  Thread t holds, for repetition j, r[4j], r[4j+1] =
+// (lane t/4, columns 8j + 2(t%4), +1) and r[4j+2], r[4j+3] = (lane t/4 + 8, same columns) -- the m16n8 accumulator
+// fragment.  Half the elements per thread of a 32-lane load of the same columns: four warps share 64 accumulator rows.
+__device__ __forceinline__ void tmem_ld_16x64(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.16x256b.x8.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+}
 // one column: thread i <- lane base+i (includes the wait); used by the rare column-at-a-time epilogue path
 __device__ __forceinline__ uint32_t tmem_ld_32x1(uint32_t taddr) {
     uint32_t r;

@@ -23,6 +23,25 @@
 #ifndef MS_FUSED_ATMEM
 #define MS_FUSED_ATMEM 1    // slim fused kernel: the query (A operand) lives in tensor memory, not in shared memory
 #endif
+#ifndef MS_DBG_SKIP_EPI
+#define MS_DBG_SKIP_EPI 0  // timing experiments only (wrong results): the lean epilogues skip their loads and maxima
+#endif
+#ifndef MS_DBG_SKIP_DEC
+#define MS_DBG_SKIP_DEC 0  // timing experiments only (wrong results): the decompressors skip the decoding of their units
+#endif
+#ifndef MS_SLIM_UT
+#define MS_SLIM_UT 32      // slim layout: rows of a tile built by one decompressor warp (32: four groups of 4 warps; 16: two groups of 8)
+#endif
+#ifndef MS_FUSED_Q16
+// Short queries (Lq_pad <= 64): four epilogue warps x 16 query rows, MMAs issued by the decompressor groups.  Correct
+// (the whole GPU suite passes with it) and measured 5 % SLOWER than the two-warp epilogue + MMA warp (2.35 vs 2.24 ms on
+// cfg2): timing experiments show the epilogue is not what bounds the kernel (skipping its loads and maxima changes
+// nothing), and the groups' leaders pay for the issue.  Kept as a build option.
+#define MS_FUSED_Q16 0
+#endif
+#ifndef MS_EPI_MODE
+#define MS_EPI_MODE 1      // lean epilogue: 0 = chain of maxima, 1 = tree of 3-input maxima, 2 = tree + two 32-column loads per wait
+#endif
 #ifndef MS_UNIFORM_WARP
 #define MS_UNIFORM_WARP 1
 #endif
@@ -119,8 +138,18 @@ struct MsShared {
     uint64_t tmem_full[4];
     uint64_t tmem_empty[4];
     uint32_t tmem_base;
+    int issue_seq;               // Q16: sequence number of the next tile whose MMAs may be issued (in-order issue token)
     float part[2][4][kMsGD];
 };
+
+__device__ __forceinline__ int lds_acquire_s32(const int* p) {
+    int v;
+    asm volatile("ld.acquire.cta.shared.s32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_release_s32(int* p, int v) {
+    asm volatile("st.release.cta.shared.s32 [%0], %1;" :: "r"(smem_u32(p)), "r"(v) : "memory");
+}
 
 // Barrier over the 128 epilogue threads (warps 0-3) that also ORs a predicate, so that a watchdog
 // abort seen by one warp stops all four at the same work item (a lone early exit would strand the
@@ -428,6 +457,20 @@ __device__ __forceinline__ void ms_epilogue(const MsParams& p, MsShared* sh, uin
     }
 }
 
+// max(seed, 32 values) as a four-level tree of 3-input maxima (FMNMX3): the chain of max32 is 16 dependent
+// instructions deep, and the lean epilogue's warps are the critical path of the fused kernel (ncu: the decompressors
+// spend 21 % of their samples waiting for a free stage, the MMA warp 38 % waiting for a drained accumulator).
+__device__ __forceinline__ float max32_tree(const uint32_t (&r)[32], float seed) {
+    auto f = [&](int i) { return __uint_as_float(r[i]); };
+    auto m3 = [](float a, float b, float c) { return fmaxf(fmaxf(a, b), c); };
+    float t[11];
+#pragma unroll
+    for (int i = 0; i < 10; i++) t[i] = m3(f(3 * i), f(3 * i + 1), f(3 * i + 2));
+    t[10] = m3(f(30), f(31), seed);
+    const float u0 = m3(t[0], t[1], t[2]), u1 = m3(t[3], t[4], t[5]), u2 = m3(t[6], t[7], t[8]), u3 = fmaxf(t[9], t[10]);
+    return fmaxf(m3(u0, u1, u2), u3);
+}
+
 // Barrier over the first `nthreads` epilogue threads (whole warps), ORing a predicate like epi_bar_or.
 __device__ __forceinline__ bool epi_bar_or_n(bool pred, int nthreads) {
     uint32_t r;
@@ -508,7 +551,7 @@ __device__ __forceinline__ void ms_epilogue_a1(const MsParams& p, MsShared* sh, 
             const int acc = it_tile & ((1 << p.na_shift) - 1);
             if (!mbar_wait(&sh->tmem_full[acc], (it_tile >> p.na_shift) & 1, p.watchdog)) { ok = false; break; }
             tc_fence_after();
-            if (live) {
+            if (live && !MS_DBG_SKIP_EPI) {
                 const uint32_t tmem_acc = tmem_lane + acc * 128;
                 const int nch = min(4, (it.ntok - t * 128) >> 5);     // 32-column chunks of this tile that hold tokens
                 // A tcgen05.ld round trip costs ~200 cycles whatever its width, and this warp is the kernel's critical
@@ -516,6 +559,33 @@ __device__ __forceinline__ void ms_epilogue_a1(const MsParams& p, MsShared* sh, 
                 // 32-column load per passage chunk halves the round trips with the same 32 registers (deeper schemes
                 // -- four 16-column buffers, two 32-column ones -- push the whole kernel over its 96-register cap and
                 // spill in the decompressors: 4.5 ms instead of 2.9).
+#if MS_EPI_MODE == 2
+                // two 32-column loads per round trip: the second chunk's columns arrive while the first are reduced
+                uint32_t ra[32], rb[32];
+                auto boundary = [&](int tk0) {
+                    while (tk0 == next_end && doc + 1 < it.nd) {       // this chunk opens the next passage
+                        flush(doc);
+                        doc++;
+                        const int nx = __shfl_sync(0xffffffffu, ends_reg, min(doc + 1, 31));
+                        next_end = doc + 1 < 32 ? nx : it.ntok;         // no lane 32: the 32nd passage ends with the item
+                    }
+                };
+#pragma unroll
+                for (int ch = 0; ch < 4; ch += 2) {
+                    if (ch < nch) {
+                        tmem_ld_32x32(tmem_acc + ch * 32, ra);
+                        if (ch + 1 < nch) tmem_ld_32x32(tmem_acc + (ch + 1) * 32, rb);
+                        boundary(t * 128 + ch * 32);
+                        tc_wait_ld32(ra);
+                        runmax = max32_tree(ra, runmax);
+                        if (ch + 1 < nch) {
+                            boundary(t * 128 + (ch + 1) * 32);
+                            tc_wait_ld32(rb);
+                            runmax = max32_tree(rb, runmax);
+                        }
+                    }
+                }
+#else
                 uint32_t r[32];
 #pragma unroll
                 for (int ch = 0; ch < 4; ch++) {
@@ -529,7 +599,125 @@ __device__ __forceinline__ void ms_epilogue_a1(const MsParams& p, MsShared* sh, 
                             next_end = doc + 1 < 32 ? nx : it.ntok;     // no lane 32: the 32nd passage ends with the item
                         }
                         tc_wait_ld32(r);
+#if MS_EPI_MODE == 1
+                        runmax = max32_tree(r, runmax);
+#else
                         runmax = max32(r, runmax);
+#endif
+                    }
+                }
+#endif
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sh->tmem_empty[acc]);
+        }
+        for (int d = doc; d < it.nd; d++) flush(d);     // the last passage, plus trailing empty ones
+        __syncwarp();
+        if (epi_bar_or_n(!ok, n_epi * 32)) ok = false;
+        const int te = threadIdx.x;
+        if (te < it.nd) {
+            float s = sh->part[parity][0][te];
+            for (int qd = 1; qd < n_epi; qd++) s += sh->part[parity][qd][te];
+            p.scores[it.out0 + te] = s;
+        }
+        parity ^= 1;
+    }
+}
+
+
+// ===================== epilogue for short queries (Lq_pad <= 64): four warps x 16 query rows =====================
+// With Lq = 64 only two TMEM lane quadrants hold query rows and their two warps, each reading 128 columns per tile, are
+// the fused kernel's critical path (ncu: ~94 % busy, the decompressors wait 21 % of their time for a free stage).  Here
+// the A operand puts query rows 16q..16q+15 on lanes 0..15 of quadrant q (lanes 16..31 carry no query row), so that
+// ALL FOUR warps own 16 accumulator rows, and a 16-lane load (tcgen05.ld.16x256b) hands a thread half the elements of
+// the 32-lane form: thread t holds rows 16q + t/4 and + 8 of the columns 8j + 2(t%4), +1.  Per passage: two running
+// maxima per thread, combined over the four threads that share the rows, then summed over the warp's 16 rows.
+template <bool ATMEM>
+__device__ __forceinline__ void ms_epilogue_q16(const MsParams& p, MsShared* sh, uint32_t tmem_base, int item_begin,
+                                                int item_end, int quad, int lane, int n_epi) {
+    const uint32_t tmem_lane = tmem_base + ((uint32_t)(quad * 32) << 16);
+    const int row_a = quad * 16 + (lane >> 2), row_b = row_a + 8;
+    int it_tile = 0, parity = 0, cur_q = -1;
+    bool ok = true;
+    for (int w = item_begin; ok && w < item_end; w++) {
+        const MsItem it = ms_item(p, w);
+        if (it.nd == 0) continue;
+        if (ATMEM && it.q != cur_q) {
+            // A operand in tensor memory: lane l < 16 of this quadrant <- query row 16 quad + l (64 columns = 128 fp16),
+            // lanes 16..31 <- zeros.  The MMAs of the previous query have completed: this warp consumed their last tile.
+            const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(p.q_rows) +
+                                                              ((size_t)it.q * p.Lq_pad + quad * 16 + (lane & 15)) * kDim);
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                uint32_t r[16];
+#pragma unroll
+                for (int v = 0; v < 4; v++) {
+                    uint4 x = make_uint4(0u, 0u, 0u, 0u);
+                    if (lane < 16) x = __ldg(src + c * 4 + v);
+                    r[4 * v] = x.x; r[4 * v + 1] = x.y; r[4 * v + 2] = x.z; r[4 * v + 3] = x.w;
+                }
+                tmem_st_32x16(tmem_lane + p.a_tmem_col + c * 16, r);
+            }
+            tc_wait_st();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sh->a_full);
+            cur_q = it.q;
+        }
+        const int lq = p.qlens[it.q];
+        const bool ok_a = row_a < lq, ok_b = row_b < lq;
+        const bool live = quad * 16 < lq;               // warp-uniform: some lane holds a real query token
+        float* part = sh->part[parity][quad];
+        int ends_reg = 0x7fffffff;                      // lane d+1 = end of passage d relative to the item's first token
+        if (lane <= it.nd) ends_reg = it.ends[lane] - it.ends[0];
+        int doc = 0;
+        int next_end = __shfl_sync(0xffffffffu, ends_reg, 1);
+        float run_a = 0.0f, run_b = 0.0f;
+        auto flush = [&](int d) {
+            float va = ok_a ? run_a : 0.0f, vb = ok_b ? run_b : 0.0f;
+            run_a = run_b = 0.0f;
+            va = fmaxf(va, __shfl_xor_sync(0xffffffffu, va, 1));
+            vb = fmaxf(vb, __shfl_xor_sync(0xffffffffu, vb, 1));
+            va = fmaxf(va, __shfl_xor_sync(0xffffffffu, va, 2));
+            vb = fmaxf(vb, __shfl_xor_sync(0xffffffffu, vb, 2));
+            float v = va + vb;                          // the same in the four threads of a row group
+#pragma unroll
+            for (int o = 4; o < 32; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0) part[d] = v;
+        };
+        auto boundary = [&](int tk0) {
+            while (tk0 == next_end && doc + 1 < it.nd) {       // this chunk opens the next passage
+                flush(doc);
+                doc++;
+                const int nx = __shfl_sync(0xffffffffu, ends_reg, min(doc + 1, 31));
+                next_end = doc + 1 < 32 ? nx : it.ntok;         // no lane 32: the 32nd passage ends with the item
+            }
+        };
+        const int ntiles = (it.ntok + 127) >> 7;
+        for (int t = 0; t < ntiles; t++, it_tile++) {
+            const int acc = it_tile & ((1 << p.na_shift) - 1);
+            if (!mbar_wait(&sh->tmem_full[acc], (it_tile >> p.na_shift) & 1, p.watchdog)) { ok = false; break; }
+            tc_fence_after();
+            if (live && !MS_DBG_SKIP_EPI) {
+                const uint32_t tmem_acc = tmem_lane + acc * 128;
+                const int nch = min(4, (it.ntok - t * 128) >> 5);     // 32-column chunks of this tile that hold tokens
+                uint32_t r[32];
+                auto f = [&](int i) { return __uint_as_float(r[i]); };
+                auto m3 = [](float a, float b, float c) { return fmaxf(fmaxf(a, b), c); };
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    if (2 * h < nch) {
+                        tmem_ld_16x64(tmem_acc + h * 64, r);       // chunks 2h and 2h + 1 (the second may hold no tokens)
+                        boundary(t * 128 + 2 * h * 32);
+                        tc_wait_ld32(r);
+                        run_a = m3(m3(f(0), f(1), f(4)), m3(f(5), f(8), f(9)), m3(f(12), f(13), run_a));
+                        run_b = m3(m3(f(2), f(3), f(6)), m3(f(7), f(10), f(11)), m3(f(14), f(15), run_b));
+                        if (2 * h + 1 < nch) {
+                            boundary(t * 128 + (2 * h + 1) * 32);
+                            run_a = m3(m3(f(16), f(17), f(20)), m3(f(21), f(24), f(25)), m3(f(28), f(29), run_a));
+                            run_b = m3(m3(f(18), f(19), f(22)), m3(f(23), f(26), f(27)), m3(f(30), f(31), run_b));
+                        }
                     }
                 }
             }
@@ -550,10 +738,10 @@ __device__ __forceinline__ void ms_epilogue_a1(const MsParams& p, MsShared* sh, 
     }
 }
 
-
 template <int MODE>
 __global__ void __launch_bounds__(kMsThreads, 2)    // <= 128 registers: two CTAs fit an SM (see ms_launch)
-maxsim_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_d, const MsParams p) {
+maxsim_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_d,
+              const __grid_constant__ CUtensorMap map_q16, const MsParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int a_bytes = p.MT * 128 * kDim * 2;
@@ -569,7 +757,10 @@ maxsim_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
     // the search pipeline's common shape gets the lean epilogue (ms_epilogue_a1), run by the Lq_pad/32 warps whose
     // TMEM lanes can hold query rows
     const bool lean = (MODE == 0) && p.MT == 1 && p.NT == 128;
-    const int n_epi = lean ? min(4, p.Lq_pad >> 5) : 4;
+    // short queries (Lq_pad <= 64): 16 query rows per TMEM lane quadrant, four epilogue warps (ms_epilogue_q16); the
+    // A tile is loaded as 16-row boxes onto shared-memory rows 32q..32q+15 (the rows in between are never read back)
+    const bool q16 = lean && p.Lq_pad <= 64 && (MS_FUSED_Q16 != 0);   // same row order as the fused kernel: same bits
+    const int n_epi = q16 ? (p.Lq_pad >> 4) : lean ? min(4, p.Lq_pad >> 5) : 4;
     const int item_begin = blockIdx.x * p.items_per_cta;
     const int item_end = min(p.num_items, item_begin + p.items_per_cta);
 
@@ -595,6 +786,7 @@ maxsim_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
         if (lane == 0) {
             tma_prefetch_desc(&map_q);
             tma_prefetch_desc(&map_d);
+            tma_prefetch_desc(&map_q16);
             int cur_q = -1, a_loads = 0, it_tile = 0;
             bool ok = true;
             for (int w = item_begin; ok && w < item_end; w++) {
@@ -602,11 +794,19 @@ maxsim_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
                 if (it.nd == 0) continue;
                 if (it.q != cur_q) {
                     if (a_loads > 0 && !mbar_wait(&sh->a_empty, (a_loads - 1) & 1, p.watchdog)) break;
-                    mbar_expect_tx(&sh->a_full, a_bytes);
-                    for (int m = 0; m < p.MT; m++)
-                        for (int h = 0; h < 2; h++)
-                            tma_load_2d(sA + (m * 2 + h) * (128 * 128), &map_q, &sh->a_full, h * 64,
-                                        it.q * p.Lq_pad + m * 128);
+                    if (q16) {
+                        mbar_expect_tx(&sh->a_full, n_epi * 2 * 16 * 128);
+                        for (int qd = 0; qd < n_epi; qd++)
+                            for (int h = 0; h < 2; h++)
+                                tma_load_2d(sA + h * (128 * 128) + qd * (32 * 128), &map_q16, &sh->a_full, h * 64,
+                                            it.q * p.Lq_pad + qd * 16);
+                    } else {
+                        mbar_expect_tx(&sh->a_full, a_bytes);
+                        for (int m = 0; m < p.MT; m++)
+                            for (int h = 0; h < 2; h++)
+                                tma_load_2d(sA + (m * 2 + h) * (128 * 128), &map_q, &sh->a_full, h * 64,
+                                            it.q * p.Lq_pad + m * 128);
+                    }
                     cur_q = it.q;
                     a_loads++;
                 }
@@ -625,7 +825,9 @@ maxsim_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
     } else if (warp == 7) {
         ms_mma_issue<false>(p, sh, sA, sB, b_bytes, tmem_base, item_begin, item_end, lane);
     } else if (warp < 4) {
-        if (lean) {
+        if (q16) {
+            if (warp < n_epi) ms_epilogue_q16<false>(p, sh, tmem_base, item_begin, item_end, warp, lane, n_epi);
+        } else if (lean) {
             if (warp < n_epi) ms_epilogue_a1<false>(p, sh, tmem_base, item_begin, item_end, warp, lane, n_epi);
         } else {
             ms_epilogue<MODE>(p, sh, tmem_base, item_begin, item_end, warp, lane);
@@ -665,9 +867,15 @@ template <int NBITS> constexpr bool kFusedAsyncStage = (NBITS <= 2);
 static constexpr int kFusedThreads = (6 + kFusedDecWarps) * 32;
 static constexpr int kFusedThreadsSlim = (4 + kFusedDecWarps) * 32;
 
-template <int NBITS, bool SLIM, int kFusedUnit, bool PRE>
+// Q16 (slim layout, Lq_pad <= 64): warps 0-3 are ALL epilogue warps, 16 query rows each (ms_epilogue_q16), and there
+// is no MMA warp: the first warp of each decompressor group issues the MMAs of the tiles its group builds, right
+// after its own unit -- it waits for its three siblings' arrivals, for a drained accumulator and for the epilogue's A
+// rows, and issues.  Tiles may be issued slightly out of order between groups; every wait names the barrier phase of
+// its own tile, and a group's leader issues its tiles in order, so the chain of dependencies never closes.
+template <int NBITS, bool SLIM, int kFusedUnit, bool PRE, bool Q16 = false>
 __global__ void __launch_bounds__(SLIM ? kFusedThreadsSlim : kFusedThreads, 1)
 maxsim_fused_kernel(const __grid_constant__ CUtensorMap map_q, const MsParams p) {
+    static_assert(!Q16 || (SLIM && MS_FUSED_ATMEM != 0), "Q16 is a variant of the slim layout with A in TMEM");
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     constexpr int PB = 16 * NBITS;                  // packed residual bytes per token
@@ -690,7 +898,7 @@ maxsim_fused_kernel(const __grid_constant__ CUtensorMap map_q, const MsParams p)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #endif
     const bool lean = SLIM || (p.MT == 1 && NT == 128);      // see maxsim_kernel
-    const int n_epi = lean ? min(4, p.Lq_pad >> 5) : 4;
+    const int n_epi = Q16 ? (p.Lq_pad >> 4) : lean ? min(4, p.Lq_pad >> 5) : 4;
     const int item_begin = blockIdx.x * p.items_per_cta;
     const int item_end = min(p.num_items, item_begin + p.items_per_cta);
     const int wpt = NT / kFusedUnit;                // decompressor warps per tile
@@ -698,11 +906,12 @@ maxsim_fused_kernel(const __grid_constant__ CUtensorMap map_q, const MsParams p)
     if (threadIdx.x == 0) {
         mbar_init(&sh->a_full, p.a_tmem_col > 0 ? n_epi : 1);
         mbar_init(&sh->a_empty, 1);
+        sh->issue_seq = 0;
         for (int s = 0; s < p.NS; s++) { mbar_init(&sh->full[s], wpt); mbar_init(&sh->empty[s], 1); }
         for (int a = 0; a < 4; a++) { mbar_init(&sh->tmem_full[a], 1); mbar_init(&sh->tmem_empty[a], n_epi); }
         fence_mbar_init();
     }
-    constexpr int kMmaWarp = SLIM ? 3 : 5, kFirstDecWarp = SLIM ? 4 : 6;
+    constexpr int kMmaWarp = Q16 ? 0 : SLIM ? 3 : 5, kFirstDecWarp = SLIM ? 4 : 6;   // Q16: warp 0 only allocates TMEM
     if (warp == kMmaWarp) {
         tmem_alloc(&sh->tmem_base, 512);
         tmem_relinquish();
@@ -727,10 +936,12 @@ maxsim_fused_kernel(const __grid_constant__ CUtensorMap map_q, const MsParams p)
         tc_fence_after();
     }
 
-    if (SLIM && warp == kMmaWarp) {
+    if (SLIM && !Q16 && warp == kMmaWarp) {
         ms_mma_issue<kATmem>(p, sh, sA, sB, b_bytes, tmem_base, item_begin, item_end, lane, &map_q);
     } else if (warp < 4) {
-        if (lean) {
+        if constexpr (Q16) {
+            if (warp < n_epi) ms_epilogue_q16<true>(p, sh, tmem_base, item_begin, item_end, warp, lane, n_epi);
+        } else if (lean) {
             if (warp < n_epi) ms_epilogue_a1<kATmem>(p, sh, tmem_base, item_begin, item_end, warp, lane, n_epi);
         } else {
             ms_epilogue<0>(p, sh, tmem_base, item_begin, item_end, warp, lane);
@@ -789,6 +1000,11 @@ maxsim_fused_kernel(const __grid_constant__ CUtensorMap map_q, const MsParams p)
         const uint32_t slot_even = (uint32_t)(q ^ tsub) << 4, slot_odd = (uint32_t)(q ^ tsub ^ 4) << 4;
         const uint32_t khalf = (uint32_t)NT * 128;          // the second k-half of the tile
         int base_g = 0;       // (tiles of the earlier items) % G
+        // Q16: the group's first warp issues the MMAs of its group's tiles
+        int seq0 = 0;                        // tiles of the earlier items: the CTA's sequence number of this item's tile 0
+        int iss_q = -1, iss_loads = 0;       // queries with work so far (the A rows of query n complete phase n of a_full)
+        const uint32_t idesc = umma_idesc_f16(128, 128);
+        const uint64_t db_base = umma_smem_desc_sw128(smem_u32(sB));
         int st = group;       // stage of this group's next tile and the parity of that use of the stage
         uint32_t st_par = 0;
         while (st >= p.NS) { st -= p.NS; st_par ^= 1; }
@@ -796,6 +1012,7 @@ maxsim_fused_kernel(const __grid_constant__ CUtensorMap map_q, const MsParams p)
         for (int w = item_begin; ok && w < item_end; w++) {
             const MsItem it = ms_item(p, w);
             if (it.nd == 0) continue;
+            if (Q16 && it.q != iss_q) { iss_q = it.q; iss_loads++; }
             // passage descriptors of the item, one per lane (lane d <- passage d)
             int64_t my_off = 0;
             int my_len = 0;
@@ -930,7 +1147,7 @@ maxsim_fused_kernel(const __grid_constant__ CUtensorMap map_q, const MsParams p)
                         sts_v4u32_relaxed(dst + khalf, 0u, 0u, 0u, 0u);
                     }
                 }
-                if (valid > 0) {
+                if (valid > 0 && !MS_DBG_SKIP_DEC) {
                     if constexpr (!kFusedAsyncStage<NBITS>) {
 #pragma unroll
                         for (int v = 0; v < NPASS; v++)
@@ -954,9 +1171,46 @@ maxsim_fused_kernel(const __grid_constant__ CUtensorMap map_q, const MsParams p)
                 fence_proxy_async_smem();      // generic-proxy writes -> visible to the tensor core's async proxy
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&sh->full[st]);
+                if constexpr (Q16) {
+                    if (cit == 0) {            // issue this tile: all four units built, accumulator drained, A rows present
+                        const int seq = seq0 + t, acc = seq & 1;
+                        bool got = mbar_wait(&sh->full[st], st_par, p.watchdog);
+                        // Tiles are issued in sequence: a parity wait cannot tell "two uses behind" from "ready", and a
+                        // leader that ran ahead of the epilogue by a whole group period would otherwise overwrite a live
+                        // accumulator.  The token passes from the leader of tile seq - 1.
+                        if (got && lds_acquire_s32(&sh->issue_seq) != seq) {
+                            const uint64_t t0 = globaltimer_ns();
+                            while (lds_acquire_s32(&sh->issue_seq) != seq) {
+                                __nanosleep(20);
+                                if (globaltimer_ns() - t0 > 2000000000ull) {
+                                    if (p.watchdog) atomicExch(p.watchdog, 1);
+                                    got = false;
+                                    break;
+                                }
+                            }
+                        }
+                        got = got && mbar_wait(&sh->tmem_empty[acc], ((seq >> 1) & 1) ^ 1, p.watchdog);
+                        got = got && mbar_wait(&sh->a_full, (iss_loads - 1) & 1, p.watchdog);
+                        if (!got) { ok = false; break; }
+                        tc_fence_after();
+                        if (elect_one()) {
+                            const uint64_t db0 = db_base + (uint64_t)(st * (b_bytes >> 4));
+                            const uint32_t d_tmem = tmem_base + acc * 128;
+#pragma unroll
+                            for (int k = 0; k < 8; k++)
+                                umma_f16_ts(d_tmem, tmem_base + p.a_tmem_col + k * 8,
+                                            db0 + (uint64_t)((k >> 2) * ((128 * 128) >> 4) + (k & 3) * 2), idesc, k > 0);
+                            umma_commit(&sh->empty[st]);
+                            umma_commit(&sh->tmem_full[acc]);
+                            sts_release_s32(&sh->issue_seq, seq + 1);
+                        }
+                        __syncwarp();
+                    }
+                }
                 st += G;                       // the group's next tile
                 while (st >= p.NS) { st -= p.NS; st_par ^= 1; }
             }
+            seq0 += ntiles;
         }
     }
 
@@ -981,10 +1235,11 @@ static int ms_configure(MsParams& p, int Lq_pad) {
 }
 
 static int ms_launch(const void* Qb, int q_rows, const void* D, uint64_t d_rows, MsParams& p, cudaStream_t st) {
-    CUtensorMap map_q, map_d;
+    CUtensorMap map_q, map_d, map_q16;
     int rc;
     if ((rc = make_bf16_2d_map(&map_q, Qb, (uint64_t)q_rows, kDim, 128)) != PLAID_OK) return rc;
     if ((rc = make_bf16_2d_map(&map_d, D, d_rows, kDim, p.NT)) != PLAID_OK) return rc;
+    if ((rc = make_bf16_2d_map(&map_q16, Qb, (uint64_t)q_rows, kDim, 16)) != PLAID_OK) return rc;   // 16-row boxes (q16 epilogue)
     // One m-tile (Lq_pad <= 128): TWO CTAs per SM, each with 2 B stages, 2 accumulators (256 TMEM columns) and its
     // own TMA / MMA / epilogue warps.  With HBM-resident operands the epilogue warps of one CTA (only Lq_pad/32 of
     // the four hold query rows) cannot keep up with the stream; two independent pipelines double them.
@@ -1004,9 +1259,9 @@ static int ms_launch(const void* Qb, int q_rows, const void* D, uint64_t d_rows,
     if (grid > p.num_items) grid = p.num_items;
     p.items_per_cta = (p.num_items + grid - 1) / grid;
     grid = (p.num_items + p.items_per_cta - 1) / p.items_per_cta;
-    if (mode == 0) maxsim_kernel<0><<<grid, kMsThreads, smem, st>>>(map_q, map_d, p);
-    else if (mode == 1) maxsim_kernel<1><<<grid, kMsThreads, smem, st>>>(map_q, map_d, p);
-    else maxsim_kernel<2><<<grid, kMsThreads, smem, st>>>(map_q, map_d, p);
+    if (mode == 0) maxsim_kernel<0><<<grid, kMsThreads, smem, st>>>(map_q, map_d, map_q16, p);
+    else if (mode == 1) maxsim_kernel<1><<<grid, kMsThreads, smem, st>>>(map_q, map_d, map_q16, p);
+    else maxsim_kernel<2><<<grid, kMsThreads, smem, st>>>(map_q, map_d, map_q16, p);
     PLAID_LAUNCH_OK("maxsim_kernel");
     return PLAID_OK;
 }
@@ -1017,8 +1272,10 @@ static int ms_launch_fused(const void* Qb, int q_rows, int nbits, MsParams& p, c
     if ((rc = make_bf16_2d_map(&map_q, Qb, (uint64_t)q_rows, kDim, 128)) != PLAID_OK) return rc;
     // as many B stages as shared memory allows; the decompressor groups share them in tile order
     const int stage_bufs = nbits <= 2 ? 2 : 1;       // kFusedAsyncStage
-    const int unit = p.NT == 64 ? 16 : 32;           // rows per decompressor warp (template parameter UT)
+    const bool slim_shape = p.MT == 1 && p.NT == 128 && p.Lq_pad <= 96;
+    const int unit = (p.NT == 64 || (slim_shape && MS_SLIM_UT == 16)) ? 16 : 32;   // rows per decompressor warp (template parameter UT)
     const bool slim = p.MT == 1 && p.NT == 128 && p.Lq_pad <= 96;
+    const bool q16 = slim && p.Lq_pad <= 64 && (MS_FUSED_ATMEM != 0) && (MS_FUSED_Q16 != 0);   // four epilogue warps x 16 query rows
 #if MS_FUSED_ATMEM
     if (slim) {                                      // A operand in tensor memory: 2 accumulators (256 columns) + 64 columns of A
         p.na_shift = 1;
@@ -1035,14 +1292,15 @@ static int ms_launch_fused(const void* Qb, int q_rows, int nbits, MsParams& p, c
     const int smem = fixed + p.NS * per_stage;
     const bool pre = p.inv_norms != nullptr;
 #define PLAID_FUSED_FN2(NB, PRE_)                                                                       \
-    (slim ? (const void*)maxsim_fused_kernel<NB, true, 32, PRE_>                                        \
+    (q16 ? (const void*)maxsim_fused_kernel<NB, true, MS_SLIM_UT, PRE_, true>                                   \
+         : slim ? (const void*)maxsim_fused_kernel<NB, true, MS_SLIM_UT, PRE_>                                \
           : unit == 16 ? (const void*)maxsim_fused_kernel<NB, false, 16, PRE_> : (const void*)maxsim_fused_kernel<NB, false, 32, PRE_>)
 #define PLAID_FUSED_FN(NB) (pre ? PLAID_FUSED_FN2(NB, true) : PLAID_FUSED_FN2(NB, false))
     const void* fn = nbits == 1 ? PLAID_FUSED_FN(1) : nbits == 2 ? PLAID_FUSED_FN(2) : nbits == 4 ? PLAID_FUSED_FN(4) : PLAID_FUSED_FN(8);
 #undef PLAID_FUSED_FN
 #undef PLAID_FUSED_FN2
-    static int configured[6][9][kMaxDevices] = {{{0}}};
-    const int variant = (slim ? 1 : unit == 16 ? 2 : 0) + (pre ? 3 : 0);
+    static int configured[8][9][kMaxDevices] = {{{0}}};
+    const int variant = (q16 ? 3 : slim ? 1 : unit == 16 ? 2 : 0) + (pre ? 4 : 0);
     if ((rc = ensure_dynamic_smem(fn, smem, configured[variant][nbits])) != PLAID_OK) return rc;
     int grid = sm_count();
     if (grid > p.num_items) grid = p.num_items;
