@@ -727,7 +727,8 @@ def main():
     def build_line():
         ms_step = ms_total / args.steps
         C, nbits = index.num_centroids, index.nbits
-        chunks = (B + eng.chunk_size(B) - 1) // eng.chunk_size(B)
+        bc_dev = eng.chunk_size(B, resident=eng.exchange is None)      # the timed region feeds device-resident embeddings
+        chunks = (B + bc_dev - 1) // bc_dev
         T1, T2, T3, ncand = stats["T1"], stats["T2"], stats["T3"], stats["ncand"]
         T3p = stats["T3_padded"]
         # ALGORITHMIC bytes / flops per step, per stage
@@ -804,7 +805,7 @@ def main():
             "data": "synthetic", "queries_per_s": B / (ms_step * 1e-3),
             "config": {"workload": f"{args.workload}: {w['desc']}", "passages_per_gpu": w["N"], "tokens_per_gpu": index.num_embeddings,
                        "centroids": C, "queries_per_step": B, "parallelism": f"pid-range shards x{world}, all-gather top-k merge",
-                       "queries_per_chunk": eng.chunk_size(B), "chunk_streams": eng.streams,
+                       "queries_per_chunk": bc_dev, "queries_per_chunk_host_fed": eng.chunk_size(B), "chunk_streams": eng.streams,
                        "l2": "inputs larger than L2 (index + centroid-score table >> 126 MB), no explicit flush",
                        "candidates_per_query": ncand / B, "T1_tokens_per_query": T1 / B, "T2_tokens_per_query": T2 / B,
                        "T3_tokens_per_query": T3 / B, "T3_padded_tokens_per_query": T3p / B,

@@ -26,6 +26,9 @@
 #ifndef MS_DBG_SKIP_EPI
 #define MS_DBG_SKIP_EPI 0  // timing experiments only (wrong results): the lean epilogues skip their loads and maxima
 #endif
+#ifndef MS_DBG_SKIP_STS
+#define MS_DBG_SKIP_STS 0
+#endif
 #ifndef MS_DBG_SKIP_DEC
 #define MS_DBG_SKIP_DEC 0  // timing experiments only (wrong results): the decompressors skip the decoding of their units
 #endif
@@ -47,6 +50,14 @@
 #endif
 #ifndef MS_FUSED_CB
 #define MS_FUSED_CB 2      // fused kernel: steps (of 4 tokens) per centroid batch; two batches are in flight
+#endif
+
+#ifdef MS_DBG_TIMING
+// development aid: per (CTA, decompressor warp) cycles spent waiting for a free stage / in total (scripts/fused_wait_probe.py)
+__device__ unsigned long long g_ms_dbg[160 * 16 * 8];
+extern "C" int plaid_debug_read_fused_waits(unsigned long long* dst) {
+    return (int)cudaMemcpyFromSymbol(dst, g_ms_dbg, sizeof(g_ms_dbg));
+}
 #endif
 
 namespace plaid {
@@ -885,7 +896,11 @@ maxsim_fused_kernel(const __grid_constant__ CUtensorMap map_q, const MsParams p)
     // two of the loads once per 32-token unit in the decompressor loop -> 4 B / 8 B, none in that loop; -3 % time).
     const int NT = SLIM ? 128 : p.NT;
     const int a_bytes = kATmem ? 0 : p.MT * 128 * kDim * 2;   // A operand in TMEM: no shared-memory copy
+#ifdef MS_DBG_STAGE_STRIDE
+    const int b_bytes = SLIM ? MS_DBG_STAGE_STRIDE : NT * kDim * 2;   // timing experiment only: overlapping stages (wrong results)
+#else
     const int b_bytes = NT * kDim * 2;
+#endif
     uint8_t* sA = smem;
     uint8_t* sB = smem + a_bytes;                   // [NS][2 k-halves][NT rows][128 B]
     uint8_t* sLUT = sB + p.NS * b_bytes;            // fp16 weight table, 256 entries x 128 B (1024-aligned)
@@ -1009,6 +1024,10 @@ maxsim_fused_kernel(const __grid_constant__ CUtensorMap map_q, const MsParams p)
         uint32_t st_par = 0;
         while (st >= p.NS) { st -= p.NS; st_par ^= 1; }
         bool ok = true;
+#ifdef MS_DBG_TIMING
+        long long dbg_wait = 0, dbg_first = 0, dbg_long = 0, dbg_nlong = 0, dbg_n200 = 0, dbg_units = 0;
+        const long long dbg_start = clock64();
+#endif
         for (int w = item_begin; ok && w < item_end; w++) {
             const MsItem it = ms_item(p, w);
             if (it.nd == 0) continue;
@@ -1093,8 +1112,12 @@ maxsim_fused_kernel(const __grid_constant__ CUtensorMap map_q, const MsParams p)
                         token_scale_h16(v, ss, j < valid, olo, ohi);
                     }
                     const uint32_t dst = tile_sa + (((CB & 1) ? (step & 1) : (u & 1)) ? slot_odd : slot_even) + step * 512;
+#if MS_DBG_SKIP_STS     // timing experiment only: keep the arithmetic alive, store nothing
+                    if ((olo.x ^ olo.y ^ olo.z ^ olo.w ^ ohi.x ^ ohi.y ^ ohi.z ^ ohi.w) == 0x12345678u) sts_v4u32_relaxed(dst, olo.x, olo.y, olo.z, olo.w);
+#else
                     sts_v4u32_relaxed(dst, olo.x, olo.y, olo.z, olo.w);
                     sts_v4u32_relaxed(dst + khalf, ohi.x, ohi.y, ohi.z, ohi.w);
+#endif
                 }
             };
             int4 pres[NPASS];
@@ -1132,7 +1155,20 @@ maxsim_fused_kernel(const __grid_constant__ CUtensorMap map_q, const MsParams p)
                     fetch(ntok0, pvalid, stage0_sa + (buf ^ 1) * (UT * PB), pres, pcode, pinv);
                     ptile = t + G;
                 }
+#ifdef MS_DBG_TIMING
+                const long long dbg_t0 = clock64();
+#endif
                 if (!mbar_wait(&sh->empty[st], st_par ^ 1, p.watchdog)) { ok = false; break; }
+#ifdef MS_DBG_TIMING
+                {
+                    const long long dw_ = clock64() - dbg_t0;
+                    dbg_wait += dw_;
+                    if (t == first) dbg_first += dw_;                 // first unit of an item
+                    if (dw_ > 3000) { dbg_long += dw_; dbg_nlong++; }
+                    if (dw_ > 200) dbg_n200++;
+                    dbg_units++;
+                }
+#endif
                 if constexpr (kFusedAsyncStage<NBITS>) {        // this unit's rows have landed (the next unit's may not)
                     if (more) cp_async_wait<1>(); else cp_async_wait<0>();
                     __syncwarp();
@@ -1212,6 +1248,18 @@ maxsim_fused_kernel(const __grid_constant__ CUtensorMap map_q, const MsParams p)
             }
             seq0 += ntiles;
         }
+#ifdef MS_DBG_TIMING
+        if (lane == 0 && blockIdx.x < 160) {
+            unsigned long long* o = g_ms_dbg + (blockIdx.x * 16 + dw) * 8;
+            o[0] = (unsigned long long)dbg_wait;
+            o[1] = (unsigned long long)(clock64() - dbg_start);
+            o[2] = (unsigned long long)dbg_first;
+            o[3] = (unsigned long long)dbg_long;
+            o[4] = (unsigned long long)dbg_nlong;
+            o[5] = (unsigned long long)dbg_n200;
+            o[6] = (unsigned long long)dbg_units;
+        }
+#endif
     }
 
 done:
@@ -1285,7 +1333,11 @@ static int ms_launch_fused(const void* Qb, int q_rows, int nbits, MsParams& p, c
 #endif
     const int fixed = 1024 + (p.a_tmem_col > 0 ? 0 : p.MT * 128 * kDim * 2) + kLutBytes + kFusedDecWarps * stage_bufs * unit * 16 * nbits +
                       (int)sizeof(MsShared) + 64;
+#ifdef MS_DBG_STAGE_STRIDE
+    const int per_stage = slim ? MS_DBG_STAGE_STRIDE : p.NT * kDim * 2;
+#else
     const int per_stage = p.NT * kDim * 2;
+#endif
     p.NS = (227 * 1024 - fixed) / per_stage;
     if (p.NS > kMsMaxStages) p.NS = kMsMaxStages;
     PLAID_CHECK_ARG(p.NS >= 2, PLAID_ERR_UNSUPPORTED, "maxsim_fused: shared memory too small for Lq_pad=%d, nbits=%d", p.Lq_pad, nbits);
