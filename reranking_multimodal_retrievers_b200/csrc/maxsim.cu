@@ -23,6 +23,9 @@
 #ifndef MS_FUSED_ATMEM
 #define MS_FUSED_ATMEM 1    // slim fused kernel: the query (A operand) lives in tensor memory, not in shared memory
 #endif
+#ifndef MS_SKIP_PAD_BATCHES
+#define MS_SKIP_PAD_BATCHES 1
+#endif
 #ifndef MS_DBG_SKIP_EPI
 #define MS_DBG_SKIP_EPI 0  // timing experiments only (wrong results): the lean epilogues skip their loads and maxima
 #endif
@@ -1191,17 +1194,26 @@ maxsim_fused_kernel(const __grid_constant__ CUtensorMap map_q, const MsParams p)
                                 sts_v4u32(stage_sa + v * 512 + lane * 16, res[v].x, res[v].y, res[v].z, res[v].w);
                         __syncwarp();
                     }
+                    // A passage's last unit is half empty on average: only the pairs of batches that hold real rows are
+                    // decoded, the rows behind them are stored as zeros (what decoding them would have produced).
+                    const int nb_used = (MS_SKIP_PAD_BATCHES && UT == 32) ? min(NBATCH, ((valid + 4 * CB - 1) / (4 * CB) + 1) & ~1) : NBATCH;   // 16-row units: measured no gain
 #pragma unroll 1
-                    for (int bt = 0; bt < NBATCH; bt += 2) {    // two batches per trip: A = bt, B = bt + 1
+                    for (int bt = 0; bt < nb_used; bt += 2) {   // two batches per trip: A = bt, B = bt + 1
                         load_cents(code, bt + 1, blo, bhi);
                         process(bt, valid, inv, stage_sa, tile_sa, alo, ahi);
-                        if (bt + 2 < NBATCH) {
+                        if (bt + 2 < nb_used) {
                             load_cents(code, bt + 2, alo, ahi);
                         } else if (more && pvalid > 0) {        // batch 0 of the next unit (its codes arrived long ago)
                             load_cents(pcode, 0, alo, ahi);
                             a_ready = true;
                         }
                         process(bt + 1, valid, inv, stage_sa, tile_sa, blo, bhi);
+                    }
+#pragma unroll 1
+                    for (int step = nb_used * CB; step < UT / 4; step++) {
+                        const uint32_t dst = tile_sa + ((step & 1) ? slot_odd : slot_even) + step * 512;
+                        sts_v4u32_relaxed(dst, 0u, 0u, 0u, 0u);
+                        sts_v4u32_relaxed(dst + khalf, 0u, 0u, 0u, 0u);
                     }
                 }
                 fence_proxy_async_smem();      // generic-proxy writes -> visible to the tensor core's async proxy
