@@ -813,7 +813,11 @@ def main():
                                            "T3_padded adds the 32-token alignment rows of the MaxSim tiles and is not used in any rate",
                        "results_per_query": stats["found"] / B},
             "e2e": {"value": world * T3 / (e2e_ms * 1e-3), "unit": "doc-tokens/s", "queries_per_s": B / (e2e_ms * 1e-3),
-                    "ms_per_step": e2e_ms, "h2d_bytes_per_step": B * Lq * 128 * 4, "d2h_bytes_per_step": B * k * 8 + B * 4,
+                    "ms_per_step": e2e_ms,
+                    # several ranks: each copies its 1/N slice of the batch from the host, one NVLink all-gather replicates it
+                    "h2d_bytes_per_step": (-(-B // world) if world > 1 else B) * Lq * 128 * 4,
+                    "nvlink_allgather_bytes_per_step": (B * Lq * 128 * 4 if world > 1 else 0),
+                    "d2h_bytes_per_step": B * k * 8 + B * 4,
                     "call": "search_custom_collection(searcher, queries, Q_host, k, remove_zero_tensors=True) -> Ranking "
                             "(src/models/flmr/searching.py:43-63 -> CB/searcher.py:80-93); pinned host embeddings in, Ranking over "
                             "host arrays out, rows become Python tuples on access",

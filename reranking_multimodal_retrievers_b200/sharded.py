@@ -143,6 +143,7 @@ class ShardedSearcher:
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.config = searcher.config
         self._xchg = None
+        self._qsend = self._qfull = None
         ix = searcher.ranker.index
         searcher.ranker.engine.exchange = (StageExchange(ix.pid_base, ix.num_passages, ix.device, group)
                                            if mode == "exact" and self.world_size > 1 else None)
@@ -154,6 +155,27 @@ class ShardedSearcher:
             self._xchg.set_pid_base(ix.pid_base)
         return self._xchg
 
+    def _replicate_host_queries(self, Q: torch.Tensor) -> torch.Tensor:
+        """Host query embeddings -> the whole batch on this rank's device.  Every rank is handed the same batch; instead of
+        G copies of all of it over G PCIe links (33.5 MB per rank for 1024 FLMR queries, with nothing to overlap the first
+        chunk's share, and the links of a box share their host side), each rank copies its 1/G slice and ONE all-gather over
+        NVLink replicates it.  The search then runs on device-resident embeddings (one chunk)."""
+        B, Lq, dim = Q.shape
+        G, dev = self.world_size, self.searcher.ranker.index.device
+        per = -(-B // G)
+        if self._qfull is None or self._qfull.shape != (G * per, Lq, dim):
+            self._qsend = torch.empty(per, Lq, dim, device=dev, dtype=torch.float32)
+            self._qfull = torch.empty(G * per, Lq, dim, device=dev, dtype=torch.float32)
+        b0 = min(B, self.rank * per)
+        b1 = min(B, b0 + per)
+        if b1 > b0:
+            mine = Q[b0:b1].to(torch.float32).contiguous()
+            if not mine.is_pinned():
+                mine = mine.pin_memory()
+            self._qsend[: b1 - b0].copy_(mine, non_blocking=True)
+        dist.all_gather_into_tensor(self._qfull, self._qsend, group=self.group)
+        return self._qfull[:B]
+
     def search_batch(self, Q: torch.Tensor, k=100, remove_zero_tensors=False):
         """-> merged (pids, scores, counts) [B, k]; the returned tensors are reused by the next call."""
         if self.world_size == 1:
@@ -161,6 +183,8 @@ class ShardedSearcher:
         s = self.searcher
         s._defaults(k)
         c = s.config
+        if not Q.is_cuda and Q.shape[0] >= self.world_size:
+            Q = self._replicate_host_queries(Q)
         x = self._exchange(Q.shape[0], k)
         s.ranker.engine.search_batch(Q, k=k, ncells=c.ncells, centroid_score_threshold=c.centroid_score_threshold,
                                      ndocs=c.ndocs, remove_zero_rows=remove_zero_tensors, global_pids=False, out=x.views())

@@ -72,6 +72,20 @@ def test_fullsize_properties_and_oracle_sample(N, B):
         assert torch.equal(pids[b].cpu(), rp) and torch.equal(scores[b].cpu(), rs)
 
 
+def test_resident_batch_runs_as_one_chunk_and_matches_the_host_fed_chunks():
+    """Device-resident batches of up to 1024 queries are searched as ONE chunk, host-fed ones in 512-query chunks behind a
+    copy stream (engine.chunk_size): the two paths return the same lists bit for bit."""
+    k, B = 100, 640
+    sx, Q, gold, eng = _build(20_000, B, 64)
+    assert eng.chunk_size(B, resident=True) == B and eng.chunk_size(B) == 512
+    pd, sd, cd = eng.search_batch(Q, k=k)                       # one chunk of 640
+    eng.check_flags()
+    ph, sh, ch = eng.search_batch(Q.cpu().pin_memory(), k=k)    # 512 + 128, H2D one chunk ahead
+    eng.check_flags()
+    assert torch.equal(pd, ph) and torch.equal(sd, sh) and torch.equal(cd, ch)
+    assert float((pd[:, 0].cpu() == gold.cpu().to(torch.int32)).float().mean()) >= 0.99
+
+
 def test_fullsize_padded_rerank_linearity_and_permutation():
     """cfg5 shape (top-100 rerank, bf16 passage embeddings): properties of the padded MaxSim on a
     4096-passage slab -- permutation equivariance over passages, invariance to padding content,
