@@ -805,7 +805,10 @@ def main():
             "data": "synthetic", "queries_per_s": B / (ms_step * 1e-3),
             "config": {"workload": f"{args.workload}: {w['desc']}", "passages_per_gpu": w["N"], "tokens_per_gpu": index.num_embeddings,
                        "centroids": C, "queries_per_step": B, "parallelism": f"pid-range shards x{world}, all-gather top-k merge",
-                       "queries_per_chunk": bc_dev, "queries_per_chunk_host_fed": eng.chunk_size(B), "chunk_streams": eng.streams,
+                       "queries_per_chunk": bc_dev,
+                       "queries_per_chunk_host_fed": (bc_dev if (eng.host_piece and eng.exchange is None and bc_dev >= B and world == 1)
+                                                      else eng.chunk_size(B)),
+                       "host_fed_pcie_piece_queries": eng.host_piece if world == 1 else None, "chunk_streams": eng.streams,
                        "l2": "inputs larger than L2 (index + centroid-score table >> 126 MB), no explicit flush",
                        "candidates_per_query": ncand / B, "T1_tokens_per_query": T1 / B, "T2_tokens_per_query": T2 / B,
                        "T3_tokens_per_query": T3 / B, "T3_padded_tokens_per_query": T3p / B,

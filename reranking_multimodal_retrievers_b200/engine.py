@@ -170,6 +170,8 @@ class SearchEngine:
         self._ws_slots = {}
         self._ws_key = None
         self._copy_stream = None
+        self._qstage = None        # device staging buffer of a host-fed chunk (_run_chunk_host)
+        self.host_piece = 256      # queries per PCIe piece of a host-fed batch (0: whole chunks behind a double buffer)
         self._ws = None
         self.last_taps: StageTaps | None = None
         self.launch_count = 0      # kernels of libplaid_b200 launched so far (bench.py reports the delta)
@@ -201,9 +203,12 @@ class SearchEngine:
         bc = min(bc, ((B + 3) // 4) * 4)
         return max(4, (bc // 4) * 4)
 
-    def _workspace(self, Bc: int, Lq_pad: int, ncells: int, ndocs: int, k: int, slot: int = 0):
+    def _workspace(self, Bc: int, Lq_pad: int, ncells: int, ndocs: int, k: int, slot: int = 0, groups: int | None = None):
+        """groups: query groups (of 4) per plaid_centroid_scores launch when a chunk is scored in pieces (host-fed batches),
+        default the whole chunk -- it fixes the number of centroid ranges and with it the layout of the partial cell lists."""
         ix = self.index
-        key = (Bc, Lq_pad, ncells, ndocs, k)
+        groups = Bc // 4 if groups is None else int(groups)
+        key = (Bc, Lq_pad, ncells, ndocs, k, groups)
         if slot:
             hit = self._ws_slots.get(slot)
             if hit is not None and hit[0] == key:
@@ -213,7 +218,6 @@ class SearchEngine:
         dev = ix.device
         C, N = ix.num_centroids, ix.num_passages
         tiles = (C + 255) // 256
-        groups = Bc // 4                                              # one CTA per 4 queries and centroid range
         csplit = int(os.environ.get("PLAID_CSPLIT", pick_csplit(groups, tiles, _sm_count(dev))))
         nlists = CELL_LISTS_PER_RANGE * csplit
         nd4 = ndocs // 4
@@ -305,17 +309,37 @@ class SearchEngine:
     def stage_candidates(self, ws, Qc: torch.Tensor, Lq_pad: int, ncells: int, thr: float,
                          remove_zero_rows: bool, Bc: int):
         """a1-a4: query prep, centroid scoring (+ pruning mask, top-ncells), candidate pids."""
+        self.stage_scores(ws, Qc, 0, Bc, Lq_pad, ncells, thr, remove_zero_rows)
+        self.stage_candidate_pids(ws, Qc.shape[0], ncells)
+
+    def stage_scores(self, ws, Qc: torch.Tensor, row0: int, rows_pad: int, Lq_pad: int, ncells: int, thr: float,
+                     remove_zero_rows: bool):
+        """a1-a2, a4 for the workspace rows row0 .. row0 + rows_pad (a multiple of 4; Qc holds the real ones): query prep and
+        centroid scoring with its pruning mask and partial top-ncells lists.  A chunk may be scored in several pieces."""
         ix = self.index
         b, Lq, _ = Qc.shape
         st = _stream()
-        C, N = ix.num_centroids, ix.num_passages
-        wd, ovf = self._flag_ptrs()
+        C = ix.num_centroids
+        wd, _ = self._flag_ptrs()
         call = self._call
-        call("prepare", "plaid_prepare_queries", _p(Qc), b, Lq, int(remove_zero_rows), Bc, Lq_pad, _p(ws["Qb"]), _p(ws["Qh"]),
-             _p(ws["qlens"]), st)
-        cq = self._candidate_qlens(ws)
-        call("centroid_scores", "plaid_centroid_scores", _p(ix.centroids_bf16), C, _p(ws["Qb"]), _p(cq), Bc, Lq_pad, float(thr),
-             ncells, ws["csplit"], _p(ws["S"]), int(self.s_dtype == torch.float16), _p(ws["idx_bits"]), _p(ws["cell_val"]), _p(ws["cell_idx"]), wd, st)
+        r0, r1 = row0, row0 + rows_pad
+        call("prepare", "plaid_prepare_queries", _p(Qc), b, Lq, int(remove_zero_rows), rows_pad, Lq_pad, _p(ws["Qb"][r0:r1]),
+             _p(ws["Qh"][r0:r1]), _p(ws["qlens"][r0:r1]), st)
+        if self.query_maxlen < NQ_MAX:
+            torch.clamp(ws["qlens"][r0:r1], max=self.query_maxlen, out=ws["cqlens"][r0:r1])
+        cq = ws["qlens"] if self.query_maxlen >= NQ_MAX else ws["cqlens"]
+        call("centroid_scores", "plaid_centroid_scores", _p(ix.centroids_bf16), C, _p(ws["Qb"][r0:r1]), _p(cq[r0:r1]), rows_pad,
+             Lq_pad, float(thr), ncells, ws["csplit"], _p(ws["S"][r0:r1]), int(self.s_dtype == torch.float16),
+             _p(ws["idx_bits"][r0:r1]), _p(ws["cell_val"][r0:r1]), _p(ws["cell_idx"][r0:r1]), wd, st)
+
+    def stage_candidate_pids(self, ws, b: int, ncells: int):
+        """a3: merge of the partial cell lists, inverted-file union -> sorted unique candidate pids of the chunk's b queries."""
+        ix = self.index
+        st = _stream()
+        C, N = ix.num_centroids, ix.num_passages
+        _, ovf = self._flag_ptrs()
+        call = self._call
+        cq = self._candidate_qlens(ws, refresh=False)
         call("candidates", "plaid_candidates", _p(ws["cell_val"]), _p(ws["cell_idx"]), _p(cq), b, ncells, ws["nlists"],
              _p(ix.ivf_pids), _p(ix.ivf_offsets), C, N, _p(ws["cells"]), _p(ws["bitmap"]), _p(ws["cand_pids"]),
              _p(ws["cand_counts"]), ws["cand_stride"], ovf, _p(ws["wprefix"]), st)
@@ -388,6 +412,38 @@ class SearchEngine:
         self.stage_rank(ws, Qc.shape[0], Lq_pad, ndocs, k, Bc, out, out_stride)
         return ws
 
+    def _run_chunk_host(self, Qh: torch.Tensor, Lq_pad: int, ncells: int, thr: float, ndocs: int, k: int,
+                        remove_zero_rows: bool, Bc: int, piece: int, out=None, out_stride=None):
+        """One chunk fed from (pinned) host memory in pieces: the embeddings cross PCIe `piece` queries at a time on the copy
+        stream, query prep + centroid scoring run per piece as it lands (its launch splits the codebook into ranges, so a
+        256-query piece still fills the SMs), and everything behind them runs once on the whole chunk.  Only the first piece's
+        copy is exposed (8.4 MB instead of the 16.8 MB of a 512-query first chunk), and the batch is searched as ONE chunk."""
+        B, Lq, dim = Qh.shape
+        dev = self.index.device
+        ws = self._workspace(Bc, Lq_pad, ncells, ndocs, k, 0, groups=piece // 4)
+        if self._qstage is None or self._qstage.shape != (Bc, Lq, dim):
+            self._qstage = torch.empty(Bc, Lq, dim, device=dev, dtype=torch.float32)
+        main = torch.cuda.current_stream(dev)
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=dev)
+        self._copy_stream.wait_stream(main)                  # the previous call's query prep has read the staging buffer
+        events = []
+        with torch.cuda.stream(self._copy_stream):
+            for r0 in range(0, B, piece):
+                r1 = min(B, r0 + piece)
+                self._qstage[r0:r1].copy_(Qh[r0:r1], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(self._copy_stream)
+                events.append(ev)
+        for i, r0 in enumerate(range(0, B, piece)):
+            r1 = min(B, r0 + piece)
+            main.wait_event(events[i])
+            rows_pad = (Bc - r0) if r1 == B else (r1 - r0)    # the last piece also zeroes the chunk's padding rows
+            self.stage_scores(ws, self._qstage[r0:r1], r0, rows_pad, Lq_pad, ncells, thr, remove_zero_rows)
+        self.stage_candidate_pids(ws, B, ncells)
+        self.stage_rank(ws, B, Lq_pad, ndocs, k, Bc, out, out_stride)
+        return ws
+
     # ----------------------------------------------------------------------------------- public
     def search_batch(self, Q: torch.Tensor, k: int = 100, ncells: int | None = None,
                      centroid_score_threshold: float | None = None, ndocs: int | None = None,
@@ -428,6 +484,26 @@ class SearchEngine:
             raise _lib.PlaidError(f"search_batch: current CUDA device {torch.cuda.current_device()} != index device {dev.index}; "
                                   "wrap the call in torch.cuda.device(index.device)")
         Bc = self.chunk_size(B, resident=Q.is_cuda and self.exchange is None)
+        # host-fed batch that fits one chunk: pieces of `host_piece` queries cross PCIe behind the centroid scoring of the
+        # previous piece (_run_chunk_host); larger batches / large codebooks: whole chunks, one ahead of the search
+        piece_req = int(os.environ.get("PLAID_HOST_PIECE", self.host_piece))
+        piece = max(4, (piece_req // 4) * 4)
+        host_pipe = (not Q.is_cuda and piece_req > 0 and self.exchange is None and self.streams == 1 and B > piece
+                     and self.chunk_size(B, resident=True) >= B and self.max_chunk == 512)
+        if host_pipe:
+            Bc = self.chunk_size(B, resident=True)
+            Qh = Q.to(torch.float32).contiguous()
+            if not Qh.is_pinned():
+                Qh = Qh.pin_memory()
+            rows = (ctypes.c_void_p(out_p.data_ptr()), ctypes.c_void_p(out_s.data_ptr()), ctypes.c_void_p(out_c.data_ptr()))
+            ws = self._run_chunk_host(Qh, Lq_pad, ncells, thr, ndocs, kk, remove_zero_rows, Bc, piece, rows, k)
+            if on_chunk is not None:
+                on_chunk(ws, B)
+            if keep_taps:
+                self.last_taps = self._taps(ws)
+            if global_pids and ix.pid_base:
+                out_p.add_((out_p >= 0).to(torch.int32) * ix.pid_base)
+            return out_p, out_s, out_c
         feed = self._host_feed(Q, Bc) if not Q.is_cuda else None
         Qd = Q.to(torch.float32).contiguous() if Q.is_cuda else None
         n_chunks = (B + Bc - 1) // Bc
@@ -452,18 +528,22 @@ class SearchEngine:
             if on_chunk is not None:
                 on_chunk(ws, n)
             if keep_taps:
-                self.last_taps = StageTaps(
-                    Qb=ws["Qb"], qlens=ws["qlens"], S=ws["S"], idx_bits=ws["idx_bits"], cells=ws["cells"],
-                    cand_pids=ws["cand_pids"], cand_counts=ws["cand_counts"], stage1_pids=ws["s1_pids"],
-                    stage1_scores=ws["s1_scores"], stage1_counts=ws["s1_counts"], stage2_pids=ws["s2_pids"],
-                    stage2_scores=ws["s2_scores"], stage2_counts=ws["s2_counts"], tok_offsets=ws["tok_offsets"],
-                    D=ws["D"], tok_stride=ws["tok_stride"], scores=ws["scores"])
+                self.last_taps = self._taps(ws)
         if nstreams > 1:
             for st in self._side_streams[:nstreams]:
                 main.wait_stream(st)
         if global_pids and ix.pid_base:
             out_p.add_((out_p >= 0).to(torch.int32) * ix.pid_base)
         return out_p, out_s, out_c
+
+    @staticmethod
+    def _taps(ws) -> StageTaps:
+        return StageTaps(
+            Qb=ws["Qb"], qlens=ws["qlens"], S=ws["S"], idx_bits=ws["idx_bits"], cells=ws["cells"],
+            cand_pids=ws["cand_pids"], cand_counts=ws["cand_counts"], stage1_pids=ws["s1_pids"],
+            stage1_scores=ws["s1_scores"], stage1_counts=ws["s1_counts"], stage2_pids=ws["s2_pids"],
+            stage2_scores=ws["s2_scores"], stage2_counts=ws["s2_counts"], tok_offsets=ws["tok_offsets"],
+            D=ws["D"], tok_stride=ws["tok_stride"], scores=ws["scores"])
 
     def _host_feed(self, Q: torch.Tensor, Bc: int):
         """Host query embeddings -> device, one chunk ahead of the compute on a copy stream."""
