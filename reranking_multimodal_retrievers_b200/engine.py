@@ -171,6 +171,7 @@ class SearchEngine:
         self._ws_key = None
         self._copy_stream = None
         self._qstage = None        # device staging buffer of a host-fed chunk (_run_chunk_host)
+        self._qstage_free = None   # event: the staging buffer has been consumed
         self.host_piece = 256      # queries per PCIe piece of a host-fed batch (0: whole chunks behind a double buffer)
         self._ws = None
         self.last_taps: StageTaps | None = None
@@ -423,10 +424,14 @@ class SearchEngine:
         ws = self._workspace(Bc, Lq_pad, ncells, ndocs, k, 0, groups=piece // 4)
         if self._qstage is None or self._qstage.shape != (Bc, Lq, dim):
             self._qstage = torch.empty(Bc, Lq, dim, device=dev, dtype=torch.float32)
+            self._qstage_free = None
         main = torch.cuda.current_stream(dev)
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream(device=dev)
-        self._copy_stream.wait_stream(main)                  # the previous call's query prep has read the staging buffer
+        if self._qstage_free is not None:
+            self._copy_stream.wait_event(self._qstage_free)  # the previous call's query prep has read the staging buffer
+        else:
+            self._copy_stream.wait_stream(main)              # first use: the buffer was allocated on the compute stream
         events = []
         with torch.cuda.stream(self._copy_stream):
             for r0 in range(0, B, piece):
@@ -440,6 +445,8 @@ class SearchEngine:
             main.wait_event(events[i])
             rows_pad = (Bc - r0) if r1 == B else (r1 - r0)    # the last piece also zeroes the chunk's padding rows
             self.stage_scores(ws, self._qstage[r0:r1], r0, rows_pad, Lq_pad, ncells, thr, remove_zero_rows)
+        self._qstage_free = torch.cuda.Event()
+        self._qstage_free.record(main)                       # the next batch may overwrite the staging buffer from here on
         self.stage_candidate_pids(ws, B, ncells)
         self.stage_rank(ws, B, Lq_pad, ndocs, k, Bc, out, out_stride)
         return ws
