@@ -172,7 +172,8 @@ class SearchEngine:
         self._copy_stream = None
         self._qstage = None        # device staging buffer of a host-fed chunk (_run_chunk_host)
         self._qstage_free = None   # event: the staging buffer has been consumed
-        self.host_piece = 256      # queries per PCIe piece of a host-fed batch (0: whole chunks behind a double buffer)
+        self.host_piece = 256      # queries per PCIe piece of a host-fed batch (0: whole chunks behind a double buffer) ...
+        self.host_piece_bytes = 8 << 20   # ... and at most this many bytes (256 FLMR queries of 64 tokens; 48 PreFLMR queries of 320)
         self._ws = None
         self.last_taps: StageTaps | None = None
         self.launch_count = 0      # kernels of libplaid_b200 launched so far (bench.py reports the delta)
@@ -494,6 +495,8 @@ class SearchEngine:
         # host-fed batch that fits one chunk: pieces of `host_piece` queries cross PCIe behind the centroid scoring of the
         # previous piece (_run_chunk_host); larger batches / large codebooks: whole chunks, one ahead of the search
         piece_req = int(os.environ.get("PLAID_HOST_PIECE", self.host_piece))
+        if piece_req > 0 and Lq * dim * 4 * piece_req > self.host_piece_bytes:     # long queries: pieces of ~8 MB
+            piece_req = max(4, self.host_piece_bytes // (Lq * dim * 4))
         piece = max(4, (piece_req // 4) * 4)
         host_pipe = (not Q.is_cuda and piece_req > 0 and self.exchange is None and self.streams == 1 and B > piece
                      and self.chunk_size(B, resident=True) >= B and self.max_chunk == 512)
