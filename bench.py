@@ -463,7 +463,7 @@ def bench_rerank(args, w, peaks, rank, world, local_rank):
         return pkg.colbert_score(q, D, mask, docs_per_query=dpq)
 
     def step_e2e():
-        s = step(Qhost.to(dev, non_blocking=True))
+        s = step(Qhost)          # host (pinned) query matrices in: colbert_score copies them in pieces behind the MaxSim
         out_host.copy_(s, non_blocking=True)
         torch.cuda.current_stream().synchronize()
 

@@ -54,7 +54,73 @@ def colbert_score_reduce(scores_padded, D_mask, config=None):
     return out[:n]
 
 
+_HOST_Q_CHUNK_BYTES = 16 << 20     # host query batches of colbert_score cross PCIe in pieces of about this size
+_COPY_STREAMS = {}
+
+
+def _padded_scores_host_queries(Q, D_padded, D_mask, docs_per_query):
+    """colbert_score with a large batch of HOST query matrices against device-resident passages (the cross-encoder
+    hand-off shape: 4096 queries x 100 passages): the queries cross PCIe in ~16 MB pieces on a copy stream, one piece ahead
+    of the MaxSim of the previous one, instead of as one exposed 134 MB copy."""
+    nQ, Lq, dim = Q.shape
+    n, Ld, _ = D_padded.shape
+    dev = D_padded.device
+    Qh = Q.to(torch.float32).contiguous()
+    if not Qh.is_pinned():
+        Qh = Qh.pin_memory()
+    chunk = max(4, (_HOST_Q_CHUNK_BYTES // (Lq * dim * 4) // 4) * 4)
+    Db = _as_bf16(D_padded).contiguous()
+    mask = _cu(D_mask).reshape(n, Ld).ne(0).to(torch.uint8).contiguous()
+    scores = torch.empty(max(n, 1), device=dev, dtype=torch.float32)
+    wd = _watchdog(dev)
+    main = torch.cuda.current_stream(dev)
+    key = (dev.type, dev.index)
+    if key not in _COPY_STREAMS:
+        _COPY_STREAMS[key] = torch.cuda.Stream(device=dev)
+    copy = _COPY_STREAMS[key]
+    bufs = [torch.empty(chunk, Lq, dim, device=dev, dtype=torch.float32) for _ in range(2)]
+    copy.wait_stream(main)                                   # the staging buffers were allocated on the compute stream
+    freed = [None, None]
+    ready = [None, None]
+
+    def issue(ci):
+        q0 = ci * chunk
+        if q0 >= nQ or q0 * docs_per_query >= n:
+            return
+        q1 = min(nQ, q0 + chunk)
+        slot = ci & 1
+        if freed[slot] is not None:
+            copy.wait_event(freed[slot])
+        with torch.cuda.stream(copy):
+            bufs[slot][: q1 - q0].copy_(Qh[q0:q1], non_blocking=True)
+            ready[slot] = torch.cuda.Event()
+            ready[slot].record(copy)
+
+    issue(0)
+    for ci in range((nQ + chunk - 1) // chunk):
+        q0 = ci * chunk
+        d0 = q0 * docs_per_query
+        if d0 >= n:
+            break
+        q1 = min(nQ, q0 + chunk)
+        d1 = min(n, q1 * docs_per_query)
+        slot = ci & 1
+        issue(ci + 1)
+        main.wait_event(ready[slot])
+        Qb, qlens = ops.prepare_queries(bufs[slot][: q1 - q0], remove_zero_rows=False)
+        freed[slot] = torch.cuda.Event()
+        freed[slot].record(main)
+        _lib.call("plaid_colbert_score_padded", _p(Qb), _p(qlens), q1 - q0, Qb.shape[0], Qb.shape[1], _p(Db[d0:d1]),
+                  _p(mask[d0:d1]), d1 - d0, Ld, int(docs_per_query), _p(scores[d0:d1]), None, Lq, _p(wd), _stream())
+    return scores[:n]
+
+
 def _padded_scores(Q, D_padded, D_mask, return_raw, docs_per_query=None):
+    if (not return_raw and docs_per_query is not None and torch.is_tensor(Q) and not Q.is_cuda and Q.dim() == 3
+            and torch.is_tensor(D_padded) and D_padded.is_cuda and D_padded.dim() == 3
+            and Q.shape[0] * Q.shape[1] * Q.shape[2] * 4 >= 2 * _HOST_Q_CHUNK_BYTES
+            and Q.shape[0] * int(docs_per_query) >= D_padded.shape[0]):
+        return _padded_scores_host_queries(Q, D_padded, D_mask, int(docs_per_query)), None
     Q = _cu(Q)
     if Q.dim() != 3 or D_padded.dim() != 3:
         raise ValueError("colbert_score expects Q [1|n, Lq, dim] and D_padded [n, Ld, dim]")

@@ -86,6 +86,23 @@ def test_resident_batch_runs_as_one_chunk_and_matches_the_host_fed_chunks():
     assert float((pd[:, 0].cpu() == gold.cpu().to(torch.int32)).float().mean()) >= 0.99
 
 
+def test_colbert_score_host_query_batch_is_copied_in_pieces_same_scores():
+    """A large HOST batch of query matrices (the rerank hand-off) crosses PCIe in ~16 MB pieces behind the MaxSim of the
+    previous piece: the scores equal those of the device-resident call bit for bit (ragged last piece, n < nQ * dpq)."""
+    import reranking_multimodal_retrievers_b200 as pkg
+    g = torch.Generator(device="cuda")
+    g.manual_seed(5)
+    nQ, dpq, Ld, Lq = 1100, 2, 16, 64
+    n = nQ * dpq - 1
+    Q = torch.nn.functional.normalize(torch.randn(nQ, Lq, 128, generator=g, device="cuda"), dim=-1)
+    D = torch.nn.functional.normalize(torch.randn(n, Ld, 128, generator=g, device="cuda"), dim=-1).bfloat16()
+    lens = torch.randint(1, Ld + 1, (n,), generator=g, device="cuda")
+    mask = torch.arange(Ld, device="cuda").unsqueeze(0) < lens.unsqueeze(1)
+    dev_scores = pkg.colbert_score(Q, D, mask, docs_per_query=dpq)
+    host_scores = pkg.colbert_score(Q.cpu().pin_memory(), D, mask, docs_per_query=dpq)
+    assert host_scores.is_cuda and torch.equal(dev_scores, host_scores)
+
+
 def test_fullsize_padded_rerank_linearity_and_permutation():
     """cfg5 shape (top-100 rerank, bf16 passage embeddings): properties of the padded MaxSim on a
     4096-passage slab -- permutation equivariance over passages, invariance to padding content,
