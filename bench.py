@@ -631,8 +631,8 @@ def main():
         return out
 
     def step_e2e_engine():
-        # HOST (pinned) query embeddings in, device lists out + D2H: the engine copies the queries chunk by chunk on a copy
-        # stream, one chunk ahead of the search (H2D of this step's inputs is inside the timed region)
+        # HOST (pinned) query embeddings in, device lists out + D2H: the engine copies the queries on a copy stream in pieces,
+        # ahead of the centroid scoring of the previous piece (H2D of this step's inputs is inside the timed region)
         p, s, c = step(Qhost)
         out_host[0].copy_(p, non_blocking=True); out_host[1].copy_(s, non_blocking=True)
         out_host[2].copy_(c, non_blocking=True)         # D2H of the step's result
