@@ -20,23 +20,24 @@
 #include "common.cuh"
 #include "decompress.cuh"
 
+// ---- build options (A/B variants: python -m reranking_multimodal_retrievers_b200.build --variant NAME -DOPT=V, scripts/ab_variants.sh) ----
 #ifndef MS_FUSED_ATMEM
-#define MS_FUSED_ATMEM 1    // slim fused kernel: the query (A operand) lives in tensor memory, not in shared memory
+#define MS_FUSED_ATMEM 1       // slim fused kernel: the query (A operand) lives in tensor memory, not in shared memory
+#endif
+#ifndef MS_FUSED_CB
+#define MS_FUSED_CB 2          // fused kernel: steps (of 4 tokens) per centroid batch; two batches are in flight (1: 2.36 ms, 4: 2.17 vs 2.11)
+#endif
+#ifndef MS_UNIFORM_WARP
+#define MS_UNIFORM_WARP 1      // warp index as a lane-0 broadcast (common.cuh: warp_index()); 0 = the pre-round-2b code generation
+#endif
+#ifndef MS_EPI_MODE
+#define MS_EPI_MODE 1          // lean epilogue: 0 = chain of maxima, 1 = tree of 3-input maxima, 2 = tree + two 32-column loads per wait
 #endif
 #ifndef MS_SKIP_PAD_BATCHES
-#define MS_SKIP_PAD_BATCHES 1
-#endif
-#ifndef MS_DBG_SKIP_EPI
-#define MS_DBG_SKIP_EPI 0  // timing experiments only (wrong results): the lean epilogues skip their loads and maxima
-#endif
-#ifndef MS_DBG_SKIP_STS
-#define MS_DBG_SKIP_STS 0
-#endif
-#ifndef MS_DBG_SKIP_DEC
-#define MS_DBG_SKIP_DEC 0  // timing experiments only (wrong results): the decompressors skip the decoding of their units
+#define MS_SKIP_PAD_BATCHES 1  // a passage's last 32-row unit decodes only the pairs of centroid batches that hold real rows
 #endif
 #ifndef MS_SLIM_UT
-#define MS_SLIM_UT 32      // slim layout: rows of a tile built by one decompressor warp (32: four groups of 4 warps; 16: two groups of 8)
+#define MS_SLIM_UT 32          // slim layout: rows of a tile built by one decompressor warp (32: four groups of 4 warps; 16: two groups of 8)
 #endif
 #ifndef MS_FUSED_Q16
 // Short queries (Lq_pad <= 64): four epilogue warps x 16 query rows, MMAs issued by the decompressor groups.  Correct
@@ -45,15 +46,17 @@
 // nothing), and the groups' leaders pay for the issue.  Kept as a build option.
 #define MS_FUSED_Q16 0
 #endif
-#ifndef MS_EPI_MODE
-#define MS_EPI_MODE 1      // lean epilogue: 0 = chain of maxima, 1 = tree of 3-input maxima, 2 = tree + two 32-column loads per wait
+// timing experiments only (WRONG results; DESIGN.md section 4, third pass): what the kernel costs without one of its parts
+#ifndef MS_DBG_SKIP_EPI
+#define MS_DBG_SKIP_EPI 0      // the lean epilogues skip their loads and maxima
 #endif
-#ifndef MS_UNIFORM_WARP
-#define MS_UNIFORM_WARP 1
+#ifndef MS_DBG_SKIP_STS
+#define MS_DBG_SKIP_STS 0      // the decompressors keep their arithmetic but store no tile rows
 #endif
-#ifndef MS_FUSED_CB
-#define MS_FUSED_CB 2      // fused kernel: steps (of 4 tokens) per centroid batch; two batches are in flight
+#ifndef MS_DBG_SKIP_DEC
+#define MS_DBG_SKIP_DEC 0      // the decompressors skip the decoding of their units
 #endif
+// (-DMS_DBG_STAGE_STRIDE=bytes: overlapping ring stages, i.e. more of them; -DMS_DBG_TIMING: per-warp stage-wait counters)
 
 #ifdef MS_DBG_TIMING
 // development aid: per (CTA, decompressor warp) cycles spent waiting for a free stage / in total (scripts/fused_wait_probe.py)
