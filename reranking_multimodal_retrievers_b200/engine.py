@@ -501,6 +501,8 @@ class SearchEngine:
         host_pipe = (not Q.is_cuda and piece_req > 0 and self.exchange is None and self.streams == 1 and B > piece
                      and self.chunk_size(B, resident=True) >= B and self.max_chunk == 512)
         if host_pipe:
+            npieces = -(-B // piece)
+            piece = ((-(-B // npieces) + 3) // 4) * 4         # equal pieces: a short last one would cost a whole wave of its own
             Bc = self.chunk_size(B, resident=True)
             Qh = Q.to(torch.float32).contiguous()
             if not Qh.is_pinned():
