@@ -203,7 +203,12 @@ class SearchEngine:
                     best, best_rate = cand, cand * cs
             bc = best
         bc = min(bc, ((B + 3) // 4) * 4)
-        return max(4, (bc // 4) * 4)
+        bc = max(4, (bc // 4) * 4)
+        if not large and B > bc:
+            # equal chunks: 520 queries are 2 x 260, not 512 + 8 (a short chunk pays the tails of every kernel for nothing)
+            n_chunks = -(-B // bc)
+            bc = min(bc, ((-(-B // n_chunks) + 3) // 4) * 4)
+        return bc
 
     def _workspace(self, Bc: int, Lq_pad: int, ncells: int, ndocs: int, k: int, slot: int = 0, groups: int | None = None):
         """groups: query groups (of 4) per plaid_centroid_scores launch when a chunk is scored in pieces (host-fed batches),

@@ -73,16 +73,22 @@ def test_fullsize_properties_and_oracle_sample(N, B):
 
 
 def test_resident_batch_runs_as_one_chunk_and_matches_the_host_fed_chunks():
-    """Device-resident batches of up to 1024 queries are searched as ONE chunk, host-fed ones in 512-query chunks behind a
-    copy stream (engine.chunk_size): the two paths return the same lists bit for bit."""
+    """Device-resident batches of up to 1024 queries are searched as ONE chunk; host-fed ones cross PCIe in equal pieces
+    (query prep + centroid scoring per piece, the rest once) or, with host_piece = 0, as whole chunks one ahead of the
+    search: all three paths return the same lists bit for bit."""
     k, B = 100, 640
     sx, Q, gold, eng = _build(20_000, B, 64)
-    assert eng.chunk_size(B, resident=True) == B and eng.chunk_size(B) == 512
+    assert eng.chunk_size(B, resident=True) == B and eng.chunk_size(B) == 320     # whole-chunk feeding: two equal chunks
     pd, sd, cd = eng.search_batch(Q, k=k)                       # one chunk of 640
     eng.check_flags()
-    ph, sh, ch = eng.search_batch(Q.cpu().pin_memory(), k=k)    # 512 + 128, H2D one chunk ahead
+    Qh = Q.cpu().pin_memory()
+    ph, sh, ch = eng.search_batch(Qh, k=k)                      # 3 pieces of 216 / 216 / 208 queries, one chunk
     eng.check_flags()
     assert torch.equal(pd, ph) and torch.equal(sd, sh) and torch.equal(cd, ch)
+    eng.host_piece = 0
+    pw, sw, cw = eng.search_batch(Qh, k=k)                      # 320 + 320, H2D one chunk ahead
+    eng.check_flags()
+    assert torch.equal(pd, pw) and torch.equal(sd, sw) and torch.equal(cd, cw)
     assert float((pd[:, 0].cpu() == gold.cpu().to(torch.int32)).float().mean()) >= 0.99
 
 
