@@ -979,8 +979,12 @@ static int launch_select(const int32_t* pids, const float* scores, const int32_t
     const size_t smem = (size_t)(sel_cap + kBktCap + kRankMax) * 8 + 256 * 4 + 16;
     static int configured[kMaxDevices] = {0};
     if (int rc = ensure_dynamic_smem((const void*)select_top_kernel, (int)smem, configured)) return rc;
-    select_top_kernel<<<B, kSelThreads, smem, st>>>(pids, scores, counts, in_stride, keep, sel_cap, out_pids, out_scores,
-                                                    out_counts, out_stride, ws_keys);
+    // one CTA per query: with more queries in a chunk than 512-thread CTAs fit on the GPU at once (592), half-size CTAs put
+    // the whole chunk on the SMs in one wave (1024-query chunks on cfg2: select1 0.165 -> 0.149 ms, select2 / top-k -10 %;
+    // 1024-thread CTAs: 0.179)
+    const int threads = B > 592 ? kSelThreads / 2 : kSelThreads;
+    select_top_kernel<<<B, threads, smem, st>>>(pids, scores, counts, in_stride, keep, sel_cap, out_pids, out_scores,
+                                                out_counts, out_stride, ws_keys);
     PLAID_LAUNCH_OK("select_top_kernel");
     return PLAID_OK;
 }
