@@ -38,6 +38,32 @@ def test_search_defaults_follow_reference():
     assert search_defaults(100) == po.search_defaults(100) and search_defaults(500) == po.search_defaults(500)
 
 
+def test_chunk_and_centroid_range_arithmetic():
+    """Query-chunk sizes and centroid-range counts of the batched engine (pure host arithmetic): device-resident batches of
+    up to 1024 queries are one chunk, larger / host-fed-by-chunk batches split into EQUAL chunks, and the range count of
+    plaid_centroid_scores follows the measured cost model."""
+    from reranking_multimodal_retrievers_b200.engine import SearchEngine, pick_csplit
+
+    class _Index:                       # just what chunk_size reads
+        num_centroids = 65536
+        device = torch.device("cpu")
+
+    eng = SearchEngine.__new__(SearchEngine)
+    eng.index, eng.s_dtype, eng.s_budget_bytes, eng.max_chunk = _Index(), torch.float16, 40 << 30, 512
+    assert eng.chunk_size(100) == 100 and eng.chunk_size(512) == 512
+    assert eng.chunk_size(520) == 260 and eng.chunk_size(1100) == 368 and eng.chunk_size(1024) == 512
+    assert eng.chunk_size(1024, resident=True) == 1024 and eng.chunk_size(640, resident=True) == 640
+    assert eng.chunk_size(1100, resident=True) == 368            # beyond one resident chunk: equal chunks again
+    for B in (1, 7, 520, 1100, 3000):
+        bc = eng.chunk_size(B)
+        assert bc % 4 == 0 and bc <= 512 and -(-B // bc) == -(-B // 512)     # balancing never adds a chunk
+    eng.max_chunk = 64
+    assert eng.chunk_size(192) == 64 and eng.chunk_size(200) == 52
+    # centroid ranges: one range when the query groups fill the SMs, several when whole waves are at stake
+    assert pick_csplit(128, 256) == 1 and pick_csplit(256, 256) == 4 and pick_csplit(64, 256) == 2
+    assert pick_csplit(108, 2048) == 4 and 1 <= pick_csplit(1, 256) <= 64
+
+
 def test_idx_bit_packing_roundtrip():
     g = torch.Generator().manual_seed(1)
     idx = torch.rand(3, 1024, generator=g) > 0.5
