@@ -170,7 +170,7 @@ class ShardedSearcher:
         b1 = min(B, b0 + per)
         if b1 > b0:
             mine = Q[b0:b1].to(torch.float32).contiguous()
-            if not mine.is_pinned():
+            if dev.type == "cuda" and not mine.is_pinned():
                 mine = mine.pin_memory()
             self._qsend[: b1 - b0].copy_(mine, non_blocking=True)
         dist.all_gather_into_tensor(self._qfull, self._qsend, group=self.group)

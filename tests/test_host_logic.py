@@ -189,6 +189,16 @@ def _gloo_worker(rank, world, port, tmpdir):
             assert torch.all(gq[2 * r:2 * r + 2] == r + 1) and torch.all(gd[4 * r:4 * r + 4] == 10 * (r + 1)) and torch.all(gm[4 * r:4 * r + 4] == r)
         (gq.sum() * 2 + gd.sum() * 3).backward()
         assert torch.all(q.grad == 2) and torch.all(d.grad == 3)                 # nothing flows to the other ranks' blocks
+        # host query batches of the sharded plugin call: every rank copies its 1/G slice, one all-gather replicates the batch
+        # (ShardedSearcher._replicate_host_queries); ragged: 5 queries over 2 ranks = slices of 3 and 2
+        import types
+        ss = sharded.ShardedSearcher.__new__(sharded.ShardedSearcher)
+        ss.world_size, ss.rank, ss.group, ss._qsend, ss._qfull = world, rank, None, None, None
+        ss.searcher = types.SimpleNamespace(ranker=types.SimpleNamespace(index=types.SimpleNamespace(device=torch.device("cpu"))))
+        for nq in (5, 4, 2):
+            Qall = torch.arange(nq * 3 * 4, dtype=torch.float32).reshape(nq, 3, 4) + 0.5      # the same batch on every rank
+            got = ss._replicate_host_queries(Qall)
+            assert got.shape == Qall.shape and torch.equal(got, Qall)
         torch.save((gp, gs, gc, merged), os.path.join(tmpdir, f"r{rank}.pt"))
     finally:
         dist.destroy_process_group()
