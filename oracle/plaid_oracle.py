@@ -315,8 +315,10 @@ def codec_decompress_gpu_form(bucket_weights, reversed_bit_map, lookup, binary_r
     i.e. ONE half add (computed here as the fp32 sum of the two halves rounded to half: exact for |x| < 2, which
     unit-norm centroids plus residual weights satisfy).  normalize=True adds ResidualCodec.decompress's
     `F.normalize(x, p=2, dim=-1).half()` (residual.py:272-273) in the arithmetic torch's CUDA kernels use for half.
-    PARITY UNPINNED against the reference kernel itself (it needs a GPU the authoring container does not have);
-    pinned indirectly: the fp32 CPU operator on the same bytes (golden D_0) differs by one half rounding."""
+    Pinned on the GPU box: the reference kernel itself (compiled from /root/reference into oracle/_ref by
+    oracle/build_ref.py --gpu) returns the same bits for nbits 1/2/4/8
+    (tests/test_gpu_ops.py::test_gpu_form_codec_operators_equal_the_reference_cuda_kernels); on CPU it is pinned
+    indirectly: the fp32 CPU operator on the same bytes (golden D_0) differs by one half rounding."""
     w = bucket_weights.half()[lookup[reversed_bit_map[binary_residuals.long()].long()].long()]
     w = w.reshape(binary_residuals.shape[0], -1)
     out = (w.float() + centroids_f16.half()[codes.long()].float()).half()

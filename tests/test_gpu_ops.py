@@ -361,6 +361,56 @@ def test_residual_codec_gpu_operators(P, nbits):
     assert torch.equal(codec.binarize(r).cpu(), po.codec_binarize(r, sx.bucket_cutoffs, nbits))
 
 
+def _ref_gpu_ops():
+    from oracle import build_ref
+    import os
+    if not all(os.path.exists(build_ref.ref_so_path(n)) for n in build_ref.GPU_SOURCES):
+        pytest.skip("oracle/_ref GPU operators not built (python oracle/build_ref.py --gpu, needs /root/reference)")
+    return {n: build_ref.load(n) for n in build_ref.GPU_SOURCES}
+
+
+@pytest.mark.parametrize("nbits", [1, 2, 4, 8])
+def test_gpu_form_codec_operators_equal_the_reference_cuda_kernels(P, nbits):
+    """The reference's OWN CUDA operators (CB/indexing/codecs/decompress_residuals.cu:8-75, packbits.cu:10-57, compiled
+    from /root/reference into oracle/_ref by oracle/build_ref.py --gpu) run on this GPU: our ResidualCodec operators
+    and the oracle's restatement of the GPU-form decompression must equal them bit for bit."""
+    pkg, ops = P
+    ref = _ref_gpu_ops()
+    from reranking_multimodal_retrievers_b200.synthetic import make_synthetic_index
+    sx = make_synthetic_index(300, 1, 70, nbits, seed=90 + nbits, num_centroids=512, mode="codes")
+    rbm, lut = po.codec_tables(nbits)
+    dev = torch.device("cuda", 0)                       # the reference kernel allocates its output on cuda:0
+    bw_h, cent_h = sx.bucket_weights.half().to(dev), sx.centroids.half().to(dev)
+    rbm_d, lut_d = rbm.to(dev), lut.to(dev)
+    for m in (sx.num_embeddings, 1, 33, 1 << 15):       # 1 << 15: the batch size ResidualCodec.decompress splits into (residual.py:246)
+        m = min(m, sx.num_embeddings)
+        res, codes = sx.residuals[:m].contiguous().to(dev), sx.codes[:m].contiguous().to(dev)
+        want = ref["decompress_residuals_gpu_cpp"].decompress_residuals_cpp(res, bw_h, rbm_d, lut_d, codes, cent_h, 128, nbits)
+        torch.cuda.synchronize()
+        assert want.dtype == torch.float16 and want.shape == (m, 128)
+        ours = pkg.ResidualCodec.decompress_residuals(res, bw_h, rbm_d, lut_d, codes, cent_h, 128, nbits)
+        assert torch.equal(ours.view(torch.int16), want.view(torch.int16)), "GPU-form decompression differs from the reference kernel"
+        restated = po.codec_decompress_gpu_form(sx.bucket_weights, rbm, lut, sx.residuals[:m], sx.codes[:m], sx.centroids)
+        assert torch.equal(restated.view(torch.int16), want.cpu().view(torch.int16)), "oracle restatement differs from the reference kernel"
+        # ResidualCodec.decompress = F.normalize(...).half() of those rows on the GPU (residual.py:272-273)
+        Dn_ref = torch.nn.functional.normalize(want, p=2, dim=-1).half()
+        Dn_restated = po.codec_decompress_gpu_form(sx.bucket_weights, rbm, lut, sx.residuals[:m], sx.codes[:m], sx.centroids,
+                                                   normalize=True)
+        assert (Dn_restated.float() - Dn_ref.cpu().float()).abs().max() <= 2 ** -10
+        assert (Dn_restated != Dn_ref.cpu()).float().mean() < 0.01
+        Dn_ours = ops.codec_decompress_residuals(res, bw_h, rbm_d, lut_d, codes, cent_h, 128, nbits, normalize=True)
+        assert (Dn_ours.float() - Dn_ref.float()).abs().max() <= 2 ** -10
+    # packbits: the reference kernel packs 32 flags per warp (sizes are multiples of 32 at its call site, residual.py:198)
+    g = torch.Generator().manual_seed(100 + nbits)
+    for n in (32, 128 * nbits * 7, 32 * 4097):
+        flags = torch.randint(0, 2, (n,), generator=g, dtype=torch.uint8)
+        flags[::5] *= 3                                   # any non-zero byte is a set flag (ballot predicate)
+        want = ref["packbits_gpu_cpp"].packbits_cpp(flags.to(dev))
+        torch.cuda.synchronize()
+        assert torch.equal(pkg.ResidualCodec.packbits(flags.to(dev)), want)
+        assert torch.equal(po.codec_packbits(flags), want.cpu())
+
+
 def test_lookup_eids_and_embedding_ids_to_pids(P, golden):
     """IndexScorer.lookup_eids / embedding_ids_to_pids (CB/search/index_storage.py:61-62,82-84)."""
     pkg, ops = P
