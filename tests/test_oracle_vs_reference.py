@@ -66,3 +66,12 @@ def test_segmented_lookup(golden, ref):
                                             ctypes.c_int(4), po._p(lengths.contiguous()), po._p(offsets.contiguous()),
                                             po._p(mine))
     assert torch.equal(out, mine)
+
+
+def test_reference_cuda_operators_are_built_and_export_their_entry_points():
+    """oracle/_ref also holds the reference's two CUDA codec operators (build_ref.py --gpu); they only RUN on the GPU box
+    (tests/test_gpu_ops.py), here: the modules load and export the names residual.py:115,130 binds."""
+    if not all(os.path.exists(build_ref.ref_so_path(n)) for n in build_ref.GPU_SOURCES):
+        pytest.skip("reference CUDA operators not built (python oracle/build_ref.py --gpu)")
+    assert callable(build_ref.load("decompress_residuals_gpu_cpp").decompress_residuals_cpp)
+    assert callable(build_ref.load("packbits_gpu_cpp").packbits_cpp)
