@@ -35,6 +35,9 @@ def _dev():
 
 def _cu(t: torch.Tensor, dtype=None) -> torch.Tensor:
     """contiguous, 16-byte aligned tensor on the current CUDA device (optionally cast)."""
+    if (t.is_cuda and (dtype is None or t.dtype == dtype) and t.is_contiguous() and not (t.data_ptr() & 15)
+            and t.device.index == torch.cuda.current_device()):
+        return t            # already what the kernels want: the common case of the operator calls, kept off the slow path
     t = t.to(device=_dev(), dtype=dtype if dtype is not None else t.dtype, non_blocking=True)
     t = t.contiguous()
     if t.data_ptr() % 16:   # a view into the middle of a buffer: the kernels use 128-bit loads
@@ -163,11 +166,37 @@ def filter_pids(pids, centroid_scores, codes, doclens, offsets, idx, nfiltered_d
 
 
 # --------------------------------------------------------------------------------------------- decompression
+_WT_CACHE = []      # [(tensors, versions, device, nbits, W, event, stream)], most recent first
+
+
 def build_weight_table(bucket_weights, reversed_bit_map, lookup, nbits):
+    """f32 [256 * 8/nbits]: packed residual byte -> the bucket weights it expands to (`bucket_weights[lookup[
+    reversed_bit_map[x]]]`, residual.py:54-89).  The operators take the three tables on every call, as the reference's
+    do; the derived table is kept for the same three tensor OBJECTS at unchanged versions (the cache holds them, so their
+    storage cannot be recycled under the key) -- a 2^15-token operator call, the batch ResidualCodec.decompress uses
+    (residual.py:246), otherwise spends more host time rebuilding this table than the device spends decoding."""
     dev = _dev()
+    key = (bucket_weights, reversed_bit_map, lookup)
+    try:
+        vers = tuple(t._version for t in key)
+    except RuntimeError:                       # inference tensors carry no version counter: not cacheable
+        vers = None
+    if vers is not None:
+        for ent in _WT_CACHE:
+            if ent[3] == int(nbits) and ent[2] == dev and ent[1] == vers and all(a is b for a, b in zip(ent[0], key)):
+                st = torch.cuda.current_stream(dev)
+                if st != ent[6]:
+                    st.wait_event(ent[5])      # built on another stream
+                return ent[4]
     W = torch.empty(256 * (8 // nbits), device=dev, dtype=torch.float32)
     bw, rbm, lut = _cu(bucket_weights, torch.float32), _cu(reversed_bit_map, torch.uint8), _cu(lookup, torch.uint8)
     _lib.call("plaid_build_weight_table", _p(bw), _p(rbm), _p(lut), int(nbits), _p(W), _stream())
+    if vers is not None:
+        ev = torch.cuda.Event()
+        st = torch.cuda.current_stream(dev)
+        ev.record(st)
+        _WT_CACHE.insert(0, (key, vers, dev, int(nbits), W, ev, st))
+        del _WT_CACHE[4:]
     return W
 
 
@@ -214,12 +243,12 @@ def codec_decompress_residuals(binary_residuals, bucket_weights, reversed_bit_ma
     if codes.numel() != n:
         raise _lib.PlaidError("decompress_residuals: codes and binary_residuals disagree on the number of tokens")
     cent = _cu(centroids, torch.float16)
-    W = build_weight_table(_cu(bucket_weights).float(), reversed_bit_map, bucket_weight_combinations, nbits)
-    out = torch.empty(max(n, 1), DIM, device=res.device, dtype=torch.float16)
+    W = build_weight_table(bucket_weights, reversed_bit_map, bucket_weight_combinations, nbits)
+    out = torch.empty(n, DIM, device=res.device, dtype=torch.float16)
     if n:
         _lib.call("plaid_decompress_tokens_f16", _p(res), _p(codes), ctypes.c_int64(n), _p(W), _p(cent), cent.shape[0],
                   int(nbits), int(bool(normalize)), _p(out), _stream())
-    return out[:n]
+    return out
 
 
 def packbits(bits):

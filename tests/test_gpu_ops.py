@@ -400,6 +400,15 @@ def test_gpu_form_codec_operators_equal_the_reference_cuda_kernels(P, nbits):
         assert (Dn_restated != Dn_ref.cpu()).float().mean() < 0.01
         Dn_ours = ops.codec_decompress_residuals(res, bw_h, rbm_d, lut_d, codes, cent_h, 128, nbits, normalize=True)
         assert (Dn_ours.float() - Dn_ref.float()).abs().max() <= 2 ** -10
+    # the derived weight table is cached per tensor objects + versions (ops.build_weight_table): an in-place change of
+    # the caller's bucket weights must show in the next call
+    res, codes = sx.residuals[:64].contiguous().to(dev), sx.codes[:64].contiguous().to(dev)
+    for _ in range(2):
+        bw_h.mul_(1.5)
+        want = ref["decompress_residuals_gpu_cpp"].decompress_residuals_cpp(res, bw_h, rbm_d, lut_d, codes, cent_h, 128, nbits)
+        ours = pkg.ResidualCodec.decompress_residuals(res, bw_h, rbm_d, lut_d, codes, cent_h, 128, nbits)
+        again = pkg.ResidualCodec.decompress_residuals(res, bw_h, rbm_d, lut_d, codes, cent_h, 128, nbits)   # cache hit
+        assert torch.equal(ours.view(torch.int16), want.view(torch.int16)) and torch.equal(again, ours)
     # packbits: the reference kernel packs 32 flags per warp (sizes are multiples of 32 at its call site, residual.py:198)
     g = torch.Generator().manual_seed(100 + nbits)
     for n in (32, 128 * nbits * 7, 32 * 4097):
