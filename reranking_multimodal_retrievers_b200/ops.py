@@ -179,7 +179,7 @@ def build_weight_table(bucket_weights, reversed_bit_map, lookup, nbits):
     key = (bucket_weights, reversed_bit_map, lookup)
     try:
         vers = tuple(t._version for t in key)
-    except RuntimeError:                       # inference tensors carry no version counter: not cacheable
+    except (RuntimeError, AttributeError):     # inference tensors carry no version counter: not cacheable
         vers = None
     if vers is not None:
         for ent in _WT_CACHE:
