@@ -1,6 +1,6 @@
 """GPU-box probe: the reference's OWN CUDA codec kernels (oracle/_ref/*_gpu_cpp.so, built from /root/reference by
 `python oracle/build_ref.py --gpu`) timed beside ours on the same B200 and the same tokens, CUDA events, after warm-up.
-Development aid / evidence for DESIGN.md; not part of bench.py.  Usage: python scripts/ref_cuda_ab.py > gpurun_out/x.json"""
+Evidence for DESIGN.md; not part of bench.py, not collected by pytest.  Lives under tests/ because it executes oracle/ (test infrastructure).  Usage: python tests/ref_cuda_ab.py > gpurun_out/x.json"""
 import json
 import os
 import sys

@@ -142,6 +142,10 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "plaid_oracle" not in text and "import oracle" not in text and "from oracle" not in text, f
+    # development scripts do not execute the oracle either (only tests/, smoke() and bench.py's CPU legs may)
+    for f in os.listdir(os.path.join(ROOT, "scripts")):
+        text = open(os.path.join(ROOT, "scripts", f)).read()
+        assert "import oracle" not in text and "from oracle" not in text, f
 
 
 def _gloo_worker(rank, world, port, tmpdir):
