@@ -75,3 +75,29 @@ def test_reference_cuda_operators_are_built_and_export_their_entry_points():
         pytest.skip("reference CUDA operators not built (python oracle/build_ref.py --gpu)")
     assert callable(build_ref.load("decompress_residuals_gpu_cpp").decompress_residuals_cpp)
     assert callable(build_ref.load("packbits_gpu_cpp").packbits_cpp)
+
+
+def test_reference_arm_runner_reproduces_the_unmodified_searcher(golden):
+    """bench.py's `--impl reference` / cpu_baseline legs run oracle/ref_search.CpuSearcher: the reference's compiled
+    operators under a restatement of IndexScorer.rank's Python glue (the reference's Python cannot travel to the GPU box).
+    The golden vectors were recorded from the UNMODIFIED `Searcher._search_all_Q` (tests/golden/make_golden.py): the runner
+    must return the same passages in the same order with the same scores -- what is timed as "the reference" computes
+    what the reference computes."""
+    import numpy as np
+    from plaid_test_helpers import nonzero_rows
+    from oracle.ref_search import CpuSearcher
+    g = golden
+    cs = CpuSearcher(golden_oracle_index(g), threads=4)
+    assert cs.kind == "reference" and cs.cores == 4
+    Q = torch.from_numpy(g["Q"])
+    k = int(g["k"])
+    toks = 0
+    for b in range(Q.shape[0]):
+        (pids, scores), t3 = cs.rank(nonzero_rows(Q[b]), int(g["ncells"]), float(g["threshold"]), int(g["ndocs"]))
+        assert pids[:k] == g[f"rank_pids_{b}"].tolist()
+        np.testing.assert_allclose(np.asarray(scores[:k], dtype=np.float32), g[f"rank_scores_{b}"], rtol=2e-6, atol=2e-5)
+        assert sorted(pids) == sorted(g[f"stage2_{b}"].tolist())                 # the exact-scored set = stage-2 survivors
+        toks += t3
+    # T3 accounting of the arm: real tokens of the exact-scored passages (what bench.py divides by the time)
+    doclens = torch.from_numpy(g["doclens"])
+    assert toks == sum(int(doclens[torch.from_numpy(g[f"stage2_{b}"]).long()].sum()) for b in range(Q.shape[0]))
