@@ -101,3 +101,28 @@ def test_reference_arm_runner_reproduces_the_unmodified_searcher(golden):
     # T3 accounting of the arm: real tokens of the exact-scored passages (what bench.py divides by the time)
     doclens = torch.from_numpy(g["doclens"])
     assert toks == sum(int(doclens[torch.from_numpy(g[f"stage2_{b}"]).long()].sum()) for b in range(Q.shape[0]))
+
+
+@pytest.mark.parametrize("nbits", [1, 8])
+def test_restatement_equals_reference_operators_at_1_and_8_bits(ref, nbits):
+    """The golden indexes are 2- and 4-bit; the reference also packs 1 and 8 bits per dimension (residual.py:47-89).
+    On a synthetic index: the reference's compiled decompress_residuals_cpp == the C restatement bit for bit, and the whole
+    CPU pipeline run through the reference's operators (the bench's reference arm) == the pure restatement."""
+    from reranking_multimodal_retrievers_b200 import synthetic
+    from oracle.ref_search import CpuSearcher
+    sx = synthetic.make_synthetic_index(400, 8, 48, nbits, seed=20 + nbits, num_centroids=256, mode="codes")
+    ix = po.OracleIndex(centroids=sx.centroids, bucket_weights=sx.bucket_weights, codes=sx.codes, residuals=sx.residuals,
+                        doclens=sx.doclens, ivf=sx.ivf, ivf_lengths=sx.ivf_lengths, nbits=nbits)
+    pids = torch.tensor([7, 0, 399, 123, 124], dtype=torch.int32)
+    out = ref["decompress_residuals_cpp"].decompress_residuals_cpp(
+        pids, ix.doclens, ix.offsets, ix.bucket_weights, ix.reversed_bit_map, ix.lookup, ix.residuals, ix.codes,
+        ix.centroids, ix.dim, ix.nbits)
+    assert torch.equal(out, po.decompress_residuals(ix, pids))
+    Q = synthetic.make_queries(sx, 3, 40, seed=5)
+    cs = CpuSearcher(ix, threads=2)
+    assert cs.kind == "reference"
+    for b in range(Q.shape[0]):
+        (rp, rs), _ = cs.rank(Q[b], 2, 0.45, 128)
+        r = po.rank(ix, Q[b], 2, 0.45, 128)
+        assert rp == r["pids"].tolist()
+        torch.testing.assert_close(torch.tensor(rs), r["scores"], rtol=2e-6, atol=2e-5)
