@@ -126,3 +126,20 @@ def test_restatement_equals_reference_operators_at_1_and_8_bits(ref, nbits):
         r = po.rank(ix, Q[b], 2, 0.45, 128)
         assert rp == r["pids"].tolist()
         torch.testing.assert_close(torch.tensor(rs), r["scores"], rtol=2e-6, atol=2e-5)
+
+
+def test_filter_pids_tie_order_matches_reference(golden, ref):
+    """Stage scores tie massively in practice (every candidate without a surviving centroid scores the same): with a
+    coarsely quantised table most candidates tie, and the restatement must keep the reference's (score, pid) order."""
+    g = golden
+    ix = golden_oracle_index(g)
+    torch.set_num_threads(4)
+    S = (torch.from_numpy(g["S_0"]) * 4).round() / 4                 # a handful of distinct values
+    idx = S.max(-1).values >= 0.5
+    cand = torch.arange(0, ix.doclens.numel(), 2, dtype=torch.int32)  # 500 candidates >= ndocs
+    ndocs = int(g["ndocs"])
+    assert cand.numel() >= ndocs
+    out = ref["filter_pids_cpp"].filter_pids_cpp(cand, S.contiguous(), ix.codes, ix.doclens, ix.offsets, idx, ndocs)
+    mine, (p1, s1, s2) = po.filter_pids(ix, cand, S.contiguous(), idx, ndocs, return_stages=True)
+    assert torch.equal(out, mine)
+    assert (s1[1:] == s1[:-1]).float().mean() > 0.3                  # the scenario really is tie-dominated
